@@ -1,0 +1,278 @@
+"""L0 oracle: exact-GP posterior, mixed kernel and base acquisition functions (torch CPU, float64).
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  **Parity unpinned**: this arithmetic lives in
+BoTorch / GPyTorch (third party, unpinned in the reference's ``setup.py:9-20``, absent from this image);
+the formulas below are the libraries' published ones as recorded in SURVEY.md App. B, anchored on the
+reference's call sites:
+
+* kernel structure       ``discrete_mixed_bo/kernels.py:18-101`` (``get_kernel``)
+* model                  ``discrete_mixed_bo/experiment_utils.py:237-351`` (``FixedNoiseGP``, constant mean)
+* EI / UCB / mean        ``discrete_mixed_bo/experiment_utils.py:391-393, 476-480, 489-492``
+* where L1 calls into it ``discrete_mixed_bo/probabilistic_reparameterization.py:314, 491, 540``
+
+Everything is written so torch autograd can differentiate it, because the reference obtains the pathwise
+gradient for the continuous parameters with ``torch.autograd.grad`` through exactly this computation
+(``probabilistic_reparameterization.py:624-633``).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import torch
+from torch import Tensor
+
+SQRT5 = math.sqrt(5.0)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Kernel specification (plain data; the product has its own classes, tests translate between the two)
+# ----------------------------------------------------------------------------------------------------------------------
+@dataclass
+class Factor:
+    """One multiplicative factor.  kind: "matern52" (gpytorch MaternKernel nu=2.5) or "categorical"
+    (botorch CategoricalKernel).  ``lengthscale`` has one entry per active dim (isotropic = repeated)."""
+
+    kind: str
+    dims: List[int]
+    lengthscale: List[float]
+    power: int = 1
+
+
+@dataclass
+class Term:
+    """outputscale * prod_f factor_f ** power_f  (gpytorch ScaleKernel(ProductKernel(...)))."""
+
+    outputscale: float
+    factors: List[Factor] = field(default_factory=list)
+    # additive inner structure: if True the factors are *summed* (ScaleKernel(AdditiveKernel(...)))
+    additive: bool = False
+
+
+KernelSpec = List[Term]
+
+
+def reference_kernel_spec(
+    kernel_type: str,
+    dim: int,
+    binary_dims: Sequence[int],
+    categorical_transformed_features: Dict[int, int],
+    cont_lengthscale: Sequence[float],
+    binary_lengthscale: Sequence[float] = (),
+    categorical_lengthscale: Sequence[float] = (),
+    outputscale: float = 1.0,
+    outputscale_sum: float = 1.0,
+    use_ard_binary: bool = False,
+) -> KernelSpec:
+    """Structure of ``get_kernel`` (``kernels.py:18-101``) with explicit hyperparameters.
+
+    * ``kernels.py:29-37``  categorical dims: the numeric columns (mixed_categorical) or the one-hot tail
+    * ``kernels.py:39-42``  continuous dims = everything that is not binary (and not categorical if
+      ``mixed_categorical``) -- non-binary ordinals and, for kernel_type "mixed", one-hot columns too
+    * ``kernels.py:45-63``  Matern-5/2 ARD on continuous dims, Matern-5/2 (isotropic unless
+      ``use_ard_binary``) on binary dims
+    * ``kernels.py:64-72``  CategoricalKernel (ARD) for ``mixed_categorical``
+    * ``kernels.py:85-89``  "mixed": Scale(k0 * k1 * ...)
+    * ``kernels.py:90-94``  "mixed_categorical": the second loop multiplies ``prod_kernel`` by ``kernels[1:]``
+      AGAIN, so every factor but the first is squared:  Scale(k0 * k1^2 * ...) + Scale(k0 + k1 + ...)
+      (SURVEY.md App. C.1 -- replicated, not fixed).
+    """
+    if kernel_type not in ("mixed", "mixed_categorical"):
+        raise ValueError(f"{kernel_type} is not supported by the oracle.")
+    if kernel_type == "mixed_categorical":
+        categorical_dims = list(categorical_transformed_features.keys())
+    elif len(categorical_transformed_features) > 0:
+        categorical_dims = list(range(min(categorical_transformed_features.keys()), dim))
+    else:
+        categorical_dims = []
+    cont_dims = sorted(set(range(dim)) - set(binary_dims))
+    if kernel_type == "mixed_categorical":
+        cont_dims = sorted(set(cont_dims) - set(categorical_dims))
+    factors: List[Factor] = []
+    if len(cont_dims) > 0:
+        assert len(cont_lengthscale) == len(cont_dims)
+        factors.append(Factor("matern52", list(cont_dims), [float(v) for v in cont_lengthscale]))
+    if len(binary_dims) > 0:
+        if use_ard_binary:
+            assert len(binary_lengthscale) == len(binary_dims)
+            ls = [float(v) for v in binary_lengthscale]
+        else:
+            assert len(binary_lengthscale) == 1
+            ls = [float(binary_lengthscale[0])] * len(binary_dims)
+        factors.append(Factor("matern52", list(binary_dims), ls))
+    if kernel_type == "mixed_categorical" and len(categorical_dims) > 0:
+        assert len(categorical_lengthscale) == len(categorical_dims)
+        factors.append(Factor("categorical", list(categorical_dims), [float(v) for v in categorical_lengthscale]))
+    if kernel_type == "mixed":
+        return [Term(float(outputscale), [Factor(f.kind, f.dims, f.lengthscale, 1) for f in factors])]
+    prod = [Factor(f.kind, f.dims, f.lengthscale, 1 if i == 0 else 2) for i, f in enumerate(factors)]
+    summ = [Factor(f.kind, f.dims, f.lengthscale, 1) for f in factors]
+    return [Term(float(outputscale), prod), Term(float(outputscale_sum), summ, additive=True)]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Kernel evaluation  [3P] gpytorch MaternKernel / ScaleKernel / ProductKernel / AdditiveKernel, botorch CategoricalKernel
+# ----------------------------------------------------------------------------------------------------------------------
+def _matern52(x1: Tensor, x2: Tensor, ls: Tensor) -> Tensor:
+    """gpytorch MaternKernel(nu=2.5): inputs divided by the lengthscale, Euclidean distance clamped at
+    sqrt(1e-30), k = (1 + sqrt5 r + 5/3 r^2) exp(-sqrt5 r)  (SURVEY.md App. B.1).  GPyTorch subtracts the
+    column mean of x1 from both inputs first (a translation) and forms r^2 by an expanded GEMM; the direct
+    difference used here agrees to ~1e-15."""
+    a = (x1 / ls).unsqueeze(-2)  # [..., B, 1, k]
+    b = (x2 / ls).unsqueeze(-3)  # [..., 1, n, k]
+    sq = ((a - b) ** 2).sum(-1)
+    r = sq.clamp_min(1e-30).sqrt()
+    return (1.0 + SQRT5 * r + (5.0 / 3.0) * r * r) * torch.exp(-SQRT5 * r)
+
+
+def _categorical(x1: Tensor, x2: Tensor, ls: Tensor) -> Tensor:
+    """botorch CategoricalKernel: exp(-mean_j(1[x_j != x'_j] / l_j))  (SURVEY.md App. B.2)."""
+    delta = (x1.unsqueeze(-2) != x2.unsqueeze(-3)).to(x1.dtype)
+    return torch.exp(-(delta / ls).mean(-1))
+
+
+def eval_kernel(spec: KernelSpec, x1: Tensor, x2: Tensor) -> Tensor:
+    """K(x1[..., B, d], x2[n, d]) -> [..., B, n]."""
+    out = None
+    for term in spec:
+        acc = None
+        for f in term.factors:
+            dims = torch.as_tensor(f.dims, dtype=torch.long)
+            ls = torch.as_tensor(f.lengthscale, dtype=x1.dtype)
+            a, b = x1[..., dims], x2[..., dims]
+            k = _matern52(a, b, ls) if f.kind == "matern52" else _categorical(a, b, ls)
+            k1 = k
+            for _ in range(f.power - 1):
+                k = k * k1
+            if acc is None:
+                acc = k
+            elif term.additive:
+                acc = acc + k
+            else:
+                acc = acc * k
+        acc = term.outputscale * acc
+        out = acc if out is None else out + acc
+    return out
+
+
+def kernel_diag(spec: KernelSpec, dtype=torch.float64) -> float:
+    """k(x, x): every factor is 1 at zero distance."""
+    v = 0.0
+    for term in spec:
+        v += term.outputscale * (len(term.factors) if term.additive else 1.0)
+    return v
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Exact GP  [3P] botorch FixedNoiseGP + gpytorch DefaultPredictionStrategy (Cholesky path), SURVEY.md App. B.3
+# ----------------------------------------------------------------------------------------------------------------------
+class OracleGP(torch.nn.Module):
+    """FixedNoiseGP with a constant mean, in eval mode, exact Cholesky caches.
+
+    mean_cache  = (K + diag(noise))^-1 (y - c)          (gpytorch exact_prediction_strategies mean_cache)
+    covar_cache = L^-T, L = chol(K + diag(noise))        (explicit inverse root on the Cholesky path)
+    mu*  = c + k* . mean_cache ;  var* = k** - || k*^T L^-T ||^2, floored at gpytorch ``min_variance`` (1e-10, f64)
+    Posterior is noise-free (``observation_noise=False``), q = 1.
+    """
+
+    def __init__(self, train_X: Tensor, train_Y: Tensor, spec: KernelSpec, noise, mean_const: float,
+                 min_variance: float = 1e-10):
+        super().__init__()
+        train_X = train_X.detach().to(torch.float64).cpu()
+        y = train_Y.detach().to(torch.float64).cpu().reshape(-1)
+        n = train_X.shape[0]
+        noise = torch.as_tensor(noise, dtype=torch.float64).reshape(-1)
+        if noise.numel() == 1:
+            noise = noise.expand(n)
+        self.spec = spec
+        self.train_X = train_X
+        self.train_Y = y
+        self.mean_const = float(mean_const)
+        self.noise = noise.clone()
+        self.min_variance = float(min_variance)
+        K = eval_kernel(spec, train_X, train_X) + torch.diag(self.noise)
+        self.L = torch.linalg.cholesky(K)
+        self.Linv = torch.linalg.solve_triangular(self.L, torch.eye(n, dtype=torch.float64), upper=False)
+        self.alpha = torch.cholesky_solve((y - self.mean_const).unsqueeze(-1), self.L).squeeze(-1)
+        self.kss = kernel_diag(spec)
+
+    def posterior(self, X: Tensor):
+        """X [..., 1, d] (q = 1) or [..., d] -> (mean [...], variance [...])."""
+        if X.shape[-2:-1] == (1,) and X.ndim >= 2:
+            Xp = X.squeeze(-2)
+        else:
+            Xp = X
+        ks = eval_kernel(self.spec, Xp, self.train_X)  # [..., n]
+        mean = self.mean_const + ks @ self.alpha
+        root = ks @ self.Linv.transpose(-1, -2)  # k*^T L^-T
+        var = self.kss - (root * root).sum(-1)
+        var = var.clamp_min(self.min_variance)
+        return mean, var
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Base acquisition functions  [3P] botorch.acquisition.analytic, SURVEY.md App. B.4
+# ----------------------------------------------------------------------------------------------------------------------
+_LOG_SQRT_2PI = math.log(math.sqrt(2 * math.pi))
+
+
+class OracleAcq(torch.nn.Module):
+    """``acq_function(X[b, mc, 1, d]) -> [b, mc]``; duck-types the BoTorch analytic AF surface the reference
+    touches (``.model``, ``.best_f`` / ``.beta``, ``.X_baseline``)."""
+
+    def __init__(self, model: OracleGP):
+        super().__init__()
+        self.model = model
+        self.X_pending = None
+
+    @property
+    def X_baseline(self):
+        return None
+
+    def set_X_pending(self, X_pending=None):
+        self.X_pending = X_pending
+
+
+class OracleEI(OracleAcq):
+    """ExpectedImprovement as in BoTorch 0.6-0.8 (the reference's era: FixedNoiseGP / fit_gpytorch_model):
+    sigma = sqrt(clamp_min(var, 1e-9)); u = (mean - best_f)/sigma;
+    EI = sigma * (exp(Normal.log_prob(u)) + u * Normal.cdf(u)),  cdf = 0.5 (1 + erf(u / sqrt2)).
+    ``variant="erfc"`` gives the later (>= 0.9) helper: phi(u) + u * 0.5 erfc(-u / sqrt2)."""
+
+    def __init__(self, model, best_f, var_floor: float = 1e-9, variant: str = "erf"):
+        super().__init__(model)
+        self.best_f = torch.as_tensor(best_f, dtype=torch.float64)
+        self.var_floor = var_floor
+        self.variant = variant
+
+    def forward(self, X):
+        mean, var = self.model.posterior(X)
+        sigma = var.clamp_min(self.var_floor).sqrt()
+        u = (mean - self.best_f) / sigma
+        updf = torch.exp(-(u ** 2) / 2 - _LOG_SQRT_2PI)
+        if self.variant == "erf":
+            ucdf = 0.5 * (1 + torch.erf(u / math.sqrt(2)))
+        else:
+            ucdf = 0.5 * torch.erfc(-u / math.sqrt(2))
+        return sigma * (updf + u * ucdf)
+
+
+class OracleUCB(OracleAcq):
+    """UpperConfidenceBound: mean + sqrt(beta * var)   (experiment_utils.py:476-480; beta = 0.2 d ln(2 iter))."""
+
+    def __init__(self, model, beta: float):
+        super().__init__(model)
+        self.beta = torch.as_tensor(beta, dtype=torch.float64)
+
+    def forward(self, X):
+        mean, var = self.model.posterior(X)
+        return mean + (self.beta * var).sqrt()
+
+
+class OraclePosteriorMean(OracleAcq):
+    """PosteriorMean (experiment_utils.py:489-492; the reference applies it to an RFF sample for TS)."""
+
+    def forward(self, X):
+        mean, _ = self.model.posterior(X)
+        return mean

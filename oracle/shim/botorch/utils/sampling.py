@@ -1,0 +1,25 @@
+"""Stand-in for botorch.utils.sampling: scrambled-Sobol draws generated on CPU."""
+import torch
+from torch.quasirandom import SobolEngine
+
+
+def draw_sobol_samples(bounds, n, q, batch_shape=None, seed=None):
+    batch_shape = batch_shape or torch.Size()
+    batch_size = int(torch.prod(torch.tensor(batch_shape)))
+    d = bounds.shape[-1]
+    lower = bounds[0]
+    rng = bounds[1] - bounds[0]
+    sobol_engine = SobolEngine(q * d, scramble=True, seed=seed)
+    samples_raw = sobol_engine.draw(batch_size * n, dtype=lower.dtype)
+    samples_raw = samples_raw.view(*batch_shape, n, q, d).to(device=lower.device)
+    if batch_shape != torch.Size():
+        samples_raw = samples_raw.permute(-3, *range(len(batch_shape)), -2, -1)
+    return lower + rng * samples_raw
+
+
+def draw_sobol_normal_samples(d, n, device=None, dtype=None, seed=None):  # imported by input.py:14, unused on the PR path
+    raise NotImplementedError
+
+
+def sample_simplex(d, n=1, qmc=False, seed=None, device=None, dtype=None):  # imported by input.py:16, unused on the PR path
+    raise NotImplementedError
