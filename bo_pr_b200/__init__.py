@@ -1,0 +1,37 @@
+"""bo_pr_b200 -- B200-native implementation of bo_pr's probabilistic-reparameterization acquisition hot path.
+
+Public names mirror the reference (``discrete_mixed_bo``): the PR acquisition wrappers, the PR input transforms, the
+mixed-kernel factory and the multi-start optimisation drivers.  All arithmetic on the path runs in ``libprb200.so``
+(hand-written sm_100a CUDA behind the C ABI in ``include/prb200.h``); there is no CPU fallback.
+"""
+from .acquisition import (  # noqa: F401
+    AcquisitionFunction,
+    ExpectedImprovement,
+    PosteriorMean,
+    UpperConfidenceBound,
+    is_nonnegative,
+)
+from .input import (  # noqa: F401
+    AnalyticProbabilisticReparameterizationInputTransform,
+    ChainedInputTransform,
+    MCProbabilisticReparameterizationInputTransform,
+    Normalize,
+    OneHotToNumeric,
+)
+from .kernels import (  # noqa: F401
+    AdditiveKernel,
+    CategoricalKernel,
+    MaternKernel,
+    ProductKernel,
+    ScaleKernel,
+    get_kernel,
+)
+from .models import FixedNoiseGP, GPState  # noqa: F401
+from .probabilistic_reparameterization import (  # noqa: F401
+    AnalyticProbabilisticReparameterization,
+    MCProbabilisticReparameterization,
+    get_probabilistic_reparameterization_input_transform,
+)
+from .wrapper import AcquisitionFunctionWrapper  # noqa: F401
+
+__version__ = "0.1.0"

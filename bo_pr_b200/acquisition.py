@@ -1,0 +1,137 @@
+"""Base acquisition functions evaluated by ``libprb200``.
+
+Surface of ``botorch.acquisition.analytic.{ExpectedImprovement, UpperConfidenceBound, PosteriorMean}`` as the reference
+uses it (``discrete_mixed_bo/experiment_utils.py:391-393, 476-480, 489-492``): ``acq(X[..., 1, d]) -> [...]`` with
+``.model``, ``.best_f`` / ``.beta``.  ``forward`` is differentiable w.r.t. ``X`` (the gradient comes from the device
+path: second triangular product + kernel-derivative contraction).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import _capi as capi
+from .models import MIN_VARIANCE, GPState, gp_state_from_model
+
+
+class AcquisitionFunction(torch.nn.Module):
+    """``botorch.acquisition.acquisition.AcquisitionFunction`` stand-in."""
+
+    def __init__(self, model=None):
+        super().__init__()
+        if model is not None:
+            self.model = model
+        self.X_pending = None
+
+    def set_X_pending(self, X_pending: Optional[Tensor] = None) -> None:
+        self.X_pending = X_pending
+
+
+class _PointsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X: Tensor, state: GPState, desc: capi.PrbAcqDesc):
+        need = X.requires_grad
+        val, _, _, grad = state.acq_points(desc, X.reshape(-1, X.shape[-1]), want_grad=need)
+        ctx.grad = grad
+        ctx.xshape = X.shape
+        return val.reshape(X.shape[:-1])
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        if ctx.grad is None:
+            return None, None, None
+        g = ctx.grad.reshape(ctx.xshape) * grad_output.unsqueeze(-1)
+        return g, None, None
+
+
+class AnalyticAcquisitionFunction(AcquisitionFunction):
+    """q = 1 analytic AF on a single-output exact GP.  ``posterior_transform`` is not supported (raises)."""
+
+    def __init__(self, model, posterior_transform=None, **kwargs):
+        super().__init__(model=model)
+        if posterior_transform is not None:
+            raise NotImplementedError("posterior transforms are outside the B200 hot path")
+
+    @property
+    def state(self) -> GPState:
+        return gp_state_from_model(self.model)
+
+    def acq_desc(self) -> capi.PrbAcqDesc:  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def forward(self, X: Tensor) -> Tensor:
+        if X.shape[-2] != 1:
+            raise AssertionError(f"Expected X to be `batch_shape x q=1 x d`, but got X with shape {tuple(X.shape)}.")
+        return _PointsFn.apply(X.squeeze(-2), self.state, self.acq_desc())
+
+
+class ExpectedImprovement(AnalyticAcquisitionFunction):
+    """EI = sigma (phi(u) + u Phi(u)), u = (mu - best_f) / sigma, sigma = sqrt(max(var, var_floor)).
+    ``variant="erf"`` / ``var_floor=1e-9`` is BoTorch <= 0.8 (the reference's era); ``"erfc"`` the later helper."""
+
+    def __init__(self, model, best_f, posterior_transform=None, maximize: bool = True, var_floor: float = 1e-9,
+                 variant: str = "erf", **kwargs):
+        super().__init__(model=model, posterior_transform=posterior_transform)
+        if not maximize:
+            raise NotImplementedError("maximize=False is not used by the reference")
+        self.maximize = maximize
+        self.register_buffer("best_f", torch.as_tensor(best_f, dtype=torch.float64).detach().clone())
+        self.var_floor = float(var_floor)
+        self.variant = variant
+
+    def acq_desc(self) -> capi.PrbAcqDesc:
+        return capi.PrbAcqDesc(kind=capi.PRB_ACQ_EI, ei_variant=0 if self.variant == "erf" else 1,
+                               param=float(self.best_f), min_variance=MIN_VARIANCE, acq_var_floor=self.var_floor)
+
+
+class UpperConfidenceBound(AnalyticAcquisitionFunction):
+    """UCB = mu + sqrt(beta var)  (``experiment_utils.py:476-480``; beta = 0.2 d ln(2 iter), ``:446-447``)."""
+
+    def __init__(self, model, beta, posterior_transform=None, maximize: bool = True, **kwargs):
+        super().__init__(model=model, posterior_transform=posterior_transform)
+        if not maximize:
+            raise NotImplementedError("maximize=False is not used by the reference")
+        self.maximize = maximize
+        self.register_buffer("beta", torch.as_tensor(beta, dtype=torch.float64).detach().clone())
+
+    def acq_desc(self) -> capi.PrbAcqDesc:
+        return capi.PrbAcqDesc(kind=capi.PRB_ACQ_UCB, ei_variant=0, param=float(self.beta),
+                               min_variance=MIN_VARIANCE, acq_var_floor=0.0)
+
+
+class PosteriorMean(AnalyticAcquisitionFunction):
+    def __init__(self, model, posterior_transform=None, maximize: bool = True, **kwargs):
+        super().__init__(model=model, posterior_transform=posterior_transform)
+        self.maximize = maximize
+
+    def acq_desc(self) -> capi.PrbAcqDesc:
+        return capi.PrbAcqDesc(kind=capi.PRB_ACQ_MEAN, ei_variant=0, param=0.0, min_variance=MIN_VARIANCE,
+                               acq_var_floor=0.0)
+
+
+def acq_desc_of(acq_function) -> capi.PrbAcqDesc:
+    """Descriptor for one of the classes above or a duck-typed BoTorch analytic AF (class name + ``best_f``/``beta``)."""
+    if isinstance(acq_function, AnalyticAcquisitionFunction):
+        return acq_function.acq_desc()
+    if getattr(acq_function, "posterior_transform", None) is not None:
+        raise NotImplementedError("posterior transforms are outside the B200 hot path")
+    name = type(acq_function).__name__
+    if name == "ExpectedImprovement":
+        if not getattr(acq_function, "maximize", True):
+            raise NotImplementedError
+        return capi.PrbAcqDesc(kind=capi.PRB_ACQ_EI, ei_variant=0, param=float(acq_function.best_f),
+                               min_variance=MIN_VARIANCE, acq_var_floor=1e-9)
+    if name == "UpperConfidenceBound":
+        return capi.PrbAcqDesc(kind=capi.PRB_ACQ_UCB, ei_variant=0, param=float(acq_function.beta),
+                               min_variance=MIN_VARIANCE, acq_var_floor=0.0)
+    if name == "PosteriorMean":
+        return capi.PrbAcqDesc(kind=capi.PRB_ACQ_MEAN, ei_variant=0, param=0.0, min_variance=MIN_VARIANCE,
+                               acq_var_floor=0.0)
+    raise NotImplementedError(f"base acquisition function {name} has no device implementation in libprb200")
+
+
+def is_nonnegative(acq_function) -> bool:
+    """``botorch.optim.initializers.is_nonnegative`` for the AFs above (used at ``run_one_replication.py:407-408``)."""
+    return type(acq_function).__name__ in ("ExpectedImprovement",)

@@ -1,0 +1,538 @@
+// C ABI of libprb200 (see include/prb200.h).  Host-side orchestration only: argument validation, workspace carving and
+// kernel sequencing on the caller's stream.  No allocation and no synchronisation on the hot entry points.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "prb_device.cuh"
+#include "prb_kernels.cuh"
+
+using namespace prb;
+
+namespace {
+
+thread_local char g_cuda_err[256] = "";
+
+int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+  return PRB_ERR_CUDA;
+}
+#define CUDA_TRY(expr)                                  \
+  do {                                                  \
+    cudaError_t _e = (expr);                            \
+    if (_e != cudaSuccess) return cuda_fail(_e, #expr); \
+  } while (0)
+
+// ---- GP-state packing --------------------------------------------------------------------------------------------
+// A1[j, k] = Linv[j, k] (k <= j < n) ; A1[n, k] = alpha[k] ; 0 elsewhere.      [Mp1, Kp]
+// A2[m, k] = Linv[k, m] (m <= k < n) ; 0 elsewhere.                             [Mp2, Kp]
+__global__ void pack_state_kernel(const double* __restrict__ Linv, const double* __restrict__ alpha, int n, int Kp,
+                                  int Mp1, int Mp2, double* __restrict__ A1, double* __restrict__ A2) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (k >= Kp) return;
+  if (r < Mp1) {
+    double v = 0.0;
+    if (r < n && k <= r) v = Linv[size_t(r) * n + k];
+    if (r == n && k < n) v = alpha[k];
+    A1[size_t(r) * Kp + k] = v;
+  }
+  if (r < Mp2) {
+    double v = 0.0;
+    if (r < n && k < n && k >= r) v = Linv[size_t(k) * n + r];
+    A2[size_t(r) * Kp + k] = v;
+  }
+}
+
+int make_spec(const prb_model_desc* d, DevSpec* out, double* kss) {
+  if (d->n_terms < 1 || d->n_terms > PRB_MAX_TERMS) return PRB_ERR_UNSUPPORTED;
+  memset(out, 0, sizeof(DevSpec));
+  out->n_terms = d->n_terms;
+  out->d_k = d->d_k;
+  double diag = 0.0;
+  for (int t = 0; t < d->n_terms; ++t) {
+    const prb_term& T = d->terms[t];
+    if (T.n_factors < 1 || T.n_factors > PRB_MAX_FACTORS) return PRB_ERR_UNSUPPORTED;
+    DevTerm& D = out->t[t];
+    D.outputscale = T.outputscale;
+    D.additive = T.additive ? 1 : 0;
+    D.n_factors = T.n_factors;
+    for (int f = 0; f < T.n_factors; ++f) {
+      const prb_factor& F = T.factors[f];
+      if (F.n_dims < 1 || F.n_dims > PRB_MAX_DIMS || F.power < 1 || F.power > 4) return PRB_ERR_UNSUPPORTED;
+      if (F.kind != PRB_FACTOR_MATERN52 && F.kind != PRB_FACTOR_CATEGORICAL) return PRB_ERR_INVALID;
+      DevFactor& G = D.f[f];
+      G.kind = F.kind;
+      G.n_dims = F.n_dims;
+      G.power = F.power;
+      for (int i = 0; i < F.n_dims; ++i) {
+        if (F.dims[i] < 0 || F.dims[i] >= d->d_k || !(F.lengthscale[i] > 0.0)) return PRB_ERR_INVALID;
+        G.dims[i] = F.dims[i];
+        G.inv_ls[i] = (F.kind == PRB_FACTOR_MATERN52) ? 1.0 / F.lengthscale[i] : 1.0 / (F.lengthscale[i] * F.n_dims);
+      }
+    }
+    diag += T.outputscale * (T.additive ? double(T.n_factors) : 1.0);
+  }
+  *kss = diag;
+  return PRB_OK;
+}
+
+int make_space(const prb_space_desc* s, DevSpace* out) {
+  if (!s || s->d < 1 || s->d > PRB_MAX_DIMS || s->n_int < 0 || s->n_cat < 0 || s->n_cat > PRB_MAX_CAT)
+    return PRB_ERR_UNSUPPORTED;
+  if (s->n_int + s->n_cat == 0 || !(s->tau > 0.0)) return PRB_ERR_INVALID;
+  memset(out, 0, sizeof(DevSpace));
+  out->d = s->d;
+  out->n_int = s->n_int;
+  out->n_cat = s->n_cat;
+  out->apply_numeric = s->apply_numeric ? 1 : 0;
+  out->tau = s->tau;
+  out->raw_int = s->raw_integer_space ? 1 : 0;
+  bool is_disc[PRB_MAX_DIMS] = {false};
+  for (int k = 0; k < s->n_int; ++k) {
+    const int c = s->int_cols[k];
+    if (c < 0 || c >= s->d || !(s->int_hi[k] > s->int_lo[k])) return PRB_ERR_INVALID;
+    out->int_cols[k] = c;
+    out->int_lo[k] = s->int_lo[k];
+    out->int_hi[k] = s->int_hi[k];
+    is_disc[c] = true;
+  }
+  int n_disc = s->n_int;
+  int expect = s->n_cat > 0 ? s->cat_start[0] : s->d;
+  for (int j = 0; j < s->n_cat; ++j) {
+    if (s->cat_start[j] != expect || s->cat_card[j] < 1 || s->cat_card[j] > PRB_MAX_CARD) return PRB_ERR_INVALID;
+    out->cat_start[j] = s->cat_start[j];
+    out->cat_card[j] = s->cat_card[j];
+    for (int k = 0; k < s->cat_card[j]; ++k) is_disc[expect + k] = true;
+    expect += s->cat_card[j];
+    n_disc += s->cat_card[j];
+  }
+  if (expect != s->d) return PRB_ERR_INVALID;  // one-hot blocks must run contiguously to the last column
+  out->n_disc = n_disc;
+  out->d_k = (s->apply_numeric && s->n_cat > 0) ? s->cat_start[0] + s->n_cat : s->d;
+  int nc = 0;
+  for (int c = 0; c < s->d; ++c)
+    if (!is_disc[c]) out->cont_cols[nc++] = c;
+  out->n_cont = nc;
+  return PRB_OK;
+}
+
+int make_acq(const prb_acq_desc* a, DevAcq* out) {
+  if (!a || a->kind < PRB_ACQ_EI || a->kind > PRB_ACQ_MEAN) return PRB_ERR_INVALID;
+  out->kind = a->kind;
+  out->ei_variant = a->ei_variant;
+  out->param = a->param;
+  out->min_variance = a->min_variance;
+  out->acq_var_floor = a->acq_var_floor;
+  return PRB_OK;
+}
+
+// ---- workspace plan ----------------------------------------------------------------------------------------------
+struct Plan {
+  int64_t B, B_pad;
+  int C, nchunks;
+  size_t off_xk, off_z, off_prob, off_a, off_dmu, off_dvar, off_S_all, off_probs;
+  size_t off_panelA, off_panelV, off_norm, off_mu, off_S_part;
+  size_t off_Xc, off_grad, off_ones, off_val, off_step;
+  size_t total;
+};
+
+constexpr size_t kPanelBudgetBytes = size_t(96) << 20;  // two panels sized to stay resident in the 126 MB L2
+
+Plan make_plan(const Model& m, int64_t n_points, int d_theta, int chunk_cols) {
+  Plan p;
+  memset(&p, 0, sizeof(p));
+  p.B = n_points;
+  p.B_pad = round_up64(n_points > 0 ? n_points : 1, 128);
+  int64_t C = chunk_cols;
+  if (C <= 0) {
+    C = int64_t(kPanelBudgetBytes / (sizeof(double) * size_t(m.Mp1 + m.Mp2))) / 128 * 128;
+    if (C < 128) C = 128;
+  }
+  C = round_up64(C, 128);
+  if (C > p.B_pad) C = p.B_pad;
+  int64_t nch = (p.B_pad + C - 1) / C;
+  C = round_up64((p.B_pad + nch - 1) / nch, 128);
+  p.C = int(C);
+  p.nchunks = int((p.B_pad + C - 1) / C);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) / 256 * 256;
+    return o;
+  };
+  const size_t dbl = sizeof(double);
+  p.off_xk = take(size_t(p.B_pad) * m.d_k * dbl);
+  p.off_z = take(size_t(p.B_pad) * d_theta);
+  p.off_prob = take(size_t(p.B_pad) * d_theta * dbl);
+  p.off_a = take(size_t(p.B_pad) * dbl);
+  p.off_dmu = take(size_t(p.B_pad) * dbl);
+  p.off_dvar = take(size_t(p.B_pad) * dbl);
+  p.off_S_all = take(size_t(p.B_pad) * m.d_k * dbl);
+  p.off_probs = take(size_t(p.B_pad) * dbl);
+  p.off_panelA = take(size_t(m.Mp2) * C * dbl);
+  p.off_panelV = take(size_t(C) * m.Mp1 * dbl);
+  p.off_norm = take(size_t(m.Mp1 / GEMM_BM) * C * dbl);
+  p.off_mu = take(size_t(C) * dbl);
+  p.off_S_part = take(size_t(m.Mp2 / GRAD_JSPLIT_ROWS) * m.d_k * C * dbl);
+  p.off_Xc = take(size_t(p.B_pad) * d_theta * dbl);
+  p.off_grad = take(size_t(p.B_pad) * d_theta * dbl);
+  p.off_ones = take(size_t(p.B_pad) * dbl);
+  p.off_val = take(size_t(p.B_pad) * dbl);
+  p.off_step = take(256);
+  p.total = off;
+  return p;
+}
+
+template <typename T>
+T* at(void* ws, size_t off) {
+  return reinterpret_cast<T*>(static_cast<char*>(ws) + off);
+}
+
+// ---- the posterior/acquisition engine over L2-resident column panels ------------------------------------------------
+int run_engine(const Model& m, const DevAcq& aq, const Plan& pl, void* ws, const double* xk, int64_t B, bool need_grad,
+               uint32_t diffmask, double* a, double* dmu, double* dvar, double* S_all, double* out_mean,
+               double* out_var, cudaStream_t st) {
+  double* panelA = at<double>(ws, pl.off_panelA);
+  double* panelV = at<double>(ws, pl.off_panelV);
+  double* norm = at<double>(ws, pl.off_norm);
+  double* mu = at<double>(ws, pl.off_mu);
+  double* S_part = at<double>(ws, pl.off_S_part);
+  for (int64_t c0 = 0; c0 < B; c0 += pl.C) {
+    const int ncols = int(B - c0 < pl.C ? B - c0 : pl.C);
+    const int ncols_pad = round_up(ncols, 128);
+    const double* xkc = xk + size_t(c0) * m.d_k;
+    CUDA_TRY(launch_kstar_panel(m, xkc, ncols, ncols_pad, panelA, st));
+    CUDA_TRY(launch_trgemm_lower(m, panelA, ncols_pad, panelV, norm, mu, st));
+    CUDA_TRY(launch_acq_epilogue(m, aq, norm, ncols_pad, mu, ncols, a + c0, dmu + c0, dvar + c0,
+                                 out_mean ? out_mean + c0 : nullptr, out_var ? out_var + c0 : nullptr, st));
+    if (need_grad) {
+      CUDA_TRY(launch_trgemm_upper(m, panelV, ncols_pad, panelA, st));
+      CUDA_TRY(launch_grad_contract(m, diffmask, xkc, ncols, ncols_pad, panelA, dmu + c0, dvar + c0, S_part, st));
+      CUDA_TRY(launch_sum_splits(m, S_part, ncols, ncols_pad, S_all + size_t(c0) * m.d_k, st));
+    }
+  }
+  return PRB_OK;
+}
+
+uint32_t cont_mask(const DevSpace& sp) {
+  uint32_t mask = 0;
+  for (int i = 0; i < sp.n_cont; ++i) mask |= 1u << sp.cont_cols[i];
+  return mask;
+}
+
+int mc_core(prb_model* model, const DevSpace& sp, const DevAcq& aq, const Plan& pl, void* ws, const double* theta,
+            int b, int mc, const double* u_int, const double* u_cat, uint64_t seed, uint64_t offset, int estimator,
+            double* ma_state, int update_ma, const double* grad_out, double* out_value, double* out_grad,
+            double* out_acq_values, cudaStream_t st) {
+  const Model& m = *reinterpret_cast<Model*>(model);
+  const int64_t B = int64_t(b) * mc;
+  double* xk = at<double>(ws, pl.off_xk);
+  uint8_t* z = at<uint8_t>(ws, pl.off_z);
+  double* prob = at<double>(ws, pl.off_prob);
+  double* a = out_acq_values ? out_acq_values : at<double>(ws, pl.off_a);
+  double* dmu = at<double>(ws, pl.off_dmu);
+  double* dvar = at<double>(ws, pl.off_dvar);
+  double* S_all = at<double>(ws, pl.off_S_all);
+  const bool need_grad = grad_out != nullptr;
+  CUDA_TRY(launch_pr_sample(sp, theta, b, mc, u_int, u_cat, seed, offset, xk, nullptr, need_grad ? z : nullptr,
+                            need_grad ? prob : nullptr, st));
+  const bool need_path = need_grad && sp.n_cont > 0;
+  int rc = run_engine(m, aq, pl, ws, xk, B, need_path, cont_mask(sp), a, dmu, dvar, S_all, nullptr, nullptr, st);
+  if (rc != PRB_OK) return rc;
+  CUDA_TRY(launch_mc_reduce(sp, b, mc, a, z, prob, S_all, estimator, ma_state, grad_out, out_value, out_grad, st));
+  if (update_ma && ma_state) CUDA_TRY(launch_ma_update(out_value, b, ma_state, st));
+  return PRB_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+int prb_version(void) { return PRB_VERSION; }
+
+const char* prb_status_string(int status) {
+  switch (status) {
+    case PRB_OK: return "ok";
+    case PRB_ERR_INVALID: return "invalid argument";
+    case PRB_ERR_UNSUPPORTED: return "exceeds a compile-time limit of libprb200";
+    case PRB_ERR_WORKSPACE: return "workspace too small";
+    case PRB_ERR_CUDA: return "CUDA error";
+    case PRB_ERR_NO_DEVICE: return "no usable sm_100 device";
+    default: return "unknown status";
+  }
+}
+
+const char* prb_last_cuda_error(void) { return g_cuda_err; }
+
+int prb_model_create(prb_model** out, const prb_model_desc* desc, void* stream) {
+  if (!out || !desc || desc->n < 1 || desc->d_k < 1 || !desc->X_train || !desc->Linv || !desc->alpha)
+    return PRB_ERR_INVALID;
+  if (desc->d_k > PRB_MAX_DIMS) return PRB_ERR_UNSUPPORTED;
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return PRB_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "device %s is sm_%d%d; libprb200 is built for sm_100a only", prop.name,
+             prop.major, prop.minor);
+    return PRB_ERR_NO_DEVICE;
+  }
+  Model* m = new (std::nothrow) Model();
+  if (!m) return PRB_ERR_INVALID;
+  memset(m, 0, sizeof(Model));
+  int rc = make_spec(desc, &m->spec, &m->kss);
+  if (rc != PRB_OK) {
+    delete m;
+    return rc;
+  }
+  m->n = desc->n;
+  m->d_k = desc->d_k;
+  m->Kp = round_up(desc->n, GEMM_BK);
+  m->Mp1 = round_up(desc->n + 1, GEMM_BM);
+  m->Mp2 = round_up(desc->n, GEMM_BM);
+  m->mean_const = desc->mean_const;
+  m->device = dev;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  if ((e = cudaMalloc(&m->A1, size_t(m->Mp1) * m->Kp * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc(&m->A2, size_t(m->Mp2) * m->Kp * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc(&m->Xtr, size_t(m->n) * m->d_k * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc(&m->alpha, size_t(m->n) * sizeof(double))) != cudaSuccess) {
+    prb_model_destroy(reinterpret_cast<prb_model*>(m));
+    return cuda_fail(e, "cudaMalloc(model)");
+  }
+  e = cudaMemcpyAsync(m->Xtr, desc->X_train, size_t(m->n) * m->d_k * sizeof(double), cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(m->alpha, desc->alpha, size_t(m->n) * sizeof(double), cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess) {
+    dim3 grid((m->Kp + 127) / 128, m->Mp1 > m->Mp2 ? m->Mp1 : m->Mp2);
+    pack_state_kernel<<<grid, 128, 0, st>>>(desc->Linv, desc->alpha, m->n, m->Kp, m->Mp1, m->Mp2, m->A1, m->A2);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = gemm_init();
+  if (e != cudaSuccess) {
+    prb_model_destroy(reinterpret_cast<prb_model*>(m));
+    return cuda_fail(e, "prb_model_create");
+  }
+  *out = reinterpret_cast<prb_model*>(m);
+  return PRB_OK;
+}
+
+int prb_model_destroy(prb_model* model) {
+  if (!model) return PRB_OK;
+  Model* m = reinterpret_cast<Model*>(model);
+  cudaFree(m->A1);
+  cudaFree(m->A2);
+  cudaFree(m->Xtr);
+  cudaFree(m->alpha);
+  delete m;
+  return PRB_OK;
+}
+
+int prb_model_n(const prb_model* model) { return model ? reinterpret_cast<const Model*>(model)->n : PRB_ERR_INVALID; }
+int prb_model_dk(const prb_model* model) {
+  return model ? reinterpret_cast<const Model*>(model)->d_k : PRB_ERR_INVALID;
+}
+
+size_t prb_workspace_bytes(const prb_model* model, int64_t n_points, int32_t d_theta, int32_t chunk_cols) {
+  if (!model || n_points < 0 || d_theta < 1) return 0;
+  return make_plan(*reinterpret_cast<const Model*>(model), n_points, d_theta, chunk_cols).total;
+}
+
+int prb_philox_uniform(uint64_t seed, uint64_t offset, int32_t mc, int32_t n_cols, double* out, void* stream) {
+  if (mc < 0 || n_cols < 0 || (!out && mc * n_cols > 0)) return PRB_ERR_INVALID;
+  CUDA_TRY(launch_philox_fill(seed, offset, mc, n_cols, out, static_cast<cudaStream_t>(stream)));
+  return PRB_OK;
+}
+
+int prb_pr_sample(const prb_space_desc* space, const double* theta, int32_t b, int32_t mc, const double* u_int,
+                  const double* u_cat, uint64_t seed, uint64_t offset, double* out_tilde_x, uint8_t* out_z,
+                  double* out_prob, void* stream) {
+  DevSpace sp;
+  int rc = make_space(space, &sp);
+  if (rc != PRB_OK) return rc;
+  if (!theta || b < 0 || mc < 0) return PRB_ERR_INVALID;
+  CUDA_TRY(launch_pr_sample(sp, theta, b, mc, u_int, u_cat, seed, offset, nullptr, out_tilde_x, out_z, out_prob,
+                            static_cast<cudaStream_t>(stream)));
+  return PRB_OK;
+}
+
+int prb_analytic_enumerate(const prb_space_desc* space, const double* theta, int32_t b, const int32_t* options,
+                           int32_t n_options, double* out_x_all, double* out_probs, void* stream) {
+  DevSpace sp;
+  int rc = make_space(space, &sp);
+  if (rc != PRB_OK) return rc;
+  if (!theta || !options || b < 0 || n_options < 1) return PRB_ERR_INVALID;
+  CUDA_TRY(launch_analytic_build(sp, theta, b, n_options, options, out_x_all, out_probs,
+                                 static_cast<cudaStream_t>(stream)));
+  return PRB_OK;
+}
+
+int prb_kernel_matrix(const prb_model_desc* desc, const double* xk, int64_t n_points, double* out, void* stream) {
+  if (!desc || !xk || !out || desc->n < 1 || desc->d_k < 1 || !desc->X_train || n_points < 0) return PRB_ERR_INVALID;
+  if (desc->d_k > PRB_MAX_DIMS) return PRB_ERR_UNSUPPORTED;
+  DevSpec spec;
+  double kss;
+  int rc = make_spec(desc, &spec, &kss);
+  if (rc != PRB_OK) return rc;
+  CUDA_TRY(launch_kernel_matrix(spec, desc->X_train, desc->n, xk, int(n_points), out,
+                                static_cast<cudaStream_t>(stream)));
+  return PRB_OK;
+}
+
+int prb_acq_points(prb_model* model, const prb_acq_desc* acq, const double* xk, int64_t n_points, double* out_acq,
+                   double* out_mean, double* out_var, double* out_dacq_dx, void* workspace, size_t workspace_bytes,
+                   int32_t chunk_cols, void* stream) {
+  if (!model || !xk || n_points < 0 || !workspace) return PRB_ERR_INVALID;
+  const Model& m = *reinterpret_cast<Model*>(model);
+  DevAcq aq;
+  int rc = make_acq(acq, &aq);
+  if (rc != PRB_OK) return rc;
+  if (n_points == 0) return PRB_OK;
+  const Plan pl = make_plan(m, n_points, m.d_k, chunk_cols);
+  if (workspace_bytes < pl.total) return PRB_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* a = out_acq ? out_acq : at<double>(workspace, pl.off_a);
+  uint32_t mask = 0;
+  for (int t = 0; t < m.spec.n_terms; ++t)
+    for (int f = 0; f < m.spec.t[t].n_factors; ++f)
+      if (m.spec.t[t].f[f].kind == PRB_FACTOR_MATERN52)
+        for (int i = 0; i < m.spec.t[t].f[f].n_dims; ++i) mask |= 1u << m.spec.t[t].f[f].dims[i];
+  return run_engine(m, aq, pl, workspace, xk, n_points, out_dacq_dx != nullptr, mask, a,
+                    at<double>(workspace, pl.off_dmu), at<double>(workspace, pl.off_dvar), out_dacq_dx, out_mean,
+                    out_var, st);
+}
+
+int prb_mc_value_grad(prb_model* model, const prb_space_desc* space, const prb_acq_desc* acq, const double* theta,
+                      int32_t b, int32_t mc, const double* u_int, const double* u_cat, uint64_t seed,
+                      uint64_t offset, int32_t estimator, double* ma_state, int32_t update_ma,
+                      const double* grad_out, double* out_value, double* out_grad, double* out_acq_values,
+                      void* workspace, size_t workspace_bytes, int32_t chunk_cols, void* stream) {
+  if (!model || !theta || !out_value || b < 0 || mc < 1 || !workspace) return PRB_ERR_INVALID;
+  if (grad_out && !out_grad) return PRB_ERR_INVALID;
+  if (estimator != PRB_EST_REINFORCE && estimator != PRB_EST_REINFORCE_MA) return PRB_ERR_INVALID;
+  if ((estimator == PRB_EST_REINFORCE_MA || update_ma) && !ma_state) return PRB_ERR_INVALID;
+  const Model& m = *reinterpret_cast<Model*>(model);
+  DevSpace sp;
+  DevAcq aq;
+  int rc = make_space(space, &sp);
+  if (rc != PRB_OK) return rc;
+  if ((rc = make_acq(acq, &aq)) != PRB_OK) return rc;
+  if (sp.d_k != m.d_k) return PRB_ERR_INVALID;
+  if (b == 0) return PRB_OK;
+  const Plan pl = make_plan(m, int64_t(b) * mc, sp.d, chunk_cols);
+  if (workspace_bytes < pl.total) return PRB_ERR_WORKSPACE;
+  return mc_core(model, sp, aq, pl, workspace, theta, b, mc, u_int, u_cat, seed, offset, estimator, ma_state,
+                 update_ma, grad_out, out_value, out_grad, out_acq_values, static_cast<cudaStream_t>(stream));
+}
+
+int prb_analytic_value_grad(prb_model* model, const prb_space_desc* space, const prb_acq_desc* acq,
+                            const double* theta, int32_t b, const int32_t* options, int32_t n_options,
+                            const double* grad_out, double* out_value, double* out_grad, double* out_probs,
+                            double* out_acq_values, void* workspace, size_t workspace_bytes, int32_t chunk_cols,
+                            void* stream) {
+  if (!model || !theta || !options || !out_value || b < 0 || n_options < 1 || !workspace) return PRB_ERR_INVALID;
+  if (grad_out && !out_grad) return PRB_ERR_INVALID;
+  const Model& m = *reinterpret_cast<Model*>(model);
+  DevSpace sp;
+  DevAcq aq;
+  int rc = make_space(space, &sp);
+  if (rc != PRB_OK) return rc;
+  if ((rc = make_acq(acq, &aq)) != PRB_OK) return rc;
+  if (sp.d_k != m.d_k) return PRB_ERR_INVALID;
+  if (b == 0) return PRB_OK;
+  const int64_t B = int64_t(b) * n_options;
+  const Plan pl = make_plan(m, B, sp.d, chunk_cols);
+  if (workspace_bytes < pl.total) return PRB_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* xk = at<double>(workspace, pl.off_xk);
+  double* probs = out_probs ? out_probs : at<double>(workspace, pl.off_probs);
+  double* a = out_acq_values ? out_acq_values : at<double>(workspace, pl.off_a);
+  double* S_all = at<double>(workspace, pl.off_S_all);
+  CUDA_TRY(launch_analytic_build(sp, theta, b, n_options, options, xk, probs, st));
+  const bool need_path = grad_out != nullptr && sp.n_cont > 0;
+  rc = run_engine(m, aq, pl, workspace, xk, B, need_path, cont_mask(sp), a, at<double>(workspace, pl.off_dmu),
+                  at<double>(workspace, pl.off_dvar), S_all, nullptr, nullptr, st);
+  if (rc != PRB_OK) return rc;
+  CUDA_TRY(launch_analytic_reduce(sp, theta, b, n_options, options, a, probs, S_all, grad_out, out_value, out_grad, st));
+  return PRB_OK;
+}
+
+int prb_mc_adam(prb_model* model, const prb_space_desc* space, const prb_acq_desc* acq, double* theta, int32_t b,
+                int32_t mc, const double* u_int, const double* u_cat, uint64_t seed, uint64_t offset,
+                int32_t estimator, double* ma_state, const double* lower, const double* upper, double lr,
+                int32_t maxiter, int32_t step0, double* adam_state, double* out_value, void* workspace,
+                size_t workspace_bytes, int32_t chunk_cols, void* stream) {
+  if (!model || !theta || !lower || !upper || !adam_state || !out_value || b < 1 || mc < 1 || maxiter < 0 || !workspace)
+    return PRB_ERR_INVALID;
+  if (estimator != PRB_EST_REINFORCE && estimator != PRB_EST_REINFORCE_MA) return PRB_ERR_INVALID;
+  if (estimator == PRB_EST_REINFORCE_MA && !ma_state) return PRB_ERR_INVALID;
+  const Model& m = *reinterpret_cast<Model*>(model);
+  DevSpace sp;
+  DevAcq aq;
+  int rc = make_space(space, &sp);
+  if (rc != PRB_OK) return rc;
+  if ((rc = make_acq(acq, &aq)) != PRB_OK) return rc;
+  if (sp.d_k != m.d_k) return PRB_ERR_INVALID;
+  const Plan pl = make_plan(m, int64_t(b) * mc, sp.d, chunk_cols);
+  if (workspace_bytes < pl.total) return PRB_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* Xc = at<double>(workspace, pl.off_Xc);
+  double* grad = at<double>(workspace, pl.off_grad);
+  double* ones = at<double>(workspace, pl.off_ones);
+  double* val = at<double>(workspace, pl.off_val);
+  int* step = at<int>(workspace, pl.off_step);
+  const int total = b * sp.d;
+  CUDA_TRY(launch_fill(ones, 1.0, b, st));
+  CUDA_TRY(cudaMemcpyAsync(step, &step0, sizeof(int), cudaMemcpyHostToDevice, st));
+  const int update_ma = ma_state ? 1 : 0;
+
+  auto one_iter = [&]() -> int {
+    CUDA_TRY(launch_clamp(theta, lower, upper, b, sp.d, Xc, st));
+    int r = mc_core(model, sp, aq, pl, workspace, Xc, b, mc, u_int, u_cat, seed, offset, estimator, ma_state,
+                    update_ma, ones, val, grad, nullptr, st);
+    if (r != PRB_OK) return r;
+    CUDA_TRY(launch_adam_step(theta, grad, adam_state, adam_state + total, total, lr, step, st));
+    return PRB_OK;
+  };
+
+  bool graphed = false;
+  if (st != nullptr && maxiter >= 4) {
+    // Capture ONE optimisation step and replay it: removes ~10 launches x maxiter of host latency (the reference spends
+    // its time exactly there at experiment sizes: 800 host-driven steps per BO iteration).
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      int r = one_iter();
+      cudaError_t e = cudaStreamEndCapture(st, &graph);
+      if (r == PRB_OK && e == cudaSuccess && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+        cudaError_t le = cudaSuccess;
+        for (int it = 0; it < maxiter && le == cudaSuccess; ++it) le = cudaGraphLaunch(exec, st);
+        graphed = (le == cudaSuccess);
+        // exec/graph must outlive the enqueued launches: release after the stream drains
+        cudaStreamSynchronize(st);
+        cudaGraphExecDestroy(exec);
+        if (!graphed) {
+          cudaGraphDestroy(graph);
+          return cuda_fail(le, "cudaGraphLaunch");
+        }
+      }
+      if (graph) cudaGraphDestroy(graph);
+      (void)cudaGetLastError();
+    }
+  }
+  if (!graphed) {
+    for (int it = 0; it < maxiter; ++it) {
+      rc = one_iter();
+      if (rc != PRB_OK) return rc;
+    }
+  }
+  // final clamp + value-only evaluation (gen.py:338-341); this call also advances the EMA state like any forward
+  CUDA_TRY(launch_clamp(theta, lower, upper, b, sp.d, theta, st));
+  return mc_core(model, sp, aq, pl, workspace, theta, b, mc, u_int, u_cat, seed, offset, estimator, ma_state,
+                 update_ma, nullptr, out_value, nullptr, nullptr, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+// Internal declarations shared by the sm_100a kernels of libprb200 (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "prb200.h"
+
+namespace prb {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Device-side kernel specification, passed BY VALUE as a kernel parameter (constant bank => uniform loads).
+// ---------------------------------------------------------------------------------------------------------------------
+struct DevFactor {
+  int32_t kind;
+  int32_t n_dims;
+  int32_t power;
+  int32_t pad;
+  int32_t dims[PRB_MAX_DIMS];
+  double inv_ls[PRB_MAX_DIMS];  // Matern: 1/l ; categorical: 1/(l * n_dims)
+};
+struct DevTerm {
+  double outputscale;
+  int32_t additive;
+  int32_t n_factors;
+  DevFactor f[PRB_MAX_FACTORS];
+};
+struct DevSpec {
+  int32_t n_terms;
+  int32_t d_k;
+  DevTerm t[PRB_MAX_TERMS];
+};
+
+struct DevSpace {
+  int32_t d, n_int, n_cat, apply_numeric;
+  int32_t n_disc, d_k, n_cont, raw_int;
+  int32_t int_cols[PRB_MAX_DIMS];
+  double int_lo[PRB_MAX_DIMS];
+  double int_hi[PRB_MAX_DIMS];
+  int32_t cat_start[PRB_MAX_CAT];
+  int32_t cat_card[PRB_MAX_CAT];
+  int32_t cont_cols[PRB_MAX_DIMS];  // theta columns that are continuous (same index in the kernel-input layout)
+  double tau;
+};
+
+struct DevAcq {
+  int32_t kind, ei_variant;
+  double param, min_variance, acq_var_floor;
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BN = 128;
+constexpr int GEMM_BK = 16;
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_LDS = GEMM_BK + 4;  // padded smem row stride (doubles): (row*20 + k) mod 16 distinct per half-warp
+constexpr int GEMM_THREADS = 256;
+constexpr size_t GEMM_SMEM_BYTES = size_t(GEMM_STAGES) * 2 * GEMM_BM * GEMM_LDS * sizeof(double);
+
+constexpr int GRAD_JSPLIT_ROWS = 128;  // rows of W handled by one CTA of the gradient contraction
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline int64_t round_up64(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+struct Model {
+  int n, d_k;
+  int Kp;        // round_up(n, 16): padded contraction length / leading dimension of the eval-major panels
+  int Mp1;       // round_up(n + 1, 128): rows of A1 = [Linv ; alpha^T ; 0]
+  int Mp2;       // round_up(n, 128): rows of A2 = Linv^T
+  double* A1;    // [Mp1, Kp] row-major
+  double* A2;    // [Mp2, Kp] row-major (upper triangular: A2[m, k] = Linv[k, m], k >= m)
+  double* Xtr;   // [n, d_k]
+  double* alpha; // [n]
+  double mean_const;
+  double kss;    // k(x, x)
+  DevSpec spec;
+  int device;
+};
+
+// launchers (prb_gemm.cu / prb_kernels.cu); all enqueue on `st` and return the CUDA status
+cudaError_t launch_trgemm_lower(const Model& m, const double* KstarT, int ncols_pad, double* VT, double* norm_part,
+                                double* mu_dot, cudaStream_t st);
+cudaError_t launch_trgemm_upper(const Model& m, const double* VT, int ncols_pad, double* W, cudaStream_t st);
+cudaError_t gemm_init();
+
+}  // namespace prb

@@ -1,0 +1,728 @@
+// PR hot-path kernels around the two triangular panel products: sampler, cross-covariance panel, acquisition epilogue,
+// pathwise-gradient contraction, MC / analytic reductions, EMA-baseline update, Adam step.
+#include "prb_device.cuh"
+#include "prb_kernels.cuh"
+
+namespace prb {
+
+// =====================================================================================================================
+// Philox materialisation (parity entry; the fused sampler calls philox_uniform() directly)
+// =====================================================================================================================
+__global__ void philox_fill_kernel(uint64_t seed, uint64_t offset, int mc, int n_cols, double* out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= mc * n_cols) return;
+  const int i = idx / n_cols, c = idx % n_cols;
+  out[idx] = philox_uniform(seed, offset, uint32_t(i), uint32_t(c));
+}
+
+cudaError_t launch_philox_fill(uint64_t seed, uint64_t offset, int mc, int n_cols, double* out, cudaStream_t st) {
+  const int total = mc * n_cols;
+  if (total == 0) return cudaSuccess;
+  philox_fill_kernel<<<(total + 255) / 256, 256, 0, st>>>(seed, offset, mc, n_cols, out);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================================
+// PR sampler: one thread per (restart b, MC sample i).
+//   reference: Normalize(reverse) -> MCProbabilisticReparameterizationInputTransform.transform (input.py:637-746)
+//              -> Normalize; rounding component z (probabilistic_reparameterization.py:454-465); prob (:470-475);
+//              OneHotToNumeric (input.py:69-88) when apply_numeric.
+// Base uniforms are indexed by (i, discrete parameter) only => shared by all restarts, as in the reference.
+// =====================================================================================================================
+__global__ void pr_sample_kernel(const DevSpace sp, const double* __restrict__ theta, int b, int mc,
+                                 const double* __restrict__ u_int, const double* __restrict__ u_cat, uint64_t seed,
+                                 uint64_t offset, double* __restrict__ xk, double* __restrict__ tilde,
+                                 uint8_t* __restrict__ zout, double* __restrict__ prob) {
+  const int64_t col = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (col >= int64_t(b) * mc) return;
+  const int bi = int(col / mc);
+  const int i = int(col % mc);
+  const double* th = theta + size_t(bi) * sp.d;
+  double* xr = xk ? xk + size_t(col) * sp.d_k : nullptr;
+  double* tr = tilde ? tilde + size_t(col) * sp.d : nullptr;
+  uint8_t* zr = zout ? zout + size_t(col) * sp.n_disc : nullptr;
+  double* pr = (prob && i == 0) ? prob + size_t(bi) * sp.n_disc : nullptr;
+  const int numeric_start = sp.n_cat > 0 ? sp.cat_start[0] : sp.d;
+
+  for (int c = 0; c < sp.d; ++c) {
+    const double v = th[c];
+    if (tr) tr[c] = v;
+    if (xr && (!sp.apply_numeric || c < numeric_start)) xr[c] = v;
+  }
+  // ---- integers (input.py:674-692)
+  for (int k = 0; k < sp.n_int; ++k) {
+    const int c = sp.int_cols[k];
+    const double x = th[c];
+    const double lo = sp.int_lo[k], hi = sp.int_hi[k];
+    const double range = __dsub_rn(hi, lo);
+    const double x_un = sp.raw_int ? x : unnormalize_int(x, lo, hi);
+    double off;
+    const double p = int_round_prob(x_un, sp.tau, &off);
+    const double u = u_int ? u_int[size_t(i) * sp.n_int + k] : philox_uniform(seed, offset, uint32_t(i), uint32_t(k));
+    const double zb = (p >= u) ? 1.0 : 0.0;
+    const double xa = off + zb;
+    const double xs = (x_un < 0.0) ? -xa : xa;
+    const double xc = fmin(fmax(xs, lo), hi);
+    const double tn = sp.raw_int ? xc : __dsub_rn(xc, lo) / range;
+    if (tr) tr[c] = tn;
+    if (xr) xr[c] = tn;
+    if (zr) zr[k] = ((__dsub_rn(tn, x) > 0.0) || (x == 1.0)) ? 1 : 0;
+    if (pr) pr[k] = p;
+  }
+  // ---- categoricals (input.py:715-744): softmax((x - 0.5)/tau), sequential cumsum, first index with cum > u (else 0)
+  int zpos = sp.n_int;
+  for (int j = 0; j < sp.n_cat; ++j) {
+    const int s = sp.cat_start[j], card = sp.cat_card[j];
+    double pk[PRB_MAX_CARD];
+    double mx = -1e300;
+    for (int k = 0; k < card; ++k) {
+      pk[k] = __dsub_rn(th[s + k], 0.5) / sp.tau;
+      mx = fmax(mx, pk[k]);
+    }
+    double sum = 0.0;
+    for (int k = 0; k < card; ++k) {
+      pk[k] = exp(__dsub_rn(pk[k], mx));
+      sum = __dadd_rn(sum, pk[k]);
+    }
+    const double inv = 1.0 / sum;
+    const double u = u_cat ? u_cat[size_t(i) * sp.n_cat + j]
+                           : philox_uniform(seed, offset, uint32_t(i), uint32_t(sp.n_int + j));
+    int cat = 0;
+    bool found = false;
+    double cum = 0.0;
+    for (int k = 0; k < card; ++k) {
+      pk[k] = __dmul_rn(pk[k], inv);
+      cum = __dadd_rn(cum, pk[k]);
+      if (!found && cum > u) {
+        cat = k;
+        found = true;
+      }
+    }
+    for (int k = 0; k < card; ++k) {
+      const double oh = (k == cat) ? 1.0 : 0.0;
+      if (tr) tr[s + k] = oh;
+      if (xr && !sp.apply_numeric) xr[s + k] = oh;
+      if (zr) zr[zpos + k] = (k == cat) ? 1 : 0;
+      if (pr) pr[zpos + k] = pk[k];
+    }
+    if (xr && sp.apply_numeric) xr[numeric_start + j] = double(cat);
+    zpos += card;
+  }
+}
+
+cudaError_t launch_pr_sample(const DevSpace& sp, const double* theta, int b, int mc, const double* u_int,
+                             const double* u_cat, uint64_t seed, uint64_t offset, double* xk, double* tilde,
+                             uint8_t* z, double* prob, cudaStream_t st) {
+  const int64_t total = int64_t(b) * mc;
+  if (total == 0) return cudaSuccess;
+  pr_sample_kernel<<<unsigned((total + 127) / 128), 128, 0, st>>>(sp, theta, b, mc, u_int, u_cat, seed, offset, xk,
+                                                                 tilde, z, prob);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================================
+// Analytic PR "sampler": one thread per (restart b, discrete configuration o).  Builds the kernel input
+// (input.py:466-488 + Normalize + OneHotToNumeric) and P(z | theta) (input.py:410-464).
+// options [n_opt, n_int + n_cat]: un-normalised integer value / category index.
+// =====================================================================================================================
+__global__ void analytic_build_kernel(const DevSpace sp, const double* __restrict__ theta, int b, int n_opt,
+                                      const int32_t* __restrict__ options, double* __restrict__ xk,
+                                      double* __restrict__ probs) {
+  const int64_t col = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (col >= int64_t(b) * n_opt) return;
+  const int bi = int(col / n_opt);
+  const int o = int(col % n_opt);
+  const double* th = theta + size_t(bi) * sp.d;
+  const int32_t* op = options + size_t(o) * (sp.n_int + sp.n_cat);
+  double* xr = xk ? xk + size_t(col) * sp.d_k : nullptr;
+  const int numeric_start = sp.n_cat > 0 ? sp.cat_start[0] : sp.d;
+  if (xr)
+    for (int c = 0; c < sp.d; ++c)
+      if (!sp.apply_numeric || c < numeric_start) xr[c] = th[c];
+  double P = 1.0;
+  for (int k = 0; k < sp.n_int; ++k) {
+    const int c = sp.int_cols[k];
+    const double lo = sp.int_lo[k], hi = sp.int_hi[k];
+    const double x_un = sp.raw_int ? th[c] : unnormalize_int(th[c], lo, hi);
+    double off;
+    const double p = int_round_prob(x_un, sp.tau, &off);
+    const double zv = double(op[k]);
+    const double diff = (off + 1.0) - zv;
+    const double f = (diff == 0.0) ? p : ((diff == 1.0) ? (1.0 - p) : 0.0);
+    P *= f;
+    if (xr) xr[c] = sp.raw_int ? zv : __dsub_rn(zv, lo) / __dsub_rn(hi, lo);
+  }
+  for (int j = 0; j < sp.n_cat; ++j) {
+    const int s = sp.cat_start[j], card = sp.cat_card[j];
+    const int cat = op[sp.n_int + j];
+    double mx = -1e300;
+    for (int k = 0; k < card; ++k) mx = fmax(mx, __dsub_rn(th[s + k], 0.5) / sp.tau);
+    double sum = 0.0, sel = 0.0;
+    for (int k = 0; k < card; ++k) {
+      const double e = exp(__dsub_rn(__dsub_rn(th[s + k], 0.5) / sp.tau, mx));
+      sum += e;
+      if (k == cat) sel = e;
+    }
+    P *= sel * (1.0 / sum);
+    if (xr) {
+      if (sp.apply_numeric) {
+        xr[numeric_start + j] = double(cat);
+      } else {
+        for (int k = 0; k < card; ++k) xr[s + k] = (k == cat) ? 1.0 : 0.0;
+      }
+    }
+  }
+  if (probs) probs[col] = P;
+}
+
+cudaError_t launch_analytic_build(const DevSpace& sp, const double* theta, int b, int n_opt, const int32_t* options,
+                                  double* xk, double* probs, cudaStream_t st) {
+  const int64_t total = int64_t(b) * n_opt;
+  if (total == 0) return cudaSuccess;
+  analytic_build_kernel<<<unsigned((total + 127) / 128), 128, 0, st>>>(sp, theta, b, n_opt, options, xk, probs);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================================
+// Cross-covariance panel  Kstar^T[col, j] = k(x_col, X_j)   (eval-major, training index contiguous, zero padded).
+//   reference: covar_module(X*, X_train) inside model.posterior ([3P]; kernel structure kernels.py:18-101).
+// grid (ceil(Kp/128), ncols_pad/32); thread <-> training point j, CTA loops over 32 evaluation points.
+// =====================================================================================================================
+constexpr int KS_ROWS = 128;
+constexpr int KS_COLS = 32;
+
+__device__ __forceinline__ double eval_kernel_value(const DevSpec& spec, const double* __restrict__ xs /*[d_k]*/,
+                                                    const double* __restrict__ Xs /*[d_k][KS_ROWS] + tid*/) {
+  double kval = 0.0;
+  for (int t = 0; t < spec.n_terms; ++t) {
+    const DevTerm& T = spec.t[t];
+    double acc = T.additive ? 0.0 : 1.0;
+    for (int f = 0; f < T.n_factors; ++f) {
+      const DevFactor& F = T.f[f];
+      double v;
+      if (F.kind == PRB_FACTOR_MATERN52) {
+        double r2 = 0.0;
+        for (int di = 0; di < F.n_dims; ++di) {
+          const int dim = F.dims[di];
+          const double df = (xs[dim] - Xs[dim * KS_ROWS]) * F.inv_ls[di];
+          r2 = fma(df, df, r2);
+        }
+        v = matern52_value(r2);
+      } else {
+        double s = 0.0;
+        for (int di = 0; di < F.n_dims; ++di) {
+          const int dim = F.dims[di];
+          s += (xs[dim] != Xs[dim * KS_ROWS]) ? F.inv_ls[di] : 0.0;
+        }
+        v = exp(-s);
+      }
+      v = ipow(v, F.power);
+      acc = T.additive ? acc + v : acc * v;
+    }
+    kval = fma(T.outputscale, acc, kval);
+  }
+  return kval;
+}
+
+__global__ void __launch_bounds__(KS_ROWS) kstar_panel_kernel(const DevSpec spec, const double* __restrict__ Xtr, int n,
+                                                               int Kp, const double* __restrict__ xk, int ncols,
+                                                               int ncols_store, double* __restrict__ KstarT) {
+  extern __shared__ double sm[];
+  const int d_k = spec.d_k;
+  double* Xs = sm;                     // [d_k][KS_ROWS]
+  double* xs = sm + d_k * KS_ROWS;     // [KS_COLS][d_k]
+  const int tid = threadIdx.x;
+  const int j = blockIdx.x * KS_ROWS + tid;
+  const int col0 = blockIdx.y * KS_COLS;
+  const bool valid = j < n;
+  for (int dd = 0; dd < d_k; ++dd) Xs[dd * KS_ROWS + tid] = valid ? Xtr[size_t(j) * d_k + dd] : 0.0;
+  for (int idx = tid; idx < KS_COLS * d_k; idx += KS_ROWS) {
+    const int c = idx / d_k;
+    xs[idx] = (col0 + c < ncols) ? xk[size_t(col0) * d_k + idx] : 0.0;
+  }
+  __syncthreads();
+  if (j >= Kp) return;
+  for (int c = 0; c < KS_COLS; ++c) {
+    const int col = col0 + c;
+    double v = 0.0;
+    if (col >= ncols_store) break;
+    if (valid && col < ncols) v = eval_kernel_value(spec, xs + c * d_k, Xs + tid);
+    KstarT[size_t(col) * Kp + j] = v;
+  }
+}
+
+cudaError_t launch_kstar_panel(const Model& m, const double* xk, int ncols, int ncols_pad, double* KstarT,
+                               cudaStream_t st) {
+  dim3 grid((m.Kp + KS_ROWS - 1) / KS_ROWS, ncols_pad / KS_COLS);
+  const size_t smem = size_t(m.d_k) * (KS_ROWS + KS_COLS) * sizeof(double);
+  kstar_panel_kernel<<<grid, KS_ROWS, smem, st>>>(m.spec, m.Xtr, m.n, m.Kp, xk, ncols, ncols_pad, KstarT);
+  return cudaGetLastError();
+}
+
+// plain K(xk, X_train) -> out[n_points, n] (leading dimension n, nothing stored beyond n_points)
+cudaError_t launch_kernel_matrix(const DevSpec& spec, const double* Xtr, int n, const double* xk, int n_points,
+                                 double* out, cudaStream_t st) {
+  if (n_points == 0) return cudaSuccess;
+  dim3 grid((n + KS_ROWS - 1) / KS_ROWS, (n_points + KS_COLS - 1) / KS_COLS);
+  const size_t smem = size_t(spec.d_k) * (KS_ROWS + KS_COLS) * sizeof(double);
+  kstar_panel_kernel<<<grid, KS_ROWS, smem, st>>>(spec, Xtr, n, n, xk, n_points, n_points, out);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================================
+// Acquisition epilogue: posterior mean / variance -> EI / UCB / mean and its partial derivatives.
+//   reference: [3P] gpytorch variance clamp (min_variance), botorch ExpectedImprovement / UpperConfidenceBound /
+//   PosteriorMean; call sites experiment_utils.py:391-393, 476-480, 489-492.
+// =====================================================================================================================
+#define PRB_LOG_SQRT_2PI 0.91893853320467274178
+#define PRB_INV_SQRT2 0.70710678118654752440
+
+__global__ void acq_epilogue_kernel(const DevAcq aq, double mean_const, double kss, const double* __restrict__ norm_part,
+                                    int mtiles, int ncols_pad, const double* __restrict__ mu_dot, int ncols,
+                                    double* __restrict__ a, double* __restrict__ dmu, double* __restrict__ dvar,
+                                    double* __restrict__ out_mean, double* __restrict__ out_var) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncols) return;
+  double vs = 0.0;
+  for (int t = 0; t < mtiles; ++t) vs += norm_part[size_t(t) * ncols_pad + col];
+  const double var_raw = kss - vs;
+  const double var = fmax(var_raw, aq.min_variance);
+  const double pass1 = (var_raw >= aq.min_variance) ? 1.0 : 0.0;
+  const double mean = mean_const + mu_dot[col];
+  double val, d_mu, d_var;
+  if (aq.kind == PRB_ACQ_EI) {
+    const double v2 = fmax(var, aq.acq_var_floor);
+    const double pass2 = (var >= aq.acq_var_floor) ? 1.0 : 0.0;
+    const double sigma = sqrt(v2);
+    const double u = (mean - aq.param) / sigma;
+    const double pdf = exp(-(u * u) / 2.0 - PRB_LOG_SQRT_2PI);
+    const double cdf = aq.ei_variant == 0 ? 0.5 * (1.0 + erf(u * PRB_INV_SQRT2)) : 0.5 * erfc(-u * PRB_INV_SQRT2);
+    val = sigma * (pdf + u * cdf);
+    d_mu = cdf;
+    d_var = pdf / (2.0 * sigma) * pass1 * pass2;
+  } else if (aq.kind == PRB_ACQ_UCB) {
+    const double bv = aq.param * var;
+    const double sd = sqrt(bv);
+    val = mean + sd;
+    d_mu = 1.0;
+    d_var = (sd > 0.0 ? aq.param / (2.0 * sd) : 0.0) * pass1;
+  } else {
+    val = mean;
+    d_mu = 1.0;
+    d_var = 0.0;
+  }
+  a[col] = val;
+  if (dmu) dmu[col] = d_mu;
+  if (dvar) dvar[col] = d_var;
+  if (out_mean) out_mean[col] = mean;
+  if (out_var) out_var[col] = var;
+}
+
+cudaError_t launch_acq_epilogue(const Model& m, const DevAcq& aq, const double* norm_part, int ncols_pad,
+                                const double* mu_dot, int ncols, double* a, double* dmu, double* dvar,
+                                double* out_mean, double* out_var, cudaStream_t st) {
+  if (ncols == 0) return cudaSuccess;
+  acq_epilogue_kernel<<<(ncols + 127) / 128, 128, 0, st>>>(aq, m.mean_const, m.kss, norm_part, m.Mp1 / GEMM_BM,
+                                                           ncols_pad, mu_dot, ncols, a, dmu, dvar, out_mean, out_var);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================================
+// Pathwise-gradient contraction:  S[col, dim] = sum_j C_j(col) * d k*_j(col) / d x_dim ,
+//   C_j = dA/dmu * alpha_j - 2 dA/dsigma^2 * W[j, col]      (W = Linv^T Linv k* = K^-1 k*)
+//   reference: torch.autograd.grad(mean_acq_values, cont_input) through the GP posterior
+//   (probabilistic_reparameterization.py:624-633).
+// grid (ncols_pad/128, Mp2/128): thread <-> evaluation point, CTA covers 128 training rows; partial sums per row block are
+// written to S_part[jblock][dim][col] and summed in a fixed order afterwards (bitwise reproducible).
+// =====================================================================================================================
+constexpr int GR_COLS = 128;
+
+__global__ void __launch_bounds__(GR_COLS) grad_contract_kernel(const DevSpec spec, uint32_t diffmask,
+                                                                const double* __restrict__ Xtr,
+                                                                const double* __restrict__ alpha, int n,
+                                                                const double* __restrict__ xk, int ncols,
+                                                                int ncols_pad, const double* __restrict__ W,
+                                                                const double* __restrict__ dmu,
+                                                                const double* __restrict__ dvar,
+                                                                double* __restrict__ S_part) {
+  extern __shared__ double sm[];
+  const int d_k = spec.d_k;
+  double* xs = sm;                                   // [d_k][GR_COLS]
+  double* accs = xs + d_k * GR_COLS;                 // [d_k][GR_COLS]
+  double* Xs = accs + d_k * GR_COLS;                 // [GRAD_JSPLIT_ROWS][d_k]
+  double* als = Xs + GRAD_JSPLIT_ROWS * d_k;         // [GRAD_JSPLIT_ROWS]
+  const int tid = threadIdx.x;
+  const int col = blockIdx.x * GR_COLS + tid;
+  const int j0 = blockIdx.y * GRAD_JSPLIT_ROWS;
+  const int jn = min(GRAD_JSPLIT_ROWS, n - j0);
+  const bool cvalid = col < ncols;
+  for (int dd = 0; dd < d_k; ++dd) {
+    xs[dd * GR_COLS + tid] = cvalid ? xk[size_t(col) * d_k + dd] : 0.0;
+    accs[dd * GR_COLS + tid] = 0.0;
+  }
+  for (int idx = tid; idx < jn * d_k; idx += GR_COLS) Xs[idx] = Xtr[size_t(j0) * d_k + idx];
+  for (int idx = tid; idx < jn; idx += GR_COLS) als[idx] = alpha[j0 + idx];
+  __syncthreads();
+  if (cvalid) {
+    const double cm = dmu[col];
+    const double cv = -2.0 * dvar[col];
+    const double* x = xs + tid;
+    double* ac = accs + tid;
+    for (int jj = 0; jj < jn; ++jj) {
+      const double Cj = fma(cv, W[size_t(j0 + jj) * ncols_pad + col], cm * als[jj]);
+      const double* Xj = Xs + jj * d_k;
+      for (int t = 0; t < spec.n_terms; ++t) {
+        const DevTerm& T = spec.t[t];
+        double Fv[PRB_MAX_FACTORS], Gv[PRB_MAX_FACTORS];
+#pragma unroll
+        for (int f = 0; f < PRB_MAX_FACTORS; ++f) {
+          Fv[f] = 1.0;
+          Gv[f] = 0.0;
+          if (f < T.n_factors) {
+            const DevFactor& F = T.f[f];
+            if (F.kind == PRB_FACTOR_MATERN52) {
+              double r2 = 0.0;
+              for (int di = 0; di < F.n_dims; ++di) {
+                const int dim = F.dims[di];
+                const double df = (x[dim * GR_COLS] - Xj[dim]) * F.inv_ls[di];
+                r2 = fma(df, df, r2);
+              }
+              Fv[f] = matern52(r2, &Gv[f]);
+            } else {
+              double s = 0.0;
+              for (int di = 0; di < F.n_dims; ++di) {
+                const int dim = F.dims[di];
+                s += (x[dim * GR_COLS] != Xj[dim]) ? F.inv_ls[di] : 0.0;
+              }
+              Fv[f] = exp(-s);
+            }
+          }
+        }
+#pragma unroll
+        for (int f = 0; f < PRB_MAX_FACTORS; ++f) {
+          if (f < T.n_factors && T.f[f].kind == PRB_FACTOR_MATERN52) {
+            const DevFactor& F = T.f[f];
+            // Q = outputscale * d(term)/dF_f * G_f * C_j
+            double q = T.outputscale * Gv[f] * Cj;
+            if (!T.additive) {
+              if (F.power > 1) q *= double(F.power) * ipow(Fv[f], F.power - 1);
+#pragma unroll
+              for (int g = 0; g < PRB_MAX_FACTORS; ++g)
+                if (g != f && g < T.n_factors) q *= ipow(Fv[g], T.f[g].power);
+            } else if (F.power > 1) {
+              q *= double(F.power) * ipow(Fv[f], F.power - 1);
+            }
+            for (int di = 0; di < F.n_dims; ++di) {
+              const int dim = F.dims[di];
+              if ((diffmask >> dim) & 1u) {
+                const double w = F.inv_ls[di] * F.inv_ls[di];
+                ac[dim * GR_COLS] = fma(q * w, x[dim * GR_COLS] - Xj[dim], ac[dim * GR_COLS]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  for (int dd = 0; dd < d_k; ++dd)
+    S_part[(size_t(blockIdx.y) * d_k + dd) * ncols_pad + col] = accs[dd * GR_COLS + tid];
+}
+
+cudaError_t launch_grad_contract(const Model& m, uint32_t diffmask, const double* xk, int ncols, int ncols_pad,
+                                 const double* W, const double* dmu, const double* dvar, double* S_part,
+                                 cudaStream_t st) {
+  dim3 grid(ncols_pad / GR_COLS, m.Mp2 / GRAD_JSPLIT_ROWS);
+  const size_t smem = (size_t(m.d_k) * (2 * GR_COLS + GRAD_JSPLIT_ROWS) + GRAD_JSPLIT_ROWS) * sizeof(double);
+  grad_contract_kernel<<<grid, GR_COLS, smem, st>>>(m.spec, diffmask, m.Xtr, m.alpha, m.n, xk, ncols, ncols_pad, W,
+                                                    dmu, dvar, S_part);
+  return cudaGetLastError();
+}
+
+// S_all[col_global, dim] = sum_jblock S_part[jblock][dim][col]   (fixed order)
+__global__ void sum_splits_kernel(const double* __restrict__ S_part, int jblocks, int d_k, int ncols, int ncols_pad,
+                                  double* __restrict__ S_all) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncols) return;
+  for (int dd = 0; dd < d_k; ++dd) {
+    double s = 0.0;
+    for (int jb = 0; jb < jblocks; ++jb) s += S_part[(size_t(jb) * d_k + dd) * ncols_pad + col];
+    S_all[size_t(col) * d_k + dd] = s;
+  }
+}
+
+cudaError_t launch_sum_splits(const Model& m, const double* S_part, int ncols, int ncols_pad, double* S_all,
+                              cudaStream_t st) {
+  if (ncols == 0) return cudaSuccess;
+  sum_splits_kernel<<<(ncols + 127) / 128, 128, 0, st>>>(S_part, m.Mp2 / GRAD_JSPLIT_ROWS, m.d_k, ncols, ncols_pad,
+                                                         S_all);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================================
+// Block reduction helper: fixed-order (lane tree, then warp 0 sums warp partials sequentially) => deterministic.
+// =====================================================================================================================
+__device__ __forceinline__ double block_sum(double v, double* red /*[32]*/) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double s = 0.0;
+  const int nw = (blockDim.x + 31) >> 5;
+  for (int w = 0; w < nw; ++w) s += red[w];
+  return s;
+}
+
+// =====================================================================================================================
+// MC reduction: one CTA per restart.
+//   value_b = mean_i a_i                                                  (probabilistic_reparameterization.py:495-498)
+//   discrete columns: grad_out_b * mean_i[ (a_i - baseline)(z_i - p) / tau ]        (:598-622)
+//   continuous columns: grad_out_b * mean_i S[i, col]                                (:624-633)
+//   baseline from the PRE-update EMA state (:600-609).
+// =====================================================================================================================
+__global__ void __launch_bounds__(128) mc_reduce_kernel(const DevSpace sp, int mc, const double* __restrict__ a,
+                                                        const uint8_t* __restrict__ z,
+                                                        const double* __restrict__ prob,
+                                                        const double* __restrict__ S_all, int estimator,
+                                                        const double* __restrict__ ma_state,
+                                                        const double* __restrict__ grad_out,
+                                                        double* __restrict__ out_value,
+                                                        double* __restrict__ out_grad) {
+  __shared__ double red[32];
+  const int bi = blockIdx.x;
+  const int tid = threadIdx.x;
+  const size_t c0 = size_t(bi) * mc;
+  double s = 0.0;
+  for (int i = tid; i < mc; i += blockDim.x) s += a[c0 + i];
+  s = block_sum(s, red);
+  if (tid == 0) out_value[bi] = s / double(mc);
+  if (!grad_out) return;
+  double baseline = 0.0;
+  if (estimator == PRB_EST_REINFORCE_MA) {
+    const double cnt = ma_state[0];
+    if (cnt != 0.0) baseline = ma_state[1] / (1.0 - pow(0.7, cnt));
+  }
+  const double go = grad_out[bi];
+  double* g = out_grad + size_t(bi) * sp.d;
+  // continuous columns
+  for (int ci = 0; ci < sp.n_cont; ++ci) {
+    const int c = sp.cont_cols[ci];
+    double t = 0.0;
+    for (int i = tid; i < mc; i += blockDim.x) t += S_all[(c0 + i) * sp.d_k + c];
+    t = block_sum(t, red);
+    if (tid == 0) g[c] = go * (t / double(mc));
+  }
+  // discrete columns: integers first, then the one-hot columns (the order of `discrete_indices`, input.py:574-597)
+  const int cat0 = sp.n_cat > 0 ? sp.cat_start[0] : 0;
+  for (int kd = 0; kd < sp.n_disc; ++kd) {
+    const double p = prob[size_t(bi) * sp.n_disc + kd];
+    double t = 0.0;
+    for (int i = tid; i < mc; i += blockDim.x) {
+      const double zi = double(z[(c0 + i) * sp.n_disc + kd]);
+      t += ((a[c0 + i] - baseline) * (zi - p)) / sp.tau;
+    }
+    t = block_sum(t, red);
+    if (tid == 0) {
+      const int c = kd < sp.n_int ? sp.int_cols[kd] : cat0 + (kd - sp.n_int);
+      g[c] = go * (t / double(mc));
+    }
+  }
+}
+
+cudaError_t launch_mc_reduce(const DevSpace& sp, int b, int mc, const double* a, const uint8_t* z, const double* prob,
+                             const double* S_all, int estimator, const double* ma_state, const double* grad_out,
+                             double* out_value, double* out_grad, cudaStream_t st) {
+  if (b == 0) return cudaSuccess;
+  mc_reduce_kernel<<<b, 128, 0, st>>>(sp, mc, a, z, prob, S_all, estimator, ma_state, grad_out, out_value, out_grad);
+  return cudaGetLastError();
+}
+
+// EMA baseline update (probabilistic_reparameterization.py:499-505): counter += 1; hidden -= (hidden - mean) * 0.3,
+// mean over ALL b*mc acquisition values of the call (= mean of the per-restart means, equal mc).
+__global__ void ma_update_kernel(const double* __restrict__ value, int b, double* __restrict__ ma_state) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < b; i += blockDim.x) s += value[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    const double mean = s / double(b);
+    const double hidden = ma_state[1];
+    ma_state[0] += 1.0;
+    ma_state[1] = hidden - (hidden - mean) * (1.0 - 0.7);
+  }
+}
+
+cudaError_t launch_ma_update(const double* value, int b, double* ma_state, cudaStream_t st) {
+  ma_update_kernel<<<1, 128, 0, st>>>(value, b, ma_state);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================================
+// Analytic reduction: one CTA per restart.
+//   value_b = sum_o P_o a_o ;  d/d theta_cont = sum_o P_o S[o, col] ;  d/d theta_disc = sum_o a_o dP_o/d theta
+//   (autograd through get_probs, input.py:410-464, including the Normalize chain-rule factor `range` for integers).
+// =====================================================================================================================
+__global__ void __launch_bounds__(128) analytic_reduce_kernel(const DevSpace sp, const double* __restrict__ theta,
+                                                              int n_opt, const int32_t* __restrict__ options,
+                                                              const double* __restrict__ a,
+                                                              const double* __restrict__ probs,
+                                                              const double* __restrict__ S_all,
+                                                              const double* __restrict__ grad_out,
+                                                              double* __restrict__ out_value,
+                                                              double* __restrict__ out_grad) {
+  __shared__ double red[32];
+  __shared__ double p_int[PRB_MAX_DIMS], dp_int[PRB_MAX_DIMS], off_int[PRB_MAX_DIMS];
+  __shared__ double sm_cat[PRB_MAX_CAT * PRB_MAX_CARD];
+  const int bi = blockIdx.x, tid = threadIdx.x;
+  const size_t c0 = size_t(bi) * n_opt;
+  const double* th = theta + size_t(bi) * sp.d;
+  double s = 0.0;
+  for (int o = tid; o < n_opt; o += blockDim.x) s += a[c0 + o] * probs[c0 + o];
+  s = block_sum(s, red);
+  if (tid == 0) out_value[bi] = s;
+  if (!grad_out) return;
+  // per-restart factor tables
+  if (tid < sp.n_int) {
+    const double lo = sp.int_lo[tid], hi = sp.int_hi[tid];
+    const double x_un = unnormalize_int(th[sp.int_cols[tid]], lo, hi);
+    double off;
+    const double p = int_round_prob(x_un, sp.tau, &off);
+    const double sgn = (x_un > 0.0) ? 1.0 : ((x_un < 0.0) ? -1.0 : 0.0);
+    p_int[tid] = p;
+    off_int[tid] = off;
+    dp_int[tid] = p * (1.0 - p) / sp.tau * sgn * (hi - lo);
+  }
+  if (tid < sp.n_cat) {
+    const int st = sp.cat_start[tid], card = sp.cat_card[tid];
+    double mx = -1e300;
+    for (int k = 0; k < card; ++k) mx = fmax(mx, __dsub_rn(th[st + k], 0.5) / sp.tau);
+    double sum = 0.0;
+    for (int k = 0; k < card; ++k) {
+      const double e = exp(__dsub_rn(__dsub_rn(th[st + k], 0.5) / sp.tau, mx));
+      sm_cat[tid * PRB_MAX_CARD + k] = e;
+      sum += e;
+    }
+    const double inv = 1.0 / sum;
+    for (int k = 0; k < card; ++k) sm_cat[tid * PRB_MAX_CARD + k] *= inv;
+  }
+  __syncthreads();
+  const double go = grad_out[bi];
+  double* g = out_grad + size_t(bi) * sp.d;
+  for (int ci = 0; ci < sp.n_cont; ++ci) {
+    const int c = sp.cont_cols[ci];
+    double t = 0.0;
+    for (int o = tid; o < n_opt; o += blockDim.x) t += probs[c0 + o] * S_all[(c0 + o) * sp.d_k + c];
+    t = block_sum(t, red);
+    if (tid == 0) g[c] = go * t;
+  }
+  const int nv = sp.n_int + sp.n_cat;
+  // integer columns
+  for (int k = 0; k < sp.n_int; ++k) {
+    double t = 0.0;
+    for (int o = tid; o < n_opt; o += blockDim.x) {
+      const int32_t* op = options + size_t(o) * nv;
+      const double diff = (off_int[k] + 1.0) - double(op[k]);
+      const double df = (diff == 0.0) ? dp_int[k] : ((diff == 1.0) ? -dp_int[k] : 0.0);
+      if (df != 0.0) {
+        double excl = 1.0;
+        for (int k2 = 0; k2 < sp.n_int; ++k2) {
+          if (k2 == k) continue;
+          const double d2 = (off_int[k2] + 1.0) - double(op[k2]);
+          excl *= (d2 == 0.0) ? p_int[k2] : ((d2 == 1.0) ? (1.0 - p_int[k2]) : 0.0);
+        }
+        for (int j = 0; j < sp.n_cat; ++j) excl *= sm_cat[j * PRB_MAX_CARD + op[sp.n_int + j]];
+        t += a[c0 + o] * excl * df;
+      }
+    }
+    t = block_sum(t, red);
+    if (tid == 0) g[sp.int_cols[k]] = go * t;
+  }
+  // one-hot columns: d softmax_c / d theta_m = softmax_c (delta_cm - softmax_m) / tau
+  for (int j = 0; j < sp.n_cat; ++j) {
+    for (int m = 0; m < sp.cat_card[j]; ++m) {
+      double t = 0.0;
+      for (int o = tid; o < n_opt; o += blockDim.x) {
+        const int32_t* op = options + size_t(o) * nv;
+        const int c = op[sp.n_int + j];
+        double excl = 1.0;
+        for (int k2 = 0; k2 < sp.n_int; ++k2) {
+          const double d2 = (off_int[k2] + 1.0) - double(op[k2]);
+          excl *= (d2 == 0.0) ? p_int[k2] : ((d2 == 1.0) ? (1.0 - p_int[k2]) : 0.0);
+        }
+        for (int j2 = 0; j2 < sp.n_cat; ++j2)
+          if (j2 != j) excl *= sm_cat[j2 * PRB_MAX_CARD + op[sp.n_int + j2]];
+        const double smc = sm_cat[j * PRB_MAX_CARD + c];
+        const double smm = sm_cat[j * PRB_MAX_CARD + m];
+        t += a[c0 + o] * excl * smc * ((c == m ? 1.0 : 0.0) - smm) / sp.tau;
+      }
+      t = block_sum(t, red);
+      if (tid == 0) g[sp.cat_start[j] + m] = go * t;
+    }
+  }
+}
+
+cudaError_t launch_analytic_reduce(const DevSpace& sp, const double* theta, int b, int n_opt, const int32_t* options,
+                                   const double* a, const double* probs, const double* S_all, const double* grad_out,
+                                   double* out_value, double* out_grad, cudaStream_t st) {
+  if (b == 0) return cudaSuccess;
+  analytic_reduce_kernel<<<b, 128, 0, st>>>(sp, theta, n_opt, options, a, probs, S_all, grad_out, out_value, out_grad);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================================
+// Multi-start Adam pieces (gen.py:304-337): X = clamp(theta) ; theta <- Adam(theta, grad = -dA/dX)
+// =====================================================================================================================
+__global__ void clamp_kernel(const double* __restrict__ theta, const double* __restrict__ lower,
+                             const double* __restrict__ upper, int b, int d, double* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= b * d) return;
+  const int c = idx % d;
+  out[idx] = fmin(fmax(theta[idx], lower[c]), upper[c]);
+}
+
+cudaError_t launch_clamp(const double* theta, const double* lower, const double* upper, int b, int d, double* out,
+                         cudaStream_t st) {
+  clamp_kernel<<<(b * d + 255) / 256, 256, 0, st>>>(theta, lower, upper, b, d, out);
+  return cudaGetLastError();
+}
+
+// torch.optim.Adam (single-tensor path, no amsgrad / weight decay): exp_avg.lerp_(g, 1-b1);
+// exp_avg_sq = b2*exp_avg_sq + (1-b2) g*g; denom = sqrt(exp_avg_sq)/sqrt(1-b2^t) + eps; theta -= lr/(1-b1^t) * exp_avg/denom
+__global__ void adam_step_kernel(double* __restrict__ theta, const double* __restrict__ acq_grad, double* __restrict__ m,
+                                 double* __restrict__ v, int total, double lr, const int* __restrict__ step_ptr) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const double t = double(*step_ptr);
+  const double g = -acq_grad[idx];  // loss = -acq(X).sum()
+  const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+  const double mi = m[idx] + (g - m[idx]) * (1.0 - b1);
+  const double vi = v[idx] * b2 + (1.0 - b2) * g * g;
+  m[idx] = mi;
+  v[idx] = vi;
+  const double bc1 = 1.0 - pow(b1, t);
+  const double bc2 = 1.0 - pow(b2, t);
+  const double step_size = lr / bc1;
+  const double denom = sqrt(vi) / sqrt(bc2) + eps;
+  theta[idx] = theta[idx] - step_size * (mi / denom);
+}
+__global__ void step_inc_kernel(int* step_ptr) { *step_ptr += 1; }
+
+cudaError_t launch_adam_step(double* theta, const double* acq_grad, double* m, double* v, int total, double lr,
+                             int* step_ptr, cudaStream_t st) {
+  step_inc_kernel<<<1, 1, 0, st>>>(step_ptr);
+  adam_step_kernel<<<(total + 255) / 256, 256, 0, st>>>(theta, acq_grad, m, v, total, lr, step_ptr);
+  return cudaGetLastError();
+}
+
+__global__ void fill_kernel(double* p, double v, int n) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) p[idx] = v;
+}
+cudaError_t launch_fill(double* p, double v, int n, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  fill_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, v, n);
+  return cudaGetLastError();
+}
+
+}  // namespace prb

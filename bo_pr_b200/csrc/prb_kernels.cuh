@@ -1,0 +1,39 @@
+// Launcher declarations for prb_kernels.cu (internal).
+#pragma once
+
+#include "prb_internal.cuh"
+
+namespace prb {
+
+cudaError_t launch_philox_fill(uint64_t seed, uint64_t offset, int mc, int n_cols, double* out, cudaStream_t st);
+cudaError_t launch_pr_sample(const DevSpace& sp, const double* theta, int b, int mc, const double* u_int,
+                             const double* u_cat, uint64_t seed, uint64_t offset, double* xk, double* tilde,
+                             uint8_t* z, double* prob, cudaStream_t st);
+cudaError_t launch_analytic_build(const DevSpace& sp, const double* theta, int b, int n_opt, const int32_t* options,
+                                  double* xk, double* probs, cudaStream_t st);
+cudaError_t launch_kstar_panel(const Model& m, const double* xk, int ncols, int ncols_pad, double* KstarT,
+                               cudaStream_t st);
+cudaError_t launch_kernel_matrix(const DevSpec& spec, const double* Xtr, int n, const double* xk, int n_points,
+                                 double* out, cudaStream_t st);
+cudaError_t launch_acq_epilogue(const Model& m, const DevAcq& aq, const double* norm_part, int ncols_pad,
+                                const double* mu_dot, int ncols, double* a, double* dmu, double* dvar,
+                                double* out_mean, double* out_var, cudaStream_t st);
+cudaError_t launch_grad_contract(const Model& m, uint32_t diffmask, const double* xk, int ncols, int ncols_pad,
+                                 const double* W, const double* dmu, const double* dvar, double* S_part,
+                                 cudaStream_t st);
+cudaError_t launch_sum_splits(const Model& m, const double* S_part, int ncols, int ncols_pad, double* S_all,
+                              cudaStream_t st);
+cudaError_t launch_mc_reduce(const DevSpace& sp, int b, int mc, const double* a, const uint8_t* z, const double* prob,
+                             const double* S_all, int estimator, const double* ma_state, const double* grad_out,
+                             double* out_value, double* out_grad, cudaStream_t st);
+cudaError_t launch_ma_update(const double* value, int b, double* ma_state, cudaStream_t st);
+cudaError_t launch_analytic_reduce(const DevSpace& sp, const double* theta, int b, int n_opt, const int32_t* options,
+                                   const double* a, const double* probs, const double* S_all, const double* grad_out,
+                                   double* out_value, double* out_grad, cudaStream_t st);
+cudaError_t launch_clamp(const double* theta, const double* lower, const double* upper, int b, int d, double* out,
+                         cudaStream_t st);
+cudaError_t launch_adam_step(double* theta, const double* acq_grad, double* m, double* v, int total, double lr,
+                             int* step_ptr, cudaStream_t st);
+cudaError_t launch_fill(double* p, double v, int n, cudaStream_t st);
+
+}  // namespace prb

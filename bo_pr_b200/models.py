@@ -1,0 +1,212 @@
+"""Exact-GP model surface (``FixedNoiseGP``) and the device-side GP state the CUDA path reads.
+
+The reference builds a BoTorch ``FixedNoiseGP`` with a ``ConstantMean`` and the ``get_kernel`` covariance
+(``discrete_mixed_bo/experiment_utils.py:237-351``) and lets GPyTorch's exact prediction strategy cache
+``(K + Sigma)^-1 (y - c)`` and the inverse Cholesky root.  ``GPState`` is that cache as plain device tensors
+(``X_train``, ``Linv``, ``alpha``, constant, kernel structure) handed to ``libprb200`` through ``prb_model_create``.
+``K(X, X)`` is assembled by the library's own kernel (``prb_kernel_matrix``); the Cholesky factorisation and the
+triangular inverse are torch/cuSOLVER calls -- the step *before* the hot path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+from typing import List, Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from . import _capi as capi
+from .kernels import TermT, kernel_terms
+
+MIN_FIXED_NOISE = 1e-6  # gpytorch raises fixed noise below this (float64) with a warning
+MIN_VARIANCE = 1e-10  # gpytorch.settings.min_variance for float64
+
+
+def _fill_model_desc(desc: capi.PrbModelDesc, terms: Sequence[TermT], n: int, d_k: int) -> None:
+    if len(terms) > capi.PRB_MAX_TERMS:
+        raise NotImplementedError(f"at most {capi.PRB_MAX_TERMS} additive terms are supported")
+    desc.n, desc.d_k, desc.n_terms = n, d_k, len(terms)
+    for t, (scale, additive, factors) in enumerate(terms):
+        if len(factors) > capi.PRB_MAX_FACTORS:
+            raise NotImplementedError(f"at most {capi.PRB_MAX_FACTORS} factors per term are supported")
+        T = desc.terms[t]
+        T.outputscale, T.additive, T.n_factors = float(scale), int(bool(additive)), len(factors)
+        for f, (kind, dims, ls, power) in enumerate(factors):
+            F = T.factors[f]
+            F.kind = capi.PRB_FACTOR_MATERN52 if kind == "matern52" else capi.PRB_FACTOR_CATEGORICAL
+            F.n_dims, F.power = len(dims), int(power)
+            for i, (dd, l) in enumerate(zip(dims, ls)):
+                F.dims[i], F.lengthscale[i] = int(dd), float(l)
+
+
+class GPState:
+    """Device-resident exact-GP caches + the ``prb_model`` handle.  One per (model, BO iteration)."""
+
+    def __init__(self, train_X: Tensor, train_Y: Tensor, terms: Sequence[TermT], noise, mean_const: float):
+        capi.require_cuda(train_X, "train_X")
+        self.lib = capi.load_library()
+        self.device = train_X.device
+        X = train_X.detach().to(torch.float64).contiguous()
+        y = train_Y.detach().to(device=self.device, dtype=torch.float64).reshape(-1).contiguous()
+        n, d_k = X.shape
+        if d_k > capi.PRB_MAX_DIMS:
+            raise NotImplementedError(f"kernel-input dimension {d_k} > {capi.PRB_MAX_DIMS}")
+        self.n, self.d_k = n, d_k
+        self.terms = list(terms)
+        self.mean_const = float(mean_const)
+        self.X_train, self.train_Y = X, y
+        noise = torch.as_tensor(noise, dtype=torch.float64, device=self.device).reshape(-1)
+        self.noise = noise.expand(n).contiguous() if noise.numel() == 1 else noise.contiguous()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            desc = capi.PrbModelDesc()
+            _fill_model_desc(desc, self.terms, n, d_k)
+            desc.X_train = X.data_ptr()
+            K = torch.empty(n, n, dtype=torch.float64, device=self.device)
+            capi.check(self.lib.prb_kernel_matrix(C.byref(desc), X.data_ptr(), n, K.data_ptr(), stream),
+                       "prb_kernel_matrix")
+            K.diagonal().add_(self.noise)
+            L = torch.linalg.cholesky(K)
+            self.Linv = torch.linalg.solve_triangular(
+                L, torch.eye(n, dtype=torch.float64, device=self.device), upper=False).contiguous()
+            self.alpha = torch.cholesky_solve((y - self.mean_const).unsqueeze(-1), L).squeeze(-1).contiguous()
+            desc.Linv, desc.alpha, desc.mean_const = self.Linv.data_ptr(), self.alpha.data_ptr(), self.mean_const
+            handle = C.c_void_p()
+            capi.check(self.lib.prb_model_create(C.byref(handle), C.byref(desc), stream), "prb_model_create")
+        self.handle = handle
+        self._desc = desc
+        self._ws: Optional[Tensor] = None
+        self.chunk_cols = 0
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h is not None and h.value:
+            try:
+                self.lib.prb_model_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    def workspace(self, n_points: int, d_theta: int) -> Tensor:
+        need = int(self.lib.prb_workspace_bytes(self.handle, int(n_points), int(d_theta), int(self.chunk_cols)))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # ---- base acquisition / posterior at explicit kernel-input points -------------------------------------------------
+    def acq_points(self, acq_desc: capi.PrbAcqDesc, xk: Tensor, want_grad: bool = False, want_post: bool = False):
+        capi.require_cuda(xk, "X")
+        xk = xk.detach().to(torch.float64).contiguous()
+        if xk.shape[-1] != self.d_k:
+            raise ValueError(f"expected inputs with {self.d_k} columns, got {xk.shape[-1]}")
+        B = xk.numel() // self.d_k
+        out = torch.empty(B, dtype=torch.float64, device=self.device)
+        mean = torch.empty(B, dtype=torch.float64, device=self.device) if want_post else None
+        var = torch.empty(B, dtype=torch.float64, device=self.device) if want_post else None
+        grad = torch.empty(B, self.d_k, dtype=torch.float64, device=self.device) if want_grad else None
+        ws = self.workspace(B, self.d_k)
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            capi.check(self.lib.prb_acq_points(self.handle, C.byref(acq_desc), xk.data_ptr(), B, out.data_ptr(),
+                                               capi.ptr(mean), capi.ptr(var), capi.ptr(grad), ws.data_ptr(),
+                                               ws.numel(), int(self.chunk_cols), st), "prb_acq_points")
+        return out, mean, var, grad
+
+
+class _ConstantMean:
+    def __init__(self, constant: float = 0.0):
+        self.constant = torch.tensor(float(constant), dtype=torch.float64)
+
+
+class _FixedNoiseLikelihood:
+    def __init__(self, noise: Tensor):
+        self.noise = noise
+
+
+class _Posterior:
+    def __init__(self, mean: Tensor, variance: Tensor):
+        self.mean, self.variance = mean, variance
+
+
+class Model(torch.nn.Module):
+    """Marker base class (``botorch.models.model.Model``)."""
+
+
+class FixedNoiseGP(Model):
+    """``botorch.models.FixedNoiseGP`` surface used by the reference (``experiment_utils.py:267-351``): ``train_inputs``,
+    ``train_targets``, ``covar_module``, ``mean_module.constant``, ``likelihood.noise``, ``posterior(X)``.
+
+    Hyperparameters are set by assignment on ``covar_module`` / ``mean_module`` (fitting the marginal likelihood is the
+    reference's ``fit_gpytorch_model`` step, outside the hot path); call ``refresh()`` after changing them.
+    Model-level input/outcome transforms and multi-output models are not supported (raise)."""
+
+    num_outputs = 1
+
+    def __init__(self, train_X: Tensor, train_Y: Tensor, train_Yvar: Tensor, covar_module=None,
+                 outcome_transform=None, input_transform=None, mean_const: float = 0.0):
+        super().__init__()
+        if outcome_transform is not None or input_transform is not None:
+            raise NotImplementedError("model-level transforms are outside the B200 hot path")
+        if train_Y.ndim == 2 and train_Y.shape[-1] != 1:
+            raise NotImplementedError("multi-output models are outside the B200 hot path")
+        if covar_module is None:
+            raise NotImplementedError("pass the covariance from get_kernel(); botorch_default is not implemented")
+        capi.require_cuda(train_X, "train_X")
+        self.train_inputs = (train_X.detach().to(torch.float64),)
+        self.train_targets = train_Y.detach().to(torch.float64).reshape(-1)
+        noise = train_Yvar.detach().to(torch.float64).reshape(-1)
+        if bool((noise < MIN_FIXED_NOISE).any()):
+            warnings.warn(f"Very small noise values detected; rounding up to {MIN_FIXED_NOISE} (GPyTorch behaviour).")
+            noise = noise.clamp_min(MIN_FIXED_NOISE)
+        self.likelihood = _FixedNoiseLikelihood(noise)
+        self.covar_module = covar_module
+        self.mean_module = _ConstantMean(mean_const)
+        self._state: Optional[GPState] = None
+
+    def refresh(self) -> "FixedNoiseGP":
+        self._state = None
+        return self
+
+    @property
+    def state(self) -> GPState:
+        if self._state is None:
+            X = self.train_inputs[0]
+            self._state = GPState(X, self.train_targets, kernel_terms(self.covar_module, X.shape[-1]),
+                                  self.likelihood.noise, float(self.mean_module.constant))
+        return self._state
+
+    def posterior(self, X: Tensor, observation_noise: bool = False, **kwargs) -> _Posterior:
+        if observation_noise:
+            raise NotImplementedError
+        desc = capi.PrbAcqDesc(kind=capi.PRB_ACQ_MEAN, ei_variant=0, param=0.0, min_variance=MIN_VARIANCE,
+                               acq_var_floor=0.0)
+        _, mean, var, _ = self.state.acq_points(desc, X, want_post=True)
+        shape = X.shape[:-1]
+        return _Posterior(mean.reshape(*shape, 1), var.reshape(*shape, 1))
+
+
+def gp_state_from_model(model) -> GPState:
+    """GP state of one of our models, or of a duck-typed BoTorch ``FixedNoiseGP``/``SingleTaskGP`` in eval mode
+    (``train_inputs[0]``, ``train_targets``, ``mean_module.constant``, ``likelihood.noise``, ``covar_module`` tree)."""
+    if isinstance(model, FixedNoiseGP):
+        return model.state
+    for attr in ("input_transform", "outcome_transform"):
+        if getattr(model, attr, None) is not None:
+            raise NotImplementedError(f"model.{attr} is not supported by the B200 hot path")
+    if hasattr(model, "models"):
+        raise NotImplementedError("ModelListGP is not supported by the B200 hot path")
+    cached = getattr(model, "_prb_state", None)
+    if cached is not None:
+        return cached
+    X = model.train_inputs[0]
+    if X.ndim != 2:
+        raise NotImplementedError("batched models are not supported by the B200 hot path")
+    noise = model.likelihood.noise.detach().reshape(-1)
+    state = GPState(X, model.train_targets, kernel_terms(model.covar_module, X.shape[-1]), noise,
+                    float(torch.as_tensor(model.mean_module.constant).detach().reshape(-1)[0]))
+    try:
+        model._prb_state = state
+    except Exception:
+        pass
+    return state

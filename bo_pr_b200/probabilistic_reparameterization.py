@@ -1,0 +1,351 @@
+"""Probabilistic-reparameterization acquisition wrappers on the B200 path.
+
+Drop-in for ``discrete_mixed_bo/probabilistic_reparameterization.py``: same class names, constructor signatures,
+attributes (``acq_function``, ``model``, ``X_baseline``, ``input_transform``, ``one_hot_to_numeric``, ``ma_counter``,
+``ma_hidden``, ``sample_candidates``) and the same 12-argument ``torch.autograd.Function``.  ``forward`` is one call into
+``libprb200`` (``prb_mc_value_grad`` / ``prb_analytic_value_grad``): sampler -> cross-covariance panel -> FP64 DMMA
+triangular products -> acquisition epilogue -> score-function / pathwise gradient reduction.  There is no torch
+re-implementation of that arithmetic here and no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from abc import ABC, abstractmethod
+from collections import OrderedDict
+from typing import Dict, List, Optional
+
+import torch
+from torch import Tensor
+from torch.autograd import Function
+from torch.nn.functional import one_hot
+
+from . import _capi as capi
+from .acquisition import AcquisitionFunction, acq_desc_of
+from .input import (
+    AnalyticProbabilisticReparameterizationInputTransform,
+    ChainedInputTransform,
+    MCProbabilisticReparameterizationInputTransform,
+    Normalize,
+    OneHotToNumeric,
+    make_space_desc,
+)
+from .models import gp_state_from_model
+from .wrapper import AcquisitionFunctionWrapper
+
+
+def get_probabilistic_reparameterization_input_transform(
+    dim: int,
+    integer_indices: List[int],
+    integer_bounds: Tensor,
+    categorical_features: Optional[Dict[int, int]] = None,
+    use_analytic: bool = False,
+    mc_samples: int = 1024,
+    resample: bool = False,
+    flip: bool = False,
+    tau: float = 0.1,
+    rng: str = "sobol",
+    philox_seed: int = 0,
+) -> ChainedInputTransform:
+    """``probabilistic_reparameterization.py:36-96``: ``{unnormalize -> round -> normalize}`` in ``eval()`` mode; the
+    Normalize pair acts on the integer columns only and is omitted when there are none."""
+    bounds = torch.zeros(2, dim, dtype=integer_bounds.dtype, device=integer_bounds.device)
+    bounds[1] = 1
+    bounds[:, integer_indices] = integer_bounds
+    tfs = OrderedDict()
+    has_ints = integer_indices is not None and len(integer_indices) > 0
+    if has_ints:
+        tfs["unnormalize"] = Normalize(d=dim, bounds=bounds, indices=integer_indices, transform_on_train=False,
+                                       transform_on_eval=True, transform_on_fantasize=False, reverse=True)
+    if use_analytic:
+        tfs["round"] = AnalyticProbabilisticReparameterizationInputTransform(
+            dim=dim, integer_indices=integer_indices, integer_bounds=integer_bounds,
+            categorical_features=categorical_features, tau=tau)
+    else:
+        tfs["round"] = MCProbabilisticReparameterizationInputTransform(
+            integer_indices=integer_indices, integer_bounds=integer_bounds, categorical_features=categorical_features,
+            resample=resample, mc_samples=mc_samples, flip=flip, tau=tau, rng=rng, philox_seed=philox_seed)
+    if has_ints:
+        tfs["normalize"] = Normalize(d=dim, bounds=bounds, indices=integer_indices, transform_on_train=False,
+                                     transform_on_eval=True, transform_on_fantasize=False, reverse=False)
+    tf = ChainedInputTransform(**tfs)
+    tf.eval()
+    return tf
+
+
+class AbstractProbabilisticReparameterization(AcquisitionFunctionWrapper, ABC):
+    """``probabilistic_reparameterization.py:99-238``."""
+
+    def __init__(
+        self,
+        acq_function: AcquisitionFunction,
+        dim: int,
+        integer_indices: Optional[List[int]] = None,
+        integer_bounds: Optional[Tensor] = None,
+        categorical_features: Optional[Dict[int, int]] = None,
+        batch_limit: Optional[int] = None,
+        apply_numeric: bool = False,
+        **kwargs,
+    ) -> None:
+        if categorical_features is None and (integer_indices is None or integer_bounds is None):
+            raise NotImplementedError("categorical_features or integer indices and integer_bounds must be provided.")
+        super().__init__(acq_function=acq_function)
+        self.batch_limit = batch_limit  # accepted for API parity; the fused path never materialises b x mc x n
+        self.dim = dim
+        self.apply_numeric = bool(apply_numeric)
+        if integer_bounds is None:
+            raise NotImplementedError("integer_bounds must be a tensor (pass a [2, 0] tensor when there are no "
+                                      "integers; the reference dereferences integer_bounds.device too)")
+        device = integer_bounds.device
+        if apply_numeric:
+            self.one_hot_to_numeric = OneHotToNumeric(categorical_features=categorical_features,
+                                                      transform_on_train=False, transform_on_eval=True,
+                                                      transform_on_fantasize=False)
+            self.one_hot_to_numeric.eval()
+        else:
+            self.one_hot_to_numeric = None
+        discrete_indices: List[int] = []
+        ints = list(integer_indices) if integer_indices is not None else []
+        self.register_buffer("integer_indices", torch.tensor(ints, dtype=torch.long, device=device))
+        self.register_buffer("integer_bounds", integer_bounds if integer_indices is not None
+                             else torch.tensor([], dtype=integer_bounds.dtype, device=device))
+        discrete_indices.extend(ints)
+        if categorical_features is not None and len(categorical_features) > 0:
+            categorical_indices = list(range(min(categorical_features.keys()), dim))
+            discrete_indices.extend(categorical_indices)
+            self.categorical_features = categorical_features
+        else:
+            categorical_indices = []
+            self.categorical_features = None
+        self.register_buffer("categorical_indices", torch.tensor(categorical_indices, dtype=torch.long, device=device))
+        self.register_buffer("cont_indices", torch.tensor(sorted(set(range(dim)) - set(discrete_indices)),
+                                                          dtype=torch.long, device=device))
+        # moving-average baseline state: (ma_counter, ma_hidden) live in ONE device buffer so the library can read the
+        # pre-call state and advance it in place without a host round trip (:185-196, :499-505)
+        self.register_buffer("_ma_state", torch.zeros(2, dtype=torch.double, device=device))
+        self.register_buffer("ma_baseline", torch.zeros(1, dtype=torch.double, device=device))
+        self._tau = kwargs.get("tau", 0.1)
+
+    @property
+    def ma_counter(self) -> Tensor:
+        return self._ma_state[0:1]
+
+    @property
+    def ma_hidden(self) -> Tensor:
+        return self._ma_state[1:2]
+
+    def _space(self) -> capi.PrbSpaceDesc:
+        return make_space_desc(self.dim, self.integer_indices.tolist(),
+                               self.integer_bounds if self.integer_indices.numel() > 0 else None,
+                               self.categorical_features, self.input_transform["round"].tau,
+                               apply_numeric=self.apply_numeric)
+
+    def sample_candidates(self, X: Tensor) -> Tensor:
+        """``:198-233``: one discrete draw per restart from p(theta*), torch's global generator (once per BO iteration)."""
+        if "unnormalize" in self.input_transform:
+            unnormalized_X = self.input_transform["unnormalize"](X)
+        else:
+            unnormalized_X = X.clone()
+        prob = self.input_transform["round"].get_rounding_prob(X=unnormalized_X)
+        discrete_idx = 0
+        for i in self.integer_indices:
+            p = prob[..., discrete_idx]
+            rounding_component = torch.distributions.Bernoulli(probs=p).sample()
+            unnormalized_X[..., i] = unnormalized_X[..., i].floor() + rounding_component
+            discrete_idx += 1
+        if self.integer_indices.numel() > 0:
+            unnormalized_X[..., self.integer_indices] = torch.minimum(
+                torch.maximum(unnormalized_X[..., self.integer_indices], self.integer_bounds[0]),
+                self.integer_bounds[1])
+        raw_idx = self.cont_indices.shape[0] + discrete_idx
+        if self.categorical_indices.shape[0] > 0:
+            for i, cardinality in self.categorical_features.items():
+                discrete_end = discrete_idx + cardinality
+                p = prob[..., discrete_idx:discrete_end]
+                z = one_hot(torch.distributions.Categorical(probs=p).sample(), num_classes=cardinality)
+                raw_end = raw_idx + cardinality
+                unnormalized_X[..., raw_idx:raw_end] = z.to(unnormalized_X)
+                discrete_idx = discrete_end
+                raw_idx = raw_end
+        if "normalize" in self.input_transform:
+            return self.input_transform["normalize"](unnormalized_X)
+        return unnormalized_X
+
+    @abstractmethod
+    def forward(self, X: Tensor) -> Tensor:
+        """Compute PR."""
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def _check_X(X: Tensor, dim: int):
+    capi.require_cuda(X, "X")
+    if X.ndim != 3 or X.shape[-2] != 1:
+        raise NotImplementedError(f"expected X of shape b x q=1 x d, got {tuple(X.shape)} (q > 1 is not supported)")
+    if X.shape[-1] != dim:
+        raise ValueError(f"expected {dim} columns, got {X.shape[-1]}")
+
+
+class _AnalyticPRFunction(Function):
+    @staticmethod
+    def forward(ctx, X: Tensor, module: "AnalyticProbabilisticReparameterization"):
+        state = gp_state_from_model(module.acq_function.model)
+        lib = state.lib
+        b, d = X.shape[0], X.shape[-1]
+        rnd = module.input_transform["round"]
+        codes = rnd.option_codes
+        n_opt = codes.shape[0]
+        theta = X.detach().to(torch.float64).reshape(b, d).contiguous()
+        need = ctx.needs_input_grad[0]
+        value = torch.empty(b, dtype=torch.float64, device=X.device)
+        grad = torch.empty(b, d, dtype=torch.float64, device=X.device) if need else None
+        ones = torch.ones(b, dtype=torch.float64, device=X.device) if need else None
+        ws = state.workspace(b * n_opt, d)
+        sp, aq = module._space(), acq_desc_of(module.acq_function)
+        with torch.cuda.device(X.device):
+            st = torch.cuda.current_stream().cuda_stream
+            capi.check(lib.prb_analytic_value_grad(state.handle, C.byref(sp), C.byref(aq), theta.data_ptr(), b,
+                                                   codes.data_ptr(), n_opt, capi.ptr(ones), value.data_ptr(),
+                                                   capi.ptr(grad), None, None, ws.data_ptr(), ws.numel(),
+                                                   int(state.chunk_cols), st), "prb_analytic_value_grad")
+        ctx.unit_grad = grad
+        return value
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        if ctx.unit_grad is None:
+            return None, None
+        return (ctx.unit_grad * grad_output.unsqueeze(-1)).unsqueeze(-2), None
+
+
+class AnalyticProbabilisticReparameterization(AbstractProbabilisticReparameterization):
+    """``probabilistic_reparameterization.py:241-320``: sum over all discrete configurations weighted by P(z | theta)."""
+
+    def __init__(
+        self,
+        acq_function: AcquisitionFunction,
+        dim: int,
+        dtype: torch.dtype,
+        device: torch.device,
+        integer_indices: Optional[List[int]] = None,
+        integer_bounds: Optional[Tensor] = None,
+        categorical_features: Optional[Dict[int, int]] = None,
+        batch_limit: Optional[int] = None,
+        apply_numeric: bool = False,
+        tau: float = 0.1,
+    ) -> None:
+        super().__init__(acq_function=acq_function, dim=dim, integer_indices=integer_indices,
+                         integer_bounds=integer_bounds, categorical_features=categorical_features,
+                         batch_limit=batch_limit, apply_numeric=apply_numeric)
+        if dtype != torch.float64:
+            raise NotImplementedError("libprb200 computes in float64 only (the reference runs in float64)")
+        self.input_transform = get_probabilistic_reparameterization_input_transform(
+            dim=dim, use_analytic=True, integer_indices=integer_indices if integer_indices is not None else [],
+            integer_bounds=integer_bounds, categorical_features=categorical_features, tau=tau)
+        self.input_transform.to(device=device)
+        if self.batch_limit is None:
+            self.batch_limit = self.input_transform["round"].all_discrete_options.shape[0]
+
+    def forward(self, X: Tensor) -> Tensor:
+        _check_X(X, self.dim)
+        return _AnalyticPRFunction.apply(X, self)
+
+
+class MCProbabilisticReparameterization(AbstractProbabilisticReparameterization):
+    """``probabilistic_reparameterization.py:323-396``.  Extra keyword ``rng``: ``"sobol"`` (reference behaviour: cached
+    scrambled-Sobol base samples) or ``"philox"`` (device-generated counter-based stream, ``philox_seed``)."""
+
+    def __init__(
+        self,
+        acq_function: AcquisitionFunction,
+        dim: int,
+        integer_indices: Optional[List[int]] = None,
+        integer_bounds: Optional[Tensor] = None,
+        categorical_features: Optional[Dict[int, int]] = None,
+        batch_limit: Optional[int] = None,
+        apply_numeric: bool = False,
+        mc_samples: int = 1024,
+        grad_estimator: str = "reinforce",
+        tau: float = 0.1,
+        rng: str = "sobol",
+        philox_seed: int = 0,
+    ) -> None:
+        super().__init__(acq_function=acq_function, dim=dim, integer_indices=integer_indices,
+                         integer_bounds=integer_bounds, categorical_features=categorical_features,
+                         batch_limit=batch_limit, apply_numeric=apply_numeric)
+        if self.batch_limit is None:
+            self.batch_limit = mc_samples
+        if grad_estimator in ("arm", "u2g"):
+            # the reference raises NameError here (undefined get_mc_probabilistic_reparameterization_input_transform,
+            # :362-372); those estimators are dead code
+            raise NotImplementedError(f"grad_estimator={grad_estimator!r} is dead code in the reference")
+        if grad_estimator not in ("reinforce", "reinforce_ma"):
+            raise ValueError(f"unknown grad_estimator {grad_estimator!r}")
+        self.grad_estimator = grad_estimator
+        self.mc_samples = mc_samples
+        self._pr_acq_function = _MCProbabilisticReparameterization()
+        self.input_transform = get_probabilistic_reparameterization_input_transform(
+            dim=dim, integer_indices=integer_indices if integer_indices is not None else [],
+            integer_bounds=integer_bounds, categorical_features=categorical_features, mc_samples=mc_samples, tau=tau,
+            rng=rng, philox_seed=philox_seed)
+        self.input_transform_flip = None
+
+    def forward(self, X: Tensor) -> Tensor:
+        return self._pr_acq_function.apply(
+            X, self.acq_function, self.input_transform, self.input_transform_flip, self.batch_limit,
+            self.integer_indices, self.cont_indices, self.categorical_indices, self.grad_estimator,
+            self.one_hot_to_numeric, self.ma_counter, self.ma_hidden,
+        )
+
+
+class _MCProbabilisticReparameterization(Function):
+    """Same call signature as the reference's Function (``probabilistic_reparameterization.py:399-648``).
+
+    ``ma_counter`` / ``ma_hidden`` must be the two adjacent one-element views of a single contiguous double[2] buffer
+    (that is how ``AbstractProbabilisticReparameterization`` stores them): the library reads the pre-call state for the
+    baseline and advances it in place."""
+
+    @staticmethod
+    def forward(ctx, input: Tensor, acq_function, input_tf, input_tf_flip, batch_limit, integer_indices, cont_indices,
+                categorical_indices, grad_estimator, one_hot_to_numeric, ma_counter, ma_hidden):
+        X = input
+        rnd = input_tf["round"]
+        d = X.shape[-1]
+        _check_X(X, d)
+        if grad_estimator not in ("reinforce", "reinforce_ma"):
+            raise NotImplementedError(grad_estimator)
+        if ma_hidden.data_ptr() != ma_counter.data_ptr() + 8:
+            raise ValueError("ma_counter and ma_hidden must be adjacent views of one double[2] device buffer")
+        state = gp_state_from_model(acq_function.model)
+        lib = state.lib
+        b = X.shape[0]
+        theta = X.detach().to(torch.float64).reshape(b, d).contiguous()
+        rnd.ensure_base_samples(1, X.device)
+        u_int, u_cat = rnd.base_sample_ptrs()
+        mc = rnd.mc_samples
+        ints = integer_indices.tolist()
+        ib = rnd.integer_bounds if len(ints) > 0 else None
+        sp = make_space_desc(d, ints, ib, rnd.categorical_features, rnd.tau,
+                             apply_numeric=one_hot_to_numeric is not None)
+        aq = acq_desc_of(acq_function)
+        need = ctx.needs_input_grad[0]
+        value = torch.empty(b, dtype=torch.float64, device=X.device)
+        grad = torch.empty(b, d, dtype=torch.float64, device=X.device) if need else None
+        ones = torch.ones(b, dtype=torch.float64, device=X.device) if need else None
+        ws = state.workspace(b * mc, d)
+        est = capi.PRB_EST_REINFORCE_MA if grad_estimator == "reinforce_ma" else capi.PRB_EST_REINFORCE
+        with torch.cuda.device(X.device):
+            st = torch.cuda.current_stream().cuda_stream
+            capi.check(lib.prb_mc_value_grad(state.handle, C.byref(sp), C.byref(aq), theta.data_ptr(), b, mc,
+                                             capi.ptr(u_int), capi.ptr(u_cat), 0, 0, est, ma_counter.data_ptr(), 1,
+                                             capi.ptr(ones), value.data_ptr(), capi.ptr(grad), None, ws.data_ptr(),
+                                             ws.numel(), int(state.chunk_cols), st), "prb_mc_value_grad")
+        ctx.unit_grad = grad
+        return value
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        none11 = (None,) * 11
+        if ctx.unit_grad is None:
+            return (None,) + none11
+        # the library evaluated the estimator for grad_output = 1; it is linear in grad_output (:613-633)
+        g = (ctx.unit_grad * grad_output.unsqueeze(-1)).unsqueeze(-2)
+        return (g,) + none11

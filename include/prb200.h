@@ -1,0 +1,206 @@
+/*
+ * prb200.h -- C ABI of the B200-native probabilistic-reparameterization (PR) acquisition hot path.
+ *
+ * The reference (facebookresearch/bo_pr) is pure Python on BoTorch/GPyTorch; it has no FFI.  The boundary this
+ * library sits behind is BoTorch's object protocol.  Each entry point below names the
+ * reference interface it replaces (paths relative to /root/reference/discrete_mixed_bo).  INTEGRATION.md shows
+ * the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every function returns 0 (PRB_OK) or a negative prb_status; nothing throws across the ABI
+ *  - all tensor pointers are CALLER-OWNED DEVICE memory, contiguous, float64 unless stated, on the current device
+ *  - the hot entry points never allocate and never synchronise; work is enqueued on `stream` (a cudaStream_t
+ *    passed as void*; NULL = legacy default stream); scratch comes from a caller-provided workspace whose size
+ *    prb_workspace_bytes() reports
+ *  - a prb_model is bound to the device that was current at creation; it is not thread-safe
+ *  - there is NO CPU implementation behind this ABI
+ */
+#ifndef PRB200_H_
+#define PRB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRB_VERSION 100
+
+#define PRB_MAX_DIMS 32     /* kernel-input columns / theta columns */
+#define PRB_MAX_FACTORS 4   /* multiplicative (or additive) factors per term */
+#define PRB_MAX_TERMS 2     /* additive ScaleKernel terms */
+#define PRB_MAX_CAT 8       /* categorical parameters */
+#define PRB_MAX_CARD 32     /* categories per categorical parameter */
+
+typedef enum {
+  PRB_OK = 0,
+  PRB_ERR_INVALID = -1,      /* bad argument (NULL pointer, negative size, unsupported combination) */
+  PRB_ERR_UNSUPPORTED = -2,  /* exceeds a compile-time limit above */
+  PRB_ERR_WORKSPACE = -3,    /* workspace too small */
+  PRB_ERR_CUDA = -4,         /* a CUDA runtime call failed; see prb_last_cuda_error() */
+  PRB_ERR_NO_DEVICE = -5     /* no sm_100 device / wrong device */
+} prb_status;
+
+/* ---- kernel structure: what get_kernel() builds (kernels.py:18-101) -------------------------------------------
+ * K(x, x') = sum_t outputscale_t * combine_f( factor_f(x, x') ^ power_f ),  combine = product, or sum if additive.
+ * factor kinds: gpytorch MaternKernel(nu=2.5) over `dims` with one lengthscale per dim (isotropic = repeated),
+ *               botorch CategoricalKernel: exp(-mean_j( [x_j != x'_j] / lengthscale_j )).                          */
+typedef enum { PRB_FACTOR_MATERN52 = 0, PRB_FACTOR_CATEGORICAL = 1 } prb_factor_kind;
+
+typedef struct {
+  int32_t kind;  /* prb_factor_kind */
+  int32_t n_dims;
+  int32_t power; /* 1, or 2 for the mixed_categorical double-multiply (kernels.py:90-94) */
+  int32_t reserved;
+  int32_t dims[PRB_MAX_DIMS];
+  double lengthscale[PRB_MAX_DIMS];
+} prb_factor;
+
+typedef struct {
+  double outputscale;
+  int32_t additive;
+  int32_t n_factors;
+  prb_factor factors[PRB_MAX_FACTORS];
+} prb_term;
+
+/* ---- GP state: the caches GPyTorch's exact prediction strategy holds ----------------------- */
+typedef struct {
+  int32_t n;             /* training points */
+  int32_t d_k;           /* kernel-input dimension (numeric layout if the model sees OneHotToNumeric inputs) */
+  const double* X_train; /* [n, d_k] row-major */
+  const double* Linv;    /* [n, n] row-major, lower triangle of inv(chol(K + diag(noise))); upper part ignored */
+  const double* alpha;   /* [n] (K + diag(noise))^-1 (y - mean_const) */
+  double mean_const;     /* ConstantMean */
+  int32_t n_terms;
+  int32_t reserved;
+  prb_term terms[PRB_MAX_TERMS];
+} prb_model_desc;
+
+typedef struct prb_model prb_model;
+
+/* ---- mixed search space: constructor arguments of the PR wrappers (probabilistic_reparameterization.py:102-112) */
+typedef struct {
+  int32_t d;      /* theta columns: [continuous..., integers..., one-hot blocks...] (problems/base.py:64-78) */
+  int32_t n_int;
+  int32_t n_cat;
+  int32_t apply_numeric; /* 1: base AF sees OneHotToNumeric(tilde_x) (input.py:69-88) */
+  int32_t int_cols[PRB_MAX_DIMS];
+  double int_lo[PRB_MAX_DIMS]; /* integer_bounds[0] */
+  double int_hi[PRB_MAX_DIMS]; /* integer_bounds[1] */
+  int32_t cat_start[PRB_MAX_CAT]; /* first one-hot column of each categorical */
+  int32_t cat_card[PRB_MAX_CAT];
+  double tau;
+  int32_t raw_integer_space; /* 1: theta's integer columns are already UN-normalised and outputs stay so (the bare
+                                "round" member of the transform chain, input.py:637-746, without the Normalize pair) */
+  int32_t reserved;
+} prb_space_desc;
+
+/* ---- base acquisition function (botorch analytic AFs; experiment_utils.py:391-393, 476-480, 489-492) ----------- */
+typedef enum { PRB_ACQ_EI = 0, PRB_ACQ_UCB = 1, PRB_ACQ_MEAN = 2 } prb_acq_kind;
+
+typedef struct {
+  int32_t kind;          /* prb_acq_kind */
+  int32_t ei_variant;    /* 0: sigma*(exp(logpdf(u)) + u*0.5*(1+erf(u/sqrt2))) (BoTorch <= 0.8); 1: erfc form */
+  double param;          /* EI: best_f ; UCB: beta */
+  double min_variance;   /* gpytorch posterior variance floor (1e-10 in float64) */
+  double acq_var_floor;  /* EI: clamp_min on the variance before sqrt (1e-9 in BoTorch <= 0.8); others: 0 */
+} prb_acq_desc;
+
+typedef enum { PRB_EST_REINFORCE = 0, PRB_EST_REINFORCE_MA = 1 } prb_estimator;
+
+/* ---- library ---------------------------------------------------------------------------------------------------- */
+int prb_version(void);
+const char* prb_status_string(int status);
+const char* prb_last_cuda_error(void);
+
+/* Builds the device-side GP state (padded copies of Linv / Linv^T with alpha appended).  Allocates; call once per
+ * BO iteration.  Replaces: the caches behind model.posterior() that acq_function(X) reads
+ * (probabilistic_reparameterization.py:314, 491; [3P] gpytorch exact prediction strategy).                       */
+int prb_model_create(prb_model** out, const prb_model_desc* desc, void* stream);
+int prb_model_destroy(prb_model* model);
+int prb_model_n(const prb_model* model);
+int prb_model_dk(const prb_model* model);
+
+/* Bytes of scratch needed to evaluate `n_points` (= b*mc, or b*n_discrete) base-AF points with this model.
+ * `chunk_cols` = 0 picks the default L2-resident panel width.                                                      */
+size_t prb_workspace_bytes(const prb_model* model, int64_t n_points, int32_t d_theta, int32_t chunk_cols);
+
+/* Counter-based Philox4x32-10 uniforms in [0,1): out[i, c] for i < mc, c < n_cols, 53-bit mantissa,
+ * counter = (i, c, offset_lo, offset_hi), key = (seed_lo, seed_hi).  The fused sampler draws the same stream
+ * on the fly.  Replaces: draw_sobol_samples(...) base samples (input.py:655-673, 696-713).                         */
+int prb_philox_uniform(uint64_t seed, uint64_t offset, int32_t mc, int32_t n_cols, double* out, void* stream);
+
+/* PR sampler, materialised (parity / debugging entry).  theta [b, d] normalised.  u_int [mc, n_int], u_cat [mc, n_cat]
+ * shared by all b (NULL => Philox(seed, offset); integer columns use stream columns 0..n_int-1, categoricals
+ * n_int..n_int+n_cat-1).
+ * out_tilde_x [b, mc, d]   sampled configurations, normalised, one-hot layout       (input.py:637-746 + Normalize)
+ * out_z       [b, mc, n_disc] uint8 rounding components used by the estimator        (probabilistic_reparameterization.py:454-465)
+ * out_prob    [b, n_disc]  rounding probabilities                                    (input.py:613-635)
+ * any output may be NULL.                                                                                            */
+int prb_pr_sample(const prb_space_desc* space, const double* theta, int32_t b, int32_t mc, const double* u_int,
+                  const double* u_cat, uint64_t seed, uint64_t offset, double* out_tilde_x, uint8_t* out_z,
+                  double* out_prob, void* stream);
+
+/* Analytic-PR enumeration, materialised: x_all [b, n_options, d_k'] = every discrete configuration pasted next to the
+ * continuous columns (normalised; one-hot layout when space->apply_numeric == 0, numeric layout otherwise) and
+ * probs [b, n_options] = P(z | theta).  Replaces: AnalyticProbabilisticReparameterizationInputTransform.transform /
+ * .get_probs (input.py:410-488).  Either output may be NULL.                                                         */
+int prb_analytic_enumerate(const prb_space_desc* space, const double* theta, int32_t b, const int32_t* options,
+                           int32_t n_options, double* out_x_all, double* out_probs, void* stream);
+
+/* Raw cross-covariance K(xk, X_train) -> out [n_points, n] row-major, using only desc->{n, d_k, X_train, terms}.
+ * Replaces: covar_module(X1, X2) ([3P] gpytorch kernels built by get_kernel, kernels.py:18-101); used by the GP-state
+ * builder for K(X_train, X_train).                                                                                  */
+int prb_kernel_matrix(const prb_model_desc* desc, const double* xk, int64_t n_points, double* out, void* stream);
+
+/* Base acquisition function at explicit kernel-input points xk [n_points, d_k].
+ * Replaces: acq_function(X) for ExpectedImprovement / UpperConfidenceBound / PosteriorMean on a FixedNoiseGP
+ * (run_one_replication.py:513-528 re-scoring; initializers.py:186 screening of non-PR AFs).
+ * out_acq / out_mean / out_var [n_points] (NULL to skip); out_dacq_dx [n_points, d_k] or NULL: gradient of the AF
+ * value w.r.t. every kernel-input column (columns that only feed a categorical factor get 0).                       */
+int prb_acq_points(prb_model* model, const prb_acq_desc* acq, const double* xk, int64_t n_points, double* out_acq,
+                   double* out_mean, double* out_var, double* out_dacq_dx, void* workspace, size_t workspace_bytes,
+                   int32_t chunk_cols, void* stream);
+
+/* MC probabilistic reparameterization, value (+ gradient).
+ * Replaces: _MCProbabilisticReparameterization.forward/backward (probabilistic_reparameterization.py:402-648).
+ * theta [b, d]; u_int/u_cat as in prb_pr_sample.
+ * ma_state: device double[2] = (ma_counter, ma_hidden), the EMA-baseline buffers of the wrapper (:185-196).
+ *           The baseline uses the PRE-call state (:600-609); if update_ma != 0 the state is advanced in place
+ *           exactly as :499-505 does (counter += 1; hidden -= 0.3 (hidden - mean(all acq values))).
+ *           May be NULL for PRB_EST_REINFORCE with update_ma == 0.
+ * grad_out [b] upstream gradient, or NULL for a value-only call (skips the second triangular product).
+ * out_value [b]; out_grad [b, d] (required iff grad_out != NULL); out_acq_values [b, mc] or NULL.                   */
+int prb_mc_value_grad(prb_model* model, const prb_space_desc* space, const prb_acq_desc* acq, const double* theta,
+                      int32_t b, int32_t mc, const double* u_int, const double* u_cat, uint64_t seed,
+                      uint64_t offset, int32_t estimator, double* ma_state, int32_t update_ma,
+                      const double* grad_out, double* out_value, double* out_grad, double* out_acq_values,
+                      void* workspace, size_t workspace_bytes, int32_t chunk_cols, void* stream);
+
+/* Analytic probabilistic reparameterization: sum over all discrete configurations.
+ * Replaces: AnalyticProbabilisticReparameterization.forward + autograd (probabilistic_reparameterization.py:285-320,
+ * input.py:410-488).  options [n_options, n_int + n_cat] int32: un-normalised integer value per integer parameter,
+ * category index per categorical (the rows of all_discrete_options, input.py:345-383).
+ * out_value [b]; out_grad [b, d] if grad_out != NULL; out_probs [b, n_options] or NULL.                             */
+int prb_analytic_value_grad(prb_model* model, const prb_space_desc* space, const prb_acq_desc* acq,
+                            const double* theta, int32_t b, const int32_t* options, int32_t n_options,
+                            const double* grad_out, double* out_value, double* out_grad, double* out_probs,
+                            double* out_acq_values, void* workspace, size_t workspace_bytes, int32_t chunk_cols,
+                            void* stream);
+
+/* Multi-start Adam on the MC-PR objective, entirely on device.
+ * Replaces: gen_candidates_torch (gen.py:264-343) for a PR acquisition function: clamp -> value+grad -> Adam(lr,
+ * betas (0.9, 0.999), eps 1e-8) repeated `maxiter` times, final clamp and value-only evaluation.
+ * theta [b, d] in/out; lower/upper [d]; adam_state: device double[2*b*d] zero-initialised by the caller (exp_avg,
+ * exp_avg_sq); `step0` = number of Adam steps already taken (bias correction).  out_value [b] final values.          */
+int prb_mc_adam(prb_model* model, const prb_space_desc* space, const prb_acq_desc* acq, double* theta, int32_t b,
+                int32_t mc, const double* u_int, const double* u_cat, uint64_t seed, uint64_t offset,
+                int32_t estimator, double* ma_state, const double* lower, const double* upper, double lr,
+                int32_t maxiter, int32_t step0, double* adam_state, double* out_value, void* workspace,
+                size_t workspace_bytes, int32_t chunk_cols, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRB200_H_ */
