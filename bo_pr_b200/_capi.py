@@ -20,11 +20,14 @@ PRB_FACTOR_MATERN52 = 0
 PRB_FACTOR_CATEGORICAL = 1
 PRB_ACQ_EI, PRB_ACQ_UCB, PRB_ACQ_MEAN = 0, 1, 2
 PRB_EST_REINFORCE, PRB_EST_REINFORCE_MA = 0, 1
+PRB_PROFILE_SLOTS = 12
+PROFILE_SLOT_NAMES = ["pr_sample", "kstar_panel", "trgemm_lower", "acq_epilogue", "trgemm_upper", "grad_contract",
+                      "sum_splits", "mc_reduce", "ma_update", "analytic", "adam", "other"]
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libprb200.so")
 
 EXPORTS = [
-    "prb_version", "prb_status_string", "prb_last_cuda_error", "prb_model_create", "prb_model_destroy",
+    "prb_version", "prb_abi_sizeof", "prb_launch_count", "prb_profile_enable", "prb_profile_read", "prb_status_string", "prb_last_cuda_error", "prb_model_create", "prb_model_destroy",
     "prb_model_n", "prb_model_dk", "prb_workspace_bytes", "prb_philox_uniform", "prb_pr_sample",
     "prb_analytic_enumerate", "prb_kernel_matrix", "prb_acq_points",
     "prb_mc_value_grad", "prb_analytic_value_grad", "prb_mc_adam",
@@ -79,6 +82,11 @@ def load_library() -> C.CDLL:
     lib = C.CDLL(LIB_PATH)
     vp, i32, i64, u64, dbl, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double, C.c_size_t
     lib.prb_version.restype = C.c_int
+    lib.prb_launch_count.restype = C.c_uint64
+    lib.prb_launch_count.argtypes = []
+    lib.prb_abi_sizeof.argtypes = [C.c_int]
+    lib.prb_profile_enable.argtypes = [C.c_int]
+    lib.prb_profile_read.argtypes = [vp, vp, i32]
     lib.prb_status_string.restype = C.c_char_p
     lib.prb_status_string.argtypes = [C.c_int]
     lib.prb_last_cuda_error.restype = C.c_char_p

@@ -9,6 +9,30 @@
 
 using namespace prb;
 
+#include <vector>
+
+namespace prb {
+unsigned long long g_launches = 0;
+
+static bool g_prof_on = false;
+struct ProfRec { int id; cudaEvent_t beg, end; };
+static std::vector<ProfRec> g_prof;
+
+ProfScope::ProfScope(int id, cudaStream_t st) : id_(id), st_(st), beg_(nullptr), end_(nullptr), on_(g_prof_on) {
+  if (!on_) return;
+  if (cudaEventCreate(&beg_) != cudaSuccess || cudaEventCreate(&end_) != cudaSuccess) {
+    on_ = false;
+    return;
+  }
+  cudaEventRecord(beg_, st_);
+}
+ProfScope::~ProfScope() {
+  if (!on_) return;
+  cudaEventRecord(end_, st_);
+  g_prof.push_back({id_, beg_, end_});
+}
+}  // namespace prb
+
 namespace {
 
 thread_local char g_cuda_err[256] = "";
@@ -252,6 +276,49 @@ extern "C" {
 
 int prb_version(void) { return PRB_VERSION; }
 
+uint64_t prb_launch_count(void) { return g_launches; }
+
+int prb_abi_sizeof(int which) {
+  switch (which) {
+    case 0: return int(sizeof(prb_factor));
+    case 1: return int(sizeof(prb_term));
+    case 2: return int(sizeof(prb_model_desc));
+    case 3: return int(sizeof(prb_space_desc));
+    case 4: return int(sizeof(prb_acq_desc));
+    default: return PRB_ERR_INVALID;
+  }
+}
+
+int prb_profile_enable(int on) {
+  g_prof_on = on != 0;
+  return PRB_OK;
+}
+
+int prb_profile_read(double* ms_by_kernel, uint64_t* launches_by_kernel, int32_t n_slots) {
+  if (n_slots < PRB_PROFILE_SLOTS) return PRB_ERR_INVALID;
+  for (int i = 0; i < n_slots; ++i) {
+    if (ms_by_kernel) ms_by_kernel[i] = 0.0;
+    if (launches_by_kernel) launches_by_kernel[i] = 0;
+  }
+  cudaError_t first = cudaSuccess;
+  for (const auto& r : g_prof) {
+    cudaError_t e = cudaEventSynchronize(r.end);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.beg, r.end);
+    if (e == cudaSuccess) {
+      if (ms_by_kernel) ms_by_kernel[r.id] += double(ms);
+      if (launches_by_kernel) launches_by_kernel[r.id] += 1;
+    } else if (first == cudaSuccess) {
+      first = e;
+    }
+    cudaEventDestroy(r.beg);
+    cudaEventDestroy(r.end);
+  }
+  g_prof.clear();
+  if (first != cudaSuccess) return cuda_fail(first, "prb_profile_read");
+  return PRB_OK;
+}
+
 const char* prb_status_string(int status) {
   switch (status) {
     case PRB_OK: return "ok";
@@ -310,6 +377,7 @@ int prb_model_create(prb_model** out, const prb_model_desc* desc, void* stream) 
     dim3 grid((m->Kp + 127) / 128, m->Mp1 > m->Mp2 ? m->Mp1 : m->Mp2);
     pack_state_kernel<<<grid, 128, 0, st>>>(desc->Linv, desc->alpha, m->n, m->Kp, m->Mp1, m->Mp2, m->A1, m->A2);
     e = cudaGetLastError();
+    count_launch();
   }
   if (e == cudaSuccess) e = gemm_init();
   if (e != cudaSuccess) {
@@ -505,12 +573,15 @@ int prb_mc_adam(prb_model* model, const prb_space_desc* space, const prb_acq_des
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      const unsigned long long l0 = g_launches;
       int r = one_iter();
+      const unsigned long long per_iter = g_launches - l0;
       cudaError_t e = cudaStreamEndCapture(st, &graph);
       if (r == PRB_OK && e == cudaSuccess && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
         cudaError_t le = cudaSuccess;
         for (int it = 0; it < maxiter && le == cudaSuccess; ++it) le = cudaGraphLaunch(exec, st);
         graphed = (le == cudaSuccess);
+        if (graphed) g_launches += per_iter * (unsigned long long)(maxiter - 1);  // replays of the captured step
         // exec/graph must outlive the enqueued launches: release after the stream drains
         cudaStreamSynchronize(st);
         cudaGraphExecDestroy(exec);

@@ -205,6 +205,7 @@ cudaError_t gemm_init() {
 
 cudaError_t launch_trgemm_lower(const Model& m, const double* KstarT, int ncols_pad, double* VT, double* norm_part,
                                 double* mu_dot, cudaStream_t st) {
+  ProfScope prof_(K_TRGEMM_LOWER, st);
   TrGemmParams p;
   p.A = m.A1;
   p.Bt = KstarT;
@@ -221,10 +222,12 @@ cudaError_t launch_trgemm_lower(const Model& m, const double* KstarT, int ncols_
   p.special_row = m.n;
   p.ncols_pad = ncols_pad;
   trgemm_dmma_kernel<<<p.mtiles * p.ntiles, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(p);
+  count_launch();
   return cudaGetLastError();
 }
 
 cudaError_t launch_trgemm_upper(const Model& m, const double* VT, int ncols_pad, double* W, cudaStream_t st) {
+  ProfScope prof_(K_TRGEMM_UPPER, st);
   TrGemmParams p;
   p.A = m.A2;
   p.Bt = VT;
@@ -241,6 +244,7 @@ cudaError_t launch_trgemm_upper(const Model& m, const double* VT, int ncols_pad,
   p.special_row = -1;
   p.ncols_pad = ncols_pad;
   trgemm_dmma_kernel<<<p.mtiles * p.ntiles, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(p);
+  count_launch();
   return cudaGetLastError();
 }
 

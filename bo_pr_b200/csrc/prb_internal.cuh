@@ -58,6 +58,24 @@ constexpr size_t GEMM_SMEM_BYTES = size_t(GEMM_STAGES) * 2 * GEMM_BM * GEMM_LDS 
 
 constexpr int GRAD_JSPLIT_ROWS = 128;  // rows of W handled by one CTA of the gradient contraction
 
+// number of kernels this library has launched (prb_launch_count(); bench.py reports it as gpu_launches)
+extern unsigned long long g_launches;
+inline void count_launch(int k = 1) { g_launches += (unsigned long long)k; }
+
+// ---- optional per-kernel timing (prb_profile_enable / prb_profile_read): CUDA events around every launch ---------------
+enum KernelId {
+  K_SAMPLE = 0, K_KSTAR, K_TRGEMM_LOWER, K_EPILOGUE, K_TRGEMM_UPPER, K_GRAD_CONTRACT, K_SUM_SPLITS, K_MC_REDUCE,
+  K_MA_UPDATE, K_ANALYTIC, K_ADAM, K_MISC, K_COUNT
+};
+struct ProfScope {  // no-op unless profiling is enabled; never use while the stream is being captured into a graph
+  ProfScope(int id, cudaStream_t st);
+  ~ProfScope();
+  int id_;
+  cudaStream_t st_;
+  cudaEvent_t beg_, end_;
+  bool on_;
+};
+
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 inline int64_t round_up64(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 

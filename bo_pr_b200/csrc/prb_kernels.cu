@@ -16,9 +16,11 @@ __global__ void philox_fill_kernel(uint64_t seed, uint64_t offset, int mc, int n
 }
 
 cudaError_t launch_philox_fill(uint64_t seed, uint64_t offset, int mc, int n_cols, double* out, cudaStream_t st) {
+  ProfScope prof_(K_MISC, st);
   const int total = mc * n_cols;
   if (total == 0) return cudaSuccess;
   philox_fill_kernel<<<(total + 255) / 256, 256, 0, st>>>(seed, offset, mc, n_cols, out);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -113,10 +115,12 @@ __global__ void pr_sample_kernel(const DevSpace sp, const double* __restrict__ t
 cudaError_t launch_pr_sample(const DevSpace& sp, const double* theta, int b, int mc, const double* u_int,
                              const double* u_cat, uint64_t seed, uint64_t offset, double* xk, double* tilde,
                              uint8_t* z, double* prob, cudaStream_t st) {
+  ProfScope prof_(K_SAMPLE, st);
   const int64_t total = int64_t(b) * mc;
   if (total == 0) return cudaSuccess;
   pr_sample_kernel<<<unsigned((total + 127) / 128), 128, 0, st>>>(sp, theta, b, mc, u_int, u_cat, seed, offset, xk,
                                                                  tilde, z, prob);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -177,9 +181,11 @@ __global__ void analytic_build_kernel(const DevSpace sp, const double* __restric
 
 cudaError_t launch_analytic_build(const DevSpace& sp, const double* theta, int b, int n_opt, const int32_t* options,
                                   double* xk, double* probs, cudaStream_t st) {
+  ProfScope prof_(K_ANALYTIC, st);
   const int64_t total = int64_t(b) * n_opt;
   if (total == 0) return cudaSuccess;
   analytic_build_kernel<<<unsigned((total + 127) / 128), 128, 0, st>>>(sp, theta, b, n_opt, options, xk, probs);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -253,19 +259,23 @@ __global__ void __launch_bounds__(KS_ROWS) kstar_panel_kernel(const DevSpec spec
 
 cudaError_t launch_kstar_panel(const Model& m, const double* xk, int ncols, int ncols_pad, double* KstarT,
                                cudaStream_t st) {
+  ProfScope prof_(K_KSTAR, st);
   dim3 grid((m.Kp + KS_ROWS - 1) / KS_ROWS, ncols_pad / KS_COLS);
   const size_t smem = size_t(m.d_k) * (KS_ROWS + KS_COLS) * sizeof(double);
   kstar_panel_kernel<<<grid, KS_ROWS, smem, st>>>(m.spec, m.Xtr, m.n, m.Kp, xk, ncols, ncols_pad, KstarT);
+  count_launch();
   return cudaGetLastError();
 }
 
 // plain K(xk, X_train) -> out[n_points, n] (leading dimension n, nothing stored beyond n_points)
 cudaError_t launch_kernel_matrix(const DevSpec& spec, const double* Xtr, int n, const double* xk, int n_points,
                                  double* out, cudaStream_t st) {
+  ProfScope prof_(K_KSTAR, st);
   if (n_points == 0) return cudaSuccess;
   dim3 grid((n + KS_ROWS - 1) / KS_ROWS, (n_points + KS_COLS - 1) / KS_COLS);
   const size_t smem = size_t(spec.d_k) * (KS_ROWS + KS_COLS) * sizeof(double);
   kstar_panel_kernel<<<grid, KS_ROWS, smem, st>>>(spec, Xtr, n, n, xk, n_points, n_points, out);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -321,9 +331,11 @@ __global__ void acq_epilogue_kernel(const DevAcq aq, double mean_const, double k
 cudaError_t launch_acq_epilogue(const Model& m, const DevAcq& aq, const double* norm_part, int ncols_pad,
                                 const double* mu_dot, int ncols, double* a, double* dmu, double* dvar,
                                 double* out_mean, double* out_var, cudaStream_t st) {
+  ProfScope prof_(K_EPILOGUE, st);
   if (ncols == 0) return cudaSuccess;
   acq_epilogue_kernel<<<(ncols + 127) / 128, 128, 0, st>>>(aq, m.mean_const, m.kss, norm_part, m.Mp1 / GEMM_BM,
                                                            ncols_pad, mu_dot, ncols, a, dmu, dvar, out_mean, out_var);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -431,10 +443,12 @@ __global__ void __launch_bounds__(GR_COLS) grad_contract_kernel(const DevSpec sp
 cudaError_t launch_grad_contract(const Model& m, uint32_t diffmask, const double* xk, int ncols, int ncols_pad,
                                  const double* W, const double* dmu, const double* dvar, double* S_part,
                                  cudaStream_t st) {
+  ProfScope prof_(K_GRAD_CONTRACT, st);
   dim3 grid(ncols_pad / GR_COLS, m.Mp2 / GRAD_JSPLIT_ROWS);
   const size_t smem = (size_t(m.d_k) * (2 * GR_COLS + GRAD_JSPLIT_ROWS) + GRAD_JSPLIT_ROWS) * sizeof(double);
   grad_contract_kernel<<<grid, GR_COLS, smem, st>>>(m.spec, diffmask, m.Xtr, m.alpha, m.n, xk, ncols, ncols_pad, W,
                                                     dmu, dvar, S_part);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -452,9 +466,11 @@ __global__ void sum_splits_kernel(const double* __restrict__ S_part, int jblocks
 
 cudaError_t launch_sum_splits(const Model& m, const double* S_part, int ncols, int ncols_pad, double* S_all,
                               cudaStream_t st) {
+  ProfScope prof_(K_SUM_SPLITS, st);
   if (ncols == 0) return cudaSuccess;
   sum_splits_kernel<<<(ncols + 127) / 128, 128, 0, st>>>(S_part, m.Mp2 / GRAD_JSPLIT_ROWS, m.d_k, ncols, ncols_pad,
                                                          S_all);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -533,8 +549,10 @@ __global__ void __launch_bounds__(128) mc_reduce_kernel(const DevSpace sp, int m
 cudaError_t launch_mc_reduce(const DevSpace& sp, int b, int mc, const double* a, const uint8_t* z, const double* prob,
                              const double* S_all, int estimator, const double* ma_state, const double* grad_out,
                              double* out_value, double* out_grad, cudaStream_t st) {
+  ProfScope prof_(K_MC_REDUCE, st);
   if (b == 0) return cudaSuccess;
   mc_reduce_kernel<<<b, 128, 0, st>>>(sp, mc, a, z, prob, S_all, estimator, ma_state, grad_out, out_value, out_grad);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -554,7 +572,9 @@ __global__ void ma_update_kernel(const double* __restrict__ value, int b, double
 }
 
 cudaError_t launch_ma_update(const double* value, int b, double* ma_state, cudaStream_t st) {
+  ProfScope prof_(K_MA_UPDATE, st);
   ma_update_kernel<<<1, 128, 0, st>>>(value, b, ma_state);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -665,8 +685,10 @@ __global__ void __launch_bounds__(128) analytic_reduce_kernel(const DevSpace sp,
 cudaError_t launch_analytic_reduce(const DevSpace& sp, const double* theta, int b, int n_opt, const int32_t* options,
                                    const double* a, const double* probs, const double* S_all, const double* grad_out,
                                    double* out_value, double* out_grad, cudaStream_t st) {
+  ProfScope prof_(K_ANALYTIC, st);
   if (b == 0) return cudaSuccess;
   analytic_reduce_kernel<<<b, 128, 0, st>>>(sp, theta, n_opt, options, a, probs, S_all, grad_out, out_value, out_grad);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -683,7 +705,9 @@ __global__ void clamp_kernel(const double* __restrict__ theta, const double* __r
 
 cudaError_t launch_clamp(const double* theta, const double* lower, const double* upper, int b, int d, double* out,
                          cudaStream_t st) {
+  ProfScope prof_(K_ADAM, st);
   clamp_kernel<<<(b * d + 255) / 256, 256, 0, st>>>(theta, lower, upper, b, d, out);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -710,8 +734,10 @@ __global__ void step_inc_kernel(int* step_ptr) { *step_ptr += 1; }
 
 cudaError_t launch_adam_step(double* theta, const double* acq_grad, double* m, double* v, int total, double lr,
                              int* step_ptr, cudaStream_t st) {
+  ProfScope prof_(K_ADAM, st);
   step_inc_kernel<<<1, 1, 0, st>>>(step_ptr);
   adam_step_kernel<<<(total + 255) / 256, 256, 0, st>>>(theta, acq_grad, m, v, total, lr, step_ptr);
+  count_launch(2);
   return cudaGetLastError();
 }
 
@@ -720,8 +746,10 @@ __global__ void fill_kernel(double* p, double v, int n) {
   if (idx < n) p[idx] = v;
 }
 cudaError_t launch_fill(double* p, double v, int n, cudaStream_t st) {
+  ProfScope prof_(K_MISC, st);
   if (n == 0) return cudaSuccess;
   fill_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, v, n);
+  count_launch();
   return cudaGetLastError();
 }
 

@@ -111,7 +111,23 @@ typedef enum { PRB_EST_REINFORCE = 0, PRB_EST_REINFORCE_MA = 1 } prb_estimator;
 
 /* ---- library ---------------------------------------------------------------------------------------------------- */
 int prb_version(void);
+/* sizeof() of the descriptor structs as compiled into the library (0 prb_factor, 1 prb_term, 2 prb_model_desc,
+ * 3 prb_space_desc, 4 prb_acq_desc): lets a foreign-language binding verify its mirror of the layout.               */
+int prb_abi_sizeof(int which);
 const char* prb_status_string(int status);
+/* Number of CUDA kernels this library has launched in this process (graph replays included).  Diagnostic: bench.py
+ * reports the difference over its timed region as "gpu_launches".                                                   */
+uint64_t prb_launch_count(void);
+
+/* Optional per-kernel device timing (diagnostic; bench.py's roofline leg).  While enabled, every kernel launch of the
+ * hot entry points is bracketed by CUDA events on the caller's stream (do not enable around prb_mc_adam: its step is
+ * captured into a CUDA graph).  prb_profile_read synchronises on the recorded events, adds up milliseconds and launch
+ * counts per slot and clears the record.  Slots: 0 sampler, 1 cross-covariance panel, 2 triangular product (lower:
+ * Linv k*), 3 acquisition epilogue, 4 triangular product (upper: Linv^T v), 5 gradient contraction, 6 split sums,
+ * 7 MC reduction, 8 EMA update, 9 analytic build/reduce, 10 Adam/clamp, 11 other.                                     */
+#define PRB_PROFILE_SLOTS 12
+int prb_profile_enable(int on);
+int prb_profile_read(double* ms_by_kernel, uint64_t* launches_by_kernel, int32_t n_slots);
 const char* prb_last_cuda_error(void);
 
 /* Builds the device-side GP state (padded copies of Linv / Linv^T with alpha appended).  Allocates; call once per

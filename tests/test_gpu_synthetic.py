@@ -1,0 +1,134 @@
+"""The synthetic sweep shape (BASELINE.json configs[4]): CUDA path vs the CPU oracle at sizes the oracle finishes in
+seconds, and size-independent properties at the full bench size (n = 1000, 64 restarts x 1024 MC samples)."""
+import ctypes as C
+
+import pytest
+import torch
+
+from bench_workload import make_problem, make_theta, sobol_base_samples
+from oracle import pr_oracle as P
+from tests.golden_util import oracle_acq, oracle_space
+from tests.product_util import close, product_acq, product_mc_pr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _problem(n, mc, acq="ei", est="reinforce_ma", seed=0):
+    g = make_problem(n, seed=seed)
+    g["case"].update(acq=acq, mc=mc, grad_estimator=est)
+    g["base_samples"] = sobol_base_samples(mc)
+    g["base_samples_categorical"] = None
+    return g
+
+
+def _assert_close(a, b, what, rtol=1e-9, atol=1e-12):
+    ok, worst = close(a, b, rtol, atol)
+    assert ok, f"{what}: worst error = {worst:.3g} x tolerance"
+
+
+@pytest.mark.parametrize("n,b,mc,acq", [(200, 8, 128, "ei"), (333, 5, 96, "ucb"), (1000, 4, 256, "ei"),
+                                        (1537, 3, 64, "ei")])
+def test_value_grad_vs_oracle(n, b, mc, acq):
+    g = _problem(n, mc, acq)
+    space, oacq = oracle_space(g), oracle_acq(g)
+    theta = make_theta(b)
+    go = torch.linspace(0.5, 1.5, b, dtype=torch.float64)
+    ref = P.mc_pr(space, theta, oacq, g["base_samples"], None, grad_estimator="reinforce_ma", ma_counter=3.0,
+                  ma_hidden=0.05, grad_output=go)
+    pr = product_mc_pr(g, DEV)
+    pr._ma_state.copy_(torch.tensor([3.0, 0.05], dtype=torch.float64))
+    X = theta.to(DEV).requires_grad_(True)
+    val = pr(X)
+    grad = torch.autograd.grad(val, X, grad_outputs=go.to(DEV))[0]
+    _assert_close(val, ref.value, "PR value")
+    _assert_close(grad, ref.grad, "PR gradient", atol=1e-11)
+    _assert_close(pr._ma_state, torch.tensor([ref.ma_counter, ref.ma_hidden]), "EMA state", rtol=1e-12)
+
+
+def test_chunking_is_bitwise_invariant():
+    """The L2-resident panel width is a performance knob only: per-column results do not depend on it."""
+    g = _problem(500, 128)
+    theta = make_theta(6).to(DEV)
+    outs = []
+    for chunk in (0, 128, 384):
+        pr = product_mc_pr(g, DEV)
+        pr.acq_function.state.chunk_cols = chunk
+        X = theta.clone().requires_grad_(True)
+        val = pr(X)
+        grad = torch.autograd.grad(val.sum(), X)[0]
+        outs.append((val.detach().clone(), grad.clone()))
+    for v, gr in outs[1:]:
+        assert torch.equal(v, outs[0][0]) and torch.equal(gr, outs[0][1])
+
+
+def test_full_size_properties():
+    """n = 1000, 64 restarts x 1024 MC samples (the bench configuration): shard invariance (what the multi-GPU split
+    relies on), bitwise repeatability, first reinforce_ma backward == plain reinforce, value-only == value of value+grad,
+    MC mean consistent with the per-sample values."""
+    n, b, mc = 1000, 64, 1024
+    g = _problem(n, mc)
+    theta = make_theta(b).to(DEV)
+    acq = product_acq(g, DEV)
+    pr = product_mc_pr(g, DEV, acq=acq)
+
+    def run(th, state=(0.0, 0.0)):
+        pr._ma_state.copy_(torch.tensor(state, dtype=torch.float64))
+        X = th.clone().requires_grad_(True)
+        val = pr(X)
+        grad = torch.autograd.grad(val.sum(), X)[0]
+        return val.detach().clone(), grad.clone()
+
+    v_all, g_all = run(theta, (5.0, 0.02))
+    v_again, g_again = run(theta, (5.0, 0.02))
+    assert torch.equal(v_all, v_again) and torch.equal(g_all, g_again)
+    # restart shards: ranks evaluate disjoint restart slices with the replicated GP state and the same pre-call EMA state
+    for G_ in (2, 8):
+        vs, gs = zip(*[run(theta[r::G_], (5.0, 0.02)) for r in range(G_)])
+        v_cat = torch.empty_like(v_all)
+        g_cat = torch.empty_like(g_all)
+        for r in range(G_):
+            v_cat[r::G_], g_cat[r::G_] = vs[r], gs[r]
+        assert torch.equal(v_cat, v_all) and torch.equal(g_cat, g_all)
+    # baseline is 0 while ma_counter == 0
+    pr2 = product_mc_pr(dict(g, case=dict(g["case"], grad_estimator="reinforce")), DEV, acq=acq)
+    X = theta.clone().requires_grad_(True)
+    g_plain = torch.autograd.grad(pr2(X).sum(), X)[0]
+    v0, g0 = run(theta, (0.0, 0.0))
+    assert torch.equal(g0, g_plain)
+    with torch.no_grad():
+        pr._ma_state.zero_()
+        v_only = pr(theta)
+    assert torch.equal(v_only, v0)
+    # EMA update: hidden = 0.3 * mean(all acquisition values) after the first call from a zero state
+    _assert_close(pr._ma_state[1], 0.3 * v0.mean(), "EMA hidden", rtol=1e-12)
+    assert float(pr._ma_state[0]) == 1.0
+    assert bool((v0 >= 0).all())  # EI is non-negative
+
+
+def test_score_function_gradient_is_unbiased_for_the_analytic_objective():
+    """on a space small enough to enumerate, the MC score-function gradient converges to the exact
+    gradient of the analytic PR objective (both from the CUDA path), and the pathwise continuous gradient likewise."""
+    from tests.golden_util import load
+    from tests.product_util import product_analytic_pr
+    g = load("int_cat_analytic_pm")
+    acq = product_acq(g, DEV)
+    an = product_analytic_pr(g, DEV, acq=acq)
+    theta = g["theta"][3:6].to(DEV)  # interior rows
+    X = theta.clone().requires_grad_(True)
+    va = an(X)
+    ga = torch.autograd.grad(va.sum(), X)[0]
+    mc = 1 << 15
+    gm = dict(g, case=dict(g["case"], mc=mc, grad_estimator="reinforce"), base_samples=None,
+              base_samples_categorical=None)
+    torch.manual_seed(0)
+    pr = product_mc_pr(gm, DEV, acq=acq)
+    X2 = theta.clone().requires_grad_(True)
+    vm = pr(X2)
+    gmc = torch.autograd.grad(vm.sum(), X2)[0]
+    assert torch.allclose(vm, va, rtol=2e-3, atol=2e-4)
+    # integer columns: the MC estimator omits the Normalize chain-rule factor `range`
+    ib = torch.tensor(g["case"]["integer_bounds"], dtype=torch.float64, device=DEV)
+    scale = torch.ones(theta.shape[-1], dtype=torch.float64, device=DEV)
+    scale[g["case"]["integer_indices"]] = ib[1] - ib[0]
+    assert torch.allclose(gmc * scale, ga, rtol=5e-2, atol=5e-3)
