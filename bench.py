@@ -229,7 +229,7 @@ def run_ours(a):
     value = torch.empty(b, dtype=torch.float64, device=dev)
     grad = torch.empty(b, d, dtype=torch.float64, device=dev)
     ma = torch.zeros(2, dtype=torch.float64, device=dev)
-    ws = state.workspace(b * mc, d)
+    ws = state.workspace(b * mc, d, b)
     stream = torch.cuda.current_stream()
 
     def step():

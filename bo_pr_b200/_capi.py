@@ -95,7 +95,7 @@ def load_library() -> C.CDLL:
     lib.prb_model_n.argtypes = [vp]
     lib.prb_model_dk.argtypes = [vp]
     lib.prb_workspace_bytes.restype = sz
-    lib.prb_workspace_bytes.argtypes = [vp, i64, i32, i32]
+    lib.prb_workspace_bytes.argtypes = [vp, i64, i32, i32, i32]
     lib.prb_philox_uniform.argtypes = [u64, u64, i32, i32, vp, vp]
     lib.prb_pr_sample.argtypes = [C.POINTER(PrbSpaceDesc), vp, i32, i32, vp, vp, u64, u64, vp, vp, vp, vp]
     lib.prb_analytic_enumerate.argtypes = [C.POINTER(PrbSpaceDesc), vp, i32, vp, i32, vp, vp, vp]

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "_lib", "libprb200.so")
-SOURCES = ["prb_gemm.cu", "prb_kernels.cu", "prb_api.cu"]
+SOURCES = ["prb_gemm.cu", "prb_gemm_tma.cu", "prb_kernels.cu", "prb_api.cu"]
 HEADERS = ["prb_internal.cuh", "prb_device.cuh", "prb_kernels.cuh", os.path.join(ROOT, "include", "prb200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

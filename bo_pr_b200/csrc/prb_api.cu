@@ -1,6 +1,7 @@
 // C ABI of libprb200 (see include/prb200.h).  Host-side orchestration only: argument validation, workspace carving and
 // kernel sequencing on the caller's stream.  No allocation and no synchronisation on the hot entry points.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -158,19 +159,30 @@ struct Plan {
   size_t off_xk, off_z, off_prob, off_a, off_dmu, off_dvar, off_S_all, off_probs;
   size_t off_panelA, off_panelV, off_norm, off_mu, off_S_part;
   size_t off_Xc, off_grad, off_ones, off_val, off_step;
+  size_t off_zbits, off_kc, off_Dc;
   size_t total;
 };
 
-constexpr size_t kPanelBudgetBytes = size_t(96) << 20;  // two panels sized to stay resident in the 126 MB L2
+// Column panels (k*, v, w) are sized to stay resident in the 126 MB L2 between the kernel that writes them and the one
+// that reads them.  PRB_PANEL_MB overrides the budget (tuning knob, read once).
+size_t panel_budget_bytes() {
+  static size_t v = 0;
+  if (v == 0) {
+    const char* e = getenv("PRB_PANEL_MB");
+    long mb = e ? atol(e) : 0;
+    v = size_t(mb > 0 ? mb : 96) << 20;
+  }
+  return v;
+}
 
-Plan make_plan(const Model& m, int64_t n_points, int d_theta, int chunk_cols) {
+Plan make_plan(const Model& m, int64_t n_points, int n_restarts, int d_theta, int chunk_cols) {
   Plan p;
   memset(&p, 0, sizeof(p));
   p.B = n_points;
   p.B_pad = round_up64(n_points > 0 ? n_points : 1, 128);
   int64_t C = chunk_cols;
   if (C <= 0) {
-    C = int64_t(kPanelBudgetBytes / (sizeof(double) * size_t(m.Mp1 + m.Mp2))) / 128 * 128;
+    C = int64_t(panel_budget_bytes() / (sizeof(double) * size_t(m.Mp1 + m.Mp2))) / 128 * 128;
     if (C < 128) C = 128;
   }
   C = round_up64(C, 128);
@@ -204,6 +216,11 @@ Plan make_plan(const Model& m, int64_t n_points, int d_theta, int chunk_cols) {
   p.off_ones = take(size_t(p.B_pad) * dbl);
   p.off_val = take(size_t(p.B_pad) * dbl);
   p.off_step = take(256);
+  p.off_zbits = take(size_t(p.B_pad) * sizeof(uint32_t));
+  if (m.sep_ok && n_restarts > 0) {
+    p.off_kc = take(size_t(n_restarts) * m.Kp * dbl);
+    p.off_Dc = take(size_t(n_restarts) * d_theta * m.Kp * dbl);
+  }
   p.total = off;
   return p;
 }
@@ -214,6 +231,17 @@ T* at(void* ws, size_t off) {
 }
 
 // ---- the posterior/acquisition engine over L2-resident column panels ------------------------------------------------
+// PRB_ENGINE=v1 selects the first-generation cp.async GEMM (kept for A/B measurements); default: TMA + mbarrier kernels
+int engine_version() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("PRB_ENGINE");
+    v = (e && strcmp(e, "v1") == 0) ? 1 : 2;
+  }
+  return v;
+}
+
+// generic kernel structures: materialised k* panel -> lower product -> epilogue -> upper product -> gradient contraction
 int run_engine(const Model& m, const DevAcq& aq, const Plan& pl, void* ws, const double* xk, int64_t B, bool need_grad,
                uint32_t diffmask, double* a, double* dmu, double* dvar, double* S_all, double* out_mean,
                double* out_var, cudaStream_t st) {
@@ -222,18 +250,93 @@ int run_engine(const Model& m, const DevAcq& aq, const Plan& pl, void* ws, const
   double* norm = at<double>(ws, pl.off_norm);
   double* mu = at<double>(ws, pl.off_mu);
   double* S_part = at<double>(ws, pl.off_S_part);
+  const bool v2 = engine_version() == 2;
+  TensorMap mapK, mapV;
+  if (v2) {
+    CUDA_TRY(make_operand_map(&mapK, panelA, pl.C, m.Kp, m.Kp));
+    CUDA_TRY(make_operand_map(&mapV, panelV, pl.C, m.Kp, m.Mp1));
+  }
   for (int64_t c0 = 0; c0 < B; c0 += pl.C) {
     const int ncols = int(B - c0 < pl.C ? B - c0 : pl.C);
     const int ncols_pad = round_up(ncols, 128);
     const double* xkc = xk + size_t(c0) * m.d_k;
     CUDA_TRY(launch_kstar_panel(m, xkc, ncols, ncols_pad, panelA, st));
-    CUDA_TRY(launch_trgemm_lower(m, panelA, ncols_pad, panelV, norm, mu, st));
+    if (v2)
+      CUDA_TRY(launch_tma_lower(m, mapK, ncols_pad, need_grad ? panelV : nullptr, norm, mu, st));
+    else
+      CUDA_TRY(launch_trgemm_lower(m, panelA, ncols_pad, panelV, norm, mu, st));
     CUDA_TRY(launch_acq_epilogue(m, aq, norm, ncols_pad, mu, ncols, a + c0, dmu + c0, dvar + c0,
                                  out_mean ? out_mean + c0 : nullptr, out_var ? out_var + c0 : nullptr, st));
     if (need_grad) {
-      CUDA_TRY(launch_trgemm_upper(m, panelV, ncols_pad, panelA, st));
+      if (v2)
+        CUDA_TRY(launch_tma_upper(m, mapV, ncols_pad, panelA, st));
+      else
+        CUDA_TRY(launch_trgemm_upper(m, panelV, ncols_pad, panelA, st));
       CUDA_TRY(launch_grad_contract(m, diffmask, xkc, ncols, ncols_pad, panelA, dmu + c0, dvar + c0, S_part, st));
-      CUDA_TRY(launch_sum_splits(m, S_part, ncols, ncols_pad, S_all + size_t(c0) * m.d_k, st));
+      CUDA_TRY(launch_sum_splits(m, S_part, nullptr, ncols, ncols_pad, S_all + size_t(c0) * m.d_k, st));
+    }
+  }
+  return PRB_OK;
+}
+
+// Does this PR space line up with the model's separable structure?  Every integer parameter must be a binary dim of the
+// binary factor (bounds [0, 1]), there are no categoricals, and the continuous columns are exactly the other factor's.
+bool sep_space_ok(const Model& m, const DevSpace& sp, BitMap* bm, DimMap* dm) {
+  if (!m.sep_ok || engine_version() != 2 || sp.n_cat != 0 || sp.d != m.d_k || sp.raw_int) return false;
+  const DevFactor& fb = m.spec.t[0].f[m.sep_bin_factor];
+  const DevFactor& fc = m.spec.t[0].f[m.sep_cont_factor];
+  if (sp.n_int != fb.n_dims || sp.n_cont != fc.n_dims) return false;
+  for (int k = 0; k < PRB_MAX_DIMS; ++k) bm->pos[k] = -1;
+  for (int k = 0; k < sp.n_int; ++k) {
+    if (sp.int_lo[k] != 0.0 || sp.int_hi[k] != 1.0) return false;
+    int pos = -1;
+    for (int di = 0; di < fb.n_dims; ++di)
+      if (fb.dims[di] == sp.int_cols[k]) pos = di;
+    if (pos < 0) return false;
+    bm->pos[k] = pos;
+  }
+  dm->n = fc.n_dims;
+  for (int di = 0; di < fc.n_dims; ++di) {
+    bool found = false;
+    for (int ci = 0; ci < sp.n_cont; ++ci) found = found || sp.cont_cols[ci] == fc.dims[di];
+    if (!found) return false;
+    dm->dims[di] = fc.dims[di];
+  }
+  return true;
+}
+
+// separable fast path: no k* panel, no W panel -- operands generated in the lower product, gradient contracted in the
+// epilogue of the upper product
+int run_engine_sep(const Model& m, const DevAcq& aq, const Plan& pl, void* ws, const double* theta, int d_theta, int nb,
+                   int mc, const DimMap& dm, bool need_grad, double* a, double* dmu, double* dvar, double* S_all,
+                   cudaStream_t st) {
+  const int64_t B = int64_t(nb) * mc;
+  double* panelV = at<double>(ws, pl.off_panelV);
+  double* norm = at<double>(ws, pl.off_norm);
+  double* mu = at<double>(ws, pl.off_mu);
+  double* S_part = at<double>(ws, pl.off_S_part);
+  double* kc = at<double>(ws, pl.off_kc);
+  double* Dc = at<double>(ws, pl.off_Dc);
+  const uint32_t* zbits = at<uint32_t>(ws, pl.off_zbits);
+  CUDA_TRY(launch_sep_restart_prep(m, theta, nb, d_theta, kc, need_grad ? Dc : nullptr, st));
+  TensorMap mapV;
+  if (need_grad) CUDA_TRY(make_operand_map(&mapV, panelV, pl.C, m.Kp, m.Mp1));
+  for (int64_t c0 = 0; c0 < B; c0 += pl.C) {
+    const int ncols = int(B - c0 < pl.C ? B - c0 : pl.C);
+    const int ncols_pad = round_up(ncols, 128);
+    SepArgs sa;
+    sa.kc = kc;
+    sa.Dc = Dc;
+    sa.zbits = zbits + c0;
+    sa.n_cont = dm.n;
+    sa.mc = mc;
+    sa.nb = nb;
+    sa.col0 = c0;
+    CUDA_TRY(launch_tma_lower_gen(m, sa, ncols_pad, need_grad ? panelV : nullptr, norm, mu, st));
+    CUDA_TRY(launch_acq_epilogue(m, aq, norm, ncols_pad, mu, ncols, a + c0, dmu + c0, dvar + c0, nullptr, nullptr, st));
+    if (need_grad) {
+      CUDA_TRY(launch_tma_upper_grad(m, mapV, sa, ncols, ncols_pad, dmu + c0, dvar + c0, S_part, st));
+      CUDA_TRY(launch_sum_splits(m, S_part, &dm, ncols, ncols_pad, S_all + size_t(c0) * m.d_k, st));
     }
   }
   return PRB_OK;
@@ -259,10 +362,20 @@ int mc_core(prb_model* model, const DevSpace& sp, const DevAcq& aq, const Plan& 
   double* dvar = at<double>(ws, pl.off_dvar);
   double* S_all = at<double>(ws, pl.off_S_all);
   const bool need_grad = grad_out != nullptr;
-  CUDA_TRY(launch_pr_sample(sp, theta, b, mc, u_int, u_cat, seed, offset, xk, nullptr, need_grad ? z : nullptr,
-                            need_grad ? prob : nullptr, st));
   const bool need_path = need_grad && sp.n_cont > 0;
-  int rc = run_engine(m, aq, pl, ws, xk, B, need_path, cont_mask(sp), a, dmu, dvar, S_all, nullptr, nullptr, st);
+  BitMap bm;
+  DimMap dm;
+  const bool sep = pl.off_kc != 0 && sep_space_ok(m, sp, &bm, &dm);
+  int rc;
+  if (sep) {
+    CUDA_TRY(launch_pr_sample(sp, theta, b, mc, u_int, u_cat, seed, offset, nullptr, nullptr, need_grad ? z : nullptr,
+                              need_grad ? prob : nullptr, &bm, at<uint32_t>(ws, pl.off_zbits), st));
+    rc = run_engine_sep(m, aq, pl, ws, theta, sp.d, b, mc, dm, need_path, a, dmu, dvar, S_all, st);
+  } else {
+    CUDA_TRY(launch_pr_sample(sp, theta, b, mc, u_int, u_cat, seed, offset, xk, nullptr, need_grad ? z : nullptr,
+                              need_grad ? prob : nullptr, nullptr, nullptr, st));
+    rc = run_engine(m, aq, pl, ws, xk, B, need_path, cont_mask(sp), a, dmu, dvar, S_all, nullptr, nullptr, st);
+  }
   if (rc != PRB_OK) return rc;
   CUDA_TRY(launch_mc_reduce(sp, b, mc, a, z, prob, S_all, estimator, ma_state, grad_out, out_value, out_grad, st));
   if (update_ma && ma_state) CUDA_TRY(launch_ma_update(out_value, b, ma_state, st));
@@ -380,6 +493,45 @@ int prb_model_create(prb_model** out, const prb_model_desc* desc, void* stream) 
     count_launch();
   }
   if (e == cudaSuccess) e = gemm_init();
+  // second-generation engine: TMA descriptors of the packed factors, padded alpha, separable-structure tables
+  const int n_pad = m->Mp1 > m->Mp2 ? m->Mp1 : m->Mp2;
+  int* bad_flag = nullptr;
+  if (e == cudaSuccess) e = tma_init();
+  if (e == cudaSuccess) e = cudaMalloc(&m->alpha_pad, size_t(n_pad) * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&m->Zbits, size_t(n_pad) * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&m->sep_tab, 64 * sizeof(double));
+  if (e == cudaSuccess) e = launch_pad_copy(m->alpha, m->n, n_pad, m->alpha_pad, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(m->Zbits, 0, size_t(n_pad) * sizeof(uint32_t), st);
+  if (e == cudaSuccess) e = make_operand_map(&m->mapA1, m->A1, m->Mp1, m->Kp, m->Kp);
+  if (e == cudaSuccess) e = make_operand_map(&m->mapA2, m->A2, m->Mp2, m->Kp, m->Kp);
+  // separable candidate: one product term of two Matern-5/2 factors, one of them isotropic over <= 32 dims
+  m->sep_ok = 0;
+  if (e == cudaSuccess && m->spec.n_terms == 1 && !m->spec.t[0].additive && m->spec.t[0].n_factors == 2) {
+    const DevTerm& T = m->spec.t[0];
+    for (int fb = 0; fb < 2 && !m->sep_ok; ++fb) {
+      const DevFactor& F = T.f[fb];
+      const DevFactor& O = T.f[1 - fb];
+      bool cand = F.kind == PRB_FACTOR_MATERN52 && O.kind == PRB_FACTOR_MATERN52 && F.power == 1 && O.power == 1 &&
+                  F.n_dims <= 32;
+      for (int i = 1; i < F.n_dims && cand; ++i) cand = F.inv_ls[i] == F.inv_ls[0];
+      for (int i = 0; i < F.n_dims && cand; ++i)
+        for (int k = 0; k < O.n_dims && cand; ++k) cand = F.dims[i] != O.dims[k];
+      if (!cand) continue;
+      m->sep_bin_factor = fb;
+      m->sep_cont_factor = 1 - fb;
+      m->sep_nbits = F.n_dims;
+      if ((e = cudaMalloc(&bad_flag, sizeof(int))) != cudaSuccess) break;
+      if ((e = cudaMemsetAsync(bad_flag, 0, sizeof(int), st)) != cudaSuccess) break;
+      if ((e = launch_sep_model_prep(*m, n_pad, bad_flag, st)) != cudaSuccess) break;
+      int bad = 1;
+      if ((e = cudaMemcpyAsync(&bad, bad_flag, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+      if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
+      cudaFree(bad_flag);
+      bad_flag = nullptr;
+      if (!bad) m->sep_ok = 1;  // the factor's training columns are exactly {0, 1}
+    }
+  }
+  if (bad_flag) cudaFree(bad_flag);
   if (e != cudaSuccess) {
     prb_model_destroy(reinterpret_cast<prb_model*>(m));
     return cuda_fail(e, "prb_model_create");
@@ -395,6 +547,9 @@ int prb_model_destroy(prb_model* model) {
   cudaFree(m->A2);
   cudaFree(m->Xtr);
   cudaFree(m->alpha);
+  cudaFree(m->alpha_pad);
+  cudaFree(m->Zbits);
+  cudaFree(m->sep_tab);
   delete m;
   return PRB_OK;
 }
@@ -404,9 +559,10 @@ int prb_model_dk(const prb_model* model) {
   return model ? reinterpret_cast<const Model*>(model)->d_k : PRB_ERR_INVALID;
 }
 
-size_t prb_workspace_bytes(const prb_model* model, int64_t n_points, int32_t d_theta, int32_t chunk_cols) {
-  if (!model || n_points < 0 || d_theta < 1) return 0;
-  return make_plan(*reinterpret_cast<const Model*>(model), n_points, d_theta, chunk_cols).total;
+size_t prb_workspace_bytes(const prb_model* model, int64_t n_points, int32_t n_restarts, int32_t d_theta,
+                           int32_t chunk_cols) {
+  if (!model || n_points < 0 || d_theta < 1 || n_restarts < 0) return 0;
+  return make_plan(*reinterpret_cast<const Model*>(model), n_points, n_restarts, d_theta, chunk_cols).total;
 }
 
 int prb_philox_uniform(uint64_t seed, uint64_t offset, int32_t mc, int32_t n_cols, double* out, void* stream) {
@@ -423,7 +579,7 @@ int prb_pr_sample(const prb_space_desc* space, const double* theta, int32_t b, i
   if (rc != PRB_OK) return rc;
   if (!theta || b < 0 || mc < 0) return PRB_ERR_INVALID;
   CUDA_TRY(launch_pr_sample(sp, theta, b, mc, u_int, u_cat, seed, offset, nullptr, out_tilde_x, out_z, out_prob,
-                            static_cast<cudaStream_t>(stream)));
+                            nullptr, nullptr, static_cast<cudaStream_t>(stream)));
   return PRB_OK;
 }
 
@@ -459,7 +615,7 @@ int prb_acq_points(prb_model* model, const prb_acq_desc* acq, const double* xk, 
   int rc = make_acq(acq, &aq);
   if (rc != PRB_OK) return rc;
   if (n_points == 0) return PRB_OK;
-  const Plan pl = make_plan(m, n_points, m.d_k, chunk_cols);
+  const Plan pl = make_plan(m, n_points, 0, m.d_k, chunk_cols);
   if (workspace_bytes < pl.total) return PRB_ERR_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   double* a = out_acq ? out_acq : at<double>(workspace, pl.off_a);
@@ -490,7 +646,7 @@ int prb_mc_value_grad(prb_model* model, const prb_space_desc* space, const prb_a
   if ((rc = make_acq(acq, &aq)) != PRB_OK) return rc;
   if (sp.d_k != m.d_k) return PRB_ERR_INVALID;
   if (b == 0) return PRB_OK;
-  const Plan pl = make_plan(m, int64_t(b) * mc, sp.d, chunk_cols);
+  const Plan pl = make_plan(m, int64_t(b) * mc, b, sp.d, chunk_cols);
   if (workspace_bytes < pl.total) return PRB_ERR_WORKSPACE;
   return mc_core(model, sp, aq, pl, workspace, theta, b, mc, u_int, u_cat, seed, offset, estimator, ma_state,
                  update_ma, grad_out, out_value, out_grad, out_acq_values, static_cast<cudaStream_t>(stream));
@@ -512,7 +668,7 @@ int prb_analytic_value_grad(prb_model* model, const prb_space_desc* space, const
   if (sp.d_k != m.d_k) return PRB_ERR_INVALID;
   if (b == 0) return PRB_OK;
   const int64_t B = int64_t(b) * n_options;
-  const Plan pl = make_plan(m, B, sp.d, chunk_cols);
+  const Plan pl = make_plan(m, B, b, sp.d, chunk_cols);
   if (workspace_bytes < pl.total) return PRB_ERR_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   double* xk = at<double>(workspace, pl.off_xk);
@@ -544,7 +700,7 @@ int prb_mc_adam(prb_model* model, const prb_space_desc* space, const prb_acq_des
   if (rc != PRB_OK) return rc;
   if ((rc = make_acq(acq, &aq)) != PRB_OK) return rc;
   if (sp.d_k != m.d_k) return PRB_ERR_INVALID;
-  const Plan pl = make_plan(m, int64_t(b) * mc, sp.d, chunk_cols);
+  const Plan pl = make_plan(m, int64_t(b) * mc, b, sp.d, chunk_cols);
   if (workspace_bytes < pl.total) return PRB_ERR_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   double* Xc = at<double>(workspace, pl.off_Xc);

@@ -1,0 +1,520 @@
+// FP64 triangular panel products, second generation: TMA + mbarrier pipeline feeding the sm_100a DMMA pipe, with the
+// cross-covariance generated inside the kernel and the pathwise-gradient contraction fused into the epilogue.
+//
+//   lower:  V^T[col, j] = sum_{k <= j} A1[j, k] * k*[col, k]      A1 = [Linv ; alpha^T]   (posterior variance + mean)
+//   upper:  W[j, col]   = sum_{k >= j} A2[j, k] * V^T[col, k]     A2 = Linv^T            (K^-1 k*, for d sigma^2 / d x)
+//
+// Reference: the dense k* @ L^-T GEMM inside GPyTorch's exact prediction strategy ([3P], reached from
+// probabilistic_reparameterization.py:491) and its autograd backward (:624-633).
+//
+// sm_100a has no tcgen05 kind for FP64; the FP64 tensor path is mma.sync DMMA (37.1 TFLOP/s measured), whose accumulators
+// live in registers, so there is no TMEM stage.  What IS Blackwell-native here: operand tiles arrive by TMA
+// (cp.async.bulk.tensor, one elected thread, no per-thread address arithmetic) into a dense [k-chunk][row][4] layout that
+// makes every DMMA fragment load a fully coalesced, conflict-free 256-byte LDS.64; stage hand-off is by full/empty
+// mbarriers (no __syncthreads in the main loop, producer runs two k-tiles ahead).
+//
+// Four modes (template):
+//   LOWER_GEN   the B operand k*[col, k] = kc[b(col), k] * tab[popc(z[col] ^ Z[k])] is GENERATED into shared memory by the
+//               consumer threads (separable "mixed" kernel: Matern over continuous dims x isotropic Matern over binary dims);
+//               the k* panel never exists in HBM.
+//   LOWER_TMA   B operand = materialised k* panel (generic kernel structures), via TMA.
+//   UPPER_W     stores W (generic path; the gradient contraction kernel consumes it).
+//   UPPER_GRAD  epilogue contracts W with the kernel derivative in registers:
+//               S[c, col] = sum_j (dA/dmu alpha_j - 2 dA/dvar W[j, col]) * kb(z_col, Z_j) * Dc[b(col), c, j]; W never hits HBM.
+#include <cuda.h>
+
+#include "prb_internal.cuh"
+
+namespace prb {
+
+constexpr int T_BM = 128, T_BN = 128, T_BK = 16, T_STAGES = 4, T_AHEAD = 2, T_THREADS = 256;
+constexpr int T_OPER_DOUBLES = T_BM * T_BK;            // 2048 doubles = 16 KB per operand per stage
+constexpr int T_CHUNK_DOUBLES = T_BM * 4;              // one k-chunk (4 k values) of 128 rows
+constexpr int T_STAGE_DOUBLES = 2 * T_OPER_DOUBLES;
+constexpr size_t T_SMEM_BYTES = size_t(T_STAGES) * T_STAGE_DOUBLES * 8 + 2 * T_STAGES * 8 + 64 * 8;
+
+enum { MODE_LOWER_GEN = 0, MODE_LOWER_TMA = 1, MODE_UPPER_W = 2, MODE_UPPER_GRAD = 3 };
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      "WAIT_%=:\n"
+      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      " @p bra DONE_%=;\n"
+      " bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+struct TmaGemmParams {
+  int mtiles, ntiles, Kp, ncols_pad;
+  // lower epilogue
+  double* C;  // V^T [ncols_pad, ldc] (lower) or W [Mp2, ncols_pad] (UPPER_W)
+  int ldc;
+  int special_row;  // row of A1 holding alpha^T (its product is the posterior-mean dot), -1 for upper
+  double* norm_part;
+  double* mu_dot;
+  // operand generation / gradient epilogue (separable kernel)
+  const double* kc;       // [nb, Kp]  outputscale * Matern52 over the continuous dims, per restart (0 beyond n)
+  const uint32_t* Zbits;  // [Mp]      bit codes of the training points over the binary dims (0 beyond n)
+  const uint32_t* zbits;  // [ncols_pad] bit codes of this panel's evaluation points
+  const double* tab;      // [ntab + 1] binary-factor value by Hamming distance
+  int ntab;
+  int mc;        // evaluation points per restart (b(col) = (col0 + col) / mc)
+  int64_t col0;  // global index of the panel's first column
+  int nb;        // number of restarts (clamp for padded columns)
+  const double* Dc;         // [nb, n_cont, Kp] outputscale * G(r) * (x_c - X_jc) / l_c^2
+  int n_cont;
+  const double* alpha_pad;  // [Mp2] alpha, 0 beyond n
+  const double* dmu;        // [ncols] dA/dmu       (panel-local)
+  const double* dvar;       // [ncols] dA/dsigma^2
+  int ncols;                // valid columns in this panel
+  double* S_part;           // [mtiles, n_cont, ncols_pad]
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(T_THREADS, 1)
+    trgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const TmaGemmParams p) {
+  constexpr bool UPPER = (MODE == MODE_UPPER_W || MODE == MODE_UPPER_GRAD);
+  constexpr bool GEN = (MODE == MODE_LOWER_GEN);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* stages = reinterpret_cast<double*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + size_t(T_STAGES) * T_STAGE_DOUBLES * 8);
+  uint64_t* empty = full + T_STAGES;
+  double* tab_s = reinterpret_cast<double*>(empty + T_STAGES);  // [64]
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int wm = warp & 3;   // 4 warps along M (32 rows each)
+  const int wn = warp >> 2;  // 2 warps along N (64 cols each)
+
+  // heavy tiles first: lower -> largest row block first, upper -> smallest row block first
+  const int t = blockIdx.x;
+  const int nt = t % p.ntiles;
+  const int mi_sched = t / p.ntiles;
+  const int mt = UPPER ? mi_sched : (p.mtiles - 1 - mi_sched);
+  const int m0 = mt * T_BM;
+  const int n0 = nt * T_BN;
+  int kbeg, kend;
+  if (UPPER) {
+    kbeg = m0;
+    kend = p.Kp;
+  } else {
+    kbeg = 0;
+    kend = (mt == p.mtiles - 1) ? p.Kp : min(p.Kp, m0 + T_BM);
+  }
+  const int num_k = (kend - kbeg) / T_BK;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmA);
+    if (!GEN) tma_prefetch_desc(&tmB);
+    for (int s = 0; s < T_STAGES; ++s) {
+      mbar_init(&full[s], GEN ? 1 + T_THREADS : 1);
+      mbar_init(&empty[s], T_THREADS / 32);
+    }
+    mbar_fence_init();
+  }
+  if ((GEN || MODE == MODE_UPPER_GRAD) && tid < 64) tab_s[tid] = (tid <= p.ntab) ? p.tab[tid] : 0.0;
+  __syncthreads();
+
+  // ---- B-operand generation: thread <-> (evaluation column, 8 of the 16 k values of a k-tile) ---------------------------
+  const int gcol = tid & (T_BN - 1);
+  const int ghalf = tid >> 7;
+  uint32_t g_zb = 0;
+  const double* g_kc = nullptr;
+  if (GEN) {
+    g_zb = p.zbits[n0 + gcol];
+    int64_t br = (p.col0 + n0 + gcol) / p.mc;
+    if (br > p.nb - 1) br = p.nb - 1;
+    g_kc = p.kc + size_t(br) * p.Kp;
+  }
+
+  auto produce = [&](int kt) {
+    const int s = kt % T_STAGES;
+    const int use = kt / T_STAGES;
+    const int k0 = kbeg + kt * T_BK;
+    double* As = stages + s * T_STAGE_DOUBLES;
+    double* Bs = As + T_OPER_DOUBLES;
+    if (GEN) {
+      // global operands first (latency overlaps the wait below)
+      const double2* kc2 = reinterpret_cast<const double2*>(g_kc + k0 + ghalf * 8);
+      const uint4* zz = reinterpret_cast<const uint4*>(p.Zbits + k0 + ghalf * 8);
+      const double2 k01 = __ldg(kc2), k23 = __ldg(kc2 + 1), k45 = __ldg(kc2 + 2), k67 = __ldg(kc2 + 3);
+      const uint4 za = __ldg(zz), zc = __ldg(zz + 1);
+      if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+      if (tid == 0) {
+        mbar_arrive_expect_tx(&full[s], T_OPER_DOUBLES * 8);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tma_load_2d(As + c * T_CHUNK_DOUBLES, &tmA, &full[s], k0 + 4 * c, m0);
+      }
+      double2 o0, o1, o2, o3;
+      o0.x = k01.x * tab_s[__popc(g_zb ^ za.x)];
+      o0.y = k01.y * tab_s[__popc(g_zb ^ za.y)];
+      o1.x = k23.x * tab_s[__popc(g_zb ^ za.z)];
+      o1.y = k23.y * tab_s[__popc(g_zb ^ za.w)];
+      o2.x = k45.x * tab_s[__popc(g_zb ^ zc.x)];
+      o2.y = k45.y * tab_s[__popc(g_zb ^ zc.y)];
+      o3.x = k67.x * tab_s[__popc(g_zb ^ zc.z)];
+      o3.y = k67.y * tab_s[__popc(g_zb ^ zc.w)];
+      double2* d0 = reinterpret_cast<double2*>(Bs + (2 * ghalf) * T_CHUNK_DOUBLES + gcol * 4);
+      double2* d1 = reinterpret_cast<double2*>(Bs + (2 * ghalf + 1) * T_CHUNK_DOUBLES + gcol * 4);
+      d0[0] = o0;
+      d0[1] = o1;
+      d1[0] = o2;
+      d1[1] = o3;
+      mbar_arrive(&full[s]);
+    } else if (tid == 0) {
+      if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+      mbar_arrive_expect_tx(&full[s], 2 * T_OPER_DOUBLES * 8);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tma_load_2d(As + c * T_CHUNK_DOUBLES, &tmA, &full[s], k0 + 4 * c, m0);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tma_load_2d(Bs + c * T_CHUNK_DOUBLES, &tmB, &full[s], k0 + 4 * c, n0);
+    }
+  };
+
+  double acc[4][8][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  for (int kt = 0; kt < T_AHEAD && kt < num_k; ++kt) produce(kt);
+
+  const int frag_r = lane >> 2;
+  const int frag_k = lane & 3;
+  const int fa_off = (wm * 32 + frag_r) * 4 + frag_k;
+  const int fb_off = (wn * 64 + frag_r) * 4 + frag_k;
+
+  for (int kt = 0; kt < num_k; ++kt) {
+    if (kt + T_AHEAD < num_k) produce(kt + T_AHEAD);
+    const int s = kt % T_STAGES;
+    mbar_wait(&full[s], (kt / T_STAGES) & 1);
+    const double* pa = stages + s * T_STAGE_DOUBLES + fa_off;
+    const double* pb = pa - fa_off + T_OPER_DOUBLES + fb_off;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      double a[4], b[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = pa[c * T_CHUNK_DOUBLES + i * 32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] = pb[c * T_CHUNK_DOUBLES + j * 32];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+  __syncthreads();  // every stage consumed, no TMA in flight: the stage buffers are free for the epilogue
+
+  // ---- epilogues ---------------------------------------------------------------------------------------------------
+  const int row_base = m0 + wm * 32 + frag_r;      // + 8 * i
+  const int col_base = n0 + wn * 64 + 2 * frag_k;  // + 8 * j + e
+  double* red = stages;                            // [4][128] scratch
+
+  if constexpr (MODE == MODE_UPPER_W) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double* crow = p.C + size_t(row_base + 8 * i) * p.ldc + col_base;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<double2*>(crow + 8 * j) = make_double2(acc[i][j][0], acc[i][j][1]);
+    }
+    return;
+  }
+
+  if constexpr (MODE == MODE_UPPER_GRAD) {
+    // T[row, col] = (dA/dmu alpha_row - 2 dA/dvar W[row, col]) * kb(z_col, Z_row), in place of the accumulators
+    double al[4];
+    uint32_t Zr[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      al[i] = p.alpha_pad[row_base + 8 * i];
+      Zr[i] = p.Zbits[row_base + 8 * i];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = col_base + 8 * j + e;
+        const bool cv_ok = col < p.ncols;
+        const double cm = cv_ok ? p.dmu[col] : 0.0;
+        const double cv = cv_ok ? -2.0 * p.dvar[col] : 0.0;
+        const uint32_t zc = p.zbits[col];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          acc[i][j][e] = fma(cv, acc[i][j][e], cm * al[i]) * tab_s[__popc(zc ^ Zr[i])];
+      }
+    // restart index of the tile's first / last column: one restart per tile is the common case (mc % 128 == 0)
+    int64_t b_lo = (p.col0 + n0) / p.mc, b_hi = (p.col0 + n0 + T_BN - 1) / p.mc;
+    if (b_lo > p.nb - 1) b_lo = p.nb - 1;
+    if (b_hi > p.nb - 1) b_hi = p.nb - 1;
+    const bool single = (b_lo == b_hi);
+    for (int c = 0; c < p.n_cont; ++c) {
+      double part[8][2];
+      if (single) {
+        const double* D = p.Dc + (size_t(b_lo) * p.n_cont + c) * p.Kp;
+        double dr[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dr[i] = (row_base + 8 * i < p.Kp) ? D[row_base + 8 * i] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s = fma(acc[i][j][e], dr[i], s);
+            part[j][e] = s;
+          }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            int64_t br = (p.col0 + col_base + 8 * j + e) / p.mc;
+            if (br > p.nb - 1) br = p.nb - 1;
+            const double* D = p.Dc + (size_t(br) * p.n_cont + c) * p.Kp;
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int row = row_base + 8 * i;
+              s = fma(acc[i][j][e], row < p.Kp ? D[row] : 0.0, s);
+            }
+            part[j][e] = s;
+          }
+      }
+      // sum over the 8 row-lanes (lane bits 2..4), then over the 4 M-warps, in a fixed order
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          double v = part[j][e];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          part[j][e] = v;
+        }
+      if (frag_r == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) red[wm * T_BN + wn * 64 + 8 * j + 2 * frag_k + e] = part[j][e];
+      }
+      __syncthreads();
+      if (tid < T_BN) {
+        const double s = ((red[tid] + red[T_BN + tid]) + red[2 * T_BN + tid]) + red[3 * T_BN + tid];
+        p.S_part[(size_t(mt) * p.n_cont + c) * p.ncols_pad + n0 + tid] = s;
+      }
+      __syncthreads();
+    }
+    return;
+  }
+
+  if constexpr (!UPPER) {
+  // lower: V^T[col, row]; 8 lanes (frag_r = 0..7) write 64 contiguous bytes per column
+  double nrm[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) nrm[j][0] = nrm[j][1] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = row_base + 8 * i;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = col_base + 8 * j + e;
+        const double v = acc[i][j][e];
+        if (p.C) p.C[size_t(col) * p.ldc + row] = v;
+        if (row == p.special_row) {
+          p.mu_dot[col] = v;
+        } else {
+          nrm[j][e] = fma(v, v, nrm[j][e]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      double v = nrm[j][e];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      nrm[j][e] = v;
+    }
+  if (frag_r == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) red[wm * T_BN + wn * 64 + 8 * j + 2 * frag_k + e] = nrm[j][e];
+  }
+  __syncthreads();
+  if (tid < T_BN) {
+    const double s = ((red[tid] + red[T_BN + tid]) + red[2 * T_BN + tid]) + red[3 * T_BN + tid];
+    p.norm_part[size_t(mt) * p.ncols_pad + n0 + tid] = s;
+  }
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+cudaError_t tma_init() {
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess) return e;
+    if (q != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(trgemm_tma_kernel<MODE_LOWER_GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                int(T_SMEM_BYTES))) != cudaSuccess)
+    return e;
+  if ((e = cudaFuncSetAttribute(trgemm_tma_kernel<MODE_LOWER_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                int(T_SMEM_BYTES))) != cudaSuccess)
+    return e;
+  if ((e = cudaFuncSetAttribute(trgemm_tma_kernel<MODE_UPPER_W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                int(T_SMEM_BYTES))) != cudaSuccess)
+    return e;
+  return cudaFuncSetAttribute(trgemm_tma_kernel<MODE_UPPER_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              int(T_SMEM_BYTES));
+}
+
+// 2-D map over a row-major [rows, ld] matrix whose contraction index is contiguous: box = 4 k values x 128 rows
+cudaError_t make_operand_map(TensorMap* out, const double* base, int rows, int k_extent, int ld) {
+  if (!g_encode) return cudaErrorNotReady;
+  cuuint64_t gdim[2] = {cuuint64_t(k_extent), cuuint64_t(rows)};
+  cuuint64_t gstride[1] = {cuuint64_t(ld) * sizeof(double)};
+  cuuint32_t box[2] = {4, cuuint32_t(T_BM)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2,
+                        const_cast<double*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+static void fill_common(TmaGemmParams& p, const Model& m, int ncols_pad, bool upper) {
+  memset(&p, 0, sizeof(p));
+  p.mtiles = (upper ? m.Mp2 : m.Mp1) / T_BM;
+  p.ntiles = ncols_pad / T_BN;
+  p.Kp = m.Kp;
+  p.ncols_pad = ncols_pad;
+  p.special_row = upper ? -1 : m.n;
+}
+
+static void fill_sep(TmaGemmParams& p, const Model& m, const SepArgs& sa) {
+  p.kc = sa.kc;
+  p.Zbits = m.Zbits;
+  p.zbits = sa.zbits;
+  p.tab = m.sep_tab;
+  p.ntab = m.sep_nbits;
+  p.mc = sa.mc;
+  p.col0 = sa.col0;
+  p.nb = sa.nb;
+  p.Dc = sa.Dc;
+  p.n_cont = sa.n_cont;
+  p.alpha_pad = m.alpha_pad;
+}
+
+cudaError_t launch_tma_lower_gen(const Model& m, const SepArgs& sa, int ncols_pad, double* VT, double* norm_part,
+                                 double* mu_dot, cudaStream_t st) {
+  ProfScope prof_(K_TRGEMM_LOWER, st);
+  TmaGemmParams p;
+  fill_common(p, m, ncols_pad, false);
+  fill_sep(p, m, sa);
+  p.C = VT;
+  p.ldc = m.Mp1;
+  p.norm_part = norm_part;
+  p.mu_dot = mu_dot;
+  trgemm_tma_kernel<MODE_LOWER_GEN><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(
+      *reinterpret_cast<const CUtensorMap*>(&m.mapA1), *reinterpret_cast<const CUtensorMap*>(&m.mapA1), p);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tma_lower(const Model& m, const TensorMap& mapB, int ncols_pad, double* VT, double* norm_part,
+                             double* mu_dot, cudaStream_t st) {
+  ProfScope prof_(K_TRGEMM_LOWER, st);
+  TmaGemmParams p;
+  fill_common(p, m, ncols_pad, false);
+  p.C = VT;
+  p.ldc = m.Mp1;
+  p.norm_part = norm_part;
+  p.mu_dot = mu_dot;
+  trgemm_tma_kernel<MODE_LOWER_TMA><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(
+      *reinterpret_cast<const CUtensorMap*>(&m.mapA1), *reinterpret_cast<const CUtensorMap*>(&mapB), p);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tma_upper(const Model& m, const TensorMap& mapB, int ncols_pad, double* W, cudaStream_t st) {
+  ProfScope prof_(K_TRGEMM_UPPER, st);
+  TmaGemmParams p;
+  fill_common(p, m, ncols_pad, true);
+  p.C = W;
+  p.ldc = ncols_pad;
+  trgemm_tma_kernel<MODE_UPPER_W><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(
+      *reinterpret_cast<const CUtensorMap*>(&m.mapA2), *reinterpret_cast<const CUtensorMap*>(&mapB), p);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tma_upper_grad(const Model& m, const TensorMap& mapB, const SepArgs& sa, int ncols, int ncols_pad,
+                                  const double* dmu, const double* dvar, double* S_part, cudaStream_t st) {
+  ProfScope prof_(K_TRGEMM_UPPER, st);
+  TmaGemmParams p;
+  fill_common(p, m, ncols_pad, true);
+  fill_sep(p, m, sa);
+  p.dmu = dmu;
+  p.dvar = dvar;
+  p.ncols = ncols;
+  p.S_part = S_part;
+  trgemm_tma_kernel<MODE_UPPER_GRAD><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(
+      *reinterpret_cast<const CUtensorMap*>(&m.mapA2), *reinterpret_cast<const CUtensorMap*>(&mapB), p);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace prb

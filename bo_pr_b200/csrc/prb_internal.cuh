@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "prb200.h"
 
@@ -79,6 +80,29 @@ struct ProfScope {  // no-op unless profiling is enabled; never use while the st
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 inline int64_t round_up64(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
+// opaque 128-byte TMA descriptor (CUtensorMap) so that only prb_gemm_tma.cu needs <cuda.h>
+struct alignas(64) TensorMap {
+  unsigned char bytes[128];
+};
+
+// per-call arguments of the separable fast path (operand generation + fused gradient epilogue)
+struct SepArgs {
+  const double* kc;       // [nb, Kp]
+  const double* Dc;       // [nb, n_cont, Kp]
+  const uint32_t* zbits;  // panel-local [ncols_pad]
+  int n_cont, mc, nb;
+  int64_t col0;
+};
+
+struct BitMap {  // integer parameter k of the PR space -> bit position in the binary-factor code (-1: not a binary dim)
+  int32_t pos[PRB_MAX_DIMS];
+};
+
+struct DimMap {  // S_part slot -> kernel-input column
+  int32_t n;
+  int32_t dims[PRB_MAX_DIMS];
+};
+
 struct Model {
   int n, d_k;
   int Kp;        // round_up(n, 16): padded contraction length / leading dimension of the eval-major panels
@@ -92,6 +116,15 @@ struct Model {
   double kss;    // k(x, x)
   DevSpec spec;
   int device;
+  // ---- second-generation engine (TMA operands) ----
+  TensorMap mapA1, mapA2;
+  double* alpha_pad;  // [max(Mp1, Mp2)] alpha, zero padded
+  // separable structure: one term = Matern52(continuous dims) x isotropic Matern52(binary dims), binary training columns
+  int sep_ok;
+  int sep_cont_factor, sep_bin_factor;  // indices into spec.t[0].f
+  int sep_nbits;                        // number of binary dims (<= 32)
+  uint32_t* Zbits;                      // [max(Mp1, Mp2)] bit codes of the training points
+  double* sep_tab;                      // [64] binary-factor value by Hamming distance
 };
 
 // launchers (prb_gemm.cu / prb_kernels.cu); all enqueue on `st` and return the CUDA status
@@ -99,5 +132,16 @@ cudaError_t launch_trgemm_lower(const Model& m, const double* KstarT, int ncols_
                                 double* mu_dot, cudaStream_t st);
 cudaError_t launch_trgemm_upper(const Model& m, const double* VT, int ncols_pad, double* W, cudaStream_t st);
 cudaError_t gemm_init();
+
+// prb_gemm_tma.cu
+cudaError_t tma_init();
+cudaError_t make_operand_map(TensorMap* out, const double* base, int rows, int k_extent, int ld);
+cudaError_t launch_tma_lower_gen(const Model& m, const SepArgs& sa, int ncols_pad, double* VT, double* norm_part,
+                                 double* mu_dot, cudaStream_t st);
+cudaError_t launch_tma_lower(const Model& m, const TensorMap& mapB, int ncols_pad, double* VT, double* norm_part,
+                             double* mu_dot, cudaStream_t st);
+cudaError_t launch_tma_upper(const Model& m, const TensorMap& mapB, int ncols_pad, double* W, cudaStream_t st);
+cudaError_t launch_tma_upper_grad(const Model& m, const TensorMap& mapB, const SepArgs& sa, int ncols, int ncols_pad,
+                                  const double* dmu, const double* dvar, double* S_part, cudaStream_t st);
 
 }  // namespace prb

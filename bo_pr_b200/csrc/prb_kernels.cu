@@ -34,7 +34,8 @@ cudaError_t launch_philox_fill(uint64_t seed, uint64_t offset, int mc, int n_col
 __global__ void pr_sample_kernel(const DevSpace sp, const double* __restrict__ theta, int b, int mc,
                                  const double* __restrict__ u_int, const double* __restrict__ u_cat, uint64_t seed,
                                  uint64_t offset, double* __restrict__ xk, double* __restrict__ tilde,
-                                 uint8_t* __restrict__ zout, double* __restrict__ prob) {
+                                 uint8_t* __restrict__ zout, double* __restrict__ prob, const BitMap bm,
+                                 uint32_t* __restrict__ zbits) {
   const int64_t col = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (col >= int64_t(b) * mc) return;
   const int bi = int(col / mc);
@@ -51,6 +52,7 @@ __global__ void pr_sample_kernel(const DevSpace sp, const double* __restrict__ t
     if (tr) tr[c] = v;
     if (xr && (!sp.apply_numeric || c < numeric_start)) xr[c] = v;
   }
+  uint32_t bits = 0;
   // ---- integers (input.py:674-692)
   for (int k = 0; k < sp.n_int; ++k) {
     const int c = sp.int_cols[k];
@@ -70,7 +72,9 @@ __global__ void pr_sample_kernel(const DevSpace sp, const double* __restrict__ t
     if (xr) xr[c] = tn;
     if (zr) zr[k] = ((__dsub_rn(tn, x) > 0.0) || (x == 1.0)) ? 1 : 0;
     if (pr) pr[k] = p;
+    if (bm.pos[k] >= 0 && tn != 0.0) bits |= 1u << bm.pos[k];
   }
+  if (zbits) zbits[col] = bits;
   // ---- categoricals (input.py:715-744): softmax((x - 0.5)/tau), sequential cumsum, first index with cum > u (else 0)
   int zpos = sp.n_int;
   for (int j = 0; j < sp.n_cat; ++j) {
@@ -114,12 +118,14 @@ __global__ void pr_sample_kernel(const DevSpace sp, const double* __restrict__ t
 
 cudaError_t launch_pr_sample(const DevSpace& sp, const double* theta, int b, int mc, const double* u_int,
                              const double* u_cat, uint64_t seed, uint64_t offset, double* xk, double* tilde,
-                             uint8_t* z, double* prob, cudaStream_t st) {
+                             uint8_t* z, double* prob, const BitMap* bm, uint32_t* zbits, cudaStream_t st) {
   ProfScope prof_(K_SAMPLE, st);
   const int64_t total = int64_t(b) * mc;
   if (total == 0) return cudaSuccess;
+  BitMap none;
+  for (int k = 0; k < PRB_MAX_DIMS; ++k) none.pos[k] = -1;
   pr_sample_kernel<<<unsigned((total + 127) / 128), 128, 0, st>>>(sp, theta, b, mc, u_int, u_cat, seed, offset, xk,
-                                                                 tilde, z, prob);
+                                                                 tilde, z, prob, bm ? *bm : none, bm ? zbits : nullptr);
   count_launch();
   return cudaGetLastError();
 }
@@ -275,6 +281,98 @@ cudaError_t launch_kernel_matrix(const DevSpec& spec, const double* Xtr, int n, 
   dim3 grid((n + KS_ROWS - 1) / KS_ROWS, (n_points + KS_COLS - 1) / KS_COLS);
   const size_t smem = size_t(spec.d_k) * (KS_ROWS + KS_COLS) * sizeof(double);
   kstar_panel_kernel<<<grid, KS_ROWS, smem, st>>>(spec, Xtr, n, n, xk, n_points, n_points, out);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// =====================================================================================================================
+// Separable structure ("mixed" kernel of kernels.py:39-63, 85-89 with binary integer dims):
+//   k*(x, X_j) = [s * M52_ARD(x_c, X_jc)] * M52_iso(Hamming(z, Z_j))  -- the second factor takes nbits + 1 distinct values.
+// Model side (once per GP state): bit codes of the training points, the Hamming table, and a check that the binary
+// columns of X_train really are {0, 1}.  Call side (once per step): kc[b, j] and Dc[b, c, j] per restart.
+// =====================================================================================================================
+__global__ void sep_model_prep_kernel(const DevFactor fb, const double* __restrict__ Xtr, int n, int d_k, int n_pad,
+                                      uint32_t* __restrict__ Zbits, double* __restrict__ tab, int* __restrict__ bad) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n_pad) {
+    uint32_t bits = 0;
+    if (j < n) {
+      for (int di = 0; di < fb.n_dims; ++di) {
+        const double v = Xtr[size_t(j) * d_k + fb.dims[di]];
+        if (v != 0.0 && v != 1.0) atomicExch(bad, 1);
+        if (v != 0.0) bits |= 1u << di;
+      }
+    }
+    Zbits[j] = bits;
+  }
+  if (j < 64) {
+    // same accumulation order as the generic kernel evaluation: r2 = fma(df, df, r2) with df = +-1/l per differing dim
+    double r2 = 0.0;
+    const double il = fb.inv_ls[0];
+    for (int h = 0; h < j && h < fb.n_dims; ++h) r2 = fma(il, il, r2);
+    tab[j] = (j <= fb.n_dims) ? matern52_value(r2) : 0.0;
+  }
+}
+
+cudaError_t launch_sep_model_prep(const Model& m, int n_pad, int* bad_flag, cudaStream_t st) {
+  ProfScope prof_(K_MISC, st);
+  const DevFactor& fb = m.spec.t[0].f[m.sep_bin_factor];
+  const int threads = 128;
+  const int blocks = (max(n_pad, 64) + threads - 1) / threads;
+  sep_model_prep_kernel<<<blocks, threads, 0, st>>>(fb, m.Xtr, m.n, m.d_k, n_pad, m.Zbits, m.sep_tab, bad_flag);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// grid (ceil(Kp / 128), nb): thread <-> training point j, block row <-> restart
+__global__ void sep_restart_prep_kernel(const DevFactor fc, double outputscale, const double* __restrict__ Xtr, int n,
+                                        int d_k, int Kp, const double* __restrict__ theta, int d_theta,
+                                        double* __restrict__ kc, double* __restrict__ Dc) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (j >= Kp) return;
+  const double* th = theta + size_t(b) * d_theta;
+  double val = 0.0, G = 0.0;
+  if (j < n) {
+    double r2 = 0.0;
+    for (int di = 0; di < fc.n_dims; ++di) {
+      const int dim = fc.dims[di];
+      const double df = (th[dim] - Xtr[size_t(j) * d_k + dim]) * fc.inv_ls[di];
+      r2 = fma(df, df, r2);
+    }
+    val = outputscale * matern52(r2, &G);
+  }
+  kc[size_t(b) * Kp + j] = val;
+  if (Dc) {
+    for (int di = 0; di < fc.n_dims; ++di) {
+      const int dim = fc.dims[di];
+      double v = 0.0;
+      if (j < n) v = outputscale * G * (fc.inv_ls[di] * fc.inv_ls[di]) * (th[dim] - Xtr[size_t(j) * d_k + dim]);
+      Dc[(size_t(b) * fc.n_dims + di) * Kp + j] = v;
+    }
+  }
+}
+
+cudaError_t launch_sep_restart_prep(const Model& m, const double* theta, int nb, int d_theta, double* kc, double* Dc,
+                                    cudaStream_t st) {
+  ProfScope prof_(K_KSTAR, st);
+  if (nb == 0) return cudaSuccess;
+  const DevFactor& fc = m.spec.t[0].f[m.sep_cont_factor];
+  dim3 grid((m.Kp + 127) / 128, nb);
+  sep_restart_prep_kernel<<<grid, 128, 0, st>>>(fc, m.spec.t[0].outputscale, m.Xtr, m.n, m.d_k, m.Kp, theta, d_theta, kc,
+                                               Dc);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// alpha zero-padded to n_pad entries
+__global__ void pad_copy_kernel(const double* __restrict__ src, int n, int n_pad, double* __restrict__ dst) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n_pad) dst[j] = j < n ? src[j] : 0.0;
+}
+cudaError_t launch_pad_copy(const double* src, int n, int n_pad, double* dst, cudaStream_t st) {
+  ProfScope prof_(K_MISC, st);
+  pad_copy_kernel<<<(n_pad + 127) / 128, 128, 0, st>>>(src, n, n_pad, dst);
   count_launch();
   return cudaGetLastError();
 }
@@ -446,6 +544,10 @@ cudaError_t launch_grad_contract(const Model& m, uint32_t diffmask, const double
   ProfScope prof_(K_GRAD_CONTRACT, st);
   dim3 grid(ncols_pad / GR_COLS, m.Mp2 / GRAD_JSPLIT_ROWS);
   const size_t smem = (size_t(m.d_k) * (2 * GR_COLS + GRAD_JSPLIT_ROWS) + GRAD_JSPLIT_ROWS) * sizeof(double);
+  if (smem > 48 * 1024) {  // d_k > 15: opt in to a larger dynamic shared-memory window (at most 99 KB at d_k = 32)
+    cudaError_t e = cudaFuncSetAttribute(grad_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+  }
   grad_contract_kernel<<<grid, GR_COLS, smem, st>>>(m.spec, diffmask, m.Xtr, m.alpha, m.n, xk, ncols, ncols_pad, W,
                                                     dmu, dvar, S_part);
   count_launch();
@@ -453,23 +555,26 @@ cudaError_t launch_grad_contract(const Model& m, uint32_t diffmask, const double
 }
 
 // S_all[col_global, dim] = sum_jblock S_part[jblock][dim][col]   (fixed order)
-__global__ void sum_splits_kernel(const double* __restrict__ S_part, int jblocks, int d_k, int ncols, int ncols_pad,
-                                  double* __restrict__ S_all) {
+__global__ void sum_splits_kernel(const double* __restrict__ S_part, int jblocks, const DimMap dm, int d_k, int ncols,
+                                  int ncols_pad, double* __restrict__ S_all) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= ncols) return;
-  for (int dd = 0; dd < d_k; ++dd) {
+  for (int dd = 0; dd < dm.n; ++dd) {
     double s = 0.0;
-    for (int jb = 0; jb < jblocks; ++jb) s += S_part[(size_t(jb) * d_k + dd) * ncols_pad + col];
-    S_all[size_t(col) * d_k + dd] = s;
+    for (int jb = 0; jb < jblocks; ++jb) s += S_part[(size_t(jb) * dm.n + dd) * ncols_pad + col];
+    S_all[size_t(col) * d_k + dm.dims[dd]] = s;
   }
 }
 
-cudaError_t launch_sum_splits(const Model& m, const double* S_part, int ncols, int ncols_pad, double* S_all,
-                              cudaStream_t st) {
+cudaError_t launch_sum_splits(const Model& m, const double* S_part, const DimMap* dm, int ncols, int ncols_pad,
+                              double* S_all, cudaStream_t st) {
   ProfScope prof_(K_SUM_SPLITS, st);
   if (ncols == 0) return cudaSuccess;
-  sum_splits_kernel<<<(ncols + 127) / 128, 128, 0, st>>>(S_part, m.Mp2 / GRAD_JSPLIT_ROWS, m.d_k, ncols, ncols_pad,
-                                                         S_all);
+  DimMap ident;
+  ident.n = m.d_k;
+  for (int i = 0; i < PRB_MAX_DIMS; ++i) ident.dims[i] = i;
+  sum_splits_kernel<<<(ncols + 127) / 128, 128, 0, st>>>(S_part, m.Mp2 / GRAD_JSPLIT_ROWS, dm ? *dm : ident, m.d_k,
+                                                         ncols, ncols_pad, S_all);
   count_launch();
   return cudaGetLastError();
 }

@@ -8,7 +8,11 @@ namespace prb {
 cudaError_t launch_philox_fill(uint64_t seed, uint64_t offset, int mc, int n_cols, double* out, cudaStream_t st);
 cudaError_t launch_pr_sample(const DevSpace& sp, const double* theta, int b, int mc, const double* u_int,
                              const double* u_cat, uint64_t seed, uint64_t offset, double* xk, double* tilde,
-                             uint8_t* z, double* prob, cudaStream_t st);
+                             uint8_t* z, double* prob, const BitMap* bm, uint32_t* zbits, cudaStream_t st);
+cudaError_t launch_sep_model_prep(const Model& m, int n_pad, int* bad_flag, cudaStream_t st);
+cudaError_t launch_sep_restart_prep(const Model& m, const double* theta, int nb, int d_theta, double* kc, double* Dc,
+                                    cudaStream_t st);
+cudaError_t launch_pad_copy(const double* src, int n, int n_pad, double* dst, cudaStream_t st);
 cudaError_t launch_analytic_build(const DevSpace& sp, const double* theta, int b, int n_opt, const int32_t* options,
                                   double* xk, double* probs, cudaStream_t st);
 cudaError_t launch_kstar_panel(const Model& m, const double* xk, int ncols, int ncols_pad, double* KstarT,
@@ -21,8 +25,8 @@ cudaError_t launch_acq_epilogue(const Model& m, const DevAcq& aq, const double* 
 cudaError_t launch_grad_contract(const Model& m, uint32_t diffmask, const double* xk, int ncols, int ncols_pad,
                                  const double* W, const double* dmu, const double* dvar, double* S_part,
                                  cudaStream_t st);
-cudaError_t launch_sum_splits(const Model& m, const double* S_part, int ncols, int ncols_pad, double* S_all,
-                              cudaStream_t st);
+cudaError_t launch_sum_splits(const Model& m, const double* S_part, const DimMap* dm, int ncols, int ncols_pad,
+                              double* S_all, cudaStream_t st);
 cudaError_t launch_mc_reduce(const DevSpace& sp, int b, int mc, const double* a, const uint8_t* z, const double* prob,
                              const double* S_all, int estimator, const double* ma_state, const double* grad_out,
                              double* out_value, double* out_grad, cudaStream_t st);

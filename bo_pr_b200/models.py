@@ -88,8 +88,9 @@ class GPState:
                 pass
             self.handle = None
 
-    def workspace(self, n_points: int, d_theta: int) -> Tensor:
-        need = int(self.lib.prb_workspace_bytes(self.handle, int(n_points), int(d_theta), int(self.chunk_cols)))
+    def workspace(self, n_points: int, d_theta: int, n_restarts: int = 0) -> Tensor:
+        need = int(self.lib.prb_workspace_bytes(self.handle, int(n_points), int(n_restarts), int(d_theta),
+                                                int(self.chunk_cols)))
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws

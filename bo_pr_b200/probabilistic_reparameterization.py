@@ -198,7 +198,7 @@ class _AnalyticPRFunction(Function):
         value = torch.empty(b, dtype=torch.float64, device=X.device)
         grad = torch.empty(b, d, dtype=torch.float64, device=X.device) if need else None
         ones = torch.ones(b, dtype=torch.float64, device=X.device) if need else None
-        ws = state.workspace(b * n_opt, d)
+        ws = state.workspace(b * n_opt, d, b)
         sp, aq = module._space(), acq_desc_of(module.acq_function)
         with torch.cuda.device(X.device):
             st = torch.cuda.current_stream().cuda_stream
@@ -330,7 +330,7 @@ class _MCProbabilisticReparameterization(Function):
         value = torch.empty(b, dtype=torch.float64, device=X.device)
         grad = torch.empty(b, d, dtype=torch.float64, device=X.device) if need else None
         ones = torch.ones(b, dtype=torch.float64, device=X.device) if need else None
-        ws = state.workspace(b * mc, d)
+        ws = state.workspace(b * mc, d, b)
         est = capi.PRB_EST_REINFORCE_MA if grad_estimator == "reinforce_ma" else capi.PRB_EST_REINFORCE
         with torch.cuda.device(X.device):
             st = torch.cuda.current_stream().cuda_stream

@@ -138,9 +138,10 @@ int prb_model_destroy(prb_model* model);
 int prb_model_n(const prb_model* model);
 int prb_model_dk(const prb_model* model);
 
-/* Bytes of scratch needed to evaluate `n_points` (= b*mc, or b*n_discrete) base-AF points with this model.
- * `chunk_cols` = 0 picks the default L2-resident panel width.                                                      */
-size_t prb_workspace_bytes(const prb_model* model, int64_t n_points, int32_t d_theta, int32_t chunk_cols);
+/* Bytes of scratch needed to evaluate `n_points` (= b*mc, or b*n_discrete) base-AF points with this model, coming from
+ * `n_restarts` = b rows of theta (0 for prb_acq_points).  `chunk_cols` = 0 picks the default L2-resident panel width. */
+size_t prb_workspace_bytes(const prb_model* model, int64_t n_points, int32_t n_restarts, int32_t d_theta,
+                           int32_t chunk_cols);
 
 /* Counter-based Philox4x32-10 uniforms in [0,1): out[i, c] for i < mc, c < n_cols, 53-bit mantissa,
  * counter = (i, c, offset_lo, offset_hi), key = (seed_lo, seed_hi).  The fused sampler draws the same stream

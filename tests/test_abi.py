@@ -51,7 +51,7 @@ def test_argument_validation_without_device(lib):
     assert lib.prb_pr_sample(C.byref(sp), None, 1, 1, None, None, 0, 0, None, None, None, None) == -1
     sp.d = 1000
     assert lib.prb_pr_sample(C.byref(sp), None, 1, 1, None, None, 0, 0, None, None, None, None) == -2
-    assert lib.prb_workspace_bytes(None, 10, 3, 0) == 0
+    assert lib.prb_workspace_bytes(None, 10, 1, 3, 0) == 0
     assert lib.prb_mc_value_grad(None, None, None, None, 1, 1, None, None, 0, 0, 0, None, 0, None, None, None, None, None,
                                  0, 0, None) == -1
 

@@ -152,7 +152,7 @@ def test_mc_pr_per_sample_values(name):
     sp, aq = pr._space(), acq_desc_of(pr.acq_function)
     value = torch.empty(b, dtype=torch.float64, device=DEV)
     av = torch.empty(b, mc, dtype=torch.float64, device=DEV)
-    ws = st.workspace(b * mc, d)
+    ws = st.workspace(b * mc, d, b)
     th = X.reshape(b, d).contiguous()
     rc = st.lib.prb_mc_value_grad(st.handle, C.byref(sp), C.byref(aq), th.data_ptr(), b, mc,
                                   None if ui is None else ui.data_ptr(), None if uc is None else uc.data_ptr(), 0, 0,
