@@ -163,48 +163,58 @@ __global__ void __launch_bounds__(T_THREADS, 1)
     g_kc = p.kc + size_t(br) * p.Kp;
   }
 
-  auto produce = [&](int kt) {
+  // TMA side of a k-tile (one elected thread): A always, B unless it is generated
+  auto produce_tma = [&](int kt) {
+    if (tid != 0) return;
     const int s = kt % T_STAGES;
     const int use = kt / T_STAGES;
     const int k0 = kbeg + kt * T_BK;
     double* As = stages + s * T_STAGE_DOUBLES;
     double* Bs = As + T_OPER_DOUBLES;
-    if (GEN) {
-      // global operands first (latency overlaps the wait below)
-      const double2* kc2 = reinterpret_cast<const double2*>(g_kc + k0 + ghalf * 8);
-      const uint4* zz = reinterpret_cast<const uint4*>(p.Zbits + k0 + ghalf * 8);
-      const double2 k01 = __ldg(kc2), k23 = __ldg(kc2 + 1), k45 = __ldg(kc2 + 2), k67 = __ldg(kc2 + 3);
-      const uint4 za = __ldg(zz), zc = __ldg(zz + 1);
-      if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
-      if (tid == 0) {
-        mbar_arrive_expect_tx(&full[s], T_OPER_DOUBLES * 8);
+    if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+    mbar_arrive_expect_tx(&full[s], (GEN ? 1 : 2) * T_OPER_DOUBLES * 8);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tma_load_2d(As + c * T_CHUNK_DOUBLES, &tmA, &full[s], k0 + 4 * c, m0);
-      }
-      double2 o0, o1, o2, o3;
-      o0.x = k01.x * tab_s[__popc(g_zb ^ za.x)];
-      o0.y = k01.y * tab_s[__popc(g_zb ^ za.y)];
-      o1.x = k23.x * tab_s[__popc(g_zb ^ za.z)];
-      o1.y = k23.y * tab_s[__popc(g_zb ^ za.w)];
-      o2.x = k45.x * tab_s[__popc(g_zb ^ zc.x)];
-      o2.y = k45.y * tab_s[__popc(g_zb ^ zc.y)];
-      o3.x = k67.x * tab_s[__popc(g_zb ^ zc.z)];
-      o3.y = k67.y * tab_s[__popc(g_zb ^ zc.w)];
-      double2* d0 = reinterpret_cast<double2*>(Bs + (2 * ghalf) * T_CHUNK_DOUBLES + gcol * 4);
-      double2* d1 = reinterpret_cast<double2*>(Bs + (2 * ghalf + 1) * T_CHUNK_DOUBLES + gcol * 4);
-      d0[0] = o0;
-      d0[1] = o1;
-      d1[0] = o2;
-      d1[1] = o3;
-      mbar_arrive(&full[s]);
-    } else if (tid == 0) {
-      if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
-      mbar_arrive_expect_tx(&full[s], 2 * T_OPER_DOUBLES * 8);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tma_load_2d(As + c * T_CHUNK_DOUBLES, &tmA, &full[s], k0 + 4 * c, m0);
+    for (int c = 0; c < 4; ++c) tma_load_2d(As + c * T_CHUNK_DOUBLES, &tmA, &full[s], k0 + 4 * c, m0);
+    if (!GEN) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) tma_load_2d(Bs + c * T_CHUNK_DOUBLES, &tmB, &full[s], k0 + 4 * c, n0);
     }
+  };
+  // generated B operand: global loads are issued a whole k-tile of DMMA work before they are consumed
+  double2 g_k01, g_k23, g_k45, g_k67;
+  uint4 g_za, g_zc;
+  auto gen_load = [&](int kt) {
+    const int k0 = kbeg + kt * T_BK;
+    const double2* kc2 = reinterpret_cast<const double2*>(g_kc + k0 + ghalf * 8);
+    const uint4* zz = reinterpret_cast<const uint4*>(p.Zbits + k0 + ghalf * 8);
+    g_k01 = __ldg(kc2);
+    g_k23 = __ldg(kc2 + 1);
+    g_k45 = __ldg(kc2 + 2);
+    g_k67 = __ldg(kc2 + 3);
+    g_za = __ldg(zz);
+    g_zc = __ldg(zz + 1);
+  };
+  auto gen_store = [&](int kt) {
+    const int s = kt % T_STAGES;
+    const int use = kt / T_STAGES;
+    double* Bs = stages + s * T_STAGE_DOUBLES + T_OPER_DOUBLES;
+    if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+    double2 o0, o1, o2, o3;
+    o0.x = g_k01.x * tab_s[__popc(g_zb ^ g_za.x)];
+    o0.y = g_k01.y * tab_s[__popc(g_zb ^ g_za.y)];
+    o1.x = g_k23.x * tab_s[__popc(g_zb ^ g_za.z)];
+    o1.y = g_k23.y * tab_s[__popc(g_zb ^ g_za.w)];
+    o2.x = g_k45.x * tab_s[__popc(g_zb ^ g_zc.x)];
+    o2.y = g_k45.y * tab_s[__popc(g_zb ^ g_zc.y)];
+    o3.x = g_k67.x * tab_s[__popc(g_zb ^ g_zc.z)];
+    o3.y = g_k67.y * tab_s[__popc(g_zb ^ g_zc.w)];
+    double2* d0 = reinterpret_cast<double2*>(Bs + (2 * ghalf) * T_CHUNK_DOUBLES + gcol * 4);
+    double2* d1 = reinterpret_cast<double2*>(Bs + (2 * ghalf + 1) * T_CHUNK_DOUBLES + gcol * 4);
+    d0[0] = o0;
+    d0[1] = o1;
+    d1[0] = o2;
+    d1[1] = o3;
+    mbar_arrive(&full[s]);
   };
 
   double acc[4][8][2];
@@ -213,45 +223,96 @@ __global__ void __launch_bounds__(T_THREADS, 1)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  for (int kt = 0; kt < T_AHEAD && kt < num_k; ++kt) produce(kt);
+  for (int kt = 0; kt < T_AHEAD && kt < num_k; ++kt) {
+    produce_tma(kt);
+    if (GEN) {
+      gen_load(kt);
+      gen_store(kt);
+    }
+  }
 
+  // Row ownership: M-warp wm owns the 8-row groups {wm, 7 - wm, 8 + wm, 15 - wm} of the tile, so that the triangular work
+  // inside a diagonal block (where whole 8 x 4 sub-blocks of A are zero and their DMMAs are skipped) is split evenly.
   const int frag_r = lane >> 2;
   const int frag_k = lane & 3;
-  const int fa_off = (wm * 32 + frag_r) * 4 + frag_k;
+  int grp[4];
+  grp[0] = wm;
+  grp[1] = 7 - wm;
+  grp[2] = 8 + wm;
+  grp[3] = 15 - wm;
+  int fa_off[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) fa_off[i] = (8 * grp[i] + frag_r) * 4 + frag_k;
   const int fb_off = (wn * 64 + frag_r) * 4 + frag_k;
 
   for (int kt = 0; kt < num_k; ++kt) {
-    if (kt + T_AHEAD < num_k) produce(kt + T_AHEAD);
+    const int nk = kt + T_AHEAD;
+    if (nk < num_k) {
+      produce_tma(nk);
+      if (GEN) gen_load(nk);
+    }
     const int s = kt % T_STAGES;
     mbar_wait(&full[s], (kt / T_STAGES) & 1);
-    const double* pa = stages + s * T_STAGE_DOUBLES + fa_off;
-    const double* pb = pa - fa_off + T_OPER_DOUBLES + fb_off;
+    const double* pa = stages + s * T_STAGE_DOUBLES;
+    const double* pb = pa + T_OPER_DOUBLES + fb_off;
+    const int q0 = kbeg + kt * T_BK - m0;  // offset of this k-tile inside the tile's diagonal block
+    if (q0 < 0 || q0 >= T_BM) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      double a[4], b[8];
+      for (int c = 0; c < 4; ++c) {
+        double a[4], b[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = pa[c * T_CHUNK_DOUBLES + i * 32];
+        for (int i = 0; i < 4; ++i) a[i] = pa[c * T_CHUNK_DOUBLES + fa_off[i]];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) b[j] = pb[c * T_CHUNK_DOUBLES + j * 32];
+        for (int j = 0; j < 8; ++j) b[j] = pb[c * T_CHUNK_DOUBLES + j * 32];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+          for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+    } else {
+      // diagonal block: sub-block (8 rows of group g) x (4 k values at offset q) of A is all zero when
+      //   lower (k <= row):  q > 8 g + 7          upper (k >= row):  q + 3 < 8 g
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int q = q0 + 4 * c;
+        bool act[4];
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          act[i] = UPPER ? (q + 3 >= 8 * grp[i]) : (q <= 8 * grp[i] + 7);
+          any = any || act[i];
+        }
+        if (!any) continue;
+        double b[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b[j] = pb[c * T_CHUNK_DOUBLES + j * 32];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (act[i]) {
+            const double a = pa[c * T_CHUNK_DOUBLES + fa_off[i]];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a, b[j]);
+          }
+        }
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
+    if (GEN && nk < num_k) gen_store(nk);
   }
   __syncthreads();  // every stage consumed, no TMA in flight: the stage buffers are free for the epilogue
 
   // ---- epilogues ---------------------------------------------------------------------------------------------------
-  const int row_base = m0 + wm * 32 + frag_r;      // + 8 * i
+  int rows[4];  // global row of accumulator sub-tile i for this lane
+#pragma unroll
+  for (int i = 0; i < 4; ++i) rows[i] = m0 + 8 * grp[i] + frag_r;
   const int col_base = n0 + wn * 64 + 2 * frag_k;  // + 8 * j + e
   double* red = stages;                            // [4][128] scratch
 
   if constexpr (MODE == MODE_UPPER_W) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      double* crow = p.C + size_t(row_base + 8 * i) * p.ldc + col_base;
+      double* crow = p.C + size_t(rows[i]) * p.ldc + col_base;
 #pragma unroll
       for (int j = 0; j < 8; ++j) *reinterpret_cast<double2*>(crow + 8 * j) = make_double2(acc[i][j][0], acc[i][j][1]);
     }
@@ -264,8 +325,8 @@ __global__ void __launch_bounds__(T_THREADS, 1)
     uint32_t Zr[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      al[i] = p.alpha_pad[row_base + 8 * i];
-      Zr[i] = p.Zbits[row_base + 8 * i];
+      al[i] = p.alpha_pad[rows[i]];
+      Zr[i] = p.Zbits[rows[i]];
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -291,7 +352,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
         const double* D = p.Dc + (size_t(b_lo) * p.n_cont + c) * p.Kp;
         double dr[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) dr[i] = (row_base + 8 * i < p.Kp) ? D[row_base + 8 * i] : 0.0;
+        for (int i = 0; i < 4; ++i) dr[i] = (rows[i] < p.Kp) ? D[rows[i]] : 0.0;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
 #pragma unroll
@@ -312,7 +373,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
             double s = 0.0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const int row = row_base + 8 * i;
+              const int row = rows[i];
               s = fma(acc[i][j][e], row < p.Kp ? D[row] : 0.0, s);
             }
             part[j][e] = s;
@@ -352,7 +413,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
   for (int j = 0; j < 8; ++j) nrm[j][0] = nrm[j][1] = 0.0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int row = row_base + 8 * i;
+    const int row = rows[i];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
 #pragma unroll
