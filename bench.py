@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--cpu-restarts", type=int, default=8, help="restarts in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-bo-iter", action="store_true")
     return ap.parse_args()
 
 
@@ -126,6 +127,85 @@ def run_reference(a):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Second metric of BASELINE.json: seconds per BO iteration on ackley13 pr__ei -- the AF-optimisation segment the reference
+# runs at run_one_replication.py:494-528 (1024 raw samples screened in chunks of 32, 20 restarts x 200 Adam steps in
+# batches of 5, candidate sampling, re-scoring with the base EI, argmax), GP fit excluded, at the end-of-run size n = 119.
+# ---------------------------------------------------------------------------------------------------------------------
+BO_OPTS = {"batch_limit": 5, "init_batch_limit": 32, "maxiter": 200, "nonnegative": True}
+
+
+def bo_iter_problem():
+    from bench_workload import make_problem, sobol_base_samples
+    g = make_problem(119, seed=5)
+    g["case"].update(mc=128, grad_estimator="reinforce_ma")
+    g["base_samples"] = sobol_base_samples(128)
+    g["base_samples_categorical"] = None
+    return g
+
+
+def bo_iter_ours(dev, one_batch=False, repeats=3):
+    import bo_pr_b200 as B
+    from tests.product_util import product_acq, product_mc_pr
+    g = bo_iter_problem()
+    acq = product_acq(g, dev)
+    bounds = torch.stack([torch.zeros(13, dtype=torch.float64), torch.ones(13, dtype=torch.float64)]).to(dev)
+    times = []
+    for rep in range(repeats + 1):
+        pr = product_mc_pr(g, dev, acq=acq)  # a fresh AF object per BO iteration, as the reference builds one
+        opts = dict(BO_OPTS, seed=rep)
+        if one_batch:
+            opts.pop("batch_limit")
+            opts.pop("init_batch_limit")
+        torch.manual_seed(rep)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        cand, vals = B.optimize_acqf(pr, bounds, q=1, num_restarts=20, raw_samples=1024, options=opts, stochastic=True,
+                                     return_best_only=False)
+        final = pr.sample_candidates(cand)
+        with torch.no_grad():
+            best = acq(final).argmax()
+        chosen = final[best].cpu()
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    return sorted(times[1:])[len(times[1:]) // 2], chosen
+
+
+def bo_iter_cpu():
+    from oracle import pr_oracle as P
+    from bo_pr_b200.initializers import draw_sobol_samples, initialize_q_batch_nonneg
+    from tests.golden_util import oracle_acq, oracle_space
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = bo_iter_problem()
+    space, oacq = oracle_space(g), oracle_acq(g)
+    base = g["base_samples"]
+    st = {"c": 0.0, "h": 0.0}
+
+    def call(X, with_grad):
+        r = P.mc_pr(space, X, oacq, base, None, grad_estimator="reinforce_ma", ma_counter=st["c"], ma_hidden=st["h"],
+                    with_grad=with_grad)
+        st["c"], st["h"] = r.ma_counter, r.ma_hidden
+        return r
+
+    torch.manual_seed(0)
+    t0 = time.perf_counter()
+    bounds = torch.stack([torch.zeros(13, dtype=torch.float64), torch.ones(13, dtype=torch.float64)])
+    X_rnd = draw_sobol_samples(bounds, 1024, 1, seed=0)
+    Y = torch.cat([call(X_rnd[s:s + 32], False).value for s in range(0, 1024, 32)])
+    ics = initialize_q_batch_nonneg(X_rnd, Y, 20)
+    outs = []
+    for s in range(0, 20, 5):
+        theta, _ = P.adam_multistart(lambda X: (lambda r: (r.value, r.grad))(call(X, True)),
+                                     lambda X: call(X, False).value, ics[s:s + 5], bounds[0], bounds[1], maxiter=200)
+        outs.append(theta)
+    cand = torch.cat(outs)
+    final = cand.clone()
+    final[..., 3:] = torch.bernoulli(P.rounding_prob(space, cand))  # sample_candidates (:198-233), binary dims
+    with torch.no_grad():
+        oacq(final).argmax()
+    return time.perf_counter() - t0
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -338,6 +418,20 @@ def run_ours(a):
         cpu = {"value": cb * mc / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"{cb} of the {b} restarts x {mc} MC samples per step (value+grad), 8 steps, torch CPU float64"}
 
+    # ---- seconds per BO iteration, ackley13 pr__ei (rank 0, N = 1 only) ---------------------------------------------------
+    bo = None
+    if rank == 0 and world == 1 and not a.no_bo_iter:
+        t_ref_sem, _ = bo_iter_ours(dev, one_batch=False)
+        t_one, _ = bo_iter_ours(dev, one_batch=True)
+        bo = {"workload": "ackley13-shape pr__ei AF-optimisation segment at n_train=119: 1024 raw samples, 20 restarts x "
+                          "200 Adam steps, mc=128, candidate sampling + base-EI re-scoring; GP fit excluded",
+              "sec_reference_semantics": t_ref_sem, "note_reference_semantics": "restart batches of 5, screening chunks "
+              "of 32 (EMA-baseline trajectory as the reference, SURVEY.md App. C.5); one prb_mc_adam call per batch",
+              "sec_all_restarts_one_batch": t_one}
+        if not a.no_cpu_baseline:
+            bo["sec_cpu_port"] = bo_iter_cpu()
+            bo["cpu_cores"] = torch.get_num_threads()
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value_evals, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -345,12 +439,12 @@ def run_ours(a):
             "data": "synthetic",
             "config": {"workload": workload_name(a), "n_train": n, "restarts_per_gpu": b, "mc": mc,
                        "evals_per_step": evals_per_step, "rng": "philox4x32-10 (seed 0, offset 0), drawn in the sampler",
-                       "l2": "per-step intermediates (k*, v, w panels: 3 x 8 x n x b x mc bytes = "
-                             f"{3 * 8 * n * b * mc / 1e9:.2f} GB) exceed the 126 MB L2; the 16 MB GP state is L2-resident "
-                             "by design; no explicit flush",
+                       "l2": "the per-step v panel (8 x n x b x mc bytes = "
+                             f"{8 * n * b * mc / 1e9:.2f} GB written then read) exceeds the 126 MB L2; the 16 MB GP state "
+                             "is L2-resident by design; no explicit flush",
                        "parallelism": f"restart-sharded x{world}, GP state replicated, no data-path collective"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "kernel_breakdown": breakdown,
+            "kernel_breakdown": breakdown, "bo_iter": bo,
         }
         if best is not None:
             line["best_candidate"] = best

@@ -33,5 +33,12 @@ from .probabilistic_reparameterization import (  # noqa: F401
     get_probabilistic_reparameterization_input_transform,
 )
 from .wrapper import AcquisitionFunctionWrapper  # noqa: F401
+from .gen import gen_candidates_scipy, gen_candidates_torch, get_best_candidates  # noqa: F401
+from .initializers import (  # noqa: F401
+    gen_batch_initial_conditions,
+    initialize_q_batch,
+    initialize_q_batch_nonneg,
+)
+from .optimize import optimize_acqf, optimize_acqf_mixed  # noqa: F401
 
 __version__ = "0.1.0"

@@ -1,0 +1,84 @@
+"""GPU: the fused on-device multi-start Adam (prb_mc_adam: gen.py:304-343 semantics in one call) against the host-driven
+loop over the same CUDA value+gradient path and against the CPU oracle's restatement; optimize_acqf end to end."""
+import pytest
+import torch
+
+from bench_workload import make_problem, make_theta, sobol_base_samples
+from oracle import pr_oracle as P
+from tests.golden_util import load, oracle_acq, oracle_space
+from tests.product_util import product_mc_pr
+
+import bo_pr_b200 as B
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _bounds(d):
+    return torch.stack([torch.zeros(d, dtype=torch.float64), torch.ones(d, dtype=torch.float64)]).to(DEV)
+
+
+@pytest.mark.parametrize("name", ["ackley13_ei", "rosenbrock10_ucb", "mixed_int_f1_ei"])
+def test_fused_adam_matches_host_loop_and_oracle(name):
+    g = load(name)
+    c = g["case"]
+    d = c["dim"]
+    ics = g["theta"].to(DEV)
+    bounds = _bounds(d)
+    steps = 12
+    # (1) fused: one prb_mc_adam call
+    pr_f = product_mc_pr(g, DEV)
+    cand_f, val_f = B.gen_candidates_torch(ics, pr_f, bounds[0], bounds[1], options={"maxiter": steps})
+    # (2) host-driven loop over the same class (torch.optim.Adam, one C-ABI call per step)
+    pr_h = product_mc_pr(g, DEV)
+    cand_h, val_h = B.gen_candidates_torch(ics, pr_h, bounds[0], bounds[1], options={"maxiter": steps, "fused": False})
+    assert torch.allclose(cand_f, cand_h, rtol=0, atol=1e-10), (cand_f - cand_h).abs().max()
+    assert torch.allclose(val_f, val_h, rtol=1e-8, atol=1e-12)
+    assert torch.allclose(pr_f._ma_state, pr_h._ma_state, rtol=1e-9, atol=0)
+    assert float(pr_f._ma_state[0]) == steps + 1  # every forward (steps + final evaluation) advanced the EMA counter
+    # (3) CPU oracle: reference semantics end to end
+    space, oacq = oracle_space(g), oracle_acq(g)
+    st = {"c": 0.0, "h": 0.0}
+
+    def vg(X):
+        r = P.mc_pr(space, X, oacq, g["base_samples"], g["base_samples_categorical"],
+                    grad_estimator=c["grad_estimator"], ma_counter=st["c"], ma_hidden=st["h"])
+        st["c"], st["h"] = r.ma_counter, r.ma_hidden
+        return r.value, r.grad
+
+    def vo(X):
+        r = P.mc_pr(space, X, oacq, g["base_samples"], g["base_samples_categorical"],
+                    grad_estimator=c["grad_estimator"], ma_counter=st["c"], ma_hidden=st["h"], with_grad=False)
+        st["c"], st["h"] = r.ma_counter, r.ma_hidden
+        return r.value
+
+    theta_o, val_o = P.adam_multistart(vg, vo, g["theta"], torch.zeros(d, dtype=torch.float64),
+                                       torch.ones(d, dtype=torch.float64), maxiter=steps)
+    assert torch.allclose(cand_f.cpu(), theta_o, rtol=0, atol=1e-8), (cand_f.cpu() - theta_o).abs().max()
+    assert torch.allclose(val_f.cpu(), val_o, rtol=1e-7, atol=1e-11)
+
+
+def test_optimize_acqf_pr_ei_improves_over_initial_conditions():
+    """The reference's call (run_one_replication.py:494-501) at the ackley13 shape: restarts in batches of 5."""
+    g = make_problem(119, seed=3)
+    g["case"].update(mc=128, grad_estimator="reinforce_ma")
+    g["base_samples"] = sobol_base_samples(128)
+    g["base_samples_categorical"] = None
+    pr = product_mc_pr(g, DEV)
+    bounds = _bounds(13)
+    torch.manual_seed(0)
+    opts = {"batch_limit": 5, "init_batch_limit": 32, "maxiter": 200, "nonnegative": True, "seed": 7}
+    ics = B.gen_batch_initial_conditions(pr, bounds, q=1, num_restarts=20, raw_samples=1024, options=opts)
+    assert float(pr._ma_state[0]) == 32  # 1024 / 32 screening calls advanced the EMA counter
+    with torch.no_grad():
+        v0 = pr(ics)
+    cand, vals = B.optimize_acqf(pr, bounds, q=1, num_restarts=20, options=opts, batch_initial_conditions=ics,
+                                 stochastic=True, return_best_only=False)
+    assert cand.shape == (20, 1, 13) and vals.shape == (20,)
+    assert bool((cand >= 0).all()) and bool((cand <= 1).all())
+    assert float(vals.max()) >= float(v0.max()) - 1e-12
+    assert float(vals.mean()) > float(v0.mean())
+    # candidates finalisation (probabilistic_reparameterization.py:198-233): valid discrete points
+    final = pr.sample_candidates(cand)
+    assert bool(((final[..., 3:] == 0) | (final[..., 3:] == 1)).all())
+    assert torch.equal(final[..., :3], cand[..., :3])
