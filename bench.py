@@ -392,7 +392,9 @@ def run_ours(a):
         # algorithmic flops of the two triangular products: n(n+1) flop per column each (+ 2n for the alpha row)
         flops_per_step = b * mc * (2.0 * n * (n + 1) + 2.0 * n)
         achieved = flops_per_step / (gemm_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "trgemm_dmma_kernel (FP64 DMMA m8n8k4; lower Linv k* and upper Linv^T v)",
+        roofline = {"bound": "tensor", "kernel": "trgemm_tma_kernel<LOWER_GEN | UPPER_GRAD> (TMA + mbarrier "
+                    "pipeline, FP64 DMMA m8n8k4: Linv k* with k* generated in-kernel; Linv^T v with the gradient "
+                    "contraction fused into the epilogue)",
                     "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
                     "traffic": None, "peak_source": FP64_PEAK_SOURCE,
                     "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "launches_per_step": gemm_launches,
