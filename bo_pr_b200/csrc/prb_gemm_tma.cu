@@ -152,6 +152,8 @@ __global__ void __launch_bounds__(T_THREADS, 1)
   __syncthreads();
 
   // ---- B-operand generation: thread <-> (evaluation column, 8 of the 16 k values of a k-tile) ---------------------------
+  // (the 32-byte column stride of the STS.128 below costs 2-way bank conflicts, 21 M per launch; a lane-pair-per-column
+  //  mapping that removes them needs 8 instead of 6 global loads per thread and k-tile and measured 1.7 % SLOWER)
   const int gcol = tid & (T_BN - 1);
   const int ghalf = tid >> 7;
   uint32_t g_zb = 0;
