@@ -24,7 +24,7 @@ PRB_PROFILE_SLOTS = 12
 PROFILE_SLOT_NAMES = ["pr_sample", "kstar_panel", "trgemm_lower", "acq_epilogue", "trgemm_upper", "grad_contract",
                       "sum_splits", "mc_reduce", "ma_update", "analytic", "adam", "other"]
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libprb200.so")
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", os.environ.get("PRB_LIB_NAME", "libprb200.so"))
 
 EXPORTS = [
     "prb_version", "prb_abi_sizeof", "prb_launch_count", "prb_profile_enable", "prb_profile_read", "prb_status_string", "prb_last_cuda_error", "prb_model_create", "prb_model_destroy",

@@ -12,7 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "_lib", "libprb200.so")
+# PRB_LIB_NAME / PRB_NVCC_EXTRA: build a tuning variant next to the default library (experiments only)
+OUT = os.path.join(HERE, "_lib", os.environ.get("PRB_LIB_NAME", "libprb200.so"))
 SOURCES = ["prb_gemm.cu", "prb_gemm_tma.cu", "prb_kernels.cu", "prb_api.cu"]
 HEADERS = ["prb_internal.cuh", "prb_device.cuh", "prb_kernels.cuh", os.path.join(ROOT, "include", "prb200.h")]
 NVCC_FLAGS = [
@@ -37,6 +38,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc not found: libprb200.so cannot be built (bo_pr_b200 has no CPU fallback)")
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    cmd += os.environ.get("PRB_NVCC_EXTRA", "").split()
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]

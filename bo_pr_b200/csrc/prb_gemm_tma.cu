@@ -27,7 +27,14 @@
 
 namespace prb {
 
-constexpr int T_BM = 128, T_BN = 128, T_BK = 16, T_STAGES = 4, T_AHEAD = 2, T_THREADS = 256;
+#ifndef PRB_T_STAGES
+#define PRB_T_STAGES 4
+#endif
+#ifndef PRB_T_AHEAD
+#define PRB_T_AHEAD 2
+#endif
+constexpr int T_BM = 128, T_BN = 128, T_BK = 16, T_STAGES = PRB_T_STAGES, T_AHEAD = PRB_T_AHEAD, T_THREADS = 256;
+static_assert(T_AHEAD >= 1 && T_AHEAD <= T_STAGES - 1, "the producer may run at most T_STAGES - 1 k-tiles ahead");
 constexpr int T_OPER_DOUBLES = T_BM * T_BK;            // 2048 doubles = 16 KB per operand per stage
 constexpr int T_CHUNK_DOUBLES = T_BM * 4;              // one k-chunk (4 k values) of 128 rows
 constexpr int T_STAGE_DOUBLES = 2 * T_OPER_DOUBLES;
