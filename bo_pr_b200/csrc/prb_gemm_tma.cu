@@ -13,6 +13,9 @@
 // makes every DMMA fragment load a fully coalesced, conflict-free 256-byte LDS.64; stage hand-off is by full/empty
 // mbarriers (no __syncthreads in the main loop, producer runs two k-tiles ahead).
 //
+// Tuning record (B200, n = 1000, 65 536 columns; profiles/): 4 stages / producer 2 k-tiles ahead beats 5/3, 5/2 and 4/3;
+// 8 warps of 32 x 64 (246-254 registers, 1 CTA/SM) beat 16 warps of 32 x 32 (128 registers): 4.49 vs 4.79 ms per step.
+//
 // Four modes (template):
 //   LOWER_GEN   the B operand k*[col, k] = kc[b(col), k] * tab[popc(z[col] ^ Z[k])] is GENERATED into shared memory by the
 //               consumer threads (separable "mixed" kernel: Matern over continuous dims x isotropic Matern over binary dims);
