@@ -14,7 +14,9 @@
 // mbarriers (no __syncthreads in the main loop, producer runs two k-tiles ahead).
 //
 // Tuning record (B200, n = 1000, 65 536 columns; profiles/): 4 stages / producer 2 k-tiles ahead beats 5/3, 5/2 and 4/3;
-// 8 warps of 32 x 64 (246-254 registers, 1 CTA/SM) beat 16 warps of 32 x 32 (128 registers): 4.49 vs 4.79 ms per step.
+// 8 warps of 32 x 64 (246-254 registers, 1 CTA/SM) beat 16 warps of 32 x 32 (128 registers): 4.49 vs 4.79 ms per step;
+// routing the whole last row tile through the masked (diagonal) body to skip its all-padding row groups costs more than
+// the 1.5 % of DMMAs it saves (4.55 vs 4.46 ms).
 //
 // Four modes (template):
 //   LOWER_GEN   the B operand k*[col, k] = kc[b(col), k] * tab[popc(z[col] ^ Z[k])] is GENERATED into shared memory by the
