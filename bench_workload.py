@@ -43,7 +43,8 @@ def make_problem(n: int, seed: int = 0, device="cpu"):
         K[s:e] = 1.3 * _matern52(Xd[s:e, :D_CONT], Xd[:, :D_CONT], ls_c) * _matern52(Xd[s:e, D_CONT:], Xd[:, D_CONT:], ls_b)
     K.diagonal().add_(1e-6)
     y = (torch.linalg.cholesky(K) @ z.to(device)).cpu()
-    y = (y - y.mean()) / y.std()
+    if n > 1:
+        y = (y - y.mean()) / y.std()
     case = dict(dim=D, integer_indices=BINARY_DIMS, integer_bounds=[[0.0] * 10, [1.0] * 10], categorical_features=None,
                 kernel_type="mixed", binary_dims=BINARY_DIMS, acq="ei", apply_numeric=False,
                 grad_estimator="reinforce_ma", beta=0.2 * D * math.log(2.0))

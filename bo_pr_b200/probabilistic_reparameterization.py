@@ -190,6 +190,9 @@ class _AnalyticPRFunction(Function):
         state = gp_state_from_model(module.acq_function.model)
         lib = state.lib
         b, d = X.shape[0], X.shape[-1]
+        if b == 0:
+            ctx.unit_grad = None
+            return X.new_empty(0, dtype=torch.float64)
         rnd = module.input_transform["round"]
         codes = rnd.option_codes
         n_opt = codes.shape[0]
@@ -281,7 +284,7 @@ class MCProbabilisticReparameterization(AbstractProbabilisticReparameterization)
             raise ValueError(f"unknown grad_estimator {grad_estimator!r}")
         self.grad_estimator = grad_estimator
         self.mc_samples = mc_samples
-        self._pr_acq_function = _MCProbabilisticReparameterization()
+        self._pr_acq_function = _MCProbabilisticReparameterization  # the autograd Function class (static methods)
         self.input_transform = get_probabilistic_reparameterization_input_transform(
             dim=dim, integer_indices=integer_indices if integer_indices is not None else [],
             integer_bounds=integer_bounds, categorical_features=categorical_features, mc_samples=mc_samples, tau=tau,
@@ -317,6 +320,9 @@ class _MCProbabilisticReparameterization(Function):
         state = gp_state_from_model(acq_function.model)
         lib = state.lib
         b = X.shape[0]
+        if b == 0:  # nothing to evaluate; the reference's EMA update would average an empty tensor (NaN): leave the state
+            ctx.unit_grad = None
+            return X.new_empty(0, dtype=torch.float64)
         theta = X.detach().to(torch.float64).reshape(b, d).contiguous()
         rnd.ensure_base_samples(1, X.device)
         u_int, u_cat = rnd.base_sample_ptrs()

@@ -140,3 +140,37 @@ def test_score_function_gradient_is_unbiased_for_the_analytic_objective():
     scale = torch.ones(theta.shape[-1], dtype=torch.float64, device=DEV)
     scale[g["case"]["integer_indices"]] = ib[1] - ib[0]
     assert torch.allclose(gmc * scale, ga, rtol=0, atol=5e-2), (gmc * scale - ga).abs().max()
+
+
+@pytest.mark.parametrize("n", [1, 2, 15, 16, 17, 127, 128, 129, 255, 257])
+def test_tile_boundary_sizes_vs_oracle(n):
+    """Training-set sizes around the 16 / 128 tile boundaries of the triangular products (padding rows, the alpha row
+    landing in its own row tile at n = 128, a single training point)."""
+    b, mc = 3, 40  # mc not a multiple of the 128-column tile: tiles straddle restarts and the last one is ragged
+    g = _problem(n, mc, "ei")
+    space, oacq = oracle_space(g), oracle_acq(g)
+    theta = make_theta(b, seed=n)
+    ref = P.mc_pr(space, theta, oacq, g["base_samples"], None, grad_estimator="reinforce_ma", ma_counter=2.0,
+                  ma_hidden=0.01)
+    pr = product_mc_pr(g, DEV)
+    pr._ma_state.copy_(torch.tensor([2.0, 0.01], dtype=torch.float64))
+    X = theta.to(DEV).requires_grad_(True)
+    val = pr(X)
+    grad = torch.autograd.grad(val.sum(), X)[0]
+    _assert_close(val, ref.value, "PR value")
+    _assert_close(grad, ref.grad, "PR gradient", atol=1e-11)
+
+
+def test_empty_and_single_sample_calls():
+    g = _problem(64, 1, "ei")
+    pr = product_mc_pr(g, DEV)
+    space, oacq = oracle_space(g), oracle_acq(g)
+    theta = make_theta(2)
+    ref = P.mc_pr(space, theta, oacq, g["base_samples"], None, grad_estimator="reinforce_ma")
+    X = theta.to(DEV).requires_grad_(True)
+    val = pr(X)  # mc = 1
+    grad = torch.autograd.grad(val.sum(), X)[0]
+    _assert_close(val, ref.value, "PR value (mc = 1)")
+    _assert_close(grad, ref.grad, "PR gradient (mc = 1)", atol=1e-11)
+    empty = pr(torch.empty(0, 1, 13, dtype=torch.float64, device=DEV))
+    assert empty.shape == (0,)
