@@ -343,6 +343,32 @@ def run_ours(a):
     evals_per_step = world * b * mc
     value_evals = evals_per_step / (ms_per_step * 1e-3)
 
+    # ---- the same step with MC de-duplication (PRB_OPT_DEDUP): reported separately, never as `value` ---------------------
+    dedup = None
+    if rank == 0:
+        z = torch.empty(b, mc, pr._space().n_int, dtype=torch.uint8, device=dev)
+        capi.check(lib.prb_pr_sample(C.byref(sp), theta_dev.data_ptr(), b, mc, None, None, 0, 0, None, z.data_ptr(), None,
+                                     stream.cuda_stream), "prb_pr_sample")
+        codes = (z.to(torch.int64) << torch.arange(z.shape[-1], device=dev)).sum(-1)
+        n_unique = sum(int(torch.unique(codes[r]).numel()) for r in range(b))
+        state.set_option(capi.PRB_OPT_DEDUP, 1)
+        for _ in range(a.warmup):
+            step()
+        torch.cuda.synchronize()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record(stream)
+        for _ in range(a.steps):
+            step()
+        d1.record(stream)
+        torch.cuda.synchronize()
+        state.set_option(capi.PRB_OPT_DEDUP, 0)
+        dms = d0.elapsed_time(d1) / a.steps
+        dedup = {"value": b * mc / (dms * 1e-3), "unit": UNIT, "ms_per_step": dms, "n_gpus": 1,
+                 "unique_columns": n_unique, "unique_fraction": n_unique / (b * mc),
+                 "note": "PRB_OPT_DEDUP: one base-AF evaluation per unique (restart, discrete configuration), weighted by "
+                         "multiplicity; identical results up to summation order; theta ~ U[0,1] (as PR converges the "
+                         "unique fraction falls further). evals/s still counted per candidate x MC sample."}
+
     # ---- end to end through the reference-facing API, host buffers ----------------------------------------------------
     e2e = None
     if not a.no_e2e:
@@ -452,7 +478,7 @@ def run_ours(a):
                              "is L2-resident by design; no explicit flush",
                        "parallelism": f"restart-sharded x{world}, GP state replicated, no data-path collective"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "kernel_breakdown": breakdown, "bo_iter": bo,
+            "kernel_breakdown": breakdown, "bo_iter": bo, "dedup": dedup,
         }
         if best is not None:
             line["best_candidate"] = best

@@ -160,6 +160,7 @@ struct Plan {
   size_t off_panelA, off_panelV, off_norm, off_mu, off_S_part;
   size_t off_Xc, off_grad, off_ones, off_val, off_step;
   size_t off_zbits, off_kc, off_Dc;
+  size_t off_ucount, off_ustart, off_utotal, off_ucode, off_uweight, off_inv, off_zbits_u, off_colb, off_wu;
   size_t total;
 };
 
@@ -226,6 +227,15 @@ Plan make_plan(const Model& m, int64_t n_points, int n_restarts, int d_theta, in
   if (m.sep_ok && n_restarts > 0) {
     p.off_kc = take(size_t(n_restarts) * m.Kp * dbl);
     p.off_Dc = take(size_t(n_restarts) * d_theta * m.Kp * dbl);
+    p.off_ucount = take(size_t(n_restarts) * sizeof(int));
+    p.off_ustart = take(size_t(n_restarts + 1) * sizeof(int));
+    p.off_utotal = take(2 * sizeof(int));
+    p.off_ucode = take(size_t(p.B_pad) * sizeof(uint32_t));
+    p.off_uweight = take(size_t(p.B_pad) * sizeof(int));
+    p.off_inv = take(size_t(p.B_pad) * sizeof(int));
+    p.off_zbits_u = take(size_t(p.B_pad) * sizeof(uint32_t));
+    p.off_colb = take(size_t(p.B_pad) * sizeof(int));
+    p.off_wu = take(size_t(p.B_pad) * dbl);
   }
   p.total = off;
   return p;
@@ -272,14 +282,14 @@ int run_engine(const Model& m, const DevAcq& aq, const Plan& pl, void* ws, const
     else
       CUDA_TRY(launch_trgemm_lower(m, panelA, ncols_pad, panelV, norm, mu, st));
     CUDA_TRY(launch_acq_epilogue(m, aq, norm, ncols_pad, mu, ncols, a + c0, dmu + c0, dvar + c0,
-                                 out_mean ? out_mean + c0 : nullptr, out_var ? out_var + c0 : nullptr, st));
+                                 out_mean ? out_mean + c0 : nullptr, out_var ? out_var + c0 : nullptr, nullptr, 0, st));
     if (need_grad) {
       if (v2)
         CUDA_TRY(launch_tma_upper(m, mapV, ncols_pad, panelA, st));
       else
         CUDA_TRY(launch_trgemm_upper(m, panelV, ncols_pad, panelA, st));
       CUDA_TRY(launch_grad_contract(m, diffmask, xkc, ncols, ncols_pad, panelA, dmu + c0, dvar + c0, S_part, st));
-      CUDA_TRY(launch_sum_splits(m, S_part, nullptr, ncols, ncols_pad, S_all + size_t(c0) * m.d_k, st));
+      CUDA_TRY(launch_sum_splits(m, S_part, nullptr, ncols, ncols_pad, S_all + size_t(c0) * m.d_k, nullptr, 0, st));
     }
   }
   return PRB_OK;
@@ -314,16 +324,18 @@ bool sep_space_ok(const Model& m, const DevSpace& sp, BitMap* bm, DimMap* dm) {
 // separable fast path: no k* panel, no W panel -- operands generated in the lower product, gradient contracted in the
 // epilogue of the upper product
 int run_engine_sep(const Model& m, const DevAcq& aq, const Plan& pl, void* ws, const double* theta, int d_theta, int nb,
-                   int mc, const DimMap& dm, bool need_grad, double* a, double* dmu, double* dvar, double* S_all,
-                   cudaStream_t st) {
-  const int64_t B = int64_t(nb) * mc;
+                   int mc, const DimMap& dm, bool need_grad, bool dedup, double* a, double* dmu, double* dvar,
+                   double* S_all, cudaStream_t st) {
+  const int64_t B = int64_t(nb) * mc;  // with de-duplication: the worst case (no two samples of a restart coincide)
   double* panelV = at<double>(ws, pl.off_panelV);
   double* norm = at<double>(ws, pl.off_norm);
   double* mu = at<double>(ws, pl.off_mu);
   double* S_part = at<double>(ws, pl.off_S_part);
   double* kc = at<double>(ws, pl.off_kc);
   double* Dc = at<double>(ws, pl.off_Dc);
-  const uint32_t* zbits = at<uint32_t>(ws, pl.off_zbits);
+  const uint32_t* zbits = dedup ? at<uint32_t>(ws, pl.off_zbits_u) : at<uint32_t>(ws, pl.off_zbits);
+  const int* colb = dedup ? at<int>(ws, pl.off_colb) : nullptr;
+  const int* ncols_dev = dedup ? at<int>(ws, pl.off_utotal) : nullptr;
   CUDA_TRY(launch_sep_restart_prep(m, theta, nb, d_theta, kc, need_grad ? Dc : nullptr, st));
   TensorMap mapV;
   if (need_grad) CUDA_TRY(make_operand_map(&mapV, panelV, pl.C, m.Kp, m.Mp1));
@@ -338,11 +350,14 @@ int run_engine_sep(const Model& m, const DevAcq& aq, const Plan& pl, void* ws, c
     sa.mc = mc;
     sa.nb = nb;
     sa.col0 = c0;
+    sa.colb = colb ? colb + c0 : nullptr;
+    sa.ncols_dev = ncols_dev;
     CUDA_TRY(launch_tma_lower_gen(m, sa, ncols_pad, need_grad ? panelV : nullptr, norm, mu, st));
-    CUDA_TRY(launch_acq_epilogue(m, aq, norm, ncols_pad, mu, ncols, a + c0, dmu + c0, dvar + c0, nullptr, nullptr, st));
+    CUDA_TRY(launch_acq_epilogue(m, aq, norm, ncols_pad, mu, ncols, a + c0, dmu + c0, dvar + c0, nullptr, nullptr,
+                                 ncols_dev, c0, st));
     if (need_grad) {
       CUDA_TRY(launch_tma_upper_grad(m, mapV, sa, ncols, ncols_pad, dmu + c0, dvar + c0, S_part, st));
-      CUDA_TRY(launch_sum_splits(m, S_part, &dm, ncols, ncols_pad, S_all + size_t(c0) * m.d_k, st));
+      CUDA_TRY(launch_sum_splits(m, S_part, &dm, ncols, ncols_pad, S_all + size_t(c0) * m.d_k, ncols_dev, c0, st));
     }
   }
   return PRB_OK;
@@ -373,10 +388,31 @@ int mc_core(prb_model* model, const DevSpace& sp, const DevAcq& aq, const Plan& 
   DimMap dm;
   const bool sep = pl.off_kc != 0 && sep_space_ok(m, sp, &bm, &dm);
   int rc;
+  const bool dedup = sep && m.opt_dedup && m.sep_nbits <= DEDUP_MAX_BITS;
+  if (dedup) {
+    // unique (restart, code) columns only; per-sample values are scattered back on request
+    double* a_u = at<double>(ws, pl.off_a);
+    CUDA_TRY(launch_pr_sample(sp, theta, b, mc, u_int, u_cat, seed, offset, nullptr, nullptr, nullptr,
+                              need_grad ? prob : nullptr, &bm, at<uint32_t>(ws, pl.off_zbits), st));
+    CUDA_TRY(launch_dedup(at<uint32_t>(ws, pl.off_zbits), b, mc, m.sep_nbits, at<int>(ws, pl.off_ucount),
+                          at<int>(ws, pl.off_ustart), at<int>(ws, pl.off_utotal), at<uint32_t>(ws, pl.off_ucode),
+                          at<int>(ws, pl.off_uweight), out_acq_values ? at<int>(ws, pl.off_inv) : nullptr,
+                          at<uint32_t>(ws, pl.off_zbits_u), at<int>(ws, pl.off_colb), at<double>(ws, pl.off_wu), st));
+    rc = run_engine_sep(m, aq, pl, ws, theta, sp.d, b, mc, dm, need_path, true, a_u, dmu, dvar, S_all, st);
+    if (rc != PRB_OK) return rc;
+    CUDA_TRY(launch_mc_reduce_dedup(sp, bm, b, mc, at<int>(ws, pl.off_ucount), at<int>(ws, pl.off_ustart),
+                                    at<double>(ws, pl.off_wu), at<uint32_t>(ws, pl.off_zbits_u), a_u, prob, S_all,
+                                    estimator, ma_state, grad_out, out_value, out_grad, st));
+    if (out_acq_values)
+      CUDA_TRY(launch_dedup_scatter(a_u, at<int>(ws, pl.off_ustart), at<int>(ws, pl.off_inv), b, mc, out_acq_values,
+                                    st));
+    if (update_ma && ma_state) CUDA_TRY(launch_ma_update(out_value, b, ma_state, st));
+    return PRB_OK;
+  }
   if (sep) {
     CUDA_TRY(launch_pr_sample(sp, theta, b, mc, u_int, u_cat, seed, offset, nullptr, nullptr, need_grad ? z : nullptr,
                               need_grad ? prob : nullptr, &bm, at<uint32_t>(ws, pl.off_zbits), st));
-    rc = run_engine_sep(m, aq, pl, ws, theta, sp.d, b, mc, dm, need_path, a, dmu, dvar, S_all, st);
+    rc = run_engine_sep(m, aq, pl, ws, theta, sp.d, b, mc, dm, need_path, false, a, dmu, dvar, S_all, st);
   } else {
     CUDA_TRY(launch_pr_sample(sp, theta, b, mc, u_int, u_cat, seed, offset, xk, nullptr, need_grad ? z : nullptr,
                               need_grad ? prob : nullptr, nullptr, nullptr, st));
@@ -558,6 +594,18 @@ int prb_model_destroy(prb_model* model) {
   cudaFree(m->sep_tab);
   delete m;
   return PRB_OK;
+}
+
+int prb_model_set_option(prb_model* model, int32_t option, int64_t value) {
+  if (!model) return PRB_ERR_INVALID;
+  Model* m = reinterpret_cast<Model*>(model);
+  switch (option) {
+    case PRB_OPT_DEDUP:
+      m->opt_dedup = value != 0;
+      return PRB_OK;
+    default:
+      return PRB_ERR_INVALID;
+  }
 }
 
 int prb_model_n(const prb_model* model) { return model ? reinterpret_cast<const Model*>(model)->n : PRB_ERR_INVALID; }

@@ -107,6 +107,8 @@ struct TmaGemmParams {
   int mc;        // evaluation points per restart (b(col) = (col0 + col) / mc)
   int64_t col0;  // global index of the panel's first column
   int nb;        // number of restarts (clamp for padded columns)
+  const int* colb;       // de-duplicated columns: restart of each column (panel-local), else NULL
+  const int* ncols_dev;  // de-duplicated columns: device scalar with the total number of columns, else NULL
   const double* Dc;         // [nb, n_cont, Kp] outputscale * G(r) * (x_c - X_jc) / l_c^2
   int n_cont;
   const double* alpha_pad;  // [Mp2] alpha, 0 beyond n
@@ -151,6 +153,14 @@ __global__ void __launch_bounds__(T_THREADS, 1)
   }
   const int num_k = (kend - kbeg) / T_BK;
 
+  // de-duplicated columns: the grid covers the worst case (no duplicates); tiles beyond the unique columns do nothing
+  int ncols_valid = p.ncols;
+  if (p.ncols_dev != nullptr) {
+    const int64_t left = int64_t(*p.ncols_dev) - p.col0;
+    if (left <= n0) return;
+    if (left < ncols_valid || ncols_valid == 0) ncols_valid = int(left);
+  }
+
   if (tid == 0) {
     tma_prefetch_desc(&tmA);
     if (!GEN) tma_prefetch_desc(&tmB);
@@ -172,7 +182,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
   const double* g_kc = nullptr;
   if (GEN) {
     g_zb = p.zbits[n0 + gcol];
-    int64_t br = (p.col0 + n0 + gcol) / p.mc;
+    int64_t br = p.colb ? int64_t(p.colb[n0 + gcol]) : (p.col0 + n0 + gcol) / p.mc;
     if (br > p.nb - 1) br = p.nb - 1;
     g_kc = p.kc + size_t(br) * p.Kp;
   }
@@ -347,7 +357,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int col = col_base + 8 * j + e;
-        const bool cv_ok = col < p.ncols;
+        const bool cv_ok = col < ncols_valid;
         const double cm = cv_ok ? p.dmu[col] : 0.0;
         const double cv = cv_ok ? -2.0 * p.dvar[col] : 0.0;
         const uint32_t zc = p.zbits[col];
@@ -356,7 +366,8 @@ __global__ void __launch_bounds__(T_THREADS, 1)
           acc[i][j][e] = fma(cv, acc[i][j][e], cm * al[i]) * tab_s[__popc(zc ^ Zr[i])];
       }
     // restart index of the tile's first / last column: one restart per tile is the common case (mc % 128 == 0)
-    int64_t b_lo = (p.col0 + n0) / p.mc, b_hi = (p.col0 + n0 + T_BN - 1) / p.mc;
+    int64_t b_lo = p.colb ? int64_t(p.colb[n0]) : (p.col0 + n0) / p.mc;
+    int64_t b_hi = p.colb ? int64_t(p.colb[n0 + T_BN - 1]) : (p.col0 + n0 + T_BN - 1) / p.mc;
     if (b_lo > p.nb - 1) b_lo = p.nb - 1;
     if (b_hi > p.nb - 1) b_hi = p.nb - 1;
     const bool single = (b_lo == b_hi);
@@ -381,7 +392,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
         for (int j = 0; j < 8; ++j)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            int64_t br = (p.col0 + col_base + 8 * j + e) / p.mc;
+            int64_t br = p.colb ? int64_t(p.colb[col_base + 8 * j + e]) : (p.col0 + col_base + 8 * j + e) / p.mc;
             if (br > p.nb - 1) br = p.nb - 1;
             const double* D = p.Dc + (size_t(br) * p.n_cont + c) * p.Kp;
             double s = 0.0;
@@ -530,6 +541,8 @@ static void fill_sep(TmaGemmParams& p, const Model& m, const SepArgs& sa) {
   p.nb = sa.nb;
   p.Dc = sa.Dc;
   p.n_cont = sa.n_cont;
+  p.colb = sa.colb;
+  p.ncols_dev = sa.ncols_dev;
   p.alpha_pad = m.alpha_pad;
 }
 

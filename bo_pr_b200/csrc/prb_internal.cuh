@@ -92,6 +92,9 @@ struct SepArgs {
   const uint32_t* zbits;  // panel-local [ncols_pad]
   int n_cont, mc, nb;
   int64_t col0;
+  // MC de-duplication: columns are the UNIQUE configurations, packed restart by restart
+  const int* colb;       // [ncols_pad] restart of each column (NULL: column / mc)
+  const int* ncols_dev;  // device scalar: total number of unique columns (NULL: every column of the panel is valid)
 };
 
 struct BitMap {  // integer parameter k of the PR space -> bit position in the binary-factor code (-1: not a binary dim)
@@ -125,7 +128,10 @@ struct Model {
   int sep_nbits;                        // number of binary dims (<= 32)
   uint32_t* Zbits;                      // [max(Mp1, Mp2)] bit codes of the training points
   double* sep_tab;                      // [64] binary-factor value by Hamming distance
+  int opt_dedup;                        // PRB_OPT_DEDUP
 };
+
+constexpr int DEDUP_MAX_BITS = 12;  // histogram de-duplication: 2^12 bins of shared memory per restart
 
 // launchers (prb_gemm.cu / prb_kernels.cu); all enqueue on `st` and return the CUDA status
 cudaError_t launch_trgemm_lower(const Model& m, const double* KstarT, int ncols_pad, double* VT, double* norm_part,

@@ -388,9 +388,11 @@ cudaError_t launch_pad_copy(const double* src, int n, int n_pad, double* dst, cu
 __global__ void acq_epilogue_kernel(const DevAcq aq, double mean_const, double kss, const double* __restrict__ norm_part,
                                     int mtiles, int ncols_pad, const double* __restrict__ mu_dot, int ncols,
                                     double* __restrict__ a, double* __restrict__ dmu, double* __restrict__ dvar,
-                                    double* __restrict__ out_mean, double* __restrict__ out_var) {
+                                    double* __restrict__ out_mean, double* __restrict__ out_var,
+                                    const int* __restrict__ ncols_dev, int64_t col0) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= ncols) return;
+  if (ncols_dev != nullptr && col0 + col >= int64_t(*ncols_dev)) return;
   double vs = 0.0;
   for (int t = 0; t < mtiles; ++t) vs += norm_part[size_t(t) * ncols_pad + col];
   const double var_raw = kss - vs;
@@ -428,11 +430,13 @@ __global__ void acq_epilogue_kernel(const DevAcq aq, double mean_const, double k
 
 cudaError_t launch_acq_epilogue(const Model& m, const DevAcq& aq, const double* norm_part, int ncols_pad,
                                 const double* mu_dot, int ncols, double* a, double* dmu, double* dvar,
-                                double* out_mean, double* out_var, cudaStream_t st) {
+                                double* out_mean, double* out_var, const int* ncols_dev, int64_t col0,
+                                cudaStream_t st) {
   ProfScope prof_(K_EPILOGUE, st);
   if (ncols == 0) return cudaSuccess;
   acq_epilogue_kernel<<<(ncols + 127) / 128, 128, 0, st>>>(aq, m.mean_const, m.kss, norm_part, m.Mp1 / GEMM_BM,
-                                                           ncols_pad, mu_dot, ncols, a, dmu, dvar, out_mean, out_var);
+                                                           ncols_pad, mu_dot, ncols, a, dmu, dvar, out_mean, out_var,
+                                                           ncols_dev, col0);
   count_launch();
   return cudaGetLastError();
 }
@@ -556,9 +560,11 @@ cudaError_t launch_grad_contract(const Model& m, uint32_t diffmask, const double
 
 // S_all[col_global, dim] = sum_jblock S_part[jblock][dim][col]   (fixed order)
 __global__ void sum_splits_kernel(const double* __restrict__ S_part, int jblocks, const DimMap dm, int d_k, int ncols,
-                                  int ncols_pad, double* __restrict__ S_all) {
+                                  int ncols_pad, double* __restrict__ S_all, const int* __restrict__ ncols_dev,
+                                  int64_t col0) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= ncols) return;
+  if (ncols_dev != nullptr && col0 + col >= int64_t(*ncols_dev)) return;
   for (int dd = 0; dd < dm.n; ++dd) {
     double s = 0.0;
     for (int jb = 0; jb < jblocks; ++jb) s += S_part[(size_t(jb) * dm.n + dd) * ncols_pad + col];
@@ -567,14 +573,14 @@ __global__ void sum_splits_kernel(const double* __restrict__ S_part, int jblocks
 }
 
 cudaError_t launch_sum_splits(const Model& m, const double* S_part, const DimMap* dm, int ncols, int ncols_pad,
-                              double* S_all, cudaStream_t st) {
+                              double* S_all, const int* ncols_dev, int64_t col0, cudaStream_t st) {
   ProfScope prof_(K_SUM_SPLITS, st);
   if (ncols == 0) return cudaSuccess;
   DimMap ident;
   ident.n = m.d_k;
   for (int i = 0; i < PRB_MAX_DIMS; ++i) ident.dims[i] = i;
   sum_splits_kernel<<<(ncols + 127) / 128, 128, 0, st>>>(S_part, m.Mp2 / GRAD_JSPLIT_ROWS, dm ? *dm : ident, m.d_k,
-                                                         ncols, ncols_pad, S_all);
+                                                         ncols, ncols_pad, S_all, ncols_dev, col0);
   count_launch();
   return cudaGetLastError();
 }
@@ -593,6 +599,185 @@ __device__ __forceinline__ double block_sum(double v, double* red /*[32]*/) {
   const int nw = (blockDim.x + 31) >> 5;
   for (int w = 0; w < nw; ++w) s += red[w];
   return s;
+}
+
+// =====================================================================================================================
+// MC de-duplication (separable path, PRB_OPT_DEDUP).  All MC samples of one restart share the continuous columns, so two
+// samples with the same binary code are the SAME evaluation point: the base acquisition value is computed once per unique
+// (restart, code) and weighted by its multiplicity in the reductions.  Exact up to the order of floating-point summation;
+// bench.py reports it separately (evals/s is always counted per candidate x MC sample).
+//   dedup_count   : one CTA per restart, shared-memory histogram over the 2^nbits codes, compaction in code order
+//   dedup_offsets : exclusive scan of the unique counts over restarts (+ total, device-resident: no host round trip)
+//   dedup_pack    : unique columns packed restart by restart: code, owning restart, weight
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) dedup_count_kernel(const uint32_t* __restrict__ zbits, int mc, int nbits,
+                                                          int* __restrict__ ucount, uint32_t* __restrict__ ucode,
+                                                          int* __restrict__ uweight, int* __restrict__ inv) {
+  extern __shared__ int dsm[];
+  const int nbins = 1 << nbits;
+  int* hist = dsm;           // [nbins]
+  int* slot = dsm + nbins;   // [nbins]
+  __shared__ int wsum[8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const uint32_t* zb = zbits + size_t(b) * mc;
+  for (int i = tid; i < nbins; i += 256) hist[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < mc; i += 256) atomicAdd(&hist[zb[i]], 1);
+  __syncthreads();
+  // slots in increasing code order: each thread owns a contiguous range of bins
+  const int per = (nbins + 255) / 256;
+  const int lo = tid * per, hi = min(nbins, lo + per);
+  int cnt = 0;
+  for (int i = lo; i < hi; ++i) cnt += hist[i] > 0;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((tid & 31) >= o) incl += v;
+  }
+  if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+  __syncthreads();
+  int base = 0;
+  for (int w = 0; w < (tid >> 5); ++w) base += wsum[w];
+  int pos = base + incl - cnt;
+  for (int i = lo; i < hi; ++i) {
+    if (hist[i] > 0) {
+      slot[i] = pos;
+      ucode[size_t(b) * mc + pos] = uint32_t(i);
+      uweight[size_t(b) * mc + pos] = hist[i];
+      ++pos;
+    }
+  }
+  if (tid == 255) ucount[b] = base + incl;
+  __syncthreads();
+  if (inv)
+    for (int i = tid; i < mc; i += 256) inv[size_t(b) * mc + i] = slot[zb[i]];
+}
+
+__global__ void dedup_offsets_kernel(const int* __restrict__ ucount, int nb, int* __restrict__ ustart,
+                                     int* __restrict__ total) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int acc = 0;
+    for (int b = 0; b < nb; ++b) {
+      ustart[b] = acc;
+      acc += ucount[b];
+    }
+    ustart[nb] = acc;
+    total[0] = acc;
+    total[1] = (acc + 127) / 128 * 128;
+  }
+}
+
+__global__ void __launch_bounds__(256) dedup_pack_kernel(const int* __restrict__ ucount, const int* __restrict__ ustart,
+                                                         const uint32_t* __restrict__ ucode,
+                                                         const int* __restrict__ uweight, int mc, int nb,
+                                                         const int* __restrict__ total, uint32_t* __restrict__ zbits_u,
+                                                         int* __restrict__ colb, double* __restrict__ w_u) {
+  const int b = blockIdx.x;
+  const int n_u = ucount[b], s0 = ustart[b];
+  for (int s = threadIdx.x; s < n_u; s += 256) {
+    zbits_u[s0 + s] = ucode[size_t(b) * mc + s];
+    colb[s0 + s] = b;
+    w_u[s0 + s] = double(uweight[size_t(b) * mc + s]);
+  }
+  if (b == nb - 1) {  // pad the last column tile with harmless entries
+    for (int s = total[0] + threadIdx.x; s < total[1]; s += 256) {
+      zbits_u[s] = 0;
+      colb[s] = nb - 1;
+      w_u[s] = 0.0;
+    }
+  }
+}
+
+cudaError_t launch_dedup(const uint32_t* zbits, int nb, int mc, int nbits, int* ucount, int* ustart, int* total,
+                         uint32_t* ucode, int* uweight, int* inv, uint32_t* zbits_u, int* colb, double* w_u,
+                         cudaStream_t st) {
+  ProfScope prof_(K_SAMPLE, st);
+  if (nb == 0) return cudaSuccess;
+  const size_t smem = size_t(2) * (size_t(1) << nbits) * sizeof(int);
+  dedup_count_kernel<<<nb, 256, smem, st>>>(zbits, mc, nbits, ucount, ucode, uweight, inv);
+  dedup_offsets_kernel<<<1, 32, 0, st>>>(ucount, nb, ustart, total);
+  dedup_pack_kernel<<<nb, 256, 0, st>>>(ucount, ustart, ucode, uweight, mc, nb, total, zbits_u, colb, w_u);
+  count_launch(3);
+  return cudaGetLastError();
+}
+
+// Weighted MC reduction over the unique columns of each restart (one CTA per restart); same quantities as mc_reduce_kernel.
+__global__ void __launch_bounds__(128) mc_reduce_dedup_kernel(const DevSpace sp, const BitMap bm, int mc,
+                                                              const int* __restrict__ ucount,
+                                                              const int* __restrict__ ustart,
+                                                              const double* __restrict__ w_u,
+                                                              const uint32_t* __restrict__ zbits_u,
+                                                              const double* __restrict__ a,
+                                                              const double* __restrict__ prob,
+                                                              const double* __restrict__ S_all, int estimator,
+                                                              const double* __restrict__ ma_state,
+                                                              const double* __restrict__ grad_out,
+                                                              double* __restrict__ out_value,
+                                                              double* __restrict__ out_grad) {
+  __shared__ double red[32];
+  const int bi = blockIdx.x, tid = threadIdx.x;
+  const int n_u = ucount[bi];
+  const size_t c0 = size_t(ustart[bi]);
+  double s = 0.0;
+  for (int i = tid; i < n_u; i += blockDim.x) s = fma(w_u[c0 + i], a[c0 + i], s);
+  s = block_sum(s, red);
+  if (tid == 0) out_value[bi] = s / double(mc);
+  if (!grad_out) return;
+  double baseline = 0.0;
+  if (estimator == PRB_EST_REINFORCE_MA) {
+    const double cnt = ma_state[0];
+    if (cnt != 0.0) baseline = ma_state[1] / (1.0 - pow(0.7, cnt));
+  }
+  const double go = grad_out[bi];
+  double* g = out_grad + size_t(bi) * sp.d;
+  for (int ci = 0; ci < sp.n_cont; ++ci) {
+    const int c = sp.cont_cols[ci];
+    double t = 0.0;
+    for (int i = tid; i < n_u; i += blockDim.x) t = fma(w_u[c0 + i], S_all[(c0 + i) * sp.d_k + c], t);
+    t = block_sum(t, red);
+    if (tid == 0) g[c] = go * (t / double(mc));
+  }
+  for (int kd = 0; kd < sp.n_int; ++kd) {
+    const double p = prob[size_t(bi) * sp.n_disc + kd];
+    const int bit = bm.pos[kd];
+    double t = 0.0;
+    for (int i = tid; i < n_u; i += blockDim.x) {
+      const double zi = double((zbits_u[c0 + i] >> bit) & 1u);
+      t += w_u[c0 + i] * (((a[c0 + i] - baseline) * (zi - p)) / sp.tau);
+    }
+    t = block_sum(t, red);
+    if (tid == 0) g[sp.int_cols[kd]] = go * (t / double(mc));
+  }
+}
+
+cudaError_t launch_mc_reduce_dedup(const DevSpace& sp, const BitMap& bm, int b, int mc, const int* ucount,
+                                   const int* ustart, const double* w_u, const uint32_t* zbits_u, const double* a,
+                                   const double* prob, const double* S_all, int estimator, const double* ma_state,
+                                   const double* grad_out, double* out_value, double* out_grad, cudaStream_t st) {
+  ProfScope prof_(K_MC_REDUCE, st);
+  if (b == 0) return cudaSuccess;
+  mc_reduce_dedup_kernel<<<b, 128, 0, st>>>(sp, bm, mc, ucount, ustart, w_u, zbits_u, a, prob, S_all, estimator,
+                                            ma_state, grad_out, out_value, out_grad);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// per-sample acquisition values from the unique ones: out[b, i] = a[ustart[b] + inv[b, i]]
+__global__ void dedup_scatter_kernel(const double* __restrict__ a, const int* __restrict__ ustart,
+                                     const int* __restrict__ inv, int mc, int64_t total, double* __restrict__ out) {
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  out[idx] = a[ustart[idx / mc] + inv[idx]];
+}
+cudaError_t launch_dedup_scatter(const double* a, const int* ustart, const int* inv, int b, int mc, double* out,
+                                 cudaStream_t st) {
+  ProfScope prof_(K_MC_REDUCE, st);
+  const int64_t total = int64_t(b) * mc;
+  if (total == 0) return cudaSuccess;
+  dedup_scatter_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(a, ustart, inv, mc, total, out);
+  count_launch();
+  return cudaGetLastError();
 }
 
 // =====================================================================================================================

@@ -21,12 +21,22 @@ cudaError_t launch_kernel_matrix(const DevSpec& spec, const double* Xtr, int n, 
                                  double* out, cudaStream_t st);
 cudaError_t launch_acq_epilogue(const Model& m, const DevAcq& aq, const double* norm_part, int ncols_pad,
                                 const double* mu_dot, int ncols, double* a, double* dmu, double* dvar,
-                                double* out_mean, double* out_var, cudaStream_t st);
+                                double* out_mean, double* out_var, const int* ncols_dev, int64_t col0,
+                                cudaStream_t st);
+cudaError_t launch_dedup(const uint32_t* zbits, int nb, int mc, int nbits, int* ucount, int* ustart, int* total,
+                         uint32_t* ucode, int* uweight, int* inv, uint32_t* zbits_u, int* colb, double* w_u,
+                         cudaStream_t st);
+cudaError_t launch_mc_reduce_dedup(const DevSpace& sp, const BitMap& bm, int b, int mc, const int* ucount,
+                                   const int* ustart, const double* w_u, const uint32_t* zbits_u, const double* a,
+                                   const double* prob, const double* S_all, int estimator, const double* ma_state,
+                                   const double* grad_out, double* out_value, double* out_grad, cudaStream_t st);
+cudaError_t launch_dedup_scatter(const double* a, const int* ustart, const int* inv, int b, int mc, double* out,
+                                 cudaStream_t st);
 cudaError_t launch_grad_contract(const Model& m, uint32_t diffmask, const double* xk, int ncols, int ncols_pad,
                                  const double* W, const double* dmu, const double* dvar, double* S_part,
                                  cudaStream_t st);
 cudaError_t launch_sum_splits(const Model& m, const double* S_part, const DimMap* dm, int ncols, int ncols_pad,
-                              double* S_all, cudaStream_t st);
+                              double* S_all, const int* ncols_dev, int64_t col0, cudaStream_t st);
 cudaError_t launch_mc_reduce(const DevSpace& sp, int b, int mc, const double* a, const uint8_t* z, const double* prob,
                              const double* S_all, int estimator, const double* ma_state, const double* grad_out,
                              double* out_value, double* out_grad, cudaStream_t st);

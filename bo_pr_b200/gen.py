@@ -116,6 +116,7 @@ def _fused_mc_adam(ics: Tensor, acqf, lower, upper, lr: float, maxiter: int) -> 
     if q != 1:
         raise NotImplementedError("q > 1 is not supported by the PR path")
     state = gp_state_from_model(acqf.acq_function.model)
+    state.set_option(capi.PRB_OPT_DEDUP, int(getattr(acqf, "dedup", False)))
     rnd = acqf.input_transform["round"]
     rnd.ensure_base_samples(1, dev)
     u_int, u_cat = rnd.base_sample_ptrs()

@@ -88,6 +88,9 @@ class GPState:
                 pass
             self.handle = None
 
+    def set_option(self, option: int, value: int) -> None:
+        capi.check(self.lib.prb_model_set_option(self.handle, int(option), int(value)), "prb_model_set_option")
+
     def workspace(self, n_points: int, d_theta: int, n_restarts: int = 0) -> Tensor:
         need = int(self.lib.prb_workspace_bytes(self.handle, int(n_points), int(n_restarts), int(d_theta),
                                                 int(self.chunk_cols)))

@@ -270,10 +270,12 @@ class MCProbabilisticReparameterization(AbstractProbabilisticReparameterization)
         tau: float = 0.1,
         rng: str = "sobol",
         philox_seed: int = 0,
+        dedup: bool = False,
     ) -> None:
         super().__init__(acq_function=acq_function, dim=dim, integer_indices=integer_indices,
                          integer_bounds=integer_bounds, categorical_features=categorical_features,
                          batch_limit=batch_limit, apply_numeric=apply_numeric)
+        self.dedup = bool(dedup)  # PRB_OPT_DEDUP: evaluate each unique discrete configuration of a restart once
         if self.batch_limit is None:
             self.batch_limit = mc_samples
         if grad_estimator in ("arm", "u2g"):
@@ -292,6 +294,7 @@ class MCProbabilisticReparameterization(AbstractProbabilisticReparameterization)
         self.input_transform_flip = None
 
     def forward(self, X: Tensor) -> Tensor:
+        gp_state_from_model(self.acq_function.model).set_option(capi.PRB_OPT_DEDUP, int(self.dedup))
         return self._pr_acq_function.apply(
             X, self.acq_function, self.input_transform, self.input_transform_flip, self.batch_limit,
             self.integer_indices, self.cont_indices, self.categorical_indices, self.grad_estimator,

@@ -135,6 +135,14 @@ const char* prb_last_cuda_error(void);
  * (probabilistic_reparameterization.py:314, 491; [3P] gpytorch exact prediction strategy).                       */
 int prb_model_create(prb_model** out, const prb_model_desc* desc, void* stream);
 int prb_model_destroy(prb_model* model);
+/* Per-model options.
+ * PRB_OPT_DEDUP (default 0): in prb_mc_value_grad / prb_mc_adam on the separable kernel structure (Matern over continuous
+ *   dims x isotropic Matern over <= 12 binary dims), evaluate the base acquisition function once per UNIQUE discrete
+ *   configuration of each restart and weight it by its multiplicity.  Same result up to floating-point summation order;
+ *   the work saved grows as the PR distribution concentrates (p -> 0/1).  Throughput with this option on must be reported
+ *   separately from the per (candidate x MC sample) figure.                                                            */
+#define PRB_OPT_DEDUP 1
+int prb_model_set_option(prb_model* model, int32_t option, int64_t value);
 int prb_model_n(const prb_model* model);
 int prb_model_dk(const prb_model* model);
 

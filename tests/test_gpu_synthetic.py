@@ -174,3 +174,71 @@ def test_empty_and_single_sample_calls():
     _assert_close(grad, ref.grad, "PR gradient (mc = 1)", atol=1e-11)
     empty = pr(torch.empty(0, 1, 13, dtype=torch.float64, device=DEV))
     assert empty.shape == (0,)
+
+
+@pytest.mark.parametrize("n,b,mc", [(300, 6, 256), (129, 3, 40), (1000, 16, 1024)])
+def test_dedup_equals_plain_path(n, b, mc):
+    """PRB_OPT_DEDUP evaluates each unique discrete configuration of a restart once and weights it by its multiplicity:
+    same values / gradients / EMA state as the per-sample path up to summation order, and the same as the oracle."""
+    g = _problem(n, mc, "ei")
+    theta = make_theta(b, seed=3)
+    theta[0, 0, 3:] = torch.tensor([0.0, 1.0] * 5, dtype=torch.float64)  # a fully converged restart: one unique config
+    acq = product_acq(g, DEV)
+    outs = []
+    for dd in (False, True):
+        pr = product_mc_pr(g, DEV, acq=acq)
+        pr.dedup = dd
+        pr._ma_state.copy_(torch.tensor([4.0, 0.03], dtype=torch.float64))
+        X = theta.to(DEV).requires_grad_(True)
+        val = pr(X)
+        grad = torch.autograd.grad(val, X, grad_outputs=torch.linspace(0.5, 2.0, b, dtype=torch.float64, device=DEV))[0]
+        outs.append((val.detach().clone(), grad.clone(), pr._ma_state.clone()))
+    _assert_close(outs[1][0], outs[0][0], "value (dedup vs plain)", rtol=1e-12, atol=1e-15)
+    _assert_close(outs[1][1], outs[0][1], "gradient (dedup vs plain)", rtol=1e-11, atol=1e-14)
+    _assert_close(outs[1][2], outs[0][2], "EMA state (dedup vs plain)", rtol=1e-12, atol=0)
+    if n <= 300:
+        space, oacq = oracle_space(g), oracle_acq(g)
+        ref = P.mc_pr(space, theta, oacq, g["base_samples"], None, grad_estimator="reinforce_ma", ma_counter=4.0,
+                      ma_hidden=0.03, grad_output=torch.linspace(0.5, 2.0, b, dtype=torch.float64))
+        _assert_close(outs[1][0], ref.value, "value (dedup vs oracle)")
+        _assert_close(outs[1][1], ref.grad, "gradient (dedup vs oracle)", atol=1e-11)
+
+
+def test_dedup_per_sample_values_and_fused_adam():
+    import ctypes as C
+    from bo_pr_b200 import _capi as capi
+    from bo_pr_b200.acquisition import acq_desc_of
+    import bo_pr_b200 as B
+    g = _problem(200, 96, "ei")
+    acq = product_acq(g, DEV)
+    pr = product_mc_pr(g, DEV, acq=acq)
+    st = acq.state
+    b, mc, d = 5, 96, 13
+    th = make_theta(b, seed=9).to(DEV).reshape(b, d).contiguous()
+    rnd = pr.input_transform["round"]
+    rnd.ensure_base_samples(1, DEV)
+    ui, _ = rnd.base_sample_ptrs()
+    sp, aq = pr._space(), acq_desc_of(acq)
+    res = []
+    for dd in (0, 1):
+        st.set_option(capi.PRB_OPT_DEDUP, dd)
+        value = torch.empty(b, dtype=torch.float64, device=DEV)
+        av = torch.empty(b, mc, dtype=torch.float64, device=DEV)
+        ws = st.workspace(b * mc, d, b)
+        assert st.lib.prb_mc_value_grad(st.handle, C.byref(sp), C.byref(aq), th.data_ptr(), b, mc, ui.data_ptr(), None, 0,
+                                        0, 0, None, 0, None, value.data_ptr(), None, av.data_ptr(), ws.data_ptr(),
+                                        ws.numel(), 0, None) == 0
+        torch.cuda.synchronize()
+        res.append((value.clone(), av.clone()))
+    assert torch.equal(res[0][1], res[1][1])  # per-sample acquisition values: bitwise identical columns
+    _assert_close(res[1][0], res[0][0], "value", rtol=1e-13, atol=0)
+    # fused on-device Adam with de-duplication follows the same trajectory
+    bounds = torch.stack([torch.zeros(d, dtype=torch.float64), torch.ones(d, dtype=torch.float64)]).to(DEV)
+    ics = make_theta(4, seed=2).to(DEV)
+    outs = []
+    for dd in (False, True):
+        prx = product_mc_pr(g, DEV, acq=acq)
+        prx.dedup = dd
+        outs.append(B.gen_candidates_torch(ics, prx, bounds[0], bounds[1], options={"maxiter": 15}))
+    assert torch.allclose(outs[0][0], outs[1][0], rtol=0, atol=1e-10)
+    assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-9, atol=1e-13)
