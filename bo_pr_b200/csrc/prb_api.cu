@@ -160,6 +160,7 @@ struct Plan {
   size_t off_panelA, off_panelV, off_norm, off_mu, off_S_part;
   size_t off_Xc, off_grad, off_ones, off_val, off_step;
   size_t off_zbits, off_kc, off_Dc;
+  size_t off_done;
   size_t off_ucount, off_ustart, off_utotal, off_ucode, off_uweight, off_inv, off_zbits_u, off_colb, off_wu;
   size_t total;
 };
@@ -224,6 +225,7 @@ Plan make_plan(const Model& m, int64_t n_points, int n_restarts, int d_theta, in
   p.off_val = take(size_t(p.B_pad) * dbl);
   p.off_step = take(256);
   p.off_zbits = take(size_t(p.B_pad) * sizeof(uint32_t));
+  p.off_done = take(256);
   if (m.sep_ok && n_restarts > 0) {
     p.off_kc = take(size_t(n_restarts) * m.Kp * dbl);
     p.off_Dc = take(size_t(n_restarts) * d_theta * m.Kp * dbl);
@@ -352,9 +354,16 @@ int run_engine_sep(const Model& m, const DevAcq& aq, const Plan& pl, void* ws, c
     sa.col0 = c0;
     sa.colb = colb ? colb + c0 : nullptr;
     sa.ncols_dev = ncols_dev;
-    CUDA_TRY(launch_tma_lower_gen(m, sa, ncols_pad, need_grad ? panelV : nullptr, norm, mu, st));
-    CUDA_TRY(launch_acq_epilogue(m, aq, norm, ncols_pad, mu, ncols, a + c0, dmu + c0, dvar + c0, nullptr, nullptr,
-                                 ncols_dev, c0, st));
+    FusedAcq fa;  // used by the kernel only when the factor has a single row tile (n + 1 <= 128)
+    fa.aq = aq;
+    fa.a = a + c0;
+    fa.dmu = dmu + c0;
+    fa.dvar = dvar + c0;
+    fa.ncols = ncols;
+    CUDA_TRY(launch_tma_lower_gen(m, sa, ncols_pad, need_grad ? panelV : nullptr, norm, mu, &fa, st));
+    if (m.Mp1 > GEMM_BM)
+      CUDA_TRY(launch_acq_epilogue(m, aq, norm, ncols_pad, mu, ncols, a + c0, dmu + c0, dvar + c0, nullptr, nullptr,
+                                   ncols_dev, c0, st));
     if (need_grad) {
       CUDA_TRY(launch_tma_upper_grad(m, mapV, sa, ncols, ncols_pad, dmu + c0, dvar + c0, S_part, st));
       CUDA_TRY(launch_sum_splits(m, S_part, &dm, ncols, ncols_pad, S_all + size_t(c0) * m.d_k, ncols_dev, c0, st));
@@ -367,6 +376,61 @@ uint32_t cont_mask(const DevSpace& sp) {
   uint32_t mask = 0;
   for (int i = 0; i < sp.n_cont; ++i) mask |= 1u << sp.cont_cols[i];
   return mask;
+}
+
+// One fused step of the separable path on a single column panel (see prb_kernels.cu, "Fused optimisation step"):
+// [clamp +] kc/Dc + sampler -> lower product (+ acquisition epilogue) -> upper product (+ gradient contraction) ->
+// reductions [+ Adam] + EMA.  theta_in is read (and clamped to [lower, upper] if given); Xc receives the clamped rows.
+int sep_step(const Model& m, const DevSpace& sp, const DevAcq& aq, const Plan& pl, void* ws, const BitMap& bm,
+             const DimMap& dm, const double* theta_in, const double* lower, const double* upper, double* Xc, int b,
+             int mc, const double* u_int, const double* u_cat, uint64_t seed, uint64_t offset, int estimator,
+             double* ma_state, int update_ma, bool need_grad, const double* grad_out, double* out_value,
+             double* out_grad, double* adam_theta, double* adam_m, double* adam_v, double lr, int* step_ptr,
+             cudaStream_t st) {
+  const int ncols = b * mc;
+  const int ncols_pad = round_up(ncols, 128);
+  double* panelV = at<double>(ws, pl.off_panelV);
+  double* norm = at<double>(ws, pl.off_norm);
+  double* mu = at<double>(ws, pl.off_mu);
+  double* S_part = at<double>(ws, pl.off_S_part);
+  double* kc = at<double>(ws, pl.off_kc);
+  double* Dc = at<double>(ws, pl.off_Dc);
+  uint32_t* zbits = at<uint32_t>(ws, pl.off_zbits);
+  uint8_t* z = at<uint8_t>(ws, pl.off_z);
+  double* prob = at<double>(ws, pl.off_prob);
+  double* a = at<double>(ws, pl.off_a);
+  double* dmu = at<double>(ws, pl.off_dmu);
+  double* dvar = at<double>(ws, pl.off_dvar);
+  CUDA_TRY(launch_sep_step_prep(m, sp, bm, theta_in, lower, upper, Xc, b, mc, u_int, u_cat, seed, offset, kc,
+                                need_grad ? Dc : nullptr, need_grad ? z : nullptr, need_grad ? prob : nullptr, zbits, st));
+  SepArgs sa;
+  sa.kc = kc;
+  sa.Dc = Dc;
+  sa.zbits = zbits;
+  sa.n_cont = dm.n;
+  sa.mc = mc;
+  sa.nb = b;
+  sa.col0 = 0;
+  sa.colb = nullptr;
+  sa.ncols_dev = nullptr;
+  FusedAcq fa;
+  fa.aq = aq;
+  fa.a = a;
+  fa.dmu = dmu;
+  fa.dvar = dvar;
+  fa.ncols = ncols;
+  CUDA_TRY(launch_tma_lower_gen(m, sa, ncols_pad, need_grad ? panelV : nullptr, norm, mu, &fa, st));
+  if (m.Mp1 > GEMM_BM)
+    CUDA_TRY(launch_acq_epilogue(m, aq, norm, ncols_pad, mu, ncols, a, dmu, dvar, nullptr, nullptr, nullptr, 0, st));
+  if (need_grad) {
+    TensorMap mapV;
+    CUDA_TRY(make_operand_map(&mapV, panelV, pl.C, m.Kp, m.Mp1));
+    CUDA_TRY(launch_tma_upper_grad(m, mapV, sa, ncols, ncols_pad, dmu, dvar, S_part, st));
+  }
+  CUDA_TRY(launch_sep_step_finish(sp, dm, b, mc, a, z, prob, S_part, m.Mp2 / GEMM_BM, ncols_pad, estimator, ma_state,
+                                  update_ma, grad_out, out_value, out_grad, need_grad ? 1 : 0, adam_theta, adam_m, adam_v,
+                                  lr, step_ptr, at<unsigned int>(ws, pl.off_done), st));
+  return PRB_OK;
 }
 
 int mc_core(prb_model* model, const DevSpace& sp, const DevAcq& aq, const Plan& pl, void* ws, const double* theta,
@@ -765,9 +829,19 @@ int prb_mc_adam(prb_model* model, const prb_space_desc* space, const prb_acq_des
   const int total = b * sp.d;
   CUDA_TRY(launch_fill(ones, 1.0, b, st));
   CUDA_TRY(cudaMemcpyAsync(step, &step0, sizeof(int), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(at<unsigned int>(workspace, pl.off_done), 0, sizeof(unsigned int), st));
   const int update_ma = ma_state ? 1 : 0;
+  // separable structure on a single column panel: four fused launches per step instead of eleven
+  BitMap bm;
+  DimMap dm;
+  const bool fused_step = pl.off_kc != 0 && sep_space_ok(m, sp, &bm, &dm) && int64_t(b) * mc <= pl.C &&
+                          !(m.opt_dedup && m.sep_nbits <= DEDUP_MAX_BITS) && getenv("PRB_NO_FUSED_STEP") == nullptr;
 
   auto one_iter = [&]() -> int {
+    if (fused_step)
+      return sep_step(m, sp, aq, pl, workspace, bm, dm, theta, lower, upper, Xc, b, mc, u_int, u_cat, seed, offset,
+                      estimator, ma_state, update_ma, true, nullptr, val, grad, theta, adam_state, adam_state + total,
+                      lr, step, st);
     CUDA_TRY(launch_clamp(theta, lower, upper, b, sp.d, Xc, st));
     int r = mc_core(model, sp, aq, pl, workspace, Xc, b, mc, u_int, u_cat, seed, offset, estimator, ma_state,
                     update_ma, ones, val, grad, nullptr, st);
@@ -811,6 +885,10 @@ int prb_mc_adam(prb_model* model, const prb_space_desc* space, const prb_acq_des
     }
   }
   // final clamp + value-only evaluation (gen.py:338-341); this call also advances the EMA state like any forward
+  if (fused_step)
+    return sep_step(m, sp, aq, pl, workspace, bm, dm, theta, lower, upper, theta, b, mc, u_int, u_cat, seed, offset,
+                    estimator, ma_state, update_ma, false, nullptr, out_value, nullptr, nullptr, nullptr, nullptr, lr,
+                    nullptr, st);
   CUDA_TRY(launch_clamp(theta, lower, upper, b, sp.d, theta, st));
   return mc_core(model, sp, aq, pl, workspace, theta, b, mc, u_int, u_cat, seed, offset, estimator, ma_state,
                  update_ma, nullptr, out_value, nullptr, nullptr, st);

@@ -69,6 +69,41 @@ __device__ __forceinline__ double matern52_value(double r2) {
   return (1.0 + s5r + (5.0 / 3.0) * (r * r)) * exp(-s5r);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Base acquisition function from the posterior mean and the raw variance k** - ||v||^2, with its partial derivatives.
+//   [3P] gpytorch variance clamp (min_variance), botorch ExpectedImprovement / UpperConfidenceBound / PosteriorMean
+//   (SURVEY.md App. B.3-B.4); call sites experiment_utils.py:391-393, 476-480, 489-492.
+// ---------------------------------------------------------------------------------------------------------------------
+#define PRB_LOG_SQRT_2PI 0.91893853320467274178
+#define PRB_INV_SQRT2 0.70710678118654752440
+__device__ __forceinline__ void acq_eval(const DevAcq& aq, double mean, double var_raw, double* val, double* d_mu,
+                                         double* d_var, double* var_out) {
+  const double var = fmax(var_raw, aq.min_variance);
+  const double pass1 = (var_raw >= aq.min_variance) ? 1.0 : 0.0;
+  if (aq.kind == PRB_ACQ_EI) {
+    const double v2 = fmax(var, aq.acq_var_floor);
+    const double pass2 = (var >= aq.acq_var_floor) ? 1.0 : 0.0;
+    const double sigma = sqrt(v2);
+    const double u = (mean - aq.param) / sigma;
+    const double pdf = exp(-(u * u) / 2.0 - PRB_LOG_SQRT_2PI);
+    const double cdf = aq.ei_variant == 0 ? 0.5 * (1.0 + erf(u * PRB_INV_SQRT2)) : 0.5 * erfc(-u * PRB_INV_SQRT2);
+    *val = sigma * (pdf + u * cdf);
+    *d_mu = cdf;
+    *d_var = pdf / (2.0 * sigma) * pass1 * pass2;
+  } else if (aq.kind == PRB_ACQ_UCB) {
+    const double bv = aq.param * var;
+    const double sd = sqrt(bv);
+    *val = mean + sd;
+    *d_mu = 1.0;
+    *d_var = (sd > 0.0 ? aq.param / (2.0 * sd) : 0.0) * pass1;
+  } else {
+    *val = mean;
+    *d_mu = 1.0;
+    *d_var = 0.0;
+  }
+  *var_out = var;
+}
+
 __device__ __forceinline__ double ipow(double v, int p) {
   double r = v;
   for (int i = 1; i < p; ++i) r *= v;

@@ -28,7 +28,7 @@
 //               S[c, col] = sum_j (dA/dmu alpha_j - 2 dA/dvar W[j, col]) * kb(z_col, Z_j) * Dc[b(col), c, j]; W never hits HBM.
 #include <cuda.h>
 
-#include "prb_internal.cuh"
+#include "prb_device.cuh"
 
 namespace prb {
 
@@ -116,6 +116,14 @@ struct TmaGemmParams {
   const double* dvar;       // [ncols] dA/dsigma^2
   int ncols;                // valid columns in this panel
   double* S_part;           // [mtiles, n_cont, ncols_pad]
+  // LOWER modes with a single row tile (n + 1 <= 128): the acquisition epilogue is fused (||v||^2 and mu are complete here)
+  int fuse_acq;
+  DevAcq aq;
+  double mean_const, kss;
+  double* acq_a;     // [ncols] acquisition value
+  double* acq_dmu;   // [ncols] dA/dmu
+  double* acq_dvar;  // [ncols] dA/dsigma^2
+  int acq_ncols;
 };
 
 template <int MODE>
@@ -448,6 +456,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
         if (p.C) p.C[size_t(col) * p.ldc + row] = v;
         if (row == p.special_row) {
           p.mu_dot[col] = v;
+          red[4 * T_BN + col - n0] = v;
         } else {
           nrm[j][e] = fma(v, v, nrm[j][e]);
         }
@@ -474,6 +483,13 @@ __global__ void __launch_bounds__(T_THREADS, 1)
   if (tid < T_BN) {
     const double s = ((red[tid] + red[T_BN + tid]) + red[2 * T_BN + tid]) + red[3 * T_BN + tid];
     p.norm_part[size_t(mt) * p.ncols_pad + n0 + tid] = s;
+    if (p.fuse_acq && n0 + tid < p.acq_ncols) {
+      double val, d_mu, d_var, var;
+      acq_eval(p.aq, p.mean_const + red[4 * T_BN + tid], p.kss - s, &val, &d_mu, &d_var, &var);
+      p.acq_a[n0 + tid] = val;
+      p.acq_dmu[n0 + tid] = d_mu;
+      p.acq_dvar[n0 + tid] = d_var;
+    }
   }
   }
 }
@@ -547,7 +563,7 @@ static void fill_sep(TmaGemmParams& p, const Model& m, const SepArgs& sa) {
 }
 
 cudaError_t launch_tma_lower_gen(const Model& m, const SepArgs& sa, int ncols_pad, double* VT, double* norm_part,
-                                 double* mu_dot, cudaStream_t st) {
+                                 double* mu_dot, const FusedAcq* fa, cudaStream_t st) {
   ProfScope prof_(K_TRGEMM_LOWER, st);
   TmaGemmParams p;
   fill_common(p, m, ncols_pad, false);
@@ -556,6 +572,16 @@ cudaError_t launch_tma_lower_gen(const Model& m, const SepArgs& sa, int ncols_pa
   p.ldc = m.Mp1;
   p.norm_part = norm_part;
   p.mu_dot = mu_dot;
+  if (fa != nullptr && p.mtiles == 1) {
+    p.fuse_acq = 1;
+    p.aq = fa->aq;
+    p.mean_const = m.mean_const;
+    p.kss = m.kss;
+    p.acq_a = fa->a;
+    p.acq_dmu = fa->dmu;
+    p.acq_dvar = fa->dvar;
+    p.acq_ncols = fa->ncols;
+  }
   trgemm_tma_kernel<MODE_LOWER_GEN><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(
       *reinterpret_cast<const CUtensorMap*>(&m.mapA1), *reinterpret_cast<const CUtensorMap*>(&m.mapA1), p);
   count_launch();

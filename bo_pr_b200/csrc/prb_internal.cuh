@@ -101,6 +101,12 @@ struct BitMap {  // integer parameter k of the PR space -> bit position in the b
   int32_t pos[PRB_MAX_DIMS];
 };
 
+struct FusedAcq {  // acquisition epilogue fused into the lower product (single row tile)
+  DevAcq aq;
+  double *a, *dmu, *dvar;
+  int ncols;
+};
+
 struct DimMap {  // S_part slot -> kernel-input column
   int32_t n;
   int32_t dims[PRB_MAX_DIMS];
@@ -143,7 +149,7 @@ cudaError_t gemm_init();
 cudaError_t tma_init();
 cudaError_t make_operand_map(TensorMap* out, const double* base, int rows, int k_extent, int ld);
 cudaError_t launch_tma_lower_gen(const Model& m, const SepArgs& sa, int ncols_pad, double* VT, double* norm_part,
-                                 double* mu_dot, cudaStream_t st);
+                                 double* mu_dot, const FusedAcq* fa, cudaStream_t st);
 cudaError_t launch_tma_lower(const Model& m, const TensorMap& mapB, int ncols_pad, double* VT, double* norm_part,
                              double* mu_dot, cudaStream_t st);
 cudaError_t launch_tma_upper(const Model& m, const TensorMap& mapB, int ncols_pad, double* W, cudaStream_t st);

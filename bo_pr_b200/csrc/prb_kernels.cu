@@ -31,16 +31,14 @@ cudaError_t launch_philox_fill(uint64_t seed, uint64_t offset, int mc, int n_col
 //              OneHotToNumeric (input.py:69-88) when apply_numeric.
 // Base uniforms are indexed by (i, discrete parameter) only => shared by all restarts, as in the reference.
 // =====================================================================================================================
-__global__ void pr_sample_kernel(const DevSpace sp, const double* __restrict__ theta, int b, int mc,
-                                 const double* __restrict__ u_int, const double* __restrict__ u_cat, uint64_t seed,
-                                 uint64_t offset, double* __restrict__ xk, double* __restrict__ tilde,
-                                 uint8_t* __restrict__ zout, double* __restrict__ prob, const BitMap bm,
-                                 uint32_t* __restrict__ zbits) {
-  const int64_t col = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (col >= int64_t(b) * mc) return;
-  const int bi = int(col / mc);
-  const int i = int(col % mc);
-  const double* th = theta + size_t(bi) * sp.d;
+// one (restart bi, MC sample i) of the sampler; `th` = the restart's (clamped) theta row, `col` = bi * mc + i
+__device__ __forceinline__ void pr_sample_point(const DevSpace& sp, const double* __restrict__ th, int bi, int i,
+                                                int64_t col, const double* __restrict__ u_int,
+                                                const double* __restrict__ u_cat, uint64_t seed, uint64_t offset,
+                                                double* __restrict__ xk, double* __restrict__ tilde,
+                                                uint8_t* __restrict__ zout, double* __restrict__ prob,
+                                                const BitMap& bm, uint32_t* __restrict__ zbits) {
+
   double* xr = xk ? xk + size_t(col) * sp.d_k : nullptr;
   double* tr = tilde ? tilde + size_t(col) * sp.d : nullptr;
   uint8_t* zr = zout ? zout + size_t(col) * sp.n_disc : nullptr;
@@ -114,6 +112,19 @@ __global__ void pr_sample_kernel(const DevSpace sp, const double* __restrict__ t
     if (xr && sp.apply_numeric) xr[numeric_start + j] = double(cat);
     zpos += card;
   }
+}
+
+
+__global__ void pr_sample_kernel(const DevSpace sp, const double* __restrict__ theta, int b, int mc,
+                                 const double* __restrict__ u_int, const double* __restrict__ u_cat, uint64_t seed,
+                                 uint64_t offset, double* __restrict__ xk, double* __restrict__ tilde,
+                                 uint8_t* __restrict__ zout, double* __restrict__ prob, const BitMap bm,
+                                 uint32_t* __restrict__ zbits) {
+  const int64_t col = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (col >= int64_t(b) * mc) return;
+  const int bi = int(col / mc);
+  pr_sample_point(sp, theta + size_t(bi) * sp.d, bi, int(col % mc), col, u_int, u_cat, seed, offset, xk, tilde, zout,
+                  prob, bm, zbits);
 }
 
 cudaError_t launch_pr_sample(const DevSpace& sp, const double* theta, int b, int mc, const double* u_int,
@@ -382,9 +393,6 @@ cudaError_t launch_pad_copy(const double* src, int n, int n_pad, double* dst, cu
 //   reference: [3P] gpytorch variance clamp (min_variance), botorch ExpectedImprovement / UpperConfidenceBound /
 //   PosteriorMean; call sites experiment_utils.py:391-393, 476-480, 489-492.
 // =====================================================================================================================
-#define PRB_LOG_SQRT_2PI 0.91893853320467274178
-#define PRB_INV_SQRT2 0.70710678118654752440
-
 __global__ void acq_epilogue_kernel(const DevAcq aq, double mean_const, double kss, const double* __restrict__ norm_part,
                                     int mtiles, int ncols_pad, const double* __restrict__ mu_dot, int ncols,
                                     double* __restrict__ a, double* __restrict__ dmu, double* __restrict__ dvar,
@@ -395,32 +403,9 @@ __global__ void acq_epilogue_kernel(const DevAcq aq, double mean_const, double k
   if (ncols_dev != nullptr && col0 + col >= int64_t(*ncols_dev)) return;
   double vs = 0.0;
   for (int t = 0; t < mtiles; ++t) vs += norm_part[size_t(t) * ncols_pad + col];
-  const double var_raw = kss - vs;
-  const double var = fmax(var_raw, aq.min_variance);
-  const double pass1 = (var_raw >= aq.min_variance) ? 1.0 : 0.0;
-  const double mean = mean_const + mu_dot[col];
-  double val, d_mu, d_var;
-  if (aq.kind == PRB_ACQ_EI) {
-    const double v2 = fmax(var, aq.acq_var_floor);
-    const double pass2 = (var >= aq.acq_var_floor) ? 1.0 : 0.0;
-    const double sigma = sqrt(v2);
-    const double u = (mean - aq.param) / sigma;
-    const double pdf = exp(-(u * u) / 2.0 - PRB_LOG_SQRT_2PI);
-    const double cdf = aq.ei_variant == 0 ? 0.5 * (1.0 + erf(u * PRB_INV_SQRT2)) : 0.5 * erfc(-u * PRB_INV_SQRT2);
-    val = sigma * (pdf + u * cdf);
-    d_mu = cdf;
-    d_var = pdf / (2.0 * sigma) * pass1 * pass2;
-  } else if (aq.kind == PRB_ACQ_UCB) {
-    const double bv = aq.param * var;
-    const double sd = sqrt(bv);
-    val = mean + sd;
-    d_mu = 1.0;
-    d_var = (sd > 0.0 ? aq.param / (2.0 * sd) : 0.0) * pass1;
-  } else {
-    val = mean;
-    d_mu = 1.0;
-    d_var = 0.0;
-  }
+  double val, d_mu, d_var, mean, var;
+  acq_eval(aq, mean_const + mu_dot[col], kss - vs, &val, &d_mu, &d_var, &var);
+  mean = mean_const + mu_dot[col];
   a[col] = val;
   if (dmu) dmu[col] = d_mu;
   if (dvar) dvar[col] = d_var;
@@ -978,6 +963,170 @@ cudaError_t launch_analytic_reduce(const DevSpace& sp, const double* theta, int 
   ProfScope prof_(K_ANALYTIC, st);
   if (b == 0) return cudaSuccess;
   analytic_reduce_kernel<<<b, 128, 0, st>>>(sp, theta, n_opt, options, a, probs, S_all, grad_out, out_value, out_grad);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// =====================================================================================================================
+// Fused optimisation step for the separable path (prb_mc_adam): at experiment sizes (n <= 220, 640 evaluations per step)
+// the step is launch-latency bound, so the eleven launches of the unfused sequence are merged into four:
+//   sep_step_prep    clamp(theta) + per-restart kernel factors (kc, Dc) + sampler          (one CTA per restart)
+//   lower product    with the acquisition epilogue fused when there is a single row tile   (prb_gemm_tma.cu)
+//   upper product    with the gradient contraction fused                                   (prb_gemm_tma.cu)
+//   sep_step_finish  split sums + MC reduction + Adam update (one CTA per restart); the last CTA to finish advances the EMA
+//                    baseline and the step counter
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) sep_step_prep_kernel(
+    const DevSpace sp, const BitMap bm, const DevFactor fc, double outputscale, const double* __restrict__ Xtr, int n,
+    int d_k, int Kp, const double* __restrict__ theta, const double* __restrict__ lower,
+    const double* __restrict__ upper, double* __restrict__ Xc, int mc, const double* __restrict__ u_int,
+    const double* __restrict__ u_cat, uint64_t seed, uint64_t offset, double* __restrict__ kc, double* __restrict__ Dc,
+    uint8_t* __restrict__ z, double* __restrict__ prob, uint32_t* __restrict__ zbits) {
+  __shared__ double th_s[PRB_MAX_DIMS];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (tid < sp.d) {
+    double v = theta[size_t(b) * sp.d + tid];
+    if (lower) v = fmin(fmax(v, lower[tid]), upper[tid]);  // columnwise_clamp (gen.py:304-305, 323)
+    th_s[tid] = v;
+    if (Xc) Xc[size_t(b) * sp.d + tid] = v;
+  }
+  __syncthreads();
+  for (int j = tid; j < Kp; j += 256) {
+    double val = 0.0, G = 0.0;
+    if (j < n) {
+      double r2 = 0.0;
+      for (int di = 0; di < fc.n_dims; ++di) {
+        const int dim = fc.dims[di];
+        const double df = (th_s[dim] - Xtr[size_t(j) * d_k + dim]) * fc.inv_ls[di];
+        r2 = fma(df, df, r2);
+      }
+      val = outputscale * matern52(r2, &G);
+    }
+    kc[size_t(b) * Kp + j] = val;
+    if (Dc) {
+      for (int di = 0; di < fc.n_dims; ++di) {
+        const int dim = fc.dims[di];
+        double v = 0.0;
+        if (j < n) v = outputscale * G * (fc.inv_ls[di] * fc.inv_ls[di]) * (th_s[dim] - Xtr[size_t(j) * d_k + dim]);
+        Dc[(size_t(b) * fc.n_dims + di) * Kp + j] = v;
+      }
+    }
+  }
+  for (int i = tid; i < mc; i += 256)
+    pr_sample_point(sp, th_s, b, i, int64_t(b) * mc + i, u_int, u_cat, seed, offset, nullptr, nullptr, z, prob, bm, zbits);
+}
+
+cudaError_t launch_sep_step_prep(const Model& m, const DevSpace& sp, const BitMap& bm, const double* theta,
+                                 const double* lower, const double* upper, double* Xc, int nb, int mc,
+                                 const double* u_int, const double* u_cat, uint64_t seed, uint64_t offset, double* kc,
+                                 double* Dc, uint8_t* z, double* prob, uint32_t* zbits, cudaStream_t st) {
+  ProfScope prof_(K_SAMPLE, st);
+  if (nb == 0) return cudaSuccess;
+  sep_step_prep_kernel<<<nb, 256, 0, st>>>(sp, bm, m.spec.t[0].f[m.sep_cont_factor], m.spec.t[0].outputscale, m.Xtr, m.n,
+                                          m.d_k, m.Kp, theta, lower, upper, Xc, mc, u_int, u_cat, seed, offset, kc, Dc, z,
+                                          prob, zbits);
+  count_launch();
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(128) sep_step_finish_kernel(
+    const DevSpace sp, const DimMap dm, int mc, const double* __restrict__ a, const uint8_t* __restrict__ z,
+    const double* __restrict__ prob, const double* __restrict__ S_part, int mtiles, int ncols_pad, int estimator,
+    double* __restrict__ ma_state, int update_ma, const double* __restrict__ grad_out, double* __restrict__ out_value,
+    double* __restrict__ out_grad, int need_grad, double* __restrict__ theta, double* __restrict__ adam_m,
+    double* __restrict__ adam_v, double lr, int* __restrict__ step_ptr, unsigned int* __restrict__ done, int nb) {
+  __shared__ double red[32];
+  __shared__ double g_s[PRB_MAX_DIMS];
+  __shared__ int last_s;
+  const int bi = blockIdx.x, tid = threadIdx.x;
+  const size_t c0 = size_t(bi) * mc;
+  // everything that depends on the pre-call optimiser / EMA state is read before this CTA signals completion
+  double baseline = 0.0;
+  if (estimator == PRB_EST_REINFORCE_MA && ma_state != nullptr) {
+    const double cnt = ma_state[0];
+    if (cnt != 0.0) baseline = ma_state[1] / (1.0 - pow(0.7, cnt));
+  }
+  const double t_step = step_ptr ? double(*step_ptr + 1) : 1.0;
+  double s = 0.0;
+  for (int i = tid; i < mc; i += blockDim.x) s += a[c0 + i];
+  s = block_sum(s, red);
+  if (tid == 0) out_value[bi] = s / double(mc);
+  if (need_grad) {
+    const double go = grad_out ? grad_out[bi] : 1.0;
+    if (tid < sp.d) g_s[tid] = 0.0;
+    __syncthreads();
+    for (int ci = 0; ci < dm.n; ++ci) {
+      double t = 0.0;
+      for (int i = tid; i < mc; i += blockDim.x) {
+        double v = 0.0;
+        for (int mt = 0; mt < mtiles; ++mt) v += S_part[(size_t(mt) * dm.n + ci) * ncols_pad + c0 + i];
+        t += v;
+      }
+      t = block_sum(t, red);
+      if (tid == 0) g_s[dm.dims[ci]] = go * (t / double(mc));
+    }
+    for (int kd = 0; kd < sp.n_int; ++kd) {
+      const double p = prob[size_t(bi) * sp.n_disc + kd];
+      double t = 0.0;
+      for (int i = tid; i < mc; i += blockDim.x) {
+        const double zi = double(z[(c0 + i) * sp.n_disc + kd]);
+        t += ((a[c0 + i] - baseline) * (zi - p)) / sp.tau;
+      }
+      t = block_sum(t, red);
+      if (tid == 0) g_s[sp.int_cols[kd]] = go * (t / double(mc));
+    }
+    __syncthreads();
+    if (tid < sp.d) {
+      const double gacq = g_s[tid];
+      if (out_grad) out_grad[size_t(bi) * sp.d + tid] = gacq;
+      if (theta != nullptr) {  // torch.optim.Adam on loss = -acq(X).sum() (same arithmetic as adam_step_kernel)
+        const size_t idx = size_t(bi) * sp.d + tid;
+        const double g = -gacq;
+        const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+        const double mi = adam_m[idx] + (g - adam_m[idx]) * (1.0 - b1);
+        const double vi = adam_v[idx] * b2 + (1.0 - b2) * g * g;
+        adam_m[idx] = mi;
+        adam_v[idx] = vi;
+        const double bc1 = 1.0 - pow(b1, t_step);
+        const double bc2 = 1.0 - pow(b2, t_step);
+        theta[idx] = theta[idx] - (lr / bc1) * (mi / (sqrt(vi) / sqrt(bc2) + eps));
+      }
+    }
+  }
+  // last CTA to finish: EMA baseline update over ALL restarts of the call (probabilistic_reparameterization.py:499-505),
+  // fixed summation order; step counter; re-arm the completion counter for the next launch
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last_s = (atomicAdd(done, 1u) == unsigned(nb - 1)) ? 1 : 0;
+  __syncthreads();
+  if (last_s) {
+    __threadfence();
+    double v = 0.0;
+    for (int i = tid; i < nb; i += blockDim.x) v += __ldcg(out_value + i);
+    v = block_sum(v, red);
+    if (tid == 0) {
+      if (update_ma && ma_state != nullptr) {
+        const double mean = v / double(nb);
+        const double hidden = ma_state[1];
+        ma_state[0] += 1.0;
+        ma_state[1] = hidden - (hidden - mean) * (1.0 - 0.7);
+      }
+      if (step_ptr && theta != nullptr) *step_ptr += 1;
+      *done = 0u;
+    }
+  }
+}
+
+cudaError_t launch_sep_step_finish(const DevSpace& sp, const DimMap& dm, int nb, int mc, const double* a, const uint8_t* z,
+                                   const double* prob, const double* S_part, int mtiles, int ncols_pad, int estimator,
+                                   double* ma_state, int update_ma, const double* grad_out, double* out_value,
+                                   double* out_grad, int need_grad, double* theta, double* adam_m, double* adam_v,
+                                   double lr, int* step_ptr, unsigned int* done, cudaStream_t st) {
+  ProfScope prof_(K_MC_REDUCE, st);
+  if (nb == 0) return cudaSuccess;
+  sep_step_finish_kernel<<<nb, 128, 0, st>>>(sp, dm, mc, a, z, prob, S_part, mtiles, ncols_pad, estimator, ma_state,
+                                             update_ma, grad_out, out_value, out_grad, need_grad, theta, adam_m, adam_v,
+                                             lr, step_ptr, done, nb);
   count_launch();
   return cudaGetLastError();
 }
