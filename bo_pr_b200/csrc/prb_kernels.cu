@@ -31,20 +31,48 @@ cudaError_t launch_philox_fill(uint64_t seed, uint64_t offset, int mc, int n_col
 //              OneHotToNumeric (input.py:69-88) when apply_numeric.
 // Base uniforms are indexed by (i, discrete parameter) only => shared by all restarts, as in the reference.
 // =====================================================================================================================
-// one (restart bi, MC sample i) of the sampler; `th` = the restart's (clamped) theta row, `col` = bi * mc + i
-__device__ __forceinline__ void pr_sample_point(const DevSpace& sp, const double* __restrict__ th, int bi, int i,
-                                                int64_t col, const double* __restrict__ u_int,
-                                                const double* __restrict__ u_cat, uint64_t seed, uint64_t offset,
-                                                double* __restrict__ xk, double* __restrict__ tilde,
-                                                uint8_t* __restrict__ zout, double* __restrict__ prob,
-                                                const BitMap& bm, uint32_t* __restrict__ zbits) {
+// Rounding probabilities of one restart (input.py:613-635).  They do not depend on the MC sample, so they are computed
+// once per restart by `nworkers` cooperating threads (worker id t): ps[0 .. n_int) integer probabilities, offs[k] =
+// floor|x_un|, ps[n_int ..) the normalised softmax entries of every one-hot block, in `discrete_indices` order.
+__device__ __forceinline__ void pr_restart_probs(const DevSpace& sp, const double* __restrict__ th, int t, int nworkers,
+                                                 double* __restrict__ ps, double* __restrict__ offs) {
+  for (int k = t; k < sp.n_int; k += nworkers) {
+    const double x = th[sp.int_cols[k]];
+    const double x_un = sp.raw_int ? x : unnormalize_int(x, sp.int_lo[k], sp.int_hi[k]);
+    double off;
+    ps[k] = int_round_prob(x_un, sp.tau, &off);
+    offs[k] = off;
+  }
+  for (int j = t; j < sp.n_cat; j += nworkers) {
+    int zpos = sp.n_int;
+    for (int jj = 0; jj < j; ++jj) zpos += sp.cat_card[jj];
+    const int s = sp.cat_start[j], card = sp.cat_card[j];
+    double* pk = ps + zpos;
+    double mx = -1e300;
+    for (int k = 0; k < card; ++k) {
+      pk[k] = __dsub_rn(th[s + k], 0.5) / sp.tau;
+      mx = fmax(mx, pk[k]);
+    }
+    double sum = 0.0;
+    for (int k = 0; k < card; ++k) {
+      pk[k] = exp(__dsub_rn(pk[k], mx));
+      sum = __dadd_rn(sum, pk[k]);
+    }
+    const double inv = 1.0 / sum;
+    for (int k = 0; k < card; ++k) pk[k] = __dmul_rn(pk[k], inv);
+  }
+}
 
-  double* xr = xk ? xk + size_t(col) * sp.d_k : nullptr;
-  double* tr = tilde ? tilde + size_t(col) * sp.d : nullptr;
-  uint8_t* zr = zout ? zout + size_t(col) * sp.n_disc : nullptr;
-  double* pr = (prob && i == 0) ? prob + size_t(bi) * sp.n_disc : nullptr;
+// One (restart, MC sample i) of the sampler.  `th` = the restart's theta row, ps / offs from pr_restart_probs.
+// Row outputs (any may be NULL): xr [d_k] kernel input, tr [d] tilde_x, zr [n_disc] rounding components; returns the bit
+// code over the binary dims selected by `bm`.
+__device__ __forceinline__ uint32_t pr_sample_point(const DevSpace& sp, const double* __restrict__ th,
+                                                    const double* __restrict__ ps, const double* __restrict__ offs,
+                                                    int i, const double* __restrict__ u_int,
+                                                    const double* __restrict__ u_cat, uint64_t seed, uint64_t offset,
+                                                    double* __restrict__ xr, double* __restrict__ tr,
+                                                    uint8_t* __restrict__ zr, const BitMap& bm) {
   const int numeric_start = sp.n_cat > 0 ? sp.cat_start[0] : sp.d;
-
   for (int c = 0; c < sp.d; ++c) {
     const double v = th[c];
     if (tr) tr[c] = v;
@@ -58,44 +86,28 @@ __device__ __forceinline__ void pr_sample_point(const DevSpace& sp, const double
     const double lo = sp.int_lo[k], hi = sp.int_hi[k];
     const double range = __dsub_rn(hi, lo);
     const double x_un = sp.raw_int ? x : unnormalize_int(x, lo, hi);
-    double off;
-    const double p = int_round_prob(x_un, sp.tau, &off);
     const double u = u_int ? u_int[size_t(i) * sp.n_int + k] : philox_uniform(seed, offset, uint32_t(i), uint32_t(k));
-    const double zb = (p >= u) ? 1.0 : 0.0;
-    const double xa = off + zb;
+    const double zb = (ps[k] >= u) ? 1.0 : 0.0;
+    const double xa = offs[k] + zb;
     const double xs = (x_un < 0.0) ? -xa : xa;
     const double xc = fmin(fmax(xs, lo), hi);
     const double tn = sp.raw_int ? xc : __dsub_rn(xc, lo) / range;
     if (tr) tr[c] = tn;
     if (xr) xr[c] = tn;
     if (zr) zr[k] = ((__dsub_rn(tn, x) > 0.0) || (x == 1.0)) ? 1 : 0;
-    if (pr) pr[k] = p;
     if (bm.pos[k] >= 0 && tn != 0.0) bits |= 1u << bm.pos[k];
   }
-  if (zbits) zbits[col] = bits;
-  // ---- categoricals (input.py:715-744): softmax((x - 0.5)/tau), sequential cumsum, first index with cum > u (else 0)
+  // ---- categoricals (input.py:715-744): sequential cumsum of the softmax, first index with cum > u (else 0)
   int zpos = sp.n_int;
   for (int j = 0; j < sp.n_cat; ++j) {
     const int s = sp.cat_start[j], card = sp.cat_card[j];
-    double pk[PRB_MAX_CARD];
-    double mx = -1e300;
-    for (int k = 0; k < card; ++k) {
-      pk[k] = __dsub_rn(th[s + k], 0.5) / sp.tau;
-      mx = fmax(mx, pk[k]);
-    }
-    double sum = 0.0;
-    for (int k = 0; k < card; ++k) {
-      pk[k] = exp(__dsub_rn(pk[k], mx));
-      sum = __dadd_rn(sum, pk[k]);
-    }
-    const double inv = 1.0 / sum;
+    const double* pk = ps + zpos;
     const double u = u_cat ? u_cat[size_t(i) * sp.n_cat + j]
                            : philox_uniform(seed, offset, uint32_t(i), uint32_t(sp.n_int + j));
     int cat = 0;
     bool found = false;
     double cum = 0.0;
     for (int k = 0; k < card; ++k) {
-      pk[k] = __dmul_rn(pk[k], inv);
       cum = __dadd_rn(cum, pk[k]);
       if (!found && cum > u) {
         cat = k;
@@ -107,36 +119,69 @@ __device__ __forceinline__ void pr_sample_point(const DevSpace& sp, const double
       if (tr) tr[s + k] = oh;
       if (xr && !sp.apply_numeric) xr[s + k] = oh;
       if (zr) zr[zpos + k] = (k == cat) ? 1 : 0;
-      if (pr) pr[zpos + k] = pk[k];
     }
     if (xr && sp.apply_numeric) xr[numeric_start + j] = double(cat);
     zpos += card;
   }
+  return bits;
 }
 
-
-__global__ void pr_sample_kernel(const DevSpace sp, const double* __restrict__ theta, int b, int mc,
-                                 const double* __restrict__ u_int, const double* __restrict__ u_cat, uint64_t seed,
-                                 uint64_t offset, double* __restrict__ xk, double* __restrict__ tilde,
-                                 uint8_t* __restrict__ zout, double* __restrict__ prob, const BitMap bm,
-                                 uint32_t* __restrict__ zbits) {
-  const int64_t col = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (col >= int64_t(b) * mc) return;
-  const int bi = int(col / mc);
-  pr_sample_point(sp, theta + size_t(bi) * sp.d, bi, int(col % mc), col, u_int, u_cat, seed, offset, xk, tilde, zout,
-                  prob, bm, zbits);
+// grid (ceil(mc / 128), b): a CTA samples 128 MC draws of one restart.  Rows are staged in shared memory and written out
+// with fully coalesced stores (a row per thread would stride 8 d bytes: 12 % of HBM peak measured; profiles/).
+constexpr int SAMPLE_ROWS = 128;
+__global__ void __launch_bounds__(SAMPLE_ROWS) pr_sample_kernel(
+    const DevSpace sp, const double* __restrict__ theta, int b, int mc, const double* __restrict__ u_int,
+    const double* __restrict__ u_cat, uint64_t seed, uint64_t offset, double* __restrict__ xk,
+    double* __restrict__ tilde, uint8_t* __restrict__ zout, double* __restrict__ prob, const BitMap bm,
+    uint32_t* __restrict__ zbits) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double* ps = reinterpret_cast<double*>(smraw);          // [n_disc]
+  double* offs = ps + sp.n_disc;                          // [n_int]
+  double* st_t = offs + sp.n_int;                         // [128][d]    if tilde
+  double* st_x = st_t + (tilde ? SAMPLE_ROWS * sp.d : 0); // [128][d_k]  if xk
+  uint8_t* st_z = reinterpret_cast<uint8_t*>(st_x + (xk ? SAMPLE_ROWS * sp.d_k : 0));  // [128][n_disc] if zout
+  const int bi = blockIdx.y, tid = threadIdx.x;
+  const int i0 = blockIdx.x * SAMPLE_ROWS;
+  const int i = i0 + tid;
+  const int nrows = min(SAMPLE_ROWS, mc - i0);
+  const double* th = theta + size_t(bi) * sp.d;
+  pr_restart_probs(sp, th, tid, SAMPLE_ROWS, ps, offs);
+  __syncthreads();
+  if (i < mc) {
+    const uint32_t bits = pr_sample_point(sp, th, ps, offs, i, u_int, u_cat, seed, offset,
+                                          xk ? st_x + tid * sp.d_k : nullptr, tilde ? st_t + tid * sp.d : nullptr,
+                                          zout ? st_z + tid * sp.n_disc : nullptr, bm);
+    if (zbits) zbits[size_t(bi) * mc + i] = bits;
+  }
+  if (prob && blockIdx.x == 0)
+    for (int k = tid; k < sp.n_disc; k += SAMPLE_ROWS) prob[size_t(bi) * sp.n_disc + k] = ps[k];
+  __syncthreads();
+  const size_t row0 = size_t(bi) * mc + i0;
+  if (tilde)
+    for (int e = tid; e < nrows * sp.d; e += SAMPLE_ROWS) tilde[row0 * sp.d + e] = st_t[e];
+  if (xk)
+    for (int e = tid; e < nrows * sp.d_k; e += SAMPLE_ROWS) xk[row0 * sp.d_k + e] = st_x[e];
+  if (zout)
+    for (int e = tid; e < nrows * sp.n_disc; e += SAMPLE_ROWS) zout[row0 * sp.n_disc + e] = st_z[e];
 }
 
 cudaError_t launch_pr_sample(const DevSpace& sp, const double* theta, int b, int mc, const double* u_int,
                              const double* u_cat, uint64_t seed, uint64_t offset, double* xk, double* tilde,
                              uint8_t* z, double* prob, const BitMap* bm, uint32_t* zbits, cudaStream_t st) {
   ProfScope prof_(K_SAMPLE, st);
-  const int64_t total = int64_t(b) * mc;
-  if (total == 0) return cudaSuccess;
+  if (int64_t(b) * mc == 0) return cudaSuccess;
   BitMap none;
   for (int k = 0; k < PRB_MAX_DIMS; ++k) none.pos[k] = -1;
-  pr_sample_kernel<<<unsigned((total + 127) / 128), 128, 0, st>>>(sp, theta, b, mc, u_int, u_cat, seed, offset, xk,
-                                                                 tilde, z, prob, bm ? *bm : none, bm ? zbits : nullptr);
+  const size_t smem = size_t(sp.n_disc + sp.n_int) * sizeof(double) +
+                      (tilde ? size_t(SAMPLE_ROWS) * sp.d * sizeof(double) : 0) +
+                      (xk ? size_t(SAMPLE_ROWS) * sp.d_k * sizeof(double) : 0) + (z ? size_t(SAMPLE_ROWS) * sp.n_disc : 0);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(pr_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+  }
+  dim3 grid((mc + SAMPLE_ROWS - 1) / SAMPLE_ROWS, b);
+  pr_sample_kernel<<<grid, SAMPLE_ROWS, smem, st>>>(sp, theta, b, mc, u_int, u_cat, seed, offset, xk, tilde, z, prob,
+                                                   bm ? *bm : none, bm ? zbits : nullptr);
   count_launch();
   return cudaGetLastError();
 }
@@ -983,6 +1028,7 @@ __global__ void __launch_bounds__(256) sep_step_prep_kernel(
     const double* __restrict__ u_cat, uint64_t seed, uint64_t offset, double* __restrict__ kc, double* __restrict__ Dc,
     uint8_t* __restrict__ z, double* __restrict__ prob, uint32_t* __restrict__ zbits) {
   __shared__ double th_s[PRB_MAX_DIMS];
+  __shared__ double ps_s[PRB_MAX_DIMS], offs_s[PRB_MAX_DIMS];  // the separable path has no categoricals: n_disc = n_int
   const int b = blockIdx.x, tid = threadIdx.x;
   if (tid < sp.d) {
     double v = theta[size_t(b) * sp.d + tid];
@@ -991,6 +1037,10 @@ __global__ void __launch_bounds__(256) sep_step_prep_kernel(
     if (Xc) Xc[size_t(b) * sp.d + tid] = v;
   }
   __syncthreads();
+  pr_restart_probs(sp, th_s, tid, 256, ps_s, offs_s);
+  __syncthreads();
+  if (prob)
+    for (int k = tid; k < sp.n_disc; k += 256) prob[size_t(b) * sp.n_disc + k] = ps_s[k];
   for (int j = tid; j < Kp; j += 256) {
     double val = 0.0, G = 0.0;
     if (j < n) {
@@ -1012,8 +1062,11 @@ __global__ void __launch_bounds__(256) sep_step_prep_kernel(
       }
     }
   }
-  for (int i = tid; i < mc; i += 256)
-    pr_sample_point(sp, th_s, b, i, int64_t(b) * mc + i, u_int, u_cat, seed, offset, nullptr, nullptr, z, prob, bm, zbits);
+  for (int i = tid; i < mc; i += 256) {
+    const size_t col = size_t(b) * mc + i;
+    zbits[col] = pr_sample_point(sp, th_s, ps_s, offs_s, i, u_int, u_cat, seed, offset, nullptr, nullptr,
+                                 z ? z + col * sp.n_disc : nullptr, bm);
+  }
 }
 
 cudaError_t launch_sep_step_prep(const Model& m, const DevSpace& sp, const BitMap& bm, const double* theta,
