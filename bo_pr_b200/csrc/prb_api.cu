@@ -339,8 +339,6 @@ int run_engine_sep(const Model& m, const DevAcq& aq, const Plan& pl, void* ws, c
   const int* colb = dedup ? at<int>(ws, pl.off_colb) : nullptr;
   const int* ncols_dev = dedup ? at<int>(ws, pl.off_utotal) : nullptr;
   CUDA_TRY(launch_sep_restart_prep(m, theta, nb, d_theta, kc, need_grad ? Dc : nullptr, st));
-  TensorMap mapV;
-  if (need_grad) CUDA_TRY(make_operand_map(&mapV, panelV, pl.C, m.Kp, m.Mp1));
   for (int64_t c0 = 0; c0 < B; c0 += pl.C) {
     const int ncols = int(B - c0 < pl.C ? B - c0 : pl.C);
     const int ncols_pad = round_up(ncols, 128);
@@ -365,7 +363,7 @@ int run_engine_sep(const Model& m, const DevAcq& aq, const Plan& pl, void* ws, c
       CUDA_TRY(launch_acq_epilogue(m, aq, norm, ncols_pad, mu, ncols, a + c0, dmu + c0, dvar + c0, nullptr, nullptr,
                                    ncols_dev, c0, st));
     if (need_grad) {
-      CUDA_TRY(launch_tma_upper_grad(m, mapV, sa, ncols, ncols_pad, dmu + c0, dvar + c0, S_part, st));
+      CUDA_TRY(launch_tma_upper_grad(m, panelV, pl.C, sa, ncols, ncols_pad, dmu + c0, dvar + c0, S_part, st));
       CUDA_TRY(launch_sum_splits(m, S_part, &dm, ncols, ncols_pad, S_all + size_t(c0) * m.d_k, ncols_dev, c0, st));
     }
   }
@@ -422,11 +420,7 @@ int sep_step(const Model& m, const DevSpace& sp, const DevAcq& aq, const Plan& p
   CUDA_TRY(launch_tma_lower_gen(m, sa, ncols_pad, need_grad ? panelV : nullptr, norm, mu, &fa, st));
   if (m.Mp1 > GEMM_BM)
     CUDA_TRY(launch_acq_epilogue(m, aq, norm, ncols_pad, mu, ncols, a, dmu, dvar, nullptr, nullptr, nullptr, 0, st));
-  if (need_grad) {
-    TensorMap mapV;
-    CUDA_TRY(make_operand_map(&mapV, panelV, pl.C, m.Kp, m.Mp1));
-    CUDA_TRY(launch_tma_upper_grad(m, mapV, sa, ncols, ncols_pad, dmu, dvar, S_part, st));
-  }
+  if (need_grad) CUDA_TRY(launch_tma_upper_grad(m, panelV, pl.C, sa, ncols, ncols_pad, dmu, dvar, S_part, st));
   CUDA_TRY(launch_sep_step_finish(sp, dm, b, mc, a, z, prob, S_part, m.Mp2 / GEMM_BM, ncols_pad, estimator, ma_state,
                                   update_ma, grad_out, out_value, out_grad, need_grad ? 1 : 0, adam_theta, adam_m, adam_v,
                                   lr, step_ptr, at<unsigned int>(ws, pl.off_done), st));

@@ -28,6 +28,8 @@
 //               S[c, col] = sum_j (dA/dmu alpha_j - 2 dA/dvar W[j, col]) * kb(z_col, Z_j) * Dc[b(col), c, j]; W never hits HBM.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "prb_device.cuh"
 
 namespace prb {
@@ -126,12 +128,17 @@ struct TmaGemmParams {
   int acq_ncols;
 };
 
-template <int MODE>
+// BN = evaluation columns per tile: 128 for throughput; 32 for small problems, where a 128-wide tiling would leave most
+// of the 148 SMs idle and the step is bound by ONE SM's DMMA rate (n = 119, 640 columns: 5 tiles, 23 us per product).
+template <int MODE, int BN>
 __global__ void __launch_bounds__(T_THREADS, 1)
     trgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const TmaGemmParams p) {
   constexpr bool UPPER = (MODE == MODE_UPPER_W || MODE == MODE_UPPER_GRAD);
   constexpr bool GEN = (MODE == MODE_LOWER_GEN);
+  constexpr int TJ = BN / 16;          // 8 x 8 accumulator tiles per warp along N (warp = 32 rows x BN / 2 columns)
+  constexpr int B_CHUNK = BN * 4;      // doubles per k-chunk of the B operand
+  constexpr int B_OPER = BN * T_BK;    // doubles per k-tile of the B operand
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* stages = reinterpret_cast<double*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + size_t(T_STAGES) * T_STAGE_DOUBLES * 8);
@@ -150,7 +157,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
   const int mi_sched = t / p.ntiles;
   const int mt = UPPER ? mi_sched : (p.mtiles - 1 - mi_sched);
   const int m0 = mt * T_BM;
-  const int n0 = nt * T_BN;
+  const int n0 = nt * BN;
   int kbeg, kend;
   if (UPPER) {
     kbeg = m0;
@@ -184,8 +191,9 @@ __global__ void __launch_bounds__(T_THREADS, 1)
   // ---- B-operand generation: thread <-> (evaluation column, 8 of the 16 k values of a k-tile) ---------------------------
   // (the 32-byte column stride of the STS.128 below costs 2-way bank conflicts, 21 M per launch; a lane-pair-per-column
   //  mapping that removes them needs 8 instead of 6 global loads per thread and k-tile and measured 1.7 % SLOWER)
-  const int gcol = tid & (T_BN - 1);
-  const int ghalf = tid >> 7;
+  // BN = 32: thread <-> (column, one pair of the 16 k values)
+  const int gcol = tid & (BN - 1);
+  const int ghalf = tid / BN;
   uint32_t g_zb = 0;
   const double* g_kc = nullptr;
   if (GEN) {
@@ -204,56 +212,69 @@ __global__ void __launch_bounds__(T_THREADS, 1)
     double* As = stages + s * T_STAGE_DOUBLES;
     double* Bs = As + T_OPER_DOUBLES;
     if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
-    mbar_arrive_expect_tx(&full[s], (GEN ? 1 : 2) * T_OPER_DOUBLES * 8);
+    mbar_arrive_expect_tx(&full[s], (T_OPER_DOUBLES + (GEN ? 0 : B_OPER)) * 8);
 #pragma unroll
     for (int c = 0; c < 4; ++c) tma_load_2d(As + c * T_CHUNK_DOUBLES, &tmA, &full[s], k0 + 4 * c, m0);
     if (!GEN) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tma_load_2d(Bs + c * T_CHUNK_DOUBLES, &tmB, &full[s], k0 + 4 * c, n0);
+      for (int c = 0; c < 4; ++c) tma_load_2d(Bs + c * B_CHUNK, &tmB, &full[s], k0 + 4 * c, n0);
     }
   };
   // generated B operand: global loads are issued a whole k-tile of DMMA work before they are consumed
   double2 g_k01, g_k23, g_k45, g_k67;
   uint4 g_za, g_zc;
+  uint2 g_zs;
   auto gen_load = [&](int kt) {
     const int k0 = kbeg + kt * T_BK;
-    const double2* kc2 = reinterpret_cast<const double2*>(g_kc + k0 + ghalf * 8);
-    const uint4* zz = reinterpret_cast<const uint4*>(p.Zbits + k0 + ghalf * 8);
-    g_k01 = __ldg(kc2);
-    g_k23 = __ldg(kc2 + 1);
-    g_k45 = __ldg(kc2 + 2);
-    g_k67 = __ldg(kc2 + 3);
-    g_za = __ldg(zz);
-    g_zc = __ldg(zz + 1);
+    if constexpr (BN == 128) {
+      const double2* kc2 = reinterpret_cast<const double2*>(g_kc + k0 + ghalf * 8);
+      const uint4* zz = reinterpret_cast<const uint4*>(p.Zbits + k0 + ghalf * 8);
+      g_k01 = __ldg(kc2);
+      g_k23 = __ldg(kc2 + 1);
+      g_k45 = __ldg(kc2 + 2);
+      g_k67 = __ldg(kc2 + 3);
+      g_za = __ldg(zz);
+      g_zc = __ldg(zz + 1);
+    } else {
+      g_k01 = __ldg(reinterpret_cast<const double2*>(g_kc + k0 + ghalf * 2));
+      g_zs = __ldg(reinterpret_cast<const uint2*>(p.Zbits + k0 + ghalf * 2));
+    }
   };
   auto gen_store = [&](int kt) {
     const int s = kt % T_STAGES;
     const int use = kt / T_STAGES;
     double* Bs = stages + s * T_STAGE_DOUBLES + T_OPER_DOUBLES;
     if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
-    double2 o0, o1, o2, o3;
-    o0.x = g_k01.x * tab_s[__popc(g_zb ^ g_za.x)];
-    o0.y = g_k01.y * tab_s[__popc(g_zb ^ g_za.y)];
-    o1.x = g_k23.x * tab_s[__popc(g_zb ^ g_za.z)];
-    o1.y = g_k23.y * tab_s[__popc(g_zb ^ g_za.w)];
-    o2.x = g_k45.x * tab_s[__popc(g_zb ^ g_zc.x)];
-    o2.y = g_k45.y * tab_s[__popc(g_zb ^ g_zc.y)];
-    o3.x = g_k67.x * tab_s[__popc(g_zb ^ g_zc.z)];
-    o3.y = g_k67.y * tab_s[__popc(g_zb ^ g_zc.w)];
-    double2* d0 = reinterpret_cast<double2*>(Bs + (2 * ghalf) * T_CHUNK_DOUBLES + gcol * 4);
-    double2* d1 = reinterpret_cast<double2*>(Bs + (2 * ghalf + 1) * T_CHUNK_DOUBLES + gcol * 4);
-    d0[0] = o0;
-    d0[1] = o1;
-    d1[0] = o2;
-    d1[1] = o3;
+    if constexpr (BN == 128) {
+      double2 o0, o1, o2, o3;
+      o0.x = g_k01.x * tab_s[__popc(g_zb ^ g_za.x)];
+      o0.y = g_k01.y * tab_s[__popc(g_zb ^ g_za.y)];
+      o1.x = g_k23.x * tab_s[__popc(g_zb ^ g_za.z)];
+      o1.y = g_k23.y * tab_s[__popc(g_zb ^ g_za.w)];
+      o2.x = g_k45.x * tab_s[__popc(g_zb ^ g_zc.x)];
+      o2.y = g_k45.y * tab_s[__popc(g_zb ^ g_zc.y)];
+      o3.x = g_k67.x * tab_s[__popc(g_zb ^ g_zc.z)];
+      o3.y = g_k67.y * tab_s[__popc(g_zb ^ g_zc.w)];
+      double2* d0 = reinterpret_cast<double2*>(Bs + (2 * ghalf) * B_CHUNK + gcol * 4);
+      double2* d1 = reinterpret_cast<double2*>(Bs + (2 * ghalf + 1) * B_CHUNK + gcol * 4);
+      d0[0] = o0;
+      d0[1] = o1;
+      d1[0] = o2;
+      d1[1] = o3;
+    } else {
+      double2 o;
+      o.x = g_k01.x * tab_s[__popc(g_zb ^ g_zs.x)];
+      o.y = g_k01.y * tab_s[__popc(g_zb ^ g_zs.y)];
+      *reinterpret_cast<double2*>(Bs + (ghalf >> 1) * B_CHUNK + gcol * 4 + (ghalf & 1) * 2) = o;
+    }
     mbar_arrive(&full[s]);
   };
 
-  double acc[4][8][2];
+  double acc[4][TJ][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < TJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   for (int kt = 0; kt < T_AHEAD && kt < num_k; ++kt) {
     produce_tma(kt);
@@ -275,7 +296,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
   int fa_off[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) fa_off[i] = (8 * grp[i] + frag_r) * 4 + frag_k;
-  const int fb_off = (wn * 64 + frag_r) * 4 + frag_k;
+  const int fb_off = (wn * (8 * TJ) + frag_r) * 4 + frag_k;
 
   for (int kt = 0; kt < num_k; ++kt) {
     const int nk = kt + T_AHEAD;
@@ -291,15 +312,15 @@ __global__ void __launch_bounds__(T_THREADS, 1)
     if (q0 < 0 || q0 >= T_BM) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        double a[4], b[8];
+        double a[4], b[TJ];
 #pragma unroll
         for (int i = 0; i < 4; ++i) a[i] = pa[c * T_CHUNK_DOUBLES + fa_off[i]];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) b[j] = pb[c * T_CHUNK_DOUBLES + j * 32];
+        for (int j = 0; j < TJ; ++j) b[j] = pb[c * B_CHUNK + j * 32];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+          for (int j = 0; j < TJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
       }
     } else {
       // diagonal block: sub-block (8 rows of group g) x (4 k values at offset q) of A is all zero when
@@ -315,15 +336,15 @@ __global__ void __launch_bounds__(T_THREADS, 1)
           any = any || act[i];
         }
         if (!any) continue;
-        double b[8];
+        double b[TJ];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) b[j] = pb[c * T_CHUNK_DOUBLES + j * 32];
+        for (int j = 0; j < TJ; ++j) b[j] = pb[c * B_CHUNK + j * 32];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (act[i]) {
             const double a = pa[c * T_CHUNK_DOUBLES + fa_off[i]];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a, b[j]);
+            for (int j = 0; j < TJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a, b[j]);
           }
         }
       }
@@ -338,7 +359,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
   int rows[4];  // global row of accumulator sub-tile i for this lane
 #pragma unroll
   for (int i = 0; i < 4; ++i) rows[i] = m0 + 8 * grp[i] + frag_r;
-  const int col_base = n0 + wn * 64 + 2 * frag_k;  // + 8 * j + e
+  const int col_base = n0 + wn * (8 * TJ) + 2 * frag_k;  // + 8 * j + e
   double* red = stages;                            // [4][128] scratch
 
   if constexpr (MODE == MODE_UPPER_W) {
@@ -346,7 +367,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
     for (int i = 0; i < 4; ++i) {
       double* crow = p.C + size_t(rows[i]) * p.ldc + col_base;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) *reinterpret_cast<double2*>(crow + 8 * j) = make_double2(acc[i][j][0], acc[i][j][1]);
+      for (int j = 0; j < TJ; ++j) *reinterpret_cast<double2*>(crow + 8 * j) = make_double2(acc[i][j][0], acc[i][j][1]);
     }
     return;
   }
@@ -361,7 +382,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
       Zr[i] = p.Zbits[rows[i]];
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < TJ; ++j)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int col = col_base + 8 * j + e;
@@ -375,19 +396,19 @@ __global__ void __launch_bounds__(T_THREADS, 1)
       }
     // restart index of the tile's first / last column: one restart per tile is the common case (mc % 128 == 0)
     int64_t b_lo = p.colb ? int64_t(p.colb[n0]) : (p.col0 + n0) / p.mc;
-    int64_t b_hi = p.colb ? int64_t(p.colb[n0 + T_BN - 1]) : (p.col0 + n0 + T_BN - 1) / p.mc;
+    int64_t b_hi = p.colb ? int64_t(p.colb[n0 + BN - 1]) : (p.col0 + n0 + BN - 1) / p.mc;
     if (b_lo > p.nb - 1) b_lo = p.nb - 1;
     if (b_hi > p.nb - 1) b_hi = p.nb - 1;
     const bool single = (b_lo == b_hi);
     for (int c = 0; c < p.n_cont; ++c) {
-      double part[8][2];
+      double part[TJ][2];
       if (single) {
         const double* D = p.Dc + (size_t(b_lo) * p.n_cont + c) * p.Kp;
         double dr[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) dr[i] = (rows[i] < p.Kp) ? D[rows[i]] : 0.0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < TJ; ++j)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             double s = 0.0;
@@ -397,7 +418,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
           }
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < TJ; ++j)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             int64_t br = p.colb ? int64_t(p.colb[col_base + 8 * j + e]) : (p.col0 + col_base + 8 * j + e) / p.mc;
@@ -414,7 +435,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
       }
       // sum over the 8 row-lanes (lane bits 2..4), then over the 4 M-warps, in a fixed order
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+      for (int j = 0; j < TJ; ++j)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           double v = part[j][e];
@@ -425,13 +446,13 @@ __global__ void __launch_bounds__(T_THREADS, 1)
         }
       if (frag_r == 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < TJ; ++j)
 #pragma unroll
-          for (int e = 0; e < 2; ++e) red[wm * T_BN + wn * 64 + 8 * j + 2 * frag_k + e] = part[j][e];
+          for (int e = 0; e < 2; ++e) red[wm * BN + wn * (8 * TJ) + 8 * j + 2 * frag_k + e] = part[j][e];
       }
       __syncthreads();
-      if (tid < T_BN) {
-        const double s = ((red[tid] + red[T_BN + tid]) + red[2 * T_BN + tid]) + red[3 * T_BN + tid];
+      if (tid < BN) {
+        const double s = ((red[tid] + red[BN + tid]) + red[2 * BN + tid]) + red[3 * BN + tid];
         p.S_part[(size_t(mt) * p.n_cont + c) * p.ncols_pad + n0 + tid] = s;
       }
       __syncthreads();
@@ -441,14 +462,14 @@ __global__ void __launch_bounds__(T_THREADS, 1)
 
   if constexpr (!UPPER) {
   // lower: V^T[col, row]; 8 lanes (frag_r = 0..7) write 64 contiguous bytes per column
-  double nrm[8][2];
+  double nrm[TJ][2];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) nrm[j][0] = nrm[j][1] = 0.0;
+  for (int j = 0; j < TJ; ++j) nrm[j][0] = nrm[j][1] = 0.0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int row = rows[i];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < TJ; ++j) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int col = col_base + 8 * j + e;
@@ -456,7 +477,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
         if (p.C) p.C[size_t(col) * p.ldc + row] = v;
         if (row == p.special_row) {
           p.mu_dot[col] = v;
-          red[4 * T_BN + col - n0] = v;
+          red[4 * BN + col - n0] = v;
         } else {
           nrm[j][e] = fma(v, v, nrm[j][e]);
         }
@@ -464,7 +485,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
+  for (int j = 0; j < TJ; ++j)
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       double v = nrm[j][e];
@@ -475,17 +496,17 @@ __global__ void __launch_bounds__(T_THREADS, 1)
     }
   if (frag_r == 0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < TJ; ++j)
 #pragma unroll
-      for (int e = 0; e < 2; ++e) red[wm * T_BN + wn * 64 + 8 * j + 2 * frag_k + e] = nrm[j][e];
+      for (int e = 0; e < 2; ++e) red[wm * BN + wn * (8 * TJ) + 8 * j + 2 * frag_k + e] = nrm[j][e];
   }
   __syncthreads();
-  if (tid < T_BN) {
-    const double s = ((red[tid] + red[T_BN + tid]) + red[2 * T_BN + tid]) + red[3 * T_BN + tid];
+  if (tid < BN) {
+    const double s = ((red[tid] + red[BN + tid]) + red[2 * BN + tid]) + red[3 * BN + tid];
     p.norm_part[size_t(mt) * p.ncols_pad + n0 + tid] = s;
     if (p.fuse_acq && n0 + tid < p.acq_ncols) {
       double val, d_mu, d_var, var;
-      acq_eval(p.aq, p.mean_const + red[4 * T_BN + tid], p.kss - s, &val, &d_mu, &d_var, &var);
+      acq_eval(p.aq, p.mean_const + red[4 * BN + tid], p.kss - s, &val, &d_mu, &d_var, &var);
       p.acq_a[n0 + tid] = val;
       p.acq_dmu[n0 + tid] = d_mu;
       p.acq_dvar[n0 + tid] = d_var;
@@ -509,26 +530,27 @@ cudaError_t tma_init() {
     if (q != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  cudaError_t e;
-  if ((e = cudaFuncSetAttribute(trgemm_tma_kernel<MODE_LOWER_GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                int(T_SMEM_BYTES))) != cudaSuccess)
-    return e;
-  if ((e = cudaFuncSetAttribute(trgemm_tma_kernel<MODE_LOWER_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                int(T_SMEM_BYTES))) != cudaSuccess)
-    return e;
-  if ((e = cudaFuncSetAttribute(trgemm_tma_kernel<MODE_UPPER_W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                int(T_SMEM_BYTES))) != cudaSuccess)
-    return e;
-  return cudaFuncSetAttribute(trgemm_tma_kernel<MODE_UPPER_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              int(T_SMEM_BYTES));
+  const void* kernels[] = {
+      reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_LOWER_GEN, 128>),
+      reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_LOWER_GEN, 32>),
+      reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_LOWER_TMA, 128>),
+      reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_UPPER_W, 128>),
+      reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_UPPER_GRAD, 128>),
+      reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_UPPER_GRAD, 32>),
+  };
+  for (const void* k : kernels) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(T_SMEM_BYTES));
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
-// 2-D map over a row-major [rows, ld] matrix whose contraction index is contiguous: box = 4 k values x 128 rows
-cudaError_t make_operand_map(TensorMap* out, const double* base, int rows, int k_extent, int ld) {
+// 2-D map over a row-major [rows, ld] matrix whose contraction index is contiguous: box = 4 k values x box_rows rows
+cudaError_t make_operand_map(TensorMap* out, const double* base, int rows, int k_extent, int ld, int box_rows) {
   if (!g_encode) return cudaErrorNotReady;
   cuuint64_t gdim[2] = {cuuint64_t(k_extent), cuuint64_t(rows)};
   cuuint64_t gstride[1] = {cuuint64_t(ld) * sizeof(double)};
-  cuuint32_t box[2] = {4, cuuint32_t(T_BM)};
+  cuuint32_t box[2] = {4, cuuint32_t(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2,
                         const_cast<double*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -537,10 +559,18 @@ cudaError_t make_operand_map(TensorMap* out, const double* base, int rows, int k
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-static void fill_common(TmaGemmParams& p, const Model& m, int ncols_pad, bool upper) {
+// column-tile width: 128 unless that leaves most SMs without a tile (small problems are bound by one SM's DMMA rate)
+static int pick_bn(const Model& m, int ncols_pad, bool upper) {
+  static const int force = getenv("PRB_BN") ? atoi(getenv("PRB_BN")) : 0;
+  if (force == 32 || force == 128) return force;
+  const int tiles128 = ((upper ? m.Mp2 : m.Mp1) / T_BM) * (ncols_pad / 128);
+  return tiles128 < 120 ? 32 : 128;
+}
+
+static void fill_common(TmaGemmParams& p, const Model& m, int ncols_pad, bool upper, int bn = T_BN) {
   memset(&p, 0, sizeof(p));
   p.mtiles = (upper ? m.Mp2 : m.Mp1) / T_BM;
-  p.ntiles = ncols_pad / T_BN;
+  p.ntiles = ncols_pad / bn;
   p.Kp = m.Kp;
   p.ncols_pad = ncols_pad;
   p.special_row = upper ? -1 : m.n;
@@ -566,7 +596,8 @@ cudaError_t launch_tma_lower_gen(const Model& m, const SepArgs& sa, int ncols_pa
                                  double* mu_dot, const FusedAcq* fa, cudaStream_t st) {
   ProfScope prof_(K_TRGEMM_LOWER, st);
   TmaGemmParams p;
-  fill_common(p, m, ncols_pad, false);
+  const int bn = pick_bn(m, ncols_pad, false);
+  fill_common(p, m, ncols_pad, false, bn);
   fill_sep(p, m, sa);
   p.C = VT;
   p.ldc = m.Mp1;
@@ -582,8 +613,11 @@ cudaError_t launch_tma_lower_gen(const Model& m, const SepArgs& sa, int ncols_pa
     p.acq_dvar = fa->dvar;
     p.acq_ncols = fa->ncols;
   }
-  trgemm_tma_kernel<MODE_LOWER_GEN><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(
-      *reinterpret_cast<const CUtensorMap*>(&m.mapA1), *reinterpret_cast<const CUtensorMap*>(&m.mapA1), p);
+  const CUtensorMap& mA = *reinterpret_cast<const CUtensorMap*>(&m.mapA1);
+  if (bn == 32)
+    trgemm_tma_kernel<MODE_LOWER_GEN, 32><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(mA, mA, p);
+  else
+    trgemm_tma_kernel<MODE_LOWER_GEN, 128><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(mA, mA, p);
   count_launch();
   return cudaGetLastError();
 }
@@ -597,7 +631,7 @@ cudaError_t launch_tma_lower(const Model& m, const TensorMap& mapB, int ncols_pa
   p.ldc = m.Mp1;
   p.norm_part = norm_part;
   p.mu_dot = mu_dot;
-  trgemm_tma_kernel<MODE_LOWER_TMA><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(
+  trgemm_tma_kernel<MODE_LOWER_TMA, 128><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(
       *reinterpret_cast<const CUtensorMap*>(&m.mapA1), *reinterpret_cast<const CUtensorMap*>(&mapB), p);
   count_launch();
   return cudaGetLastError();
@@ -609,24 +643,33 @@ cudaError_t launch_tma_upper(const Model& m, const TensorMap& mapB, int ncols_pa
   fill_common(p, m, ncols_pad, true);
   p.C = W;
   p.ldc = ncols_pad;
-  trgemm_tma_kernel<MODE_UPPER_W><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(
+  trgemm_tma_kernel<MODE_UPPER_W, 128><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(
       *reinterpret_cast<const CUtensorMap*>(&m.mapA2), *reinterpret_cast<const CUtensorMap*>(&mapB), p);
   count_launch();
   return cudaGetLastError();
 }
 
-cudaError_t launch_tma_upper_grad(const Model& m, const TensorMap& mapB, const SepArgs& sa, int ncols, int ncols_pad,
-                                  const double* dmu, const double* dvar, double* S_part, cudaStream_t st) {
+cudaError_t launch_tma_upper_grad(const Model& m, const double* panelV, int panel_rows, const SepArgs& sa, int ncols,
+                                  int ncols_pad, const double* dmu, const double* dvar, double* S_part,
+                                  cudaStream_t st) {
   ProfScope prof_(K_TRGEMM_UPPER, st);
   TmaGemmParams p;
-  fill_common(p, m, ncols_pad, true);
+  const int bn = pick_bn(m, ncols_pad, true);
+  fill_common(p, m, ncols_pad, true, bn);
   fill_sep(p, m, sa);
   p.dmu = dmu;
   p.dvar = dvar;
   p.ncols = ncols;
   p.S_part = S_part;
-  trgemm_tma_kernel<MODE_UPPER_GRAD><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(
-      *reinterpret_cast<const CUtensorMap*>(&m.mapA2), *reinterpret_cast<const CUtensorMap*>(&mapB), p);
+  TensorMap mapV;  // the v panel [panel_rows, Mp1], box = 4 k values x bn columns
+  cudaError_t e = make_operand_map(&mapV, panelV, panel_rows, m.Kp, m.Mp1, bn);
+  if (e != cudaSuccess) return e;
+  const CUtensorMap& mA = *reinterpret_cast<const CUtensorMap*>(&m.mapA2);
+  const CUtensorMap& mB = *reinterpret_cast<const CUtensorMap*>(&mapV);
+  if (bn == 32)
+    trgemm_tma_kernel<MODE_UPPER_GRAD, 32><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(mA, mB, p);
+  else
+    trgemm_tma_kernel<MODE_UPPER_GRAD, 128><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(mA, mB, p);
   count_launch();
   return cudaGetLastError();
 }

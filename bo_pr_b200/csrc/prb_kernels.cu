@@ -1082,7 +1082,17 @@ cudaError_t launch_sep_step_prep(const Model& m, const DevSpace& sp, const BitMa
   return cudaGetLastError();
 }
 
-__global__ void __launch_bounds__(128) sep_step_finish_kernel(
+constexpr int FINISH_THREADS = 512;
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One CTA per restart, one WARP per reduction (value, each continuous column, each discrete column): no block-wide
+// barrier inside the reductions -- at experiment sizes the step is latency bound and thirteen sequential block reductions
+// cost 17 us; this form costs ~3 us.  Fixed lane-strided order + xor-tree => deterministic.
+__global__ void __launch_bounds__(FINISH_THREADS) sep_step_finish_kernel(
     const DevSpace sp, const DimMap dm, int mc, const double* __restrict__ a, const uint8_t* __restrict__ z,
     const double* __restrict__ prob, const double* __restrict__ S_part, int mtiles, int ncols_pad, int estimator,
     double* __restrict__ ma_state, int update_ma, const double* __restrict__ grad_out, double* __restrict__ out_value,
@@ -1091,7 +1101,7 @@ __global__ void __launch_bounds__(128) sep_step_finish_kernel(
   __shared__ double red[32];
   __shared__ double g_s[PRB_MAX_DIMS];
   __shared__ int last_s;
-  const int bi = blockIdx.x, tid = threadIdx.x;
+  const int bi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t c0 = size_t(bi) * mc;
   // everything that depends on the pre-call optimiser / EMA state is read before this CTA signals completion
   double baseline = 0.0;
@@ -1100,50 +1110,49 @@ __global__ void __launch_bounds__(128) sep_step_finish_kernel(
     if (cnt != 0.0) baseline = ma_state[1] / (1.0 - pow(0.7, cnt));
   }
   const double t_step = step_ptr ? double(*step_ptr + 1) : 1.0;
-  double s = 0.0;
-  for (int i = tid; i < mc; i += blockDim.x) s += a[c0 + i];
-  s = block_sum(s, red);
-  if (tid == 0) out_value[bi] = s / double(mc);
-  if (need_grad) {
-    const double go = grad_out ? grad_out[bi] : 1.0;
-    if (tid < sp.d) g_s[tid] = 0.0;
-    __syncthreads();
-    for (int ci = 0; ci < dm.n; ++ci) {
-      double t = 0.0;
-      for (int i = tid; i < mc; i += blockDim.x) {
+  const double go = (need_grad && grad_out) ? grad_out[bi] : 1.0;
+  const int n_tasks = need_grad ? 1 + dm.n + sp.n_int : 1;
+  for (int task = warp; task < n_tasks; task += FINISH_THREADS / 32) {
+    double t = 0.0;
+    if (task == 0) {
+      for (int i = lane; i < mc; i += 32) t += a[c0 + i];
+      t = warp_sum(t);
+      if (lane == 0) out_value[bi] = t / double(mc);
+    } else if (task <= dm.n) {
+      const int ci = task - 1;
+      for (int i = lane; i < mc; i += 32) {
         double v = 0.0;
         for (int mt = 0; mt < mtiles; ++mt) v += S_part[(size_t(mt) * dm.n + ci) * ncols_pad + c0 + i];
         t += v;
       }
-      t = block_sum(t, red);
-      if (tid == 0) g_s[dm.dims[ci]] = go * (t / double(mc));
-    }
-    for (int kd = 0; kd < sp.n_int; ++kd) {
+      t = warp_sum(t);
+      if (lane == 0) g_s[dm.dims[ci]] = go * (t / double(mc));
+    } else {
+      const int kd = task - 1 - dm.n;
       const double p = prob[size_t(bi) * sp.n_disc + kd];
-      double t = 0.0;
-      for (int i = tid; i < mc; i += blockDim.x) {
+      for (int i = lane; i < mc; i += 32) {
         const double zi = double(z[(c0 + i) * sp.n_disc + kd]);
         t += ((a[c0 + i] - baseline) * (zi - p)) / sp.tau;
       }
-      t = block_sum(t, red);
-      if (tid == 0) g_s[sp.int_cols[kd]] = go * (t / double(mc));
+      t = warp_sum(t);
+      if (lane == 0) g_s[sp.int_cols[kd]] = go * (t / double(mc));
     }
-    __syncthreads();
-    if (tid < sp.d) {
-      const double gacq = g_s[tid];
-      if (out_grad) out_grad[size_t(bi) * sp.d + tid] = gacq;
-      if (theta != nullptr) {  // torch.optim.Adam on loss = -acq(X).sum() (same arithmetic as adam_step_kernel)
-        const size_t idx = size_t(bi) * sp.d + tid;
-        const double g = -gacq;
-        const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
-        const double mi = adam_m[idx] + (g - adam_m[idx]) * (1.0 - b1);
-        const double vi = adam_v[idx] * b2 + (1.0 - b2) * g * g;
-        adam_m[idx] = mi;
-        adam_v[idx] = vi;
-        const double bc1 = 1.0 - pow(b1, t_step);
-        const double bc2 = 1.0 - pow(b2, t_step);
-        theta[idx] = theta[idx] - (lr / bc1) * (mi / (sqrt(vi) / sqrt(bc2) + eps));
-      }
+  }
+  __syncthreads();
+  if (need_grad && tid < sp.d) {
+    const double gacq = g_s[tid];
+    if (out_grad) out_grad[size_t(bi) * sp.d + tid] = gacq;
+    if (theta != nullptr) {  // torch.optim.Adam on loss = -acq(X).sum() (same arithmetic as adam_step_kernel)
+      const size_t idx = size_t(bi) * sp.d + tid;
+      const double g = -gacq;
+      const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+      const double mi = adam_m[idx] + (g - adam_m[idx]) * (1.0 - b1);
+      const double vi = adam_v[idx] * b2 + (1.0 - b2) * g * g;
+      adam_m[idx] = mi;
+      adam_v[idx] = vi;
+      const double bc1 = 1.0 - pow(b1, t_step);
+      const double bc2 = 1.0 - pow(b2, t_step);
+      theta[idx] = theta[idx] - (lr / bc1) * (mi / (sqrt(vi) / sqrt(bc2) + eps));
     }
   }
   // last CTA to finish: EMA baseline update over ALL restarts of the call (probabilistic_reparameterization.py:499-505),
@@ -1177,7 +1186,7 @@ cudaError_t launch_sep_step_finish(const DevSpace& sp, const DimMap& dm, int nb,
                                    double lr, int* step_ptr, unsigned int* done, cudaStream_t st) {
   ProfScope prof_(K_MC_REDUCE, st);
   if (nb == 0) return cudaSuccess;
-  sep_step_finish_kernel<<<nb, 128, 0, st>>>(sp, dm, mc, a, z, prob, S_part, mtiles, ncols_pad, estimator, ma_state,
+  sep_step_finish_kernel<<<nb, FINISH_THREADS, 0, st>>>(sp, dm, mc, a, z, prob, S_part, mtiles, ncols_pad, estimator, ma_state,
                                              update_ma, grad_out, out_value, out_grad, need_grad, theta, adam_m, adam_v,
                                              lr, step_ptr, done, nb);
   count_launch();
