@@ -249,16 +249,6 @@ T* at(void* ws, size_t off) {
 }
 
 // ---- the posterior/acquisition engine over L2-resident column panels ------------------------------------------------
-// PRB_ENGINE=v1 selects the first-generation cp.async GEMM (kept for A/B measurements); default: TMA + mbarrier kernels
-int engine_version() {
-  static int v = 0;
-  if (v == 0) {
-    const char* e = getenv("PRB_ENGINE");
-    v = (e && strcmp(e, "v1") == 0) ? 1 : 2;
-  }
-  return v;
-}
-
 // generic kernel structures: materialised k* panel -> lower product -> epilogue -> upper product -> gradient contraction
 int run_engine(const Model& m, const DevAcq& aq, const Plan& pl, void* ws, const double* xk, int64_t B, bool need_grad,
                uint32_t diffmask, double* a, double* dmu, double* dvar, double* S_all, double* out_mean,
@@ -268,28 +258,19 @@ int run_engine(const Model& m, const DevAcq& aq, const Plan& pl, void* ws, const
   double* norm = at<double>(ws, pl.off_norm);
   double* mu = at<double>(ws, pl.off_mu);
   double* S_part = at<double>(ws, pl.off_S_part);
-  const bool v2 = engine_version() == 2;
   TensorMap mapK, mapV;
-  if (v2) {
-    CUDA_TRY(make_operand_map(&mapK, panelA, pl.C, m.Kp, m.Kp));
-    CUDA_TRY(make_operand_map(&mapV, panelV, pl.C, m.Kp, m.Mp1));
-  }
+  CUDA_TRY(make_operand_map(&mapK, panelA, pl.C, m.Kp, m.Kp));
+  CUDA_TRY(make_operand_map(&mapV, panelV, pl.C, m.Kp, m.Mp1));
   for (int64_t c0 = 0; c0 < B; c0 += pl.C) {
     const int ncols = int(B - c0 < pl.C ? B - c0 : pl.C);
     const int ncols_pad = round_up(ncols, 128);
     const double* xkc = xk + size_t(c0) * m.d_k;
     CUDA_TRY(launch_kstar_panel(m, xkc, ncols, ncols_pad, panelA, st));
-    if (v2)
-      CUDA_TRY(launch_tma_lower(m, mapK, ncols_pad, need_grad ? panelV : nullptr, norm, mu, st));
-    else
-      CUDA_TRY(launch_trgemm_lower(m, panelA, ncols_pad, panelV, norm, mu, st));
+    CUDA_TRY(launch_tma_lower(m, mapK, ncols_pad, need_grad ? panelV : nullptr, norm, mu, st));
     CUDA_TRY(launch_acq_epilogue(m, aq, norm, ncols_pad, mu, ncols, a + c0, dmu + c0, dvar + c0,
                                  out_mean ? out_mean + c0 : nullptr, out_var ? out_var + c0 : nullptr, nullptr, 0, st));
     if (need_grad) {
-      if (v2)
-        CUDA_TRY(launch_tma_upper(m, mapV, ncols_pad, panelA, st));
-      else
-        CUDA_TRY(launch_trgemm_upper(m, panelV, ncols_pad, panelA, st));
+      CUDA_TRY(launch_tma_upper(m, mapV, ncols_pad, panelA, st));
       CUDA_TRY(launch_grad_contract(m, diffmask, xkc, ncols, ncols_pad, panelA, dmu + c0, dvar + c0, S_part, st));
       CUDA_TRY(launch_sum_splits(m, S_part, nullptr, ncols, ncols_pad, S_all + size_t(c0) * m.d_k, nullptr, 0, st));
     }
@@ -300,7 +281,7 @@ int run_engine(const Model& m, const DevAcq& aq, const Plan& pl, void* ws, const
 // Does this PR space line up with the model's separable structure?  Every integer parameter must be a binary dim of the
 // binary factor (bounds [0, 1]), there are no categoricals, and the continuous columns are exactly the other factor's.
 bool sep_space_ok(const Model& m, const DevSpace& sp, BitMap* bm, DimMap* dm) {
-  if (!m.sep_ok || engine_version() != 2 || sp.n_cat != 0 || sp.d != m.d_k || sp.raw_int) return false;
+  if (!m.sep_ok || sp.n_cat != 0 || sp.d != m.d_k || sp.raw_int) return false;
   const DevFactor& fb = m.spec.t[0].f[m.sep_bin_factor];
   const DevFactor& fc = m.spec.t[0].f[m.sep_cont_factor];
   if (sp.n_int != fb.n_dims || sp.n_cont != fc.n_dims) return false;
@@ -592,7 +573,6 @@ int prb_model_create(prb_model** out, const prb_model_desc* desc, void* stream) 
     e = cudaGetLastError();
     count_launch();
   }
-  if (e == cudaSuccess) e = gemm_init();
   // second-generation engine: TMA descriptors of the packed factors, padded alpha, separable-structure tables
   const int n_pad = m->Mp1 > m->Mp2 ? m->Mp1 : m->Mp2;
   int* bad_flag = nullptr;

@@ -11,7 +11,9 @@
 // live in registers, so there is no TMEM stage.  What IS Blackwell-native here: operand tiles arrive by TMA
 // (cp.async.bulk.tensor, one elected thread, no per-thread address arithmetic) into a dense [k-chunk][row][4] layout that
 // makes every DMMA fragment load a fully coalesced, conflict-free 256-byte LDS.64; stage hand-off is by full/empty
-// mbarriers (no __syncthreads in the main loop, producer runs two k-tiles ahead).
+// mbarriers (no __syncthreads in the main loop, producer runs two k-tiles ahead).  The first-generation kernel of this
+// round (cp.async + bar.sync per k-tile, materialised operands; removed) reached 56 % of the DMMA peak: the LDGSTS address
+// registers were recycled by the next LDS (long-scoreboard stall, 15 % of samples) and every k-tile ended in a CTA barrier.
 //
 // Tuning record (B200, n = 1000, 65 536 columns; profiles/): 4 stages / producer 2 k-tiles ahead beats 5/3, 5/2 and 4/3;
 // 8 warps of 32 x 64 (246-254 registers, 1 CTA/SM) beat 16 warps of 32 x 32 (128 registers): 4.49 vs 4.79 ms per step;

@@ -49,13 +49,8 @@ struct DevAcq {
   double param, min_variance, acq_var_floor;
 };
 
-constexpr int GEMM_BM = 128;
-constexpr int GEMM_BN = 128;
-constexpr int GEMM_BK = 16;
-constexpr int GEMM_STAGES = 4;
-constexpr int GEMM_LDS = GEMM_BK + 4;  // padded smem row stride (doubles): (row*20 + k) mod 16 distinct per half-warp
-constexpr int GEMM_THREADS = 256;
-constexpr size_t GEMM_SMEM_BYTES = size_t(GEMM_STAGES) * 2 * GEMM_BM * GEMM_LDS * sizeof(double);
+constexpr int GEMM_BM = 128;  // row tile of the triangular products (prb_gemm_tma.cu)
+constexpr int GEMM_BK = 16;   // contraction tile; Kp is a multiple of it
 
 constexpr int GRAD_JSPLIT_ROWS = 128;  // rows of W handled by one CTA of the gradient contraction
 
@@ -138,12 +133,6 @@ struct Model {
 };
 
 constexpr int DEDUP_MAX_BITS = 12;  // histogram de-duplication: 2^12 bins of shared memory per restart
-
-// launchers (prb_gemm.cu / prb_kernels.cu); all enqueue on `st` and return the CUDA status
-cudaError_t launch_trgemm_lower(const Model& m, const double* KstarT, int ncols_pad, double* VT, double* norm_part,
-                                double* mu_dot, cudaStream_t st);
-cudaError_t launch_trgemm_upper(const Model& m, const double* VT, int ncols_pad, double* W, cudaStream_t st);
-cudaError_t gemm_init();
 
 // prb_gemm_tma.cu
 cudaError_t tma_init();

@@ -144,8 +144,10 @@ def gen_batch_initial_conditions(
             X_rnd = fix_features(X_rnd, fixed_features=fixed_features)
             with torch.no_grad():
                 limit = X_rnd.shape[0] if batch_limit is None else batch_limit
-                Y_rnd = torch.cat([acq_function(X_rnd[s:s + limit].to(device=device)).cpu()
-                                   for s in range(0, X_rnd.shape[0], limit)])
+                # one host->device copy and one device->host read for the whole screening pass (the reference moves every
+                # chunk separately, initializers.py:184-190; the chunked CALLS are kept, they advance the EMA state)
+                X_dev = X_rnd.to(device=device)
+                Y_rnd = torch.cat([acq_function(X_dev[s:s + limit]) for s in range(0, X_dev.shape[0], limit)]).cpu()
             batch_initial_conditions = init_func(X=X_rnd, Y=Y_rnd, n=num_restarts, **init_kwargs).to(device=device)
             if not any(issubclass(w.category, BadInitialCandidatesWarning) for w in ws):
                 return batch_initial_conditions
