@@ -294,6 +294,7 @@ class MCProbabilisticReparameterization(AbstractProbabilisticReparameterization)
         self.input_transform_flip = None
 
     def forward(self, X: Tensor) -> Tensor:
+        _check_X(X, self.dim)
         gp_state_from_model(self.acq_function.model).set_option(capi.PRB_OPT_DEDUP, int(self.dedup))
         return self._pr_acq_function.apply(
             X, self.acq_function, self.input_transform, self.input_transform_flip, self.batch_limit,
