@@ -82,8 +82,14 @@ class ExpectedImprovement(AnalyticAcquisitionFunction):
         self.variant = variant
 
     def acq_desc(self) -> capi.PrbAcqDesc:
-        return capi.PrbAcqDesc(kind=capi.PRB_ACQ_EI, ei_variant=0 if self.variant == "erf" else 1,
-                               param=float(self.best_f), min_variance=MIN_VARIANCE, acq_var_floor=self.var_floor)
+        # float(best_f) is a device->host read when the buffer lives on the GPU: redo it only when best_f changes
+        ver = (self.best_f.data_ptr(), self.best_f._version, self.variant, self.var_floor)
+        if getattr(self, "_desc_ver", None) != ver:
+            self._desc = capi.PrbAcqDesc(kind=capi.PRB_ACQ_EI, ei_variant=0 if self.variant == "erf" else 1,
+                                         param=float(self.best_f), min_variance=MIN_VARIANCE,
+                                         acq_var_floor=self.var_floor)
+            self._desc_ver = ver
+        return self._desc
 
 
 class UpperConfidenceBound(AnalyticAcquisitionFunction):
@@ -97,8 +103,12 @@ class UpperConfidenceBound(AnalyticAcquisitionFunction):
         self.register_buffer("beta", torch.as_tensor(beta, dtype=torch.float64).detach().clone())
 
     def acq_desc(self) -> capi.PrbAcqDesc:
-        return capi.PrbAcqDesc(kind=capi.PRB_ACQ_UCB, ei_variant=0, param=float(self.beta),
-                               min_variance=MIN_VARIANCE, acq_var_floor=0.0)
+        ver = (self.beta.data_ptr(), self.beta._version)
+        if getattr(self, "_desc_ver", None) != ver:
+            self._desc = capi.PrbAcqDesc(kind=capi.PRB_ACQ_UCB, ei_variant=0, param=float(self.beta),
+                                         min_variance=MIN_VARIANCE, acq_var_floor=0.0)
+            self._desc_ver = ver
+        return self._desc
 
 
 class PosteriorMean(AnalyticAcquisitionFunction):

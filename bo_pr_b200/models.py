@@ -77,6 +77,9 @@ class GPState:
         self.handle = handle
         self._desc = desc
         self._ws: Optional[Tensor] = None
+        self._ws_need = {}
+        self._ones: Optional[Tensor] = None
+        self._options = {}
         self.chunk_cols = 0
 
     def __del__(self):
@@ -89,11 +92,23 @@ class GPState:
             self.handle = None
 
     def set_option(self, option: int, value: int) -> None:
+        if self._options.get(int(option)) == int(value):
+            return
+        self._options[int(option)] = int(value)
         capi.check(self.lib.prb_model_set_option(self.handle, int(option), int(value)), "prb_model_set_option")
 
+    def ones(self, b: int) -> Tensor:
+        """Cached all-ones upstream gradient (the library evaluates the estimator for grad_output = 1)."""
+        t = self._ones
+        if t is None or t.numel() < b:
+            t = self._ones = torch.ones(max(b, 64), dtype=torch.float64, device=self.device)
+        return t[:b]
+
     def workspace(self, n_points: int, d_theta: int, n_restarts: int = 0) -> Tensor:
-        need = int(self.lib.prb_workspace_bytes(self.handle, int(n_points), int(n_restarts), int(d_theta),
-                                                int(self.chunk_cols)))
+        key = (int(n_points), int(n_restarts), int(d_theta), int(self.chunk_cols))
+        need = self._ws_need.get(key)
+        if need is None:
+            need = self._ws_need[key] = int(self.lib.prb_workspace_bytes(self.handle, *key))
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws

@@ -134,10 +134,14 @@ class AbstractProbabilisticReparameterization(AcquisitionFunctionWrapper, ABC):
         return self._ma_state[1:2]
 
     def _space(self) -> capi.PrbSpaceDesc:
-        return make_space_desc(self.dim, self.integer_indices.tolist(),
-                               self.integer_bounds if self.integer_indices.numel() > 0 else None,
-                               self.categorical_features, self.input_transform["round"].tau,
-                               apply_numeric=self.apply_numeric)
+        tau = self.input_transform["round"].tau
+        cached = self.__dict__.get("_space_cached")
+        if cached is None or cached[0] != tau:
+            sp = make_space_desc(self.dim, self.integer_indices.tolist(),
+                                 self.integer_bounds if self.integer_indices.numel() > 0 else None,
+                                 self.categorical_features, tau, apply_numeric=self.apply_numeric)
+            cached = self.__dict__["_space_cached"] = (tau, sp)
+        return cached[1]
 
     def sample_candidates(self, X: Tensor) -> Tensor:
         """``:198-233``: one discrete draw per restart from p(theta*), torch's global generator (once per BO iteration)."""
@@ -331,15 +335,21 @@ class _MCProbabilisticReparameterization(Function):
         rnd.ensure_base_samples(1, X.device)
         u_int, u_cat = rnd.base_sample_ptrs()
         mc = rnd.mc_samples
-        ints = integer_indices.tolist()
-        ib = rnd.integer_bounds if len(ints) > 0 else None
-        sp = make_space_desc(d, ints, ib, rnd.categorical_features, rnd.tau,
-                             apply_numeric=one_hot_to_numeric is not None)
+        # the space descriptor only depends on constructor arguments: build it once per transform (reading the index /
+        # bounds buffers back from the device costs a host sync per call otherwise)
+        key = (d, one_hot_to_numeric is not None, rnd.tau)
+        cache = rnd.__dict__.setdefault("_space_desc_cache", {})
+        sp = cache.get(key)
+        if sp is None:
+            ints = integer_indices.tolist()
+            ib = rnd.integer_bounds if len(ints) > 0 else None
+            sp = cache[key] = make_space_desc(d, ints, ib, rnd.categorical_features, rnd.tau,
+                                              apply_numeric=one_hot_to_numeric is not None)
         aq = acq_desc_of(acq_function)
         need = ctx.needs_input_grad[0]
         value = torch.empty(b, dtype=torch.float64, device=X.device)
         grad = torch.empty(b, d, dtype=torch.float64, device=X.device) if need else None
-        ones = torch.ones(b, dtype=torch.float64, device=X.device) if need else None
+        ones = state.ones(b) if need else None
         ws = state.workspace(b * mc, d, b)
         est = capi.PRB_EST_REINFORCE_MA if grad_estimator == "reinforce_ma" else capi.PRB_EST_REINFORCE
         with torch.cuda.device(X.device):
