@@ -17,6 +17,7 @@
 //
 // Tuning record (B200, n = 1000, 65 536 columns; profiles/): 4 stages / producer 2 k-tiles ahead beats 5/3, 5/2 and 4/3;
 // 8 warps of 32 x 64 (246-254 registers, 1 CTA/SM) beat 16 warps of 32 x 32 (128 registers): 4.49 vs 4.79 ms per step;
+// two 4-warp CTAs per SM with 64-column tiles (same 32 x 64 warp tile) beat one 8-warp CTA by 1-2 % (4.41 vs 4.46 ms);
 // routing the whole last row tile through the masked (diagonal) body to skip its all-padding row groups costs more than
 // the 1.5 % of DMMAs it saves (4.55 vs 4.46 ms).
 //
@@ -46,8 +47,8 @@ constexpr int T_BM = 128, T_BN = 128, T_BK = 16, T_STAGES = PRB_T_STAGES, T_AHEA
 static_assert(T_AHEAD >= 1 && T_AHEAD <= T_STAGES - 1, "the producer may run at most T_STAGES - 1 k-tiles ahead");
 constexpr int T_OPER_DOUBLES = T_BM * T_BK;            // 2048 doubles = 16 KB per operand per stage
 constexpr int T_CHUNK_DOUBLES = T_BM * 4;              // one k-chunk (4 k values) of 128 rows
-constexpr int T_STAGE_DOUBLES = 2 * T_OPER_DOUBLES;
-constexpr size_t T_SMEM_BYTES = size_t(T_STAGES) * T_STAGE_DOUBLES * 8 + 2 * T_STAGES * 8 + 64 * 8;
+constexpr size_t tma_smem_bytes(int bn) { return size_t(T_STAGES) * (T_OPER_DOUBLES + bn * T_BK) * 8 + 2 * T_STAGES * 8 + 64 * 8; }
+constexpr size_t T_SMEM_BYTES = tma_smem_bytes(128);
 
 enum { MODE_LOWER_GEN = 0, MODE_LOWER_TMA = 1, MODE_UPPER_W = 2, MODE_UPPER_GRAD = 3 };
 
@@ -132,18 +133,22 @@ struct TmaGemmParams {
 
 // BN = evaluation columns per tile: 128 for throughput; 32 for small problems, where a 128-wide tiling would leave most
 // of the 148 SMs idle and the step is bound by ONE SM's DMMA rate (n = 119, 640 columns: 5 tiles, 23 us per product).
-template <int MODE, int BN>
-__global__ void __launch_bounds__(T_THREADS, 1)
+template <int MODE, int BN, int THREADS = T_THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 128 ? 2 : 1)
     trgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const TmaGemmParams p) {
   constexpr bool UPPER = (MODE == MODE_UPPER_W || MODE == MODE_UPPER_GRAD);
   constexpr bool GEN = (MODE == MODE_LOWER_GEN);
-  constexpr int TJ = BN / 16;          // 8 x 8 accumulator tiles per warp along N (warp = 32 rows x BN / 2 columns)
+  constexpr int NWN = THREADS / 128;   // warps along N (4 along M)
+  constexpr int TJ = BN / (8 * NWN);   // 8 x 8 accumulator tiles per warp along N (warp = 32 rows x 8 TJ columns)
+  constexpr int GEN_VPT = BN * T_BK / THREADS;  // generated operand values per thread and k-tile (8 or 2)
+  static_assert(GEN_VPT == 8 || GEN_VPT == 2, "operand generator mappings");
   constexpr int B_CHUNK = BN * 4;      // doubles per k-chunk of the B operand
   constexpr int B_OPER = BN * T_BK;    // doubles per k-tile of the B operand
+  constexpr int STAGE_DOUBLES = T_OPER_DOUBLES + B_OPER;  // A tile + B tile of one k-tile
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* stages = reinterpret_cast<double*>(smem_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + size_t(T_STAGES) * T_STAGE_DOUBLES * 8);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + size_t(T_STAGES) * STAGE_DOUBLES * 8);
   uint64_t* empty = full + T_STAGES;
   double* tab_s = reinterpret_cast<double*>(empty + T_STAGES);  // [64]
 
@@ -182,8 +187,8 @@ __global__ void __launch_bounds__(T_THREADS, 1)
     tma_prefetch_desc(&tmA);
     if (!GEN) tma_prefetch_desc(&tmB);
     for (int s = 0; s < T_STAGES; ++s) {
-      mbar_init(&full[s], GEN ? 1 + T_THREADS : 1);
-      mbar_init(&empty[s], T_THREADS / 32);
+      mbar_init(&full[s], GEN ? 1 + THREADS : 1);
+      mbar_init(&empty[s], THREADS / 32);
     }
     mbar_fence_init();
   }
@@ -211,7 +216,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
     const int s = kt % T_STAGES;
     const int use = kt / T_STAGES;
     const int k0 = kbeg + kt * T_BK;
-    double* As = stages + s * T_STAGE_DOUBLES;
+    double* As = stages + s * STAGE_DOUBLES;
     double* Bs = As + T_OPER_DOUBLES;
     if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
     mbar_arrive_expect_tx(&full[s], (T_OPER_DOUBLES + (GEN ? 0 : B_OPER)) * 8);
@@ -228,7 +233,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
   uint2 g_zs;
   auto gen_load = [&](int kt) {
     const int k0 = kbeg + kt * T_BK;
-    if constexpr (BN == 128) {
+    if constexpr (GEN_VPT == 8) {
       const double2* kc2 = reinterpret_cast<const double2*>(g_kc + k0 + ghalf * 8);
       const uint4* zz = reinterpret_cast<const uint4*>(p.Zbits + k0 + ghalf * 8);
       g_k01 = __ldg(kc2);
@@ -245,9 +250,9 @@ __global__ void __launch_bounds__(T_THREADS, 1)
   auto gen_store = [&](int kt) {
     const int s = kt % T_STAGES;
     const int use = kt / T_STAGES;
-    double* Bs = stages + s * T_STAGE_DOUBLES + T_OPER_DOUBLES;
+    double* Bs = stages + s * STAGE_DOUBLES + T_OPER_DOUBLES;
     if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
-    if constexpr (BN == 128) {
+    if constexpr (GEN_VPT == 8) {
       double2 o0, o1, o2, o3;
       o0.x = g_k01.x * tab_s[__popc(g_zb ^ g_za.x)];
       o0.y = g_k01.y * tab_s[__popc(g_zb ^ g_za.y)];
@@ -308,7 +313,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
     }
     const int s = kt % T_STAGES;
     mbar_wait(&full[s], (kt / T_STAGES) & 1);
-    const double* pa = stages + s * T_STAGE_DOUBLES;
+    const double* pa = stages + s * STAGE_DOUBLES;
     const double* pb = pa + T_OPER_DOUBLES + fb_off;
     const int q0 = kbeg + kt * T_BK - m0;  // offset of this k-tile inside the tile's diagonal block
     if (q0 < 0 || q0 >= T_BM) {
@@ -535,6 +540,8 @@ cudaError_t tma_init() {
   const void* kernels[] = {
       reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_LOWER_GEN, 128>),
       reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_LOWER_GEN, 32>),
+      reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_LOWER_GEN, 64, 128>),
+      reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_UPPER_GRAD, 64, 128>),
       reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_LOWER_TMA, 128>),
       reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_UPPER_W, 128>),
       reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_UPPER_GRAD, 128>),
@@ -561,12 +568,16 @@ cudaError_t make_operand_map(TensorMap* out, const double* base, int rows, int k
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-// column-tile width: 128 unless that leaves most SMs without a tile (small problems are bound by one SM's DMMA rate)
+// Column-tile width of the separable-path products (PRB_BN overrides, for A/B runs):
+//   64  (default) 4 warps of 32 x 64 per CTA, TWO CTAs per SM: one CTA's TMA prologue, epilogue and end-of-tile barrier
+//       overlap the other's main loop -- 1-2 % faster than one 8-warp 128-column CTA per SM at every n from 200 to 4000;
+//   32  when even 128-wide tiling leaves most SMs without a tile: small problems are bound by ONE SM's DMMA rate;
+//   128 one 8-warp CTA per SM (the generic-path kernels use this shape).
 static int pick_bn(const Model& m, int ncols_pad, bool upper) {
   static const int force = getenv("PRB_BN") ? atoi(getenv("PRB_BN")) : 0;
-  if (force == 32 || force == 128) return force;
+  if (force == 32 || force == 64 || force == 128) return force;
   const int tiles128 = ((upper ? m.Mp2 : m.Mp1) / T_BM) * (ncols_pad / 128);
-  return tiles128 < 120 ? 32 : 128;
+  return tiles128 < 120 ? 32 : 64;
 }
 
 static void fill_common(TmaGemmParams& p, const Model& m, int ncols_pad, bool upper, int bn = T_BN) {
@@ -618,6 +629,8 @@ cudaError_t launch_tma_lower_gen(const Model& m, const SepArgs& sa, int ncols_pa
   const CUtensorMap& mA = *reinterpret_cast<const CUtensorMap*>(&m.mapA1);
   if (bn == 32)
     trgemm_tma_kernel<MODE_LOWER_GEN, 32><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(mA, mA, p);
+  else if (bn == 64)  // 4 warps per CTA, two CTAs per SM
+    trgemm_tma_kernel<MODE_LOWER_GEN, 64, 128><<<p.mtiles * p.ntiles, 128, tma_smem_bytes(64), st>>>(mA, mA, p);
   else
     trgemm_tma_kernel<MODE_LOWER_GEN, 128><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(mA, mA, p);
   count_launch();
@@ -670,6 +683,8 @@ cudaError_t launch_tma_upper_grad(const Model& m, const double* panelV, int pane
   const CUtensorMap& mB = *reinterpret_cast<const CUtensorMap*>(&mapV);
   if (bn == 32)
     trgemm_tma_kernel<MODE_UPPER_GRAD, 32><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(mA, mB, p);
+  else if (bn == 64)
+    trgemm_tma_kernel<MODE_UPPER_GRAD, 64, 128><<<p.mtiles * p.ntiles, 128, tma_smem_bytes(64), st>>>(mA, mB, p);
   else
     trgemm_tma_kernel<MODE_UPPER_GRAD, 128><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(mA, mB, p);
   count_launch();
