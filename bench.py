@@ -448,9 +448,9 @@ def run_ours(a):
         cb = a.cpu_restarts
         cpu_problem = dict(problem)
         cstep = cpu_oracle_step_fn(cpu_problem, mc, cb)
-        sec = time_cpu(cstep, steps=8, warmup=1)
+        sec = time_cpu(cstep, steps=24, warmup=2)
         cpu = {"value": cb * mc / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{cb} of the {b} restarts x {mc} MC samples per step (value+grad), 8 steps, torch CPU float64"}
+               "sample": f"{cb} of the {b} restarts x {mc} MC samples per step (value+grad), 24 steps (~10 s), torch CPU float64"}
 
     # ---- seconds per BO iteration, ackley13 pr__ei (rank 0, N = 1 only) ---------------------------------------------------
     bo = None

@@ -15,7 +15,11 @@ Parity status
   BoTorch / GPyTorch, which are third-party, unpinned (``setup.py:9-20``: ``botorch>=0.6``, ``gpytorch``)
   and absent from ``/root/reference`` and from this image.  ``oracle/gp_oracle.py`` restates their
   published formulas.  The reference holds no golden vectors or tests for this
-  boundary, so L0 is **parity unpinned**: it is anchored only on the reference's call sites
-  (``experiment_utils.py:267-351, 391-393, 476-480``; ``kernels.py:18-101``) and on internal known-answer
-  checks (posterior at training inputs, finite differences, Σ probs = 1).
+  boundary, so L0 is **parity unpinned** with respect to BoTorch/GPyTorch outputs: it is anchored on the
+  reference's call sites (``experiment_utils.py:267-351, 391-393, 476-480``; ``kernels.py:18-101``), on
+  internal known-answer checks (posterior at training inputs, finite differences, Σ probs = 1) and on an
+  INDEPENDENT implementation of the same published formulas that is installed here: scikit-learn's
+  ``GaussianProcessRegressor`` with ``Matern(nu=2.5)`` kernels (kernel matrix 1e-10, posterior mean 1e-8,
+  variance 1e-6) and ``scipy.stats.norm`` for EI (``tests/test_oracle_l0_independent.py``).  Library-specific
+  constants (EI variance floor, ``min_variance``, ``min_fixed_noise``) stay exposed as parameters.
 """
