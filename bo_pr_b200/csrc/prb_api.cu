@@ -14,6 +14,7 @@ using namespace prb;
 
 namespace prb {
 unsigned long long g_launches = 0;
+bool g_pdl_on = false;
 
 static bool g_prof_on = false;
 struct ProfRec { int id; cudaEvent_t beg, end; };
@@ -382,6 +383,8 @@ int sep_step(const Model& m, const DevSpace& sp, const DevAcq& aq, const Plan& p
   double* dvar = at<double>(ws, pl.off_dvar);
   CUDA_TRY(launch_sep_step_prep(m, sp, bm, theta_in, lower, upper, Xc, b, mc, u_int, u_cat, seed, offset, kc,
                                 need_grad ? Dc : nullptr, need_grad ? z : nullptr, need_grad ? prob : nullptr, zbits, st));
+  static const bool use_pdl = getenv("PRB_NO_PDL") == nullptr;
+  PdlScope pdl(use_pdl);  // the remaining kernels of the step overlap their launch + prologue with their predecessor
   SepArgs sa;
   sa.kc = kc;
   sa.Dc = Dc;

@@ -175,9 +175,11 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 2 : 1)
   }
   const int num_k = (kend - kbeg) / T_BK;
 
+  grid_dep_launch();  // PDL: let the next kernel of the step start its prologue (no-op for ordinary launches)
   // de-duplicated columns: the grid covers the worst case (no duplicates); tiles beyond the unique columns do nothing
   int ncols_valid = p.ncols;
   if (p.ncols_dev != nullptr) {
+    grid_dep_wait();
     const int64_t left = int64_t(*p.ncols_dev) - p.col0;
     if (left <= n0) return;
     if (left < ncols_valid || ncols_valid == 0) ncols_valid = int(left);
@@ -194,6 +196,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 2 : 1)
   }
   if ((GEN || MODE == MODE_UPPER_GRAD) && tid < 64) tab_s[tid] = (tid <= p.ntab) ? p.tab[tid] : 0.0;
   __syncthreads();
+  grid_dep_wait();  // PDL: everything above is independent of the predecessor kernel; its outputs are read from here on
 
   // ---- B-operand generation: thread <-> (evaluation column, 8 of the 16 k values of a k-tile) ---------------------------
   // (the 32-byte column stride of the STS.128 below costs 2-way bank conflicts, 21 M per launch; a lane-pair-per-column
@@ -627,14 +630,18 @@ cudaError_t launch_tma_lower_gen(const Model& m, const SepArgs& sa, int ncols_pa
     p.acq_ncols = fa->ncols;
   }
   const CUtensorMap& mA = *reinterpret_cast<const CUtensorMap*>(&m.mapA1);
+  cudaError_t le;
   if (bn == 32)
-    trgemm_tma_kernel<MODE_LOWER_GEN, 32><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(mA, mA, p);
+    le = launch_kernel(trgemm_tma_kernel<MODE_LOWER_GEN, 32, T_THREADS>, dim3(p.mtiles * p.ntiles), dim3(T_THREADS),
+                       T_SMEM_BYTES, st, mA, mA, p);
   else if (bn == 64)  // 4 warps per CTA, two CTAs per SM
-    trgemm_tma_kernel<MODE_LOWER_GEN, 64, 128><<<p.mtiles * p.ntiles, 128, tma_smem_bytes(64), st>>>(mA, mA, p);
+    le = launch_kernel(trgemm_tma_kernel<MODE_LOWER_GEN, 64, 128>, dim3(p.mtiles * p.ntiles), dim3(128),
+                       tma_smem_bytes(64), st, mA, mA, p);
   else
-    trgemm_tma_kernel<MODE_LOWER_GEN, 128><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(mA, mA, p);
+    le = launch_kernel(trgemm_tma_kernel<MODE_LOWER_GEN, 128, T_THREADS>, dim3(p.mtiles * p.ntiles), dim3(T_THREADS),
+                       T_SMEM_BYTES, st, mA, mA, p);
   count_launch();
-  return cudaGetLastError();
+  return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 cudaError_t launch_tma_lower(const Model& m, const TensorMap& mapB, int ncols_pad, double* VT, double* norm_part,
@@ -682,13 +689,16 @@ cudaError_t launch_tma_upper_grad(const Model& m, const double* panelV, int pane
   const CUtensorMap& mA = *reinterpret_cast<const CUtensorMap*>(&m.mapA2);
   const CUtensorMap& mB = *reinterpret_cast<const CUtensorMap*>(&mapV);
   if (bn == 32)
-    trgemm_tma_kernel<MODE_UPPER_GRAD, 32><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(mA, mB, p);
+    e = launch_kernel(trgemm_tma_kernel<MODE_UPPER_GRAD, 32, T_THREADS>, dim3(p.mtiles * p.ntiles), dim3(T_THREADS),
+                      T_SMEM_BYTES, st, mA, mB, p);
   else if (bn == 64)
-    trgemm_tma_kernel<MODE_UPPER_GRAD, 64, 128><<<p.mtiles * p.ntiles, 128, tma_smem_bytes(64), st>>>(mA, mB, p);
+    e = launch_kernel(trgemm_tma_kernel<MODE_UPPER_GRAD, 64, 128>, dim3(p.mtiles * p.ntiles), dim3(128),
+                      tma_smem_bytes(64), st, mA, mB, p);
   else
-    trgemm_tma_kernel<MODE_UPPER_GRAD, 128><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(mA, mB, p);
+    e = launch_kernel(trgemm_tma_kernel<MODE_UPPER_GRAD, 128, T_THREADS>, dim3(p.mtiles * p.ntiles), dim3(T_THREADS),
+                      T_SMEM_BYTES, st, mA, mB, p);
   count_launch();
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace prb

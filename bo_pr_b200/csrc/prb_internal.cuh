@@ -72,6 +72,37 @@ struct ProfScope {  // no-op unless profiling is enabled; never use while the st
   bool on_;
 };
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------
+// Inside a PdlScope the launchers below attach cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel of the
+// fused optimisation step is scheduled while the previous one still runs, executes its prologue (barrier init, descriptor
+// prefetch) and blocks in griddepcontrol.wait until the predecessor has completed and flushed.  Every kernel of the step
+// calls grid_dep_launch() first and grid_dep_wait() before it touches anything a predecessor wrote.
+extern bool g_pdl_on;
+struct PdlScope {
+  explicit PdlScope(bool on) : prev_(g_pdl_on) { g_pdl_on = on; }
+  ~PdlScope() { g_pdl_on = prev_; }
+  bool prev_;
+};
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = g_pdl_on ? attr : nullptr;
+  cfg.numAttrs = g_pdl_on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 inline int64_t round_up64(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 

@@ -443,6 +443,8 @@ __global__ void acq_epilogue_kernel(const DevAcq aq, double mean_const, double k
                                     double* __restrict__ a, double* __restrict__ dmu, double* __restrict__ dvar,
                                     double* __restrict__ out_mean, double* __restrict__ out_var,
                                     const int* __restrict__ ncols_dev, int64_t col0) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= ncols) return;
   if (ncols_dev != nullptr && col0 + col >= int64_t(*ncols_dev)) return;
@@ -464,11 +466,11 @@ cudaError_t launch_acq_epilogue(const Model& m, const DevAcq& aq, const double* 
                                 cudaStream_t st) {
   ProfScope prof_(K_EPILOGUE, st);
   if (ncols == 0) return cudaSuccess;
-  acq_epilogue_kernel<<<(ncols + 127) / 128, 128, 0, st>>>(aq, m.mean_const, m.kss, norm_part, m.Mp1 / GEMM_BM,
-                                                           ncols_pad, mu_dot, ncols, a, dmu, dvar, out_mean, out_var,
-                                                           ncols_dev, col0);
+  cudaError_t e = launch_kernel(acq_epilogue_kernel, dim3((ncols + 127) / 128), dim3(128), 0, st, aq, m.mean_const, m.kss,
+                                norm_part, m.Mp1 / GEMM_BM, ncols_pad, mu_dot, ncols, a, dmu, dvar, out_mean, out_var,
+                                ncols_dev, col0);
   count_launch();
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 // =====================================================================================================================
@@ -1029,6 +1031,7 @@ __global__ void __launch_bounds__(256) sep_step_prep_kernel(
     uint8_t* __restrict__ z, double* __restrict__ prob, uint32_t* __restrict__ zbits) {
   __shared__ double th_s[PRB_MAX_DIMS];
   __shared__ double ps_s[PRB_MAX_DIMS], offs_s[PRB_MAX_DIMS];  // the separable path has no categoricals: n_disc = n_int
+  grid_dep_launch();
   const int b = blockIdx.x, tid = threadIdx.x;
   if (tid < sp.d) {
     double v = theta[size_t(b) * sp.d + tid];
@@ -1101,6 +1104,8 @@ __global__ void __launch_bounds__(FINISH_THREADS) sep_step_finish_kernel(
   __shared__ double red[32];
   __shared__ double g_s[PRB_MAX_DIMS];
   __shared__ int last_s;
+  grid_dep_launch();
+  grid_dep_wait();
   const int bi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t c0 = size_t(bi) * mc;
   // everything that depends on the pre-call optimiser / EMA state is read before this CTA signals completion
@@ -1186,11 +1191,11 @@ cudaError_t launch_sep_step_finish(const DevSpace& sp, const DimMap& dm, int nb,
                                    double lr, int* step_ptr, unsigned int* done, cudaStream_t st) {
   ProfScope prof_(K_MC_REDUCE, st);
   if (nb == 0) return cudaSuccess;
-  sep_step_finish_kernel<<<nb, FINISH_THREADS, 0, st>>>(sp, dm, mc, a, z, prob, S_part, mtiles, ncols_pad, estimator, ma_state,
-                                             update_ma, grad_out, out_value, out_grad, need_grad, theta, adam_m, adam_v,
-                                             lr, step_ptr, done, nb);
+  cudaError_t e = launch_kernel(sep_step_finish_kernel, dim3(nb), dim3(FINISH_THREADS), 0, st, sp, dm, mc, a, z, prob, S_part,
+                                mtiles, ncols_pad, estimator, ma_state, update_ma, grad_out, out_value, out_grad, need_grad,
+                                theta, adam_m, adam_v, lr, step_ptr, done, nb);
   count_launch();
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 // =====================================================================================================================
