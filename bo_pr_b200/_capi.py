@@ -28,7 +28,7 @@ PROFILE_SLOT_NAMES = ["pr_sample", "kstar_panel", "trgemm_lower", "acq_epilogue"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", os.environ.get("PRB_LIB_NAME", "libprb200.so"))
 
 EXPORTS = [
-    "prb_version", "prb_abi_sizeof", "prb_launch_count", "prb_profile_enable", "prb_profile_read", "prb_status_string", "prb_last_cuda_error", "prb_model_create", "prb_model_destroy", "prb_model_set_option",
+    "prb_version", "prb_abi_sizeof", "prb_debug_small_timestamps", "prb_launch_count", "prb_profile_enable", "prb_profile_read", "prb_status_string", "prb_last_cuda_error", "prb_model_create", "prb_model_destroy", "prb_model_set_option",
     "prb_model_n", "prb_model_dk", "prb_workspace_bytes", "prb_philox_uniform", "prb_pr_sample",
     "prb_analytic_enumerate", "prb_kernel_matrix", "prb_acq_points",
     "prb_mc_value_grad", "prb_analytic_value_grad", "prb_mc_adam",
@@ -86,6 +86,7 @@ def load_library() -> C.CDLL:
     lib.prb_launch_count.restype = C.c_uint64
     lib.prb_launch_count.argtypes = []
     lib.prb_abi_sizeof.argtypes = [C.c_int]
+    lib.prb_debug_small_timestamps.argtypes = [vp]
     lib.prb_profile_enable.argtypes = [C.c_int]
     lib.prb_profile_read.argtypes = [vp, vp, i32]
     lib.prb_status_string.restype = C.c_char_p

@@ -161,7 +161,7 @@ struct Plan {
   size_t off_panelA, off_panelV, off_norm, off_mu, off_S_part;
   size_t off_Xc, off_grad, off_ones, off_val, off_step;
   size_t off_zbits, off_kc, off_Dc;
-  size_t off_done;
+  size_t off_done, off_small, small_bytes;
   size_t off_ucount, off_ustart, off_utotal, off_ucode, off_uweight, off_inv, off_zbits_u, off_colb, off_wu;
   size_t total;
 };
@@ -230,6 +230,8 @@ Plan make_plan(const Model& m, int64_t n_points, int n_restarts, int d_theta, in
   if (m.sep_ok && n_restarts > 0) {
     p.off_kc = take(size_t(n_restarts) * m.Kp * dbl);
     p.off_Dc = take(size_t(n_restarts) * d_theta * m.Kp * dbl);
+    p.small_bytes = (size_t(p.B_pad / 32 + n_restarts) * (1 + d_theta)) * dbl + size_t(n_restarts + 2) * sizeof(int) + 64;
+    p.off_small = take(p.small_bytes);
     p.off_ucount = take(size_t(n_restarts) * sizeof(int));
     p.off_ustart = take(size_t(n_restarts + 1) * sizeof(int));
     p.off_utotal = take(2 * sizeof(int));
@@ -486,6 +488,12 @@ int prb_abi_sizeof(int which) {
   }
 }
 
+int prb_debug_small_timestamps(long long* out16) {
+  if (!out16) return PRB_ERR_INVALID;
+  CUDA_TRY(small_step_timestamps(out16));
+  return PRB_OK;
+}
+
 int prb_profile_enable(int on) {
   g_prof_on = on != 0;
   return PRB_OK;
@@ -580,6 +588,7 @@ int prb_model_create(prb_model** out, const prb_model_desc* desc, void* stream) 
   const int n_pad = m->Mp1 > m->Mp2 ? m->Mp1 : m->Mp2;
   int* bad_flag = nullptr;
   if (e == cudaSuccess) e = tma_init();
+  if (e == cudaSuccess) e = small_step_init();
   if (e == cudaSuccess) e = cudaMalloc(&m->alpha_pad, size_t(n_pad) * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&m->Zbits, size_t(n_pad) * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&m->sep_tab, 64 * sizeof(double));
@@ -814,7 +823,18 @@ int prb_mc_adam(prb_model* model, const prb_space_desc* space, const prb_acq_des
   const bool fused_step = pl.off_kc != 0 && sep_space_ok(m, sp, &bm, &dm) && int64_t(b) * mc <= pl.C &&
                           !(m.opt_dedup && m.sep_nbits <= DEDUP_MAX_BITS) && getenv("PRB_NO_FUSED_STEP") == nullptr;
 
+  // experiment sizes (n + 1 <= 128, mc % 32 == 0): the whole step is ONE kernel (prb_small.cu)
+  const bool small_step = fused_step && small_step_eligible(m, sp, dm, b, mc) &&
+                          small_step_scratch_bytes(b, mc, sp.d) <= pl.small_bytes;
+  if (small_step) CUDA_TRY(cudaMemsetAsync(at<char>(workspace, pl.off_small), 0, pl.small_bytes, st));
+
   auto one_iter = [&]() -> int {
+    if (small_step) {
+      CUDA_TRY(launch_small_step(m, sp, aq, bm, dm, theta, lower, upper, Xc, b, mc, u_int, u_cat, seed, offset, estimator,
+                                 ma_state, update_ma, true, nullptr, val, grad, theta, adam_state, adam_state + total, lr,
+                                 step, at<char>(workspace, pl.off_small), st));
+      return PRB_OK;
+    }
     if (fused_step)
       return sep_step(m, sp, aq, pl, workspace, bm, dm, theta, lower, upper, Xc, b, mc, u_int, u_cat, seed, offset,
                       estimator, ma_state, update_ma, true, nullptr, val, grad, theta, adam_state, adam_state + total,
@@ -862,6 +882,12 @@ int prb_mc_adam(prb_model* model, const prb_space_desc* space, const prb_acq_des
     }
   }
   // final clamp + value-only evaluation (gen.py:338-341); this call also advances the EMA state like any forward
+  if (small_step) {
+    CUDA_TRY(launch_small_step(m, sp, aq, bm, dm, theta, lower, upper, theta, b, mc, u_int, u_cat, seed, offset, estimator,
+                               ma_state, update_ma, false, nullptr, out_value, nullptr, nullptr, nullptr, nullptr, lr,
+                               nullptr, at<char>(workspace, pl.off_small), st));
+    return PRB_OK;
+  }
   if (fused_step)
     return sep_step(m, sp, aq, pl, workspace, bm, dm, theta, lower, upper, theta, b, mc, u_int, u_cat, seed, offset,
                     estimator, ma_state, update_ma, false, nullptr, out_value, nullptr, nullptr, nullptr, nullptr, lr,

@@ -110,4 +110,120 @@ __device__ __forceinline__ double ipow(double v, int p) {
   return r;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// PR sampler building blocks (shared by pr_sample_kernel, the fused step kernels and the small-problem step kernel)
+// ---------------------------------------------------------------------------------------------------------------------
+// Rounding probabilities of one restart (input.py:613-635).  They do not depend on the MC sample, so they are computed
+// once per restart by `nworkers` cooperating threads (worker id t): ps[0 .. n_int) integer probabilities, offs[k] =
+// floor|x_un|, ps[n_int ..) the normalised softmax entries of every one-hot block, in `discrete_indices` order.
+__device__ __forceinline__ void pr_restart_probs(const DevSpace& sp, const double* __restrict__ th, int t, int nworkers,
+                                                 double* __restrict__ ps, double* __restrict__ offs) {
+  for (int k = t; k < sp.n_int; k += nworkers) {
+    const double x = th[sp.int_cols[k]];
+    const double x_un = sp.raw_int ? x : unnormalize_int(x, sp.int_lo[k], sp.int_hi[k]);
+    double off;
+    ps[k] = int_round_prob(x_un, sp.tau, &off);
+    offs[k] = off;
+  }
+  for (int j = t; j < sp.n_cat; j += nworkers) {
+    int zpos = sp.n_int;
+    for (int jj = 0; jj < j; ++jj) zpos += sp.cat_card[jj];
+    const int s = sp.cat_start[j], card = sp.cat_card[j];
+    double* pk = ps + zpos;
+    double mx = -1e300;
+    for (int k = 0; k < card; ++k) {
+      pk[k] = __dsub_rn(th[s + k], 0.5) / sp.tau;
+      mx = fmax(mx, pk[k]);
+    }
+    double sum = 0.0;
+    for (int k = 0; k < card; ++k) {
+      pk[k] = exp(__dsub_rn(pk[k], mx));
+      sum = __dadd_rn(sum, pk[k]);
+    }
+    const double inv = 1.0 / sum;
+    for (int k = 0; k < card; ++k) pk[k] = __dmul_rn(pk[k], inv);
+  }
+}
+
+// Integer parameter k of MC sample i (input.py:674-692; probabilistic_reparameterization.py:454-465): returns the sampled,
+// clamped, re-normalised value and the rounding component z used by the score-function estimator.
+__device__ __forceinline__ double pr_sample_int(const DevSpace& sp, const double* __restrict__ th,
+                                                const double* __restrict__ ps, const double* __restrict__ offs, int i,
+                                                int k, const double* __restrict__ u_int, uint64_t seed, uint64_t offset,
+                                                uint8_t* z_out) {
+  const double x = th[sp.int_cols[k]];
+  const double lo = sp.int_lo[k], hi = sp.int_hi[k];
+  const double range = __dsub_rn(hi, lo);
+  const double x_un = sp.raw_int ? x : unnormalize_int(x, lo, hi);
+  const double u = u_int ? u_int[size_t(i) * sp.n_int + k] : philox_uniform(seed, offset, uint32_t(i), uint32_t(k));
+  const double zb = (ps[k] >= u) ? 1.0 : 0.0;
+  const double xa = offs[k] + zb;
+  const double xs = (x_un < 0.0) ? -xa : xa;
+  const double xc = fmin(fmax(xs, lo), hi);
+  const double tn = sp.raw_int ? xc : __dsub_rn(xc, lo) / range;
+  *z_out = ((__dsub_rn(tn, x) > 0.0) || (x == 1.0)) ? 1 : 0;
+  return tn;
+}
+
+// One (restart, MC sample i) of the sampler.  `th` = the restart's theta row, ps / offs from pr_restart_probs.
+// Row outputs (any may be NULL): xr [d_k] kernel input, tr [d] tilde_x, zr [n_disc] rounding components; returns the bit
+// code over the binary dims selected by `bm`.
+__device__ __forceinline__ uint32_t pr_sample_point(const DevSpace& sp, const double* __restrict__ th,
+                                                    const double* __restrict__ ps, const double* __restrict__ offs,
+                                                    int i, const double* __restrict__ u_int,
+                                                    const double* __restrict__ u_cat, uint64_t seed, uint64_t offset,
+                                                    double* __restrict__ xr, double* __restrict__ tr,
+                                                    uint8_t* __restrict__ zr, const BitMap& bm) {
+  const int numeric_start = sp.n_cat > 0 ? sp.cat_start[0] : sp.d;
+  for (int c = 0; c < sp.d; ++c) {
+    const double v = th[c];
+    if (tr) tr[c] = v;
+    if (xr && (!sp.apply_numeric || c < numeric_start)) xr[c] = v;
+  }
+  uint32_t bits = 0;
+  // ---- integers (input.py:674-692)
+  for (int k = 0; k < sp.n_int; ++k) {
+    uint8_t zk;
+    const double tn = pr_sample_int(sp, th, ps, offs, i, k, u_int, seed, offset, &zk);
+    const int c = sp.int_cols[k];
+    if (tr) tr[c] = tn;
+    if (xr) xr[c] = tn;
+    if (zr) zr[k] = zk;
+    if (bm.pos[k] >= 0 && tn != 0.0) bits |= 1u << bm.pos[k];
+  }
+  // ---- categoricals (input.py:715-744): sequential cumsum of the softmax, first index with cum > u (else 0)
+  int zpos = sp.n_int;
+  for (int j = 0; j < sp.n_cat; ++j) {
+    const int s = sp.cat_start[j], card = sp.cat_card[j];
+    const double* pk = ps + zpos;
+    const double u = u_cat ? u_cat[size_t(i) * sp.n_cat + j]
+                           : philox_uniform(seed, offset, uint32_t(i), uint32_t(sp.n_int + j));
+    int cat = 0;
+    bool found = false;
+    double cum = 0.0;
+    for (int k = 0; k < card; ++k) {
+      cum = __dadd_rn(cum, pk[k]);
+      if (!found && cum > u) {
+        cat = k;
+        found = true;
+      }
+    }
+    for (int k = 0; k < card; ++k) {
+      const double oh = (k == cat) ? 1.0 : 0.0;
+      if (tr) tr[s + k] = oh;
+      if (xr && !sp.apply_numeric) xr[s + k] = oh;
+      if (zr) zr[zpos + k] = (k == cat) ? 1 : 0;
+    }
+    if (xr && sp.apply_numeric) xr[numeric_start + j] = double(cat);
+    zpos += card;
+  }
+  return bits;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 }  // namespace prb

@@ -165,6 +165,18 @@ struct Model {
 
 constexpr int DEDUP_MAX_BITS = 12;  // histogram de-duplication: 2^12 bins of shared memory per restart
 
+// prb_small.cu: one kernel per optimisation step for experiment-sized separable problems
+bool small_step_eligible(const Model& m, const DevSpace& sp, const DimMap& dm, int b, int mc);
+size_t small_step_scratch_bytes(int b, int mc, int d);
+cudaError_t small_step_init();
+cudaError_t small_step_timestamps(long long* host_out);
+cudaError_t launch_small_step(const Model& m, const DevSpace& sp, const DevAcq& aq, const BitMap& bm, const DimMap& dm,
+                              const double* theta_in, const double* lower, const double* upper, double* Xc, int b, int mc,
+                              const double* u_int, const double* u_cat, uint64_t seed, uint64_t offset, int estimator,
+                              double* ma_state, int update_ma, bool need_grad, const double* grad_out, double* out_value,
+                              double* out_grad, double* adam_theta, double* adam_m, double* adam_v, double lr,
+                              int* step_ptr, void* scratch, cudaStream_t st);
+
 // prb_gemm_tma.cu
 cudaError_t tma_init();
 cudaError_t make_operand_map(TensorMap* out, const double* base, int rows, int k_extent, int ld, int box_rows = 128);

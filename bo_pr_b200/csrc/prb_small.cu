@@ -1,0 +1,557 @@
+// One kernel per optimisation step for experiment-sized problems on the separable path (n + 1 <= 128, mc % 32 == 0).
+//
+// At the reference's own sizes (ackley13: n = 20 .. 119, 5 restarts x 128 MC samples per step, 800 Adam steps per BO
+// iteration, gen.py:320-337) a step is ~7e7 flop: microseconds of a B200, so wall time is the latency of the kernels in
+// the dependency chain.  The fused four-kernel step (prb_kernels.cu) costs ~42 us; this kernel does the whole step in one
+// launch.  A CTA owns 32 evaluation columns (MC samples) of one restart end to end:
+//
+//   TMA: the packed factor A1 = [Linv ; alpha^T] (<= 128 x 128 doubles) -> shared memory, overlapped with
+//   prep:     clamp(theta), rounding probabilities, the 32 samples (bit codes), per-restart kernel factors kc / Dc
+//   generate: k*[col, k] = kc[k] * tab[popc(z_col ^ Z_k)]                       -> shared (B operand)
+//   lower:    v = Linv k*, mu = alpha . k*        (DMMA, zero 8 x 4 sub-blocks of the triangle skipped)
+//   epilogue: ||v||^2, mu -> EI / UCB / mean and derivatives; v^T written over k* in shared memory (B operand of the next)
+//   upper:    w = Linv^T v, reading A1 TRANSPOSED out of the same shared tile (conflict-free: a fragment is 2 x 128 B)
+//   epilogue: S[c, col] = sum_j (dA/dmu alpha_j - 2 dA/dvar w_j) kb(z, Z_j) Dc[c, j]
+//   reduce:   per-tile partial sums of value / pathwise / score-function terms -> global; the LAST tile of a restart
+//             finishes the MC means and applies the Adam update; the LAST restart advances the EMA baseline and the step.
+//
+// Nothing but 14 doubles per tile leaves the SM.  Reductions are fixed-order (deterministic).
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "prb_device.cuh"
+#include "prb_kernels.cuh"
+#include "prb_ptx.cuh"
+
+namespace prb {
+
+constexpr int S_THREADS = 256;
+constexpr int S_BN = 32;
+constexpr int S_MAXC = 8;  // continuous dims supported by this kernel
+
+struct SmallStepParams {
+  DevSpace sp;
+  BitMap bm;
+  DimMap dm;
+  DevFactor fc;
+  DevAcq aq;
+  double outputscale, mean_const, kss;
+  const double* Xtr;
+  int n, d_k, nchunks;  // nchunks = ceil(n / 4): k-chunks that hold non-zero columns of A1
+  const double* alpha_pad;
+  const uint32_t* Zbits;
+  const double* tab;
+  int ntab;
+  const double* theta;  // [nb, d] optimiser parameters (read, clamped)
+  const double* lower;
+  const double* upper;
+  double* Xc;  // clamped rows out (may alias theta for the in-place final clamp), or NULL
+  int mc, nb, tiles;
+  const double* u_int;
+  const double* u_cat;
+  uint64_t seed, offset;
+  int estimator;
+  double* ma_state;
+  int update_ma, need_grad;
+  const double* grad_out;
+  double* out_value;
+  double* out_grad;
+  double* adam_theta;
+  double* adam_m;
+  double* adam_v;
+  double lr;
+  int* step_ptr;
+  double* partial;           // [nb, tiles, 1 + d]
+  unsigned int* tile_done;   // [nb]
+  unsigned int* done;        // [1]
+};
+
+// shared-memory carve-up (doubles unless noted)
+constexpr int SM_A = 128 * 128;        // A1, [k-chunk][row][4]
+constexpr int SM_B = 32 * 128;         // k* tile, then v^T tile: [k-chunk][col][4]
+constexpr int SM_KC = 128;
+constexpr int SM_DC = S_MAXC * 128;
+constexpr int SM_AL = 128;
+constexpr int SM_RED = 5 * 32 + 32;
+constexpr int SM_S = S_MAXC * 32;
+constexpr int SM_ACQ = 3 * 32;
+constexpr int SM_VEC = 4 * 32;         // th, ps, offs, g
+constexpr int SM_TAB = 64;
+constexpr int SM_DOUBLES = SM_A + SM_B + SM_KC + SM_DC + SM_AL + SM_RED + SM_S + SM_ACQ + SM_VEC + SM_TAB;
+constexpr size_t SMALL_SMEM_BYTES = size_t(SM_DOUBLES) * 8 + 128 * 4 + 32 * 4 + 32 * 32 + 16 + 16;
+
+// phase timestamps of CTA 0 (clock64), read back by prb_debug_small_timestamps(): diagnostic for the latency budget
+__device__ long long g_small_ts[16];
+#define SMALL_TS(k)                                            \
+  do {                                                         \
+    if (blockIdx.x == 0 && threadIdx.x == 0) g_small_ts[k] = clock64(); \
+  } while (0)
+
+__global__ void __launch_bounds__(S_THREADS, 1)
+    sep_small_step_kernel(const __grid_constant__ CUtensorMap tmA, const SmallStepParams p) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  double* A_s = reinterpret_cast<double*>(smraw);
+  double* B_s = A_s + SM_A;
+  double* kc_s = B_s + SM_B;
+  double* Dc_s = kc_s + SM_KC;
+  double* al_s = Dc_s + SM_DC;
+  double* red = al_s + SM_AL;
+  double* S_s = red + SM_RED;
+  double* a_s = S_s + SM_S;
+  double* dmu_s = a_s + 32;
+  double* dvar_s = dmu_s + 32;
+  double* th_s = dvar_s + 32;
+  double* ps_s = th_s + 32;
+  double* offs_s = ps_s + 32;
+  double* g_s = offs_s + 32;
+  double* tab_s = g_s + 32;
+  uint32_t* Zb_s = reinterpret_cast<uint32_t*>(tab_s + SM_TAB);  // [128]
+  uint32_t* zb_s = Zb_s + 128;                                   // [32]
+  uint8_t* z_s = reinterpret_cast<uint8_t*>(zb_s + 32);          // [32][n_disc <= 32]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(z_s + 32 * 32);
+  int* flag_s = reinterpret_cast<int*>(bar + 1);
+
+  const DevSpace& sp = p.sp;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 3, wn = warp >> 2;  // 4 warps along the 128 rows, 2 along the 32 columns
+  const int bi = blockIdx.x / p.tiles, tile = blockIdx.x % p.tiles;
+  const int i0 = tile * S_BN;  // first MC sample of this tile
+  const int n = p.n;
+
+  SMALL_TS(0);
+  // ---- 0. A1 -> shared memory by TMA (only the k-chunks that hold non-zero columns) --------------------------------
+  if (tid == 0) {
+    tma_prefetch_desc(&tmA);
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (warp == 0) {  // one box (4 k values x 128 rows) per lane: the 32 TMA issues go out in parallel
+    if (lane == 0) mbar_arrive_expect_tx(bar, uint32_t(p.nchunks) * 128 * 4 * 8);
+    __syncwarp();
+    if (lane < p.nchunks) tma_load_2d(A_s + lane * 512, &tmA, bar, 4 * lane, 0);
+  }
+  if (tid < 64) tab_s[tid] = (tid <= p.ntab) ? p.tab[tid] : 0.0;
+  if (tid < 128) {
+    Zb_s[tid] = p.Zbits[tid];
+    al_s[tid] = p.alpha_pad[tid];
+  }
+  // Everything that depends on the pre-call optimiser / EMA state is read before this CTA signals completion.  The three
+  // pow() calls (EMA de-biasing, Adam bias corrections) are FP64 and slow: one thread does them off the critical path.
+  if (tid == S_THREADS - 1) {
+    double baseline = 0.0;
+    if (p.estimator == PRB_EST_REINFORCE_MA && p.ma_state != nullptr) {
+      const double cnt = p.ma_state[0];
+      if (cnt != 0.0) baseline = p.ma_state[1] / (1.0 - pow(0.7, cnt));
+    }
+    g_s[0] = baseline;
+    if (p.adam_theta != nullptr) {
+      const double t_step = p.step_ptr ? double(*p.step_ptr + 1) : 1.0;
+      g_s[1] = 1.0 - pow(0.9, t_step);
+      g_s[2] = 1.0 - pow(0.999, t_step);
+    }
+  }
+
+  SMALL_TS(1);
+  // ---- 1. prep: clamp, rounding probabilities, this tile's 32 samples, per-restart kernel factors ----------------------
+  if (tid < sp.d) {
+    double v = p.theta[size_t(bi) * sp.d + tid];
+    if (p.lower) v = fmin(fmax(v, p.lower[tid]), p.upper[tid]);
+    th_s[tid] = v;
+    if (p.Xc && tile == 0) p.Xc[size_t(bi) * sp.d + tid] = v;
+  }
+  if (tid < S_BN) zb_s[tid] = 0u;
+  __syncthreads();
+  if (tid < 128) {
+    // warps 0-3: rounding probabilities, then the 32 samples x n_int binary parameters of this tile, one (sample, parameter)
+    // pair per thread and pass; the barrier between the two is a named barrier over these four warps only
+    pr_restart_probs(sp, th_s, tid, 128, ps_s, offs_s);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int col = tid & 31;
+    for (int k = tid >> 5; k < sp.n_int; k += 4) {
+      uint8_t zk;
+      const double tn = pr_sample_int(sp, th_s, ps_s, offs_s, i0 + col, k, p.u_int, p.seed, p.offset, &zk);
+      z_s[col * sp.n_disc + k] = zk;
+      if (p.bm.pos[k] >= 0 && tn != 0.0) atomicOr(&zb_s[col], 1u << p.bm.pos[k]);
+    }
+  } else {
+    // warps 4-7: the restart's continuous-factor values and derivatives for the 128 (padded) training points
+    const int j = tid - 128;
+    double val = 0.0, G = 0.0;
+    if (j < n) {
+      double r2 = 0.0;
+      for (int di = 0; di < p.fc.n_dims; ++di) {
+        const int dim = p.fc.dims[di];
+        const double df = (th_s[dim] - p.Xtr[size_t(j) * p.d_k + dim]) * p.fc.inv_ls[di];
+        r2 = fma(df, df, r2);
+      }
+      val = p.outputscale * matern52(r2, &G);
+    }
+    kc_s[j] = val;
+    for (int di = 0; di < p.fc.n_dims; ++di) {
+      const int dim = p.fc.dims[di];
+      double v = 0.0;
+      if (j < n) v = p.outputscale * G * (p.fc.inv_ls[di] * p.fc.inv_ls[di]) * (th_s[dim] - p.Xtr[size_t(j) * p.d_k + dim]);
+      Dc_s[di * 128 + j] = v;
+    }
+  }
+  __syncthreads();
+
+  SMALL_TS(2);
+  // ---- 2. generate the B operand: k*[col, k] for the 32 columns x 4 nchunks k values -------------------------------------
+  {
+    // lane <-> (k within a chunk, 8 columns): a warp store covers 32 consecutive doubles of B_s (conflict-free)
+    const int k4 = tid & 3;
+    const int col = (tid >> 2) & 31;
+    const int chi = tid >> 7;  // chunks chi * 16 .. chi * 16 + 15
+    const uint32_t zc = zb_s[col];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      const int c = chi * 16 + t;
+      const int k = 4 * c + k4;
+      B_s[c * 128 + col * 4 + k4] = kc_s[k] * tab_s[__popc(zc ^ Zb_s[k])];
+    }
+  }
+  __syncthreads();
+  SMALL_TS(3);
+  mbar_wait(bar, 0);
+  SMALL_TS(4);
+
+  // row ownership as in prb_gemm_tma.cu: M-warp wm owns the 8-row groups {wm, 7 - wm, 8 + wm, 15 - wm}
+  const int frag_r = lane >> 2, frag_k = lane & 3;
+  int grp[4];
+  grp[0] = wm;
+  grp[1] = 7 - wm;
+  grp[2] = 8 + wm;
+  grp[3] = 15 - wm;
+  const int fb_off = (wn * 16 + frag_r) * 4 + frag_k;
+  const int rows_valid = n + 1;  // rows of A1 at or beyond this index are zero
+
+  // ---- 3. lower product: V[row, col] = sum_{k <= row} A1[row, k] k*[col, k] ---------------------------------------------
+  // A warp owns only 4 x 2 accumulator tiles here, and a DMMA that depends on the previous one waits ~200 cycles: the
+  // contraction is split over NS independent accumulator sets (k-chunk c -> set c % NS), summed in a fixed order at the end.
+  constexpr int NS = 4;
+  double acc[4][2][2];
+  int fa_off[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) fa_off[i] = (8 * grp[i] + frag_r) * 4 + frag_k;
+  // Sub-block (8-row group g) x (k-chunk c) of the lower triangle is non-zero for c < 2 g + 2: each accumulator tile has a
+  // contiguous chunk range, walked with NS chunks in flight and no branch inside the unrolled body.
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int cend = (8 * grp[i] < rows_valid) ? min(p.nchunks, 2 * grp[i] + 2) : 0;
+    double as[NS][2][2];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) as[s][0][0] = as[s][0][1] = as[s][1][0] = as[s][1][1] = 0.0;
+    int c = 0;
+    for (; c + NS <= cend; c += NS) {
+      double a[NS], b0[NS], b1[NS];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        a[s] = A_s[(c + s) * 512 + fa_off[i]];
+        b0[s] = B_s[(c + s) * 128 + fb_off];
+        b1[s] = B_s[(c + s) * 128 + fb_off + 32];
+      }
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        dmma884(as[s][0][0], as[s][0][1], a[s], b0[s]);
+        dmma884(as[s][1][0], as[s][1][1], a[s], b1[s]);
+      }
+    }
+    for (; c < cend; ++c) {
+      const double a = A_s[c * 512 + fa_off[i]];
+      dmma884(as[0][0][0], as[0][0][1], a, B_s[c * 128 + fb_off]);
+      dmma884(as[0][1][0], as[0][1][1], a, B_s[c * 128 + fb_off + 32]);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) acc[i][j][e] = (as[0][j][e] + as[1][j][e]) + (as[2][j][e] + as[3][j][e]);
+  }
+  __syncthreads();  // every warp is done reading k*: B_s is rewritten with v^T below
+  SMALL_TS(5);
+
+  // ---- 4. epilogue: ||v||^2, mu, acquisition; v^T -> B_s as the next B operand -------------------------------------------
+  {
+    double nrm[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = 8 * grp[i] + frag_r;
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = wn * 16 + 8 * j + 2 * frag_k + e;
+          const double v = acc[i][j][e];
+          if (row == n) {
+            red[5 * 32 + col] = v;  // alpha . k*
+            B_s[(row >> 2) * 128 + col * 4 + (row & 3)] = 0.0;  // the alpha row is not part of v
+          } else {
+            nrm[j][e] = fma(v, v, nrm[j][e]);
+            B_s[(row >> 2) * 128 + col * 4 + (row & 3)] = v;
+          }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double v = nrm[j][e];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (frag_r == 0) red[wm * 32 + wn * 16 + 8 * j + 2 * frag_k + e] = v;
+      }
+  }
+  __syncthreads();
+  if (tid < S_BN) {
+    const double s = ((red[tid] + red[32 + tid]) + red[64 + tid]) + red[96 + tid];
+    double val, d_mu, d_var, var;
+    acq_eval(p.aq, p.mean_const + red[5 * 32 + tid], p.kss - s, &val, &d_mu, &d_var, &var);
+    a_s[tid] = val;
+    dmu_s[tid] = d_mu;
+    dvar_s[tid] = d_var;
+  }
+  // no barrier here: a_s / dmu_s / dvar_s are first read behind the barriers of the gradient contraction / partial sums
+
+  SMALL_TS(6);
+  if (p.need_grad) {
+    // ---- 5. upper product: W[m, col] = sum_{k >= m} Linv[k, m] V[k, col], A1 read transposed out of A_s ---------------
+    int ft_off[4];  // element (m = 8 g + r, k) of Linv^T lives at A_s[(m / 4) * 512 + k * 4 + m % 4]
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ft_off[i] = (2 * grp[i] + (frag_r >> 2)) * 512 + frag_k * 4 + (frag_r & 3);
+    // sub-block (group g) x (chunk c) of the upper triangle is non-zero for c >= 2 g
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int cbeg = (8 * grp[i] < n) ? 2 * grp[i] : p.nchunks;
+      double as[NS][2][2];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) as[s][0][0] = as[s][0][1] = as[s][1][0] = as[s][1][1] = 0.0;
+      int c = cbeg;
+      for (; c + NS <= p.nchunks; c += NS) {
+        double a[NS], b0[NS], b1[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          a[s] = A_s[ft_off[i] + (c + s) * 16];
+          b0[s] = B_s[(c + s) * 128 + fb_off];
+          b1[s] = B_s[(c + s) * 128 + fb_off + 32];
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          dmma884(as[s][0][0], as[s][0][1], a[s], b0[s]);
+          dmma884(as[s][1][0], as[s][1][1], a[s], b1[s]);
+        }
+      }
+      for (; c < p.nchunks; ++c) {
+        const double a = A_s[ft_off[i] + c * 16];
+        dmma884(as[0][0][0], as[0][0][1], a, B_s[c * 128 + fb_off]);
+        dmma884(as[0][1][0], as[0][1][1], a, B_s[c * 128 + fb_off + 32]);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) acc[i][j][e] = (as[0][j][e] + as[1][j][e]) + (as[2][j][e] + as[3][j][e]);
+    }
+    __syncthreads();  // dmu_s / dvar_s written by warp 0 after the lower product are visible from here on
+    SMALL_TS(7);
+    // ---- 6. gradient contraction: S[c, col] = sum_m (dA/dmu alpha_m - 2 dA/dvar W[m, col]) kb(z_col, Z_m) Dc[c, m] -------
+    int rows[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rows[i] = 8 * grp[i] + frag_r;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = wn * 16 + 8 * j + 2 * frag_k + e;
+        const double cm = dmu_s[col];
+        const double cv = -2.0 * dvar_s[col];
+        const uint32_t zc = zb_s[col];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          acc[i][j][e] = (rows[i] < n) ? fma(cv, acc[i][j][e], cm * al_s[rows[i]]) * tab_s[__popc(zc ^ Zb_s[rows[i]])] : 0.0;
+      }
+    for (int c = 0; c < p.dm.n; ++c) {
+      double part[2][2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          double s = 0.0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) s = fma(acc[i][j][e], Dc_s[c * 128 + rows[i]], s);
+          s += __shfl_xor_sync(0xffffffffu, s, 4);
+          s += __shfl_xor_sync(0xffffffffu, s, 8);
+          s += __shfl_xor_sync(0xffffffffu, s, 16);
+          part[j][e] = s;
+        }
+      __syncthreads();  // red from the previous use has been consumed
+      if (frag_r == 0) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) red[wm * 32 + wn * 16 + 8 * j + 2 * frag_k + e] = part[j][e];
+      }
+      __syncthreads();
+      if (tid < S_BN) S_s[c * 32 + tid] = ((red[tid] + red[32 + tid]) + red[64 + tid]) + red[96 + tid];
+    }
+    __syncthreads();
+  }
+
+  SMALL_TS(8);
+  // ---- 7. per-tile partial sums over the 32 columns (one warp per output), then the completion chain --------------------
+  const int d = sp.d;
+  double* my_part = p.partial + (size_t(bi) * p.tiles + tile) * (1 + d);
+  const int n_tasks = p.need_grad ? 1 + p.dm.n + sp.n_int : 1;
+  for (int task = warp; task < n_tasks; task += S_THREADS / 32) {
+    if (task == 0) {
+      const double t = warp_sum(a_s[lane]);
+      if (lane == 0) my_part[0] = t;
+    } else if (task <= p.dm.n) {
+      const double t = warp_sum(S_s[(task - 1) * 32 + lane]);
+      if (lane == 0) my_part[1 + p.dm.dims[task - 1]] = t;
+    } else {
+      const int kd = task - 1 - p.dm.n;
+      const double pk = ps_s[kd];
+      const double zi = double(z_s[lane * sp.n_disc + kd]);
+      const double t = warp_sum(((a_s[lane] - g_s[0]) * (zi - pk)) / sp.tau);
+      if (lane == 0) my_part[1 + sp.int_cols[kd]] = t;
+    }
+  }
+  SMALL_TS(9);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) flag_s[0] = (atomicAdd(p.tile_done + bi, 1u) == unsigned(p.tiles - 1)) ? 1 : 0;
+  __syncthreads();
+  SMALL_TS(10);
+  if (!flag_s[0]) return;
+  // last tile of this restart: MC means over all tiles in a fixed order, Adam update
+  __threadfence();
+  if (tid <= d && (tid == 0 || p.need_grad)) {
+    double s = 0.0;
+    for (int t = 0; t < p.tiles; ++t) s += __ldcg(p.partial + (size_t(bi) * p.tiles + t) * (1 + d) + tid);
+    s /= double(p.mc);
+    if (tid == 0) {
+      p.out_value[bi] = s;
+    } else {
+      const int c = tid - 1;
+      const double go = p.grad_out ? p.grad_out[bi] : 1.0;
+      const double gacq = go * s;
+      if (p.out_grad) p.out_grad[size_t(bi) * d + c] = gacq;
+      if (p.adam_theta != nullptr) {  // torch.optim.Adam on loss = -acq(X).sum() (as adam_step_kernel)
+        const size_t idx = size_t(bi) * d + c;
+        const double g = -gacq;
+        const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+        const double mi = p.adam_m[idx] + (g - p.adam_m[idx]) * (1.0 - b1);
+        const double vi = p.adam_v[idx] * b2 + (1.0 - b2) * g * g;
+        p.adam_m[idx] = mi;
+        p.adam_v[idx] = vi;
+        const double bc1 = g_s[1];
+        const double bc2 = g_s[2];
+        p.adam_theta[idx] = p.adam_theta[idx] - (p.lr / bc1) * (mi / (sqrt(vi) / sqrt(bc2) + eps));
+      }
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    p.tile_done[bi] = 0u;
+    flag_s[1] = (atomicAdd(p.done, 1u) == unsigned(p.nb - 1)) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!flag_s[1]) return;
+  // last restart of the call: EMA baseline over ALL restarts (probabilistic_reparameterization.py:499-505), step counter
+  __threadfence();
+  if (warp == 0) {
+    double v = 0.0;
+    for (int i = lane; i < p.nb; i += 32) v += __ldcg(p.out_value + i);
+    v = warp_sum(v);
+    if (lane == 0) {
+      if (p.update_ma && p.ma_state != nullptr) {
+        const double mean = v / double(p.nb);
+        const double hidden = p.ma_state[1];
+        p.ma_state[0] += 1.0;
+        p.ma_state[1] = hidden - (hidden - mean) * (1.0 - 0.7);
+      }
+      if (p.step_ptr && p.adam_theta != nullptr) *p.step_ptr += 1;
+      *p.done = 0u;
+    }
+  }
+}
+
+cudaError_t small_step_timestamps(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_small_ts, sizeof(long long) * 16);
+}
+
+bool small_step_eligible(const Model& m, const DevSpace& sp, const DimMap& dm, int b, int mc) {
+  static const bool off = getenv("PRB_NO_SMALL_STEP") != nullptr;
+  return !off && m.sep_ok && m.Mp1 == 128 && m.Kp <= 128 && mc % S_BN == 0 && mc >= S_BN && dm.n <= S_MAXC &&
+         sp.n_disc <= 32 && sp.n_cat == 0 && sp.d <= 32 && b >= 1;
+}
+
+size_t small_step_scratch_bytes(int b, int mc, int d) {
+  return (size_t(b) * (mc / S_BN) * (1 + d)) * sizeof(double) + size_t(b + 1) * sizeof(unsigned int) + 64;
+}
+
+cudaError_t small_step_init() {
+  return cudaFuncSetAttribute(sep_small_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMALL_SMEM_BYTES));
+}
+
+cudaError_t launch_small_step(const Model& m, const DevSpace& sp, const DevAcq& aq, const BitMap& bm, const DimMap& dm,
+                              const double* theta_in, const double* lower, const double* upper, double* Xc, int b, int mc,
+                              const double* u_int, const double* u_cat, uint64_t seed, uint64_t offset, int estimator,
+                              double* ma_state, int update_ma, bool need_grad, const double* grad_out, double* out_value,
+                              double* out_grad, double* adam_theta, double* adam_m, double* adam_v, double lr,
+                              int* step_ptr, void* scratch, cudaStream_t st) {
+  ProfScope prof_(K_ADAM, st);
+  SmallStepParams p;
+  memset(&p, 0, sizeof(p));
+  p.sp = sp;
+  p.bm = bm;
+  p.dm = dm;
+  p.fc = m.spec.t[0].f[m.sep_cont_factor];
+  p.aq = aq;
+  p.outputscale = m.spec.t[0].outputscale;
+  p.mean_const = m.mean_const;
+  p.kss = m.kss;
+  p.Xtr = m.Xtr;
+  p.n = m.n;
+  p.d_k = m.d_k;
+  p.nchunks = (m.n + 3) / 4;
+  p.alpha_pad = m.alpha_pad;
+  p.Zbits = m.Zbits;
+  p.tab = m.sep_tab;
+  p.ntab = m.sep_nbits;
+  p.theta = theta_in;
+  p.lower = lower;
+  p.upper = upper;
+  p.Xc = Xc;
+  p.mc = mc;
+  p.nb = b;
+  p.tiles = mc / S_BN;
+  p.u_int = u_int;
+  p.u_cat = u_cat;
+  p.seed = seed;
+  p.offset = offset;
+  p.estimator = estimator;
+  p.ma_state = ma_state;
+  p.update_ma = update_ma;
+  p.need_grad = need_grad ? 1 : 0;
+  p.grad_out = grad_out;
+  p.out_value = out_value;
+  p.out_grad = out_grad;
+  p.adam_theta = adam_theta;
+  p.adam_m = adam_m;
+  p.adam_v = adam_v;
+  p.lr = lr;
+  p.step_ptr = step_ptr;
+  p.partial = static_cast<double*>(scratch);
+  p.tile_done = reinterpret_cast<unsigned int*>(p.partial + size_t(b) * p.tiles * (1 + sp.d));
+  p.done = p.tile_done + b;
+  sep_small_step_kernel<<<b * p.tiles, S_THREADS, SMALL_SMEM_BYTES, st>>>(
+      *reinterpret_cast<const CUtensorMap*>(&m.mapA1), p);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace prb

@@ -125,6 +125,10 @@ uint64_t prb_launch_count(void);
  * counts per slot and clears the record.  Slots: 0 sampler, 1 cross-covariance panel, 2 triangular product (lower:
  * Linv k*), 3 acquisition epilogue, 4 triangular product (upper: Linv^T v), 5 gradient contraction, 6 split sums,
  * 7 MC reduction, 8 EMA update, 9 analytic build/reduce, 10 Adam/clamp, 11 other.                                     */
+/* Diagnostic: clock64() timestamps of CTA 0 at the phase boundaries of the last small-problem step kernel
+ * (prb_small.cu): 0 start, 1 TMA issued, 2 prep done, 3 operand generated, 4 A1 landed, 5 lower product, 6 acquisition
+ * epilogue, 7 upper product, 8 gradient contraction, 9 partial sums, 10 completion counter.  out16: host long long[16]. */
+int prb_debug_small_timestamps(long long* out16);
 #define PRB_PROFILE_SLOTS 12
 int prb_profile_enable(int on);
 int prb_profile_read(double* ms_by_kernel, uint64_t* launches_by_kernel, int32_t n_slots);

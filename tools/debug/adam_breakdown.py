@@ -30,3 +30,9 @@ for b in (5, 20):
     lib.prb_profile_enable(1); run(None, 50)
     msk = (C.c_double * 12)(); cnt = (C.c_uint64 * 12)(); lib.prb_profile_read(msk, cnt, 12); lib.prb_profile_enable(0)
     print({nm: (round(msk[i] / 51 * 1e3, 1), int(cnt[i]) // 51) for i, nm in enumerate(capi.PROFILE_SLOT_NAMES) if cnt[i]}, "us per step")
+
+ts = (C.c_longlong * 16)()
+lib.prb_debug_small_timestamps(ts)
+t = [ts[i] for i in range(11)]
+names = ["tma issue+const", "prep", "gen", "wait A1", "lower", "acq epilogue", "upper", "grad contraction", "partials", "fence+atomic"]
+print("small-step phases of CTA 0 (cycles):", {names[i]: t[i + 1] - t[i] for i in range(10)}, "total", t[10] - t[0])
