@@ -230,7 +230,7 @@ Plan make_plan(const Model& m, int64_t n_points, int n_restarts, int d_theta, in
   if (m.sep_ok && n_restarts > 0) {
     p.off_kc = take(size_t(n_restarts) * m.Kp * dbl);
     p.off_Dc = take(size_t(n_restarts) * d_theta * m.Kp * dbl);
-    p.small_bytes = (size_t(p.B_pad / 32 + n_restarts) * (1 + d_theta)) * dbl + size_t(n_restarts + 2) * sizeof(int) + 64;
+    p.small_bytes = (size_t(p.B_pad / 32 + n_restarts) * (1 + d_theta)) * dbl + size_t(n_restarts + 4) * sizeof(int) + 64;
     p.off_small = take(p.small_bytes);
     p.off_ucount = take(size_t(n_restarts) * sizeof(int));
     p.off_ustart = take(size_t(n_restarts + 1) * sizeof(int));
@@ -827,6 +827,13 @@ int prb_mc_adam(prb_model* model, const prb_space_desc* space, const prb_acq_des
   const bool small_step = fused_step && small_step_eligible(m, sp, dm, b, mc) &&
                           small_step_scratch_bytes(b, mc, sp.d) <= pl.small_bytes;
   if (small_step) CUDA_TRY(cudaMemsetAsync(at<char>(workspace, pl.off_small), 0, pl.small_bytes, st));
+  if (small_step && small_adam_persistent_ok(b, mc)) {
+    // the whole optimisation -- maxiter Adam steps and the final evaluation -- as one cooperative persistent kernel
+    CUDA_TRY(launch_small_adam_persistent(m, sp, aq, bm, dm, theta, lower, upper, b, mc, u_int, u_cat, seed, offset,
+                                          estimator, ma_state, update_ma, val, out_value, adam_state, adam_state + total,
+                                          lr, maxiter, step0, at<char>(workspace, pl.off_small), st));
+    return PRB_OK;
+  }
 
   auto one_iter = [&]() -> int {
     if (small_step) {

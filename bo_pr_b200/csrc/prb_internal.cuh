@@ -177,6 +177,14 @@ cudaError_t launch_small_step(const Model& m, const DevSpace& sp, const DevAcq& 
                               double* out_grad, double* adam_theta, double* adam_m, double* adam_v, double lr,
                               int* step_ptr, void* scratch, cudaStream_t st);
 
+bool small_adam_persistent_ok(int b, int mc);
+cudaError_t launch_small_adam_persistent(const Model& m, const DevSpace& sp, const DevAcq& aq, const BitMap& bm,
+                                         const DimMap& dm, double* theta, const double* lower, const double* upper, int b,
+                                         int mc, const double* u_int, const double* u_cat, uint64_t seed, uint64_t offset,
+                                         int estimator, double* ma_state, int update_ma, double* step_value,
+                                         double* final_value, double* adam_m, double* adam_v, double lr, int maxiter,
+                                         int step0, void* scratch, cudaStream_t st);
+
 // prb_gemm_tma.cu
 cudaError_t tma_init();
 cudaError_t make_operand_map(TensorMap* out, const double* base, int rows, int k_extent, int ld, int box_rows = 128);

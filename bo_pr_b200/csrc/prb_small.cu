@@ -65,7 +65,18 @@ struct SmallStepParams {
   double* partial;           // [nb, tiles, 1 + d]
   unsigned int* tile_done;   // [nb]
   unsigned int* done;        // [1]
+  // persistent mode (cooperative launch, every CTA resident): `iters` = maxiter Adam steps + the final clamp-and-evaluate,
+  // separated by a grid-wide barrier on `release`; single-step mode: iters = 1, persistent = 0
+  int iters, persistent, step0;
+  unsigned int* release;     // [1]
+  double* final_value;       // [nb] values of the final evaluation (persistent mode)
 };
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* ptr) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
 
 // shared-memory carve-up (doubles unless noted)
 constexpr int SM_A = 128 * 128;        // A1, [k-chunk][row][4]
@@ -137,17 +148,26 @@ __global__ void __launch_bounds__(S_THREADS, 1)
     Zb_s[tid] = p.Zbits[tid];
     al_s[tid] = p.alpha_pad[tid];
   }
-  // Everything that depends on the pre-call optimiser / EMA state is read before this CTA signals completion.  The three
+  const DimMap& dmref = p.dm;
+  for (int it = 0; it < p.iters; ++it) {
+  // persistent mode: the last iteration is the final clamp (in place) + value-only evaluation (gen.py:338-341)
+  const bool fin = p.persistent && (it == p.iters - 1);
+  const int need_grad = fin ? 0 : p.need_grad;
+  const bool do_adam = (p.adam_theta != nullptr) && !fin;
+  double* const Xc = fin ? p.adam_theta : p.Xc;
+  double* const out_value = fin ? p.final_value : p.out_value;
+  // Everything that depends on the pre-step optimiser / EMA state is read before this CTA signals completion.  The three
   // pow() calls (EMA de-biasing, Adam bias corrections) are FP64 and slow: one thread does them off the critical path.
+  // State that another CTA rewrote in the previous iteration is read with ld.cg (L1 is not coherent across SMs).
   if (tid == S_THREADS - 1) {
     double baseline = 0.0;
     if (p.estimator == PRB_EST_REINFORCE_MA && p.ma_state != nullptr) {
-      const double cnt = p.ma_state[0];
-      if (cnt != 0.0) baseline = p.ma_state[1] / (1.0 - pow(0.7, cnt));
+      const double cnt = __ldcg(p.ma_state);
+      if (cnt != 0.0) baseline = __ldcg(p.ma_state + 1) / (1.0 - pow(0.7, cnt));
     }
     g_s[0] = baseline;
-    if (p.adam_theta != nullptr) {
-      const double t_step = p.step_ptr ? double(*p.step_ptr + 1) : 1.0;
+    if (do_adam) {
+      const double t_step = p.persistent ? double(p.step0 + it + 1) : (p.step_ptr ? double(*p.step_ptr + 1) : 1.0);
       g_s[1] = 1.0 - pow(0.9, t_step);
       g_s[2] = 1.0 - pow(0.999, t_step);
     }
@@ -156,10 +176,10 @@ __global__ void __launch_bounds__(S_THREADS, 1)
   SMALL_TS(1);
   // ---- 1. prep: clamp, rounding probabilities, this tile's 32 samples, per-restart kernel factors ----------------------
   if (tid < sp.d) {
-    double v = p.theta[size_t(bi) * sp.d + tid];
+    double v = __ldcg(p.theta + size_t(bi) * sp.d + tid);
     if (p.lower) v = fmin(fmax(v, p.lower[tid]), p.upper[tid]);
     th_s[tid] = v;
-    if (p.Xc && tile == 0) p.Xc[size_t(bi) * sp.d + tid] = v;
+    if (Xc && tile == 0) Xc[size_t(bi) * sp.d + tid] = v;
   }
   if (tid < S_BN) zb_s[tid] = 0u;
   __syncthreads();
@@ -215,7 +235,7 @@ __global__ void __launch_bounds__(S_THREADS, 1)
   }
   __syncthreads();
   SMALL_TS(3);
-  mbar_wait(bar, 0);
+  if (it == 0) mbar_wait(bar, 0);  // A1 stays resident for every later iteration
   SMALL_TS(4);
 
   // row ownership as in prb_gemm_tma.cu: M-warp wm owns the 8-row groups {wm, 7 - wm, 8 + wm, 15 - wm}
@@ -316,7 +336,7 @@ __global__ void __launch_bounds__(S_THREADS, 1)
   // no barrier here: a_s / dmu_s / dvar_s are first read behind the barriers of the gradient contraction / partial sums
 
   SMALL_TS(6);
-  if (p.need_grad) {
+  if (need_grad) {
     // ---- 5. upper product: W[m, col] = sum_{k >= m} Linv[k, m] V[k, col], A1 read transposed out of A_s ---------------
     int ft_off[4];  // element (m = 8 g + r, k) of Linv^T lives at A_s[(m / 4) * 512 + k * 4 + m % 4]
 #pragma unroll
@@ -371,7 +391,7 @@ __global__ void __launch_bounds__(S_THREADS, 1)
         for (int i = 0; i < 4; ++i)
           acc[i][j][e] = (rows[i] < n) ? fma(cv, acc[i][j][e], cm * al_s[rows[i]]) * tab_s[__popc(zc ^ Zb_s[rows[i]])] : 0.0;
       }
-    for (int c = 0; c < p.dm.n; ++c) {
+    for (int c = 0; c < dmref.n; ++c) {
       double part[2][2];
 #pragma unroll
       for (int j = 0; j < 2; ++j)
@@ -402,16 +422,16 @@ __global__ void __launch_bounds__(S_THREADS, 1)
   // ---- 7. per-tile partial sums over the 32 columns (one warp per output), then the completion chain --------------------
   const int d = sp.d;
   double* my_part = p.partial + (size_t(bi) * p.tiles + tile) * (1 + d);
-  const int n_tasks = p.need_grad ? 1 + p.dm.n + sp.n_int : 1;
+  const int n_tasks = need_grad ? 1 + dmref.n + sp.n_int : 1;
   for (int task = warp; task < n_tasks; task += S_THREADS / 32) {
     if (task == 0) {
       const double t = warp_sum(a_s[lane]);
       if (lane == 0) my_part[0] = t;
-    } else if (task <= p.dm.n) {
+    } else if (task <= dmref.n) {
       const double t = warp_sum(S_s[(task - 1) * 32 + lane]);
-      if (lane == 0) my_part[1 + p.dm.dims[task - 1]] = t;
+      if (lane == 0) my_part[1 + dmref.dims[task - 1]] = t;
     } else {
-      const int kd = task - 1 - p.dm.n;
+      const int kd = task - 1 - dmref.n;
       const double pk = ps_s[kd];
       const double zi = double(z_s[lane * sp.n_disc + kd]);
       const double t = warp_sum(((a_s[lane] - g_s[0]) * (zi - pk)) / sp.tau);
@@ -421,62 +441,83 @@ __global__ void __launch_bounds__(S_THREADS, 1)
   SMALL_TS(9);
   __threadfence();
   __syncthreads();
-  if (tid == 0) flag_s[0] = (atomicAdd(p.tile_done + bi, 1u) == unsigned(p.tiles - 1)) ? 1 : 0;
+  if (tid == 0) {
+    flag_s[0] = (atomicAdd(p.tile_done + bi, 1u) == unsigned(p.tiles - 1)) ? 1 : 0;
+    flag_s[1] = 0;
+  }
   __syncthreads();
   SMALL_TS(10);
-  if (!flag_s[0]) return;
-  // last tile of this restart: MC means over all tiles in a fixed order, Adam update
-  __threadfence();
-  if (tid <= d && (tid == 0 || p.need_grad)) {
-    double s = 0.0;
-    for (int t = 0; t < p.tiles; ++t) s += __ldcg(p.partial + (size_t(bi) * p.tiles + t) * (1 + d) + tid);
-    s /= double(p.mc);
+  if (flag_s[0]) {
+    // last tile of this restart: MC means over all tiles in a fixed order, Adam update
+    __threadfence();
+    if (tid <= d && (tid == 0 || need_grad)) {
+      double s = 0.0;
+      for (int t = 0; t < p.tiles; ++t) s += __ldcg(p.partial + (size_t(bi) * p.tiles + t) * (1 + d) + tid);
+      s /= double(p.mc);
+      if (tid == 0) {
+        out_value[bi] = s;
+      } else {
+        const int c = tid - 1;
+        const double go = p.grad_out ? p.grad_out[bi] : 1.0;
+        const double gacq = go * s;
+        if (p.out_grad) p.out_grad[size_t(bi) * d + c] = gacq;
+        if (do_adam) {  // torch.optim.Adam on loss = -acq(X).sum() (as adam_step_kernel)
+          const size_t idx = size_t(bi) * d + c;
+          const double g = -gacq;
+          const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+          const double m_old = __ldcg(p.adam_m + idx);
+          const double mi = m_old + (g - m_old) * (1.0 - b1);
+          const double vi = __ldcg(p.adam_v + idx) * b2 + (1.0 - b2) * g * g;
+          p.adam_m[idx] = mi;
+          p.adam_v[idx] = vi;
+          const double bc1 = g_s[1];
+          const double bc2 = g_s[2];
+          p.adam_theta[idx] = __ldcg(p.adam_theta + idx) - (p.lr / bc1) * (mi / (sqrt(vi) / sqrt(bc2) + eps));
+        }
+      }
+    }
+    __threadfence();
+    __syncthreads();
     if (tid == 0) {
-      p.out_value[bi] = s;
-    } else {
-      const int c = tid - 1;
-      const double go = p.grad_out ? p.grad_out[bi] : 1.0;
-      const double gacq = go * s;
-      if (p.out_grad) p.out_grad[size_t(bi) * d + c] = gacq;
-      if (p.adam_theta != nullptr) {  // torch.optim.Adam on loss = -acq(X).sum() (as adam_step_kernel)
-        const size_t idx = size_t(bi) * d + c;
-        const double g = -gacq;
-        const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
-        const double mi = p.adam_m[idx] + (g - p.adam_m[idx]) * (1.0 - b1);
-        const double vi = p.adam_v[idx] * b2 + (1.0 - b2) * g * g;
-        p.adam_m[idx] = mi;
-        p.adam_v[idx] = vi;
-        const double bc1 = g_s[1];
-        const double bc2 = g_s[2];
-        p.adam_theta[idx] = p.adam_theta[idx] - (p.lr / bc1) * (mi / (sqrt(vi) / sqrt(bc2) + eps));
+      p.tile_done[bi] = 0u;
+      flag_s[1] = (atomicAdd(p.done, 1u) == unsigned(p.nb - 1)) ? 1 : 0;
+    }
+    __syncthreads();
+    if (flag_s[1]) {
+      // last restart of the step: EMA baseline over ALL restarts (probabilistic_reparameterization.py:499-505), step counter
+      __threadfence();
+      if (warp == 0) {
+        double v = 0.0;
+        for (int i = lane; i < p.nb; i += 32) v += __ldcg(out_value + i);
+        v = warp_sum(v);
+        if (lane == 0) {
+          if (p.update_ma && p.ma_state != nullptr) {
+            const double mean = v / double(p.nb);
+            const double hidden = __ldcg(p.ma_state + 1);
+            p.ma_state[0] = __ldcg(p.ma_state) + 1.0;
+            p.ma_state[1] = hidden - (hidden - mean) * (1.0 - 0.7);
+          }
+          if (!p.persistent && p.step_ptr && do_adam) *p.step_ptr += 1;
+          *p.done = 0u;
+          if (p.persistent) {  // open the grid barrier: everything this step wrote is visible before the flag is
+            __threadfence();
+            atomicExch(p.release, unsigned(it + 1));
+          }
+        }
       }
     }
   }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    p.tile_done[bi] = 0u;
-    flag_s[1] = (atomicAdd(p.done, 1u) == unsigned(p.nb - 1)) ? 1 : 0;
-  }
-  __syncthreads();
-  if (!flag_s[1]) return;
-  // last restart of the call: EMA baseline over ALL restarts (probabilistic_reparameterization.py:499-505), step counter
-  __threadfence();
-  if (warp == 0) {
-    double v = 0.0;
-    for (int i = lane; i < p.nb; i += 32) v += __ldcg(p.out_value + i);
-    v = warp_sum(v);
-    if (lane == 0) {
-      if (p.update_ma && p.ma_state != nullptr) {
-        const double mean = v / double(p.nb);
-        const double hidden = p.ma_state[1];
-        p.ma_state[0] += 1.0;
-        p.ma_state[1] = hidden - (hidden - mean) * (1.0 - 0.7);
+  if (p.persistent && it + 1 < p.iters) {
+    // grid-wide barrier between steps (all CTAs are co-resident: cooperative launch); bounded spin, trap instead of hanging
+    if (tid == 0) {
+      unsigned int spins = 0;
+      while (ld_acquire_u32(p.release) < unsigned(it + 1)) {
+        if (++spins > (1u << 28)) __trap();
       }
-      if (p.step_ptr && p.adam_theta != nullptr) *p.step_ptr += 1;
-      *p.done = 0u;
     }
+    __syncthreads();
   }
+  }  // iterations
 }
 
 cudaError_t small_step_timestamps(long long* host_out) {
@@ -490,21 +531,16 @@ bool small_step_eligible(const Model& m, const DevSpace& sp, const DimMap& dm, i
 }
 
 size_t small_step_scratch_bytes(int b, int mc, int d) {
-  return (size_t(b) * (mc / S_BN) * (1 + d)) * sizeof(double) + size_t(b + 1) * sizeof(unsigned int) + 64;
+  return (size_t(b) * (mc / S_BN) * (1 + d)) * sizeof(double) + size_t(b + 2) * sizeof(unsigned int) + 64;
 }
 
 cudaError_t small_step_init() {
   return cudaFuncSetAttribute(sep_small_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMALL_SMEM_BYTES));
 }
 
-cudaError_t launch_small_step(const Model& m, const DevSpace& sp, const DevAcq& aq, const BitMap& bm, const DimMap& dm,
-                              const double* theta_in, const double* lower, const double* upper, double* Xc, int b, int mc,
-                              const double* u_int, const double* u_cat, uint64_t seed, uint64_t offset, int estimator,
-                              double* ma_state, int update_ma, bool need_grad, const double* grad_out, double* out_value,
-                              double* out_grad, double* adam_theta, double* adam_m, double* adam_v, double lr,
-                              int* step_ptr, void* scratch, cudaStream_t st) {
-  ProfScope prof_(K_ADAM, st);
-  SmallStepParams p;
+static void fill_small_params(SmallStepParams& p, const Model& m, const DevSpace& sp, const DevAcq& aq, const BitMap& bm,
+                              const DimMap& dm, int b, int mc, const double* u_int, const double* u_cat, uint64_t seed,
+                              uint64_t offset, int estimator, double* ma_state, int update_ma, void* scratch) {
   memset(&p, 0, sizeof(p));
   p.sp = sp;
   p.bm = bm;
@@ -522,10 +558,6 @@ cudaError_t launch_small_step(const Model& m, const DevSpace& sp, const DevAcq& 
   p.Zbits = m.Zbits;
   p.tab = m.sep_tab;
   p.ntab = m.sep_nbits;
-  p.theta = theta_in;
-  p.lower = lower;
-  p.upper = upper;
-  p.Xc = Xc;
   p.mc = mc;
   p.nb = b;
   p.tiles = mc / S_BN;
@@ -536,6 +568,26 @@ cudaError_t launch_small_step(const Model& m, const DevSpace& sp, const DevAcq& 
   p.estimator = estimator;
   p.ma_state = ma_state;
   p.update_ma = update_ma;
+  p.partial = static_cast<double*>(scratch);
+  p.tile_done = reinterpret_cast<unsigned int*>(p.partial + size_t(b) * p.tiles * (1 + sp.d));
+  p.done = p.tile_done + b;
+  p.release = p.done + 1;
+  p.iters = 1;
+}
+
+cudaError_t launch_small_step(const Model& m, const DevSpace& sp, const DevAcq& aq, const BitMap& bm, const DimMap& dm,
+                              const double* theta_in, const double* lower, const double* upper, double* Xc, int b, int mc,
+                              const double* u_int, const double* u_cat, uint64_t seed, uint64_t offset, int estimator,
+                              double* ma_state, int update_ma, bool need_grad, const double* grad_out, double* out_value,
+                              double* out_grad, double* adam_theta, double* adam_m, double* adam_v, double lr,
+                              int* step_ptr, void* scratch, cudaStream_t st) {
+  ProfScope prof_(K_ADAM, st);
+  SmallStepParams p;
+  fill_small_params(p, m, sp, aq, bm, dm, b, mc, u_int, u_cat, seed, offset, estimator, ma_state, update_ma, scratch);
+  p.theta = theta_in;
+  p.lower = lower;
+  p.upper = upper;
+  p.Xc = Xc;
   p.need_grad = need_grad ? 1 : 0;
   p.grad_out = grad_out;
   p.out_value = out_value;
@@ -545,13 +597,58 @@ cudaError_t launch_small_step(const Model& m, const DevSpace& sp, const DevAcq& 
   p.adam_v = adam_v;
   p.lr = lr;
   p.step_ptr = step_ptr;
-  p.partial = static_cast<double*>(scratch);
-  p.tile_done = reinterpret_cast<unsigned int*>(p.partial + size_t(b) * p.tiles * (1 + sp.d));
-  p.done = p.tile_done + b;
   sep_small_step_kernel<<<b * p.tiles, S_THREADS, SMALL_SMEM_BYTES, st>>>(
       *reinterpret_cast<const CUtensorMap*>(&m.mapA1), p);
   count_launch();
   return cudaGetLastError();
+}
+
+// Can the whole multi-start Adam run as ONE cooperative launch?  Every CTA must be resident (one per SM: 182 KB of
+// shared memory each) because the steps are separated by a grid-wide barrier.
+bool small_adam_persistent_ok(int b, int mc) {
+  static int sms = -1, coop = 0;
+  if (sms < 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess)
+      sms = 0;
+  }
+  static const bool off = getenv("PRB_NO_PERSISTENT") != nullptr;
+  return !off && coop && b * (mc / S_BN) <= sms;
+}
+
+// gen_candidates_torch (gen.py:304-343) as one persistent kernel: maxiter x (clamp -> value + gradient -> Adam), then the
+// final clamp and value-only evaluation; the steps are separated by a grid barrier instead of kernel boundaries.
+cudaError_t launch_small_adam_persistent(const Model& m, const DevSpace& sp, const DevAcq& aq, const BitMap& bm,
+                                         const DimMap& dm, double* theta, const double* lower, const double* upper, int b,
+                                         int mc, const double* u_int, const double* u_cat, uint64_t seed, uint64_t offset,
+                                         int estimator, double* ma_state, int update_ma, double* step_value,
+                                         double* final_value, double* adam_m, double* adam_v, double lr, int maxiter,
+                                         int step0, void* scratch, cudaStream_t st) {
+  ProfScope prof_(K_ADAM, st);
+  SmallStepParams p;
+  fill_small_params(p, m, sp, aq, bm, dm, b, mc, u_int, u_cat, seed, offset, estimator, ma_state, update_ma, scratch);
+  p.theta = theta;
+  p.lower = lower;
+  p.upper = upper;
+  p.Xc = nullptr;
+  p.need_grad = 1;
+  p.out_value = step_value;
+  p.final_value = final_value;
+  p.adam_theta = theta;
+  p.adam_m = adam_m;
+  p.adam_v = adam_v;
+  p.lr = lr;
+  p.iters = maxiter + 1;
+  p.persistent = 1;
+  p.step0 = step0;
+  CUtensorMap tm = *reinterpret_cast<const CUtensorMap*>(&m.mapA1);
+  void* args[] = {&tm, &p};
+  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&sep_small_step_kernel), dim3(b * p.tiles),
+                                              dim3(S_THREADS), args, SMALL_SMEM_BYTES, st);
+  g_launches += 1;  // one launch; it stands for (maxiter + 1) fused steps
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace prb
