@@ -433,6 +433,16 @@ int mc_core(prb_model* model, const DevSpace& sp, const DevAcq& aq, const Plan& 
   const bool sep = pl.off_kc != 0 && sep_space_ok(m, sp, &bm, &dm);
   int rc;
   const bool dedup = sep && m.opt_dedup && m.sep_nbits <= DEDUP_MAX_BITS;
+  // experiment sizes: the whole call -- sampler, both products, acquisition, reductions, EMA -- is one kernel (prb_small.cu)
+  if (sep && !dedup && out_acq_values == nullptr && small_step_eligible(m, sp, dm, b, mc) &&
+      small_step_scratch_bytes(b, mc, sp.d) <= pl.small_bytes) {
+    // completion counters live behind the per-tile partial sums: zero the (small) scratch; launches re-arm them themselves
+    CUDA_TRY(cudaMemsetAsync(at<char>(ws, pl.off_small), 0, small_step_scratch_bytes(b, mc, sp.d), st));
+    CUDA_TRY(launch_small_step(m, sp, aq, bm, dm, theta, nullptr, nullptr, nullptr, b, mc, u_int, u_cat, seed, offset,
+                               estimator, ma_state, (update_ma && ma_state) ? 1 : 0, need_grad, grad_out, out_value,
+                               out_grad, nullptr, nullptr, nullptr, 0.0, nullptr, at<char>(ws, pl.off_small), st));
+    return PRB_OK;
+  }
   if (dedup) {
     // unique (restart, code) columns only; per-sample values are scattered back on request
     double* a_u = at<double>(ws, pl.off_a);
@@ -754,6 +764,34 @@ int prb_mc_value_grad(prb_model* model, const prb_space_desc* space, const prb_a
   if (workspace_bytes < pl.total) return PRB_ERR_WORKSPACE;
   return mc_core(model, sp, aq, pl, workspace, theta, b, mc, u_int, u_cat, seed, offset, estimator, ma_state,
                  update_ma, grad_out, out_value, out_grad, out_acq_values, static_cast<cudaStream_t>(stream));
+}
+
+int prb_mc_screen(prb_model* model, const prb_space_desc* space, const prb_acq_desc* acq, const double* theta, int32_t n_rows,
+                  int32_t chunk_rows, int32_t mc, const double* u_int, const double* u_cat, uint64_t seed, uint64_t offset,
+                  int32_t estimator, double* ma_state, double* out_value, void* workspace, size_t workspace_bytes,
+                  int32_t chunk_cols, void* stream) {
+  if (!model || !theta || !out_value || n_rows < 0 || chunk_rows < 1 || mc < 1 || !workspace) return PRB_ERR_INVALID;
+  if (estimator != PRB_EST_REINFORCE && estimator != PRB_EST_REINFORCE_MA) return PRB_ERR_INVALID;
+  const Model& m = *reinterpret_cast<Model*>(model);
+  DevSpace sp;
+  DevAcq aq;
+  int rc = make_space(space, &sp);
+  if (rc != PRB_OK) return rc;
+  if ((rc = make_acq(acq, &aq)) != PRB_OK) return rc;
+  if (sp.d_k != m.d_k) return PRB_ERR_INVALID;
+  const int cmax = chunk_rows < n_rows ? chunk_rows : n_rows;
+  if (cmax == 0) return PRB_OK;
+  const Plan pl = make_plan(m, int64_t(cmax) * mc, cmax, sp.d, chunk_cols);
+  if (workspace_bytes < pl.total) return PRB_ERR_WORKSPACE;
+  for (int r0 = 0; r0 < n_rows; r0 += chunk_rows) {
+    const int nr = n_rows - r0 < chunk_rows ? n_rows - r0 : chunk_rows;
+    // every chunk is one forward call of the reference: value only, EMA state advanced once
+    rc = mc_core(model, sp, aq, pl, workspace, theta + size_t(r0) * sp.d, nr, mc, u_int, u_cat, seed, offset, estimator,
+                 ma_state, ma_state ? 1 : 0, nullptr, out_value + r0, nullptr, nullptr,
+                 static_cast<cudaStream_t>(stream));
+    if (rc != PRB_OK) return rc;
+  }
+  return PRB_OK;
 }
 
 int prb_analytic_value_grad(prb_model* model, const prb_space_desc* space, const prb_acq_desc* acq,

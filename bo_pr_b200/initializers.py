@@ -147,7 +147,12 @@ def gen_batch_initial_conditions(
                 # one host->device copy and one device->host read for the whole screening pass (the reference moves every
                 # chunk separately, initializers.py:184-190; the chunked CALLS are kept, they advance the EMA state)
                 X_dev = X_rnd.to(device=device)
-                Y_rnd = torch.cat([acq_function(X_dev[s:s + limit]) for s in range(0, X_dev.shape[0], limit)]).cpu()
+                if hasattr(acq_function, "screen") and q == 1:
+                    # MC-PR acquisition functions run the chunk loop inside the library (prb_mc_screen)
+                    Y_rnd = acq_function.screen(X_dev, limit).cpu()
+                else:
+                    Y_rnd = torch.cat([acq_function(X_dev[s:s + limit])
+                                       for s in range(0, X_dev.shape[0], limit)]).cpu()
             batch_initial_conditions = init_func(X=X_rnd, Y=Y_rnd, n=num_restarts, **init_kwargs).to(device=device)
             if not any(issubclass(w.category, BadInitialCandidatesWarning) for w in ws):
                 return batch_initial_conditions

@@ -150,16 +150,15 @@ class AbstractProbabilisticReparameterization(AcquisitionFunctionWrapper, ABC):
         else:
             unnormalized_X = X.clone()
         prob = self.input_transform["round"].get_rounding_prob(X=unnormalized_X)
-        discrete_idx = 0
-        for i in self.integer_indices:
-            p = prob[..., discrete_idx]
-            rounding_component = torch.distributions.Bernoulli(probs=p).sample()
-            unnormalized_X[..., i] = unnormalized_X[..., i].floor() + rounding_component
-            discrete_idx += 1
-        if self.integer_indices.numel() > 0:
-            unnormalized_X[..., self.integer_indices] = torch.minimum(
-                torch.maximum(unnormalized_X[..., self.integer_indices], self.integer_bounds[0]),
-                self.integer_bounds[1])
+        n_int = int(self.integer_indices.numel())
+        if n_int > 0:
+            # all integer parameters in one draw (the reference loops over them, :204-215; the per-parameter Bernoulli
+            # draws are independent, so only the consumption order of torch's generator differs)
+            idx = self.integer_indices
+            rounding_component = torch.bernoulli(prob[..., :n_int])
+            vals = unnormalized_X[..., idx].floor() + rounding_component
+            unnormalized_X[..., idx] = torch.minimum(torch.maximum(vals, self.integer_bounds[0]), self.integer_bounds[1])
+        discrete_idx = n_int
         raw_idx = self.cont_indices.shape[0] + discrete_idx
         if self.categorical_indices.shape[0] > 0:
             for i, cardinality in self.categorical_features.items():
@@ -296,6 +295,34 @@ class MCProbabilisticReparameterization(AbstractProbabilisticReparameterization)
             integer_bounds=integer_bounds, categorical_features=categorical_features, mc_samples=mc_samples, tau=tau,
             rng=rng, philox_seed=philox_seed)
         self.input_transform_flip = None
+
+    def screen(self, X: Tensor, chunk_rows: Optional[int] = None) -> Tensor:
+        """Value-only evaluation of ``X [n, 1, d]`` in consecutive chunks of ``chunk_rows`` rows, one ``prb_mc_screen`` call
+        (no host work between chunks).  Equivalent to ``torch.cat([self(X[s:s + chunk_rows]) for s in ...])`` under
+        ``torch.no_grad()``, including the EMA-baseline state (one update per chunk)."""
+        _check_X(X, self.dim)
+        n, d = X.shape[0], X.shape[-1]
+        chunk = n if chunk_rows is None else int(chunk_rows)
+        out = torch.empty(n, dtype=torch.float64, device=X.device)
+        if n == 0:
+            return out
+        state = gp_state_from_model(self.acq_function.model)
+        state.set_option(capi.PRB_OPT_DEDUP, int(self.dedup))
+        rnd = self.input_transform["round"]
+        rnd.ensure_base_samples(1, X.device)
+        u_int, u_cat = rnd.base_sample_ptrs()
+        theta = X.detach().to(torch.float64).reshape(n, d).contiguous()
+        rows = min(chunk, n)
+        ws = state.workspace(rows * rnd.mc_samples, d, rows)
+        est = capi.PRB_EST_REINFORCE_MA if self.grad_estimator == "reinforce_ma" else capi.PRB_EST_REINFORCE
+        sp, aq = self._space(), acq_desc_of(self.acq_function)
+        with torch.cuda.device(X.device):
+            st = torch.cuda.current_stream().cuda_stream
+            capi.check(state.lib.prb_mc_screen(state.handle, C.byref(sp), C.byref(aq), theta.data_ptr(), n, chunk,
+                                               rnd.mc_samples, capi.ptr(u_int), capi.ptr(u_cat), 0, 0, est,
+                                               self.ma_counter.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                               int(state.chunk_cols), st), "prb_mc_screen")
+        return out
 
     def forward(self, X: Tensor) -> Tensor:
         _check_X(X, self.dim)

@@ -207,6 +207,16 @@ int prb_mc_value_grad(prb_model* model, const prb_space_desc* space, const prb_a
                       const double* grad_out, double* out_value, double* out_grad, double* out_acq_values,
                       void* workspace, size_t workspace_bytes, int32_t chunk_cols, void* stream);
 
+/* Raw-sample screening: the value-only MC-PR forward of prb_mc_value_grad applied to theta [n_rows, d] in consecutive chunks
+ * of `chunk_rows` rows, one enqueue after the other with no host work in between.  Each chunk counts as ONE forward call for
+ * the EMA-baseline state, exactly as the chunked loop it replaces.
+ * Replaces: the init_batch_limit loop of gen_batch_initial_conditions (initializers.py:179-191).
+ * out_value [n_rows].  The workspace must cover prb_workspace_bytes(model, chunk_rows * mc, chunk_rows, d, chunk_cols).   */
+int prb_mc_screen(prb_model* model, const prb_space_desc* space, const prb_acq_desc* acq, const double* theta,
+                  int32_t n_rows, int32_t chunk_rows, int32_t mc, const double* u_int, const double* u_cat, uint64_t seed,
+                  uint64_t offset, int32_t estimator, double* ma_state, double* out_value, void* workspace,
+                  size_t workspace_bytes, int32_t chunk_cols, void* stream);
+
 /* Analytic probabilistic reparameterization: sum over all discrete configurations.
  * Replaces: AnalyticProbabilisticReparameterization.forward + autograd (probabilistic_reparameterization.py:285-320,
  * input.py:410-488).  options [n_options, n_int + n_cat] int32: un-normalised integer value per integer parameter,

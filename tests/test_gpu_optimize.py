@@ -82,3 +82,39 @@ def test_optimize_acqf_pr_ei_improves_over_initial_conditions():
     final = pr.sample_candidates(cand)
     assert bool(((final[..., 3:] == 0) | (final[..., 3:] == 1)).all())
     assert torch.equal(final[..., :3], cand[..., :3])
+
+
+def test_screen_equals_chunked_forward_calls():
+    """prb_mc_screen (the init_batch_limit loop inside the library) = the chunked Python loop, EMA state included."""
+    g = make_problem(100, seed=4)
+    g["case"].update(mc=64, grad_estimator="reinforce_ma")
+    g["base_samples"] = sobol_base_samples(64)
+    g["base_samples_categorical"] = None
+    X = make_theta(70, seed=8).to(DEV)  # ragged last chunk
+    pr_a = product_mc_pr(g, DEV)
+    with torch.no_grad():
+        ya = torch.cat([pr_a(X[s:s + 32]) for s in range(0, 70, 32)])
+    pr_b = product_mc_pr(g, DEV)
+    yb = pr_b.screen(X, 32)
+    assert torch.allclose(ya, yb, rtol=1e-12, atol=1e-15)
+    assert torch.allclose(pr_a._ma_state, pr_b._ma_state, rtol=1e-12, atol=0)
+    assert float(pr_b._ma_state[0]) == 3.0
+
+
+@pytest.mark.parametrize("b,mc,n", [(40, 128, 100), (3, 32, 127), (6, 96, 60)])
+def test_small_step_paths_match_host_loop(b, mc, n):
+    """Experiment-sized problems: the persistent cooperative kernel (restarts x mc / 32 <= 148 CTAs), the one-kernel step
+    replayed from a graph (more CTAs than SMs) and the host-driven loop over single fused calls follow one trajectory."""
+    g = make_problem(n, seed=6)
+    g["case"].update(mc=mc, grad_estimator="reinforce_ma")
+    g["base_samples"] = sobol_base_samples(mc)
+    g["base_samples_categorical"] = None
+    bounds = _bounds(13)
+    ics = make_theta(b, seed=5).to(DEV)
+    pr_f = product_mc_pr(g, DEV)
+    cand_f, val_f = B.gen_candidates_torch(ics, pr_f, bounds[0], bounds[1], options={"maxiter": 8})
+    pr_h = product_mc_pr(g, DEV)
+    cand_h, val_h = B.gen_candidates_torch(ics, pr_h, bounds[0], bounds[1], options={"maxiter": 8, "fused": False})
+    assert torch.allclose(cand_f, cand_h, rtol=0, atol=1e-10), (cand_f - cand_h).abs().max()
+    assert torch.allclose(val_f, val_h, rtol=1e-8, atol=1e-12)
+    assert torch.allclose(pr_f._ma_state, pr_h._ma_state, rtol=1e-9, atol=0)
