@@ -160,7 +160,8 @@ __device__ __forceinline__ double pr_sample_int(const DevSpace& sp, const double
   const double xa = offs[k] + zb;
   const double xs = (x_un < 0.0) ? -xa : xa;
   const double xc = fmin(fmax(xs, lo), hi);
-  const double tn = sp.raw_int ? xc : __dsub_rn(xc, lo) / range;
+  // x / 1.0 == x exactly: binary parameters (range 1) skip the FP64 divide without changing a bit
+  const double tn = sp.raw_int ? xc : (range == 1.0 ? __dsub_rn(xc, lo) : __dsub_rn(xc, lo) / range);
   *z_out = ((__dsub_rn(tn, x) > 0.0) || (x == 1.0)) ? 1 : 0;
   return tn;
 }

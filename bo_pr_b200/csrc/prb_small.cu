@@ -89,14 +89,18 @@ constexpr int SM_S = S_MAXC * 32;
 constexpr int SM_ACQ = 3 * 32;
 constexpr int SM_VEC = 4 * 32;         // th, ps, offs, g
 constexpr int SM_TAB = 64;
-constexpr int SM_DOUBLES = SM_A + SM_B + SM_KC + SM_DC + SM_AL + SM_RED + SM_S + SM_ACQ + SM_VEC + SM_TAB;
+constexpr int SM_U = 32 * 32;          // base uniforms of this tile's 32 samples (fixed for the life of the kernel)
+constexpr int SM_X = 128 * S_MAXC;     // training inputs, continuous-factor columns only
+constexpr int SM_PART = 8 * 33;        // staging of the per-tile partial sums in the finish chain
+constexpr int SM_DOUBLES =
+    SM_A + SM_B + SM_KC + SM_DC + SM_AL + SM_RED + SM_S + SM_ACQ + SM_VEC + SM_TAB + SM_U + SM_X + SM_PART;
 constexpr size_t SMALL_SMEM_BYTES = size_t(SM_DOUBLES) * 8 + 128 * 4 + 32 * 4 + 32 * 32 + 16 + 16;
 
 // phase timestamps of CTA 0 (clock64), read back by prb_debug_small_timestamps(): diagnostic for the latency budget
 __device__ long long g_small_ts[16];
-#define SMALL_TS(k)                                            \
-  do {                                                         \
-    if (blockIdx.x == 0 && threadIdx.x == 0) g_small_ts[k] = clock64(); \
+#define SMALL_TS(k)                                                               \
+  do {                                                                            \
+    if (blockIdx.x == 0 && threadIdx.x == 0 && ts_on) g_small_ts[k] = clock64(); \
   } while (0)
 
 __global__ void __launch_bounds__(S_THREADS, 1)
@@ -117,7 +121,10 @@ __global__ void __launch_bounds__(S_THREADS, 1)
   double* offs_s = ps_s + 32;
   double* g_s = offs_s + 32;
   double* tab_s = g_s + 32;
-  uint32_t* Zb_s = reinterpret_cast<uint32_t*>(tab_s + SM_TAB);  // [128]
+  double* u_s = tab_s + SM_TAB;   // [32][n_int]
+  double* X_s = u_s + SM_U;       // [128][S_MAXC]
+  double* pt_s = X_s + SM_X;      // [8][33]
+  uint32_t* Zb_s = reinterpret_cast<uint32_t*>(pt_s + SM_PART);  // [128]
   uint32_t* zb_s = Zb_s + 128;                                   // [32]
   uint8_t* z_s = reinterpret_cast<uint8_t*>(zb_s + 32);          // [32][n_disc <= 32]
   uint64_t* bar = reinterpret_cast<uint64_t*>(z_s + 32 * 32);
@@ -130,6 +137,7 @@ __global__ void __launch_bounds__(S_THREADS, 1)
   const int i0 = tile * S_BN;  // first MC sample of this tile
   const int n = p.n;
 
+  bool ts_on = true;  // timestamps: the launch prologue, then the second iteration (a steady-state gradient step) if any
   SMALL_TS(0);
   // ---- 0. A1 -> shared memory by TMA (only the k-chunks that hold non-zero columns) --------------------------------
   if (tid == 0) {
@@ -147,9 +155,20 @@ __global__ void __launch_bounds__(S_THREADS, 1)
   if (tid < 128) {
     Zb_s[tid] = p.Zbits[tid];
     al_s[tid] = p.alpha_pad[tid];
+    for (int di = 0; di < p.fc.n_dims; ++di)
+      X_s[tid * S_MAXC + di] = (tid < n) ? p.Xtr[size_t(tid) * p.d_k + p.fc.dims[di]] : 0.0;
+  }
+  // The base uniforms of this tile's samples never change between steps (the reference caches its Sobol base samples, the
+  // Philox stream is keyed on (sample, parameter) only): fetched / generated once, kept in shared memory.
+  for (int e = tid; e < S_BN * sp.n_int; e += S_THREADS) {
+    const int col = e / sp.n_int, k = e % sp.n_int;
+    u_s[e] = p.u_int ? p.u_int[size_t(i0 + col) * sp.n_int + k]
+                     : philox_uniform(p.seed, p.offset, uint32_t(i0 + col), uint32_t(k));
   }
   const DimMap& dmref = p.dm;
   for (int it = 0; it < p.iters; ++it) {
+  ts_on = (it == (p.iters > 2 ? 1 : p.iters - 1));
+  SMALL_TS(11);
   // persistent mode: the last iteration is the final clamp (in place) + value-only evaluation (gen.py:338-341)
   const bool fin = p.persistent && (it == p.iters - 1);
   const int need_grad = fin ? 0 : p.need_grad;
@@ -191,7 +210,7 @@ __global__ void __launch_bounds__(S_THREADS, 1)
     const int col = tid & 31;
     for (int k = tid >> 5; k < sp.n_int; k += 4) {
       uint8_t zk;
-      const double tn = pr_sample_int(sp, th_s, ps_s, offs_s, i0 + col, k, p.u_int, p.seed, p.offset, &zk);
+      const double tn = pr_sample_int(sp, th_s, ps_s, offs_s, col, k, u_s, 0, 0, &zk);  // u = u_s[col * n_int + k]
       z_s[col * sp.n_disc + k] = zk;
       if (p.bm.pos[k] >= 0 && tn != 0.0) atomicOr(&zb_s[col], 1u << p.bm.pos[k]);
     }
@@ -203,7 +222,7 @@ __global__ void __launch_bounds__(S_THREADS, 1)
       double r2 = 0.0;
       for (int di = 0; di < p.fc.n_dims; ++di) {
         const int dim = p.fc.dims[di];
-        const double df = (th_s[dim] - p.Xtr[size_t(j) * p.d_k + dim]) * p.fc.inv_ls[di];
+        const double df = (th_s[dim] - X_s[j * S_MAXC + di]) * p.fc.inv_ls[di];
         r2 = fma(df, df, r2);
       }
       val = p.outputscale * matern52(r2, &G);
@@ -212,7 +231,7 @@ __global__ void __launch_bounds__(S_THREADS, 1)
     for (int di = 0; di < p.fc.n_dims; ++di) {
       const int dim = p.fc.dims[di];
       double v = 0.0;
-      if (j < n) v = p.outputscale * G * (p.fc.inv_ls[di] * p.fc.inv_ls[di]) * (th_s[dim] - p.Xtr[size_t(j) * p.d_k + dim]);
+      if (j < n) v = p.outputscale * G * (p.fc.inv_ls[di] * p.fc.inv_ls[di]) * (th_s[dim] - X_s[j * S_MAXC + di]);
       Dc_s[di * 128 + j] = v;
     }
   }
@@ -439,30 +458,33 @@ __global__ void __launch_bounds__(S_THREADS, 1)
     }
   }
   SMALL_TS(9);
+  // ---- 8. completion: ONE ticket over all CTAs of the step.  The last CTA to arrive finishes the step for every restart:
+  // MC means from the per-tile partial sums (fixed order), Adam update, EMA baseline, and opens the grid barrier.
   __threadfence();
   __syncthreads();
-  if (tid == 0) {
-    flag_s[0] = (atomicAdd(p.tile_done + bi, 1u) == unsigned(p.tiles - 1)) ? 1 : 0;
-    flag_s[1] = 0;
-  }
+  if (tid == 0) flag_s[0] = (atomicAdd(p.done, 1u) == unsigned(p.nb * p.tiles - 1)) ? 1 : 0;
   __syncthreads();
   SMALL_TS(10);
   if (flag_s[0]) {
-    // last tile of this restart: MC means over all tiles in a fixed order, Adam update
     __threadfence();
-    if (tid <= d && (tid == 0 || need_grad)) {
+    const int nslot = need_grad ? 1 + d : 1;
+    for (int e = tid; e < p.nb * nslot; e += S_THREADS) {
+      const int rb = e / nslot, sl = e % nslot;
+      const double* src = p.partial + size_t(rb) * p.tiles * (1 + d) + sl;
       double s = 0.0;
-      for (int t = 0; t < p.tiles; ++t) s += __ldcg(p.partial + (size_t(bi) * p.tiles + t) * (1 + d) + tid);
+#pragma unroll 4
+      for (int t = 0; t < p.tiles; ++t) s += __ldcg(src + size_t(t) * (1 + d));
       s /= double(p.mc);
-      if (tid == 0) {
-        out_value[bi] = s;
+      if (sl == 0) {
+        out_value[rb] = s;
+        if (rb < SM_PART) pt_s[rb] = s;
       } else {
-        const int c = tid - 1;
-        const double go = p.grad_out ? p.grad_out[bi] : 1.0;
+        const int c = sl - 1;
+        const double go = p.grad_out ? p.grad_out[rb] : 1.0;
         const double gacq = go * s;
-        if (p.out_grad) p.out_grad[size_t(bi) * d + c] = gacq;
+        if (p.out_grad) p.out_grad[size_t(rb) * d + c] = gacq;
         if (do_adam) {  // torch.optim.Adam on loss = -acq(X).sum() (as adam_step_kernel)
-          const size_t idx = size_t(bi) * d + c;
+          const size_t idx = size_t(rb) * d + c;
           const double g = -gacq;
           const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
           const double m_old = __ldcg(p.adam_m + idx);
@@ -470,43 +492,33 @@ __global__ void __launch_bounds__(S_THREADS, 1)
           const double vi = __ldcg(p.adam_v + idx) * b2 + (1.0 - b2) * g * g;
           p.adam_m[idx] = mi;
           p.adam_v[idx] = vi;
-          const double bc1 = g_s[1];
-          const double bc2 = g_s[2];
-          p.adam_theta[idx] = __ldcg(p.adam_theta + idx) - (p.lr / bc1) * (mi / (sqrt(vi) / sqrt(bc2) + eps));
+          p.adam_theta[idx] = __ldcg(p.adam_theta + idx) - (p.lr / g_s[1]) * (mi / (sqrt(vi) / sqrt(g_s[2]) + eps));
         }
       }
     }
-    __threadfence();
     __syncthreads();
-    if (tid == 0) {
-      p.tile_done[bi] = 0u;
-      flag_s[1] = (atomicAdd(p.done, 1u) == unsigned(p.nb - 1)) ? 1 : 0;
-    }
-    __syncthreads();
-    if (flag_s[1]) {
-      // last restart of the step: EMA baseline over ALL restarts (probabilistic_reparameterization.py:499-505), step counter
-      __threadfence();
-      if (warp == 0) {
-        double v = 0.0;
-        for (int i = lane; i < p.nb; i += 32) v += __ldcg(out_value + i);
-        v = warp_sum(v);
-        if (lane == 0) {
-          if (p.update_ma && p.ma_state != nullptr) {
-            const double mean = v / double(p.nb);
-            const double hidden = __ldcg(p.ma_state + 1);
-            p.ma_state[0] = __ldcg(p.ma_state) + 1.0;
-            p.ma_state[1] = hidden - (hidden - mean) * (1.0 - 0.7);
-          }
-          if (!p.persistent && p.step_ptr && do_adam) *p.step_ptr += 1;
-          *p.done = 0u;
-          if (p.persistent) {  // open the grid barrier: everything this step wrote is visible before the flag is
-            __threadfence();
-            atomicExch(p.release, unsigned(it + 1));
-          }
+    if (warp == 0) {
+      // EMA baseline over ALL restarts (probabilistic_reparameterization.py:499-505), fixed summation order
+      double v = 0.0;
+      for (int i = lane; i < p.nb; i += 32) v += (i < SM_PART) ? pt_s[i] : out_value[i];
+      v = warp_sum(v);
+      if (lane == 0) {
+        if (p.update_ma && p.ma_state != nullptr) {
+          const double mean = v / double(p.nb);
+          const double hidden = __ldcg(p.ma_state + 1);
+          p.ma_state[0] = __ldcg(p.ma_state) + 1.0;
+          p.ma_state[1] = hidden - (hidden - mean) * (1.0 - 0.7);
+        }
+        if (!p.persistent && p.step_ptr && do_adam) *p.step_ptr += 1;
+        *p.done = 0u;
+        if (p.persistent) {  // open the grid barrier: everything this step wrote is visible before the flag is
+          __threadfence();
+          atomicExch(p.release, unsigned(it + 1));
         }
       }
     }
   }
+  SMALL_TS(12);
   if (p.persistent && it + 1 < p.iters) {
     // grid-wide barrier between steps (all CTAs are co-resident: cooperative launch); bounded spin, trap instead of hanging
     if (tid == 0) {
@@ -517,6 +529,7 @@ __global__ void __launch_bounds__(S_THREADS, 1)
     }
     __syncthreads();
   }
+  SMALL_TS(13);
   }  // iterations
 }
 

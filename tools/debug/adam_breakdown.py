@@ -33,6 +33,8 @@ for b in (5, 20):
 
 ts = (C.c_longlong * 16)()
 lib.prb_debug_small_timestamps(ts)
-t = [ts[i] for i in range(11)]
-names = ["tma issue+const", "prep", "gen", "wait A1", "lower", "acq epilogue", "upper", "grad contraction", "partials", "fence+atomic"]
-print("small-step phases of CTA 0 (cycles):", {names[i]: t[i + 1] - t[i] for i in range(10)}, "total", t[10] - t[0])
+t = [ts[i] for i in range(14)]
+seq = [11, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 13]
+names = ["state reads", "prep", "gen", "wait A1", "lower", "acq epilogue", "upper", "grad contraction", "partials",
+         "fence+ticket", "finish chain", "grid barrier"]
+print("steady-state step of CTA 0 (cycles):", {names[i]: t[seq[i + 1]] - t[seq[i]] for i in range(12)}, "total", t[13] - t[11])
