@@ -31,7 +31,7 @@ EXPORTS = [
     "prb_version", "prb_abi_sizeof", "prb_debug_small_timestamps", "prb_launch_count", "prb_profile_enable", "prb_profile_read", "prb_status_string", "prb_last_cuda_error", "prb_model_create", "prb_model_destroy", "prb_model_set_option",
     "prb_model_n", "prb_model_dk", "prb_workspace_bytes", "prb_philox_uniform", "prb_pr_sample",
     "prb_analytic_enumerate", "prb_kernel_matrix", "prb_acq_points",
-    "prb_mc_value_grad", "prb_mc_screen", "prb_analytic_value_grad", "prb_mc_adam",
+    "prb_mc_value_grad", "prb_mc_screen", "prb_analytic_value_grad", "prb_mc_adam", "prb_analytic_adam",
 ]
 
 
@@ -112,6 +112,8 @@ def load_library() -> C.CDLL:
                                             vp, vp, vp, vp, vp, sz, i32, vp]
     lib.prb_mc_adam.argtypes = [vp, C.POINTER(PrbSpaceDesc), C.POINTER(PrbAcqDesc), vp, i32, i32, vp, vp, u64, u64,
                                 i32, vp, vp, vp, dbl, i32, i32, vp, vp, vp, sz, i32, vp]
+    lib.prb_analytic_adam.argtypes = [vp, C.POINTER(PrbSpaceDesc), C.POINTER(PrbAcqDesc), vp, i32, vp, i32, vp, vp, dbl, i32,
+                                      i32, vp, vp, vp, sz, i32, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("prb_version",):

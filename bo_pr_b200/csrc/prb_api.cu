@@ -162,6 +162,7 @@ struct Plan {
   size_t off_Xc, off_grad, off_ones, off_val, off_step;
   size_t off_zbits, off_kc, off_Dc;
   size_t off_done, off_small, small_bytes;
+  int grad_jrows;  // training rows per CTA of the generic gradient contraction (16 for small panels, else 128)
   size_t off_ucount, off_ustart, off_utotal, off_ucode, off_uweight, off_inv, off_zbits_u, off_colb, off_wu;
   size_t total;
 };
@@ -219,7 +220,10 @@ Plan make_plan(const Model& m, int64_t n_points, int n_restarts, int d_theta, in
   p.off_panelV = take(size_t(C) * m.Mp1 * dbl);
   p.off_norm = take(size_t(m.Mp1 / GEMM_BM) * C * dbl);
   p.off_mu = take(size_t(C) * dbl);
-  p.off_S_part = take(size_t(m.Mp2 / GRAD_JSPLIT_ROWS) * m.d_k * C * dbl);
+  // small panels: 16 training rows per CTA of the generic gradient contraction instead of 128 (8x the CTAs; the kernel is
+  // a serial loop over its rows, 90 us at n = 119 with one CTA per 128 columns)
+  p.grad_jrows = ((m.Mp2 / GEMM_BM) * (C / 128) < 120) ? 16 : GRAD_JSPLIT_ROWS;
+  p.off_S_part = take(size_t(m.Mp2 / p.grad_jrows) * m.d_k * C * dbl);
   p.off_Xc = take(size_t(p.B_pad) * d_theta * dbl);
   p.off_grad = take(size_t(p.B_pad) * d_theta * dbl);
   p.off_ones = take(size_t(p.B_pad) * dbl);
@@ -261,21 +265,21 @@ int run_engine(const Model& m, const DevAcq& aq, const Plan& pl, void* ws, const
   double* norm = at<double>(ws, pl.off_norm);
   double* mu = at<double>(ws, pl.off_mu);
   double* S_part = at<double>(ws, pl.off_S_part);
-  TensorMap mapK, mapV;
-  CUDA_TRY(make_operand_map(&mapK, panelA, pl.C, m.Kp, m.Kp));
-  CUDA_TRY(make_operand_map(&mapV, panelV, pl.C, m.Kp, m.Mp1));
+
   for (int64_t c0 = 0; c0 < B; c0 += pl.C) {
     const int ncols = int(B - c0 < pl.C ? B - c0 : pl.C);
     const int ncols_pad = round_up(ncols, 128);
     const double* xkc = xk + size_t(c0) * m.d_k;
     CUDA_TRY(launch_kstar_panel(m, xkc, ncols, ncols_pad, panelA, st));
-    CUDA_TRY(launch_tma_lower(m, mapK, ncols_pad, need_grad ? panelV : nullptr, norm, mu, st));
+    CUDA_TRY(launch_tma_lower(m, panelA, pl.C, ncols_pad, need_grad ? panelV : nullptr, norm, mu, st));
     CUDA_TRY(launch_acq_epilogue(m, aq, norm, ncols_pad, mu, ncols, a + c0, dmu + c0, dvar + c0,
                                  out_mean ? out_mean + c0 : nullptr, out_var ? out_var + c0 : nullptr, nullptr, 0, st));
     if (need_grad) {
-      CUDA_TRY(launch_tma_upper(m, mapV, ncols_pad, panelA, st));
-      CUDA_TRY(launch_grad_contract(m, diffmask, xkc, ncols, ncols_pad, panelA, dmu + c0, dvar + c0, S_part, st));
-      CUDA_TRY(launch_sum_splits(m, S_part, nullptr, ncols, ncols_pad, S_all + size_t(c0) * m.d_k, nullptr, 0, st));
+      CUDA_TRY(launch_tma_upper(m, panelV, pl.C, ncols_pad, panelA, st));
+      CUDA_TRY(launch_grad_contract(m, diffmask, xkc, ncols, ncols_pad, panelA, dmu + c0, dvar + c0, S_part,
+                                    pl.grad_jrows, st));
+      CUDA_TRY(launch_sum_splits(m, S_part, m.Mp2 / pl.grad_jrows, nullptr, ncols, ncols_pad,
+                                 S_all + size_t(c0) * m.d_k, nullptr, 0, st));
     }
   }
   return PRB_OK;
@@ -348,7 +352,8 @@ int run_engine_sep(const Model& m, const DevAcq& aq, const Plan& pl, void* ws, c
                                    ncols_dev, c0, st));
     if (need_grad) {
       CUDA_TRY(launch_tma_upper_grad(m, panelV, pl.C, sa, ncols, ncols_pad, dmu + c0, dvar + c0, S_part, st));
-      CUDA_TRY(launch_sum_splits(m, S_part, &dm, ncols, ncols_pad, S_all + size_t(c0) * m.d_k, ncols_dev, c0, st));
+      CUDA_TRY(launch_sum_splits(m, S_part, m.Mp2 / GEMM_BM, &dm, ncols, ncols_pad, S_all + size_t(c0) * m.d_k, ncols_dev,
+                                 c0, st));
     }
   }
   return PRB_OK;
@@ -476,6 +481,58 @@ int mc_core(prb_model* model, const DevSpace& sp, const DevAcq& aq, const Plan& 
   CUDA_TRY(launch_mc_reduce(sp, b, mc, a, z, prob, S_all, estimator, ma_state, grad_out, out_value, out_grad, st));
   if (update_ma && ma_state) CUDA_TRY(launch_ma_update(out_value, b, ma_state, st));
   return PRB_OK;
+}
+
+// clamp -> value + gradient -> Adam, `maxiter` times, then the final clamp and value-only evaluation (gen.py:304-343).  One
+// step is captured into a CUDA graph and replayed; `core(X, grad_ones_or_null, value_out, grad_out_or_null)` enqueues one
+// evaluation of the acquisition function on `st`.
+template <typename Core>
+int adam_graph_loop(Core core, double* theta, const double* lower, const double* upper, int b, int d, double lr, int maxiter,
+                    int step0, double* adam_state, double* out_value, double* Xc, double* grad, double* ones, double* val,
+                    int* step, cudaStream_t st) {
+  const int total = b * d;
+  CUDA_TRY(launch_fill(ones, 1.0, b, st));
+  CUDA_TRY(cudaMemcpyAsync(step, &step0, sizeof(int), cudaMemcpyHostToDevice, st));
+  auto one_iter = [&]() -> int {
+    CUDA_TRY(launch_clamp(theta, lower, upper, b, d, Xc, st));
+    int r = core(Xc, ones, val, grad);
+    if (r != PRB_OK) return r;
+    CUDA_TRY(launch_adam_step(theta, grad, adam_state, adam_state + total, total, lr, step, st));
+    return PRB_OK;
+  };
+  bool graphed = false;
+  if (st != nullptr && maxiter >= 4) {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      const unsigned long long l0 = g_launches;
+      int r = one_iter();
+      const unsigned long long per_iter = g_launches - l0;
+      cudaError_t e = cudaStreamEndCapture(st, &graph);
+      if (r == PRB_OK && e == cudaSuccess && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+        cudaError_t le = cudaSuccess;
+        for (int it = 0; it < maxiter && le == cudaSuccess; ++it) le = cudaGraphLaunch(exec, st);
+        graphed = (le == cudaSuccess);
+        if (graphed) g_launches += per_iter * (unsigned long long)(maxiter - 1);
+        cudaStreamSynchronize(st);  // exec/graph must outlive the enqueued launches
+        cudaGraphExecDestroy(exec);
+        if (!graphed) {
+          cudaGraphDestroy(graph);
+          return cuda_fail(le, "cudaGraphLaunch");
+        }
+      }
+      if (graph) cudaGraphDestroy(graph);
+      (void)cudaGetLastError();
+    }
+  }
+  if (!graphed) {
+    for (int it = 0; it < maxiter; ++it) {
+      int rc = one_iter();
+      if (rc != PRB_OK) return rc;
+    }
+  }
+  CUDA_TRY(launch_clamp(theta, lower, upper, b, d, theta, st));
+  return core(theta, nullptr, out_value, nullptr);
 }
 
 }  // namespace
@@ -824,6 +881,43 @@ int prb_analytic_value_grad(prb_model* model, const prb_space_desc* space, const
   if (rc != PRB_OK) return rc;
   CUDA_TRY(launch_analytic_reduce(sp, theta, b, n_options, options, a, probs, S_all, grad_out, out_value, out_grad, st));
   return PRB_OK;
+}
+
+int prb_analytic_adam(prb_model* model, const prb_space_desc* space, const prb_acq_desc* acq, double* theta, int32_t b,
+                      const int32_t* options, int32_t n_options, const double* lower, const double* upper, double lr,
+                      int32_t maxiter, int32_t step0, double* adam_state, double* out_value, void* workspace,
+                      size_t workspace_bytes, int32_t chunk_cols, void* stream) {
+  if (!model || !theta || !options || !lower || !upper || !adam_state || !out_value || b < 1 || n_options < 1 ||
+      maxiter < 0 || !workspace)
+    return PRB_ERR_INVALID;
+  const Model& m = *reinterpret_cast<Model*>(model);
+  DevSpace sp;
+  DevAcq aq;
+  int rc = make_space(space, &sp);
+  if (rc != PRB_OK) return rc;
+  if ((rc = make_acq(acq, &aq)) != PRB_OK) return rc;
+  if (sp.d_k != m.d_k) return PRB_ERR_INVALID;
+  const int64_t B = int64_t(b) * n_options;
+  const Plan pl = make_plan(m, B, b, sp.d, chunk_cols);
+  if (workspace_bytes < pl.total) return PRB_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* xk = at<double>(workspace, pl.off_xk);
+  double* probs = at<double>(workspace, pl.off_probs);
+  double* a = at<double>(workspace, pl.off_a);
+  double* S_all = at<double>(workspace, pl.off_S_all);
+  auto core = [&](const double* X, const double* go, double* value, double* g) -> int {
+    CUDA_TRY(launch_analytic_build(sp, X, b, n_options, options, xk, probs, st));
+    const bool need_path = go != nullptr && sp.n_cont > 0;
+    int r = run_engine(m, aq, pl, workspace, xk, B, need_path, cont_mask(sp), a, at<double>(workspace, pl.off_dmu),
+                       at<double>(workspace, pl.off_dvar), S_all, nullptr, nullptr, st);
+    if (r != PRB_OK) return r;
+    CUDA_TRY(launch_analytic_reduce(sp, X, b, n_options, options, a, probs, S_all, go, value, g, st));
+    return PRB_OK;
+  };
+  return adam_graph_loop(core, theta, lower, upper, b, sp.d, lr, maxiter, step0, adam_state, out_value,
+                         at<double>(workspace, pl.off_Xc), at<double>(workspace, pl.off_grad),
+                         at<double>(workspace, pl.off_ones), at<double>(workspace, pl.off_val),
+                         at<int>(workspace, pl.off_step), st);
 }
 
 int prb_mc_adam(prb_model* model, const prb_space_desc* space, const prb_acq_desc* acq, double* theta, int32_t b,

@@ -505,6 +505,8 @@ cudaError_t tma_init() {
       reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_UPPER_GRAD, 64, 128>),
       reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_LOWER_TMA, 128>),
       reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_UPPER_W, 128>),
+      reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_LOWER_TMA, 32>),
+      reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_UPPER_W, 32>),
       reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_UPPER_GRAD, 128>),
       reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_UPPER_GRAD, 32>),
   };
@@ -602,29 +604,52 @@ cudaError_t launch_tma_lower_gen(const Model& m, const SepArgs& sa, int ncols_pa
   return le != cudaSuccess ? le : cudaGetLastError();
 }
 
-cudaError_t launch_tma_lower(const Model& m, const TensorMap& mapB, int ncols_pad, double* VT, double* norm_part,
-                             double* mu_dot, cudaStream_t st) {
+// generic path (materialised operands): 128-column tiles, or 32 when that leaves most SMs idle
+static int pick_bn_generic(const Model& m, int ncols_pad, bool upper) {
+  const int tiles128 = ((upper ? m.Mp2 : m.Mp1) / T_BM) * (ncols_pad / 128);
+  return tiles128 < 120 ? 32 : 128;
+}
+
+cudaError_t launch_tma_lower(const Model& m, const double* panelK, int panel_rows, int ncols_pad, double* VT,
+                             double* norm_part, double* mu_dot, cudaStream_t st) {
   ProfScope prof_(K_TRGEMM_LOWER, st);
   TmaGemmParams p;
-  fill_common(p, m, ncols_pad, false);
+  const int bn = pick_bn_generic(m, ncols_pad, false);
+  fill_common(p, m, ncols_pad, false, bn);
   p.C = VT;
   p.ldc = m.Mp1;
   p.norm_part = norm_part;
   p.mu_dot = mu_dot;
-  trgemm_tma_kernel<MODE_LOWER_TMA, 128><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(
-      *reinterpret_cast<const CUtensorMap*>(&m.mapA1), *reinterpret_cast<const CUtensorMap*>(&mapB), p);
+  TensorMap mapK;  // the k* panel [panel_rows, Kp], box = 4 k values x bn columns
+  cudaError_t e = make_operand_map(&mapK, panelK, panel_rows, m.Kp, m.Kp, bn);
+  if (e != cudaSuccess) return e;
+  const CUtensorMap& mA = *reinterpret_cast<const CUtensorMap*>(&m.mapA1);
+  const CUtensorMap& mB = *reinterpret_cast<const CUtensorMap*>(&mapK);
+  if (bn == 32)
+    trgemm_tma_kernel<MODE_LOWER_TMA, 32><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(mA, mB, p);
+  else
+    trgemm_tma_kernel<MODE_LOWER_TMA, 128><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(mA, mB, p);
   count_launch();
   return cudaGetLastError();
 }
 
-cudaError_t launch_tma_upper(const Model& m, const TensorMap& mapB, int ncols_pad, double* W, cudaStream_t st) {
+cudaError_t launch_tma_upper(const Model& m, const double* panelV, int panel_rows, int ncols_pad, double* W,
+                             cudaStream_t st) {
   ProfScope prof_(K_TRGEMM_UPPER, st);
   TmaGemmParams p;
-  fill_common(p, m, ncols_pad, true);
+  const int bn = pick_bn_generic(m, ncols_pad, true);
+  fill_common(p, m, ncols_pad, true, bn);
   p.C = W;
   p.ldc = ncols_pad;
-  trgemm_tma_kernel<MODE_UPPER_W, 128><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(
-      *reinterpret_cast<const CUtensorMap*>(&m.mapA2), *reinterpret_cast<const CUtensorMap*>(&mapB), p);
+  TensorMap mapV;
+  cudaError_t e = make_operand_map(&mapV, panelV, panel_rows, m.Kp, m.Mp1, bn);
+  if (e != cudaSuccess) return e;
+  const CUtensorMap& mA = *reinterpret_cast<const CUtensorMap*>(&m.mapA2);
+  const CUtensorMap& mB = *reinterpret_cast<const CUtensorMap*>(&mapV);
+  if (bn == 32)
+    trgemm_tma_kernel<MODE_UPPER_W, 32><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(mA, mB, p);
+  else
+    trgemm_tma_kernel<MODE_UPPER_W, 128><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(mA, mB, p);
   count_launch();
   return cudaGetLastError();
 }

@@ -190,9 +190,10 @@ cudaError_t tma_init();
 cudaError_t make_operand_map(TensorMap* out, const double* base, int rows, int k_extent, int ld, int box_rows = 128);
 cudaError_t launch_tma_lower_gen(const Model& m, const SepArgs& sa, int ncols_pad, double* VT, double* norm_part,
                                  double* mu_dot, const FusedAcq* fa, cudaStream_t st);
-cudaError_t launch_tma_lower(const Model& m, const TensorMap& mapB, int ncols_pad, double* VT, double* norm_part,
-                             double* mu_dot, cudaStream_t st);
-cudaError_t launch_tma_upper(const Model& m, const TensorMap& mapB, int ncols_pad, double* W, cudaStream_t st);
+cudaError_t launch_tma_lower(const Model& m, const double* panelK, int panel_rows, int ncols_pad, double* VT,
+                             double* norm_part, double* mu_dot, cudaStream_t st);
+cudaError_t launch_tma_upper(const Model& m, const double* panelV, int panel_rows, int ncols_pad, double* W,
+                             cudaStream_t st);
 cudaError_t launch_tma_upper_grad(const Model& m, const double* panelV, int panel_rows, const SepArgs& sa, int ncols,
                                   int ncols_pad, const double* dmu, const double* dvar, double* S_part,
                                   cudaStream_t st);

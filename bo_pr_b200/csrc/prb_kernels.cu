@@ -199,23 +199,24 @@ __device__ __forceinline__ double eval_kernel_value(const DevSpec& spec, const d
 
 __global__ void __launch_bounds__(KS_ROWS) kstar_panel_kernel(const DevSpec spec, const double* __restrict__ Xtr, int n,
                                                                int Kp, const double* __restrict__ xk, int ncols,
-                                                               int ncols_store, double* __restrict__ KstarT) {
+                                                               int ncols_store, double* __restrict__ KstarT,
+                                                               int ks_cols) {
   extern __shared__ double sm[];
   const int d_k = spec.d_k;
   double* Xs = sm;                     // [d_k][KS_ROWS]
-  double* xs = sm + d_k * KS_ROWS;     // [KS_COLS][d_k]
+  double* xs = sm + d_k * KS_ROWS;     // [ks_cols][d_k]
   const int tid = threadIdx.x;
   const int j = blockIdx.x * KS_ROWS + tid;
-  const int col0 = blockIdx.y * KS_COLS;
+  const int col0 = blockIdx.y * ks_cols;
   const bool valid = j < n;
   for (int dd = 0; dd < d_k; ++dd) Xs[dd * KS_ROWS + tid] = valid ? Xtr[size_t(j) * d_k + dd] : 0.0;
-  for (int idx = tid; idx < KS_COLS * d_k; idx += KS_ROWS) {
+  for (int idx = tid; idx < ks_cols * d_k; idx += KS_ROWS) {
     const int c = idx / d_k;
     xs[idx] = (col0 + c < ncols) ? xk[size_t(col0) * d_k + idx] : 0.0;
   }
   __syncthreads();
   if (j >= Kp) return;
-  for (int c = 0; c < KS_COLS; ++c) {
+  for (int c = 0; c < ks_cols; ++c) {
     const int col = col0 + c;
     double v = 0.0;
     if (col >= ncols_store) break;
@@ -227,9 +228,11 @@ __global__ void __launch_bounds__(KS_ROWS) kstar_panel_kernel(const DevSpec spec
 cudaError_t launch_kstar_panel(const Model& m, const double* xk, int ncols, int ncols_pad, double* KstarT,
                                cudaStream_t st) {
   ProfScope prof_(K_KSTAR, st);
-  dim3 grid((m.Kp + KS_ROWS - 1) / KS_ROWS, ncols_pad / KS_COLS);
+  // few columns: 8 per CTA instead of 32, so that a small panel still spreads over the SMs
+  const int ks_cols = (m.Kp + KS_ROWS - 1) / KS_ROWS * (ncols_pad / KS_COLS) < 148 ? 8 : KS_COLS;
+  dim3 grid((m.Kp + KS_ROWS - 1) / KS_ROWS, ncols_pad / ks_cols);
   const size_t smem = size_t(m.d_k) * (KS_ROWS + KS_COLS) * sizeof(double);
-  kstar_panel_kernel<<<grid, KS_ROWS, smem, st>>>(m.spec, m.Xtr, m.n, m.Kp, xk, ncols, ncols_pad, KstarT);
+  kstar_panel_kernel<<<grid, KS_ROWS, smem, st>>>(m.spec, m.Xtr, m.n, m.Kp, xk, ncols, ncols_pad, KstarT, ks_cols);
   count_launch();
   return cudaGetLastError();
 }
@@ -241,7 +244,7 @@ cudaError_t launch_kernel_matrix(const DevSpec& spec, const double* Xtr, int n, 
   if (n_points == 0) return cudaSuccess;
   dim3 grid((n + KS_ROWS - 1) / KS_ROWS, (n_points + KS_COLS - 1) / KS_COLS);
   const size_t smem = size_t(spec.d_k) * (KS_ROWS + KS_COLS) * sizeof(double);
-  kstar_panel_kernel<<<grid, KS_ROWS, smem, st>>>(spec, Xtr, n, n, xk, n_points, n_points, out);
+  kstar_panel_kernel<<<grid, KS_ROWS, smem, st>>>(spec, Xtr, n, n, xk, n_points, n_points, out, KS_COLS);
   count_launch();
   return cudaGetLastError();
 }
@@ -395,17 +398,17 @@ __global__ void __launch_bounds__(GR_COLS) grad_contract_kernel(const DevSpec sp
                                                                 int ncols_pad, const double* __restrict__ W,
                                                                 const double* __restrict__ dmu,
                                                                 const double* __restrict__ dvar,
-                                                                double* __restrict__ S_part) {
+                                                                double* __restrict__ S_part, int jrows) {
   extern __shared__ double sm[];
   const int d_k = spec.d_k;
   double* xs = sm;                                   // [d_k][GR_COLS]
   double* accs = xs + d_k * GR_COLS;                 // [d_k][GR_COLS]
-  double* Xs = accs + d_k * GR_COLS;                 // [GRAD_JSPLIT_ROWS][d_k]
-  double* als = Xs + GRAD_JSPLIT_ROWS * d_k;         // [GRAD_JSPLIT_ROWS]
+  double* Xs = accs + d_k * GR_COLS;                 // [jrows][d_k]
+  double* als = Xs + jrows * d_k;                    // [jrows]
   const int tid = threadIdx.x;
   const int col = blockIdx.x * GR_COLS + tid;
-  const int j0 = blockIdx.y * GRAD_JSPLIT_ROWS;
-  const int jn = min(GRAD_JSPLIT_ROWS, n - j0);
+  const int j0 = blockIdx.y * jrows;
+  const int jn = max(0, min(jrows, n - j0));
   const bool cvalid = col < ncols;
   for (int dd = 0; dd < d_k; ++dd) {
     xs[dd * GR_COLS + tid] = cvalid ? xk[size_t(col) * d_k + dd] : 0.0;
@@ -480,17 +483,17 @@ __global__ void __launch_bounds__(GR_COLS) grad_contract_kernel(const DevSpec sp
 }
 
 cudaError_t launch_grad_contract(const Model& m, uint32_t diffmask, const double* xk, int ncols, int ncols_pad,
-                                 const double* W, const double* dmu, const double* dvar, double* S_part,
+                                 const double* W, const double* dmu, const double* dvar, double* S_part, int jrows,
                                  cudaStream_t st) {
   ProfScope prof_(K_GRAD_CONTRACT, st);
-  dim3 grid(ncols_pad / GR_COLS, m.Mp2 / GRAD_JSPLIT_ROWS);
-  const size_t smem = (size_t(m.d_k) * (2 * GR_COLS + GRAD_JSPLIT_ROWS) + GRAD_JSPLIT_ROWS) * sizeof(double);
+  dim3 grid(ncols_pad / GR_COLS, m.Mp2 / jrows);
+  const size_t smem = (size_t(m.d_k) * (2 * GR_COLS + jrows) + jrows) * sizeof(double);
   if (smem > 48 * 1024) {  // d_k > 15: opt in to a larger dynamic shared-memory window (at most 99 KB at d_k = 32)
     cudaError_t e = cudaFuncSetAttribute(grad_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
   }
   grad_contract_kernel<<<grid, GR_COLS, smem, st>>>(m.spec, diffmask, m.Xtr, m.alpha, m.n, xk, ncols, ncols_pad, W,
-                                                    dmu, dvar, S_part);
+                                                    dmu, dvar, S_part, jrows);
   count_launch();
   return cudaGetLastError();
 }
@@ -509,14 +512,14 @@ __global__ void sum_splits_kernel(const double* __restrict__ S_part, int jblocks
   }
 }
 
-cudaError_t launch_sum_splits(const Model& m, const double* S_part, const DimMap* dm, int ncols, int ncols_pad,
-                              double* S_all, const int* ncols_dev, int64_t col0, cudaStream_t st) {
+cudaError_t launch_sum_splits(const Model& m, const double* S_part, int jblocks, const DimMap* dm, int ncols,
+                              int ncols_pad, double* S_all, const int* ncols_dev, int64_t col0, cudaStream_t st) {
   ProfScope prof_(K_SUM_SPLITS, st);
   if (ncols == 0) return cudaSuccess;
   DimMap ident;
   ident.n = m.d_k;
   for (int i = 0; i < PRB_MAX_DIMS; ++i) ident.dims[i] = i;
-  sum_splits_kernel<<<(ncols + 127) / 128, 128, 0, st>>>(S_part, m.Mp2 / GRAD_JSPLIT_ROWS, dm ? *dm : ident, m.d_k,
+  sum_splits_kernel<<<(ncols + 127) / 128, 128, 0, st>>>(S_part, jblocks, dm ? *dm : ident, m.d_k,
                                                          ncols, ncols_pad, S_all, ncols_dev, col0);
   count_launch();
   return cudaGetLastError();
@@ -724,51 +727,54 @@ cudaError_t launch_dedup_scatter(const double* a, const int* ustart, const int* 
 //   continuous columns: grad_out_b * mean_i S[i, col]                                (:624-633)
 //   baseline from the PRE-update EMA state (:600-609).
 // =====================================================================================================================
-__global__ void __launch_bounds__(128) mc_reduce_kernel(const DevSpace sp, int mc, const double* __restrict__ a,
-                                                        const uint8_t* __restrict__ z,
-                                                        const double* __restrict__ prob,
-                                                        const double* __restrict__ S_all, int estimator,
-                                                        const double* __restrict__ ma_state,
-                                                        const double* __restrict__ grad_out,
-                                                        double* __restrict__ out_value,
-                                                        double* __restrict__ out_grad) {
-  __shared__ double red[32];
+constexpr int REDUCE_THREADS = 512;
+__global__ void __launch_bounds__(REDUCE_THREADS) mc_reduce_kernel(const DevSpace sp, int mc, const double* __restrict__ a,
+                                                                   const uint8_t* __restrict__ z,
+                                                                   const double* __restrict__ prob,
+                                                                   const double* __restrict__ S_all, int estimator,
+                                                                   const double* __restrict__ ma_state,
+                                                                   const double* __restrict__ grad_out,
+                                                                   double* __restrict__ out_value,
+                                                                   double* __restrict__ out_grad) {
+  // one CTA per restart, one WARP per output (value, each continuous column, each discrete column): lane-strided partial
+  // sums + xor tree, fixed order => deterministic; no block-wide barrier (thirteen sequential block reductions cost 17 us
+  // at experiment sizes, this form ~4 us)
   const int bi = blockIdx.x;
-  const int tid = threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t c0 = size_t(bi) * mc;
-  double s = 0.0;
-  for (int i = tid; i < mc; i += blockDim.x) s += a[c0 + i];
-  s = block_sum(s, red);
-  if (tid == 0) out_value[bi] = s / double(mc);
-  if (!grad_out) return;
   double baseline = 0.0;
-  if (estimator == PRB_EST_REINFORCE_MA) {
+  if (grad_out && estimator == PRB_EST_REINFORCE_MA) {
     const double cnt = ma_state[0];
     if (cnt != 0.0) baseline = ma_state[1] / (1.0 - pow(0.7, cnt));
   }
-  const double go = grad_out[bi];
-  double* g = out_grad + size_t(bi) * sp.d;
-  // continuous columns
-  for (int ci = 0; ci < sp.n_cont; ++ci) {
-    const int c = sp.cont_cols[ci];
-    double t = 0.0;
-    for (int i = tid; i < mc; i += blockDim.x) t += S_all[(c0 + i) * sp.d_k + c];
-    t = block_sum(t, red);
-    if (tid == 0) g[c] = go * (t / double(mc));
-  }
-  // discrete columns: integers first, then the one-hot columns (the order of `discrete_indices`, input.py:574-597)
+  const double go = grad_out ? grad_out[bi] : 0.0;
+  double* g = grad_out ? out_grad + size_t(bi) * sp.d : nullptr;
   const int cat0 = sp.n_cat > 0 ? sp.cat_start[0] : 0;
-  for (int kd = 0; kd < sp.n_disc; ++kd) {
-    const double p = prob[size_t(bi) * sp.n_disc + kd];
+  const int n_tasks = grad_out ? 1 + sp.n_cont + sp.n_disc : 1;
+  for (int task = warp; task < n_tasks; task += REDUCE_THREADS / 32) {
     double t = 0.0;
-    for (int i = tid; i < mc; i += blockDim.x) {
-      const double zi = double(z[(c0 + i) * sp.n_disc + kd]);
-      t += ((a[c0 + i] - baseline) * (zi - p)) / sp.tau;
-    }
-    t = block_sum(t, red);
-    if (tid == 0) {
-      const int c = kd < sp.n_int ? sp.int_cols[kd] : cat0 + (kd - sp.n_int);
-      g[c] = go * (t / double(mc));
+    if (task == 0) {
+      for (int i = lane; i < mc; i += 32) t += a[c0 + i];
+      t = warp_sum(t);
+      if (lane == 0) out_value[bi] = t / double(mc);
+    } else if (task <= sp.n_cont) {
+      const int c = sp.cont_cols[task - 1];
+      for (int i = lane; i < mc; i += 32) t += S_all[(c0 + i) * sp.d_k + c];
+      t = warp_sum(t);
+      if (lane == 0) g[c] = go * (t / double(mc));
+    } else {
+      // discrete columns: integers first, then the one-hot columns (the order of `discrete_indices`, input.py:574-597)
+      const int kd = task - 1 - sp.n_cont;
+      const double p = prob[size_t(bi) * sp.n_disc + kd];
+      for (int i = lane; i < mc; i += 32) {
+        const double zi = double(z[(c0 + i) * sp.n_disc + kd]);
+        t += ((a[c0 + i] - baseline) * (zi - p)) / sp.tau;
+      }
+      t = warp_sum(t);
+      if (lane == 0) {
+        const int c = kd < sp.n_int ? sp.int_cols[kd] : cat0 + (kd - sp.n_int);
+        g[c] = go * (t / double(mc));
+      }
     }
   }
 }
@@ -778,7 +784,8 @@ cudaError_t launch_mc_reduce(const DevSpace& sp, int b, int mc, const double* a,
                              double* out_value, double* out_grad, cudaStream_t st) {
   ProfScope prof_(K_MC_REDUCE, st);
   if (b == 0) return cudaSuccess;
-  mc_reduce_kernel<<<b, 128, 0, st>>>(sp, mc, a, z, prob, S_all, estimator, ma_state, grad_out, out_value, out_grad);
+  mc_reduce_kernel<<<b, REDUCE_THREADS, 0, st>>>(sp, mc, a, z, prob, S_all, estimator, ma_state, grad_out, out_value,
+                                                 out_grad);
   count_launch();
   return cudaGetLastError();
 }
@@ -810,86 +817,90 @@ cudaError_t launch_ma_update(const double* value, int b, double* ma_state, cudaS
 //   value_b = sum_o P_o a_o ;  d/d theta_cont = sum_o P_o S[o, col] ;  d/d theta_disc = sum_o a_o dP_o/d theta
 //   (autograd through get_probs, input.py:410-464, including the Normalize chain-rule factor `range` for integers).
 // =====================================================================================================================
-__global__ void __launch_bounds__(128) analytic_reduce_kernel(const DevSpace sp, const double* __restrict__ theta,
-                                                              int n_opt, const int32_t* __restrict__ options,
-                                                              const double* __restrict__ a,
-                                                              const double* __restrict__ probs,
-                                                              const double* __restrict__ S_all,
-                                                              const double* __restrict__ grad_out,
-                                                              double* __restrict__ out_value,
-                                                              double* __restrict__ out_grad) {
-  __shared__ double red[32];
+__global__ void __launch_bounds__(REDUCE_THREADS) analytic_reduce_kernel(
+    const DevSpace sp, const double* __restrict__ theta, int n_opt, const int32_t* __restrict__ options,
+    const double* __restrict__ a, const double* __restrict__ probs, const double* __restrict__ S_all,
+    const double* __restrict__ grad_out, double* __restrict__ out_value, double* __restrict__ out_grad) {
+  // one CTA per restart; per-restart factor tables first, then one WARP per output (value, continuous columns, integer
+  // columns, one-hot columns): lane-strided sums over the configurations + xor tree, fixed order => deterministic
   __shared__ double p_int[PRB_MAX_DIMS], dp_int[PRB_MAX_DIMS], off_int[PRB_MAX_DIMS];
   __shared__ double sm_cat[PRB_MAX_CAT * PRB_MAX_CARD];
-  const int bi = blockIdx.x, tid = threadIdx.x;
+  const int bi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t c0 = size_t(bi) * n_opt;
   const double* th = theta + size_t(bi) * sp.d;
-  double s = 0.0;
-  for (int o = tid; o < n_opt; o += blockDim.x) s += a[c0 + o] * probs[c0 + o];
-  s = block_sum(s, red);
-  if (tid == 0) out_value[bi] = s;
-  if (!grad_out) return;
-  // per-restart factor tables
-  if (tid < sp.n_int) {
-    const double lo = sp.int_lo[tid], hi = sp.int_hi[tid];
-    const double x_un = unnormalize_int(th[sp.int_cols[tid]], lo, hi);
-    double off;
-    const double p = int_round_prob(x_un, sp.tau, &off);
-    const double sgn = (x_un > 0.0) ? 1.0 : ((x_un < 0.0) ? -1.0 : 0.0);
-    p_int[tid] = p;
-    off_int[tid] = off;
-    dp_int[tid] = p * (1.0 - p) / sp.tau * sgn * (hi - lo);
-  }
-  if (tid < sp.n_cat) {
-    const int st = sp.cat_start[tid], card = sp.cat_card[tid];
-    double mx = -1e300;
-    for (int k = 0; k < card; ++k) mx = fmax(mx, __dsub_rn(th[st + k], 0.5) / sp.tau);
-    double sum = 0.0;
-    for (int k = 0; k < card; ++k) {
-      const double e = exp(__dsub_rn(__dsub_rn(th[st + k], 0.5) / sp.tau, mx));
-      sm_cat[tid * PRB_MAX_CARD + k] = e;
-      sum += e;
+  if (grad_out) {
+    if (tid < sp.n_int) {
+      const double lo = sp.int_lo[tid], hi = sp.int_hi[tid];
+      const double x_un = unnormalize_int(th[sp.int_cols[tid]], lo, hi);
+      double off;
+      const double p = int_round_prob(x_un, sp.tau, &off);
+      const double sgn = (x_un > 0.0) ? 1.0 : ((x_un < 0.0) ? -1.0 : 0.0);
+      p_int[tid] = p;
+      off_int[tid] = off;
+      dp_int[tid] = p * (1.0 - p) / sp.tau * sgn * (hi - lo);
     }
-    const double inv = 1.0 / sum;
-    for (int k = 0; k < card; ++k) sm_cat[tid * PRB_MAX_CARD + k] *= inv;
+    if (tid >= 64 && tid - 64 < sp.n_cat) {
+      const int j = tid - 64;
+      const int st = sp.cat_start[j], card = sp.cat_card[j];
+      double mx = -1e300;
+      for (int k = 0; k < card; ++k) mx = fmax(mx, __dsub_rn(th[st + k], 0.5) / sp.tau);
+      double sum = 0.0;
+      for (int k = 0; k < card; ++k) {
+        const double e = exp(__dsub_rn(__dsub_rn(th[st + k], 0.5) / sp.tau, mx));
+        sm_cat[j * PRB_MAX_CARD + k] = e;
+        sum += e;
+      }
+      const double inv = 1.0 / sum;
+      for (int k = 0; k < card; ++k) sm_cat[j * PRB_MAX_CARD + k] *= inv;
+    }
   }
   __syncthreads();
-  const double go = grad_out[bi];
-  double* g = out_grad + size_t(bi) * sp.d;
-  for (int ci = 0; ci < sp.n_cont; ++ci) {
-    const int c = sp.cont_cols[ci];
-    double t = 0.0;
-    for (int o = tid; o < n_opt; o += blockDim.x) t += probs[c0 + o] * S_all[(c0 + o) * sp.d_k + c];
-    t = block_sum(t, red);
-    if (tid == 0) g[c] = go * t;
-  }
+  const double go = grad_out ? grad_out[bi] : 0.0;
+  double* g = grad_out ? out_grad + size_t(bi) * sp.d : nullptr;
   const int nv = sp.n_int + sp.n_cat;
-  // integer columns
-  for (int k = 0; k < sp.n_int; ++k) {
+  int n_onehot = 0;
+  for (int j = 0; j < sp.n_cat; ++j) n_onehot += sp.cat_card[j];
+  const int n_tasks = grad_out ? 1 + sp.n_cont + sp.n_int + n_onehot : 1;
+  for (int task = warp; task < n_tasks; task += REDUCE_THREADS / 32) {
     double t = 0.0;
-    for (int o = tid; o < n_opt; o += blockDim.x) {
-      const int32_t* op = options + size_t(o) * nv;
-      const double diff = (off_int[k] + 1.0) - double(op[k]);
-      const double df = (diff == 0.0) ? dp_int[k] : ((diff == 1.0) ? -dp_int[k] : 0.0);
-      if (df != 0.0) {
-        double excl = 1.0;
-        for (int k2 = 0; k2 < sp.n_int; ++k2) {
-          if (k2 == k) continue;
-          const double d2 = (off_int[k2] + 1.0) - double(op[k2]);
-          excl *= (d2 == 0.0) ? p_int[k2] : ((d2 == 1.0) ? (1.0 - p_int[k2]) : 0.0);
+    if (task == 0) {
+      for (int o = lane; o < n_opt; o += 32) t += a[c0 + o] * probs[c0 + o];
+      t = warp_sum(t);
+      if (lane == 0) out_value[bi] = t;
+    } else if (task <= sp.n_cont) {
+      const int c = sp.cont_cols[task - 1];
+      for (int o = lane; o < n_opt; o += 32) t += probs[c0 + o] * S_all[(c0 + o) * sp.d_k + c];
+      t = warp_sum(t);
+      if (lane == 0) g[c] = go * t;
+    } else if (task <= sp.n_cont + sp.n_int) {
+      // integer column k: d P / d theta = (+-) dp_k * product of the other factors
+      const int k = task - 1 - sp.n_cont;
+      for (int o = lane; o < n_opt; o += 32) {
+        const int32_t* op = options + size_t(o) * nv;
+        const double diff = (off_int[k] + 1.0) - double(op[k]);
+        const double df = (diff == 0.0) ? dp_int[k] : ((diff == 1.0) ? -dp_int[k] : 0.0);
+        if (df != 0.0) {
+          double excl = 1.0;
+          for (int k2 = 0; k2 < sp.n_int; ++k2) {
+            if (k2 == k) continue;
+            const double d2 = (off_int[k2] + 1.0) - double(op[k2]);
+            excl *= (d2 == 0.0) ? p_int[k2] : ((d2 == 1.0) ? (1.0 - p_int[k2]) : 0.0);
+          }
+          for (int j = 0; j < sp.n_cat; ++j) excl *= sm_cat[j * PRB_MAX_CARD + op[sp.n_int + j]];
+          t += a[c0 + o] * excl * df;
         }
-        for (int j = 0; j < sp.n_cat; ++j) excl *= sm_cat[j * PRB_MAX_CARD + op[sp.n_int + j]];
-        t += a[c0 + o] * excl * df;
       }
-    }
-    t = block_sum(t, red);
-    if (tid == 0) g[sp.int_cols[k]] = go * t;
-  }
-  // one-hot columns: d softmax_c / d theta_m = softmax_c (delta_cm - softmax_m) / tau
-  for (int j = 0; j < sp.n_cat; ++j) {
-    for (int m = 0; m < sp.cat_card[j]; ++m) {
-      double t = 0.0;
-      for (int o = tid; o < n_opt; o += blockDim.x) {
+      t = warp_sum(t);
+      if (lane == 0) g[sp.int_cols[k]] = go * t;
+    } else {
+      // one-hot column m of categorical j: d softmax_c / d theta_m = softmax_c (delta_cm - softmax_m) / tau
+      int rem = task - 1 - sp.n_cont - sp.n_int, j = 0;
+      while (rem >= sp.cat_card[j]) {
+        rem -= sp.cat_card[j];
+        ++j;
+      }
+      const int mcol = rem;
+      for (int o = lane; o < n_opt; o += 32) {
         const int32_t* op = options + size_t(o) * nv;
         const int c = op[sp.n_int + j];
         double excl = 1.0;
@@ -900,11 +911,11 @@ __global__ void __launch_bounds__(128) analytic_reduce_kernel(const DevSpace sp,
         for (int j2 = 0; j2 < sp.n_cat; ++j2)
           if (j2 != j) excl *= sm_cat[j2 * PRB_MAX_CARD + op[sp.n_int + j2]];
         const double smc = sm_cat[j * PRB_MAX_CARD + c];
-        const double smm = sm_cat[j * PRB_MAX_CARD + m];
-        t += a[c0 + o] * excl * smc * ((c == m ? 1.0 : 0.0) - smm) / sp.tau;
+        const double smm = sm_cat[j * PRB_MAX_CARD + mcol];
+        t += a[c0 + o] * excl * smc * ((c == mcol ? 1.0 : 0.0) - smm) / sp.tau;
       }
-      t = block_sum(t, red);
-      if (tid == 0) g[sp.cat_start[j] + m] = go * t;
+      t = warp_sum(t);
+      if (lane == 0) g[sp.cat_start[j] + mcol] = go * t;
     }
   }
 }
@@ -914,7 +925,8 @@ cudaError_t launch_analytic_reduce(const DevSpace& sp, const double* theta, int 
                                    double* out_value, double* out_grad, cudaStream_t st) {
   ProfScope prof_(K_ANALYTIC, st);
   if (b == 0) return cudaSuccess;
-  analytic_reduce_kernel<<<b, 128, 0, st>>>(sp, theta, n_opt, options, a, probs, S_all, grad_out, out_value, out_grad);
+  analytic_reduce_kernel<<<b, REDUCE_THREADS, 0, st>>>(sp, theta, n_opt, options, a, probs, S_all, grad_out, out_value,
+                                                       out_grad);
   count_launch();
   return cudaGetLastError();
 }

@@ -42,10 +42,10 @@ cudaError_t launch_mc_reduce_dedup(const DevSpace& sp, const BitMap& bm, int b, 
 cudaError_t launch_dedup_scatter(const double* a, const int* ustart, const int* inv, int b, int mc, double* out,
                                  cudaStream_t st);
 cudaError_t launch_grad_contract(const Model& m, uint32_t diffmask, const double* xk, int ncols, int ncols_pad,
-                                 const double* W, const double* dmu, const double* dvar, double* S_part,
+                                 const double* W, const double* dmu, const double* dvar, double* S_part, int jrows,
                                  cudaStream_t st);
-cudaError_t launch_sum_splits(const Model& m, const double* S_part, const DimMap* dm, int ncols, int ncols_pad,
-                              double* S_all, const int* ncols_dev, int64_t col0, cudaStream_t st);
+cudaError_t launch_sum_splits(const Model& m, const double* S_part, int jblocks, const DimMap* dm, int ncols,
+                              int ncols_pad, double* S_all, const int* ncols_dev, int64_t col0, cudaStream_t st);
 cudaError_t launch_mc_reduce(const DevSpace& sp, int b, int mc, const double* a, const uint8_t* z, const double* prob,
                              const double* S_all, int estimator, const double* ma_state, const double* grad_out,
                              double* out_value, double* out_grad, cudaStream_t st);

@@ -97,12 +97,51 @@ class FixedFeatureAcquisitionFunction(torch.nn.Module):
 
 
 def _is_fusable(acquisition_function, options, callback, optimizer, fixed_features) -> bool:
-    from .probabilistic_reparameterization import MCProbabilisticReparameterization
+    from .probabilistic_reparameterization import (AnalyticProbabilisticReparameterization,
+                                                   MCProbabilisticReparameterization)
 
-    return (isinstance(acquisition_function, MCProbabilisticReparameterization) and callback is None
+    return (isinstance(acquisition_function, (MCProbabilisticReparameterization,
+                                              AnalyticProbabilisticReparameterization)) and callback is None
             and optimizer is torch.optim.Adam and not options.get("decay", False) and not fixed_features
             and options.get("fused", True)
             and (options.get("rel_tol") is None or options.get("rel_tol") == float("-inf")))
+
+
+def _fused_analytic_adam(ics: Tensor, acqf, lower, upper, lr: float, maxiter: int) -> Tuple[Tensor, Tensor]:
+    """``prb_analytic_adam``: the whole multi-start Adam on the analytic PR objective in one call."""
+    from .acquisition import acq_desc_of
+    from .models import gp_state_from_model
+
+    capi.require_cuda(ics, "initial_conditions")
+    dev = ics.device
+    b, q, d = ics.shape
+    if q != 1:
+        raise NotImplementedError("q > 1 is not supported by the PR path")
+    state = gp_state_from_model(acqf.acq_function.model)
+    codes = acqf.input_transform["round"].option_codes
+    if codes.device != dev:
+        codes = codes.to(dev)
+    n_opt = codes.shape[0]
+    theta = ics.detach().to(torch.float64).reshape(b, d).contiguous().clone()
+    lo = torch.as_tensor(lower, dtype=torch.float64, device=dev).expand(d).contiguous()
+    hi = torch.as_tensor(upper, dtype=torch.float64, device=dev).expand(d).contiguous()
+    adam = torch.zeros(2 * b * d, dtype=torch.float64, device=dev)
+    value = torch.empty(b, dtype=torch.float64, device=dev)
+    ws = state.workspace(b * n_opt, d, b)
+    sp, aq = acqf._space(), acq_desc_of(acqf.acq_function)
+    with torch.cuda.device(dev):
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            capi.check(state.lib.prb_analytic_adam(state.handle, C.byref(sp), C.byref(aq), theta.data_ptr(), b,
+                                                   codes.data_ptr(), n_opt, lo.data_ptr(), hi.data_ptr(), float(lr),
+                                                   int(maxiter), 0, adam.data_ptr(), value.data_ptr(), ws.data_ptr(),
+                                                   ws.numel(), int(state.chunk_cols), side.cuda_stream),
+                       "prb_analytic_adam")
+        torch.cuda.current_stream(dev).wait_stream(side)
+        for t in (theta, lo, hi, adam, value, ws, codes):
+            t.record_stream(side)
+    return theta.reshape(b, 1, d).to(ics.dtype), value
 
 
 def _fused_mc_adam(ics: Tensor, acqf, lower, upper, lr: float, maxiter: int) -> Tuple[Tensor, Tensor]:
@@ -181,7 +220,10 @@ def gen_candidates_torch(
         options["rel_tol"] = float("-inf")  # the reference writes this into the caller's dict too (gen.py:311-313)
     maxiter = int(options.get("maxiter", 10000))
     if _is_fusable(acquisition_function, options, callback, optimizer, fixed_features):
-        return _fused_mc_adam(initial_conditions, acquisition_function, lower_bounds, upper_bounds, lr, maxiter)
+        from .probabilistic_reparameterization import AnalyticProbabilisticReparameterization
+        fused = (_fused_analytic_adam if isinstance(acquisition_function, AnalyticProbabilisticReparameterization)
+                 else _fused_mc_adam)
+        return fused(initial_conditions, acquisition_function, lower_bounds, upper_bounds, lr, maxiter)
 
     clamp = lambda t: columnwise_clamp(t, lower_bounds, upper_bounds)  # noqa: E731
     theta = clamp(initial_conditions).detach().clone().requires_grad_(True)

@@ -239,6 +239,14 @@ int prb_mc_adam(prb_model* model, const prb_space_desc* space, const prb_acq_des
                 int32_t maxiter, int32_t step0, double* adam_state, double* out_value, void* workspace,
                 size_t workspace_bytes, int32_t chunk_cols, void* stream);
 
+/* Multi-start Adam on the ANALYTIC PR objective, on device (same loop as prb_mc_adam around prb_analytic_value_grad).
+ * Replaces: gen_candidates_torch (gen.py:264-343) for an AnalyticProbabilisticReparameterization, which every pr__* label
+ * optimises with Adam too (run_one_replication.py:176-183).                                                          */
+int prb_analytic_adam(prb_model* model, const prb_space_desc* space, const prb_acq_desc* acq, double* theta, int32_t b,
+                      const int32_t* options, int32_t n_options, const double* lower, const double* upper, double lr,
+                      int32_t maxiter, int32_t step0, double* adam_state, double* out_value, void* workspace,
+                      size_t workspace_bytes, int32_t chunk_cols, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
