@@ -271,9 +271,19 @@ int run_engine(const Model& m, const DevAcq& aq, const Plan& pl, void* ws, const
     const int ncols_pad = round_up(ncols, 128);
     const double* xkc = xk + size_t(c0) * m.d_k;
     CUDA_TRY(launch_kstar_panel(m, xkc, ncols, ncols_pad, panelA, st));
-    CUDA_TRY(launch_tma_lower(m, panelA, pl.C, ncols_pad, need_grad ? panelV : nullptr, norm, mu, st));
-    CUDA_TRY(launch_acq_epilogue(m, aq, norm, ncols_pad, mu, ncols, a + c0, dmu + c0, dvar + c0,
-                                 out_mean ? out_mean + c0 : nullptr, out_var ? out_var + c0 : nullptr, nullptr, 0, st));
+    FusedAcq fa;  // single row tile: the acquisition epilogue runs inside the lower product
+    fa.aq = aq;
+    fa.a = a + c0;
+    fa.dmu = dmu + c0;
+    fa.dvar = dvar + c0;
+    fa.ncols = ncols;
+    const bool fuse = m.Mp1 == GEMM_BM && out_mean == nullptr && out_var == nullptr;
+    CUDA_TRY(launch_tma_lower(m, panelA, pl.C, ncols_pad, need_grad ? panelV : nullptr, norm, mu, fuse ? &fa : nullptr,
+                              st));
+    if (!fuse)
+      CUDA_TRY(launch_acq_epilogue(m, aq, norm, ncols_pad, mu, ncols, a + c0, dmu + c0, dvar + c0,
+                                   out_mean ? out_mean + c0 : nullptr, out_var ? out_var + c0 : nullptr, nullptr, 0,
+                                   st));
     if (need_grad) {
       CUDA_TRY(launch_tma_upper(m, panelV, pl.C, ncols_pad, panelA, st));
       CUDA_TRY(launch_grad_contract(m, diffmask, xkc, ncols, ncols_pad, panelA, dmu + c0, dvar + c0, S_part,
@@ -412,9 +422,58 @@ int sep_step(const Model& m, const DevSpace& sp, const DevAcq& aq, const Plan& p
   if (m.Mp1 > GEMM_BM)
     CUDA_TRY(launch_acq_epilogue(m, aq, norm, ncols_pad, mu, ncols, a, dmu, dvar, nullptr, nullptr, nullptr, 0, st));
   if (need_grad) CUDA_TRY(launch_tma_upper_grad(m, panelV, pl.C, sa, ncols, ncols_pad, dmu, dvar, S_part, st));
-  CUDA_TRY(launch_sep_step_finish(sp, dm, b, mc, a, z, prob, S_part, m.Mp2 / GEMM_BM, ncols_pad, estimator, ma_state,
+  CUDA_TRY(launch_sep_step_finish(sp, dm, dm.n, 0, b, mc, a, z, prob, S_part, m.Mp2 / GEMM_BM, ncols_pad, estimator,
+                                  ma_state,
                                   update_ma, grad_out, out_value, out_grad, need_grad ? 1 : 0, adam_theta, adam_m, adam_v,
                                   lr, step_ptr, at<unsigned int>(ws, pl.off_done), st));
+  return PRB_OK;
+}
+
+// The same fusion for kernel structures that do not separate (ordinals inside the ARD Matern, categorical kernels), on a
+// single column panel: [clamp +] sampler -> k* panel -> lower product (+ acquisition epilogue when there is one row tile)
+// -> upper product -> gradient contraction -> reductions [+ Adam] + EMA: six launches instead of twelve.
+int generic_step(const Model& m, const DevSpace& sp, const DevAcq& aq, const Plan& pl, void* ws, const double* theta_in,
+                 const double* lower, const double* upper, double* Xc, int b, int mc, const double* u_int,
+                 const double* u_cat, uint64_t seed, uint64_t offset, int estimator, double* ma_state, int update_ma,
+                 bool need_grad, const double* grad_out, double* out_value, double* out_grad, double* adam_theta,
+                 double* adam_m, double* adam_v, double lr, int* step_ptr, cudaStream_t st) {
+  const int ncols = b * mc;
+  const int ncols_pad = round_up(ncols, 128);
+  double* panelA = at<double>(ws, pl.off_panelA);
+  double* panelV = at<double>(ws, pl.off_panelV);
+  double* norm = at<double>(ws, pl.off_norm);
+  double* mu = at<double>(ws, pl.off_mu);
+  double* S_part = at<double>(ws, pl.off_S_part);
+  double* xk = at<double>(ws, pl.off_xk);
+  uint8_t* z = at<uint8_t>(ws, pl.off_z);
+  double* prob = at<double>(ws, pl.off_prob);
+  double* a = at<double>(ws, pl.off_a);
+  double* dmu = at<double>(ws, pl.off_dmu);
+  double* dvar = at<double>(ws, pl.off_dvar);
+  const bool need_path = need_grad && sp.n_cont > 0;
+  CUDA_TRY(launch_pr_sample(sp, theta_in, b, mc, u_int, u_cat, seed, offset, xk, nullptr, need_grad ? z : nullptr,
+                            need_grad ? prob : nullptr, nullptr, nullptr, st, lower, upper, Xc));
+  CUDA_TRY(launch_kstar_panel(m, xk, ncols, ncols_pad, panelA, st));
+  FusedAcq fa;
+  fa.aq = aq;
+  fa.a = a;
+  fa.dmu = dmu;
+  fa.dvar = dvar;
+  fa.ncols = ncols;
+  const bool fuse = m.Mp1 == GEMM_BM;
+  CUDA_TRY(launch_tma_lower(m, panelA, pl.C, ncols_pad, need_path ? panelV : nullptr, norm, mu, fuse ? &fa : nullptr, st));
+  if (!fuse)
+    CUDA_TRY(launch_acq_epilogue(m, aq, norm, ncols_pad, mu, ncols, a, dmu, dvar, nullptr, nullptr, nullptr, 0, st));
+  if (need_path) {
+    CUDA_TRY(launch_tma_upper(m, panelV, pl.C, ncols_pad, panelA, st));
+    CUDA_TRY(launch_grad_contract(m, cont_mask(sp), xk, ncols, ncols_pad, panelA, dmu, dvar, S_part, pl.grad_jrows, st));
+  }
+  DimMap dm;
+  dm.n = need_path ? sp.n_cont : 0;
+  for (int i = 0; i < sp.n_cont; ++i) dm.dims[i] = sp.cont_cols[i];
+  CUDA_TRY(launch_sep_step_finish(sp, dm, m.d_k, 1, b, mc, a, z, prob, S_part, m.Mp2 / pl.grad_jrows, ncols_pad, estimator,
+                                  ma_state, update_ma, grad_out, out_value, out_grad, need_grad ? 1 : 0, adam_theta,
+                                  adam_m, adam_v, lr, step_ptr, at<unsigned int>(ws, pl.off_done), st));
   return PRB_OK;
 }
 
@@ -967,7 +1026,14 @@ int prb_mc_adam(prb_model* model, const prb_space_desc* space, const prb_acq_des
     return PRB_OK;
   }
 
+  // kernel structures that do not separate: the six-launch fused step on a single column panel
+  const bool generic_fused = !fused_step && int64_t(b) * mc <= pl.C && !(pl.off_kc != 0 && sep_space_ok(m, sp, &bm, &dm)) &&
+                             getenv("PRB_NO_FUSED_STEP") == nullptr;
+
   auto one_iter = [&]() -> int {
+    if (generic_fused)
+      return generic_step(m, sp, aq, pl, workspace, theta, lower, upper, Xc, b, mc, u_int, u_cat, seed, offset, estimator,
+                          ma_state, update_ma, true, nullptr, val, grad, theta, adam_state, adam_state + total, lr, step, st);
     if (small_step) {
       CUDA_TRY(launch_small_step(m, sp, aq, bm, dm, theta, lower, upper, Xc, b, mc, u_int, u_cat, seed, offset, estimator,
                                  ma_state, update_ma, true, nullptr, val, grad, theta, adam_state, adam_state + total, lr,
@@ -1021,6 +1087,10 @@ int prb_mc_adam(prb_model* model, const prb_space_desc* space, const prb_acq_des
     }
   }
   // final clamp + value-only evaluation (gen.py:338-341); this call also advances the EMA state like any forward
+  if (generic_fused)
+    return generic_step(m, sp, aq, pl, workspace, theta, lower, upper, theta, b, mc, u_int, u_cat, seed, offset, estimator,
+                        ma_state, update_ma, false, nullptr, out_value, nullptr, nullptr, nullptr, nullptr, lr, nullptr,
+                        st);
   if (small_step) {
     CUDA_TRY(launch_small_step(m, sp, aq, bm, dm, theta, lower, upper, theta, b, mc, u_int, u_cat, seed, offset, estimator,
                                ma_state, update_ma, false, nullptr, out_value, nullptr, nullptr, nullptr, nullptr, lr,

@@ -611,7 +611,7 @@ static int pick_bn_generic(const Model& m, int ncols_pad, bool upper) {
 }
 
 cudaError_t launch_tma_lower(const Model& m, const double* panelK, int panel_rows, int ncols_pad, double* VT,
-                             double* norm_part, double* mu_dot, cudaStream_t st) {
+                             double* norm_part, double* mu_dot, const FusedAcq* fa, cudaStream_t st) {
   ProfScope prof_(K_TRGEMM_LOWER, st);
   TmaGemmParams p;
   const int bn = pick_bn_generic(m, ncols_pad, false);
@@ -620,6 +620,16 @@ cudaError_t launch_tma_lower(const Model& m, const double* panelK, int panel_row
   p.ldc = m.Mp1;
   p.norm_part = norm_part;
   p.mu_dot = mu_dot;
+  if (fa != nullptr && p.mtiles == 1) {
+    p.fuse_acq = 1;
+    p.aq = fa->aq;
+    p.mean_const = m.mean_const;
+    p.kss = m.kss;
+    p.acq_a = fa->a;
+    p.acq_dmu = fa->dmu;
+    p.acq_dvar = fa->dvar;
+    p.acq_ncols = fa->ncols;
+  }
   TensorMap mapK;  // the k* panel [panel_rows, Kp], box = 4 k values x bn columns
   cudaError_t e = make_operand_map(&mapK, panelK, panel_rows, m.Kp, m.Kp, bn);
   if (e != cudaSuccess) return e;

@@ -191,7 +191,7 @@ cudaError_t make_operand_map(TensorMap* out, const double* base, int rows, int k
 cudaError_t launch_tma_lower_gen(const Model& m, const SepArgs& sa, int ncols_pad, double* VT, double* norm_part,
                                  double* mu_dot, const FusedAcq* fa, cudaStream_t st);
 cudaError_t launch_tma_lower(const Model& m, const double* panelK, int panel_rows, int ncols_pad, double* VT,
-                             double* norm_part, double* mu_dot, cudaStream_t st);
+                             double* norm_part, double* mu_dot, const FusedAcq* fa, cudaStream_t st);
 cudaError_t launch_tma_upper(const Model& m, const double* panelV, int panel_rows, int ncols_pad, double* W,
                              cudaStream_t st);
 cudaError_t launch_tma_upper_grad(const Model& m, const double* panelV, int panel_rows, const SepArgs& sa, int ncols,

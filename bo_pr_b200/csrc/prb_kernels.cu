@@ -38,8 +38,10 @@ __global__ void __launch_bounds__(SAMPLE_ROWS) pr_sample_kernel(
     const DevSpace sp, const double* __restrict__ theta, int b, int mc, const double* __restrict__ u_int,
     const double* __restrict__ u_cat, uint64_t seed, uint64_t offset, double* __restrict__ xk,
     double* __restrict__ tilde, uint8_t* __restrict__ zout, double* __restrict__ prob, const BitMap bm,
-    uint32_t* __restrict__ zbits) {
+    uint32_t* __restrict__ zbits, const double* __restrict__ lower, const double* __restrict__ upper,
+    double* __restrict__ Xc) {
   extern __shared__ __align__(16) unsigned char smraw[];
+  __shared__ double th_s[PRB_MAX_DIMS];  // the restart's theta row, clamped to [lower, upper] if given (gen.py:304-305, 323)
   double* ps = reinterpret_cast<double*>(smraw);          // [n_disc]
   double* offs = ps + sp.n_disc;                          // [n_int]
   double* st_t = offs + sp.n_int;                         // [128][d]    if tilde
@@ -49,7 +51,14 @@ __global__ void __launch_bounds__(SAMPLE_ROWS) pr_sample_kernel(
   const int i0 = blockIdx.x * SAMPLE_ROWS;
   const int i = i0 + tid;
   const int nrows = min(SAMPLE_ROWS, mc - i0);
-  const double* th = theta + size_t(bi) * sp.d;
+  if (tid < sp.d) {
+    double v = theta[size_t(bi) * sp.d + tid];
+    if (lower) v = fmin(fmax(v, lower[tid]), upper[tid]);
+    th_s[tid] = v;
+    if (Xc && blockIdx.x == 0) Xc[size_t(bi) * sp.d + tid] = v;
+  }
+  __syncthreads();
+  const double* th = th_s;
   pr_restart_probs(sp, th, tid, SAMPLE_ROWS, ps, offs);
   __syncthreads();
   if (i < mc) {
@@ -72,7 +81,8 @@ __global__ void __launch_bounds__(SAMPLE_ROWS) pr_sample_kernel(
 
 cudaError_t launch_pr_sample(const DevSpace& sp, const double* theta, int b, int mc, const double* u_int,
                              const double* u_cat, uint64_t seed, uint64_t offset, double* xk, double* tilde,
-                             uint8_t* z, double* prob, const BitMap* bm, uint32_t* zbits, cudaStream_t st) {
+                             uint8_t* z, double* prob, const BitMap* bm, uint32_t* zbits, cudaStream_t st,
+                             const double* lower, const double* upper, double* Xc) {
   ProfScope prof_(K_SAMPLE, st);
   if (int64_t(b) * mc == 0) return cudaSuccess;
   BitMap none;
@@ -86,7 +96,7 @@ cudaError_t launch_pr_sample(const DevSpace& sp, const double* theta, int b, int
   }
   dim3 grid((mc + SAMPLE_ROWS - 1) / SAMPLE_ROWS, b);
   pr_sample_kernel<<<grid, SAMPLE_ROWS, smem, st>>>(sp, theta, b, mc, u_int, u_cat, seed, offset, xk, tilde, z, prob,
-                                                   bm ? *bm : none, bm ? zbits : nullptr);
+                                                   bm ? *bm : none, bm ? zbits : nullptr, lower, upper, Xc);
   count_launch();
   return cudaGetLastError();
 }
@@ -1007,8 +1017,9 @@ constexpr int FINISH_THREADS = 512;
 // barrier inside the reductions -- at experiment sizes the step is latency bound and thirteen sequential block reductions
 // cost 17 us; this form costs ~3 us.  Fixed lane-strided order + xor-tree => deterministic.
 __global__ void __launch_bounds__(FINISH_THREADS) sep_step_finish_kernel(
-    const DevSpace sp, const DimMap dm, int mc, const double* __restrict__ a, const uint8_t* __restrict__ z,
-    const double* __restrict__ prob, const double* __restrict__ S_part, int mtiles, int ncols_pad, int estimator,
+    const DevSpace sp, const DimMap dm, int slots, int slot_is_dim, int mc, const double* __restrict__ a,
+    const uint8_t* __restrict__ z, const double* __restrict__ prob, const double* __restrict__ S_part, int mtiles,
+    int ncols_pad, int estimator,
     double* __restrict__ ma_state, int update_ma, const double* __restrict__ grad_out, double* __restrict__ out_value,
     double* __restrict__ out_grad, int need_grad, double* __restrict__ theta, double* __restrict__ adam_m,
     double* __restrict__ adam_v, double lr, int* __restrict__ step_ptr, unsigned int* __restrict__ done, int nb) {
@@ -1027,7 +1038,10 @@ __global__ void __launch_bounds__(FINISH_THREADS) sep_step_finish_kernel(
   }
   const double t_step = step_ptr ? double(*step_ptr + 1) : 1.0;
   const double go = (need_grad && grad_out) ? grad_out[bi] : 1.0;
-  const int n_tasks = need_grad ? 1 + dm.n + sp.n_int : 1;
+  // S_part is [mtiles][slots][ncols_pad]: the separable path stores one slot per continuous dim (slot = index in dm), the
+  // generic gradient contraction one slot per kernel-input column (slot = the column itself)
+  const int cat0 = sp.n_cat > 0 ? sp.cat_start[0] : 0;
+  const int n_tasks = need_grad ? 1 + dm.n + sp.n_disc : 1;
   for (int task = warp; task < n_tasks; task += FINISH_THREADS / 32) {
     double t = 0.0;
     if (task == 0) {
@@ -1036,14 +1050,16 @@ __global__ void __launch_bounds__(FINISH_THREADS) sep_step_finish_kernel(
       if (lane == 0) out_value[bi] = t / double(mc);
     } else if (task <= dm.n) {
       const int ci = task - 1;
+      const int slot = slot_is_dim ? dm.dims[ci] : ci;
       for (int i = lane; i < mc; i += 32) {
         double v = 0.0;
-        for (int mt = 0; mt < mtiles; ++mt) v += S_part[(size_t(mt) * dm.n + ci) * ncols_pad + c0 + i];
+        for (int mt = 0; mt < mtiles; ++mt) v += S_part[(size_t(mt) * slots + slot) * ncols_pad + c0 + i];
         t += v;
       }
       t = warp_sum(t);
       if (lane == 0) g_s[dm.dims[ci]] = go * (t / double(mc));
     } else {
+      // discrete columns: integers first, then the one-hot columns (the order of `discrete_indices`, input.py:574-597)
       const int kd = task - 1 - dm.n;
       const double p = prob[size_t(bi) * sp.n_disc + kd];
       for (int i = lane; i < mc; i += 32) {
@@ -1051,7 +1067,7 @@ __global__ void __launch_bounds__(FINISH_THREADS) sep_step_finish_kernel(
         t += ((a[c0 + i] - baseline) * (zi - p)) / sp.tau;
       }
       t = warp_sum(t);
-      if (lane == 0) g_s[sp.int_cols[kd]] = go * (t / double(mc));
+      if (lane == 0) g_s[kd < sp.n_int ? sp.int_cols[kd] : cat0 + (kd - sp.n_int)] = go * (t / double(mc));
     }
   }
   __syncthreads();
@@ -1095,14 +1111,16 @@ __global__ void __launch_bounds__(FINISH_THREADS) sep_step_finish_kernel(
   }
 }
 
-cudaError_t launch_sep_step_finish(const DevSpace& sp, const DimMap& dm, int nb, int mc, const double* a, const uint8_t* z,
+cudaError_t launch_sep_step_finish(const DevSpace& sp, const DimMap& dm, int slots, int slot_is_dim, int nb, int mc,
+                                   const double* a, const uint8_t* z,
                                    const double* prob, const double* S_part, int mtiles, int ncols_pad, int estimator,
                                    double* ma_state, int update_ma, const double* grad_out, double* out_value,
                                    double* out_grad, int need_grad, double* theta, double* adam_m, double* adam_v,
                                    double lr, int* step_ptr, unsigned int* done, cudaStream_t st) {
   ProfScope prof_(K_MC_REDUCE, st);
   if (nb == 0) return cudaSuccess;
-  cudaError_t e = launch_kernel(sep_step_finish_kernel, dim3(nb), dim3(FINISH_THREADS), 0, st, sp, dm, mc, a, z, prob, S_part,
+  cudaError_t e = launch_kernel(sep_step_finish_kernel, dim3(nb), dim3(FINISH_THREADS), 0, st, sp, dm, slots, slot_is_dim,
+                                mc, a, z, prob, S_part,
                                 mtiles, ncols_pad, estimator, ma_state, update_ma, grad_out, out_value, out_grad, need_grad,
                                 theta, adam_m, adam_v, lr, step_ptr, done, nb);
   count_launch();

@@ -8,7 +8,8 @@ namespace prb {
 cudaError_t launch_philox_fill(uint64_t seed, uint64_t offset, int mc, int n_cols, double* out, cudaStream_t st);
 cudaError_t launch_pr_sample(const DevSpace& sp, const double* theta, int b, int mc, const double* u_int,
                              const double* u_cat, uint64_t seed, uint64_t offset, double* xk, double* tilde,
-                             uint8_t* z, double* prob, const BitMap* bm, uint32_t* zbits, cudaStream_t st);
+                             uint8_t* z, double* prob, const BitMap* bm, uint32_t* zbits, cudaStream_t st,
+                             const double* lower = nullptr, const double* upper = nullptr, double* Xc = nullptr);
 cudaError_t launch_sep_model_prep(const Model& m, int n_pad, int* bad_flag, cudaStream_t st);
 cudaError_t launch_sep_restart_prep(const Model& m, const double* theta, int nb, int d_theta, double* kc, double* Dc,
                                     cudaStream_t st);
@@ -16,7 +17,8 @@ cudaError_t launch_sep_step_prep(const Model& m, const DevSpace& sp, const BitMa
                                  const double* lower, const double* upper, double* Xc, int nb, int mc,
                                  const double* u_int, const double* u_cat, uint64_t seed, uint64_t offset, double* kc,
                                  double* Dc, uint8_t* z, double* prob, uint32_t* zbits, cudaStream_t st);
-cudaError_t launch_sep_step_finish(const DevSpace& sp, const DimMap& dm, int nb, int mc, const double* a, const uint8_t* z,
+cudaError_t launch_sep_step_finish(const DevSpace& sp, const DimMap& dm, int slots, int slot_is_dim, int nb, int mc,
+                                   const double* a, const uint8_t* z,
                                    const double* prob, const double* S_part, int mtiles, int ncols_pad, int estimator,
                                    double* ma_state, int update_ma, const double* grad_out, double* out_value,
                                    double* out_grad, int need_grad, double* theta, double* adam_m, double* adam_v,
