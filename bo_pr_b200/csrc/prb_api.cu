@@ -220,9 +220,9 @@ Plan make_plan(const Model& m, int64_t n_points, int n_restarts, int d_theta, in
   p.off_panelV = take(size_t(C) * m.Mp1 * dbl);
   p.off_norm = take(size_t(m.Mp1 / GEMM_BM) * C * dbl);
   p.off_mu = take(size_t(C) * dbl);
-  // small panels: 16 training rows per CTA of the generic gradient contraction instead of 128 (8x the CTAs; the kernel is
-  // a serial loop over its rows, 90 us at n = 119 with one CTA per 128 columns)
-  p.grad_jrows = ((m.Mp2 / GEMM_BM) * (C / 128) < 120) ? 16 : GRAD_JSPLIT_ROWS;
+  // small panels: 4 training rows per CTA of the generic gradient contraction instead of 128 (32x the CTAs; the kernel is
+  // a serial loop over its rows: 90 us at n = 119 with 128 rows per CTA, 36 us with 16)
+  p.grad_jrows = ((m.Mp2 / GEMM_BM) * (C / 128) < 120) ? 4 : GRAD_JSPLIT_ROWS;
   p.off_S_part = take(size_t(m.Mp2 / p.grad_jrows) * m.d_k * C * dbl);
   p.off_Xc = take(size_t(p.B_pad) * d_theta * dbl);
   p.off_grad = take(size_t(p.B_pad) * d_theta * dbl);

@@ -238,8 +238,8 @@ __global__ void __launch_bounds__(KS_ROWS) kstar_panel_kernel(const DevSpec spec
 cudaError_t launch_kstar_panel(const Model& m, const double* xk, int ncols, int ncols_pad, double* KstarT,
                                cudaStream_t st) {
   ProfScope prof_(K_KSTAR, st);
-  // few columns: 8 per CTA instead of 32, so that a small panel still spreads over the SMs
-  const int ks_cols = (m.Kp + KS_ROWS - 1) / KS_ROWS * (ncols_pad / KS_COLS) < 148 ? 8 : KS_COLS;
+  // few columns: 4 per CTA instead of 32, so that a small panel still spreads over the SMs
+  const int ks_cols = (m.Kp + KS_ROWS - 1) / KS_ROWS * (ncols_pad / KS_COLS) < 148 ? 4 : KS_COLS;
   dim3 grid((m.Kp + KS_ROWS - 1) / KS_ROWS, ncols_pad / ks_cols);
   const size_t smem = size_t(m.d_k) * (KS_ROWS + KS_COLS) * sizeof(double);
   kstar_panel_kernel<<<grid, KS_ROWS, smem, st>>>(m.spec, m.Xtr, m.n, m.Kp, xk, ncols, ncols_pad, KstarT, ks_cols);
@@ -1039,28 +1039,34 @@ __global__ void __launch_bounds__(FINISH_THREADS) sep_step_finish_kernel(
   const double t_step = step_ptr ? double(*step_ptr + 1) : 1.0;
   const double go = (need_grad && grad_out) ? grad_out[bi] : 1.0;
   // S_part is [mtiles][slots][ncols_pad]: the separable path stores one slot per continuous dim (slot = index in dm), the
-  // generic gradient contraction one slot per kernel-input column (slot = the column itself)
+  // generic gradient contraction one slot per kernel-input column (slot = the column itself).  With many row blocks (the
+  // small-panel generic contraction uses 4-row blocks) each continuous column is split over NSPLIT warps by row-block range.
+  __shared__ double csum[PRB_MAX_DIMS][4];
+  const int nsplit = mtiles >= 8 ? 4 : 1;
+  const int mt_per = (mtiles + nsplit - 1) / nsplit;
   const int cat0 = sp.n_cat > 0 ? sp.cat_start[0] : 0;
-  const int n_tasks = need_grad ? 1 + dm.n + sp.n_disc : 1;
+  const int n_cont_tasks = dm.n * nsplit;
+  const int n_tasks = need_grad ? 1 + n_cont_tasks + sp.n_disc : 1;
   for (int task = warp; task < n_tasks; task += FINISH_THREADS / 32) {
     double t = 0.0;
     if (task == 0) {
       for (int i = lane; i < mc; i += 32) t += a[c0 + i];
       t = warp_sum(t);
       if (lane == 0) out_value[bi] = t / double(mc);
-    } else if (task <= dm.n) {
-      const int ci = task - 1;
+    } else if (task <= n_cont_tasks) {
+      const int ci = (task - 1) / nsplit, part = (task - 1) % nsplit;
       const int slot = slot_is_dim ? dm.dims[ci] : ci;
+      const int mt0 = part * mt_per, mt1 = min(mtiles, mt0 + mt_per);
       for (int i = lane; i < mc; i += 32) {
         double v = 0.0;
-        for (int mt = 0; mt < mtiles; ++mt) v += S_part[(size_t(mt) * slots + slot) * ncols_pad + c0 + i];
+        for (int mt = mt0; mt < mt1; ++mt) v += S_part[(size_t(mt) * slots + slot) * ncols_pad + c0 + i];
         t += v;
       }
       t = warp_sum(t);
-      if (lane == 0) g_s[dm.dims[ci]] = go * (t / double(mc));
+      if (lane == 0) csum[ci][part] = t;
     } else {
       // discrete columns: integers first, then the one-hot columns (the order of `discrete_indices`, input.py:574-597)
-      const int kd = task - 1 - dm.n;
+      const int kd = task - 1 - n_cont_tasks;
       const double p = prob[size_t(bi) * sp.n_disc + kd];
       for (int i = lane; i < mc; i += 32) {
         const double zi = double(z[(c0 + i) * sp.n_disc + kd]);
@@ -1069,6 +1075,12 @@ __global__ void __launch_bounds__(FINISH_THREADS) sep_step_finish_kernel(
       t = warp_sum(t);
       if (lane == 0) g_s[kd < sp.n_int ? sp.int_cols[kd] : cat0 + (kd - sp.n_int)] = go * (t / double(mc));
     }
+  }
+  __syncthreads();
+  if (need_grad && tid < dm.n) {
+    double t = csum[tid][0];
+    for (int part = 1; part < nsplit; ++part) t += csum[tid][part];
+    g_s[dm.dims[tid]] = go * (t / double(mc));
   }
   __syncthreads();
   if (need_grad && tid < sp.d) {
