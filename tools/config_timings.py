@@ -46,11 +46,12 @@ CONFIGS = {
 def bounds_for(c):
     d = c["dim"]
     lo, hi = torch.zeros(d, dtype=torch.float64), torch.ones(d, dtype=torch.float64)
-    if c.get("trust_region"):  # run_one_replication.py:410-440: x_center +- 0.8 * length / 2, binary dims reset to [0, 1]
-        centre = torch.full((d,), 0.45, dtype=torch.float64)
-        lo, hi = (centre - 0.4).clamp(0, 1), (centre + 0.4).clamp(0, 1)
-        for bdim in c["binary_dims"]:
-            lo[bdim], hi[bdim] = 0.0, 1.0
+    if c.get("trust_region"):  # run_one_replication.py:410-440 at the initial TurboState (length 0.8)
+        from bo_pr_b200.trust_region import TurboState, trust_region_bounds
+        centre = torch.full((1, d), 0.45, dtype=torch.float64)
+        return trust_region_bounds(TurboState(dim=d, batch_size=1, is_constrained=False), centre,
+                                   torch.zeros(1, 1, dtype=torch.float64), torch.stack([lo, hi]),
+                                   binary_dims=c["binary_dims"])
     return torch.stack([lo, hi])
 
 
