@@ -231,11 +231,13 @@ Plan make_plan(const Model& m, int64_t n_points, int n_restarts, int d_theta, in
   p.off_step = take(256);
   p.off_zbits = take(size_t(p.B_pad) * sizeof(uint32_t));
   p.off_done = take(256);
+  if (n_restarts > 0) {  // scratch of the single-kernel step (prb_small.cu)
+    p.small_bytes = (size_t(p.B_pad / 32 + n_restarts) * (1 + d_theta)) * dbl + size_t(n_restarts + 4) * sizeof(int) + 64;
+    p.off_small = take(p.small_bytes);
+  }
   if (m.sep_ok && n_restarts > 0) {
     p.off_kc = take(size_t(n_restarts) * m.Kp * dbl);
     p.off_Dc = take(size_t(n_restarts) * d_theta * m.Kp * dbl);
-    p.small_bytes = (size_t(p.B_pad / 32 + n_restarts) * (1 + d_theta)) * dbl + size_t(n_restarts + 4) * sizeof(int) + 64;
-    p.off_small = take(p.small_bytes);
     p.off_ucount = take(size_t(n_restarts) * sizeof(int));
     p.off_ustart = take(size_t(n_restarts + 1) * sizeof(int));
     p.off_utotal = take(2 * sizeof(int));
@@ -498,11 +500,15 @@ int mc_core(prb_model* model, const DevSpace& sp, const DevAcq& aq, const Plan& 
   int rc;
   const bool dedup = sep && m.opt_dedup && m.sep_nbits <= DEDUP_MAX_BITS;
   // experiment sizes: the whole call -- sampler, both products, acquisition, reductions, EMA -- is one kernel (prb_small.cu)
-  if (sep && !dedup && out_acq_values == nullptr && small_step_eligible(m, sp, dm, b, mc) &&
-      small_step_scratch_bytes(b, mc, sp.d) <= pl.small_bytes) {
+  int small_kind = 0;  // 1: separable kernel, 2: generic single-term kernel
+  if (out_acq_values == nullptr && small_step_scratch_bytes(b, mc, sp.d) <= pl.small_bytes) {
+    if (sep && !dedup && small_step_eligible(m, sp, dm, b, mc)) small_kind = 1;
+    else if (!sep && small_gen_eligible(m, sp, &dm, b, mc)) small_kind = 2;
+  }
+  if (small_kind != 0) {
     // completion counters live behind the per-tile partial sums: zero the (small) scratch; launches re-arm them themselves
     CUDA_TRY(cudaMemsetAsync(at<char>(ws, pl.off_small), 0, small_step_scratch_bytes(b, mc, sp.d), st));
-    CUDA_TRY(launch_small_step(m, sp, aq, bm, dm, theta, nullptr, nullptr, nullptr, b, mc, u_int, u_cat, seed, offset,
+    CUDA_TRY(launch_small_step(m, small_kind == 2, sp, aq, bm, dm, theta, nullptr, nullptr, nullptr, b, mc, u_int, u_cat, seed, offset,
                                estimator, ma_state, (update_ma && ma_state) ? 1 : 0, need_grad, grad_out, out_value,
                                out_grad, nullptr, nullptr, nullptr, 0.0, nullptr, at<char>(ws, pl.off_small), st));
     return PRB_OK;
@@ -1015,19 +1021,24 @@ int prb_mc_adam(prb_model* model, const prb_space_desc* space, const prb_acq_des
                           !(m.opt_dedup && m.sep_nbits <= DEDUP_MAX_BITS) && getenv("PRB_NO_FUSED_STEP") == nullptr;
 
   // experiment sizes (n + 1 <= 128, mc % 32 == 0): the whole step is ONE kernel (prb_small.cu)
-  const bool small_step = fused_step && small_step_eligible(m, sp, dm, b, mc) &&
-                          small_step_scratch_bytes(b, mc, sp.d) <= pl.small_bytes;
+  const bool sep_space = pl.off_kc != 0 && sep_space_ok(m, sp, &bm, &dm);
+  bool small_gen = false;  // single-term kernels that do not separate use the generic variant of the same kernel
+  bool small_step = fused_step && small_step_eligible(m, sp, dm, b, mc) &&
+                    small_step_scratch_bytes(b, mc, sp.d) <= pl.small_bytes;
+  if (!small_step && !sep_space && small_step_scratch_bytes(b, mc, sp.d) <= pl.small_bytes &&
+      small_gen_eligible(m, sp, &dm, b, mc) && getenv("PRB_NO_FUSED_STEP") == nullptr)
+    small_step = small_gen = true;
   if (small_step) CUDA_TRY(cudaMemsetAsync(at<char>(workspace, pl.off_small), 0, pl.small_bytes, st));
   if (small_step && small_adam_persistent_ok(b, mc)) {
     // the whole optimisation -- maxiter Adam steps and the final evaluation -- as one cooperative persistent kernel
-    CUDA_TRY(launch_small_adam_persistent(m, sp, aq, bm, dm, theta, lower, upper, b, mc, u_int, u_cat, seed, offset,
+    CUDA_TRY(launch_small_adam_persistent(m, small_gen, sp, aq, bm, dm, theta, lower, upper, b, mc, u_int, u_cat, seed, offset,
                                           estimator, ma_state, update_ma, val, out_value, adam_state, adam_state + total,
                                           lr, maxiter, step0, at<char>(workspace, pl.off_small), st));
     return PRB_OK;
   }
 
   // kernel structures that do not separate: the six-launch fused step on a single column panel
-  const bool generic_fused = !fused_step && int64_t(b) * mc <= pl.C && !(pl.off_kc != 0 && sep_space_ok(m, sp, &bm, &dm)) &&
+  const bool generic_fused = !fused_step && !small_step && int64_t(b) * mc <= pl.C && !sep_space &&
                              getenv("PRB_NO_FUSED_STEP") == nullptr;
 
   auto one_iter = [&]() -> int {
@@ -1035,7 +1046,7 @@ int prb_mc_adam(prb_model* model, const prb_space_desc* space, const prb_acq_des
       return generic_step(m, sp, aq, pl, workspace, theta, lower, upper, Xc, b, mc, u_int, u_cat, seed, offset, estimator,
                           ma_state, update_ma, true, nullptr, val, grad, theta, adam_state, adam_state + total, lr, step, st);
     if (small_step) {
-      CUDA_TRY(launch_small_step(m, sp, aq, bm, dm, theta, lower, upper, Xc, b, mc, u_int, u_cat, seed, offset, estimator,
+      CUDA_TRY(launch_small_step(m, small_gen, sp, aq, bm, dm, theta, lower, upper, Xc, b, mc, u_int, u_cat, seed, offset, estimator,
                                  ma_state, update_ma, true, nullptr, val, grad, theta, adam_state, adam_state + total, lr,
                                  step, at<char>(workspace, pl.off_small), st));
       return PRB_OK;
@@ -1092,7 +1103,7 @@ int prb_mc_adam(prb_model* model, const prb_space_desc* space, const prb_acq_des
                         ma_state, update_ma, false, nullptr, out_value, nullptr, nullptr, nullptr, nullptr, lr, nullptr,
                         st);
   if (small_step) {
-    CUDA_TRY(launch_small_step(m, sp, aq, bm, dm, theta, lower, upper, theta, b, mc, u_int, u_cat, seed, offset, estimator,
+    CUDA_TRY(launch_small_step(m, small_gen, sp, aq, bm, dm, theta, lower, upper, theta, b, mc, u_int, u_cat, seed, offset, estimator,
                                ma_state, update_ma, false, nullptr, out_value, nullptr, nullptr, nullptr, nullptr, lr,
                                nullptr, at<char>(workspace, pl.off_small), st));
     return PRB_OK;

@@ -167,18 +167,19 @@ constexpr int DEDUP_MAX_BITS = 12;  // histogram de-duplication: 2^12 bins of sh
 
 // prb_small.cu: one kernel per optimisation step for experiment-sized separable problems
 bool small_step_eligible(const Model& m, const DevSpace& sp, const DimMap& dm, int b, int mc);
+bool small_gen_eligible(const Model& m, const DevSpace& sp, DimMap* dm, int b, int mc);  // generic single-term variant
 size_t small_step_scratch_bytes(int b, int mc, int d);
 cudaError_t small_step_init();
 cudaError_t small_step_timestamps(long long* host_out);
-cudaError_t launch_small_step(const Model& m, const DevSpace& sp, const DevAcq& aq, const BitMap& bm, const DimMap& dm,
-                              const double* theta_in, const double* lower, const double* upper, double* Xc, int b, int mc,
+cudaError_t launch_small_step(const Model& m, bool gen, const DevSpace& sp, const DevAcq& aq, const BitMap& bm,
+                              const DimMap& dm, const double* theta_in, const double* lower, const double* upper, double* Xc, int b, int mc,
                               const double* u_int, const double* u_cat, uint64_t seed, uint64_t offset, int estimator,
                               double* ma_state, int update_ma, bool need_grad, const double* grad_out, double* out_value,
                               double* out_grad, double* adam_theta, double* adam_m, double* adam_v, double lr,
                               int* step_ptr, void* scratch, cudaStream_t st);
 
 bool small_adam_persistent_ok(int b, int mc);
-cudaError_t launch_small_adam_persistent(const Model& m, const DevSpace& sp, const DevAcq& aq, const BitMap& bm,
+cudaError_t launch_small_adam_persistent(const Model& m, bool gen, const DevSpace& sp, const DevAcq& aq, const BitMap& bm,
                                          const DimMap& dm, double* theta, const double* lower, const double* upper, int b,
                                          int mc, const double* u_int, const double* u_cat, uint64_t seed, uint64_t offset,
                                          int estimator, double* ma_state, int update_ma, double* step_value,

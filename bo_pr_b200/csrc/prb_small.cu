@@ -34,7 +34,10 @@ struct SmallStepParams {
   DevSpace sp;
   BitMap bm;
   DimMap dm;
-  DevFactor fc;
+  DevTerm term;  // the model's (single) product term
+  int cf;        // separable kernel: index of the continuous factor in `term`
+  int gf;        // generic kernel: index of the Matern factor that holds every continuous PR parameter (-1: none)
+  double gw[8];  // generic kernel: 1 / lengthscale^2 of continuous parameter c inside factor gf
   DevAcq aq;
   double outputscale, mean_const, kss;
   const double* Xtr;
@@ -90,10 +93,12 @@ constexpr int SM_ACQ = 3 * 32;
 constexpr int SM_VEC = 4 * 32;         // th, ps, offs, g
 constexpr int SM_TAB = 64;
 constexpr int SM_U = 32 * 32;          // base uniforms of this tile's 32 samples (fixed for the life of the kernel)
-constexpr int SM_X = 128 * S_MAXC;     // training inputs, continuous-factor columns only
+constexpr int G_MAXD = 16;             // generic variant: kernel-input dimension limit
+constexpr int SM_X = 128 * G_MAXD;     // training inputs: separable [row][S_MAXC] (continuous factor); generic [dim][128]
+constexpr int SM_XK = G_MAXD * 32;     // generic variant: kernel inputs of this tile's 32 samples, [dim][col]
 constexpr int SM_PART = 8 * 33;        // staging of the per-tile partial sums in the finish chain
 constexpr int SM_DOUBLES =
-    SM_A + SM_B + SM_KC + SM_DC + SM_AL + SM_RED + SM_S + SM_ACQ + SM_VEC + SM_TAB + SM_U + SM_X + SM_PART;
+    SM_A + SM_B + SM_KC + SM_DC + SM_AL + SM_RED + SM_S + SM_ACQ + SM_VEC + SM_TAB + SM_U + SM_X + SM_XK + SM_PART;
 constexpr size_t SMALL_SMEM_BYTES = size_t(SM_DOUBLES) * 8 + 128 * 4 + 32 * 4 + 32 * 32 + 16 + 16;
 
 // phase timestamps of CTA 0 (clock64), read back by prb_debug_small_timestamps(): diagnostic for the latency budget
@@ -103,8 +108,72 @@ __device__ long long g_small_ts[16];
     if (blockIdx.x == 0 && threadIdx.x == 0 && ts_on) g_small_ts[k] = clock64(); \
   } while (0)
 
+// Generic variant (GEN): a single product term of Matern / categorical factors over arbitrary dims -- integer parameters of
+// any range inside an ARD factor (rosenbrock10_scaled, mixed_int_f1: kernels.py:52-66 with non-binary integers).  k* is
+// evaluated entry by entry from the sampled kernel inputs; the pathwise gradient needs d k / d x_c only for the continuous
+// parameters, which all sit in factor `gf`:  d k / d x_c = Q(row, col) * gw[c] * (x_c - X[row, c]) with
+// Q = outputscale * p F_gf^(p-1) G_gf * prod_{g != gf} F_g^p_g   (WITH_G: returns Q instead of k).
+// The evaluation is written for a block of NR training rows x NC columns per thread so that the FP64 dependency chains
+// (distance accumulation, sqrt, exp) of the entries interleave: with 8 warps per SM a one-entry-at-a-time loop is bound by
+// instruction latency, not throughput.
+template <int NR, int NC, bool WITH_G>
+__device__ __forceinline__ void small_eval_block(const DevTerm& T, int gf, const double* __restrict__ xk_s,
+                                                 const int (&cols)[NC], const double* __restrict__ X_s,
+                                                 const int (&rows)[NR], double (&out)[NR][NC]) {
+#pragma unroll
+  for (int r = 0; r < NR; ++r)
+#pragma unroll
+    for (int c = 0; c < NC; ++c) out[r][c] = T.outputscale;
+  for (int f = 0; f < T.n_factors; ++f) {
+    const DevFactor& F = T.f[f];
+    const bool matern = F.kind == PRB_FACTOR_MATERN52;
+    double r2[NR][NC];
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) r2[r][c] = 0.0;
+    for (int di = 0; di < F.n_dims; ++di) {
+      const int dim = F.dims[di];
+      const double ils = F.inv_ls[di];
+      double xc[NC], xr[NR];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) xc[c] = xk_s[dim * 32 + cols[c]];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) xr[r] = X_s[dim * 128 + rows[r]];
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          if (matern) {
+            const double df = (xc[c] - xr[r]) * ils;
+            r2[r][c] = fma(df, df, r2[r][c]);
+          } else {
+            r2[r][c] += (xc[c] != xr[r]) ? ils : 0.0;
+          }
+        }
+    }
+    const bool grad_here = WITH_G && f == gf;
+    const double pw = (F.power > 1) ? double(F.power) : 1.0;
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        double v, G = 0.0;
+        if (matern)
+          v = matern52(r2[r][c], &G);
+        else
+          v = exp(-r2[r][c]);
+        if (grad_here)
+          out[r][c] *= (F.power > 1 ? pw * ipow(v, F.power - 1) : 1.0) * G;
+        else
+          out[r][c] *= ipow(v, F.power);
+      }
+  }
+}
+
+template <bool GEN>
 __global__ void __launch_bounds__(S_THREADS, 1)
-    sep_small_step_kernel(const __grid_constant__ CUtensorMap tmA, const SmallStepParams p) {
+    small_step_kernel(const __grid_constant__ CUtensorMap tmA, const SmallStepParams p) {
   extern __shared__ __align__(128) unsigned char smraw[];
   double* A_s = reinterpret_cast<double*>(smraw);
   double* B_s = A_s + SM_A;
@@ -122,8 +191,9 @@ __global__ void __launch_bounds__(S_THREADS, 1)
   double* g_s = offs_s + 32;
   double* tab_s = g_s + 32;
   double* u_s = tab_s + SM_TAB;   // [32][n_int]
-  double* X_s = u_s + SM_U;       // [128][S_MAXC]
-  double* pt_s = X_s + SM_X;      // [8][33]
+  double* X_s = u_s + SM_U;       // [128][S_MAXC], GEN: [d_k][128]
+  double* xk_s = X_s + SM_X;      // GEN: [d_k][32]
+  double* pt_s = xk_s + SM_XK;    // [8][33]
   uint32_t* Zb_s = reinterpret_cast<uint32_t*>(pt_s + SM_PART);  // [128]
   uint32_t* zb_s = Zb_s + 128;                                   // [32]
   uint8_t* z_s = reinterpret_cast<uint8_t*>(zb_s + 32);          // [32][n_disc <= 32]
@@ -151,12 +221,19 @@ __global__ void __launch_bounds__(S_THREADS, 1)
     __syncwarp();
     if (lane < p.nchunks) tma_load_2d(A_s + lane * 512, &tmA, bar, 4 * lane, 0);
   }
-  if (tid < 64) tab_s[tid] = (tid <= p.ntab) ? p.tab[tid] : 0.0;
+  const DevFactor& fc = p.term.f[p.cf];
+  if constexpr (!GEN) {
+    if (tid < 64) tab_s[tid] = (tid <= p.ntab) ? p.tab[tid] : 0.0;
+  }
   if (tid < 128) {
-    Zb_s[tid] = p.Zbits[tid];
     al_s[tid] = p.alpha_pad[tid];
-    for (int di = 0; di < p.fc.n_dims; ++di)
-      X_s[tid * S_MAXC + di] = (tid < n) ? p.Xtr[size_t(tid) * p.d_k + p.fc.dims[di]] : 0.0;
+    if constexpr (GEN) {
+      for (int dd = 0; dd < p.d_k; ++dd) X_s[dd * 128 + tid] = (tid < n) ? p.Xtr[size_t(tid) * p.d_k + dd] : 0.0;
+    } else {
+      Zb_s[tid] = p.Zbits[tid];
+      for (int di = 0; di < fc.n_dims; ++di)
+        X_s[tid * S_MAXC + di] = (tid < n) ? p.Xtr[size_t(tid) * p.d_k + fc.dims[di]] : 0.0;
+    }
   }
   // The base uniforms of this tile's samples never change between steps (the reference caches its Sobol base samples, the
   // Philox stream is keyed on (sample, parameter) only): fetched / generated once, kept in shared memory.
@@ -212,7 +289,22 @@ __global__ void __launch_bounds__(S_THREADS, 1)
       uint8_t zk;
       const double tn = pr_sample_int(sp, th_s, ps_s, offs_s, col, k, u_s, 0, 0, &zk);  // u = u_s[col * n_int + k]
       z_s[col * sp.n_disc + k] = zk;
-      if (p.bm.pos[k] >= 0 && tn != 0.0) atomicOr(&zb_s[col], 1u << p.bm.pos[k]);
+      if constexpr (GEN) {
+        xk_s[sp.int_cols[k] * 32 + col] = tn;
+      } else {
+        if (p.bm.pos[k] >= 0 && tn != 0.0) atomicOr(&zb_s[col], 1u << p.bm.pos[k]);
+      }
+    }
+  } else if constexpr (GEN) {
+    // warps 4-7: continuous kernel inputs of the 32 columns and the restart's gradient directions gw_c (x_c - X[j, c])
+    const int j = tid - 128;
+    for (int e = j; e < 32 * dmref.n; e += 128) {
+      const int dim = dmref.dims[e >> 5];
+      xk_s[dim * 32 + (e & 31)] = th_s[dim];
+    }
+    for (int c = 0; c < dmref.n; ++c) {
+      const int dim = dmref.dims[c];
+      Dc_s[c * 128 + j] = (j < n) ? p.gw[c] * (th_s[dim] - X_s[dim * 128 + j]) : 0.0;
     }
   } else {
     // warps 4-7: the restart's continuous-factor values and derivatives for the 128 (padded) training points
@@ -220,18 +312,18 @@ __global__ void __launch_bounds__(S_THREADS, 1)
     double val = 0.0, G = 0.0;
     if (j < n) {
       double r2 = 0.0;
-      for (int di = 0; di < p.fc.n_dims; ++di) {
-        const int dim = p.fc.dims[di];
-        const double df = (th_s[dim] - X_s[j * S_MAXC + di]) * p.fc.inv_ls[di];
+      for (int di = 0; di < fc.n_dims; ++di) {
+        const int dim = fc.dims[di];
+        const double df = (th_s[dim] - X_s[j * S_MAXC + di]) * fc.inv_ls[di];
         r2 = fma(df, df, r2);
       }
       val = p.outputscale * matern52(r2, &G);
     }
     kc_s[j] = val;
-    for (int di = 0; di < p.fc.n_dims; ++di) {
-      const int dim = p.fc.dims[di];
+    for (int di = 0; di < fc.n_dims; ++di) {
+      const int dim = fc.dims[di];
       double v = 0.0;
-      if (j < n) v = p.outputscale * G * (p.fc.inv_ls[di] * p.fc.inv_ls[di]) * (th_s[dim] - X_s[j * S_MAXC + di]);
+      if (j < n) v = p.outputscale * G * (fc.inv_ls[di] * fc.inv_ls[di]) * (th_s[dim] - X_s[j * S_MAXC + di]);
       Dc_s[di * 128 + j] = v;
     }
   }
@@ -244,12 +336,30 @@ __global__ void __launch_bounds__(S_THREADS, 1)
     const int k4 = tid & 3;
     const int col = (tid >> 2) & 31;
     const int chi = tid >> 7;  // chunks chi * 16 .. chi * 16 + 15
-    const uint32_t zc = zb_s[col];
+    if constexpr (GEN) {
+      // chunks interleaved over the two thread halves (c = 2 t + chi), 8 rows of one column per pass
+      const int cols1[1] = {col};
+      for (int t0 = 0; t0 < 16; t0 += 8) {
+        if (2 * t0 + chi >= p.nchunks) break;
+        int rws[8];
 #pragma unroll
-    for (int t = 0; t < 16; ++t) {
-      const int c = chi * 16 + t;
-      const int k = 4 * c + k4;
-      B_s[c * 128 + col * 4 + k4] = kc_s[k] * tab_s[__popc(zc ^ Zb_s[k])];
+        for (int t = 0; t < 8; ++t) rws[t] = min(4 * (2 * (t0 + t) + chi) + k4, 127);
+        double kv[8][1];
+        small_eval_block<8, 1, false>(p.term, -1, xk_s, cols1, X_s, rws, kv);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int c = 2 * (t0 + t) + chi;
+          if (c < 32) B_s[c * 128 + col * 4 + k4] = (4 * c + k4 < n) ? kv[t][0] : 0.0;
+        }
+      }
+    } else {
+      const uint32_t zc = zb_s[col];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const int c = chi * 16 + t;
+        const int k = 4 * c + k4;
+        B_s[c * 128 + col * 4 + k4] = kc_s[k] * tab_s[__popc(zc ^ Zb_s[k])];
+      }
     }
   }
   __syncthreads();
@@ -398,6 +508,18 @@ __global__ void __launch_bounds__(S_THREADS, 1)
     int rows[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) rows[i] = 8 * grp[i] + frag_r;
+    double qk[4][4];  // GEN: Q(row i, column (j, e))
+    if constexpr (GEN) {
+      if (dmref.n > 0) {
+        int cl[4], rw[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          cl[q] = wn * 16 + 8 * (q >> 1) + 2 * frag_k + (q & 1);
+          rw[q] = rows[q];
+        }
+        small_eval_block<4, 4, true>(p.term, p.gf, xk_s, cl, X_s, rw, qk);
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -405,10 +527,19 @@ __global__ void __launch_bounds__(S_THREADS, 1)
         const int col = wn * 16 + 8 * j + 2 * frag_k + e;
         const double cm = dmu_s[col];
         const double cv = -2.0 * dvar_s[col];
-        const uint32_t zc = zb_s[col];
+        if constexpr (GEN) {
+          if (dmref.n > 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          acc[i][j][e] = (rows[i] < n) ? fma(cv, acc[i][j][e], cm * al_s[rows[i]]) * tab_s[__popc(zc ^ Zb_s[rows[i]])] : 0.0;
+            for (int i = 0; i < 4; ++i)
+              acc[i][j][e] = (rows[i] < n) ? fma(cv, acc[i][j][e], cm * al_s[rows[i]]) * qk[i][2 * j + e] : 0.0;
+          }
+        } else {
+          const uint32_t zc = zb_s[col];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            acc[i][j][e] =
+                (rows[i] < n) ? fma(cv, acc[i][j][e], cm * al_s[rows[i]]) * tab_s[__popc(zc ^ Zb_s[rows[i]])] : 0.0;
+        }
       }
     for (int c = 0; c < dmref.n; ++c) {
       double part[2][2];
@@ -543,22 +674,68 @@ bool small_step_eligible(const Model& m, const DevSpace& sp, const DimMap& dm, i
          sp.n_disc <= 32 && sp.n_cat == 0 && sp.d <= 32 && b >= 1;
 }
 
+// Generic variant: one product term; every continuous PR parameter inside one Matern factor; no categoricals.
+static bool small_gen_setup(const Model& m, const DevSpace& sp, DimMap* dm, int* gf_out, double* gw) {
+  if (m.spec.n_terms != 1 || m.spec.t[0].additive || sp.n_cat != 0 || sp.d != m.d_k || m.d_k > G_MAXD ||
+      sp.n_cont > S_MAXC || sp.n_disc > 32)
+    return false;
+  const DevTerm& T = m.spec.t[0];
+  int gf = -1;
+  dm->n = sp.n_cont;
+  for (int c = 0; c < sp.n_cont; ++c) {
+    const int dim = sp.cont_cols[c];
+    dm->dims[c] = dim;
+    int hits = 0;
+    for (int f = 0; f < T.n_factors; ++f)
+      for (int di = 0; di < T.f[f].n_dims; ++di)
+        if (T.f[f].dims[di] == dim) {
+          if (T.f[f].kind != PRB_FACTOR_MATERN52 || (gf >= 0 && gf != f)) return false;
+          gf = f;
+          ++hits;
+          if (gw) gw[c] = T.f[f].inv_ls[di] * T.f[f].inv_ls[di];
+        }
+    if (hits > 1) return false;              // the same dim listed twice in a factor
+    if (hits == 0 && gw) gw[c] = 0.0;        // a parameter the kernel ignores: zero pathwise gradient
+  }
+  *gf_out = gf;
+  return true;
+}
+
+bool small_gen_eligible(const Model& m, const DevSpace& sp, DimMap* dm, int b, int mc) {
+  static const bool off = getenv("PRB_NO_SMALL_STEP") != nullptr || getenv("PRB_NO_SMALL_GEN") != nullptr;
+  int gf;
+  return !off && m.Mp1 == 128 && m.Kp <= 128 && mc % S_BN == 0 && mc >= S_BN && b >= 1 &&
+         small_gen_setup(m, sp, dm, &gf, nullptr);
+}
+
 size_t small_step_scratch_bytes(int b, int mc, int d) {
   return (size_t(b) * (mc / S_BN) * (1 + d)) * sizeof(double) + size_t(b + 2) * sizeof(unsigned int) + 64;
 }
 
 cudaError_t small_step_init() {
-  return cudaFuncSetAttribute(sep_small_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMALL_SMEM_BYTES));
+  cudaError_t e = cudaFuncSetAttribute(small_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       int(SMALL_SMEM_BYTES));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(small_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              int(SMALL_SMEM_BYTES));
 }
 
-static void fill_small_params(SmallStepParams& p, const Model& m, const DevSpace& sp, const DevAcq& aq, const BitMap& bm,
-                              const DimMap& dm, int b, int mc, const double* u_int, const double* u_cat, uint64_t seed,
-                              uint64_t offset, int estimator, double* ma_state, int update_ma, void* scratch) {
+static void fill_small_params(SmallStepParams& p, bool gen, const Model& m, const DevSpace& sp, const DevAcq& aq,
+                              const BitMap& bm, const DimMap& dm, int b, int mc, const double* u_int, const double* u_cat,
+                              uint64_t seed, uint64_t offset, int estimator, double* ma_state, int update_ma,
+                              void* scratch) {
   memset(&p, 0, sizeof(p));
   p.sp = sp;
   p.bm = bm;
   p.dm = dm;
-  p.fc = m.spec.t[0].f[m.sep_cont_factor];
+  p.term = m.spec.t[0];
+  if (gen) {
+    DimMap dm2;
+    small_gen_setup(m, sp, &dm2, &p.gf, p.gw);
+    p.dm = dm2;
+  } else {
+    p.cf = m.sep_cont_factor;
+  }
   p.aq = aq;
   p.outputscale = m.spec.t[0].outputscale;
   p.mean_const = m.mean_const;
@@ -588,15 +765,15 @@ static void fill_small_params(SmallStepParams& p, const Model& m, const DevSpace
   p.iters = 1;
 }
 
-cudaError_t launch_small_step(const Model& m, const DevSpace& sp, const DevAcq& aq, const BitMap& bm, const DimMap& dm,
-                              const double* theta_in, const double* lower, const double* upper, double* Xc, int b, int mc,
-                              const double* u_int, const double* u_cat, uint64_t seed, uint64_t offset, int estimator,
-                              double* ma_state, int update_ma, bool need_grad, const double* grad_out, double* out_value,
-                              double* out_grad, double* adam_theta, double* adam_m, double* adam_v, double lr,
-                              int* step_ptr, void* scratch, cudaStream_t st) {
+cudaError_t launch_small_step(const Model& m, bool gen, const DevSpace& sp, const DevAcq& aq, const BitMap& bm,
+                              const DimMap& dm, const double* theta_in, const double* lower, const double* upper,
+                              double* Xc, int b, int mc, const double* u_int, const double* u_cat, uint64_t seed,
+                              uint64_t offset, int estimator, double* ma_state, int update_ma, bool need_grad,
+                              const double* grad_out, double* out_value, double* out_grad, double* adam_theta,
+                              double* adam_m, double* adam_v, double lr, int* step_ptr, void* scratch, cudaStream_t st) {
   ProfScope prof_(K_ADAM, st);
   SmallStepParams p;
-  fill_small_params(p, m, sp, aq, bm, dm, b, mc, u_int, u_cat, seed, offset, estimator, ma_state, update_ma, scratch);
+  fill_small_params(p, gen, m, sp, aq, bm, dm, b, mc, u_int, u_cat, seed, offset, estimator, ma_state, update_ma, scratch);
   p.theta = theta_in;
   p.lower = lower;
   p.upper = upper;
@@ -610,13 +787,16 @@ cudaError_t launch_small_step(const Model& m, const DevSpace& sp, const DevAcq& 
   p.adam_v = adam_v;
   p.lr = lr;
   p.step_ptr = step_ptr;
-  sep_small_step_kernel<<<b * p.tiles, S_THREADS, SMALL_SMEM_BYTES, st>>>(
-      *reinterpret_cast<const CUtensorMap*>(&m.mapA1), p);
+  const CUtensorMap& tm = *reinterpret_cast<const CUtensorMap*>(&m.mapA1);
+  if (gen)
+    small_step_kernel<true><<<b * p.tiles, S_THREADS, SMALL_SMEM_BYTES, st>>>(tm, p);
+  else
+    small_step_kernel<false><<<b * p.tiles, S_THREADS, SMALL_SMEM_BYTES, st>>>(tm, p);
   count_launch();
   return cudaGetLastError();
 }
 
-// Can the whole multi-start Adam run as ONE cooperative launch?  Every CTA must be resident (one per SM: 182 KB of
+// Can the whole multi-start Adam run as ONE cooperative launch?  Every CTA must be resident (one per SM: ~210 KB of
 // shared memory each) because the steps are separated by a grid-wide barrier.
 bool small_adam_persistent_ok(int b, int mc) {
   static int sms = -1, coop = 0;
@@ -633,7 +813,7 @@ bool small_adam_persistent_ok(int b, int mc) {
 
 // gen_candidates_torch (gen.py:304-343) as one persistent kernel: maxiter x (clamp -> value + gradient -> Adam), then the
 // final clamp and value-only evaluation; the steps are separated by a grid barrier instead of kernel boundaries.
-cudaError_t launch_small_adam_persistent(const Model& m, const DevSpace& sp, const DevAcq& aq, const BitMap& bm,
+cudaError_t launch_small_adam_persistent(const Model& m, bool gen, const DevSpace& sp, const DevAcq& aq, const BitMap& bm,
                                          const DimMap& dm, double* theta, const double* lower, const double* upper, int b,
                                          int mc, const double* u_int, const double* u_cat, uint64_t seed, uint64_t offset,
                                          int estimator, double* ma_state, int update_ma, double* step_value,
@@ -641,7 +821,7 @@ cudaError_t launch_small_adam_persistent(const Model& m, const DevSpace& sp, con
                                          int step0, void* scratch, cudaStream_t st) {
   ProfScope prof_(K_ADAM, st);
   SmallStepParams p;
-  fill_small_params(p, m, sp, aq, bm, dm, b, mc, u_int, u_cat, seed, offset, estimator, ma_state, update_ma, scratch);
+  fill_small_params(p, gen, m, sp, aq, bm, dm, b, mc, u_int, u_cat, seed, offset, estimator, ma_state, update_ma, scratch);
   p.theta = theta;
   p.lower = lower;
   p.upper = upper;
@@ -658,8 +838,9 @@ cudaError_t launch_small_adam_persistent(const Model& m, const DevSpace& sp, con
   p.step0 = step0;
   CUtensorMap tm = *reinterpret_cast<const CUtensorMap*>(&m.mapA1);
   void* args[] = {&tm, &p};
-  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&sep_small_step_kernel), dim3(b * p.tiles),
-                                              dim3(S_THREADS), args, SMALL_SMEM_BYTES, st);
+  const void* fn = gen ? reinterpret_cast<const void*>(&small_step_kernel<true>)
+                       : reinterpret_cast<const void*>(&small_step_kernel<false>);
+  cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(b * p.tiles), dim3(S_THREADS), args, SMALL_SMEM_BYTES, st);
   g_launches += 1;  // one launch; it stands for (maxiter + 1) fused steps
   return e != cudaSuccess ? e : cudaGetLastError();
 }

@@ -30,3 +30,11 @@ for name in ("rosenbrock10_scaled pr__ucb", "mixed_int_f1_TR pr__ei"):
     lib.prb_profile_enable(1); run(None, 50)
     msk = (C.c_double * 12)(); cnt = (C.c_uint64 * 12)(); lib.prb_profile_read(msk, cnt, 12); lib.prb_profile_enable(0)
     print({nm: (round(msk[i] / 51 * 1e3, 1), int(cnt[i]) // 51) for i, nm in enumerate(capi.PROFILE_SLOT_NAMES) if cnt[i]}, "us per step (plain launches, events)")
+    ts = (C.c_longlong * 16)()
+    run(side.cuda_stream, 200)
+    lib.prb_debug_small_timestamps(ts)
+    t = [ts[i] for i in range(14)]
+    seq = [11, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 13]
+    names = ["state reads", "prep", "gen", "wait A1", "lower", "acq epilogue", "upper", "grad contraction", "partials",
+             "fence+ticket", "finish chain", "grid barrier"]
+    print("steady-state step of CTA 0 (cycles):", {names[i]: t[seq[i + 1]] - t[seq[i]] for i in range(12)}, "total", t[13] - t[11])
