@@ -38,6 +38,7 @@ struct SmallStepParams {
   int cf;        // separable kernel: index of the continuous factor in `term`
   int gf;        // generic kernel: index of the Matern factor that holds every continuous PR parameter (-1: none)
   double gw[8];  // generic kernel: 1 / lengthscale^2 of continuous parameter c inside factor gf
+  uint32_t contmask;  // generic kernel: kernel-input dims that are continuous PR parameters
   DevAcq aq;
   double outputscale, mean_const, kss;
   const double* Xtr;
@@ -108,32 +109,80 @@ __device__ long long g_small_ts[16];
     if (blockIdx.x == 0 && threadIdx.x == 0 && ts_on) g_small_ts[k] = clock64(); \
   } while (0)
 
-// Generic variant (GEN): a single product term of Matern / categorical factors over arbitrary dims -- integer parameters of
+// Generic variant (GEN): a single product term of Matern-5/2 factors (power 1 or 2) over arbitrary dims -- integer parameters of
 // any range inside an ARD factor (rosenbrock10_scaled, mixed_int_f1: kernels.py:52-66 with non-binary integers).  k* is
 // evaluated entry by entry from the sampled kernel inputs; the pathwise gradient needs d k / d x_c only for the continuous
 // parameters, which all sit in factor `gf`:  d k / d x_c = Q(row, col) * gw[c] * (x_c - X[row, c]) with
 // Q = outputscale * p F_gf^(p-1) G_gf * prod_{g != gf} F_g^p_g   (WITH_G: returns Q instead of k).
+// Branch-free sqrt / exp for the block evaluation below: the library versions carry slow-path branches, which keep the
+// compiler from interleaving the 16 independent evaluations of a thread.  Arguments are bounded here (r2 in [1e-30, 1e8],
+// exponent in [-690, 0]); both are accurate to about one ulp, far inside the 1e-9 parity tolerance.
+__device__ __forceinline__ double sqrt_nb(double x) {
+  double y = double(rsqrtf(__double2float_rn(x)));  // ~2^-22 relative
+  const double hx = 0.5 * x;
+  y = y * fma(-hx * y, y, 1.5);
+  y = y * fma(-hx * y, y, 1.5);
+  const double sq = x * y;
+  return fma(0.5 * y, fma(-sq, sq, x), sq);
+}
+__device__ __forceinline__ double exp_neg_nb(double x) {  // x <= 0
+  x = fmax(x, -690.0);
+  const double kf = rint(x * 1.4426950408889634074);
+  double r = fma(kf, -6.93147180369123816490e-01, x);
+  r = fma(kf, -1.90821492927058770002e-10, r);
+  double q = 1.6059043836821613e-10;  // 1/13!
+  q = fma(q, r, 2.08767569878681e-09);
+  q = fma(q, r, 2.505210838544172e-08);
+  q = fma(q, r, 2.755731922398589e-07);
+  q = fma(q, r, 2.755731922398589e-06);
+  q = fma(q, r, 2.48015873015873e-05);
+  q = fma(q, r, 1.984126984126984e-04);
+  q = fma(q, r, 1.388888888888889e-03);
+  q = fma(q, r, 8.333333333333333e-03);
+  q = fma(q, r, 4.1666666666666664e-02);
+  q = fma(q, r, 1.6666666666666666e-01);
+  q = fma(q, r, 0.5);
+  q = fma(q, r, 1.0);
+  q = fma(q, r, 1.0);
+  const int k = __double2int_rn(kf);
+  return __hiloint2double(__double2hiint(q) + (k << 20), __double2loint(q));
+}
+__device__ __forceinline__ double matern52_nb(double r2, double* G) {
+  const double r = sqrt_nb(fmax(r2, 1e-30));
+  const double s5r = PRB_SQRT5 * r;
+  const double e = exp_neg_nb(-s5r);
+  *G = -(5.0 / 3.0) * (1.0 + s5r) * e;
+  return (1.0 + s5r + (5.0 / 3.0) * (r * r)) * e;
+}
+
 // The evaluation is written for a block of NR training rows x NC columns per thread so that the FP64 dependency chains
 // (distance accumulation, sqrt, exp) of the entries interleave: with 8 warps per SM a one-entry-at-a-time loop is bound by
-// instruction latency, not throughput.
-template <int NR, int NC, bool WITH_G>
-__device__ __forceinline__ void small_eval_block(const DevTerm& T, int gf, const double* __restrict__ xk_s,
+// instruction latency, not throughput.  The continuous parameters are the same for every column of a restart: their share
+// of factor gf's squared distance is computed once per training row (rc_s) and the dims in `contmask` are skipped here.
+template <int NR, int NC>
+__device__ __forceinline__ void small_eval_block(const DevTerm& T, int gf, uint32_t contmask,
+                                                 const double* __restrict__ rc_s, const double* __restrict__ xk_s,
                                                  const int (&cols)[NC], const double* __restrict__ X_s,
-                                                 const int (&rows)[NR], double (&out)[NR][NC]) {
+                                                 const int (&rows)[NR], double (&kv)[NR][NC], double (&qv)[NR][NC]) {
 #pragma unroll
   for (int r = 0; r < NR; ++r)
 #pragma unroll
-    for (int c = 0; c < NC; ++c) out[r][c] = T.outputscale;
-  for (int f = 0; f < T.n_factors; ++f) {
+    for (int c = 0; c < NC; ++c) kv[r][c] = qv[r][c] = T.outputscale;
+  for (int f = 0; f < T.n_factors; ++f) {  // every factor is Matern-5/2 with power 1 or 2 (small_gen_setup)
     const DevFactor& F = T.f[f];
-    const bool matern = F.kind == PRB_FACTOR_MATERN52;
+    const bool grad_here = f == gf;
+    const bool squared = F.power == 2;
     double r2[NR][NC];
 #pragma unroll
-    for (int r = 0; r < NR; ++r)
+    for (int r = 0; r < NR; ++r) {
+      const double base = grad_here ? rc_s[rows[r]] : 0.0;
 #pragma unroll
-      for (int c = 0; c < NC; ++c) r2[r][c] = 0.0;
+      for (int c = 0; c < NC; ++c) r2[r][c] = base;
+    }
+#pragma unroll 1
     for (int di = 0; di < F.n_dims; ++di) {
       const int dim = F.dims[di];
+      if (grad_here && ((contmask >> dim) & 1u)) continue;
       const double ils = F.inv_ls[di];
       double xc[NC], xr[NR];
 #pragma unroll
@@ -144,29 +193,18 @@ __device__ __forceinline__ void small_eval_block(const DevTerm& T, int gf, const
       for (int r = 0; r < NR; ++r)
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-          if (matern) {
-            const double df = (xc[c] - xr[r]) * ils;
-            r2[r][c] = fma(df, df, r2[r][c]);
-          } else {
-            r2[r][c] += (xc[c] != xr[r]) ? ils : 0.0;
-          }
+          const double df = (xc[c] - xr[r]) * ils;
+          r2[r][c] = fma(df, df, r2[r][c]);
         }
     }
-    const bool grad_here = WITH_G && f == gf;
-    const double pw = (F.power > 1) ? double(F.power) : 1.0;
 #pragma unroll
     for (int r = 0; r < NR; ++r)
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        double v, G = 0.0;
-        if (matern)
-          v = matern52(r2[r][c], &G);
-        else
-          v = exp(-r2[r][c]);
-        if (grad_here)
-          out[r][c] *= (F.power > 1 ? pw * ipow(v, F.power - 1) : 1.0) * G;
-        else
-          out[r][c] *= ipow(v, F.power);
+        double G;
+        const double v = matern52_nb(r2[r][c], &G);
+        kv[r][c] *= squared ? v * v : v;
+        qv[r][c] *= grad_here ? (squared ? 2.0 * v * G : G) : (squared ? v * v : v);
       }
   }
 }
@@ -302,10 +340,14 @@ __global__ void __launch_bounds__(S_THREADS, 1)
       const int dim = dmref.dims[e >> 5];
       xk_s[dim * 32 + (e & 31)] = th_s[dim];
     }
+    double rc = 0.0;
     for (int c = 0; c < dmref.n; ++c) {
       const int dim = dmref.dims[c];
-      Dc_s[c * 128 + j] = (j < n) ? p.gw[c] * (th_s[dim] - X_s[dim * 128 + j]) : 0.0;
+      const double df = th_s[dim] - X_s[dim * 128 + j];
+      Dc_s[c * 128 + j] = (j < n) ? p.gw[c] * df : 0.0;
+      rc = fma(p.gw[c] * df, df, rc);
     }
+    kc_s[j] = rc;  // continuous share of factor gf's squared distance
   } else {
     // warps 4-7: the restart's continuous-factor values and derivatives for the 128 (padded) training points
     const int j = tid - 128;
@@ -330,6 +372,15 @@ __global__ void __launch_bounds__(S_THREADS, 1)
   __syncthreads();
 
   SMALL_TS(2);
+  // row ownership as in prb_gemm_tma.cu: M-warp wm owns the 8-row groups {wm, 7 - wm, 8 + wm, 15 - wm}
+  const int frag_r = lane >> 2, frag_k = lane & 3;
+  int grp[4];
+  grp[0] = wm;
+  grp[1] = 7 - wm;
+  grp[2] = 8 + wm;
+  grp[3] = 15 - wm;
+  [[maybe_unused]] double qk[4][4];  // GEN: gradient factor Q(row group i, column q) of this thread's accumulator entries
+
   // ---- 2. generate the B operand: k*[col, k] for the 32 columns x 4 nchunks k values -------------------------------------
   {
     // lane <-> (k within a chunk, 8 columns): a warp store covers 32 consecutive doubles of B_s (conflict-free)
@@ -337,20 +388,31 @@ __global__ void __launch_bounds__(S_THREADS, 1)
     const int col = (tid >> 2) & 31;
     const int chi = tid >> 7;  // chunks chi * 16 .. chi * 16 + 15
     if constexpr (GEN) {
-      // chunks interleaved over the two thread halves (c = 2 t + chi), 8 rows of one column per pass
-      const int cols1[1] = {col};
-      for (int t0 = 0; t0 < 16; t0 += 8) {
-        if (2 * t0 + chi >= p.nchunks) break;
-        int rws[8];
+      // Every thread evaluates exactly the (row, column) entries its accumulators own in the two products: the value goes
+      // to the B operand, the gradient factor Q stays in registers for the contraction after the upper product.
+      int cl[4];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) rws[t] = min(4 * (2 * (t0 + t) + chi) + k4, 127);
-        double kv[8][1];
-        small_eval_block<8, 1, false>(p.term, -1, xk_s, cols1, X_s, rws, kv);
+      for (int q = 0; q < 4; ++q) cl[q] = wn * 16 + 8 * (q >> 1) + 2 * frag_k + (q & 1);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const int c = 2 * (t0 + t) + chi;
-          if (c < 32) B_s[c * 128 + col * 4 + k4] = (4 * c + k4 < n) ? kv[t][0] : 0.0;
+      for (int h = 0; h < 2; ++h) {
+        const int rw[2] = {8 * grp[2 * h] + frag_r, 8 * grp[2 * h + 1] + frag_r};
+        double kv[2][4], qv[2][4];
+        if (8 * min(grp[2 * h], grp[2 * h + 1]) < n) {  // warp-uniform: skip row groups that are all padding
+          small_eval_block<2, 4>(p.term, p.gf, p.contmask, kc_s, xk_s, cl, X_s, rw, kv, qv);
+        } else {
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) kv[r][q] = qv[r][q] = 0.0;
         }
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int row = rw[r];
+            B_s[(row >> 2) * 128 + cl[q] * 4 + (row & 3)] = (row < n) ? kv[r][q] : 0.0;
+            qk[2 * h + r][q] = qv[r][q];
+          }
       }
     } else {
       const uint32_t zc = zb_s[col];
@@ -367,13 +429,6 @@ __global__ void __launch_bounds__(S_THREADS, 1)
   if (it == 0) mbar_wait(bar, 0);  // A1 stays resident for every later iteration
   SMALL_TS(4);
 
-  // row ownership as in prb_gemm_tma.cu: M-warp wm owns the 8-row groups {wm, 7 - wm, 8 + wm, 15 - wm}
-  const int frag_r = lane >> 2, frag_k = lane & 3;
-  int grp[4];
-  grp[0] = wm;
-  grp[1] = 7 - wm;
-  grp[2] = 8 + wm;
-  grp[3] = 15 - wm;
   const int fb_off = (wn * 16 + frag_r) * 4 + frag_k;
   const int rows_valid = n + 1;  // rows of A1 at or beyond this index are zero
 
@@ -508,18 +563,6 @@ __global__ void __launch_bounds__(S_THREADS, 1)
     int rows[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) rows[i] = 8 * grp[i] + frag_r;
-    double qk[4][4];  // GEN: Q(row i, column (j, e))
-    if constexpr (GEN) {
-      if (dmref.n > 0) {
-        int cl[4], rw[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          cl[q] = wn * 16 + 8 * (q >> 1) + 2 * frag_k + (q & 1);
-          rw[q] = rows[q];
-        }
-        small_eval_block<4, 4, true>(p.term, p.gf, xk_s, cl, X_s, rw, qk);
-      }
-    }
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -680,6 +723,8 @@ static bool small_gen_setup(const Model& m, const DevSpace& sp, DimMap* dm, int*
       sp.n_cont > S_MAXC || sp.n_disc > 32)
     return false;
   const DevTerm& T = m.spec.t[0];
+  for (int f = 0; f < T.n_factors; ++f)
+    if (T.f[f].kind != PRB_FACTOR_MATERN52 || T.f[f].power < 1 || T.f[f].power > 2) return false;
   int gf = -1;
   dm->n = sp.n_cont;
   for (int c = 0; c < sp.n_cont; ++c) {
@@ -689,7 +734,7 @@ static bool small_gen_setup(const Model& m, const DevSpace& sp, DimMap* dm, int*
     for (int f = 0; f < T.n_factors; ++f)
       for (int di = 0; di < T.f[f].n_dims; ++di)
         if (T.f[f].dims[di] == dim) {
-          if (T.f[f].kind != PRB_FACTOR_MATERN52 || (gf >= 0 && gf != f)) return false;
+          if (gf >= 0 && gf != f) return false;
           gf = f;
           ++hits;
           if (gw) gw[c] = T.f[f].inv_ls[di] * T.f[f].inv_ls[di];
@@ -733,6 +778,7 @@ static void fill_small_params(SmallStepParams& p, bool gen, const Model& m, cons
     DimMap dm2;
     small_gen_setup(m, sp, &dm2, &p.gf, p.gw);
     p.dm = dm2;
+    for (int c = 0; c < dm2.n; ++c) p.contmask |= 1u << dm2.dims[c];
   } else {
     p.cf = m.sep_cont_factor;
   }
