@@ -40,6 +40,12 @@ from .initializers import (  # noqa: F401
     initialize_q_batch_nonneg,
 )
 from .optimize import optimize_acqf, optimize_acqf_mixed  # noqa: F401
+from .rffs import (  # noqa: F401
+    RandomFourierFeatures,
+    RFFSampleModel,
+    get_gp_sample_w_transforms,
+    get_gp_samples,
+)
 from .trust_region import TurboState, trust_region_bounds, trust_region_center, update_state  # noqa: F401
 
 __version__ = "0.1.0"

@@ -28,7 +28,7 @@ PROFILE_SLOT_NAMES = ["pr_sample", "kstar_panel", "trgemm_lower", "acq_epilogue"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", os.environ.get("PRB_LIB_NAME", "libprb200.so"))
 
 EXPORTS = [
-    "prb_version", "prb_abi_sizeof", "prb_debug_small_timestamps", "prb_launch_count", "prb_profile_enable", "prb_profile_read", "prb_status_string", "prb_last_cuda_error", "prb_model_create", "prb_model_destroy", "prb_model_set_option",
+    "prb_version", "prb_abi_sizeof", "prb_debug_small_timestamps", "prb_launch_count", "prb_profile_enable", "prb_profile_read", "prb_status_string", "prb_last_cuda_error", "prb_model_create", "prb_rff_model_create", "prb_model_destroy", "prb_model_set_option",
     "prb_model_n", "prb_model_dk", "prb_workspace_bytes", "prb_philox_uniform", "prb_pr_sample",
     "prb_analytic_enumerate", "prb_kernel_matrix", "prb_acq_points",
     "prb_mc_value_grad", "prb_mc_screen", "prb_analytic_value_grad", "prb_mc_adam", "prb_analytic_adam",
@@ -93,6 +93,7 @@ def load_library() -> C.CDLL:
     lib.prb_status_string.argtypes = [C.c_int]
     lib.prb_last_cuda_error.restype = C.c_char_p
     lib.prb_model_create.argtypes = [C.POINTER(vp), C.POINTER(PrbModelDesc), vp]
+    lib.prb_rff_model_create.argtypes = [C.POINTER(vp), C.c_int32, C.c_int32, vp, vp, vp, C.c_double, vp]
     lib.prb_model_destroy.argtypes = [vp]
     lib.prb_model_set_option.argtypes = [vp, i32, i64]
     lib.prb_model_n.argtypes = [vp]

@@ -268,6 +268,11 @@ int run_engine(const Model& m, const DevAcq& aq, const Plan& pl, void* ws, const
   double* mu = at<double>(ws, pl.off_mu);
   double* S_part = at<double>(ws, pl.off_S_part);
 
+  if (m.rff_m > 0) {  // deterministic posterior sample: the acquisition value is the sample path itself (PosteriorMean)
+    if (aq.kind != PRB_ACQ_MEAN) return PRB_ERR_INVALID;
+    CUDA_TRY(launch_rff_eval(m, xk, B, diffmask, need_grad, a, S_all, out_mean, out_var, st));
+    return PRB_OK;
+  }
   for (int64_t c0 = 0; c0 < B; c0 += pl.C) {
     const int ncols = int(B - c0 < pl.C ? B - c0 : pl.C);
     const int ncols_pad = round_up(ncols, 128);
@@ -764,9 +769,54 @@ int prb_model_create(prb_model** out, const prb_model_desc* desc, void* stream) 
   return PRB_OK;
 }
 
+int prb_rff_model_create(prb_model** out, int32_t d_k, int32_t n_features, const double* W, const double* bias,
+                         const double* weights, double scale, void* stream) {
+  if (!out || d_k < 1 || n_features < 1 || !W || !bias || !weights) return PRB_ERR_INVALID;
+  if (d_k > PRB_MAX_DIMS) return PRB_ERR_UNSUPPORTED;
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return PRB_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "device %s is sm_%d%d; libprb200 is built for sm_100a only", prop.name,
+             prop.major, prop.minor);
+    return PRB_ERR_NO_DEVICE;
+  }
+  Model* m = new (std::nothrow) Model();
+  if (!m) return PRB_ERR_INVALID;
+  memset(m, 0, sizeof(Model));
+  // the plan arithmetic (workspace sizes) sees a one-point model; none of the GP buffers exists
+  m->n = 1;
+  m->d_k = d_k;
+  m->Kp = round_up(1, GEMM_BK);
+  m->Mp1 = GEMM_BM;
+  m->Mp2 = GEMM_BM;
+  m->device = dev;
+  m->spec.d_k = d_k;
+  m->rff_m = n_features;
+  m->rff_scale = scale;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t fm = size_t(n_features) * sizeof(double);
+  cudaError_t e;
+  if ((e = cudaMalloc(&m->rff_W, fm * d_k)) == cudaSuccess && (e = cudaMalloc(&m->rff_b, fm)) == cudaSuccess &&
+      (e = cudaMalloc(&m->rff_w, fm)) == cudaSuccess &&
+      (e = cudaMemcpyAsync(m->rff_W, W, fm * d_k, cudaMemcpyDeviceToDevice, st)) == cudaSuccess &&
+      (e = cudaMemcpyAsync(m->rff_b, bias, fm, cudaMemcpyDeviceToDevice, st)) == cudaSuccess)
+    e = cudaMemcpyAsync(m->rff_w, weights, fm, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) {
+    prb_model_destroy(reinterpret_cast<prb_model*>(m));
+    return cuda_fail(e, "prb_rff_model_create");
+  }
+  *out = reinterpret_cast<prb_model*>(m);
+  return PRB_OK;
+}
+
 int prb_model_destroy(prb_model* model) {
   if (!model) return PRB_OK;
   Model* m = reinterpret_cast<Model*>(model);
+  cudaFree(m->rff_W);
+  cudaFree(m->rff_b);
+  cudaFree(m->rff_w);
   cudaFree(m->A1);
   cudaFree(m->A2);
   cudaFree(m->Xtr);
@@ -860,6 +910,7 @@ int prb_acq_points(prb_model* model, const prb_acq_desc* acq, const double* xk, 
     for (int f = 0; f < m.spec.t[t].n_factors; ++f)
       if (m.spec.t[t].f[f].kind == PRB_FACTOR_MATERN52)
         for (int i = 0; i < m.spec.t[t].f[f].n_dims; ++i) mask |= 1u << m.spec.t[t].f[f].dims[i];
+  if (m.rff_m > 0) mask = m.d_k >= 32 ? 0xffffffffu : ((1u << m.d_k) - 1u);  // a feature map is smooth in every input
   return run_engine(m, aq, pl, workspace, xk, n_points, out_dacq_dx != nullptr, mask, a,
                     at<double>(workspace, pl.off_dmu), at<double>(workspace, pl.off_dvar), out_dacq_dx, out_mean,
                     out_var, st);
@@ -1038,7 +1089,7 @@ int prb_mc_adam(prb_model* model, const prb_space_desc* space, const prb_acq_des
   }
 
   // kernel structures that do not separate: the six-launch fused step on a single column panel
-  const bool generic_fused = !fused_step && !small_step && int64_t(b) * mc <= pl.C && !sep_space &&
+  const bool generic_fused = !fused_step && !small_step && m.rff_m == 0 && int64_t(b) * mc <= pl.C && !sep_space &&
                              getenv("PRB_NO_FUSED_STEP") == nullptr;
 
   auto one_iter = [&]() -> int {

@@ -161,6 +161,13 @@ struct Model {
   uint32_t* Zbits;                      // [max(Mp1, Mp2)] bit codes of the training points
   double* sep_tab;                      // [64] binary-factor value by Hamming distance
   int opt_dedup;                        // PRB_OPT_DEDUP
+  // random-Fourier-feature posterior sample (prb_rff_model_create): f(x) = rff_scale * sum_j rff_w[j] cos(x . W[:, j] + b_j);
+  // rff_m > 0 marks the model as deterministic -- no GP state, every engine call goes to rff_eval_kernel
+  int rff_m;
+  double* rff_W;  // [d_k, m]
+  double* rff_b;  // [m]
+  double* rff_w;  // [m]
+  double rff_scale;
 };
 
 constexpr int DEDUP_MAX_BITS = 12;  // histogram de-duplication: 2^12 bins of shared memory per restart

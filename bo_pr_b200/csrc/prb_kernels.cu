@@ -392,6 +392,75 @@ cudaError_t launch_acq_epilogue(const Model& m, const DevAcq& aq, const double* 
 }
 
 // =====================================================================================================================
+// Random-Fourier-feature posterior sample (Thompson sampling, `pr__ts`):  f(x) = scale * sum_j w_j cos(x . W[:, j] + b_j)
+//   reference: rffs.py:24-133 (get_gp_samples -> deterministic model) under PosteriorMean (experiment_utils.py:481-492);
+//   the feature map is BoTorch's RandomFourierFeatures [3P]: cos((x / l) @ omega + b) * sqrt(2 outputscale / m), with the
+//   lengthscales folded into W by the host.  One warp per evaluation point, lanes stride over the features (W is [d_k, m]:
+//   coalesced), gradient  df/dx_c = -scale * sum_j w_j sin(.) W[c, j]  for the dims in `diffmask`, 8 dims per pass.
+// =====================================================================================================================
+constexpr int RFF_WARPS = 8;
+__global__ void __launch_bounds__(RFF_WARPS * 32) rff_eval_kernel(const double* __restrict__ W, const double* __restrict__ bias,
+                                                                  const double* __restrict__ w, int m, int d_k,
+                                                                  double scale, const double* __restrict__ xk,
+                                                                  int64_t ncols, uint32_t diffmask, int need_grad,
+                                                                  double* __restrict__ a, double* __restrict__ S_all,
+                                                                  double* __restrict__ out_mean,
+                                                                  double* __restrict__ out_var) {
+  __shared__ double xs[RFF_WARPS][PRB_MAX_DIMS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t col = int64_t(blockIdx.x) * RFF_WARPS + warp;
+  if (col >= ncols) return;
+  if (lane < d_k) xs[warp][lane] = xk[size_t(col) * d_k + lane];
+  __syncwarp();
+  const double* x = xs[warp];
+  int dims[PRB_MAX_DIMS];
+  int nd = 0;
+  if (need_grad)
+    for (int c = 0; c < d_k; ++c)
+      if ((diffmask >> c) & 1u) dims[nd++] = c;
+  double f = 0.0;
+  for (int pass = 0; pass == 0 || pass * 8 < nd; ++pass) {
+    double g[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int j = lane; j < m; j += 32) {
+      double ph = bias[j];
+      for (int c = 0; c < d_k; ++c) ph = fma(x[c], W[size_t(c) * m + j], ph);
+      double sn, cs;
+      sincos(ph, &sn, &cs);
+      const double wj = w[j];
+      if (pass == 0) f = fma(wj, cs, f);
+      const double ws = -wj * sn;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (pass * 8 + q < nd) g[q] = fma(ws, W[size_t(dims[pass * 8 + q]) * m + j], g[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (pass * 8 + q < nd) {
+        const double t = warp_sum(g[q]);
+        if (lane == 0) S_all[size_t(col) * d_k + dims[pass * 8 + q]] = scale * t;
+      }
+    }
+  }
+  f = scale * warp_sum(f);
+  if (lane == 0) {
+    if (a) a[col] = f;
+    if (out_mean) out_mean[col] = f;
+    if (out_var) out_var[col] = 0.0;
+  }
+}
+
+cudaError_t launch_rff_eval(const Model& m, const double* xk, int64_t ncols, uint32_t diffmask, bool need_grad, double* a,
+                            double* S_all, double* out_mean, double* out_var, cudaStream_t st) {
+  ProfScope prof_(K_KSTAR, st);
+  if (ncols == 0) return cudaSuccess;
+  const unsigned grid = unsigned((ncols + RFF_WARPS - 1) / RFF_WARPS);
+  rff_eval_kernel<<<grid, RFF_WARPS * 32, 0, st>>>(m.rff_W, m.rff_b, m.rff_w, m.rff_m, m.d_k, m.rff_scale, xk, ncols, diffmask,
+                                                  need_grad ? 1 : 0, a, S_all, out_mean, out_var);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// =====================================================================================================================
 // Pathwise-gradient contraction:  S[col, dim] = sum_j C_j(col) * d k*_j(col) / d x_dim ,
 //   C_j = dA/dmu * alpha_j - 2 dA/dsigma^2 * W[j, col]      (W = Linv^T Linv k* = K^-1 k*)
 //   reference: torch.autograd.grad(mean_acq_values, cont_input) through the GP posterior

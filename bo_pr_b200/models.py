@@ -40,42 +40,14 @@ def _fill_model_desc(desc: capi.PrbModelDesc, terms: Sequence[TermT], n: int, d_
                 F.dims[i], F.lengthscale[i] = int(dd), float(l)
 
 
-class GPState:
-    """Device-resident exact-GP caches + the ``prb_model`` handle.  One per (model, BO iteration)."""
+class DeviceState:
+    """A ``prb_model`` handle plus the per-model caches every entry point needs (workspace, options)."""
 
-    def __init__(self, train_X: Tensor, train_Y: Tensor, terms: Sequence[TermT], noise, mean_const: float):
-        capi.require_cuda(train_X, "train_X")
+    def _init_common(self, device: torch.device, d_k: int) -> None:
         self.lib = capi.load_library()
-        self.device = train_X.device
-        X = train_X.detach().to(torch.float64).contiguous()
-        y = train_Y.detach().to(device=self.device, dtype=torch.float64).reshape(-1).contiguous()
-        n, d_k = X.shape
-        if d_k > capi.PRB_MAX_DIMS:
-            raise NotImplementedError(f"kernel-input dimension {d_k} > {capi.PRB_MAX_DIMS}")
-        self.n, self.d_k = n, d_k
-        self.terms = list(terms)
-        self.mean_const = float(mean_const)
-        self.X_train, self.train_Y = X, y
-        noise = torch.as_tensor(noise, dtype=torch.float64, device=self.device).reshape(-1)
-        self.noise = noise.expand(n).contiguous() if noise.numel() == 1 else noise.contiguous()
-        with torch.cuda.device(self.device):
-            stream = torch.cuda.current_stream().cuda_stream
-            desc = capi.PrbModelDesc()
-            _fill_model_desc(desc, self.terms, n, d_k)
-            desc.X_train = X.data_ptr()
-            K = torch.empty(n, n, dtype=torch.float64, device=self.device)
-            capi.check(self.lib.prb_kernel_matrix(C.byref(desc), X.data_ptr(), n, K.data_ptr(), stream),
-                       "prb_kernel_matrix")
-            K.diagonal().add_(self.noise)
-            L = torch.linalg.cholesky(K)
-            self.Linv = torch.linalg.solve_triangular(
-                L, torch.eye(n, dtype=torch.float64, device=self.device), upper=False).contiguous()
-            self.alpha = torch.cholesky_solve((y - self.mean_const).unsqueeze(-1), L).squeeze(-1).contiguous()
-            desc.Linv, desc.alpha, desc.mean_const = self.Linv.data_ptr(), self.alpha.data_ptr(), self.mean_const
-            handle = C.c_void_p()
-            capi.check(self.lib.prb_model_create(C.byref(handle), C.byref(desc), stream), "prb_model_create")
-        self.handle = handle
-        self._desc = desc
+        self.device = device
+        self.d_k = int(d_k)
+        self.handle = C.c_void_p()
         self._ws: Optional[Tensor] = None
         self._ws_need = {}
         self._ones: Optional[Tensor] = None
@@ -131,6 +103,65 @@ class GPState:
                                                capi.ptr(mean), capi.ptr(var), capi.ptr(grad), ws.data_ptr(),
                                                ws.numel(), int(self.chunk_cols), st), "prb_acq_points")
         return out, mean, var, grad
+
+
+class RFFState(DeviceState):
+    """Device copy of one random-Fourier-feature posterior sample ``f(x) = scale * cos(x W + b) . w`` (``prb_rff_model_create``)."""
+
+    def __init__(self, W: Tensor, bias: Tensor, weights: Tensor, scale: float):
+        capi.require_cuda(W, "W")
+        self._init_common(W.device, W.shape[0])
+        self.W = W.detach().to(torch.float64).contiguous()
+        self.bias = bias.detach().to(device=W.device, dtype=torch.float64).reshape(-1).contiguous()
+        self.weights = weights.detach().to(device=W.device, dtype=torch.float64).reshape(-1).contiguous()
+        self.scale = float(scale)
+        m = self.W.shape[1]
+        if self.bias.numel() != m or self.weights.numel() != m:
+            raise ValueError("W [d, m], bias [m] and weights [m] do not agree")
+        if self.d_k > capi.PRB_MAX_DIMS:
+            raise NotImplementedError(f"input dimension {self.d_k} > {capi.PRB_MAX_DIMS}")
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            capi.check(self.lib.prb_rff_model_create(C.byref(self.handle), self.d_k, m, self.W.data_ptr(),
+                                                     self.bias.data_ptr(), self.weights.data_ptr(), self.scale, stream),
+                       "prb_rff_model_create")
+
+
+class GPState(DeviceState):
+    """Device-resident exact-GP caches + the ``prb_model`` handle.  One per (model, BO iteration)."""
+
+    def __init__(self, train_X: Tensor, train_Y: Tensor, terms: Sequence[TermT], noise, mean_const: float):
+        capi.require_cuda(train_X, "train_X")
+        self._init_common(train_X.device, train_X.shape[-1])
+        X = train_X.detach().to(torch.float64).contiguous()
+        y = train_Y.detach().to(device=self.device, dtype=torch.float64).reshape(-1).contiguous()
+        n, d_k = X.shape
+        if d_k > capi.PRB_MAX_DIMS:
+            raise NotImplementedError(f"kernel-input dimension {d_k} > {capi.PRB_MAX_DIMS}")
+        self.n, self.d_k = n, d_k
+        self.terms = list(terms)
+        self.mean_const = float(mean_const)
+        self.X_train, self.train_Y = X, y
+        noise = torch.as_tensor(noise, dtype=torch.float64, device=self.device).reshape(-1)
+        self.noise = noise.expand(n).contiguous() if noise.numel() == 1 else noise.contiguous()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            desc = capi.PrbModelDesc()
+            _fill_model_desc(desc, self.terms, n, d_k)
+            desc.X_train = X.data_ptr()
+            K = torch.empty(n, n, dtype=torch.float64, device=self.device)
+            capi.check(self.lib.prb_kernel_matrix(C.byref(desc), X.data_ptr(), n, K.data_ptr(), stream),
+                       "prb_kernel_matrix")
+            K.diagonal().add_(self.noise)
+            L = torch.linalg.cholesky(K)
+            self.Linv = torch.linalg.solve_triangular(
+                L, torch.eye(n, dtype=torch.float64, device=self.device), upper=False).contiguous()
+            self.alpha = torch.cholesky_solve((y - self.mean_const).unsqueeze(-1), L).squeeze(-1).contiguous()
+            desc.Linv, desc.alpha, desc.mean_const = self.Linv.data_ptr(), self.alpha.data_ptr(), self.mean_const
+            handle = C.c_void_p()
+            capi.check(self.lib.prb_model_create(C.byref(handle), C.byref(desc), stream), "prb_model_create")
+        self.handle = handle
+        self._desc = desc
 
 
 class _ConstantMean:
@@ -208,7 +239,7 @@ class FixedNoiseGP(Model):
 def gp_state_from_model(model) -> GPState:
     """GP state of one of our models, or of a duck-typed BoTorch ``FixedNoiseGP``/``SingleTaskGP`` in eval mode
     (``train_inputs[0]``, ``train_targets``, ``mean_module.constant``, ``likelihood.noise``, ``covar_module`` tree)."""
-    if isinstance(model, FixedNoiseGP):
+    if isinstance(model, FixedNoiseGP) or isinstance(getattr(model, "state", None), DeviceState):
         return model.state
     for attr in ("input_transform", "outcome_transform"):
         if getattr(model, attr, None) is not None:

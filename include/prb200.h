@@ -138,6 +138,14 @@ const char* prb_last_cuda_error(void);
  * BO iteration.  Replaces: the caches behind model.posterior() that acq_function(X) reads
  * (probabilistic_reparameterization.py:314, 491; [3P] gpytorch exact prediction strategy).                       */
 int prb_model_create(prb_model** out, const prb_model_desc* desc, void* stream);
+/* A deterministic posterior SAMPLE as the model (Thompson sampling, label `pr__ts`):
+ *   f(x) = scale * sum_j weights[j] * cos(x . W[:, j] + bias[j]),   W [d_k, n_features] row-major (lengthscales folded in),
+ * used with PRB_ACQ_MEAN in every entry point that takes a prb_model (other acquisition kinds return PRB_ERR_INVALID).
+ * Replaces: the GenericDeterministicModel built by get_gp_samples / get_gp_sample_w_transforms (rffs.py:24-133) from
+ * BoTorch's RandomFourierFeatures ([3P]) and evaluated under PosteriorMean (experiment_utils.py:481-492).  All pointers
+ * are device memory and are copied.                                                                                   */
+int prb_rff_model_create(prb_model** out, int32_t d_k, int32_t n_features, const double* W, const double* bias,
+                         const double* weights, double scale, void* stream);
 int prb_model_destroy(prb_model* model);
 /* Per-model options.
  * PRB_OPT_DEDUP (default 0): in prb_mc_value_grad / prb_mc_adam on the separable kernel structure (Matern over continuous

@@ -118,3 +118,37 @@ def test_small_step_paths_match_host_loop(b, mc, n):
     assert torch.allclose(cand_f, cand_h, rtol=0, atol=1e-10), (cand_f - cand_h).abs().max()
     assert torch.allclose(val_f, val_h, rtol=1e-8, atol=1e-12)
     assert torch.allclose(pr_f._ma_state, pr_h._ma_state, rtol=1e-9, atol=0)
+
+
+@pytest.mark.parametrize("name,n,mc", [("rosenbrock10_ucb", 150, 64), ("mixed_int_f1_ei", 131, 48), ("rosenbrock10_ucb", 90, 40)])
+def test_generic_fused_step_matches_host_loop_and_oracle(name, n, mc):
+    """Kernels that do not separate, outside the single-kernel limits (n + 1 > 128 or mc not a multiple of 32): the
+    six-launch fused step replayed from a graph, the host-driven loop and the oracle follow one trajectory."""
+    from tests.random_cases import build_problem
+
+    c = dict(load(name)["case"], n_train=n, mc=mc, b=4, seed=11)
+    g = build_problem(c)
+    d = c["dim"]
+    bounds = _bounds(d)
+    ics = g["theta"].to(DEV)
+    steps = 6
+    pr_f = product_mc_pr(g, DEV)
+    cand_f, val_f = B.gen_candidates_torch(ics, pr_f, bounds[0], bounds[1], options={"maxiter": steps})
+    pr_h = product_mc_pr(g, DEV)
+    cand_h, val_h = B.gen_candidates_torch(ics, pr_h, bounds[0], bounds[1], options={"maxiter": steps, "fused": False})
+    assert torch.allclose(cand_f, cand_h, rtol=0, atol=1e-10), (cand_f - cand_h).abs().max()
+    assert torch.allclose(val_f, val_h, rtol=1e-8, atol=1e-12)
+    assert torch.allclose(pr_f._ma_state, pr_h._ma_state, rtol=1e-9, atol=0)
+    space, oacq = oracle_space(g), oracle_acq(g)
+    st = {"c": 0.0, "h": 0.0}
+
+    def vg(X, with_grad=True):
+        r = P.mc_pr(space, X, oacq, g["base_samples"], g["base_samples_categorical"],
+                    grad_estimator=c["grad_estimator"], ma_counter=st["c"], ma_hidden=st["h"], with_grad=with_grad)
+        st["c"], st["h"] = r.ma_counter, r.ma_hidden
+        return (r.value, r.grad) if with_grad else r.value
+
+    theta_o, val_o = P.adam_multistart(vg, lambda X: vg(X, False), g["theta"], torch.zeros(d, dtype=torch.float64),
+                                       torch.ones(d, dtype=torch.float64), maxiter=steps)
+    assert torch.allclose(cand_f.cpu(), theta_o, rtol=0, atol=1e-8), (cand_f.cpu() - theta_o).abs().max()
+    assert torch.allclose(val_f.cpu(), val_o, rtol=1e-7, atol=1e-11)
