@@ -19,7 +19,13 @@
 // 8 warps of 32 x 64 (246-254 registers, 1 CTA/SM) beat 16 warps of 32 x 32 (128 registers): 4.49 vs 4.79 ms per step;
 // two 4-warp CTAs per SM with 64-column tiles (same 32 x 64 warp tile) beat one 8-warp CTA by 1-2 % (4.41 vs 4.46 ms);
 // routing the whole last row tile through the masked (diagonal) body to skip its all-padding row groups costs more than
-// the 1.5 % of DMMAs it saves (4.55 vs 4.46 ms).
+// the 1.5 % of DMMAs it saves (4.55 vs 4.46 ms).  Diagonal k-tiles (22 % of the k-tiles at n = 1000, 0.53 of a full
+// tile's DMMAs) cost 0.63 of a full k-tile in warp time (ncu source page): predicating the DMMAs instead of branching
+// around them is slower (4.73 vs 4.40 ms: every predicated DMMA gets its own WARPSYNC), and dispatching each k-tile to
+// one of nine branch-free bodies specialised on the warp's activity pattern changes nothing (4.41 ms) -- what remains
+// per row tile is the CTA prologue / epilogue (~7 % of warp time), not the masked body.  One warp per sub-partition
+// already reaches 97 % of the DMMA peak from registers (tools/microbench/dmma_occupancy.cu), so two 4-warp CTAs per SM
+// cover each other's epilogues.
 //
 // Four modes (template):
 //   LOWER_GEN   the B operand k*[col, k] = kc[b(col), k] * tab[popc(z[col] ^ Z[k])] is GENERATED into shared memory by the
