@@ -25,7 +25,12 @@
 // one of nine branch-free bodies specialised on the warp's activity pattern changes nothing (4.41 ms) -- what remains
 // per row tile is the CTA prologue / epilogue (~7 % of warp time), not the masked body.  One warp per sub-partition
 // already reaches 97 % of the DMMA peak from registers (tools/microbench/dmma_occupancy.cu), so two 4-warp CTAs per SM
-// cover each other's epilogues.
+// cover each other's epilogues.  A persistent variant (2 CTAs per SM striding over the heavy-first tile list, mbarrier
+// pipeline kept alive across tiles, next tile's first TMA loads issued before the epilogue, separate epilogue scratch) was
+// built and measured SLOWER: 4.59 ms, and 4.52 ms for the same restructured code launched one tile per CTA -- the
+// hardware's own CTA dispatch de-synchronises the two CTAs of an SM, whereas persistent CTAs walk equally long tiles in
+// lockstep and hit their epilogues together.  A persistent version needs a deliberate half-tile phase shift between the
+// two CTAs of an SM (or a dynamic tile queue) to pay.
 //
 // Four modes (template):
 //   LOWER_GEN   the B operand k*[col, k] = kc[b(col), k] * tab[popc(z[col] ^ Z[k])] is GENERATED into shared memory by the
