@@ -556,20 +556,11 @@ int mc_core(prb_model* model, const DevSpace& sp, const DevAcq& aq, const Plan& 
 // clamp -> value + gradient -> Adam, `maxiter` times, then the final clamp and value-only evaluation (gen.py:304-343).  One
 // step is captured into a CUDA graph and replayed; `core(X, grad_ones_or_null, value_out, grad_out_or_null)` enqueues one
 // evaluation of the acquisition function on `st`.
-template <typename Core>
-int adam_graph_loop(Core core, double* theta, const double* lower, const double* upper, int b, int d, double lr, int maxiter,
-                    int step0, double* adam_state, double* out_value, double* Xc, double* grad, double* ones, double* val,
-                    int* step, cudaStream_t st) {
-  const int total = b * d;
-  CUDA_TRY(launch_fill(ones, 1.0, b, st));
-  CUDA_TRY(cudaMemcpyAsync(step, &step0, sizeof(int), cudaMemcpyHostToDevice, st));
-  auto one_iter = [&]() -> int {
-    CUDA_TRY(launch_clamp(theta, lower, upper, b, d, Xc, st));
-    int r = core(Xc, ones, val, grad);
-    if (r != PRB_OK) return r;
-    CUDA_TRY(launch_adam_step(theta, grad, adam_state, adam_state + total, total, lr, step, st));
-    return PRB_OK;
-  };
+// Run `one_iter` maxiter times: captured once into a CUDA graph and replayed when the caller gave a real stream (removes the
+// per-launch host latency: the reference spends its time exactly there at experiment sizes, 800 host-driven steps per BO
+// iteration), else as plain launches.
+template <typename Iter>
+int replay_steps(Iter one_iter, int maxiter, cudaStream_t st) {
   bool graphed = false;
   if (st != nullptr && maxiter >= 4) {
     cudaGraph_t graph = nullptr;
@@ -601,6 +592,25 @@ int adam_graph_loop(Core core, double* theta, const double* lower, const double*
       if (rc != PRB_OK) return rc;
     }
   }
+  return PRB_OK;
+}
+
+template <typename Core>
+int adam_graph_loop(Core core, double* theta, const double* lower, const double* upper, int b, int d, double lr, int maxiter,
+                    int step0, double* adam_state, double* out_value, double* Xc, double* grad, double* ones, double* val,
+                    int* step, cudaStream_t st) {
+  const int total = b * d;
+  CUDA_TRY(launch_fill(ones, 1.0, b, st));
+  CUDA_TRY(cudaMemcpyAsync(step, &step0, sizeof(int), cudaMemcpyHostToDevice, st));
+  auto one_iter = [&]() -> int {
+    CUDA_TRY(launch_clamp(theta, lower, upper, b, d, Xc, st));
+    int r = core(Xc, ones, val, grad);
+    if (r != PRB_OK) return r;
+    CUDA_TRY(launch_adam_step(theta, grad, adam_state, adam_state + total, total, lr, step, st));
+    return PRB_OK;
+  };
+  int rc = replay_steps(one_iter, maxiter, st);
+  if (rc != PRB_OK) return rc;
   CUDA_TRY(launch_clamp(theta, lower, upper, b, d, theta, st));
   return core(theta, nullptr, out_value, nullptr);
 }
@@ -1021,6 +1031,63 @@ int prb_analytic_adam(prb_model* model, const prb_space_desc* space, const prb_a
   double* probs = at<double>(workspace, pl.off_probs);
   double* a = at<double>(workspace, pl.off_a);
   double* S_all = at<double>(workspace, pl.off_S_all);
+  // One column panel and a GP model: a step is seven launches (six with a single row tile) -- clamp + enumeration, k* panel,
+  // lower product [+ acquisition epilogue], upper product, gradient contraction, reduction + row-block sums + Adam.
+  if (B <= pl.C && m.rff_m == 0 && getenv("PRB_NO_FUSED_STEP") == nullptr) {
+    const int ncols = int(B), ncols_pad = round_up(int(B), 128), total = b * sp.d;
+    double* panelA = at<double>(workspace, pl.off_panelA);
+    double* panelV = at<double>(workspace, pl.off_panelV);
+    double* norm = at<double>(workspace, pl.off_norm);
+    double* mu = at<double>(workspace, pl.off_mu);
+    double* S_part = at<double>(workspace, pl.off_S_part);
+    double* dmu = at<double>(workspace, pl.off_dmu);
+    double* dvar = at<double>(workspace, pl.off_dvar);
+    double* Xc = at<double>(workspace, pl.off_Xc);
+    double* grad = at<double>(workspace, pl.off_grad);
+    double* ones = at<double>(workspace, pl.off_ones);
+    double* val = at<double>(workspace, pl.off_val);
+    int* step = at<int>(workspace, pl.off_step);
+    unsigned int* done = at<unsigned int>(workspace, pl.off_done);
+    CUDA_TRY(launch_fill(ones, 1.0, b, st));
+    CUDA_TRY(cudaMemcpyAsync(step, &step0, sizeof(int), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(done, 0, sizeof(unsigned int), st));
+    auto fused = [&](bool with_grad, double* value_out) -> int {
+      const double* X = theta;
+      if (with_grad) {  // X = clamp(theta) written to Xc by the enumeration kernel
+        CUDA_TRY(launch_analytic_build(sp, theta, b, n_options, options, xk, probs, st, lower, upper, Xc));
+        X = Xc;
+      } else {  // final evaluation (gen.py:338-341): theta itself is clamped
+        CUDA_TRY(launch_clamp(theta, lower, upper, b, sp.d, theta, st));
+        CUDA_TRY(launch_analytic_build(sp, theta, b, n_options, options, xk, probs, st));
+      }
+      const bool need_path = with_grad && sp.n_cont > 0;
+      CUDA_TRY(launch_kstar_panel(m, xk, ncols, ncols_pad, panelA, st));
+      FusedAcq fa;
+      fa.aq = aq;
+      fa.a = a;
+      fa.dmu = dmu;
+      fa.dvar = dvar;
+      fa.ncols = ncols;
+      const bool fuse = m.Mp1 == GEMM_BM;
+      CUDA_TRY(launch_tma_lower(m, panelA, pl.C, ncols_pad, need_path ? panelV : nullptr, norm, mu, fuse ? &fa : nullptr,
+                                st));
+      if (!fuse)
+        CUDA_TRY(launch_acq_epilogue(m, aq, norm, ncols_pad, mu, ncols, a, dmu, dvar, nullptr, nullptr, nullptr, 0, st));
+      if (need_path) {
+        CUDA_TRY(launch_tma_upper(m, panelV, pl.C, ncols_pad, panelA, st));
+        CUDA_TRY(launch_grad_contract(m, cont_mask(sp), xk, ncols, ncols_pad, panelA, dmu, dvar, S_part, pl.grad_jrows,
+                                      st));
+      }
+      CUDA_TRY(launch_analytic_reduce(sp, X, b, n_options, options, a, probs, nullptr, with_grad ? ones : nullptr,
+                                      value_out, with_grad ? grad : nullptr, st, need_path ? S_part : nullptr,
+                                      m.Mp2 / pl.grad_jrows, ncols_pad, with_grad ? theta : nullptr, adam_state,
+                                      adam_state + total, lr, step, done));
+      return PRB_OK;
+    };
+    rc = replay_steps([&]() -> int { return fused(true, val); }, maxiter, st);
+    if (rc != PRB_OK) return rc;
+    return fused(false, out_value);
+  }
   auto core = [&](const double* X, const double* go, double* value, double* g) -> int {
     CUDA_TRY(launch_analytic_build(sp, X, b, n_options, options, xk, probs, st));
     const bool need_path = go != nullptr && sp.n_cont > 0;

@@ -106,25 +106,34 @@ cudaError_t launch_pr_sample(const DevSpace& sp, const double* theta, int b, int
 // (input.py:466-488 + Normalize + OneHotToNumeric) and P(z | theta) (input.py:410-464).
 // options [n_opt, n_int + n_cat]: un-normalised integer value / category index.
 // =====================================================================================================================
+// Optional fused clamp (prb_analytic_adam): theta is clamped to [lower, upper] on the fly and configuration 0 of every
+// restart writes the clamped row to Xc (which may alias theta only if no other thread still reads the raw row: the fused
+// step passes a separate buffer, the final evaluation clamps in a launch of its own).
 __global__ void analytic_build_kernel(const DevSpace sp, const double* __restrict__ theta, int b, int n_opt,
                                       const int32_t* __restrict__ options, double* __restrict__ xk,
-                                      double* __restrict__ probs) {
+                                      double* __restrict__ probs, const double* __restrict__ lower,
+                                      const double* __restrict__ upper, double* __restrict__ Xc) {
   const int64_t col = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (col >= int64_t(b) * n_opt) return;
   const int bi = int(col / n_opt);
   const int o = int(col % n_opt);
-  const double* th = theta + size_t(bi) * sp.d;
+  auto th = [&](int c) -> double {
+    const double v = theta[size_t(bi) * sp.d + c];
+    return lower ? fmin(fmax(v, lower[c]), upper[c]) : v;
+  };
+  if (Xc && o == 0)
+    for (int c = 0; c < sp.d; ++c) Xc[size_t(bi) * sp.d + c] = th(c);
   const int32_t* op = options + size_t(o) * (sp.n_int + sp.n_cat);
   double* xr = xk ? xk + size_t(col) * sp.d_k : nullptr;
   const int numeric_start = sp.n_cat > 0 ? sp.cat_start[0] : sp.d;
   if (xr)
     for (int c = 0; c < sp.d; ++c)
-      if (!sp.apply_numeric || c < numeric_start) xr[c] = th[c];
+      if (!sp.apply_numeric || c < numeric_start) xr[c] = th(c);
   double P = 1.0;
   for (int k = 0; k < sp.n_int; ++k) {
     const int c = sp.int_cols[k];
     const double lo = sp.int_lo[k], hi = sp.int_hi[k];
-    const double x_un = sp.raw_int ? th[c] : unnormalize_int(th[c], lo, hi);
+    const double x_un = sp.raw_int ? th(c) : unnormalize_int(th(c), lo, hi);
     double off;
     const double p = int_round_prob(x_un, sp.tau, &off);
     const double zv = double(op[k]);
@@ -137,10 +146,10 @@ __global__ void analytic_build_kernel(const DevSpace sp, const double* __restric
     const int s = sp.cat_start[j], card = sp.cat_card[j];
     const int cat = op[sp.n_int + j];
     double mx = -1e300;
-    for (int k = 0; k < card; ++k) mx = fmax(mx, __dsub_rn(th[s + k], 0.5) / sp.tau);
+    for (int k = 0; k < card; ++k) mx = fmax(mx, __dsub_rn(th(s + k), 0.5) / sp.tau);
     double sum = 0.0, sel = 0.0;
     for (int k = 0; k < card; ++k) {
-      const double e = exp(__dsub_rn(__dsub_rn(th[s + k], 0.5) / sp.tau, mx));
+      const double e = exp(__dsub_rn(__dsub_rn(th(s + k), 0.5) / sp.tau, mx));
       sum += e;
       if (k == cat) sel = e;
     }
@@ -157,11 +166,13 @@ __global__ void analytic_build_kernel(const DevSpace sp, const double* __restric
 }
 
 cudaError_t launch_analytic_build(const DevSpace& sp, const double* theta, int b, int n_opt, const int32_t* options,
-                                  double* xk, double* probs, cudaStream_t st) {
+                                  double* xk, double* probs, cudaStream_t st, const double* lower, const double* upper,
+                                  double* Xc) {
   ProfScope prof_(K_ANALYTIC, st);
   const int64_t total = int64_t(b) * n_opt;
   if (total == 0) return cudaSuccess;
-  analytic_build_kernel<<<unsigned((total + 127) / 128), 128, 0, st>>>(sp, theta, b, n_opt, options, xk, probs);
+  analytic_build_kernel<<<unsigned((total + 127) / 128), 128, 0, st>>>(sp, theta, b, n_opt, options, xk, probs, lower,
+                                                                       upper, Xc);
   count_launch();
   return cudaGetLastError();
 }
@@ -899,14 +910,24 @@ cudaError_t launch_ma_update(const double* value, int b, double* ma_state, cudaS
 __global__ void __launch_bounds__(REDUCE_THREADS) analytic_reduce_kernel(
     const DevSpace sp, const double* __restrict__ theta, int n_opt, const int32_t* __restrict__ options,
     const double* __restrict__ a, const double* __restrict__ probs, const double* __restrict__ S_all,
-    const double* __restrict__ grad_out, double* __restrict__ out_value, double* __restrict__ out_grad) {
+    const double* __restrict__ grad_out, double* __restrict__ out_value, double* __restrict__ out_grad,
+    const double* __restrict__ S_part, int jblocks, int ncols_pad, double* __restrict__ adam_theta,
+    double* __restrict__ adam_m, double* __restrict__ adam_v, double lr, int* __restrict__ step_ptr,
+    unsigned int* __restrict__ done) {
   // one CTA per restart; per-restart factor tables first, then one WARP per output (value, continuous columns, integer
   // columns, one-hot columns): lane-strided sums over the configurations + xor tree, fixed order => deterministic
   __shared__ double p_int[PRB_MAX_DIMS], dp_int[PRB_MAX_DIMS], off_int[PRB_MAX_DIMS];
   __shared__ double sm_cat[PRB_MAX_CAT * PRB_MAX_CARD];
+  __shared__ double csum[PRB_MAX_DIMS][4];
+  __shared__ int last_s;
   const int bi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t c0 = size_t(bi) * n_opt;
   const double* th = theta + size_t(bi) * sp.d;
+  // fused step (S_part != NULL): the row-block partial sums of the gradient contraction are added up here, split over
+  // nsplit warps per continuous column; the pre-step optimiser state is read before this CTA signals completion
+  const int nsplit = (S_part != nullptr && jblocks >= 8) ? 4 : 1;
+  const int jb_per = (jblocks + nsplit - 1) / nsplit;
+  const double t_step = step_ptr ? double(*step_ptr + 1) : 1.0;
   if (grad_out) {
     if (tid < sp.n_int) {
       const double lo = sp.int_lo[tid], hi = sp.int_hi[tid];
@@ -939,21 +960,32 @@ __global__ void __launch_bounds__(REDUCE_THREADS) analytic_reduce_kernel(
   const int nv = sp.n_int + sp.n_cat;
   int n_onehot = 0;
   for (int j = 0; j < sp.n_cat; ++j) n_onehot += sp.cat_card[j];
-  const int n_tasks = grad_out ? 1 + sp.n_cont + sp.n_int + n_onehot : 1;
+  const int n_cont_tasks = sp.n_cont * nsplit;
+  const int n_tasks = grad_out ? 1 + n_cont_tasks + sp.n_int + n_onehot : 1;
   for (int task = warp; task < n_tasks; task += REDUCE_THREADS / 32) {
     double t = 0.0;
     if (task == 0) {
       for (int o = lane; o < n_opt; o += 32) t += a[c0 + o] * probs[c0 + o];
       t = warp_sum(t);
       if (lane == 0) out_value[bi] = t;
-    } else if (task <= sp.n_cont) {
-      const int c = sp.cont_cols[task - 1];
-      for (int o = lane; o < n_opt; o += 32) t += probs[c0 + o] * S_all[(c0 + o) * sp.d_k + c];
+    } else if (task <= n_cont_tasks) {
+      const int ci = (task - 1) / nsplit, part = (task - 1) % nsplit;
+      const int c = sp.cont_cols[ci];
+      if (S_part != nullptr) {
+        const int jb0 = part * jb_per, jb1 = min(jblocks, jb0 + jb_per);
+        for (int o = lane; o < n_opt; o += 32) {
+          double v = 0.0;
+          for (int jb = jb0; jb < jb1; ++jb) v += S_part[(size_t(jb) * sp.d_k + c) * ncols_pad + c0 + o];
+          t += probs[c0 + o] * v;
+        }
+      } else {
+        for (int o = lane; o < n_opt; o += 32) t += probs[c0 + o] * S_all[(c0 + o) * sp.d_k + c];
+      }
       t = warp_sum(t);
-      if (lane == 0) g[c] = go * t;
-    } else if (task <= sp.n_cont + sp.n_int) {
+      if (lane == 0) csum[ci][part] = t;
+    } else if (task <= n_cont_tasks + sp.n_int) {
       // integer column k: d P / d theta = (+-) dp_k * product of the other factors
-      const int k = task - 1 - sp.n_cont;
+      const int k = task - 1 - n_cont_tasks;
       for (int o = lane; o < n_opt; o += 32) {
         const int32_t* op = options + size_t(o) * nv;
         const double diff = (off_int[k] + 1.0) - double(op[k]);
@@ -973,7 +1005,7 @@ __global__ void __launch_bounds__(REDUCE_THREADS) analytic_reduce_kernel(
       if (lane == 0) g[sp.int_cols[k]] = go * t;
     } else {
       // one-hot column m of categorical j: d softmax_c / d theta_m = softmax_c (delta_cm - softmax_m) / tau
-      int rem = task - 1 - sp.n_cont - sp.n_int, j = 0;
+      int rem = task - 1 - n_cont_tasks - sp.n_int, j = 0;
       while (rem >= sp.cat_card[j]) {
         rem -= sp.cat_card[j];
         ++j;
@@ -997,15 +1029,48 @@ __global__ void __launch_bounds__(REDUCE_THREADS) analytic_reduce_kernel(
       if (lane == 0) g[sp.cat_start[j] + mcol] = go * t;
     }
   }
+  if (grad_out == nullptr) return;
+  __syncthreads();
+  if (tid < sp.n_cont) {
+    double t = csum[tid][0];
+    for (int part = 1; part < nsplit; ++part) t += csum[tid][part];
+    g[sp.cont_cols[tid]] = go * t;
+  }
+  if (adam_theta == nullptr) return;
+  __syncthreads();
+  if (tid < sp.d) {  // torch.optim.Adam on loss = -acq(X).sum() (same arithmetic as adam_step_kernel)
+    const size_t idx = size_t(bi) * sp.d + tid;
+    const double gr = -g[tid];
+    const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+    const double mi = adam_m[idx] + (gr - adam_m[idx]) * (1.0 - b1);
+    const double vi = adam_v[idx] * b2 + (1.0 - b2) * gr * gr;
+    adam_m[idx] = mi;
+    adam_v[idx] = vi;
+    const double bc1 = 1.0 - pow(b1, t_step);
+    const double bc2 = 1.0 - pow(b2, t_step);
+    adam_theta[idx] = adam_theta[idx] - (lr / bc1) * (mi / (sqrt(vi) / sqrt(bc2) + eps));
+  }
+  // the last CTA advances the step counter and re-arms the completion counter
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last_s = (atomicAdd(done, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (last_s && tid == 0) {
+    if (step_ptr) *step_ptr += 1;
+    *done = 0u;
+  }
 }
 
 cudaError_t launch_analytic_reduce(const DevSpace& sp, const double* theta, int b, int n_opt, const int32_t* options,
                                    const double* a, const double* probs, const double* S_all, const double* grad_out,
-                                   double* out_value, double* out_grad, cudaStream_t st) {
+                                   double* out_value, double* out_grad, cudaStream_t st, const double* S_part,
+                                   int jblocks, int ncols_pad, double* adam_theta, double* adam_m, double* adam_v,
+                                   double lr, int* step_ptr, unsigned int* done) {
   ProfScope prof_(K_ANALYTIC, st);
   if (b == 0) return cudaSuccess;
   analytic_reduce_kernel<<<b, REDUCE_THREADS, 0, st>>>(sp, theta, n_opt, options, a, probs, S_all, grad_out, out_value,
-                                                       out_grad);
+                                                       out_grad, S_part, jblocks, ncols_pad, adam_theta, adam_m, adam_v,
+                                                       lr, step_ptr, done);
   count_launch();
   return cudaGetLastError();
 }

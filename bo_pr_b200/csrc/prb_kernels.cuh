@@ -25,7 +25,8 @@ cudaError_t launch_sep_step_finish(const DevSpace& sp, const DimMap& dm, int slo
                                    double lr, int* step_ptr, unsigned int* done, cudaStream_t st);
 cudaError_t launch_pad_copy(const double* src, int n, int n_pad, double* dst, cudaStream_t st);
 cudaError_t launch_analytic_build(const DevSpace& sp, const double* theta, int b, int n_opt, const int32_t* options,
-                                  double* xk, double* probs, cudaStream_t st);
+                                  double* xk, double* probs, cudaStream_t st, const double* lower = nullptr,
+                                  const double* upper = nullptr, double* Xc = nullptr);
 cudaError_t launch_kstar_panel(const Model& m, const double* xk, int ncols, int ncols_pad, double* KstarT,
                                cudaStream_t st);
 cudaError_t launch_kernel_matrix(const DevSpec& spec, const double* Xtr, int n, const double* xk, int n_points,
@@ -56,7 +57,10 @@ cudaError_t launch_mc_reduce(const DevSpace& sp, int b, int mc, const double* a,
 cudaError_t launch_ma_update(const double* value, int b, double* ma_state, cudaStream_t st);
 cudaError_t launch_analytic_reduce(const DevSpace& sp, const double* theta, int b, int n_opt, const int32_t* options,
                                    const double* a, const double* probs, const double* S_all, const double* grad_out,
-                                   double* out_value, double* out_grad, cudaStream_t st);
+                                   double* out_value, double* out_grad, cudaStream_t st, const double* S_part = nullptr,
+                                   int jblocks = 0, int ncols_pad = 0, double* adam_theta = nullptr,
+                                   double* adam_m = nullptr, double* adam_v = nullptr, double lr = 0.0,
+                                   int* step_ptr = nullptr, unsigned int* done = nullptr);
 cudaError_t launch_clamp(const double* theta, const double* lower, const double* upper, int b, int d, double* out,
                          cudaStream_t st);
 cudaError_t launch_adam_step(double* theta, const double* acq_grad, double* m, double* v, int total, double lr,

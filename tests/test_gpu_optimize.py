@@ -152,3 +152,39 @@ def test_generic_fused_step_matches_host_loop_and_oracle(name, n, mc):
                                        torch.ones(d, dtype=torch.float64), maxiter=steps)
     assert torch.allclose(cand_f.cpu(), theta_o, rtol=0, atol=1e-8), (cand_f.cpu() - theta_o).abs().max()
     assert torch.allclose(val_f.cpu(), val_o, rtol=1e-7, atol=1e-11)
+
+
+@pytest.mark.parametrize("name,n", [("chemistry_analytic_ei", None), ("int_cat_analytic_pm", None), ("chemistry_analytic_ei", 140)])
+def test_fused_analytic_adam_matches_host_loop_and_oracle(name, n):
+    """Analytic PR (enumeration): prb_analytic_adam -- the seven-launch fused step replayed from a CUDA graph (six launches
+    with a single row tile) -- against the host-driven torch.optim.Adam loop over the same class and against the oracle."""
+    from tests.product_util import product_analytic_pr
+    from tests.random_cases import build_problem
+
+    g = load(name)
+    if n is not None:  # a second row tile (n + 1 > 128): separate acquisition epilogue
+        g = build_problem(dict(g["case"], n_train=n, b=3, mc=8, seed=5))
+    c = g["case"]
+    d = c["dim"]
+    bounds = _bounds(d)
+    ics = g["theta"].to(DEV)
+    steps = 7
+    pr_f = product_analytic_pr(g, DEV)
+    cand_f, val_f = B.gen_candidates_torch(ics, pr_f, bounds[0], bounds[1], options={"maxiter": steps})
+    pr_h = product_analytic_pr(g, DEV)
+    cand_h, val_h = B.gen_candidates_torch(ics, pr_h, bounds[0], bounds[1], options={"maxiter": steps, "fused": False})
+    assert torch.allclose(cand_f, cand_h, rtol=0, atol=1e-10), (cand_f - cand_h).abs().max()
+    assert torch.allclose(val_f, val_h, rtol=1e-8, atol=1e-12)
+    space, oacq = oracle_space(g), oracle_acq(g)
+
+    def vg(X):
+        v, gr, _, _ = P.analytic_pr(space, X, oacq, apply_numeric=c["apply_numeric"])
+        return v, gr
+
+    def vo(X):
+        return P.analytic_pr(space, X, oacq, apply_numeric=c["apply_numeric"], with_grad=False)[0]
+
+    theta_o, val_o = P.adam_multistart(vg, vo, g["theta"], torch.zeros(d, dtype=torch.float64),
+                                       torch.ones(d, dtype=torch.float64), maxiter=steps)
+    assert torch.allclose(cand_f.cpu(), theta_o, rtol=0, atol=1e-8), (cand_f.cpu() - theta_o).abs().max()
+    assert torch.allclose(val_f.cpu(), val_o, rtol=1e-7, atol=1e-11)
