@@ -29,8 +29,12 @@
 // pipeline kept alive across tiles, next tile's first TMA loads issued before the epilogue, separate epilogue scratch) was
 // built and measured SLOWER: 4.59 ms, and 4.52 ms for the same restructured code launched one tile per CTA -- the
 // hardware's own CTA dispatch de-synchronises the two CTAs of an SM, whereas persistent CTAs walk equally long tiles in
-// lockstep and hit their epilogues together.  A persistent version needs a deliberate half-tile phase shift between the
-// two CTAs of an SM (or a dynamic tile queue) to pay.
+// lockstep and hit their epilogues together.  A second attempt that left the tile body untouched (stage parities offset
+// by a per-stage bit mask, scratch in the last stage buffer, prefetch into stages 0-1) gave the same picture: 4.57 ms with
+// one tile per CTA -- merely wrapping the tile body in a loop costs 4 % through ptxas' scheduling of the hot loop -- and
+// 4.66 ms persistent.  Moving the per-dim CTA barriers of the UPPER_GRAD epilogue into one also lost (2.12 -> 2.15 ms).
+// The kernel as it stands is a fragile local optimum of ptxas' register allocation; the next step needs the main loop
+// pinned down (hand-scheduled or CUTLASS-style explicit pipelining) before restructuring around it.
 //
 // Four modes (template):
 //   LOWER_GEN   the B operand k*[col, k] = kc[b(col), k] * tab[popc(z[col] ^ Z[k])] is GENERATED into shared memory by the
