@@ -343,6 +343,30 @@ def run_ours(a):
     evals_per_step = world * b * mc
     value_evals = evals_per_step / (ms_per_step * 1e-3)
 
+    # ---- value-only evaluation (raw-sample screening, gen_batch_initial_conditions): lower product only -----------------
+    value_only = None
+    if rank == 0:
+        def vstep():
+            capi.check(lib.prb_mc_value_grad(state.handle, C.byref(sp), C.byref(aq), theta_dev.data_ptr(), b, mc, None,
+                                             None, 0, 0, capi.PRB_EST_REINFORCE_MA, ma.data_ptr(), 1, None,
+                                             value.data_ptr(), None, None, ws.data_ptr(), ws.numel(), 0,
+                                             stream.cuda_stream), "prb_mc_value_grad")
+        for _ in range(a.warmup):
+            vstep()
+        torch.cuda.synchronize()
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record(stream)
+        for _ in range(a.steps):
+            vstep()
+        v1.record(stream)
+        torch.cuda.synchronize()
+        vms = v0.elapsed_time(v1) / a.steps
+        # F_v(n) = n^2 + ~70 n flop per evaluation (one triangular product + kernel + dots)
+        value_only = {"value": b * mc / (vms * 1e-3), "unit": UNIT, "ms_per_step": vms, "n_gpus": 1,
+                      "roofline_frac": (b * mc * (n * n + 70.0 * n) / (vms * 1e-3)) / (FP64_PEAK_TFLOPS * 1e12),
+                      "note": "value-only calls (no gradient): the screening of raw samples before the multi-start "
+                              "optimisation; fraction of the FP64 DMMA peak on F_v(n) = n^2 + 70 n flop per evaluation"}
+
     # ---- the same step with MC de-duplication (PRB_OPT_DEDUP): reported separately, never as `value` ---------------------
     dedup = None
     if rank == 0:
@@ -478,7 +502,7 @@ def run_ours(a):
                              "is L2-resident by design; no explicit flush",
                        "parallelism": f"restart-sharded x{world}, GP state replicated, no data-path collective"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "kernel_breakdown": breakdown, "bo_iter": bo, "dedup": dedup,
+            "kernel_breakdown": breakdown, "bo_iter": bo, "dedup": dedup, "value_only": value_only,
         }
         if best is not None:
             line["best_candidate"] = best
