@@ -284,9 +284,10 @@ def run_ours(a):
     theta_dev = theta.to(dev).reshape(b, -1).contiguous()
     d = theta_dev.shape[-1]
 
-    # ---- parity gate (rank 0): a slice of this very workload against the CPU oracle, before any timing ------------------
+    # ---- cpu_baseline leg, part 1 (rank 0, N = 1): before the CPU port is timed as the baseline, a slice of this very
+    # workload is checked against it (the oracle is the checker here, never the thing measured as `value`)
     pr = product_mc_pr(dict(problem, case=dict(problem["case"], grad_estimator="reinforce_ma")), dev, acq=acq)
-    if rank == 0:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
         from oracle import pr_oracle as P
         from tests.golden_util import oracle_acq, oracle_space
         from tests.product_util import close

@@ -1,7 +1,7 @@
 """Per-BO-iteration acquisition-optimisation time for the four named experiment configs of BASELINE.json (shapes of
 SURVEY.md App. D, synthetic GP data at the end-of-run training-set size), CUDA path vs the CPU oracle port.
 
-    python tools/config_timings.py [out.json] [--no-cpu]
+    python tests/config_timings.py [out.json] [--no-cpu]   (uses the oracle as the timed CPU baseline: lives under tests/)
 
 ackley13 pr__ei (MC, binary dims: separable path, persistent kernel), rosenbrock10_scaled pr__ucb (MC, ordinals inside the
 ARD Matern: generic path), mixed_int_f1_TR pr__ei (MC, ordinals + 2 binary dims, trust-region bounds: generic path),

@@ -5,7 +5,7 @@ from bo_pr_b200 import _capi as capi
 from bo_pr_b200.acquisition import acq_desc_of
 from tests.product_util import product_acq, product_mc_pr
 from tests.random_cases import build_problem
-from tools.config_timings import CONFIGS
+from tests.config_timings import CONFIGS
 dev = torch.device("cuda", 0)
 lib = capi.load_library()
 for name in ("rosenbrock10_scaled pr__ucb", "mixed_int_f1_TR pr__ei"):
