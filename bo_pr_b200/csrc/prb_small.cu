@@ -1,4 +1,6 @@
-// One kernel per optimisation step for experiment-sized problems on the separable path (n + 1 <= 128, mc % 32 == 0).
+// One kernel per optimisation step for experiment-sized problems (n + 1 <= 128, mc % 32 == 0): the separable "mixed"
+// kernel over binary integers (small_step_kernel<false>) and single-term Matern products over integers of any range
+// (small_step_kernel<true>, see small_eval_block).
 //
 // At the reference's own sizes (ackley13: n = 20 .. 119, 5 restarts x 128 MC samples per step, 800 Adam steps per BO
 // iteration, gen.py:320-337) a step is ~7e7 flop: microseconds of a B200, so wall time is the latency of the kernels in
@@ -719,7 +721,7 @@ bool small_step_eligible(const Model& m, const DevSpace& sp, const DimMap& dm, i
 
 // Generic variant: one product term; every continuous PR parameter inside one Matern factor; no categoricals.
 static bool small_gen_setup(const Model& m, const DevSpace& sp, DimMap* dm, int* gf_out, double* gw) {
-  if (m.spec.n_terms != 1 || m.spec.t[0].additive || sp.n_cat != 0 || sp.d != m.d_k || m.d_k > G_MAXD ||
+  if (m.spec.n_terms != 1 || m.spec.t[0].additive || sp.n_cat != 0 || sp.raw_int || sp.d != m.d_k || m.d_k > G_MAXD ||
       sp.n_cont > S_MAXC || sp.n_disc > 32)
     return false;
   const DevTerm& T = m.spec.t[0];
