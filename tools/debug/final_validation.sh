@@ -2,6 +2,6 @@ set -x
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" 2>&1 | tail -3
 timeout 900 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo "bench rc=$?"; tail -c 600 gpurun_out/bench_final.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; tail -c 700 gpurun_out/bench_ref.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches_v5.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-bo-iter > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:trgemm_tma --launch-skip 4 -c 2 -f -o gpurun_out/r01_trgemm_tma_v5 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-bo-iter > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
+
+
 ls -la gpurun_out/ | tail -8
