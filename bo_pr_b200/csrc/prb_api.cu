@@ -460,6 +460,19 @@ int generic_step(const Model& m, const DevSpace& sp, const DevAcq& aq, const Pla
   const bool need_path = need_grad && sp.n_cont > 0;
   CUDA_TRY(launch_pr_sample(sp, theta_in, b, mc, u_int, u_cat, seed, offset, xk, nullptr, need_grad ? z : nullptr,
                             need_grad ? prob : nullptr, nullptr, nullptr, st, lower, upper, Xc));
+  if (m.rff_m > 0) {
+    // deterministic posterior sample (Thompson sampling): three launches -- clamp + sampler, feature evaluation (value and
+    // gradient, written in the finish kernel's [dim][col] layout), finish
+    if (aq.kind != PRB_ACQ_MEAN) return PRB_ERR_INVALID;
+    CUDA_TRY(launch_rff_eval(m, xk, ncols, cont_mask(sp), need_path, a, S_part, nullptr, nullptr, st, ncols_pad));
+    DimMap dmr;
+    dmr.n = need_path ? sp.n_cont : 0;
+    for (int i = 0; i < sp.n_cont; ++i) dmr.dims[i] = sp.cont_cols[i];
+    CUDA_TRY(launch_sep_step_finish(sp, dmr, m.d_k, 1, b, mc, a, z, prob, S_part, 1, ncols_pad, estimator, ma_state,
+                                    update_ma, grad_out, out_value, out_grad, need_grad ? 1 : 0, adam_theta, adam_m, adam_v,
+                                    lr, step_ptr, at<unsigned int>(ws, pl.off_done), st));
+    return PRB_OK;
+  }
   CUDA_TRY(launch_kstar_panel(m, xk, ncols, ncols_pad, panelA, st));
   FusedAcq fa;
   fa.aq = aq;
@@ -615,6 +628,18 @@ int adam_graph_loop(Core core, double* theta, const double* lower, const double*
   return core(theta, nullptr, out_value, nullptr);
 }
 
+// The library carries sm_100a code only.  (Attribute queries: cudaGetDeviceProperties costs milliseconds per call.)
+int check_device(int dev) {
+  int major = 0, minor = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (major != 10) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "device %d is sm_%d%d; libprb200 is built for sm_100a only", dev, major, minor);
+    return PRB_ERR_NO_DEVICE;
+  }
+  return PRB_OK;
+}
+
 }  // namespace
 
 // =====================================================================================================================
@@ -691,13 +716,7 @@ int prb_model_create(prb_model** out, const prb_model_desc* desc, void* stream) 
   if (desc->d_k > PRB_MAX_DIMS) return PRB_ERR_UNSUPPORTED;
   int dev = -1;
   if (cudaGetDevice(&dev) != cudaSuccess) return PRB_ERR_NO_DEVICE;
-  cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
-  if (prop.major != 10) {
-    snprintf(g_cuda_err, sizeof(g_cuda_err), "device %s is sm_%d%d; libprb200 is built for sm_100a only", prop.name,
-             prop.major, prop.minor);
-    return PRB_ERR_NO_DEVICE;
-  }
+  if (int rc_dev = check_device(dev)) return rc_dev;
   Model* m = new (std::nothrow) Model();
   if (!m) return PRB_ERR_INVALID;
   memset(m, 0, sizeof(Model));
@@ -785,13 +804,7 @@ int prb_rff_model_create(prb_model** out, int32_t d_k, int32_t n_features, const
   if (d_k > PRB_MAX_DIMS) return PRB_ERR_UNSUPPORTED;
   int dev = -1;
   if (cudaGetDevice(&dev) != cudaSuccess) return PRB_ERR_NO_DEVICE;
-  cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
-  if (prop.major != 10) {
-    snprintf(g_cuda_err, sizeof(g_cuda_err), "device %s is sm_%d%d; libprb200 is built for sm_100a only", prop.name,
-             prop.major, prop.minor);
-    return PRB_ERR_NO_DEVICE;
-  }
+  if (int rc_dev = check_device(dev)) return rc_dev;
   Model* m = new (std::nothrow) Model();
   if (!m) return PRB_ERR_INVALID;
   memset(m, 0, sizeof(Model));
@@ -1156,7 +1169,7 @@ int prb_mc_adam(prb_model* model, const prb_space_desc* space, const prb_acq_des
   }
 
   // kernel structures that do not separate: the six-launch fused step on a single column panel
-  const bool generic_fused = !fused_step && !small_step && m.rff_m == 0 && int64_t(b) * mc <= pl.C && !sep_space &&
+  const bool generic_fused = !fused_step && !small_step && int64_t(b) * mc <= pl.C && !sep_space &&
                              getenv("PRB_NO_FUSED_STEP") == nullptr;
 
   auto one_iter = [&]() -> int {

@@ -410,63 +410,101 @@ cudaError_t launch_acq_epilogue(const Model& m, const DevAcq& aq, const double* 
 //   coalesced), gradient  df/dx_c = -scale * sum_j w_j sin(.) W[c, j]  for the dims in `diffmask`, 8 dims per pass.
 // =====================================================================================================================
 constexpr int RFF_WARPS = 8;
+constexpr int RFF_MAXG = 8;  // gradient dims per pass
+// WPC warps cooperate on one evaluation point (WPC = 1 for wide panels, RFF_WARPS when there are too few points to fill the
+// GPU otherwise); the feature range is split between them and the partial sums meet in shared memory (fixed order).
+template <int WPC>
 __global__ void __launch_bounds__(RFF_WARPS * 32) rff_eval_kernel(const double* __restrict__ W, const double* __restrict__ bias,
                                                                   const double* __restrict__ w, int m, int d_k,
                                                                   double scale, const double* __restrict__ xk,
                                                                   int64_t ncols, uint32_t diffmask, int need_grad,
                                                                   double* __restrict__ a, double* __restrict__ S_all,
                                                                   double* __restrict__ out_mean,
-                                                                  double* __restrict__ out_var) {
-  __shared__ double xs[RFF_WARPS][PRB_MAX_DIMS];
+                                                                  double* __restrict__ out_var, int64_t dim_stride) {
+  constexpr int CPB = RFF_WARPS / WPC;  // evaluation points per block
+  __shared__ double xs[CPB][PRB_MAX_DIMS];
+  __shared__ double part[RFF_WARPS][1 + RFF_MAXG];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t col = int64_t(blockIdx.x) * RFF_WARPS + warp;
-  if (col >= ncols) return;
-  if (lane < d_k) xs[warp][lane] = xk[size_t(col) * d_k + lane];
-  __syncwarp();
-  const double* x = xs[warp];
+  const int cslot = warp / WPC, sub = warp % WPC;
+  const int64_t col = int64_t(blockIdx.x) * CPB + cslot;
+  const bool valid = col < ncols;
+  if (valid && sub == 0 && lane < d_k) xs[cslot][lane] = xk[size_t(col) * d_k + lane];
+  __syncthreads();
+  const double* x = xs[cslot];
   int dims[PRB_MAX_DIMS];
   int nd = 0;
   if (need_grad)
     for (int c = 0; c < d_k; ++c)
       if ((diffmask >> c) & 1u) dims[nd++] = c;
-  double f = 0.0;
-  for (int pass = 0; pass == 0 || pass * 8 < nd; ++pass) {
-    double g[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int j = lane; j < m; j += 32) {
-      double ph = bias[j];
-      for (int c = 0; c < d_k; ++c) ph = fma(x[c], W[size_t(c) * m + j], ph);
-      double sn, cs;
-      sincos(ph, &sn, &cs);
-      const double wj = w[j];
-      if (pass == 0) f = fma(wj, cs, f);
-      const double ws = -wj * sn;
+  const int per = (m + WPC - 1) / WPC;
+  const int j0 = sub * per, j1 = min(m, j0 + per);
+  for (int pass = 0; pass == 0 || pass * RFF_MAXG < nd; ++pass) {
+    double f = 0.0;
+    double g[RFF_MAXG] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (valid) {
+      for (int j = j0 + lane; j < j1; j += 32) {
+        double ph = bias[j];
+        for (int c = 0; c < d_k; ++c) ph = fma(x[c], W[size_t(c) * m + j], ph);
+        double sn, cs;
+        sincos(ph, &sn, &cs);
+        const double wj = w[j];
+        f = fma(wj, cs, f);
+        const double ws = -wj * sn;
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (pass * 8 + q < nd) g[q] = fma(ws, W[size_t(dims[pass * 8 + q]) * m + j], g[q]);
-    }
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      if (pass * 8 + q < nd) {
-        const double t = warp_sum(g[q]);
-        if (lane == 0) S_all[size_t(col) * d_k + dims[pass * 8 + q]] = scale * t;
+        for (int q = 0; q < RFF_MAXG; ++q)
+          if (pass * RFF_MAXG + q < nd) g[q] = fma(ws, W[size_t(dims[pass * RFF_MAXG + q]) * m + j], g[q]);
       }
     }
-  }
-  f = scale * warp_sum(f);
-  if (lane == 0) {
-    if (a) a[col] = f;
-    if (out_mean) out_mean[col] = f;
-    if (out_var) out_var[col] = 0.0;
+    f = warp_sum(f);
+#pragma unroll
+    for (int q = 0; q < RFF_MAXG; ++q) g[q] = warp_sum(g[q]);
+    if (WPC > 1) {
+      __syncthreads();  // the previous pass has been read
+      if (lane == 0) {
+        part[warp][0] = f;
+#pragma unroll
+        for (int q = 0; q < RFF_MAXG; ++q) part[warp][1 + q] = g[q];
+      }
+      __syncthreads();
+      if (sub == 0 && lane == 0) {
+        for (int s2 = 1; s2 < WPC; ++s2) {
+          f += part[warp + s2][0];
+#pragma unroll
+          for (int q = 0; q < RFF_MAXG; ++q) g[q] += part[warp + s2][1 + q];
+        }
+      }
+    }
+    if (valid && sub == 0 && lane == 0) {
+      if (pass == 0) {
+        const double fv = scale * f;
+        if (a) a[col] = fv;
+        if (out_mean) out_mean[col] = fv;
+        if (out_var) out_var[col] = 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < RFF_MAXG; ++q)
+        if (pass * RFF_MAXG + q < nd) {
+          // dim_stride == 0: S[col, dim] (the engine's layout); else S[dim * dim_stride + col] (the fused step's finish kernel)
+          const int dd = dims[pass * RFF_MAXG + q];
+          S_all[dim_stride ? size_t(dd) * dim_stride + col : size_t(col) * d_k + dd] = scale * g[q];
+        }
+    }
   }
 }
 
 cudaError_t launch_rff_eval(const Model& m, const double* xk, int64_t ncols, uint32_t diffmask, bool need_grad, double* a,
-                            double* S_all, double* out_mean, double* out_var, cudaStream_t st) {
+                            double* S_all, double* out_mean, double* out_var, cudaStream_t st, int64_t dim_stride) {
   ProfScope prof_(K_KSTAR, st);
   if (ncols == 0) return cudaSuccess;
-  const unsigned grid = unsigned((ncols + RFF_WARPS - 1) / RFF_WARPS);
-  rff_eval_kernel<<<grid, RFF_WARPS * 32, 0, st>>>(m.rff_W, m.rff_b, m.rff_w, m.rff_m, m.d_k, m.rff_scale, xk, ncols, diffmask,
-                                                  need_grad ? 1 : 0, a, S_all, out_mean, out_var);
+  if (ncols < 8 * 148 * RFF_WARPS) {  // few points: all eight warps of a block share one point
+    rff_eval_kernel<RFF_WARPS><<<unsigned(ncols), RFF_WARPS * 32, 0, st>>>(m.rff_W, m.rff_b, m.rff_w, m.rff_m, m.d_k, m.rff_scale,
+                                                                         xk, ncols, diffmask, need_grad ? 1 : 0, a, S_all,
+                                                                         out_mean, out_var, dim_stride);
+  } else {
+    const unsigned grid = unsigned((ncols + RFF_WARPS - 1) / RFF_WARPS);
+    rff_eval_kernel<1><<<grid, RFF_WARPS * 32, 0, st>>>(m.rff_W, m.rff_b, m.rff_w, m.rff_m, m.d_k, m.rff_scale, xk, ncols,
+                                                      diffmask, need_grad ? 1 : 0, a, S_all, out_mean, out_var, dim_stride);
+  }
   count_launch();
   return cudaGetLastError();
 }

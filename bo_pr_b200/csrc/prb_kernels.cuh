@@ -32,7 +32,7 @@ cudaError_t launch_kstar_panel(const Model& m, const double* xk, int ncols, int 
 cudaError_t launch_kernel_matrix(const DevSpec& spec, const double* Xtr, int n, const double* xk, int n_points,
                                  double* out, cudaStream_t st);
 cudaError_t launch_rff_eval(const Model& m, const double* xk, int64_t ncols, uint32_t diffmask, bool need_grad, double* a,
-                            double* S_all, double* out_mean, double* out_var, cudaStream_t st);
+                            double* S_all, double* out_mean, double* out_var, cudaStream_t st, int64_t dim_stride = 0);
 cudaError_t launch_acq_epilogue(const Model& m, const DevAcq& aq, const double* norm_part, int ncols_pad,
                                 const double* mu_dot, int ncols, double* a, double* dmu, double* dvar,
                                 double* out_mean, double* out_var, const int* ncols_dev, int64_t col0,

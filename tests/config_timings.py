@@ -36,6 +36,12 @@ CONFIGS = {
                                    integer_bounds=[[0.0] * 8, [1.0, 1.0, 2.0, 2.0, 4.0, 4.0, 6.0, 6.0]],
                                    categorical_features=None, kernel_type="mixed", binary_dims=[8, 9], n_train=119, acq="ei",
                                    apply_numeric=False, grad_estimator="reinforce_ma", analytic=False, trust_region=True),
+    # Thompson sampling over an RFF posterior sample (rffs.py, experiment_utils.py:481-492): BoTorch's feature map only
+    # accepts Scale(Matern), so the GP here uses one ARD Matern over all 13 inputs; the sample draw (m x m Cholesky, once per
+    # BO iteration) is inside the timed segment
+    "ackley13 pr__ts": dict(dim=13, integer_indices=list(range(3, 13)), integer_bounds=[[0.0] * 10, [1.0] * 10],
+                            categorical_features=None, kernel_type="mixed", binary_dims=list(range(3, 13)), n_train=119,
+                            acq="pm", apply_numeric=False, grad_estimator="reinforce_ma", analytic=False, ts=True),
     "chemistry_analytic pr__ei": dict(dim=22, integer_indices=[], integer_bounds=[[], []],
                                       categorical_features={2: 4, 3: 12, 4: 4}, kernel_type="mixed_categorical",
                                       binary_dims=[], n_train=219, acq="ei", apply_numeric=True, grad_estimator=None,
@@ -55,16 +61,32 @@ def bounds_for(c):
     return torch.stack([lo, hi])
 
 
+def ts_gp(g):
+    """Scale(Matern-5/2 ARD over every input) GP on the config's training data (what RandomFourierFeatures accepts)."""
+    from bo_pr_b200.kernels import MaternKernel, ScaleKernel
+    X, y = g["train_X_model"].to(DEV), g["train_Y"].to(DEV)
+    base = MaternKernel(nu=2.5, ard_num_dims=X.shape[-1])
+    base.lengthscale = torch.full((1, X.shape[-1]), 0.7, dtype=torch.float64)
+    covar = ScaleKernel(base)
+    covar.outputscale = torch.tensor(1.0, dtype=torch.float64)
+    return B.FixedNoiseGP(X, y.unsqueeze(-1), torch.full_like(y, 1e-4).unsqueeze(-1), covar_module=covar)
+
+
 def ours(c, g, repeats=3):
-    acq = product_acq(g, DEV)
+    gp = ts_gp(g) if c.get("ts") else None
+    acq = None if c.get("ts") else product_acq(g, DEV)
     bounds = bounds_for(c).to(DEV)
     times = []
     for rep in range(repeats + 1):
-        pr = product_analytic_pr(g, DEV, acq=acq) if c["analytic"] else product_mc_pr(g, DEV, acq=acq)
         opts = dict(OPTS, seed=rep, nonnegative=(c["acq"] == "ei"))
         torch.manual_seed(rep)
+        if not c.get("ts"):
+            pr = product_analytic_pr(g, DEV, acq=acq) if c["analytic"] else product_mc_pr(g, DEV, acq=acq)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
+        if c.get("ts"):  # a fresh posterior sample per BO iteration, drawn inside the timed segment
+            acq = B.PosteriorMean(B.get_gp_samples(gp, num_outputs=1, n_samples=1, num_rff_features=512))
+            pr = product_mc_pr(g, DEV, acq=acq)
         cand, vals = B.optimize_acqf(pr, bounds, q=1, num_restarts=20, raw_samples=1024, options=opts, stochastic=True,
                                      return_best_only=False)
         final = pr.sample_candidates(cand)
@@ -81,7 +103,15 @@ def ours(c, g, repeats=3):
 def cpu(c, g):
     from bo_pr_b200.initializers import draw_sobol_samples, initialize_q_batch, initialize_q_batch_nonneg
     torch.set_num_threads(os.cpu_count() or 1)
-    space, oacq = oracle_space(g), oracle_acq(g)
+    space = oracle_space(g)
+    if c.get("ts"):  # the same kind of sample, evaluated by the CPU oracle (drawn on the GPU box's device, copied over)
+        from oracle import gp_oracle as G
+        from oracle.rff_oracle import OracleRFFSample
+        torch.manual_seed(0)
+        sm = B.get_gp_samples(ts_gp(g), num_outputs=1, n_samples=1, num_rff_features=512)
+        oacq = G.OraclePosteriorMean(OracleRFFSample(sm.basis.weights, sm.basis.bias, sm.weights, sm.basis.scale))
+    else:
+        oacq = oracle_acq(g)
     st = {"c": 0.0, "h": 0.0}
 
     def vg(X, with_grad=True):
