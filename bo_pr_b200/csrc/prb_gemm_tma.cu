@@ -32,7 +32,8 @@
 // lockstep and hit their epilogues together.  A second attempt that left the tile body untouched (stage parities offset
 // by a per-stage bit mask, scratch in the last stage buffer, prefetch into stages 0-1) gave the same picture: 4.57 ms with
 // one tile per CTA -- merely wrapping the tile body in a loop costs 4 % through ptxas' scheduling of the hot loop -- and
-// 4.66 ms persistent.  Moving the per-dim CTA barriers of the UPPER_GRAD epilogue into one also lost (2.12 -> 2.15 ms).
+// 4.66 ms persistent.  Moving the per-dim CTA barriers of the UPPER_GRAD epilogue into one also lost (2.12 -> 2.15 ms),
+// as did unrolling the k-tile loop by 2 or 4 (4.49 / 4.48 ms).
 // The kernel as it stands is a fragile local optimum of ptxas' register allocation; the next step needs the main loop
 // pinned down (hand-scheduled or CUTLASS-style explicit pipelining) before restructuring around it.
 //
