@@ -14,7 +14,7 @@ using namespace prb;
 
 namespace prb {
 unsigned long long g_launches = 0;
-bool g_pdl_on = false;
+thread_local bool g_pdl_on = false;  // per host thread: a PdlScope only affects the launches of the call that opened it
 
 static bool g_prof_on = false;
 struct ProfRec { int id; cudaEvent_t beg, end; };

@@ -77,7 +77,7 @@ struct ProfScope {  // no-op unless profiling is enabled; never use while the st
 // fused optimisation step is scheduled while the previous one still runs, executes its prologue (barrier init, descriptor
 // prefetch) and blocks in griddepcontrol.wait until the predecessor has completed and flushed.  Every kernel of the step
 // calls grid_dep_launch() first and grid_dep_wait() before it touches anything a predecessor wrote.
-extern bool g_pdl_on;
+extern thread_local bool g_pdl_on;
 struct PdlScope {
   explicit PdlScope(bool on) : prev_(g_pdl_on) { g_pdl_on = on; }
   ~PdlScope() { g_pdl_on = prev_; }
