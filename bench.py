@@ -38,7 +38,7 @@ import torch  # noqa: E402
 METRIC = "pr_acqf_value_grad_evals_per_sec"
 UNIT = "evals/s"
 FP64_PEAK_TFLOPS = 37.1  # measured on this pool's B200: DMMA microbenchmark, profiles/r01_fp64_peak_microbench.txt
-NCU_TRAFFIC_BYTES_PER_LAUNCH = (0.007028e9 + 485.605e6 + 2.337150e9 + 15.52e6) / 2  # profiles/r01_trgemm_tma_ncu.txt
+NCU_TRAFFIC_BYTES_PER_LAUNCH = (17.44e6 + 484.57e6 + 572.04e6 + 15.42e6) / 2  # profiles/r01_trgemm_tma_ncu.txt
 FP64_PEAK_SOURCE = ("measured FP64 DMMA peak (tools/microbench/fp64_peak.cu, profiles/r01_fp64_peak_microbench.txt; "
                     "cuBLAS DGEMM 35.5 TF/s, profiles/r01_cublas_dgemm_peak.json); MEASURED_PEAKS.json has no FP64 entry")
 
@@ -450,9 +450,10 @@ def run_ours(a):
                     "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
                     "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if (n, b, mc) == (1000, 64, 1024) else None,
                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum averaged over the two "
-                    "launches of a step (profiles/r01_trgemm_tma_ncu.txt: lower 0.007 + 0.486 GB, upper 2.337 + 0.016 GB);"
-                    " algorithmic HBM bytes per launch = the v panel once, 0.537 GB -- the upper product re-reads it "
-                    "4.4x (row tiles of one column panel are not co-scheduled) at 13.5 % of DRAM bandwidth",
+                    "launches of a step (profiles/r01_trgemm_tma_ncu.txt: lower 0.017 + 0.485 GB, upper 0.572 + 0.015 GB);"
+                    " algorithmic HBM bytes per launch = the v panel once, 0.537 GB (written by the lower product, read by "
+                    "the upper one): 1.01x -- column tiles are scheduled in groups so that the row tiles of a column tile "
+                    "re-read the panel from L2 (2.34 GB of DRAM reads per upper launch before the grouped order)",
                     "peak_source": FP64_PEAK_SOURCE,
                     "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "launches_per_step": gemm_launches,
                     "share_of_step": gemm_ms / sum(v["ms_per_step"] for v in breakdown.values()),

@@ -71,6 +71,7 @@ enum { MODE_LOWER_GEN = 0, MODE_LOWER_TMA = 1, MODE_UPPER_W = 2, MODE_UPPER_GRAD
 
 struct TmaGemmParams {
   int mtiles, ntiles, Kp, ncols_pad;
+  int ngroup;  // column tiles per scheduling group (see the launch order in the kernel)
   // lower epilogue
   double* C;  // V^T [ncols_pad, ldc] (lower) or W [Mp2, ncols_pad] (UPPER_W)
   int ldc;
@@ -132,10 +133,17 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 2 : 1)
   const int wm = warp & 3;   // 4 warps along M (32 rows each)
   const int wn = warp >> 2;  // 2 warps along N (64 cols each)
 
-  // heavy tiles first: lower -> largest row block first, upper -> smallest row block first
+  // Launch order: column tiles are taken in groups of p.ngroup; inside a group every row tile of those columns is scheduled
+  // back to back (heavy first: lower -> largest row block first, upper -> smallest row block first), so the B-operand
+  // columns that the row tiles of one column tile re-read (the v panel in the upper product, the k* panel on the generic
+  // path) are still in L2 instead of coming from HBM once per row tile.  p.ngroup = ntiles: plain row-tile-major order.
   const int t = blockIdx.x;
-  const int nt = t % p.ntiles;
-  const int mi_sched = t / p.ntiles;
+  const int per_group = p.ngroup * p.mtiles;
+  const int grp_i = t / per_group;
+  const int r_in = t - grp_i * per_group;
+  const int gcols = min(p.ngroup, p.ntiles - grp_i * p.ngroup);  // column tiles in this (possibly last, shorter) group
+  const int mi_sched = r_in / gcols;
+  const int nt = grp_i * p.ngroup + (r_in - mi_sched * gcols);
   const int mt = UPPER ? mi_sched : (p.mtiles - 1 - mi_sched);
   const int m0 = mt * T_BM;
   const int n0 = nt * BN;
@@ -566,6 +574,14 @@ static void fill_common(TmaGemmParams& p, const Model& m, int ncols_pad, bool up
   p.Kp = m.Kp;
   p.ncols_pad = ncols_pad;
   p.special_row = upper ? -1 : m.n;
+  // scheduling groups of ~4 waves of CTAs (PRB_GROUP_WAVES overrides; 0 = row-tile-major order).  Measured at n = 1000,
+  // 65 536 columns: the upper product's DRAM reads fall from 2.34 GB to 0.57 GB per launch (algorithmic 0.54 GB; L2 hit rate
+  // 64 % -> 86 %) at unchanged run time -- the kernel is tensor-pipe bound -- with groups of 1 wave 1.5 % slower.
+  static const int waves = getenv("PRB_GROUP_WAVES") ? atoi(getenv("PRB_GROUP_WAVES")) : 4;
+  const int slots = (bn == 64 ? 2 : 1) * 148;
+  int g = waves > 0 ? (waves * slots) / (p.mtiles > 0 ? p.mtiles : 1) : p.ntiles;
+  if (g < 1) g = 1;
+  p.ngroup = g < p.ntiles ? g : p.ntiles;
 }
 
 static void fill_sep(TmaGemmParams& p, const Model& m, const SepArgs& sa) {
