@@ -21,6 +21,7 @@ PRB_FACTOR_CATEGORICAL = 1
 PRB_ACQ_EI, PRB_ACQ_UCB, PRB_ACQ_MEAN = 0, 1, 2
 PRB_EST_REINFORCE, PRB_EST_REINFORCE_MA = 0, 1
 PRB_OPT_DEDUP = 1
+PRB_OPT_UNFUSED = 2
 PRB_PROFILE_SLOTS = 12
 PROFILE_SLOT_NAMES = ["pr_sample", "kstar_panel", "trgemm_lower", "acq_epilogue", "trgemm_upper", "grad_contract",
                       "sum_splits", "mc_reduce", "ma_update", "analytic", "adam", "other"]

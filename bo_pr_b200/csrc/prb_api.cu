@@ -10,15 +10,30 @@
 
 using namespace prb;
 
+#include <mutex>
 #include <vector>
 
 namespace prb {
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 thread_local bool g_pdl_on = false;  // per host thread: a PdlScope only affects the launches of the call that opened it
 
-static bool g_prof_on = false;
+const EnvKnobs& env_knobs() {
+  static const EnvKnobs k = [] {
+    EnvKnobs e;
+    e.no_pdl = getenv("PRB_NO_PDL") != nullptr;
+    e.no_fused_step = getenv("PRB_NO_FUSED_STEP") != nullptr;
+    e.panel_mb = getenv("PRB_PANEL_MB") ? atol(getenv("PRB_PANEL_MB")) : 0;
+    e.force_bn = getenv("PRB_BN") ? atoi(getenv("PRB_BN")) : 0;
+    e.group_waves = getenv("PRB_GROUP_WAVES") ? atoi(getenv("PRB_GROUP_WAVES")) : 4;
+    return e;
+  }();
+  return k;
+}
+
+static std::atomic<bool> g_prof_on{false};
 struct ProfRec { int id; cudaEvent_t beg, end; };
-static std::vector<ProfRec> g_prof;
+static std::vector<ProfRec> g_prof;  // diagnostic record (prb_profile_*), guarded by g_prof_mu
+static std::mutex g_prof_mu;
 
 ProfScope::ProfScope(int id, cudaStream_t st) : id_(id), st_(st), beg_(nullptr), end_(nullptr), on_(g_prof_on) {
   if (!on_) return;
@@ -31,6 +46,7 @@ ProfScope::ProfScope(int id, cudaStream_t st) : id_(id), st_(st), beg_(nullptr),
 ProfScope::~ProfScope() {
   if (!on_) return;
   cudaEventRecord(end_, st_);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof.push_back({id_, beg_, end_});
 }
 }  // namespace prb
@@ -170,13 +186,8 @@ struct Plan {
 // Column panels (k*, v, w) are sized to stay resident in the 126 MB L2 between the kernel that writes them and the one
 // that reads them.  PRB_PANEL_MB overrides the budget (tuning knob, read once).
 size_t panel_budget_bytes() {
-  static size_t v = 0;
-  if (v == 0) {
-    const char* e = getenv("PRB_PANEL_MB");
-    long mb = e ? atol(e) : 0;
-    v = size_t(mb > 0 ? mb : 96) << 20;
-  }
-  return v;
+  const long mb = env_knobs().panel_mb;
+  return size_t(mb > 0 ? mb : 96) << 20;
 }
 
 Plan make_plan(const Model& m, int64_t n_points, int n_restarts, int d_theta, int chunk_cols) {
@@ -191,7 +202,7 @@ Plan make_plan(const Model& m, int64_t n_points, int n_restarts, int d_theta, in
     // fewer launches, and the partial last wave of the triangular tile schedule is amortised over more tiles
     // (measured: 96 MB -> 5.22 ms, 1.1 GB -> 4.77 ms per 65 536-column step at n = 1000).
     size_t budget = panel_budget_bytes();
-    if (m.sep_ok && n_restarts > 0 && getenv("PRB_PANEL_MB") == nullptr) budget = size_t(2048) << 20;
+    if (m.sep_ok && n_restarts > 0 && env_knobs().panel_mb <= 0) budget = size_t(2048) << 20;
     C = int64_t(budget / (sizeof(double) * size_t(m.Mp1 + m.Mp2))) / 128 * 128;
     if (C < 128) C = 128;
   }
@@ -390,7 +401,7 @@ int sep_step(const Model& m, const DevSpace& sp, const DevAcq& aq, const Plan& p
              int mc, const double* u_int, const double* u_cat, uint64_t seed, uint64_t offset, int estimator,
              double* ma_state, int update_ma, bool need_grad, const double* grad_out, double* out_value,
              double* out_grad, double* adam_theta, double* adam_m, double* adam_v, double lr, int* step_ptr,
-             cudaStream_t st) {
+             cudaStream_t st, double* a_out = nullptr) {
   const int ncols = b * mc;
   const int ncols_pad = round_up(ncols, 128);
   double* panelV = at<double>(ws, pl.off_panelV);
@@ -402,13 +413,12 @@ int sep_step(const Model& m, const DevSpace& sp, const DevAcq& aq, const Plan& p
   uint32_t* zbits = at<uint32_t>(ws, pl.off_zbits);
   uint8_t* z = at<uint8_t>(ws, pl.off_z);
   double* prob = at<double>(ws, pl.off_prob);
-  double* a = at<double>(ws, pl.off_a);
+  double* a = a_out ? a_out : at<double>(ws, pl.off_a);
   double* dmu = at<double>(ws, pl.off_dmu);
   double* dvar = at<double>(ws, pl.off_dvar);
   CUDA_TRY(launch_sep_step_prep(m, sp, bm, theta_in, lower, upper, Xc, b, mc, u_int, u_cat, seed, offset, kc,
                                 need_grad ? Dc : nullptr, need_grad ? z : nullptr, need_grad ? prob : nullptr, zbits, st));
-  static const bool use_pdl = getenv("PRB_NO_PDL") == nullptr;
-  PdlScope pdl(use_pdl);  // the remaining kernels of the step overlap their launch + prologue with their predecessor
+  PdlScope pdl(!env_knobs().no_pdl);  // the remaining kernels of the step overlap their launch + prologue with their predecessor
   SepArgs sa;
   sa.kc = kc;
   sa.Dc = Dc;
@@ -432,7 +442,7 @@ int sep_step(const Model& m, const DevSpace& sp, const DevAcq& aq, const Plan& p
   CUDA_TRY(launch_sep_step_finish(sp, dm, dm.n, 0, b, mc, a, z, prob, S_part, m.Mp2 / GEMM_BM, ncols_pad, estimator,
                                   ma_state,
                                   update_ma, grad_out, out_value, out_grad, need_grad ? 1 : 0, adam_theta, adam_m, adam_v,
-                                  lr, step_ptr, at<unsigned int>(ws, pl.off_done), st));
+                                  lr, step_ptr, m.done_ctr, st));
   return PRB_OK;
 }
 
@@ -443,7 +453,7 @@ int generic_step(const Model& m, const DevSpace& sp, const DevAcq& aq, const Pla
                  const double* lower, const double* upper, double* Xc, int b, int mc, const double* u_int,
                  const double* u_cat, uint64_t seed, uint64_t offset, int estimator, double* ma_state, int update_ma,
                  bool need_grad, const double* grad_out, double* out_value, double* out_grad, double* adam_theta,
-                 double* adam_m, double* adam_v, double lr, int* step_ptr, cudaStream_t st) {
+                 double* adam_m, double* adam_v, double lr, int* step_ptr, cudaStream_t st, double* a_out = nullptr) {
   const int ncols = b * mc;
   const int ncols_pad = round_up(ncols, 128);
   double* panelA = at<double>(ws, pl.off_panelA);
@@ -454,7 +464,7 @@ int generic_step(const Model& m, const DevSpace& sp, const DevAcq& aq, const Pla
   double* xk = at<double>(ws, pl.off_xk);
   uint8_t* z = at<uint8_t>(ws, pl.off_z);
   double* prob = at<double>(ws, pl.off_prob);
-  double* a = at<double>(ws, pl.off_a);
+  double* a = a_out ? a_out : at<double>(ws, pl.off_a);
   double* dmu = at<double>(ws, pl.off_dmu);
   double* dvar = at<double>(ws, pl.off_dvar);
   const bool need_path = need_grad && sp.n_cont > 0;
@@ -470,7 +480,7 @@ int generic_step(const Model& m, const DevSpace& sp, const DevAcq& aq, const Pla
     for (int i = 0; i < sp.n_cont; ++i) dmr.dims[i] = sp.cont_cols[i];
     CUDA_TRY(launch_sep_step_finish(sp, dmr, m.d_k, 1, b, mc, a, z, prob, S_part, 1, ncols_pad, estimator, ma_state,
                                     update_ma, grad_out, out_value, out_grad, need_grad ? 1 : 0, adam_theta, adam_m, adam_v,
-                                    lr, step_ptr, at<unsigned int>(ws, pl.off_done), st));
+                                    lr, step_ptr, m.done_ctr, st));
     return PRB_OK;
   }
   CUDA_TRY(launch_kstar_panel(m, xk, ncols, ncols_pad, panelA, st));
@@ -493,7 +503,7 @@ int generic_step(const Model& m, const DevSpace& sp, const DevAcq& aq, const Pla
   for (int i = 0; i < sp.n_cont; ++i) dm.dims[i] = sp.cont_cols[i];
   CUDA_TRY(launch_sep_step_finish(sp, dm, m.d_k, 1, b, mc, a, z, prob, S_part, m.Mp2 / pl.grad_jrows, ncols_pad, estimator,
                                   ma_state, update_ma, grad_out, out_value, out_grad, need_grad ? 1 : 0, adam_theta,
-                                  adam_m, adam_v, lr, step_ptr, at<unsigned int>(ws, pl.off_done), st));
+                                  adam_m, adam_v, lr, step_ptr, m.done_ctr, st));
   return PRB_OK;
 }
 
@@ -551,6 +561,19 @@ int mc_core(prb_model* model, const DevSpace& sp, const DevAcq& aq, const Plan& 
     if (update_ma && ma_state) CUDA_TRY(launch_ma_update(out_value, b, ma_state, st));
     return PRB_OK;
   }
+  // One column panel (every experiment shape and the benchmark shape): the fused step -- 4-5 launches chained by
+  // programmatic dependent launch (separable structure) or 6 (generic) instead of 8-12 stream-ordered ones.  The multi-
+  // launch sequence below remains for multi-panel calls and as the cross-check path (PRB_OPT_UNFUSED).
+  if (B <= pl.C && !m.opt_unfused && !env_knobs().no_fused_step) {
+    const int upd = (update_ma && ma_state) ? 1 : 0;
+    if (sep)
+      return sep_step(m, sp, aq, pl, ws, bm, dm, theta, nullptr, nullptr, nullptr, b, mc, u_int, u_cat, seed, offset,
+                      estimator, ma_state, upd, need_grad, grad_out, out_value, out_grad, nullptr, nullptr, nullptr, 0.0,
+                      nullptr, st, out_acq_values);
+    return generic_step(m, sp, aq, pl, ws, theta, nullptr, nullptr, nullptr, b, mc, u_int, u_cat, seed, offset, estimator,
+                        ma_state, upd, need_grad, grad_out, out_value, out_grad, nullptr, nullptr, nullptr, 0.0, nullptr,
+                        st, out_acq_values);
+  }
   if (sep) {
     CUDA_TRY(launch_pr_sample(sp, theta, b, mc, u_int, u_cat, seed, offset, nullptr, nullptr, need_grad ? z : nullptr,
                               need_grad ? prob : nullptr, &bm, at<uint32_t>(ws, pl.off_zbits), st));
@@ -566,33 +589,54 @@ int mc_core(prb_model* model, const DevSpace& sp, const DevAcq& aq, const Plan& 
   return PRB_OK;
 }
 
-// clamp -> value + gradient -> Adam, `maxiter` times, then the final clamp and value-only evaluation (gen.py:304-343).  One
-// step is captured into a CUDA graph and replayed; `core(X, grad_ones_or_null, value_out, grad_out_or_null)` enqueues one
-// evaluation of the acquisition function on `st`.
-// Run `one_iter` maxiter times: captured once into a CUDA graph and replayed when the caller gave a real stream (removes the
+// Run `one_iter` maxiter times.  With a real stream the step is captured once into a CUDA graph and replayed (removes the
 // per-launch host latency: the reference spends its time exactly there at experiment sizes, 800 host-driven steps per BO
-// iteration), else as plain launches.
+// iteration), else it is issued as plain launches.  The executable graph is cached on the model
+// (`slot`): a later call re-captures its step -- a host-side recording of a handful of launches -- and updates the cached
+// executable in place (cudaGraphExecUpdate only affects FUTURE launches, so replays still in flight are untouched).  No
+// instantiation and no stream synchronisation in steady state; an executable whose topology no longer matches is parked
+// on the model and released by prb_model_destroy.
 template <typename Iter>
-int replay_steps(Iter one_iter, int maxiter, cudaStream_t st) {
+int replay_steps(Model& m, int slot, Iter one_iter, int maxiter, cudaStream_t st) {
   bool graphed = false;
   if (st != nullptr && maxiter >= 4) {
     cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-      const unsigned long long l0 = g_launches;
+      const unsigned long long l0 = g_launches.load(std::memory_order_relaxed);
       int r = one_iter();
-      const unsigned long long per_iter = g_launches - l0;
+      const unsigned long long per_iter = g_launches.load(std::memory_order_relaxed) - l0;
       cudaError_t e = cudaStreamEndCapture(st, &graph);
-      if (r == PRB_OK && e == cudaSuccess && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
-        cudaError_t le = cudaSuccess;
-        for (int it = 0; it < maxiter && le == cudaSuccess; ++it) le = cudaGraphLaunch(exec, st);
-        graphed = (le == cudaSuccess);
-        if (graphed) g_launches += per_iter * (unsigned long long)(maxiter - 1);
-        cudaStreamSynchronize(st);  // exec/graph must outlive the enqueued launches
-        cudaGraphExecDestroy(exec);
-        if (!graphed) {
-          cudaGraphDestroy(graph);
-          return cuda_fail(le, "cudaGraphLaunch");
+      if (r == PRB_OK && e == cudaSuccess && graph != nullptr) {
+        cudaGraphExec_t& exec = m.graph_exec[slot];
+        bool ready = false;
+        if (exec != nullptr) {
+          cudaGraphExecUpdateResultInfo info;
+          memset(&info, 0, sizeof(info));
+          if (cudaGraphExecUpdate(exec, graph, &info) == cudaSuccess) {
+            ready = true;
+          } else {
+            (void)cudaGetLastError();
+            if (m.n_graph_dead < int(sizeof(m.graph_dead) / sizeof(m.graph_dead[0]))) {
+              m.graph_dead[m.n_graph_dead++] = exec;
+            } else {  // parking lot full (a caller alternating between many topologies): drain, then release
+              cudaStreamSynchronize(st);
+              cudaGraphExecDestroy(exec);
+            }
+            exec = nullptr;
+          }
+        }
+        if (!ready) ready = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+        if (ready) {
+          cudaError_t le = cudaSuccess;
+          for (int it = 0; it < maxiter && le == cudaSuccess; ++it) le = cudaGraphLaunch(exec, st);
+          if (le != cudaSuccess) {
+            cudaGraphDestroy(graph);
+            return cuda_fail(le, "cudaGraphLaunch");
+          }
+          graphed = true;
+          count_launch(int(per_iter) * (maxiter - 1));  // replays of the captured step
+        } else {
+          exec = nullptr;
         }
       }
       if (graph) cudaGraphDestroy(graph);
@@ -609,7 +653,7 @@ int replay_steps(Iter one_iter, int maxiter, cudaStream_t st) {
 }
 
 template <typename Core>
-int adam_graph_loop(Core core, double* theta, const double* lower, const double* upper, int b, int d, double lr, int maxiter,
+int adam_graph_loop(Model& m, int slot, Core core, double* theta, const double* lower, const double* upper, int b, int d, double lr, int maxiter,
                     int step0, double* adam_state, double* out_value, double* Xc, double* grad, double* ones, double* val,
                     int* step, cudaStream_t st) {
   const int total = b * d;
@@ -622,7 +666,7 @@ int adam_graph_loop(Core core, double* theta, const double* lower, const double*
     CUDA_TRY(launch_adam_step(theta, grad, adam_state, adam_state + total, total, lr, step, st));
     return PRB_OK;
   };
-  int rc = replay_steps(one_iter, maxiter, st);
+  int rc = replay_steps(m, slot, one_iter, maxiter, st);
   if (rc != PRB_OK) return rc;
   CUDA_TRY(launch_clamp(theta, lower, upper, b, d, theta, st));
   return core(theta, nullptr, out_value, nullptr);
@@ -647,7 +691,7 @@ extern "C" {
 
 int prb_version(void) { return PRB_VERSION; }
 
-uint64_t prb_launch_count(void) { return g_launches; }
+uint64_t prb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int prb_abi_sizeof(int which) {
   switch (which) {
@@ -678,6 +722,7 @@ int prb_profile_read(double* ms_by_kernel, uint64_t* launches_by_kernel, int32_t
     if (launches_by_kernel) launches_by_kernel[i] = 0;
   }
   cudaError_t first = cudaSuccess;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   for (const auto& r : g_prof) {
     cudaError_t e = cudaEventSynchronize(r.end);
     float ms = 0.f;
@@ -758,6 +803,8 @@ int prb_model_create(prb_model** out, const prb_model_desc* desc, void* stream) 
   if (e == cudaSuccess) e = cudaMalloc(&m->alpha_pad, size_t(n_pad) * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&m->Zbits, size_t(n_pad) * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&m->sep_tab, 64 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&m->done_ctr, 64);
+  if (e == cudaSuccess) e = cudaMemsetAsync(m->done_ctr, 0, 64, st);
   if (e == cudaSuccess) e = launch_pad_copy(m->alpha, m->n, n_pad, m->alpha_pad, st);
   if (e == cudaSuccess) e = cudaMemsetAsync(m->Zbits, 0, size_t(n_pad) * sizeof(uint32_t), st);
   if (e == cudaSuccess) e = make_operand_map(&m->mapA1, m->A1, m->Mp1, m->Kp, m->Kp);
@@ -822,7 +869,8 @@ int prb_rff_model_create(prb_model** out, int32_t d_k, int32_t n_features, const
   const size_t fm = size_t(n_features) * sizeof(double);
   cudaError_t e;
   if ((e = cudaMalloc(&m->rff_W, fm * d_k)) == cudaSuccess && (e = cudaMalloc(&m->rff_b, fm)) == cudaSuccess &&
-      (e = cudaMalloc(&m->rff_w, fm)) == cudaSuccess &&
+      (e = cudaMalloc(&m->rff_w, fm)) == cudaSuccess && (e = cudaMalloc(&m->done_ctr, 64)) == cudaSuccess &&
+      (e = cudaMemsetAsync(m->done_ctr, 0, 64, st)) == cudaSuccess &&
       (e = cudaMemcpyAsync(m->rff_W, W, fm * d_k, cudaMemcpyDeviceToDevice, st)) == cudaSuccess &&
       (e = cudaMemcpyAsync(m->rff_b, bias, fm, cudaMemcpyDeviceToDevice, st)) == cudaSuccess)
     e = cudaMemcpyAsync(m->rff_w, weights, fm, cudaMemcpyDeviceToDevice, st);
@@ -837,7 +885,11 @@ int prb_rff_model_create(prb_model** out, int32_t d_k, int32_t n_features, const
 int prb_model_destroy(prb_model* model) {
   if (!model) return PRB_OK;
   Model* m = reinterpret_cast<Model*>(model);
-  cudaFree(m->rff_W);
+  cudaFree(m->rff_W);  // cudaFree synchronises the device: no replay of a cached graph is in flight past this point
+  for (int i = 0; i < 2; ++i)
+    if (m->graph_exec[i]) cudaGraphExecDestroy(m->graph_exec[i]);
+  for (int i = 0; i < m->n_graph_dead; ++i) cudaGraphExecDestroy(m->graph_dead[i]);
+  cudaFree(m->done_ctr);
   cudaFree(m->rff_b);
   cudaFree(m->rff_w);
   cudaFree(m->A1);
@@ -857,6 +909,9 @@ int prb_model_set_option(prb_model* model, int32_t option, int64_t value) {
   switch (option) {
     case PRB_OPT_DEDUP:
       m->opt_dedup = value != 0;
+      return PRB_OK;
+    case PRB_OPT_UNFUSED:
+      m->opt_unfused = value != 0;
       return PRB_OK;
     default:
       return PRB_ERR_INVALID;
@@ -1046,7 +1101,7 @@ int prb_analytic_adam(prb_model* model, const prb_space_desc* space, const prb_a
   double* S_all = at<double>(workspace, pl.off_S_all);
   // One column panel and a GP model: a step is seven launches (six with a single row tile) -- clamp + enumeration, k* panel,
   // lower product [+ acquisition epilogue], upper product, gradient contraction, reduction + row-block sums + Adam.
-  if (B <= pl.C && m.rff_m == 0 && getenv("PRB_NO_FUSED_STEP") == nullptr) {
+  if (B <= pl.C && m.rff_m == 0 && !env_knobs().no_fused_step) {
     const int ncols = int(B), ncols_pad = round_up(int(B), 128), total = b * sp.d;
     double* panelA = at<double>(workspace, pl.off_panelA);
     double* panelV = at<double>(workspace, pl.off_panelV);
@@ -1060,7 +1115,7 @@ int prb_analytic_adam(prb_model* model, const prb_space_desc* space, const prb_a
     double* ones = at<double>(workspace, pl.off_ones);
     double* val = at<double>(workspace, pl.off_val);
     int* step = at<int>(workspace, pl.off_step);
-    unsigned int* done = at<unsigned int>(workspace, pl.off_done);
+    unsigned int* done = m.done_ctr;
     CUDA_TRY(launch_fill(ones, 1.0, b, st));
     CUDA_TRY(cudaMemcpyAsync(step, &step0, sizeof(int), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(done, 0, sizeof(unsigned int), st));
@@ -1097,7 +1152,7 @@ int prb_analytic_adam(prb_model* model, const prb_space_desc* space, const prb_a
                                       adam_state + total, lr, step, done));
       return PRB_OK;
     };
-    rc = replay_steps([&]() -> int { return fused(true, val); }, maxiter, st);
+    rc = replay_steps(*reinterpret_cast<Model*>(model), 1, [&]() -> int { return fused(true, val); }, maxiter, st);
     if (rc != PRB_OK) return rc;
     return fused(false, out_value);
   }
@@ -1110,7 +1165,7 @@ int prb_analytic_adam(prb_model* model, const prb_space_desc* space, const prb_a
     CUDA_TRY(launch_analytic_reduce(sp, X, b, n_options, options, a, probs, S_all, go, value, g, st));
     return PRB_OK;
   };
-  return adam_graph_loop(core, theta, lower, upper, b, sp.d, lr, maxiter, step0, adam_state, out_value,
+  return adam_graph_loop(*reinterpret_cast<Model*>(model), 1, core, theta, lower, upper, b, sp.d, lr, maxiter, step0, adam_state, out_value,
                          at<double>(workspace, pl.off_Xc), at<double>(workspace, pl.off_grad),
                          at<double>(workspace, pl.off_ones), at<double>(workspace, pl.off_val),
                          at<int>(workspace, pl.off_step), st);
@@ -1143,13 +1198,13 @@ int prb_mc_adam(prb_model* model, const prb_space_desc* space, const prb_acq_des
   const int total = b * sp.d;
   CUDA_TRY(launch_fill(ones, 1.0, b, st));
   CUDA_TRY(cudaMemcpyAsync(step, &step0, sizeof(int), cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemsetAsync(at<unsigned int>(workspace, pl.off_done), 0, sizeof(unsigned int), st));
+  CUDA_TRY(cudaMemsetAsync(m.done_ctr, 0, sizeof(unsigned int), st));
   const int update_ma = ma_state ? 1 : 0;
   // separable structure on a single column panel: four fused launches per step instead of eleven
   BitMap bm;
   DimMap dm;
   const bool fused_step = pl.off_kc != 0 && sep_space_ok(m, sp, &bm, &dm) && int64_t(b) * mc <= pl.C &&
-                          !(m.opt_dedup && m.sep_nbits <= DEDUP_MAX_BITS) && getenv("PRB_NO_FUSED_STEP") == nullptr;
+                          !(m.opt_dedup && m.sep_nbits <= DEDUP_MAX_BITS) && !env_knobs().no_fused_step;
 
   // experiment sizes (n + 1 <= 128, mc % 32 == 0): the whole step is ONE kernel (prb_small.cu)
   const bool sep_space = pl.off_kc != 0 && sep_space_ok(m, sp, &bm, &dm);
@@ -1157,7 +1212,7 @@ int prb_mc_adam(prb_model* model, const prb_space_desc* space, const prb_acq_des
   bool small_step = fused_step && small_step_eligible(m, sp, dm, b, mc) &&
                     small_step_scratch_bytes(b, mc, sp.d) <= pl.small_bytes;
   if (!small_step && !sep_space && small_step_scratch_bytes(b, mc, sp.d) <= pl.small_bytes &&
-      small_gen_eligible(m, sp, &dm, b, mc) && getenv("PRB_NO_FUSED_STEP") == nullptr)
+      small_gen_eligible(m, sp, &dm, b, mc) && !env_knobs().no_fused_step)
     small_step = small_gen = true;
   if (small_step) CUDA_TRY(cudaMemsetAsync(at<char>(workspace, pl.off_small), 0, pl.small_bytes, st));
   if (small_step && small_adam_persistent_ok(b, mc)) {
@@ -1170,7 +1225,7 @@ int prb_mc_adam(prb_model* model, const prb_space_desc* space, const prb_acq_des
 
   // kernel structures that do not separate: the six-launch fused step on a single column panel
   const bool generic_fused = !fused_step && !small_step && int64_t(b) * mc <= pl.C && !sep_space &&
-                             getenv("PRB_NO_FUSED_STEP") == nullptr;
+                             !env_knobs().no_fused_step;
 
   auto one_iter = [&]() -> int {
     if (generic_fused)
@@ -1194,40 +1249,9 @@ int prb_mc_adam(prb_model* model, const prb_space_desc* space, const prb_acq_des
     return PRB_OK;
   };
 
-  bool graphed = false;
-  if (st != nullptr && maxiter >= 4) {
-    // Capture ONE optimisation step and replay it: removes ~10 launches x maxiter of host latency (the reference spends
-    // its time exactly there at experiment sizes: 800 host-driven steps per BO iteration).
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
-    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-      const unsigned long long l0 = g_launches;
-      int r = one_iter();
-      const unsigned long long per_iter = g_launches - l0;
-      cudaError_t e = cudaStreamEndCapture(st, &graph);
-      if (r == PRB_OK && e == cudaSuccess && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
-        cudaError_t le = cudaSuccess;
-        for (int it = 0; it < maxiter && le == cudaSuccess; ++it) le = cudaGraphLaunch(exec, st);
-        graphed = (le == cudaSuccess);
-        if (graphed) g_launches += per_iter * (unsigned long long)(maxiter - 1);  // replays of the captured step
-        // exec/graph must outlive the enqueued launches: release after the stream drains
-        cudaStreamSynchronize(st);
-        cudaGraphExecDestroy(exec);
-        if (!graphed) {
-          cudaGraphDestroy(graph);
-          return cuda_fail(le, "cudaGraphLaunch");
-        }
-      }
-      if (graph) cudaGraphDestroy(graph);
-      (void)cudaGetLastError();
-    }
-  }
-  if (!graphed) {
-    for (int it = 0; it < maxiter; ++it) {
-      rc = one_iter();
-      if (rc != PRB_OK) return rc;
-    }
-  }
+  // ONE optimisation step is captured and replayed maxiter times (cached executable graph, see replay_steps)
+  rc = replay_steps(*reinterpret_cast<Model*>(model), 0, one_iter, maxiter, st);
+  if (rc != PRB_OK) return rc;
   // final clamp + value-only evaluation (gen.py:338-341); this call also advances the EMA state like any forward
   if (generic_fused)
     return generic_step(m, sp, aq, pl, workspace, theta, lower, upper, theta, b, mc, u_int, u_cat, seed, offset, estimator,

@@ -561,7 +561,7 @@ cudaError_t make_operand_map(TensorMap* out, const double* base, int rows, int k
 //   32  when even 128-wide tiling leaves most SMs without a tile: small problems are bound by ONE SM's DMMA rate;
 //   128 one 8-warp CTA per SM (the generic-path kernels use this shape).
 static int pick_bn(const Model& m, int ncols_pad, bool upper) {
-  static const int force = getenv("PRB_BN") ? atoi(getenv("PRB_BN")) : 0;
+  const int force = env_knobs().force_bn;
   if (force == 32 || force == 64 || force == 128) return force;
   const int tiles128 = ((upper ? m.Mp2 : m.Mp1) / T_BM) * (ncols_pad / 128);
   return tiles128 < 120 ? 32 : 64;
@@ -577,7 +577,7 @@ static void fill_common(TmaGemmParams& p, const Model& m, int ncols_pad, bool up
   // scheduling groups of ~4 waves of CTAs (PRB_GROUP_WAVES overrides; 0 = row-tile-major order).  Measured at n = 1000,
   // 65 536 columns: the upper product's DRAM reads fall from 2.34 GB to 0.57 GB per launch (algorithmic 0.54 GB; L2 hit rate
   // 64 % -> 86 %) at unchanged run time -- the kernel is tensor-pipe bound -- with groups of 1 wave 1.5 % slower.
-  static const int waves = getenv("PRB_GROUP_WAVES") ? atoi(getenv("PRB_GROUP_WAVES")) : 4;
+  const int waves = env_knobs().group_waves;
   const int slots = (bn == 64 ? 2 : 1) * 148;
   int g = waves > 0 ? (waves * slots) / (p.mtiles > 0 ? p.mtiles : 1) : p.ntiles;
   if (g < 1) g = 1;

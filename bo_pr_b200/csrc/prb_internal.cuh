@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "prb200.h"
 
 namespace prb {
@@ -55,8 +57,18 @@ constexpr int GEMM_BK = 16;   // contraction tile; Kp is a multiple of it
 constexpr int GRAD_JSPLIT_ROWS = 128;  // rows of W handled by one CTA of the gradient contraction
 
 // number of kernels this library has launched (prb_launch_count(); bench.py reports it as gpu_launches)
-extern unsigned long long g_launches;
-inline void count_launch(int k = 1) { g_launches += (unsigned long long)k; }
+extern std::atomic<unsigned long long> g_launches;
+inline void count_launch(int k = 1) { g_launches.fetch_add((unsigned long long)k, std::memory_order_relaxed); }
+
+// Tuning / A-B knobs from the environment, read ONCE per process (first use), never on a hot call.
+struct EnvKnobs {
+  bool no_pdl;          // PRB_NO_PDL: plain stream-ordered launches inside the fused steps
+  bool no_fused_step;   // PRB_NO_FUSED_STEP: the unfused multi-launch sequence everywhere
+  long panel_mb;        // PRB_PANEL_MB: column-panel budget override (0 = default)
+  int force_bn;         // PRB_BN: column-tile width override of the separable products (0 = pick by tile count)
+  int group_waves;      // PRB_GROUP_WAVES: scheduling-group size in waves of CTAs (default 4; 0 = row-tile-major)
+};
+const EnvKnobs& env_knobs();
 
 // ---- optional per-kernel timing (prb_profile_enable / prb_profile_read): CUDA events around every launch ---------------
 enum KernelId {
@@ -161,6 +173,16 @@ struct Model {
   uint32_t* Zbits;                      // [max(Mp1, Mp2)] bit codes of the training points
   double* sep_tab;                      // [64] binary-factor value by Hamming distance
   int opt_dedup;                        // PRB_OPT_DEDUP
+  int opt_unfused;                      // PRB_OPT_UNFUSED: plain calls take the multi-launch sequence (cross-check path)
+  // completion counter of the fused step kernels' "last CTA" logic: zeroed once here, re-armed by the kernels themselves
+  unsigned int* done_ctr;
+  // cached executable graphs of the fused optimisation loops (slot 0: prb_mc_adam, 1: prb_analytic_adam).  A later call
+  // re-captures its step (a few microseconds) and UPDATES the cached executable in place instead of instantiating a new one;
+  // executables that could not be updated (different launch topology) are parked and destroyed with the model, so no call
+  // ever has to wait for the stream to drain.
+  cudaGraphExec_t graph_exec[2];
+  cudaGraphExec_t graph_dead[16];
+  int n_graph_dead;
   // random-Fourier-feature posterior sample (prb_rff_model_create): f(x) = rff_scale * sum_j rff_w[j] cos(x . W[:, j] + b_j);
   // rff_m > 0 marks the model as deterministic -- no GP state, every engine call goes to rff_eval_kernel
   int rff_m;

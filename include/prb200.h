@@ -9,9 +9,11 @@
  * Conventions
  *  - every function returns 0 (PRB_OK) or a negative prb_status; nothing throws across the ABI
  *  - all tensor pointers are CALLER-OWNED DEVICE memory, contiguous, float64 unless stated, on the current device
- *  - the hot entry points never allocate and never synchronise; work is enqueued on `stream` (a cudaStream_t
- *    passed as void*; NULL = legacy default stream); scratch comes from a caller-provided workspace whose size
- *    prb_workspace_bytes() reports
+ *  - the hot entry points never allocate device memory and never synchronise; work is enqueued on `stream` (a
+ *    cudaStream_t passed as void*; NULL = legacy default stream); scratch comes from a caller-provided workspace whose
+ *    size prb_workspace_bytes() reports.  prb_mc_adam / prb_analytic_adam replay one captured optimisation step as a CUDA
+ *    graph: the FIRST call on a model (or the first with a different launch topology) instantiates the executable graph
+ *    and caches it on the model; later calls update it in place (no instantiation, no synchronisation)
  *  - a prb_model is bound to the device that was current at creation; it is not thread-safe
  *  - there is NO CPU implementation behind this ABI
  */
@@ -154,6 +156,9 @@ int prb_model_destroy(prb_model* model);
  *   the work saved grows as the PR distribution concentrates (p -> 0/1).  Throughput with this option on must be reported
  *   separately from the per (candidate x MC sample) figure.                                                            */
 #define PRB_OPT_DEDUP 1
+/* PRB_OPT_UNFUSED (default 0): prb_mc_value_grad / prb_mc_screen take the stream-ordered multi-launch sequence (one kernel
+ *   per stage) instead of the fused single-panel step.  Same arithmetic; kept as the cross-check path of the test-suite. */
+#define PRB_OPT_UNFUSED 2
 int prb_model_set_option(prb_model* model, int32_t option, int64_t value);
 int prb_model_n(const prb_model* model);
 int prb_model_dk(const prb_model* model);

@@ -59,8 +59,33 @@ def test_chunking_is_bitwise_invariant():
         val = pr(X)
         grad = torch.autograd.grad(val.sum(), X)[0]
         outs.append((val.detach().clone(), grad.clone()))
-    for v, gr in outs[1:]:
-        assert torch.equal(v, outs[0][0]) and torch.equal(gr, outs[0][1])
+    # multi-panel calls (the stream-ordered multi-launch sequence) agree bitwise with each other ...
+    assert torch.equal(outs[1][0], outs[2][0]) and torch.equal(outs[1][1], outs[2][1])
+    # ... and with the single-panel fused step up to the order of the row-tile partial sums
+    _assert_close(outs[0][0], outs[1][0], "fused vs multi-panel value", rtol=1e-13, atol=1e-15)
+    _assert_close(outs[0][1], outs[1][1], "fused vs multi-panel gradient", rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("n,b,mc,acq", [(1000, 6, 256, "ei"), (300, 5, 128, "ucb")])
+def test_fused_step_equals_unfused_sequence(n, b, mc, acq):
+    """prb_mc_value_grad on one column panel runs the fused step (prep -> lower -> [epilogue] -> upper -> finish, chained by
+    programmatic dependent launch); PRB_OPT_UNFUSED selects the one-kernel-per-stage sequence.  Same arithmetic, different
+    kernels and reduction trees: values, gradients, per-sample values and EMA state must agree to rounding."""
+    from bo_pr_b200 import _capi as capi
+    g = _problem(n, mc, acq)
+    theta = make_theta(b).to(DEV)
+    res = []
+    for unfused in (0, 1):
+        pr = product_mc_pr(g, DEV)
+        pr.acq_function.state.set_option(capi.PRB_OPT_UNFUSED, unfused)
+        pr._ma_state.copy_(torch.tensor([2.0, 0.03], dtype=torch.float64))
+        X = theta.clone().requires_grad_(True)
+        val = pr(X)
+        grad = torch.autograd.grad(val.sum(), X)[0]
+        res.append((val.detach().clone(), grad.clone(), pr._ma_state.clone()))
+    _assert_close(res[0][0], res[1][0], "value", rtol=1e-13, atol=1e-15)
+    _assert_close(res[0][1], res[1][1], "gradient", rtol=1e-11, atol=1e-14)
+    _assert_close(res[0][2], res[1][2], "EMA state", rtol=1e-13)
 
 
 def test_full_size_properties():
