@@ -1,32 +1,38 @@
 #!/usr/bin/env python
 """Benchmark of the PR acquisition hot path (BASELINE.json: "PR acqf value+grad evals/sec (cand x MC)").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ackley13|rosenbrock|chemistry]
 
-One "step" = one MC-PR EI value+gradient evaluation of `restarts` restarts x `mc` MC samples against an exact GP with
-n_train training points (d = 13: 3 continuous + 10 binary, kernel "mixed") -- BASELINE.json configs[4] at the size its
-target names (n_train = 1000, 64 restarts, 1024 MC samples).  One eval = one (candidate x MC sample) base-acquisition
-value+gradient.  Multi-GPU: restarts are sharded, GP state replicated, no data-path collective (weak scaling: 64
-restarts PER GPU); NCCL is used once, after the timed region, for the best-candidate allgather/argmax.
+One "step" = one MC-PR value+gradient evaluation of `restarts` restarts x `mc` MC samples against an exact GP with n_train
+training points -- BASELINE.json configs[4] at the size its target names (n_train = 1000, d = 13: 3 continuous + 10 binary,
+kernel "mixed", EI, 64 restarts, 1024 MC samples).  One eval = one (candidate x MC sample) base-acquisition
+value+gradient.
+
+Multi-GPU is the north-star split: the 64 restarts are the TOTAL, restart r -> rank r mod G, the GP
+state is replicated, no collective inside a step ("scaling": "strong").  The weak-scaling figure (64 restarts per rank)
+is an extra key.  NCCL appears where the path has its exchange: the all-gathers of the sharded raw-sample screening and of
+the per-restart results inside the `bo_iter_sharded` leg (optimize_acqf(shard=True)), timed there.
 
 `value`      device-resident inputs, straight through the C ABI (prb_mc_value_grad), CUDA events, max over ranks.
 `e2e`        the same metric through the reference-facing API (MCProbabilisticReparameterization.forward + autograd),
              theta in pinned HOST memory, host<->device copies inside the timed region.
-`roofline`   the dominant kernel (the FP64 DMMA triangular products), timed live with CUDA events per launch.
+`roofline`   the dominant kernel (the FP64 DMMA triangular products), timed live with CUDA events per launch; the
+             denominator is measured in the same run (`peak_live`: mma.sync.m8n8k4.f64 from registers) next to the
+             library baseline for the same two products (cuBLAS dtrmm / dgemm).
 `cpu_baseline` / `--impl reference`: the CPU oracle (port of the reference path: reference L1 semantics over restated
              BoTorch/GPyTorch arithmetic; the reference is pure Python and BoTorch is not installed, so there is no
-             oracle/_ref) on the box's host cores, on a bounded sample of the same workload.
+             oracle/_ref) on the box's host cores.  `--impl reference` runs the SAME step (all restarts).
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import glob
 import json
 import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -37,10 +43,8 @@ import torch  # noqa: E402
 
 METRIC = "pr_acqf_value_grad_evals_per_sec"
 UNIT = "evals/s"
-FP64_PEAK_TFLOPS = 37.1  # measured on this pool's B200: DMMA microbenchmark, profiles/r01_fp64_peak_microbench.txt
-NCU_TRAFFIC_BYTES_PER_LAUNCH = (17.44e6 + 484.57e6 + 572.04e6 + 15.42e6) / 2  # profiles/r01_trgemm_tma_ncu.txt
-FP64_PEAK_SOURCE = ("measured FP64 DMMA peak (tools/microbench/fp64_peak.cu, profiles/r01_fp64_peak_microbench.txt; "
-                    "cuBLAS DGEMM 35.5 TF/s, profiles/r01_cublas_dgemm_peak.json); MEASURED_PEAKS.json has no FP64 entry")
+FP64_PEAK_FALLBACK = 37.1  # DMMA microbenchmark of round 1 (profiles/r01_fp64_peak_microbench.txt); used if the live run fails
+TRAFFIC_TABLE = os.path.join(ROOT, "profiles", "r02_traffic.json")  # ncu dram bytes per launch, keyed "workload,n,b,mc"
 
 
 def parse_args():
@@ -49,19 +53,28 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ackley13", choices=["ackley13", "rosenbrock", "chemistry"])
     ap.add_argument("--n-train", type=int, default=1000)
-    ap.add_argument("--restarts", type=int, default=64, help="restarts per GPU")
+    ap.add_argument("--restarts", type=int, default=64, help="restarts in TOTAL (sharded r mod G over the ranks)")
     ap.add_argument("--mc", type=int, default=1024)
-    ap.add_argument("--cpu-restarts", type=int, default=8, help="restarts in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-restarts", type=int, default=8, help="restarts in the bounded cpu_baseline sample (ours arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-bo-iter", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip value-only / dedup / generic / weak / library legs")
     return ap.parse_args()
 
 
+WORKLOADS = {
+    "ackley13": "d=13 (3 continuous + 10 binary, kernel 'mixed': Matern ARD x isotropic Matern over the binary dims), EI",
+    "rosenbrock": "d=10 (4 continuous + 6 ordinals {0..3} inside ONE ARD Matern: the kernel does not separate), UCB",
+    "chemistry": "d=22 one-hot / 5 numeric (2 continuous + categoricals 4, 12, 4; kernel 'mixed_categorical'), EI",
+}
+
+
 def workload_name(a):
-    return (f"synthetic PR-EI value+grad: n_train={a.n_train}, d=13 (3 continuous + 10 binary, kernel 'mixed'), "
-            f"{a.restarts} restarts/GPU x {a.mc} MC samples, tau=0.1, reinforce_ma")
+    return (f"synthetic PR value+grad [{a.workload}]: n_train={a.n_train}, {WORKLOADS[a.workload]}, "
+            f"{a.restarts} restarts in total x {a.mc} MC samples, tau=0.1, reinforce_ma")
 
 
 def algorithmic_flops_per_eval(n: int) -> float:
@@ -69,26 +82,48 @@ def algorithmic_flops_per_eval(n: int) -> float:
     return 2.0 * n * n + 100.0 * n
 
 
+def make_workload(a, device="cpu"):
+    """(problem dict, theta_all [restarts, 1, d]) for the named synthetic shape; everything seeded."""
+    if a.workload == "ackley13":
+        from bench_workload import make_problem, make_theta
+        g = make_problem(a.n_train, seed=0, device=device)
+        g["case"]["mc"] = a.mc
+        g["base_samples"] = g["base_samples_categorical"] = None
+        return g, make_theta(a.restarts, seed=1)
+    from bench_workload import make_generic_problem
+    return make_generic_problem(a.workload, a.n_train, a.restarts, a.mc)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # CPU oracle leg (cpu_baseline and --impl reference)
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_oracle_step_fn(problem, mc, restarts, seed=1):
-    from bench_workload import make_theta, sobol_base_samples
+def cpu_oracle_step_fn(problem, theta, mc, chunk=2, mc_chunk=None):
+    """One value+grad step of the CPU oracle over `theta` (all of it), restarts in chunks of `chunk` to bound the
+    [B, n, d] temporaries (the reference chunks too: batch_limit); `mc_chunk` = the reference's own pr_batch_limit."""
+    from bench_workload import sobol_base_samples
     from oracle import pr_oracle as P
     from tests.golden_util import oracle_acq, oracle_space
 
     torch.set_num_threads(os.cpu_count() or 1)
     space, oacq = oracle_space(problem), oracle_acq(problem)
-    theta = make_theta(restarts, seed=seed)
-    base = sobol_base_samples(mc)
+    c = problem["case"]
+    base_i = problem.get("base_samples")
+    base_c = problem.get("base_samples_categorical")
+    if base_i is None and len(c["integer_indices"]) > 0:
+        base_i = sobol_base_samples(mc, n_cols=len(c["integer_indices"]))
+    if base_c is None and c["categorical_features"]:
+        base_c = sobol_base_samples(mc, n_cols=len(c["categorical_features"]), seed=4321)
+    acq = oacq
+    if mc_chunk is not None:
+        acq = lambda X: torch.cat([oacq(X[:, s:s + mc_chunk]) for s in range(0, X.shape[1], mc_chunk)], dim=1)  # noqa: E731
     state = {"c": 0.0, "h": 0.0}
+    b = theta.shape[0]
 
     def step():
-        # restarts in chunks of 2 to bound the oracle's [B, n, d] temporaries (the reference chunks too: batch_limit)
         vals = []
-        for s in range(0, restarts, 2):
-            r = P.mc_pr(space, theta[s:s + 2], oacq, base, None, grad_estimator="reinforce_ma", ma_counter=state["c"],
-                        ma_hidden=state["h"])
+        for s in range(0, b, chunk):
+            r = P.mc_pr(space, theta[s:s + chunk], acq, base_i, base_c, grad_estimator="reinforce_ma",
+                        ma_counter=state["c"], ma_hidden=state["h"], apply_numeric=c["apply_numeric"])
             vals.append(r.value)
         state["c"], state["h"] = r.ma_counter, r.ma_hidden
         return torch.cat(vals)
@@ -105,27 +140,36 @@ def time_cpu(step, steps, warmup):
     return (time.perf_counter() - t0) / steps
 
 
+def config_of(a, world, extra=None):
+    cfg = {"workload": workload_name(a), "n_train": a.n_train, "restarts_total": a.restarts, "mc": a.mc,
+           "evals_per_step": a.restarts * a.mc}
+    cfg.update(extra or {})
+    return cfg
+
+
 def run_reference(a):
+    """The reference arm: the CPU port of the path on all host threads, the SAME step as the ours-arm (all restarts)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from bench_workload import make_problem
-
-    problem = make_problem(a.n_train, seed=0)
-    problem["case"]["mc"] = a.mc
-    b = a.cpu_restarts
-    step = cpu_oracle_step_fn(problem, a.mc, b)
+    problem, theta = make_workload(a)
+    step = cpu_oracle_step_fn(problem, theta, a.mc, chunk=2)
     sec = time_cpu(step, a.steps, a.warmup)
-    value = b * a.mc / sec
+    value = a.restarts * a.mc / sec
     cores = torch.get_num_threads()
-    sample = f"{b} of the {a.restarts} restarts x {a.mc} MC samples per step (value+grad), torch CPU float64"
+    # "as shipped" chunking (SURVEY.md 8d): restart batches of 5, MC chunks of pr_batch_limit = 32 -- bounded sample
+    nb = min(10, a.restarts)
+    shipped = cpu_oracle_step_fn(problem, theta[:nb], a.mc, chunk=5, mc_chunk=32)
+    sec_s = time_cpu(shipped, 2, 1)
+    sample = f"all {a.restarts} restarts x {a.mc} MC samples per step (value+grad), restart chunks of 2, torch CPU float64"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "n_train": a.n_train, "restarts_per_gpu": a.restarts, "mc": a.mc},
+        "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": config_of(a, 1),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "as_shipped": {"value": nb * a.mc / sec_s, "unit": UNIT, "sample": f"{nb} restarts in batches of 5, MC chunks of 32 "
+                       "(the reference's batch_limit / pr_batch_limit), 2 steps"},
     }
     print(json.dumps(line), flush=True)
 
@@ -165,10 +209,7 @@ def bo_iter_ours(dev, one_batch=False, repeats=3):
         t0 = time.perf_counter()
         cand, vals = B.optimize_acqf(pr, bounds, q=1, num_restarts=20, raw_samples=1024, options=opts, stochastic=True,
                                      return_best_only=False)
-        final = pr.sample_candidates(cand)
-        with torch.no_grad():
-            best = acq(final).argmax()
-        chosen = final[best].cpu()
+        chosen = B.finalize_candidates(pr, cand)[0].cpu()
         torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
     return sorted(times[1:])[len(times[1:]) // 2], chosen
@@ -207,6 +248,57 @@ def bo_iter_cpu():
     with torch.no_grad():
         oacq(final).argmax()
     return time.perf_counter() - t0
+
+
+def bo_iter_sharded(a, problem, acq, dev, dist, world, repeats=2):
+    """One acquisition-optimisation segment at the benchmark's n_train with the work split over the ranks as `north_star`
+    describes: GP state replicated (each rank builds it from the same data), raw samples AND restarts sharded r mod G, one
+    all-gather for the screening values, one for the per-restart results, argmax + candidate sampling + base-AF re-scoring
+    replicated.  64 restarts x 1024 raw samples x 128 MC samples, 200 Adam steps.  Wall clock, max over ranks."""
+    import bo_pr_b200 as B
+    from tests.product_util import product_acq, product_mc_pr
+    d = problem["case"]["dim"]
+    bounds = torch.stack([torch.zeros(d, dtype=torch.float64), torch.ones(d, dtype=torch.float64)]).to(dev)
+    g128 = dict(problem, case=dict(problem["case"], mc=128, grad_estimator="reinforce_ma"))
+
+    def sync():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    best = None
+    for rep in range(repeats + 1):
+        torch.manual_seed(rep)
+        sync()
+        t0 = time.perf_counter()
+        acq_r = product_acq(problem, dev)  # GP-state replication: K, Cholesky, inverse factor, alpha on this rank
+        acq_r.state
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        pr = product_mc_pr(g128, dev, acq=acq_r)
+        opts = {"maxiter": 200, "nonnegative": problem["case"]["acq"] == "ei", "seed": rep, "init_batch_limit": 128}
+        ics = B.gen_batch_initial_conditions(pr, bounds, q=1, num_restarts=a.restarts, raw_samples=1024, options=opts,
+                                             shard=world > 1)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        cand, vals = B.optimize_acqf(pr, bounds, q=1, num_restarts=a.restarts, options=opts, batch_initial_conditions=ics,
+                                     stochastic=True, return_best_only=False, shard=world > 1)
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        chosen, chosen_val = B.finalize_candidates(pr, cand, seed=rep)
+        chosen.cpu()
+        torch.cuda.synchronize()
+        t4 = time.perf_counter()
+        ph = torch.tensor([t4 - t0, t1 - t0, t2 - t1, t3 - t2, t4 - t3], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+        if rep > 0 and (best is None or float(ph[0]) < best[0]):
+            best = ph.tolist()
+    return {"workload": f"{a.workload} shape at n_train={a.n_train}: 1024 raw samples, {a.restarts} restarts x 200 Adam "
+                        "steps, mc=128, candidate sampling + base-AF re-scoring on the device",
+            "sec": best[0], "phases_sec": {"gp_state_build_replicated": best[1], "raw_sample_screening_sharded": best[2],
+                                           "adam_sharded_plus_allgather": best[3], "finalise": best[4]},
+            "n_gpus": world, "timing": "wall clock between device synchronisations, max over ranks, best of 2"}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -254,6 +346,62 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def cuda_time(fn, steps, warmup, stream):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def library_baseline(n, cols, dev):
+    """cuBLAS on the same two products (outside the timed region): dtrmm for Linv K* and Linv^T V (what a library-only
+    implementation would call once k* is materialised) and the dense dgemm GPyTorch itself runs.  ms per step (both
+    products), or None where the call could not be made."""
+    out = {"cublas_dtrmm_ms": None, "cublas_dgemm_ms": None, "cublas_dgemm_tflops_dense": None}
+    stream = torch.cuda.current_stream()
+    try:
+        A = torch.randn(n, n, dtype=torch.float64, device=dev).tril_()
+        Bm = torch.randn(cols, n, dtype=torch.float64, device=dev)  # row-major [cols, n] == column-major [n, cols]
+        Cm = torch.empty_like(Bm)
+        ms = cuda_time(lambda: (torch.matmul(Bm, A.t(), out=Cm), torch.matmul(Cm, A, out=Bm)), 3, 1, stream)
+        out["cublas_dgemm_ms"] = ms
+        out["cublas_dgemm_tflops_dense"] = 2 * 2.0 * n * n * cols / (ms * 1e-3) / 1e12
+        cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "lib", "libcublas.so*"))
+        for sp in sys.path:
+            cands += glob.glob(os.path.join(sp, "nvidia", "cublas", "lib", "libcublas.so*"))
+        lib = None
+        for pth in cands:
+            try:
+                lib = C.CDLL(pth)
+                break
+            except OSError:
+                continue
+        if lib is not None:
+            fn = lib.cublasDtrmm_v2
+            fn.restype = C.c_int
+            fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                           C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+            handle = torch.cuda.current_blas_handle()
+            one = C.c_double(1.0)
+
+            def trmm(trans, src, dst):  # side = left (0), uplo = lower (0), diag = non-unit (0); column-major [n, cols]
+                rc = fn(handle, 0, 0, trans, 0, n, cols, C.addressof(one), A.data_ptr(), n, src.data_ptr(), n,
+                        dst.data_ptr(), n)
+                if rc != 0:
+                    raise RuntimeError(f"cublasDtrmm_v2 status {rc}")
+
+            out["cublas_dtrmm_ms"] = cuda_time(lambda: (trmm(0, Bm, Cm), trmm(1, Cm, Bm)), 3, 1, stream)
+    except Exception as e:  # the baseline is a courtesy figure; never fail the bench over it
+        out["error"] = repr(e)[:200]
+    return out
+
+
 def run_ours(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -267,35 +415,36 @@ def run_ours(a):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    from bench_workload import make_problem, make_theta
     from bo_pr_b200 import _capi as capi
     from bo_pr_b200.acquisition import acq_desc_of
     from tests.product_util import product_acq, product_mc_pr  # thin constructors over the public API
 
     lib = capi.load_library()
-    n, b, mc = a.n_train, a.restarts, a.mc
-    problem = make_problem(n, seed=0, device=dev)
-    problem["case"]["mc"] = mc
-    problem["base_samples"] = None
-    problem["base_samples_categorical"] = None
+    n, mc = a.n_train, a.mc
+    problem, theta_all = make_workload(a, device=dev)
     acq = product_acq(problem, dev)
     state = acq.state  # GP state replicated on every rank (built from the same seeded data)
-    theta = make_theta(b, seed=1 + rank)  # this rank's restarts
+    theta = theta_all[rank::world].contiguous()  # restart r -> rank r mod G
+    b = theta.shape[0]
     theta_dev = theta.to(dev).reshape(b, -1).contiguous()
     d = theta_dev.shape[-1]
+    sep = a.workload == "ackley13"
 
-    # ---- cpu_baseline leg, part 1 (rank 0, N = 1): before the CPU port is timed as the baseline, a slice of this very
-    # workload is checked against it (the oracle is the checker here, never the thing measured as `value`)
-    pr = product_mc_pr(dict(problem, case=dict(problem["case"], grad_estimator="reinforce_ma")), dev, acq=acq)
+    # ---- parity gate (rank 0, N = 1): before the CPU port is timed as the baseline, a slice of this very workload is
+    # checked against it (the oracle is the checker here, never the thing measured as `value`)
+    prob_ma = dict(problem, case=dict(problem["case"], grad_estimator="reinforce_ma"))
+    pr = product_mc_pr(prob_ma, dev, acq=acq)
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         from oracle import pr_oracle as P
         from tests.golden_util import oracle_acq, oracle_space
         from tests.product_util import close
         rnd = pr.input_transform["round"]
         rnd.ensure_base_samples(1, dev)
+        ui, uc = rnd.base_sample_ptrs()
         Xs = theta[:2].clone()
-        ref = P.mc_pr(oracle_space(problem), Xs, oracle_acq(problem), rnd.base_samples.cpu(), None,
-                      grad_estimator="reinforce_ma")
+        ref = P.mc_pr(oracle_space(problem), Xs, oracle_acq(problem), None if ui is None else ui.cpu(),
+                      None if uc is None else uc.cpu(), grad_estimator="reinforce_ma",
+                      apply_numeric=problem["case"]["apply_numeric"])
         Xd = Xs.to(dev).requires_grad_(True)
         v = pr(Xd)
         gr = torch.autograd.grad(v.sum(), Xd)[0]
@@ -307,92 +456,63 @@ def run_ours(a):
 
     # ---- device-resident throughput through the C ABI (Philox drawn on the fly: u_int = u_cat = NULL) -----------------
     sp, aq = pr._space(), acq_desc_of(acq)
-    ones = torch.ones(b, dtype=torch.float64, device=dev)
-    value = torch.empty(b, dtype=torch.float64, device=dev)
-    grad = torch.empty(b, d, dtype=torch.float64, device=dev)
-    ma = torch.zeros(2, dtype=torch.float64, device=dev)
-    ws = state.workspace(b * mc, d, b)
     stream = torch.cuda.current_stream()
 
-    def step():
-        capi.check(lib.prb_mc_value_grad(state.handle, C.byref(sp), C.byref(aq), theta_dev.data_ptr(), b, mc, None, None,
-                                         0, 0, capi.PRB_EST_REINFORCE_MA, ma.data_ptr(), 1, ones.data_ptr(),
-                                         value.data_ptr(), grad.data_ptr(), None, ws.data_ptr(), ws.numel(), 0,
-                                         stream.cuda_stream), "prb_mc_value_grad")
+    def make_step(theta_d, with_grad=True):
+        bb = theta_d.shape[0]
+        ones = torch.ones(bb, dtype=torch.float64, device=dev)
+        value = torch.empty(bb, dtype=torch.float64, device=dev)
+        grad = torch.empty(bb, d, dtype=torch.float64, device=dev)
+        ma = torch.zeros(2, dtype=torch.float64, device=dev)
+        ws = state.workspace(bb * mc, d, bb)
+
+        def step():
+            capi.check(lib.prb_mc_value_grad(state.handle, C.byref(sp), C.byref(aq), theta_d.data_ptr(), bb, mc, None,
+                                             None, 0, 0, capi.PRB_EST_REINFORCE_MA, ma.data_ptr(), 1,
+                                             ones.data_ptr() if with_grad else None, value.data_ptr(),
+                                             grad.data_ptr() if with_grad else None, None, ws.data_ptr(), ws.numel(), 0,
+                                             stream.cuda_stream), "prb_mc_value_grad")
+        step.keep = (ones, value, grad, ma, ws)
+        return step
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(a.warmup):
-        step()
-    barrier()
+    def timed(step_fn, steps, warmup):
+        for _ in range(warmup):
+            step_fn()
+        barrier()
+        l0 = lib.prb_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step_fn()
+        e1.record(stream)
+        barrier()
+        launches = torch.tensor([float(lib.prb_launch_count() - l0)], dtype=torch.float64, device=dev)
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+        return float(ms) / steps, int(launches)
+
+    step = make_step(theta_dev)
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    l0 = lib.prb_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(a.steps):
-        step()
-    e1.record(stream)
-    barrier()
-    launches = int(lib.prb_launch_count() - l0)
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(ms) / a.steps
-    evals_per_step = world * b * mc
+    ms_per_step, launches = timed(step, a.steps, a.warmup)
+    evals_per_step = a.restarts * mc
     value_evals = evals_per_step / (ms_per_step * 1e-3)
 
-    # ---- value-only evaluation (raw-sample screening, gen_batch_initial_conditions): lower product only -----------------
-    value_only = None
-    if rank == 0:
-        def vstep():
-            capi.check(lib.prb_mc_value_grad(state.handle, C.byref(sp), C.byref(aq), theta_dev.data_ptr(), b, mc, None,
-                                             None, 0, 0, capi.PRB_EST_REINFORCE_MA, ma.data_ptr(), 1, None,
-                                             value.data_ptr(), None, None, ws.data_ptr(), ws.numel(), 0,
-                                             stream.cuda_stream), "prb_mc_value_grad")
-        for _ in range(a.warmup):
-            vstep()
-        torch.cuda.synchronize()
-        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        v0.record(stream)
-        for _ in range(a.steps):
-            vstep()
-        v1.record(stream)
-        torch.cuda.synchronize()
-        vms = v0.elapsed_time(v1) / a.steps
-        # F_v(n) = n^2 + ~70 n flop per evaluation (one triangular product + kernel + dots)
-        value_only = {"value": b * mc / (vms * 1e-3), "unit": UNIT, "ms_per_step": vms, "n_gpus": 1,
-                      "roofline_frac": (b * mc * (n * n + 70.0 * n) / (vms * 1e-3)) / (FP64_PEAK_TFLOPS * 1e12),
-                      "note": "value-only calls (no gradient): the screening of raw samples before the multi-start "
-                              "optimisation; fraction of the FP64 DMMA peak on F_v(n) = n^2 + 70 n flop per evaluation"}
-
-    # ---- the same step with MC de-duplication (PRB_OPT_DEDUP): reported separately, never as `value` ---------------------
-    dedup = None
-    if rank == 0:
-        z = torch.empty(b, mc, pr._space().n_int, dtype=torch.uint8, device=dev)
-        capi.check(lib.prb_pr_sample(C.byref(sp), theta_dev.data_ptr(), b, mc, None, None, 0, 0, None, z.data_ptr(), None,
-                                     stream.cuda_stream), "prb_pr_sample")
-        codes = (z.to(torch.int64) << torch.arange(z.shape[-1], device=dev)).sum(-1)
-        n_unique = sum(int(torch.unique(codes[r]).numel()) for r in range(b))
-        state.set_option(capi.PRB_OPT_DEDUP, 1)
-        for _ in range(a.warmup):
-            step()
-        torch.cuda.synchronize()
-        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        d0.record(stream)
-        for _ in range(a.steps):
-            step()
-        d1.record(stream)
-        torch.cuda.synchronize()
-        state.set_option(capi.PRB_OPT_DEDUP, 0)
-        dms = d0.elapsed_time(d1) / a.steps
-        dedup = {"value": b * mc / (dms * 1e-3), "unit": UNIT, "ms_per_step": dms, "n_gpus": 1,
-                 "unique_columns": n_unique, "unique_fraction": n_unique / (b * mc),
-                 "note": "PRB_OPT_DEDUP: one base-AF evaluation per unique (restart, discrete configuration), weighted by "
-                         "multiplicity; identical results up to summation order; theta ~ U[0,1] (as PR converges the "
-                         "unique fraction falls further). evals/s still counted per candidate x MC sample."}
+    # ---- weak scaling (extra): 64 restarts on EVERY rank, as round 1 reported --------------------------------------------
+    weak = None
+    if world > 1 and not a.no_extras:
+        from bench_workload import make_theta
+        th_w = (make_theta(a.restarts, seed=1 + rank) if a.workload == "ackley13" else theta_all).to(dev)
+        th_w = th_w.reshape(a.restarts, -1).contiguous()
+        w_ms, _ = timed(make_step(th_w), max(5, a.steps // 2), a.warmup)
+        weak = {"value": world * a.restarts * mc / (w_ms * 1e-3), "unit": UNIT, "ms_per_step": w_ms,
+                "restarts_per_gpu": a.restarts, "scaling": "weak"}
 
     # ---- end to end through the reference-facing API, host buffers ----------------------------------------------------
     e2e = None
@@ -420,14 +540,42 @@ def run_ours(a):
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": evals_per_step / (float(t) / a.steps), "unit": UNIT,
-               "h2d_bytes_per_step": world * theta_host.numel() * 8,
-               "d2h_bytes_per_step": world * (val_host.numel() + grad_host.numel()) * 8,
+               "h2d_bytes_per_step": a.restarts * d * 8, "d2h_bytes_per_step": a.restarts * (1 + d) * 8,
                "ms_per_step": float(t) / a.steps * 1e3}
     clocks = sampler.stop() if sampler is not None else None
+
+    # ---- value-only evaluation (raw-sample screening) and MC de-duplication: rank 0, N = 1, reported separately ---------
+    value_only = dedup = None
+    if rank == 0 and world == 1 and not a.no_extras:
+        vms = cuda_time(make_step(theta_dev, with_grad=False), a.steps, a.warmup, stream)
+        value_only = {"value": b * mc / (vms * 1e-3), "unit": UNIT, "ms_per_step": vms, "n_gpus": 1,
+                      "note": "value-only calls (no gradient): the screening of raw samples before the multi-start "
+                              "optimisation; F_v(n) = n^2 + 70 n flop per evaluation (SURVEY.md 8d)",
+                      "flop_per_eval": n * n + 70.0 * n}
+        if sep:
+            z = torch.empty(b, mc, sp.n_int, dtype=torch.uint8, device=dev)
+            capi.check(lib.prb_pr_sample(C.byref(sp), theta_dev.data_ptr(), b, mc, None, None, 0, 0, None, z.data_ptr(),
+                                         None, stream.cuda_stream), "prb_pr_sample")
+            codes = (z.to(torch.int64) << torch.arange(z.shape[-1], device=dev)).sum(-1)
+            n_unique = sum(int(torch.unique(codes[r]).numel()) for r in range(b))
+            state.set_option(capi.PRB_OPT_DEDUP, 1)
+            dms = cuda_time(step, a.steps, a.warmup, stream)
+            state.set_option(capi.PRB_OPT_DEDUP, 0)
+            dedup = {"value": b * mc / (dms * 1e-3), "unit": UNIT, "ms_per_step": dms, "n_gpus": 1,
+                     "unique_columns": n_unique, "unique_fraction": n_unique / (b * mc),
+                     "note": "PRB_OPT_DEDUP: one base-AF evaluation per unique (restart, discrete configuration), weighted "
+                             "by multiplicity; identical results up to summation order; theta ~ U[0,1] (as PR converges "
+                             "the unique fraction falls further). evals/s still counted per candidate x MC sample."}
 
     # ---- roofline of the dominant kernel: per-launch CUDA events inside the library (separate pass) --------------------
     roofline, breakdown = None, None
     if rank == 0:
+        peaks = {}
+        for mode, name in ((0, "dmma_m8n8k4"), (1, "dfma"), (2, "dmma_and_dfma_interleaved")):
+            tf = C.c_double(0.0)
+            if lib.prb_debug_fp64_peak(mode, C.byref(tf), stream.cuda_stream) == 0:
+                peaks[name] = tf.value
+        peak = peaks.get("dmma_m8n8k4") or FP64_PEAK_FALLBACK
         torch.cuda.synchronize()
         lib.prb_profile_enable(1)
         for _ in range(3):
@@ -440,43 +588,88 @@ def run_ours(a):
         breakdown = {nm: {"ms_per_step": msk[i] / 3, "launches_per_step": int(cnt[i]) // 3}
                      for i, nm in enumerate(capi.PROFILE_SLOT_NAMES) if cnt[i]}
         gemm_ms = (msk[2] + msk[4]) / 3
-        gemm_launches = int(cnt[2] + cnt[4]) // 3
+        gemm_launches = max(int(cnt[2] + cnt[4]) // 3, 1)
         # algorithmic flops of the two triangular products: n(n+1) flop per column each (+ 2n for the alpha row)
         flops_per_step = b * mc * (2.0 * n * (n + 1) + 2.0 * n)
         achieved = flops_per_step / (gemm_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "trgemm_tma_kernel<LOWER_GEN | UPPER_GRAD> (TMA + mbarrier "
-                    "pipeline, FP64 DMMA m8n8k4: Linv k* with k* generated in-kernel; Linv^T v with the gradient "
-                    "contraction fused into the epilogue)",
-                    "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
-                    "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if (n, b, mc) == (1000, 64, 1024) else None,
-                    "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum averaged over the two "
-                    "launches of a step (profiles/r01_trgemm_tma_ncu.txt: lower 0.017 + 0.485 GB, upper 0.572 + 0.015 GB);"
-                    " algorithmic HBM bytes per launch = the v panel once, 0.537 GB (written by the lower product, read by "
-                    "the upper one): 1.01x -- column tiles are scheduled in groups so that the row tiles of a column tile "
-                    "re-read the panel from L2 (2.34 GB of DRAM reads per upper launch before the grouped order)",
-                    "peak_source": FP64_PEAK_SOURCE,
-                    "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "launches_per_step": gemm_launches,
+        traffic = None
+        try:
+            traffic = json.load(open(TRAFFIC_TABLE)).get(f"{a.workload},{n},{b},{mc}")
+        except Exception:
+            pass
+        lib_base = library_baseline(n, b * mc, dev) if not a.no_extras else {}
+        roofline = {"bound": "tensor",
+                    "kernel": "trgemm_tma_kernel (TMA + mbarrier pipeline, FP64 DMMA m8n8k4): lower Linv k* "
+                              + ("with k* generated in-kernel" if sep else "from the k* panel")
+                              + "; upper Linv^T v with the gradient contraction fused into the epilogue",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": None if traffic is None else traffic.get("bytes_per_launch"),
+                    "traffic_source": None if traffic is None else traffic.get("source"),
+                    "algorithmic_hbm_bytes_per_step": 8.0 * (n * (n + 1) / 2 + n * (d + 1)) + 8.0 * b * d + 8.0 * b * (1 + d),
+                    "peak_source": "peak_live.dmma_m8n8k4: mma.sync.m8n8k4.f64 from registers on every SM, measured in this "
+                                   "run outside the timed region (prb_debug_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                    "peak_live": peaks, "library": lib_base,
+                    "avg_launch_ms": gemm_ms / gemm_launches, "launches_per_step": gemm_launches,
                     "share_of_step": gemm_ms / sum(v["ms_per_step"] for v in breakdown.values()),
-                    "algorithmic_flop_per_launch": flops_per_step / max(gemm_launches, 1),
-                    "whole_step_frac": evals_per_step / world * algorithmic_flops_per_eval(n) / (ms_per_step * 1e-3)
-                    / 1e12 / FP64_PEAK_TFLOPS}
+                    "algorithmic_flop_per_launch": flops_per_step / gemm_launches,
+                    "whole_step_frac": b * mc * algorithmic_flops_per_eval(n) / (ms_per_step * 1e-3) / 1e12 / peak}
+        if value_only is not None:
+            value_only["roofline_frac"] = value_only["value"] * value_only["flop_per_eval"] / (peak * 1e12)
 
-    # ---- the one collective of the path: best-candidate allgather + argmax (not timed) ---------------------------------
-    best = None
-    if dist is not None:
-        from bo_pr_b200.distributed import gather_best
-        best_val, best_theta, best_rank = gather_best(value, theta_dev)
-        best = {"value": float(best_val), "rank": int(best_rank)}
+    # ---- one BO iteration with the north-star sharding (all ranks) ---------------------------------------------------------
+    bo_sh = None
+    if not a.no_bo_iter:
+        bo_sh = bo_iter_sharded(a, problem, acq, dev, dist, world)
 
     # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cb = a.cpu_restarts
-        cpu_problem = dict(problem)
-        cstep = cpu_oracle_step_fn(cpu_problem, mc, cb)
+        cb = min(a.cpu_restarts, a.restarts)
+        cpu_problem = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in problem.items()}
+        cstep = cpu_oracle_step_fn(cpu_problem, theta_all[:cb], mc)
         sec = time_cpu(cstep, steps=24, warmup=2)
         cpu = {"value": cb * mc / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{cb} of the {b} restarts x {mc} MC samples per step (value+grad), 24 steps (~10 s), torch CPU float64"}
+               "sample": f"{cb} of the {a.restarts} restarts x {mc} MC samples per step (value+grad), 24 steps (~10 s), "
+                         "torch CPU float64"}
+
+    # ---- the generic (non-separable) kernel structure at the same size: rank 0, N = 1 ---------------------------------------
+    generic = None
+    if rank == 0 and world == 1 and not a.no_extras and a.workload == "ackley13":
+        generic = {}
+        for wl in ("rosenbrock", "chemistry"):
+            a2 = argparse.Namespace(**dict(vars(a), workload=wl))
+            p2, th2 = make_workload(a2, device=dev)
+            acq2 = product_acq(p2, dev)
+            pr2 = product_mc_pr(dict(p2, case=dict(p2["case"], grad_estimator="reinforce_ma")), dev, acq=acq2)
+            sp2, aq2 = pr2._space(), acq_desc_of(acq2)
+            th2d = th2.to(dev).reshape(a.restarts, -1).contiguous()
+            d2 = th2d.shape[-1]
+            st2 = acq2.state
+            ones2 = torch.ones(a.restarts, dtype=torch.float64, device=dev)
+            v2 = torch.empty(a.restarts, dtype=torch.float64, device=dev)
+            g2 = torch.empty(a.restarts, d2, dtype=torch.float64, device=dev)
+            ma2 = torch.zeros(2, dtype=torch.float64, device=dev)
+            ws2 = st2.workspace(a.restarts * mc, d2, a.restarts)
+
+            def step2():
+                capi.check(lib.prb_mc_value_grad(st2.handle, C.byref(sp2), C.byref(aq2), th2d.data_ptr(), a.restarts, mc,
+                                                 None, None, 0, 0, capi.PRB_EST_REINFORCE_MA, ma2.data_ptr(), 1,
+                                                 ones2.data_ptr(), v2.data_ptr(), g2.data_ptr(), None, ws2.data_ptr(),
+                                                 ws2.numel(), 0, stream.cuda_stream), "prb_mc_value_grad")
+            gms = cuda_time(step2, max(5, a.steps // 2), a.warmup, stream)
+            lib.prb_profile_enable(1)
+            step2()
+            torch.cuda.synchronize()
+            msk = (C.c_double * capi.PRB_PROFILE_SLOTS)()
+            cnt = (C.c_uint64 * capi.PRB_PROFILE_SLOTS)()
+            capi.check(lib.prb_profile_read(msk, cnt, capi.PRB_PROFILE_SLOTS), "prb_profile_read")
+            lib.prb_profile_enable(0)
+            generic[wl] = {"workload": WORKLOADS[wl], "value": a.restarts * mc / (gms * 1e-3), "unit": UNIT,
+                           "ms_per_step": gms,
+                           "whole_step_frac": a.restarts * mc * algorithmic_flops_per_eval(n) / (gms * 1e-3) / 1e12
+                           / (roofline["peak"] if roofline else FP64_PEAK_FALLBACK),
+                           "kernel_breakdown_ms": {nm: msk[i] for i, nm in enumerate(capi.PROFILE_SLOT_NAMES) if cnt[i]}}
+            del st2, ws2, acq2, pr2
 
     # ---- seconds per BO iteration, ackley13 pr__ei (rank 0, N = 1 only) ---------------------------------------------------
     bo = None
@@ -495,19 +688,21 @@ def run_ours(a):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value_evals, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": workload_name(a), "n_train": n, "restarts_per_gpu": b, "mc": mc,
-                       "evals_per_step": evals_per_step, "rng": "philox4x32-10 (seed 0, offset 0), drawn in the sampler",
-                       "l2": "the per-step v panel (8 x n x b x mc bytes = "
-                             f"{8 * n * b * mc / 1e9:.2f} GB written then read) exceeds the 126 MB L2; the 16 MB GP state "
-                             "is L2-resident by design; no explicit flush",
-                       "parallelism": f"restart-sharded x{world}, GP state replicated, no data-path collective"},
+            "config": config_of(a, world, {
+                "restarts_per_gpu": b, "rng": "philox4x32-10 (seed 0, offset 0), drawn in the sampler",
+                "l2": "the per-step v panel (8 x n x b x mc bytes = "
+                      f"{8 * n * b * mc / 1e9:.2f} GB per GPU, written then read) "
+                      + ("exceeds the 126 MB L2" if 8 * n * b * mc > 126e6 else "fits the 126 MB L2 (it is an intermediate "
+                         "the step itself produces, not an input: inputs are theta and the 16 MB GP state)")
+                      + "; no explicit flush",
+                "parallelism": f"{a.restarts} restarts in total sharded r mod {world}, GP state replicated, no data-path "
+                               "collective inside a step"}),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "kernel_breakdown": breakdown, "bo_iter": bo, "dedup": dedup, "value_only": value_only,
+            "kernel_breakdown": breakdown, "bo_iter": bo, "bo_iter_sharded": bo_sh, "weak": weak, "dedup": dedup,
+            "value_only": value_only, "generic_path": generic,
         }
-        if best is not None:
-            line["best_candidate"] = best
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -61,3 +61,53 @@ def sobol_base_samples(mc: int, n_cols: int = 10, seed: int = 1234):
     """[mc, 1, n_cols] scrambled Sobol, as the reference draws them (input.py:667-672)."""
     from torch.quasirandom import SobolEngine
     return SobolEngine(n_cols, scramble=True, seed=seed).draw(mc, dtype=torch.float64).view(mc, 1, n_cols)
+
+
+GENERIC_CASES = {
+    # rosenbrock10_scaled shape (SURVEY.md App. D): 4 continuous + 6 ordinals {0..3}, ALL inside one ARD Matern -> the
+    # kernel does not separate into (per-restart) x (per-sample) factors: generic path
+    "rosenbrock": dict(dim=10, integer_indices=list(range(4, 10)), integer_bounds=[[0.0] * 6, [3.0] * 6],
+                       categorical_features=None, kernel_type="mixed", binary_dims=[], acq="ucb",
+                       beta=0.2 * 10 * math.log(2 * 100), apply_numeric=False, grad_estimator="reinforce_ma"),
+    # chemistry shape, MC variant: 2 continuous + categoricals (4, 12, 4), kernel "mixed_categorical" (two additive terms,
+    # squared categorical factor), base AF sees the numeric layout (OneHotToNumeric)
+    "chemistry": dict(dim=22, integer_indices=[], integer_bounds=[[], []], categorical_features={2: 4, 3: 12, 4: 4},
+                      kernel_type="mixed_categorical", binary_dims=[], acq="ei", apply_numeric=True,
+                      grad_estimator="reinforce_ma"),
+}
+
+
+def make_generic_problem(kind: str, n: int, restarts: int, mc: int, seed: int = 0):
+    """(problem, theta [restarts, 1, dim]) for the kernel structures that do NOT separate, at any n_train.  X_train is laid
+    out as the model sees it (numeric layout when apply_numeric); y is a smooth seeded function of it, standardised (any
+    targets give a valid exact-GP state; the hot path only sees alpha and the Cholesky factor)."""
+    c = dict(GENERIC_CASES[kind], mc=mc, n_train=n, b=restarts, seed=seed)
+    g = torch.Generator().manual_seed(seed + 77)
+    cf = c["categorical_features"] or {}
+    ints = c["integer_indices"]
+    ib = torch.tensor(c["integer_bounds"], dtype=torch.float64).reshape(2, -1)
+    n_cont = min(cf.keys()) if cf else c["dim"] - len(ints)
+    if cf:
+        n_cont -= len(ints)
+    cols = [torch.rand(n, n_cont, generator=g, dtype=torch.float64)]
+    for k in range(len(ints)):
+        lo, hi = float(ib[0, k]), float(ib[1, k])
+        v = torch.randint(int(lo), int(hi) + 1, (n, 1), generator=g).to(torch.float64)
+        cols.append((v - lo) / (hi - lo))
+    for card in cf.values():  # numeric codes (apply_numeric) -- the only layout the categorical cases here use
+        cols.append(torch.randint(0, card, (n, 1), generator=g).to(torch.float64))
+    Xk = torch.cat(cols, dim=-1)
+    dk = Xk.shape[-1]
+    cat_dims = list(cf.keys()) if c["kernel_type"] == "mixed_categorical" else []
+    cont_dims = sorted(set(range(dk)) - set(c["binary_dims"]) - set(cat_dims))
+    hp = dict(cont_lengthscale=(0.4 + 0.8 * torch.rand(len(cont_dims), generator=g, dtype=torch.float64)).tolist(),
+              binary_lengthscale=[], categorical_lengthscale=(0.6 + 1.2 * torch.rand(len(cat_dims), generator=g,
+                                                                                      dtype=torch.float64)).tolist(),
+              outputscale=1.1, outputscale_sum=0.4)
+    w = torch.randn(dk, generator=g, dtype=torch.float64)
+    y = torch.sin(3.0 * (Xk / Xk.abs().max(dim=0).values.clamp_min(1.0)) @ w) + 0.1 * torch.randn(n, generator=g,
+                                                                                                    dtype=torch.float64)
+    y = (y - y.mean()) / y.std()
+    theta = torch.rand(restarts, 1, c["dim"], generator=g, dtype=torch.float64)
+    return dict(case=c, train_X_model=Xk, train_Y=y, hp=hp, noise=1e-4, mean_const=0.05, cont_dims=cont_dims,
+                cat_dims=cat_dims, base_samples=None, base_samples_categorical=None), theta

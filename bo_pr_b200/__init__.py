@@ -40,6 +40,7 @@ from .initializers import (  # noqa: F401
     initialize_q_batch_nonneg,
 )
 from .optimize import optimize_acqf, optimize_acqf_mixed  # noqa: F401
+from .finalize import finalize_candidates  # noqa: F401
 from .rffs import (  # noqa: F401
     RandomFourierFeatures,
     RFFSampleModel,

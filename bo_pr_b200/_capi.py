@@ -29,9 +29,10 @@ PROFILE_SLOT_NAMES = ["pr_sample", "kstar_panel", "trgemm_lower", "acq_epilogue"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", os.environ.get("PRB_LIB_NAME", "libprb200.so"))
 
 EXPORTS = [
-    "prb_version", "prb_abi_sizeof", "prb_debug_small_timestamps", "prb_launch_count", "prb_profile_enable", "prb_profile_read", "prb_status_string", "prb_last_cuda_error", "prb_model_create", "prb_rff_model_create", "prb_model_destroy", "prb_model_set_option",
+    "prb_version", "prb_abi_sizeof", "prb_debug_small_timestamps", "prb_debug_fp64_peak", "prb_launch_count", "prb_profile_enable", "prb_profile_read", "prb_status_string", "prb_last_cuda_error", "prb_model_create", "prb_rff_model_create", "prb_model_destroy", "prb_model_set_option",
     "prb_model_n", "prb_model_dk", "prb_workspace_bytes", "prb_philox_uniform", "prb_pr_sample",
-    "prb_analytic_enumerate", "prb_kernel_matrix", "prb_acq_points",
+    "prb_analytic_enumerate", "prb_kernel_matrix", "prb_acq_points", "prb_sample_candidates", "prb_finalize_candidates",
+    "prb_trust_region_bounds",
     "prb_mc_value_grad", "prb_mc_screen", "prb_analytic_value_grad", "prb_mc_adam", "prb_analytic_adam",
 ]
 
@@ -88,6 +89,7 @@ def load_library() -> C.CDLL:
     lib.prb_launch_count.argtypes = []
     lib.prb_abi_sizeof.argtypes = [C.c_int]
     lib.prb_debug_small_timestamps.argtypes = [vp]
+    lib.prb_debug_fp64_peak.argtypes = [C.c_int, vp, vp]
     lib.prb_profile_enable.argtypes = [C.c_int]
     lib.prb_profile_read.argtypes = [vp, vp, i32]
     lib.prb_status_string.restype = C.c_char_p
@@ -103,6 +105,10 @@ def load_library() -> C.CDLL:
     lib.prb_workspace_bytes.argtypes = [vp, i64, i32, i32, i32]
     lib.prb_philox_uniform.argtypes = [u64, u64, i32, i32, vp, vp]
     lib.prb_pr_sample.argtypes = [C.POINTER(PrbSpaceDesc), vp, i32, i32, vp, vp, u64, u64, vp, vp, vp, vp]
+    lib.prb_sample_candidates.argtypes = [C.POINTER(PrbSpaceDesc), vp, i32, vp, u64, u64, vp, vp, vp]
+    lib.prb_finalize_candidates.argtypes = [vp, C.POINTER(PrbSpaceDesc), C.POINTER(PrbAcqDesc), vp, i32, vp, u64, u64, vp,
+                                            vp, vp, vp, vp, sz, vp]
+    lib.prb_trust_region_bounds.argtypes = [vp, vp, i32, i32, i32, dbl, vp, vp, vp, vp, vp, vp]
     lib.prb_analytic_enumerate.argtypes = [C.POINTER(PrbSpaceDesc), vp, i32, vp, i32, vp, vp, vp]
     lib.prb_kernel_matrix.argtypes = [C.POINTER(PrbModelDesc), vp, i64, vp, vp]
     lib.prb_acq_points.argtypes = [vp, C.POINTER(PrbAcqDesc), vp, i64, vp, vp, vp, vp, vp, sz, i32, vp]

@@ -710,6 +710,20 @@ int prb_debug_small_timestamps(long long* out16) {
   return PRB_OK;
 }
 
+int prb_debug_fp64_peak(int mode, double* out_tflops, void* stream) {
+  if (!out_tflops || mode < 0 || mode > 2) return PRB_ERR_INVALID;
+  int dev = -1, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return PRB_ERR_NO_DEVICE;
+  if (int rc_dev = check_device(dev)) return rc_dev;
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  double* scratch = nullptr;
+  CUDA_TRY(cudaMalloc(&scratch, size_t(2) * sms * 256 * sizeof(double)));
+  cudaError_t e = run_fp64_peak(mode, 1 << 15, scratch, sms, out_tflops, static_cast<cudaStream_t>(stream));
+  cudaFree(scratch);
+  if (e != cudaSuccess) return cuda_fail(e, "prb_debug_fp64_peak");
+  return PRB_OK;
+}
+
 int prb_profile_enable(int on) {
   g_prof_on = on != 0;
   return PRB_OK;
@@ -944,6 +958,51 @@ int prb_pr_sample(const prb_space_desc* space, const double* theta, int32_t b, i
   if (!theta || b < 0 || mc < 0) return PRB_ERR_INVALID;
   CUDA_TRY(launch_pr_sample(sp, theta, b, mc, u_int, u_cat, seed, offset, nullptr, out_tilde_x, out_z, out_prob,
                             nullptr, nullptr, static_cast<cudaStream_t>(stream)));
+  return PRB_OK;
+}
+
+int prb_sample_candidates(const prb_space_desc* space, const double* theta, int32_t b, const double* u, uint64_t seed,
+                          uint64_t offset, double* out_x, double* out_xk, void* stream) {
+  DevSpace sp;
+  int rc = make_space(space, &sp);
+  if (rc != PRB_OK) return rc;
+  if (!theta || b < 0 || (!out_x && !out_xk)) return PRB_ERR_INVALID;
+  CUDA_TRY(launch_sample_candidates(sp, theta, b, u, seed, offset, out_x, out_xk, static_cast<cudaStream_t>(stream)));
+  return PRB_OK;
+}
+
+int prb_finalize_candidates(prb_model* model, const prb_space_desc* space, const prb_acq_desc* acq, const double* theta,
+                            int32_t b, const double* u, uint64_t seed, uint64_t offset, double* out_x, double* out_acq,
+                            double* out_best, int32_t* out_best_index, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  if (!model || !theta || !out_x || b < 1 || !workspace) return PRB_ERR_INVALID;
+  const Model& m = *reinterpret_cast<Model*>(model);
+  DevSpace sp;
+  DevAcq aq;
+  int rc = make_space(space, &sp);
+  if (rc != PRB_OK) return rc;
+  if ((rc = make_acq(acq, &aq)) != PRB_OK) return rc;
+  if (sp.d_k != m.d_k) return PRB_ERR_INVALID;
+  const Plan pl = make_plan(m, b, 0, m.d_k, 0);
+  if (workspace_bytes < pl.total) return PRB_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* xk = at<double>(workspace, pl.off_xk);
+  double* a = out_acq ? out_acq : at<double>(workspace, pl.off_a);
+  CUDA_TRY(launch_sample_candidates(sp, theta, b, u, seed, offset, out_x, xk, st));
+  rc = run_engine(m, aq, pl, workspace, xk, b, false, 0u, a, at<double>(workspace, pl.off_dmu),
+                  at<double>(workspace, pl.off_dvar), nullptr, nullptr, nullptr, st);
+  if (rc != PRB_OK) return rc;
+  if (out_best || out_best_index) CUDA_TRY(launch_best_row(a, out_x, b, sp.d, out_best, out_best_index, st));
+  return PRB_OK;
+}
+
+int prb_trust_region_bounds(const double* X, const double* Y, int32_t n, int32_t d, int32_t n_constraints, double length,
+                            const double* lower, const double* upper, const uint8_t* reset01, double* out_bounds,
+                            int32_t* out_center_index, void* stream) {
+  if (!X || !Y || n < 1 || d < 1 || n_constraints < 0 || !lower || !upper || !out_bounds || !(length > 0.0))
+    return PRB_ERR_INVALID;
+  CUDA_TRY(launch_tr_bounds(X, Y, n, d, n_constraints, length, lower, upper, reset01, out_bounds, out_center_index,
+                            static_cast<cudaStream_t>(stream)));
   return PRB_OK;
 }
 

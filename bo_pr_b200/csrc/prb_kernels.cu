@@ -2,6 +2,7 @@
 // pathwise-gradient contraction, MC / analytic reductions, EMA-baseline update, Adam step.
 #include "prb_device.cuh"
 #include "prb_kernels.cuh"
+#include "prb_ptx.cuh"
 
 namespace prb {
 
@@ -1369,6 +1370,80 @@ cudaError_t launch_fill(double* p, double v, int n, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   fill_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, v, n);
   count_launch();
+  return cudaGetLastError();
+}
+
+// =====================================================================================================================
+// FP64 pipe microbenchmark (diagnostic; bench.py runs it OUTSIDE its timed region to put the roofline denominator of the
+// triangular products into the same record as the measurement).  Register-resident operands, 8 independent accumulator
+// chains per warp, every SM busy with 2 CTAs of 8 warps.
+//   mode 0: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4, the instruction the products use)      512 flop per warp instruction
+//   mode 1: scalar DFMA                                                                   64 flop per warp instruction
+//   mode 2: even warps DMMA, odd warps DFMA (do the two share one FP64 datapath?)          flops of both counted
+// =====================================================================================================================
+template <int MODE>
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* __restrict__ out, int iters, double a0) {
+  const bool use_mma = MODE == 0 || (MODE == 2 && ((threadIdx.x >> 5) & 1) == 0);
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    c[i][0] = double(threadIdx.x);
+    c[i][1] = double(i);
+  }
+  const double a = a0, b = 1.0 - a0;
+  if (use_mma) {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dmma884(c[i][0], c[i][1], a, b);
+    }
+  } else {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        c[i][0] = fma(c[i][0], a, b);
+        c[i][1] = fma(c[i][1], a, b);
+      }
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  out[size_t(blockIdx.x) * blockDim.x + threadIdx.x] = s;
+}
+
+cudaError_t run_fp64_peak(int mode, int iters, double* scratch /* [>= 2 * sms * 256] */, int sms, double* tflops,
+                          cudaStream_t st) {
+  cudaEvent_t e0, e1;
+  cudaError_t e = cudaEventCreate(&e0);
+  if (e != cudaSuccess) return e;
+  if ((e = cudaEventCreate(&e1)) != cudaSuccess) {
+    cudaEventDestroy(e0);
+    return e;
+  }
+  const int blocks = 2 * sms, threads = 256;
+  float best = 1e30f;
+  for (int rep = 0; rep < 4 && e == cudaSuccess; ++rep) {  // rep 0 warms up
+    cudaEventRecord(e0, st);
+    if (mode == 0) fp64_peak_kernel<0><<<blocks, threads, 0, st>>>(scratch, iters, 0.5);
+    else if (mode == 1) fp64_peak_kernel<1><<<blocks, threads, 0, st>>>(scratch, iters, 0.5);
+    else fp64_peak_kernel<2><<<blocks, threads, 0, st>>>(scratch, iters, 0.5);
+    count_launch();
+    cudaEventRecord(e1, st);
+    e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    if (e == cudaSuccess && rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (e != cudaSuccess) return e;
+  const double warps = double(blocks) * threads / 32.0;
+  const double per_warp_iter_mma = 8.0 * 512.0, per_warp_iter_fma = 16.0 * 64.0;
+  double flop;
+  if (mode == 0) flop = warps * iters * per_warp_iter_mma;
+  else if (mode == 1) flop = warps * iters * per_warp_iter_fma;
+  else flop = 0.5 * warps * iters * (per_warp_iter_mma + per_warp_iter_fma);
+  *tflops = flop / (double(best) * 1e-3) * 1e-12;
   return cudaGetLastError();
 }
 

@@ -66,5 +66,14 @@ cudaError_t launch_clamp(const double* theta, const double* lower, const double*
 cudaError_t launch_adam_step(double* theta, const double* acq_grad, double* m, double* v, int total, double lr,
                              int* step_ptr, cudaStream_t st);
 cudaError_t launch_fill(double* p, double v, int n, cudaStream_t st);
+// prb_finalize.cu
+cudaError_t launch_sample_candidates(const DevSpace& sp, const double* theta, int b, const double* u, uint64_t seed,
+                                     uint64_t offset, double* out_x, double* out_xk, cudaStream_t st);
+cudaError_t launch_best_row(const double* vals, const double* rows, int b, int d, double* out_best, int32_t* out_index,
+                            cudaStream_t st);
+cudaError_t launch_tr_bounds(const double* X, const double* Y, int n, int d, int n_con, double length, const double* lower,
+                             const double* upper, const uint8_t* reset01, double* out_bounds, int32_t* out_center,
+                             cudaStream_t st);
+cudaError_t run_fp64_peak(int mode, int iters, double* scratch, int sms, double* tflops, cudaStream_t st);
 
 }  // namespace prb

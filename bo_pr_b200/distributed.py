@@ -71,3 +71,78 @@ def broadcast_gp_data(train_X: Tensor, train_Y: Tensor, src: int = 0) -> Tuple[T
         dist.broadcast(train_X, src)
         dist.broadcast(train_Y, src)
     return train_X, train_Y
+
+
+def broadcast_tensor(t: Tensor, src: int = 0) -> Tensor:
+    """In-place broadcast of ``t`` from ``src`` (no-op in a single process)."""
+    _, world = _world()
+    if world > 1:
+        dist.broadcast(t, src)
+    return t
+
+
+def broadcast_int(value: Optional[int], src: int = 0, device=None) -> Optional[int]:
+    """Rank ``src``'s integer on every rank (e.g. the Sobol seed the reference takes from torch's global generator)."""
+    rank, world = _world()
+    if world == 1:
+        return value
+    buf = torch.tensor([-1 if value is None else int(value)], dtype=torch.int64, device=device)
+    dist.broadcast(buf, src)
+    v = int(buf.item())
+    return None if v < 0 else v
+
+
+def sync_pr_base_samples(acq_function, device) -> None:
+    """Every rank must draw the SAME base uniforms (the reference caches one scrambled-Sobol draw per acquisition-function
+    object, ``input.py:655-673``; the seed comes from torch's global generator, which differs between ranks): rank 0's
+    buffers are broadcast.  No-op for acquisition functions without an MC PR transform and for the Philox stream."""
+    _, world = _world()
+    tf = getattr(acq_function, "input_transform", None)
+    if world == 1 or tf is None or "round" not in tf:
+        return
+    rnd = tf["round"]
+    if not hasattr(rnd, "ensure_base_samples"):
+        return
+    rnd.ensure_base_samples(1, device)
+    for name in ("base_samples", "base_samples_categorical"):
+        if hasattr(rnd, name):
+            dist.broadcast(getattr(rnd, name), 0)
+
+
+def allreduce_mean_(t: Tensor) -> Tensor:
+    """Mean over ranks, in place (sum then divide: every rank holds an equal share of the MC samples)."""
+    _, world = _world()
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t.div_(world)
+    return t
+
+
+def mc_sharded_adam(local_value_and_grad, local_value, sync_state, ics: Tensor, lower, upper, lr: float = 0.025,
+                    maxiter: int = 200) -> Tuple[Tensor, Tensor]:
+    """Multi-start Adam with the MC samples -- not the restarts -- split over the ranks (fewer
+    restarts than GPUs).  Every rank holds all restarts and an equal slice of the base samples; per step the local MC means
+    of the value and the gradient ``[b, 1 + d]`` meet in ONE all-reduce, then every rank applies the identical Adam update
+    (``gen.py:304-343`` arithmetic: clamp -> value + gradient -> Adam -> ... -> final clamp + value).
+
+    ``local_value_and_grad(X[b, 1, d]) -> (value [b], d value.sum() / dX [b, 1, d])`` and ``local_value(X) -> [b]`` evaluate
+    this rank's slice; ``sync_state()`` averages whatever estimator state depends on the MC mean (the EMA baseline is linear
+    in it, so the mean of the per-rank states IS the state of the unsharded call)."""
+    clamp = lambda t: torch.max(torch.min(t, upper), lower)  # noqa: E731
+    theta = clamp(ics.detach().clone()).requires_grad_(True)
+    opt = torch.optim.Adam([theta], lr=lr)
+    b, q, d = theta.shape
+    for _ in range(maxiter):
+        with torch.no_grad():
+            X = clamp(theta)
+        v, g = local_value_and_grad(X)
+        packed = torch.cat([v.reshape(b, 1), g.reshape(b, q * d)], dim=1).contiguous()
+        allreduce_mean_(packed)
+        sync_state()
+        opt.zero_grad()
+        theta.grad = -packed[:, 1:].reshape(b, q, d)
+        opt.step()
+    out = clamp(theta.detach())
+    vals = allreduce_mean_(local_value(out).clone())
+    sync_state()
+    return out, vals

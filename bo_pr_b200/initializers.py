@@ -113,8 +113,16 @@ def gen_batch_initial_conditions(
     options: Optional[Dict[str, Union[bool, float, int]]] = None,
     inequality_constraints: Optional[List[Tuple[Tensor, Tensor, float]]] = None,
     equality_constraints: Optional[List[Tuple[Tensor, Tensor, float]]] = None,
+    shard: bool = False,
 ) -> Tensor:
-    """``initializers.py:53-206``.  Returns ``num_restarts x q x d`` initial conditions on ``bounds.device``."""
+    """``initializers.py:53-206``.  Returns ``num_restarts x q x d`` initial conditions on ``bounds.device``.
+
+    ``shard=True`` (inside an initialised ``torch.distributed`` group): the raw samples are drawn from ONE seed (rank 0's,
+    broadcast), every rank screens the rows ``rank::world`` (``initializers.py:179-191`` is the loop being split), the
+    values are all-gathered back into raw-sample order, rank 0 runs the Boltzmann selection with its generator and the
+    chosen initial conditions are broadcast -- every rank returns the same tensor.  With ``init_batch_limit`` each rank
+    makes ``1/world`` of the screening calls, so the EMA baseline of a ``reinforce_ma`` PR function has seen fewer updates
+    when the optimisation starts than in the single-process run (that state is per-call by design)."""
     if inequality_constraints is not None or equality_constraints is not None:
         raise NotImplementedError("parameter constraints are outside the PR hot path")
     options = options or {}
@@ -136,6 +144,15 @@ def gen_batch_initial_conditions(
     bounds_cpu = bounds.cpu()
     factor, max_factor = 1, 5
     batch_initial_conditions = None
+    rank, world = (0, 1)
+    if shard:
+        from . import distributed as D
+        rank, world = D._world()
+        if world > 1:
+            if seed is None:  # the reference lets SobolEngine seed itself; ranks must agree, so rank 0 picks
+                seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+            seed = D.broadcast_int(seed, 0, device=device)
+            D.sync_pr_base_samples(acq_function, device)
     while factor < max_factor:
         with warnings.catch_warnings(record=True) as ws:
             warnings.simplefilter("always")
@@ -147,14 +164,26 @@ def gen_batch_initial_conditions(
                 # one host->device copy and one device->host read for the whole screening pass (the reference moves every
                 # chunk separately, initializers.py:184-190; the chunked CALLS are kept, they advance the EMA state)
                 X_dev = X_rnd.to(device=device)
+                X_loc = X_dev[rank::world] if world > 1 else X_dev
                 if hasattr(acq_function, "screen") and q == 1:
                     # MC-PR acquisition functions run the chunk loop inside the library (prb_mc_screen)
-                    Y_rnd = acq_function.screen(X_dev, limit).cpu()
+                    Y_loc = acq_function.screen(X_loc, limit)
                 else:
-                    Y_rnd = torch.cat([acq_function(X_dev[s:s + limit])
-                                       for s in range(0, X_dev.shape[0], limit)]).cpu()
-            batch_initial_conditions = init_func(X=X_rnd, Y=Y_rnd, n=num_restarts, **init_kwargs).to(device=device)
-            if not any(issubclass(w.category, BadInitialCandidatesWarning) for w in ws):
+                    Y_loc = torch.cat([acq_function(X_loc[s:s + limit]) for s in range(0, X_loc.shape[0], limit)])
+                if world > 1:
+                    Y_loc = D.gather_restarts(Y_loc.contiguous(), X_dev.shape[0])
+                Y_rnd = Y_loc.cpu()
+            bad = False
+            if rank == 0:
+                batch_initial_conditions = init_func(X=X_rnd, Y=Y_rnd, n=num_restarts, **init_kwargs).to(device=device)
+                bad = any(issubclass(w.category, BadInitialCandidatesWarning) for w in ws)
+            if world > 1:
+                if rank != 0:
+                    batch_initial_conditions = torch.empty(num_restarts, q, bounds.shape[-1], dtype=X_rnd.dtype,
+                                                           device=device)
+                D.broadcast_tensor(batch_initial_conditions, 0)
+                bad = bool(D.broadcast_int(int(bad), 0, device=device))
+            if not bad:
                 return batch_initial_conditions
             factor += 1
             if seed is not None:

@@ -18,7 +18,8 @@ from typing import Any, Callable, Dict, List, Optional, Tuple, Union
 import torch
 from torch import Tensor
 
-from .distributed import gather_restarts, shard_restarts
+from .distributed import (_world, gather_restarts, mc_sharded_adam, allreduce_mean_, shard_restarts,
+                          sync_pr_base_samples)
 from .gen import FixedFeatureAcquisitionFunction, gen_candidates_scipy, gen_candidates_torch
 from .initializers import gen_batch_initial_conditions
 
@@ -26,6 +27,53 @@ INIT_OPTION_KEYS = {  # keys consumed by the initialisation, not forwarded to th
     "alpha", "batch_limit", "eta", "init_batch_limit", "nonnegative", "n_burnin", "sample_around_best",
     "sample_around_best_sigma", "sample_around_best_prob_perturb", "sample_around_best_subset_sigma", "seed", "thinning",
 }
+
+
+def world_size() -> int:
+    return _world()[1]
+
+
+def _mc_shardable(acq_function, options, fixed_features) -> bool:
+    from .probabilistic_reparameterization import MCProbabilisticReparameterization
+    if not isinstance(acq_function, MCProbabilisticReparameterization) or fixed_features:
+        return False
+    rnd = acq_function.input_transform["round"]
+    return rnd.rng == "sobol" and rnd.mc_samples % world_size() == 0 and not options.get("decay", False)
+
+
+def _optimize_mc_sharded(pr, ics: Tensor, bounds: Tensor, options) -> Tuple[Tensor, Tensor]:
+    """MC-sharded multi-start Adam on an ``MCProbabilisticReparameterization``: this rank keeps rows ``rank::world`` of the
+    (already synchronised) base samples, so its forward is the MC mean over its slice; ``mc_sharded_adam`` all-reduces the
+    means.  The EMA-baseline buffers are averaged after every call (the update is linear in the call's mean value)."""
+    rank, world = _world()
+    rnd = pr.input_transform["round"]
+    full = {}
+    for name in ("base_samples", "base_samples_categorical"):
+        if hasattr(rnd, name):
+            full[name] = getattr(rnd, name)
+            rnd.register_buffer(name, full[name][rank::world].contiguous())
+    mc_full = rnd.mc_samples
+    rnd.mc_samples = mc_full // world
+    try:
+        def vg(X):
+            Xg = X.detach().requires_grad_(True)
+            v = pr(Xg)
+            g = torch.autograd.grad(v.sum(), Xg)[0]
+            return v.detach(), g
+
+        def v_only(X):
+            with torch.no_grad():
+                return pr(X)
+
+        def sync_state():
+            allreduce_mean_(pr._ma_state[1:2])
+
+        return mc_sharded_adam(vg, v_only, sync_state, ics, bounds[0], bounds[1], lr=options.get("lr", 0.025),
+                               maxiter=int(options.get("maxiter", 10000)))
+    finally:
+        rnd.mc_samples = mc_full
+        for name, t in full.items():
+            rnd.register_buffer(name, t)
 
 
 def optimize_acqf(
@@ -84,9 +132,20 @@ def optimize_acqf(
             raise ValueError("Must specify `raw_samples` when `batch_initial_conditions` is `None`.")
         batch_initial_conditions = gen_batch_initial_conditions(
             acq_function=acq_function, bounds=bounds, q=q, num_restarts=num_restarts, raw_samples=raw_samples,
-            fixed_features=fixed_features, options=options)
+            fixed_features=fixed_features, options=options, shard=shard)
+    elif shard:
+        sync_pr_base_samples(acq_function, bounds.device)
 
     n_total = batch_initial_conditions.shape[0]
+    if shard and stochastic and n_total < world_size() and _mc_shardable(acq_function, options, fixed_features):
+        # fewer restarts than GPUs: split the MC samples instead, one [b, 1 + d] all-reduce per Adam step
+        cand, vals = _optimize_mc_sharded(acq_function, batch_initial_conditions, bounds, options)
+        if post_processing_func is not None:
+            cand = post_processing_func(cand)
+        if return_best_only:
+            best = torch.argmax(vals.view(-1), dim=0)
+            cand, vals = cand[best], vals[best]
+        return cand, vals
     local_ics = shard_restarts(batch_initial_conditions) if shard else batch_initial_conditions
     batch_limit: int = options.get("batch_limit", max(local_ics.shape[0], 1))
     gen_candidates = gen_candidates_torch if stochastic else gen_candidates_scipy

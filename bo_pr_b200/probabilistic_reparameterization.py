@@ -143,35 +143,64 @@ class AbstractProbabilisticReparameterization(AcquisitionFunctionWrapper, ABC):
             cached = self.__dict__["_space_cached"] = (tau, sp)
         return cached[1]
 
-    def sample_candidates(self, X: Tensor) -> Tensor:
-        """``:198-233``: one discrete draw per restart from p(theta*), torch's global generator (once per BO iteration)."""
-        if "unnormalize" in self.input_transform:
-            unnormalized_X = self.input_transform["unnormalize"](X)
-        else:
-            unnormalized_X = X.clone()
-        prob = self.input_transform["round"].get_rounding_prob(X=unnormalized_X)
-        n_int = int(self.integer_indices.numel())
-        if n_int > 0:
-            # all integer parameters in one draw (the reference loops over them, :204-215; the per-parameter Bernoulli
-            # draws are independent, so only the consumption order of torch's generator differs)
-            idx = self.integer_indices
-            rounding_component = torch.bernoulli(prob[..., :n_int])
-            vals = unnormalized_X[..., idx].floor() + rounding_component
-            unnormalized_X[..., idx] = torch.minimum(torch.maximum(vals, self.integer_bounds[0]), self.integer_bounds[1])
-        discrete_idx = n_int
-        raw_idx = self.cont_indices.shape[0] + discrete_idx
+    def sample_candidates(self, X: Tensor, rng: str = "torch", seed: Optional[int] = None, offset: int = 1 << 32,
+                          draw_device=None, u: Optional[Tensor] = None) -> Tensor:
+        """``:198-233``: one discrete draw per restart from p(theta*).  ``X [b, 1, d]`` -> ``[b, 1, d]``.
+
+        ``rng="torch"`` (default, the reference's behaviour): the rounding probabilities come from the device
+        (``prb_pr_sample``), the draws from torch's global generator in the reference's own order -- one
+        ``Bernoulli(probs=p).sample()`` per integer parameter (:204-209), then one ``Categorical(probs=p).sample()`` per
+        one-hot block (:219-229) -- on ``draw_device`` (default: ``X.device``, i.e. the CUDA generator, as the reference
+        running on the same GPU; ``"cpu"`` reproduces a CPU run of the reference bit for bit, which is what the golden
+        fixtures record).  ``rng="philox"``: the whole draw is ONE kernel (``prb_sample_candidates``) on the counter-based
+        stream ``(seed, offset)``, or on explicit uniforms ``u [b, n_int + n_cat]``; no host round trip."""
+        _check_X(X, self.dim)
+        if rng == "philox" or u is not None:
+            return self._sample_candidates_device(X, 0 if seed is None else int(seed), int(offset), u)[0]
+        if rng != "torch":
+            raise ValueError("rng must be 'torch' or 'philox'")
+        tf = self.input_transform
+        x_un = tf["unnormalize"](X) if "unnormalize" in tf else X.clone()
+        prob = tf["round"].get_rounding_prob(X=x_un)
+        dev = X.device if draw_device is None else torch.device(draw_device)
+        x_un, prob = x_un.to(dev), prob.to(dev)
+        ints = self.integer_indices.to(dev)
+        col = 0
+        for i in ints.tolist():  # one Bernoulli call per integer parameter: the generator is consumed in this order
+            z = torch.distributions.Bernoulli(probs=prob[..., col]).sample()
+            x_un[..., i] = x_un[..., i].floor() + z
+            col += 1
+        if ints.numel() > 0:
+            ib = self.integer_bounds.to(dev)
+            x_un[..., ints] = torch.minimum(torch.maximum(x_un[..., ints], ib[0]), ib[1])
+        start = self.cont_indices.shape[0] + col  # first one-hot column
         if self.categorical_indices.shape[0] > 0:
-            for i, cardinality in self.categorical_features.items():
-                discrete_end = discrete_idx + cardinality
-                p = prob[..., discrete_idx:discrete_end]
-                z = one_hot(torch.distributions.Categorical(probs=p).sample(), num_classes=cardinality)
-                raw_end = raw_idx + cardinality
-                unnormalized_X[..., raw_idx:raw_end] = z.to(unnormalized_X)
-                discrete_idx = discrete_end
-                raw_idx = raw_end
-        if "normalize" in self.input_transform:
-            return self.input_transform["normalize"](unnormalized_X)
-        return unnormalized_X
+            for cardinality in self.categorical_features.values():
+                cat = torch.distributions.Categorical(probs=prob[..., col:col + cardinality]).sample()
+                x_un[..., start:start + cardinality] = one_hot(cat, num_classes=cardinality).to(x_un)
+                col += cardinality
+                start += cardinality
+        x_un = x_un.to(X.device)
+        return tf["normalize"](x_un) if "normalize" in tf else x_un
+
+    def _sample_candidates_device(self, X: Tensor, seed: int, offset: int, u: Optional[Tensor] = None,
+                                  want_xk: bool = False):
+        b, d = X.shape[0], X.shape[-1]
+        theta = X.detach().to(torch.float64).reshape(b, d).contiguous()
+        out = torch.empty(b, d, dtype=torch.float64, device=X.device)
+        sp = self._space()
+        xk = torch.empty(b, sp_dk(sp), dtype=torch.float64, device=X.device) if want_xk else None
+        if u is not None:
+            capi.require_cuda(u, "u")
+            u = u.detach().to(torch.float64).reshape(b, -1).contiguous()
+            if u.shape[1] != sp.n_int + sp.n_cat:
+                raise ValueError(f"u must have {sp.n_int + sp.n_cat} columns (one per integer / categorical parameter)")
+        lib = capi.load_library()
+        with torch.cuda.device(X.device):
+            st = torch.cuda.current_stream().cuda_stream
+            capi.check(lib.prb_sample_candidates(C.byref(sp), theta.data_ptr(), b, capi.ptr(u), seed, offset,
+                                                 out.data_ptr(), capi.ptr(xk), st), "prb_sample_candidates")
+        return out.reshape(b, 1, d).to(X.dtype), xk
 
     @abstractmethod
     def forward(self, X: Tensor) -> Tensor:
@@ -179,6 +208,11 @@ class AbstractProbabilisticReparameterization(AcquisitionFunctionWrapper, ABC):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+def sp_dk(sp: capi.PrbSpaceDesc) -> int:
+    """Kernel-input width of a PR space: numeric layout when the base AF sees OneHotToNumeric inputs."""
+    return (sp.cat_start[0] + sp.n_cat) if (sp.apply_numeric and sp.n_cat > 0) else sp.d
+
+
 def _check_X(X: Tensor, dim: int):
     capi.require_cuda(X, "X")
     if X.ndim != 3 or X.shape[-2] != 1:

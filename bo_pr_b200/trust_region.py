@@ -115,6 +115,8 @@ def trust_region_bounds(
     Binary columns and every one-hot column from ``categorical_start`` on are reset to ``[0, 1]``: the region only
     restricts continuous and wide-integer parameters.
     """
+    if X.is_cuda:
+        return _trust_region_bounds_device(state, X, Y, standard_bounds, binary_dims, categorical_start)
     span = state.length * (standard_bounds[1] - standard_bounds[0])
     center = trust_region_center(X, Y, state.is_constrained).to(standard_bounds)
     bounds = torch.stack((torch.maximum(center - span, standard_bounds[0]), torch.minimum(center + span, standard_bounds[1])))
@@ -126,3 +128,35 @@ def trust_region_bounds(
         bounds[0, categorical_start:] = 0
         bounds[1, categorical_start:] = 1
     return bounds
+
+
+def _trust_region_bounds_device(state: TurboState, X: Tensor, Y: Tensor, standard_bounds: Tensor, binary_dims,
+                                categorical_start) -> Tensor:
+    """The same box from ``prb_trust_region_bounds``: centre selection (argmax / best feasible / least violating), span,
+    clipping and the [0, 1] reset of binary and one-hot columns in one kernel on the current stream -- no host read of
+    ``Y.argmax()`` in the middle of a BO iteration."""
+    import ctypes as C
+
+    from . import _capi as capi
+
+    lib = capi.load_library()
+    n, d = X.shape[0], X.shape[-1]
+    Xd = X.detach().to(torch.float64).reshape(n, d).contiguous()
+    Yd = Y.detach().to(device=X.device, dtype=torch.float64).reshape(n, -1).contiguous()
+    n_con = Yd.shape[1] - 1 if state.is_constrained else 0
+    if not state.is_constrained and Yd.shape[1] != 1:
+        Yd = Yd[:, :1].contiguous()
+    sb = standard_bounds.detach().to(device=X.device, dtype=torch.float64).contiguous()
+    reset = torch.zeros(d, dtype=torch.uint8)
+    if binary_dims is not None and len(binary_dims) > 0:
+        reset[torch.as_tensor(list(binary_dims), dtype=torch.long)] = 1
+    if categorical_start is not None:
+        reset[categorical_start:] = 1
+    reset = reset.to(X.device)
+    out = torch.empty(2, d, dtype=torch.float64, device=X.device)
+    with torch.cuda.device(X.device):
+        st = torch.cuda.current_stream().cuda_stream
+        capi.check(lib.prb_trust_region_bounds(Xd.data_ptr(), Yd.data_ptr(), n, d, n_con, float(state.length),
+                                               sb[0].data_ptr(), sb[1].data_ptr(), reset.data_ptr(), out.data_ptr(), None,
+                                               st), "prb_trust_region_bounds")
+    return out.to(standard_bounds.dtype)

@@ -131,6 +131,10 @@ uint64_t prb_launch_count(void);
  * (prb_small.cu): 0 start, 1 TMA issued, 2 prep done, 3 operand generated, 4 A1 landed, 5 lower product, 6 acquisition
  * epilogue, 7 upper product, 8 gradient contraction, 9 partial sums, 10 completion counter.  out16: host long long[16]. */
 int prb_debug_small_timestamps(long long* out16);
+/* Diagnostic: FP64 pipe microbenchmark on the current device (allocates, synchronises; never on a hot path).  mode 0:
+ * mma.sync.m8n8k4.f64 from registers (the roofline denominator of the triangular products), 1: scalar DFMA, 2: both
+ * interleaved warp by warp.  bench.py calls it outside its timed region and prints the result in `roofline.peak_live`.  */
+int prb_debug_fp64_peak(int mode, double* out_tflops, void* stream);
 #define PRB_PROFILE_SLOTS 12
 int prb_profile_enable(int on);
 int prb_profile_read(double* ms_by_kernel, uint64_t* launches_by_kernel, int32_t n_slots);
@@ -183,6 +187,35 @@ int prb_philox_uniform(uint64_t seed, uint64_t offset, int32_t mc, int32_t n_col
 int prb_pr_sample(const prb_space_desc* space, const double* theta, int32_t b, int32_t mc, const double* u_int,
                   const double* u_cat, uint64_t seed, uint64_t offset, double* out_tilde_x, uint8_t* out_z,
                   double* out_prob, void* stream);
+
+/* Final discrete draw per restart from p(theta*), on the device.
+ * Replaces: AbstractProbabilisticReparameterization.sample_candidates (probabilistic_reparameterization.py:198-233).
+ * theta [b, d] normalised.  u [b, n_int + n_cat] uniforms in [0, 1) (integer parameters first, then one per categorical),
+ * or NULL => Philox(seed, offset) with counter (restart, parameter).  Integer k: z = [u < p_k] (torch.bernoulli's rule),
+ * value = clamp(floor(x_un) + z) -- floor of the SIGNED un-normalised value, as :207-208 --, re-normalised; categorical:
+ * inverse CDF of softmax((x - 0.5)/tau) (first index with cumsum > u; the last one if rounding leaves none), one-hot.
+ * out_x [b, d] one-hot layout; out_xk [b, d_k] the rows as the base AF sees them (numeric layout if apply_numeric);
+ * either may be NULL.                                                                                                 */
+int prb_sample_candidates(const prb_space_desc* space, const double* theta, int32_t b, const double* u, uint64_t seed,
+                          uint64_t offset, double* out_x, double* out_xk, void* stream);
+
+/* sample_candidates + base-AF re-scoring of the sampled rows + argmax over the restarts, one enqueue, no host round trip.
+ * Replaces: run_one_replication.py:500-528 (sample_candidates, one_hot_to_numeric, true_acq_func(...).max(dim=0),
+ * candidates[best_idx]).  out_x [b, d]; out_acq [b] or NULL; out_best [1 + d] = (best value, best row) or NULL;
+ * out_best_index device int32 or NULL (lowest index wins ties).  Workspace: prb_workspace_bytes(model, b, 0, d_k, 0).     */
+int prb_finalize_candidates(prb_model* model, const prb_space_desc* space, const prb_acq_desc* acq, const double* theta,
+                            int32_t b, const double* u, uint64_t seed, uint64_t offset, double* out_x, double* out_acq,
+                            double* out_best, int32_t* out_best_index, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
+/* Trust-region box around the incumbent, on the device.
+ * Replaces: run_one_replication.py:410-440.  X [n, d], Y [n, 1 + n_constraints] (column 0 the objective, maximised; the
+ * rest constraint slacks, >= 0 feasible).  Centre: best feasible row, else the least-violating one (:413-423).
+ * out_bounds [2, d] = clamp(centre -/+ length * (upper - lower), lower, upper), columns with reset01[c] != 0 (binary dims,
+ * one-hot blocks) reset to [0, 1]; out_center_index device int32 or NULL.                                              */
+int prb_trust_region_bounds(const double* X, const double* Y, int32_t n, int32_t d, int32_t n_constraints, double length,
+                            const double* lower, const double* upper, const uint8_t* reset01, double* out_bounds,
+                            int32_t* out_center_index, void* stream);
 
 /* Analytic-PR enumeration, materialised: x_all [b, n_options, d_k'] = every discrete configuration pasted next to the
  * continuous columns (normalised; one-hot layout when space->apply_numeric == 0, numeric layout otherwise) and

@@ -80,6 +80,13 @@ def make_cases():
         kernel_type="mixed", binary_dims=[2], n_train=20, b=6, mc=0, acq="pm", apply_numeric=False,
         grad_estimator=None, analytic=True, calls=1, seed=16, edge_rows=True,
     )
+    # ---- the same four shapes at the sizes the named configs actually run at: end-of-run n_train,
+    # mc = 128, restart batches of 5 (one case with all 20 restarts).  One call each to keep the fixtures small.
+    cases["named_ackley13_ei"] = dict(cases["ackley13_ei"], n_train=119, b=20, mc=128, calls=1, seed=21)
+    cases["named_rosenbrock10_ucb"] = dict(cases["rosenbrock10_ucb"], n_train=119, b=5, mc=128, calls=1, seed=22,
+                                           beta=0.2 * 10 * math.log(2 * 100))
+    cases["named_chemistry_analytic_ei"] = dict(cases["chemistry_analytic_ei"], n_train=219, b=5, seed=23)
+    cases["named_mixed_int_f1_ei"] = dict(cases["mixed_int_f1_ei"], n_train=119, b=5, mc=128, calls=1, seed=24)
     return cases
 
 
@@ -213,6 +220,13 @@ def run_case(name, c):
             out["calls"].append(rec)
         out["base_samples"] = getattr(rnd, "base_samples", None)
         out["base_samples_categorical"] = getattr(rnd, "base_samples_categorical", None)
+    # final discrete draw per restart (probabilistic_reparameterization.py:198-233) under a fixed seed of torch's global
+    # (CPU) generator: the reference's own call sequence, one Bernoulli draw per integer parameter, one Categorical per block
+    sc_seed = c["seed"] + 31
+    torch.manual_seed(sc_seed)
+    with torch.no_grad():
+        sc_out = pr.sample_candidates(theta.clone())
+    out["sample_candidates"] = dict(seed=sc_seed, X=theta.clone(), out=sc_out.clone())
     return out
 
 

@@ -238,6 +238,46 @@ def mc_pr(
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# Final discrete draw per restart  (probabilistic_reparameterization.py:198-233)
+# ----------------------------------------------------------------------------------------------------------------------
+def sample_candidates(space: PRSpace, X: Tensor, u: Optional[Tensor] = None) -> Tensor:
+    """``X [b, 1, d]`` normalised -> one sampled configuration per restart, normalised.
+
+    * 199-203  un-normalise, rounding probabilities of the UN-normalised point
+    * 204-209  integer i: ``floor(x_un) + Bernoulli(p)`` -- floor of the SIGNED value (unlike the MC transform's floor|x|)
+    * 210-215  clamp to integer_bounds
+    * 217-229  categorical: ``one_hot(Categorical(probs=p).sample())`` written at the one-hot block
+    * 231-233  normalise
+    ``u is None``: torch's global generator, consumed in the reference's order (one Bernoulli call per integer parameter,
+    then one Categorical call per block) -- pinned bit for bit on the golden draws.  ``u [b, n_int + n_cat]``: explicit
+    uniforms with ``z = [u < p]`` (torch.bernoulli's rule) and the inverse CDF ``first index with cumsum(p) > u`` (last
+    index if none) -- the definition the device kernel ``prb_sample_candidates`` implements for its Philox stream."""
+    X = X.detach().to(torch.float64)
+    x_un = unnormalize(space, X).clone()
+    prob = rounding_prob(space, x_un)
+    k = 0
+    for i in space.integer_indices:
+        p = prob[..., k]
+        z = torch.distributions.Bernoulli(probs=p).sample() if u is None else (u[:, k].view_as(p) < p).to(p)
+        x_un[..., i] = x_un[..., i].floor() + z
+        k += 1
+    if space.n_int > 0:
+        idx = torch.as_tensor(space.integer_indices)
+        x_un[..., idx] = torch.minimum(torch.maximum(x_un[..., idx], space.integer_bounds[0]), space.integer_bounds[1])
+    for j, (s, c) in enumerate(zip(space.cat_starts, space.cat_cards)):
+        p = prob[..., k:k + c]
+        if u is None:
+            cat = torch.distributions.Categorical(probs=p).sample()
+        else:
+            m = p.cumsum(dim=-1) > u[:, space.n_int + j].view(-1, 1, 1)
+            first = ((m.long().cumsum(dim=-1) == 1) & m).long().argmax(dim=-1)
+            cat = torch.where(m.any(dim=-1), first, torch.full_like(first, c - 1))
+        x_un[..., s:s + c] = torch.nn.functional.one_hot(cat, num_classes=c).to(x_un)
+        k += c
+    return normalize(space, x_un)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # Analytic PR  (input.py:273-383, 410-488; probabilistic_reparameterization.py:285-320)
 # ----------------------------------------------------------------------------------------------------------------------
 def all_discrete_options(space: PRSpace) -> Tensor:

@@ -7,8 +7,10 @@ from oracle import gp_oracle as G
 from oracle import pr_oracle as P
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-MC_CASES = ["ackley13_ei", "rosenbrock10_ucb", "chemistry_mc_ei", "mixed_int_f1_ei", "neg_int_onehot_ei"]
-ANALYTIC_CASES = ["chemistry_analytic_ei", "int_cat_analytic_pm"]
+# named_*: the same shapes at the sizes the named configs run at (n_train = 119 / 219, mc = 128, 5 or 20 restarts)
+MC_CASES = ["ackley13_ei", "rosenbrock10_ucb", "chemistry_mc_ei", "mixed_int_f1_ei", "neg_int_onehot_ei",
+            "named_ackley13_ei", "named_rosenbrock10_ucb", "named_mixed_int_f1_ei"]
+ANALYTIC_CASES = ["chemistry_analytic_ei", "int_cat_analytic_pm", "named_chemistry_analytic_ei"]
 
 
 def load(name):

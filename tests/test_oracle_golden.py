@@ -58,3 +58,14 @@ def test_analytic_probs_sum_to_one_inside_bounds():
     space = oracle_space(g)
     probs = P.analytic_probs(space, g["theta"], P.all_discrete_options(space))
     torch.testing.assert_close(probs.sum(-1), torch.ones(probs.shape[0], dtype=torch.float64), rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("name", MC_CASES + ANALYTIC_CASES)
+def test_sample_candidates_matches_reference_draws(name):
+    """a12: the final discrete draw per restart under the recorded torch seed -- same generator consumption order as the
+    reference (one Bernoulli call per integer parameter, one Categorical call per one-hot block) => identical rows."""
+    g = load(name)
+    rec = g["sample_candidates"]
+    torch.manual_seed(rec["seed"])
+    out = P.sample_candidates(oracle_space(g), rec["X"])
+    assert torch.equal(out, rec["out"])
