@@ -10,7 +10,7 @@ import ctypes as C
 import os
 from typing import Optional
 
-PRB_MAX_DIMS = 32
+PRB_MAX_DIMS = 64
 PRB_MAX_FACTORS = 4
 PRB_MAX_TERMS = 2
 PRB_MAX_CAT = 8

@@ -271,7 +271,7 @@ T* at(void* ws, size_t off) {
 // ---- the posterior/acquisition engine over L2-resident column panels ------------------------------------------------
 // generic kernel structures: materialised k* panel -> lower product -> epilogue -> upper product -> gradient contraction
 int run_engine(const Model& m, const DevAcq& aq, const Plan& pl, void* ws, const double* xk, int64_t B, bool need_grad,
-               uint32_t diffmask, double* a, double* dmu, double* dvar, double* S_all, double* out_mean,
+               uint64_t diffmask, double* a, double* dmu, double* dvar, double* S_all, double* out_mean,
                double* out_var, cudaStream_t st) {
   double* panelA = at<double>(ws, pl.off_panelA);
   double* panelV = at<double>(ws, pl.off_panelV);
@@ -387,9 +387,9 @@ int run_engine_sep(const Model& m, const DevAcq& aq, const Plan& pl, void* ws, c
   return PRB_OK;
 }
 
-uint32_t cont_mask(const DevSpace& sp) {
-  uint32_t mask = 0;
-  for (int i = 0; i < sp.n_cont; ++i) mask |= 1u << sp.cont_cols[i];
+uint64_t cont_mask(const DevSpace& sp) {
+  uint64_t mask = 0;
+  for (int i = 0; i < sp.n_cont; ++i) mask |= uint64_t(1) << sp.cont_cols[i];
   return mask;
 }
 
@@ -989,7 +989,7 @@ int prb_finalize_candidates(prb_model* model, const prb_space_desc* space, const
   double* xk = at<double>(workspace, pl.off_xk);
   double* a = out_acq ? out_acq : at<double>(workspace, pl.off_a);
   CUDA_TRY(launch_sample_candidates(sp, theta, b, u, seed, offset, out_x, xk, st));
-  rc = run_engine(m, aq, pl, workspace, xk, b, false, 0u, a, at<double>(workspace, pl.off_dmu),
+  rc = run_engine(m, aq, pl, workspace, xk, b, false, uint64_t(0), a, at<double>(workspace, pl.off_dmu),
                   at<double>(workspace, pl.off_dvar), nullptr, nullptr, nullptr, st);
   if (rc != PRB_OK) return rc;
   if (out_best || out_best_index) CUDA_TRY(launch_best_row(a, out_x, b, sp.d, out_best, out_best_index, st));
@@ -1042,12 +1042,12 @@ int prb_acq_points(prb_model* model, const prb_acq_desc* acq, const double* xk, 
   if (workspace_bytes < pl.total) return PRB_ERR_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   double* a = out_acq ? out_acq : at<double>(workspace, pl.off_a);
-  uint32_t mask = 0;
+  uint64_t mask = 0;
   for (int t = 0; t < m.spec.n_terms; ++t)
     for (int f = 0; f < m.spec.t[t].n_factors; ++f)
       if (m.spec.t[t].f[f].kind == PRB_FACTOR_MATERN52)
-        for (int i = 0; i < m.spec.t[t].f[f].n_dims; ++i) mask |= 1u << m.spec.t[t].f[f].dims[i];
-  if (m.rff_m > 0) mask = m.d_k >= 32 ? 0xffffffffu : ((1u << m.d_k) - 1u);  // a feature map is smooth in every input
+        for (int i = 0; i < m.spec.t[t].f[f].n_dims; ++i) mask |= uint64_t(1) << m.spec.t[t].f[f].dims[i];
+  if (m.rff_m > 0) mask = m.d_k >= 64 ? ~uint64_t(0) : ((uint64_t(1) << m.d_k) - 1u);  // a feature map is smooth in every input
   return run_engine(m, aq, pl, workspace, xk, n_points, out_dacq_dx != nullptr, mask, a,
                     at<double>(workspace, pl.off_dmu), at<double>(workspace, pl.off_dvar), out_dacq_dx, out_mean,
                     out_var, st);
@@ -1276,10 +1276,15 @@ int prb_mc_adam(prb_model* model, const prb_space_desc* space, const prb_acq_des
   if (small_step) CUDA_TRY(cudaMemsetAsync(at<char>(workspace, pl.off_small), 0, pl.small_bytes, st));
   if (small_step && small_adam_persistent_ok(b, mc)) {
     // the whole optimisation -- maxiter Adam steps and the final evaluation -- as one cooperative persistent kernel
-    CUDA_TRY(launch_small_adam_persistent(m, small_gen, sp, aq, bm, dm, theta, lower, upper, b, mc, u_int, u_cat, seed, offset,
-                                          estimator, ma_state, update_ma, val, out_value, adam_state, adam_state + total,
-                                          lr, maxiter, step0, at<char>(workspace, pl.off_small), st));
-    return PRB_OK;
+    cudaError_t ce = launch_small_adam_persistent(m, small_gen, sp, aq, bm, dm, theta, lower, upper, b, mc, u_int, u_cat,
+                                                  seed, offset, estimator, ma_state, update_ma, val, out_value, adam_state,
+                                                  adam_state + total, lr, maxiter, step0, at<char>(workspace, pl.off_small),
+                                                  st);
+    if (ce == cudaSuccess) return PRB_OK;
+    // fewer co-resident CTAs than the device attributes promise (MPS / SM partition): the replayed one-kernel step below
+    if (ce != cudaErrorCooperativeLaunchTooLarge && ce != cudaErrorLaunchOutOfResources)
+      return cuda_fail(ce, "launch_small_adam_persistent");
+    (void)cudaGetLastError();
   }
 
   // kernel structures that do not separate: the six-launch fused step on a single column panel

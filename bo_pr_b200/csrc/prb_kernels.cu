@@ -418,7 +418,7 @@ template <int WPC>
 __global__ void __launch_bounds__(RFF_WARPS * 32) rff_eval_kernel(const double* __restrict__ W, const double* __restrict__ bias,
                                                                   const double* __restrict__ w, int m, int d_k,
                                                                   double scale, const double* __restrict__ xk,
-                                                                  int64_t ncols, uint32_t diffmask, int need_grad,
+                                                                  int64_t ncols, uint64_t diffmask, int need_grad,
                                                                   double* __restrict__ a, double* __restrict__ S_all,
                                                                   double* __restrict__ out_mean,
                                                                   double* __restrict__ out_var, int64_t dim_stride) {
@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(RFF_WARPS * 32) rff_eval_kernel(const double* 
   }
 }
 
-cudaError_t launch_rff_eval(const Model& m, const double* xk, int64_t ncols, uint32_t diffmask, bool need_grad, double* a,
+cudaError_t launch_rff_eval(const Model& m, const double* xk, int64_t ncols, uint64_t diffmask, bool need_grad, double* a,
                             double* S_all, double* out_mean, double* out_var, cudaStream_t st, int64_t dim_stride) {
   ProfScope prof_(K_KSTAR, st);
   if (ncols == 0) return cudaSuccess;
@@ -520,7 +520,7 @@ cudaError_t launch_rff_eval(const Model& m, const double* xk, int64_t ncols, uin
 // =====================================================================================================================
 constexpr int GR_COLS = 128;
 
-__global__ void __launch_bounds__(GR_COLS) grad_contract_kernel(const DevSpec spec, uint32_t diffmask,
+__global__ void __launch_bounds__(GR_COLS) grad_contract_kernel(const DevSpec spec, uint64_t diffmask,
                                                                 const double* __restrict__ Xtr,
                                                                 const double* __restrict__ alpha, int n,
                                                                 const double* __restrict__ xk, int ncols,
@@ -611,7 +611,7 @@ __global__ void __launch_bounds__(GR_COLS) grad_contract_kernel(const DevSpec sp
     S_part[(size_t(blockIdx.y) * d_k + dd) * ncols_pad + col] = accs[dd * GR_COLS + tid];
 }
 
-cudaError_t launch_grad_contract(const Model& m, uint32_t diffmask, const double* xk, int ncols, int ncols_pad,
+cudaError_t launch_grad_contract(const Model& m, uint64_t diffmask, const double* xk, int ncols, int ncols_pad,
                                  const double* W, const double* dmu, const double* dvar, double* S_part, int jrows,
                                  cudaStream_t st) {
   ProfScope prof_(K_GRAD_CONTRACT, st);
@@ -1123,7 +1123,12 @@ cudaError_t launch_analytic_reduce(const DevSpace& sp, const double* theta, int 
 //   sep_step_finish  split sums + MC reduction + Adam update (one CTA per restart); the last CTA to finish advances the EMA
 //                    baseline and the step counter
 // =====================================================================================================================
-__global__ void __launch_bounds__(256) sep_step_prep_kernel(
+constexpr int PREP_THREADS = 128;
+// grid (nb, nsplit): CTA (b, s) owns the s-th slice of the training points (kc, Dc) and of the MC samples (sampler) of
+// restart b, so that a call with few restarts (8 per GPU in the 8-GPU split) still spreads over the SMs: one CTA per restart
+// measured 41-47 us at n = 1000, mc = 1024 -- 7 % of a 0.6 ms step.  The rounding probabilities are recomputed per CTA (a
+// dozen sigmoids).
+__global__ void __launch_bounds__(PREP_THREADS) sep_step_prep_kernel(
     const DevSpace sp, const BitMap bm, const DevFactor fc, double outputscale, const double* __restrict__ Xtr, int n,
     int d_k, int Kp, const double* __restrict__ theta, const double* __restrict__ lower,
     const double* __restrict__ upper, double* __restrict__ Xc, int mc, const double* __restrict__ u_int,
@@ -1133,18 +1138,21 @@ __global__ void __launch_bounds__(256) sep_step_prep_kernel(
   __shared__ double ps_s[PRB_MAX_DIMS], offs_s[PRB_MAX_DIMS];  // the separable path has no categoricals: n_disc = n_int
   grid_dep_launch();
   const int b = blockIdx.x, tid = threadIdx.x;
+  const int split = blockIdx.y, nsplit = gridDim.y;
   if (tid < sp.d) {
     double v = theta[size_t(b) * sp.d + tid];
     if (lower) v = fmin(fmax(v, lower[tid]), upper[tid]);  // columnwise_clamp (gen.py:304-305, 323)
     th_s[tid] = v;
-    if (Xc) Xc[size_t(b) * sp.d + tid] = v;
+    if (Xc && split == 0) Xc[size_t(b) * sp.d + tid] = v;
   }
   __syncthreads();
-  pr_restart_probs(sp, th_s, tid, 256, ps_s, offs_s);
+  pr_restart_probs(sp, th_s, tid, PREP_THREADS, ps_s, offs_s);
   __syncthreads();
-  if (prob)
-    for (int k = tid; k < sp.n_disc; k += 256) prob[size_t(b) * sp.n_disc + k] = ps_s[k];
-  for (int j = tid; j < Kp; j += 256) {
+  if (prob && split == 0)
+    for (int k = tid; k < sp.n_disc; k += PREP_THREADS) prob[size_t(b) * sp.n_disc + k] = ps_s[k];
+  const int jper = (Kp + nsplit - 1) / nsplit;
+  const int j_end = min(Kp, (split + 1) * jper);
+  for (int j = split * jper + tid; j < j_end; j += PREP_THREADS) {
     double val = 0.0, G = 0.0;
     if (j < n) {
       double r2 = 0.0;
@@ -1165,7 +1173,9 @@ __global__ void __launch_bounds__(256) sep_step_prep_kernel(
       }
     }
   }
-  for (int i = tid; i < mc; i += 256) {
+  const int iper = (mc + nsplit - 1) / nsplit;
+  const int i_end = min(mc, (split + 1) * iper);
+  for (int i = split * iper + tid; i < i_end; i += PREP_THREADS) {
     const size_t col = size_t(b) * mc + i;
     zbits[col] = pr_sample_point(sp, th_s, ps_s, offs_s, i, u_int, u_cat, seed, offset, nullptr, nullptr,
                                  z ? z + col * sp.n_disc : nullptr, bm);
@@ -1178,14 +1188,22 @@ cudaError_t launch_sep_step_prep(const Model& m, const DevSpace& sp, const BitMa
                                  double* Dc, uint8_t* z, double* prob, uint32_t* zbits, cudaStream_t st) {
   ProfScope prof_(K_SAMPLE, st);
   if (nb == 0) return cudaSuccess;
-  sep_step_prep_kernel<<<nb, 256, 0, st>>>(sp, bm, m.spec.t[0].f[m.sep_cont_factor], m.spec.t[0].outputscale, m.Xtr, m.n,
-                                          m.d_k, m.Kp, theta, lower, upper, Xc, mc, u_int, u_cat, seed, offset, kc, Dc, z,
-                                          prob, zbits);
+  // ~4 CTAs per SM in total, but no slice thinner than one item per thread
+  const int work = (m.Kp > mc ? m.Kp : mc);
+  int nsplit = (4 * 148 + nb - 1) / nb;
+  const int max_split = (work + PREP_THREADS - 1) / PREP_THREADS;
+  if (nsplit > max_split) nsplit = max_split;
+  if (nsplit < 1) nsplit = 1;
+  sep_step_prep_kernel<<<dim3(nb, nsplit), PREP_THREADS, 0, st>>>(sp, bm, m.spec.t[0].f[m.sep_cont_factor],
+                                                                 m.spec.t[0].outputscale, m.Xtr, m.n, m.d_k, m.Kp, theta,
+                                                                 lower, upper, Xc, mc, u_int, u_cat, seed, offset, kc, Dc,
+                                                                 z, prob, zbits);
   count_launch();
   return cudaGetLastError();
 }
 
-constexpr int FINISH_THREADS = 512;
+constexpr int FINISH_THREADS = 1024;
+constexpr int FIN_ILP = 8;  // independent partial sums per lane in the finish kernel's reductions
 // One CTA per restart, one WARP per reduction (value, each continuous column, each discrete column): no block-wide
 // barrier inside the reductions -- at experiment sizes the step is latency bound and thirteen sequential block reductions
 // cost 17 us; this form costs ~3 us.  Fixed lane-strided order + xor-tree => deterministic.
@@ -1222,29 +1240,58 @@ __global__ void __launch_bounds__(FINISH_THREADS) sep_step_finish_kernel(
   const int n_tasks = need_grad ? 1 + n_cont_tasks + sp.n_disc : 1;
   for (int task = warp; task < n_tasks; task += FINISH_THREADS / 32) {
     double t = 0.0;
+    // lane-strided sums with FIN_ILP independent chains per lane (the loads of one trip are all in flight together: a
+    // single dependent chain of mc / 32 global loads cost ~1 us each and made this kernel 37 us); chains are combined in a
+    // fixed order, then the xor tree => deterministic
+    double tc[FIN_ILP];
+#pragma unroll
+    for (int q = 0; q < FIN_ILP; ++q) tc[q] = 0.0;
     if (task == 0) {
-      for (int i = lane; i < mc; i += 32) t += a[c0 + i];
+      for (int i0 = lane; i0 < mc; i0 += 32 * FIN_ILP) {
+#pragma unroll
+        for (int q = 0; q < FIN_ILP; ++q) {
+          const int i = i0 + 32 * q;
+          if (i < mc) tc[q] += a[c0 + i];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < FIN_ILP; ++q) t += tc[q];
       t = warp_sum(t);
       if (lane == 0) out_value[bi] = t / double(mc);
     } else if (task <= n_cont_tasks) {
       const int ci = (task - 1) / nsplit, part = (task - 1) % nsplit;
       const int slot = slot_is_dim ? dm.dims[ci] : ci;
       const int mt0 = part * mt_per, mt1 = min(mtiles, mt0 + mt_per);
-      for (int i = lane; i < mc; i += 32) {
-        double v = 0.0;
-        for (int mt = mt0; mt < mt1; ++mt) v += S_part[(size_t(mt) * slots + slot) * ncols_pad + c0 + i];
-        t += v;
+      for (int i0 = lane; i0 < mc; i0 += 32 * FIN_ILP) {
+        for (int mt = mt0; mt < mt1; ++mt) {
+          const double* row = S_part + (size_t(mt) * slots + slot) * ncols_pad + c0;
+#pragma unroll
+          for (int q = 0; q < FIN_ILP; ++q) {
+            const int i = i0 + 32 * q;
+            if (i < mc) tc[q] += row[i];
+          }
+        }
       }
+#pragma unroll
+      for (int q = 0; q < FIN_ILP; ++q) t += tc[q];
       t = warp_sum(t);
       if (lane == 0) csum[ci][part] = t;
     } else {
       // discrete columns: integers first, then the one-hot columns (the order of `discrete_indices`, input.py:574-597)
       const int kd = task - 1 - n_cont_tasks;
       const double p = prob[size_t(bi) * sp.n_disc + kd];
-      for (int i = lane; i < mc; i += 32) {
-        const double zi = double(z[(c0 + i) * sp.n_disc + kd]);
-        t += ((a[c0 + i] - baseline) * (zi - p)) / sp.tau;
+      for (int i0 = lane; i0 < mc; i0 += 32 * FIN_ILP) {
+#pragma unroll
+        for (int q = 0; q < FIN_ILP; ++q) {
+          const int i = i0 + 32 * q;
+          if (i < mc) {
+            const double zi = double(z[(c0 + i) * sp.n_disc + kd]);
+            tc[q] += ((a[c0 + i] - baseline) * (zi - p)) / sp.tau;
+          }
+        }
       }
+#pragma unroll
+      for (int q = 0; q < FIN_ILP; ++q) t += tc[q];
       t = warp_sum(t);
       if (lane == 0) g_s[kd < sp.n_int ? sp.int_cols[kd] : cat0 + (kd - sp.n_int)] = go * (t / double(mc));
     }

@@ -31,7 +31,7 @@ cudaError_t launch_kstar_panel(const Model& m, const double* xk, int ncols, int 
                                cudaStream_t st);
 cudaError_t launch_kernel_matrix(const DevSpec& spec, const double* Xtr, int n, const double* xk, int n_points,
                                  double* out, cudaStream_t st);
-cudaError_t launch_rff_eval(const Model& m, const double* xk, int64_t ncols, uint32_t diffmask, bool need_grad, double* a,
+cudaError_t launch_rff_eval(const Model& m, const double* xk, int64_t ncols, uint64_t diffmask, bool need_grad, double* a,
                             double* S_all, double* out_mean, double* out_var, cudaStream_t st, int64_t dim_stride = 0);
 cudaError_t launch_acq_epilogue(const Model& m, const DevAcq& aq, const double* norm_part, int ncols_pad,
                                 const double* mu_dot, int ncols, double* a, double* dmu, double* dvar,
@@ -46,7 +46,7 @@ cudaError_t launch_mc_reduce_dedup(const DevSpace& sp, const BitMap& bm, int b, 
                                    const double* grad_out, double* out_value, double* out_grad, cudaStream_t st);
 cudaError_t launch_dedup_scatter(const double* a, const int* ustart, const int* inv, int b, int mc, double* out,
                                  cudaStream_t st);
-cudaError_t launch_grad_contract(const Model& m, uint32_t diffmask, const double* xk, int ncols, int ncols_pad,
+cudaError_t launch_grad_contract(const Model& m, uint64_t diffmask, const double* xk, int ncols, int ncols_pad,
                                  const double* W, const double* dmu, const double* dvar, double* S_part, int jrows,
                                  cudaStream_t st);
 cudaError_t launch_sum_splits(const Model& m, const double* S_part, int jblocks, const DimMap* dm, int ncols,

@@ -100,9 +100,12 @@ def _is_fusable(acquisition_function, options, callback, optimizer, fixed_featur
     from .probabilistic_reparameterization import (AnalyticProbabilisticReparameterization,
                                                    MCProbabilisticReparameterization)
 
-    return (isinstance(acquisition_function, (MCProbabilisticReparameterization,
-                                              AnalyticProbabilisticReparameterization)) and callback is None
-            and optimizer is torch.optim.Adam and not options.get("decay", False) and not fixed_features
+    if not isinstance(acquisition_function, (MCProbabilisticReparameterization, AnalyticProbabilisticReparameterization)):
+        return False
+    rnd = acquisition_function.input_transform["round"]
+    if getattr(rnd, "resample", False):
+        return False  # fresh base samples on every forward: the device loop keeps one draw for all steps
+    return (callback is None and optimizer is torch.optim.Adam and not options.get("decay", False) and not fixed_features
             and options.get("fused", True)
             and (options.get("rel_tol") is None or options.get("rel_tol") == float("-inf")))
 
@@ -219,7 +222,9 @@ def gen_candidates_torch(
     if options.get("rel_tol") is None:
         options["rel_tol"] = float("-inf")  # the reference writes this into the caller's dict too (gen.py:311-313)
     maxiter = int(options.get("maxiter", 10000))
-    if _is_fusable(acquisition_function, options, callback, optimizer, fixed_features):
+    # the device loop clamps against explicit bounds; `None` bounds (the reference then does not clamp) take the host loop
+    if lower_bounds is not None and upper_bounds is not None and \
+            _is_fusable(acquisition_function, options, callback, optimizer, fixed_features):
         from .probabilistic_reparameterization import AnalyticProbabilisticReparameterization
         fused = (_fused_analytic_adam if isinstance(acquisition_function, AnalyticProbabilisticReparameterization)
                  else _fused_mc_adam)

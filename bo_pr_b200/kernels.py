@@ -60,6 +60,7 @@ class _StationaryKernel(Kernel):
         if c is not None and bool(((v < c.lower_bound) | (v > c.upper_bound)).any()):
             raise ValueError(f"lengthscale {v.tolist()} violates Interval({c.lower_bound}, {c.upper_bound})")
         self._lengthscale = v.clone()
+        self._version = getattr(self, "_version", 0) + 1
 
 
 class MaternKernel(_StationaryKernel):
@@ -91,6 +92,7 @@ class ScaleKernel(Kernel):
         if not bool(v > 0):
             raise ValueError("outputscale must be positive")
         self._outputscale = v.clone()
+        self._version = getattr(self, "_version", 0) + 1
 
 
 class ProductKernel(Kernel):
@@ -232,3 +234,21 @@ def kernel_terms(covar_module, d_k: int) -> List[TermT]:
         additive = type(base).__name__ == "AdditiveKernel"
         terms.append((scale, additive, _factors(base, d_k, additive)))
     return terms
+
+
+def kernel_fingerprint(k) -> tuple:
+    """Cheap identity of a kernel tree's hyper-parameters: the classes above bump ``_version`` on every assignment;
+    duck-typed GPyTorch kernels are fingerprinted through the storage and in-place version counter of their (raw)
+    parameter tensors.  ``GPState`` caches are rebuilt when this changes (stale Cholesky factors would silently give wrong
+    PR values)."""
+    name = type(k).__name__
+    out = [name, id(k), getattr(k, "_version", 0)]
+    for attr in ("raw_lengthscale", "raw_outputscale"):
+        t = getattr(k, attr, None)
+        if torch.is_tensor(t):
+            out += [t.data_ptr(), t._version]
+    if name == "ScaleKernel":
+        out.append(kernel_fingerprint(k.base_kernel))
+    elif name in ("ProductKernel", "AdditiveKernel"):
+        out += [kernel_fingerprint(m) for m in k.kernels]
+    return tuple(out)

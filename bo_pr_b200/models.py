@@ -17,7 +17,7 @@ import torch
 from torch import Tensor
 
 from . import _capi as capi
-from .kernels import TermT, kernel_terms
+from .kernels import TermT, kernel_fingerprint, kernel_terms
 
 MIN_FIXED_NOISE = 1e-6  # gpytorch raises fixed noise below this (float64) with a warning
 MIN_VARIANCE = 1e-10  # gpytorch.settings.min_variance for float64
@@ -218,12 +218,19 @@ class FixedNoiseGP(Model):
         self._state = None
         return self
 
+    def _fingerprint(self) -> tuple:
+        return _model_fingerprint(self)
+
     @property
     def state(self) -> GPState:
-        if self._state is None:
+        """The device GP state, rebuilt whenever the training data, the noise, the mean constant or any kernel
+        hyper-parameter has changed since it was built (a stale Cholesky factor would silently give wrong PR values)."""
+        fp = self._fingerprint()
+        if self._state is None or self._state_fp != fp:
             X = self.train_inputs[0]
             self._state = GPState(X, self.train_targets, kernel_terms(self.covar_module, X.shape[-1]),
                                   self.likelihood.noise, float(self.mean_module.constant))
+            self._state_fp = fp
         return self._state
 
     def posterior(self, X: Tensor, observation_noise: bool = False, **kwargs) -> _Posterior:
@@ -236,6 +243,24 @@ class FixedNoiseGP(Model):
         return _Posterior(mean.reshape(*shape, 1), var.reshape(*shape, 1))
 
 
+def _tensor_fp(t) -> tuple:
+    if torch.is_tensor(t):
+        return (t.data_ptr(), t._version, tuple(t.shape))
+    return (t,)
+
+
+def _model_fingerprint(model) -> tuple:
+    """Identity of everything the device GP state is built from: storage + in-place version counter of the training
+    tensors, the noise and the mean constant, and the kernel tree's hyper-parameters (``kernel_fingerprint``).  Re-assigning
+    or mutating any of them in place changes it; a few microseconds per call."""
+    mm = model.mean_module
+    const = getattr(mm, "raw_constant", None)
+    if const is None:
+        const = getattr(mm, "constant", None)
+    return (_tensor_fp(model.train_inputs[0]), _tensor_fp(model.train_targets), _tensor_fp(model.likelihood.noise),
+            _tensor_fp(const), kernel_fingerprint(model.covar_module))
+
+
 def gp_state_from_model(model) -> GPState:
     """GP state of one of our models, or of a duck-typed BoTorch ``FixedNoiseGP``/``SingleTaskGP`` in eval mode
     (``train_inputs[0]``, ``train_targets``, ``mean_module.constant``, ``likelihood.noise``, ``covar_module`` tree)."""
@@ -246,9 +271,10 @@ def gp_state_from_model(model) -> GPState:
             raise NotImplementedError(f"model.{attr} is not supported by the B200 hot path")
     if hasattr(model, "models"):
         raise NotImplementedError("ModelListGP is not supported by the B200 hot path")
+    fp = _model_fingerprint(model)
     cached = getattr(model, "_prb_state", None)
-    if cached is not None:
-        return cached
+    if cached is not None and cached[0] == fp:
+        return cached[1]
     X = model.train_inputs[0]
     if X.ndim != 2:
         raise NotImplementedError("batched models are not supported by the B200 hot path")
@@ -256,7 +282,7 @@ def gp_state_from_model(model) -> GPState:
     state = GPState(X, model.train_targets, kernel_terms(model.covar_module, X.shape[-1]), noise,
                     float(torch.as_tensor(model.mean_module.constant).detach().reshape(-1)[0]))
     try:
-        model._prb_state = state
+        model._prb_state = (fp, state)
     except Exception:
         pass
     return state

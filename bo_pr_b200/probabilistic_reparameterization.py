@@ -232,6 +232,10 @@ class _AnalyticPRFunction(Function):
             return X.new_empty(0, dtype=torch.float64)
         rnd = module.input_transform["round"]
         codes = rnd.option_codes
+        if codes.device != X.device:  # the transform lives on the constructor's `device`: never hand the kernel a foreign pointer
+            codes = module.__dict__.get("_codes_on")
+            if codes is None or codes.device != X.device:
+                codes = module.__dict__["_codes_on"] = rnd.option_codes.to(X.device)
         n_opt = codes.shape[0]
         theta = X.detach().to(torch.float64).reshape(b, d).contiguous()
         need = ctx.needs_input_grad[0]
@@ -359,13 +363,78 @@ class MCProbabilisticReparameterization(AbstractProbabilisticReparameterization)
         return out
 
     def forward(self, X: Tensor) -> Tensor:
+        """One ``prb_mc_value_grad`` enqueue.  The reference's ``forward`` hands twelve arguments to its autograd Function
+        (:383-396; that Function is kept below with the same signature); this one passes the module itself, and
+        everything that only depends on constructor arguments is resolved once per (module, device) -- the host time before
+        the first kernel is queued is on the critical path of a sub-millisecond step (8 restarts per GPU)."""
         _check_X(X, self.dim)
-        gp_state_from_model(self.acq_function.model).set_option(capi.PRB_OPT_DEDUP, int(self.dedup))
-        return self._pr_acq_function.apply(
-            X, self.acq_function, self.input_transform, self.input_transform_flip, self.batch_limit,
-            self.integer_indices, self.cont_indices, self.categorical_indices, self.grad_estimator,
-            self.one_hot_to_numeric, self.ma_counter, self.ma_hidden,
-        )
+        return _MCPRCall.apply(X, self)
+
+    def _call_ctx(self, dev: torch.device):
+        cc = self.__dict__.get("_cc")
+        if cc is None or cc["dev"] != dev:
+            rnd = self.input_transform["round"]
+            cc = self.__dict__["_cc"] = {
+                "dev": dev, "idx": dev.index if dev.index is not None else torch.cuda.current_device(), "rnd": rnd,
+                "est": capi.PRB_EST_REINFORCE_MA if self.grad_estimator == "reinforce_ma" else capi.PRB_EST_REINFORCE,
+                "sp": C.byref(self._space()), "sp_obj": self._space(), "tau": rnd.tau, "ma_ptr": self._ma_state.data_ptr(),
+                "fn": capi.load_library().prb_mc_value_grad,
+            }
+        return cc
+
+    def _launch(self, X: Tensor, need: bool):
+        """(value [b], unit gradient [b, d] or None): the library call behind ``forward``."""
+        b, d = X.shape[0], X.shape[-1]
+        dev = X.device
+        if b == 0:  # nothing to evaluate; the reference's EMA update would average an empty tensor (NaN): leave the state
+            return X.new_empty(0, dtype=torch.float64), None
+        cc = self._call_ctx(dev)
+        rnd = cc["rnd"]
+        if cc["tau"] != rnd.tau or cc["ma_ptr"] != self._ma_state.data_ptr():  # tau edited / module moved: rebuild
+            self.__dict__.pop("_cc", None)
+            self.__dict__.pop("_space_cached", None)
+            cc = self._call_ctx(dev)
+        state = gp_state_from_model(self.acq_function.model)
+        state.set_option(capi.PRB_OPT_DEDUP, int(self.dedup))
+        if rnd.resample or cc.get("u_ver") is None:
+            rnd.ensure_base_samples(1, dev)
+            ui, uc = rnd.base_sample_ptrs()
+            cc["u_ver"] = (capi.ptr(ui), capi.ptr(uc), ui, uc)
+        u_int, u_cat = cc["u_ver"][0], cc["u_ver"][1]
+        theta = X if (X.dtype is torch.float64 and X.is_contiguous()) else \
+            X.detach().to(torch.float64).reshape(b, d).contiguous()
+        value = torch.empty(b, dtype=torch.float64, device=dev)
+        grad = torch.empty(b, d, dtype=torch.float64, device=dev) if need else None
+        ones = state.ones(b) if need else None
+        mc = rnd.mc_samples
+        ws = state.workspace(b * mc, d, b)
+        aq = acq_desc_of(self.acq_function)
+        idx = cc["idx"]
+        args = (state.handle, cc["sp"], C.byref(aq), theta.data_ptr(), b, mc, u_int, u_cat, 0, 0, cc["est"],
+                self._ma_state.data_ptr(), 1, capi.ptr(ones), value.data_ptr(), capi.ptr(grad), None, ws.data_ptr(),
+                ws.numel(), int(state.chunk_cols))
+        if torch._C._cuda_getDevice() == idx:
+            capi.check(cc["fn"](*args, torch._C._cuda_getCurrentRawStream(idx)), "prb_mc_value_grad")
+        else:
+            with torch.cuda.device(dev):
+                capi.check(cc["fn"](*args, torch._C._cuda_getCurrentRawStream(idx)), "prb_mc_value_grad")
+        return value, grad
+
+
+class _MCPRCall(Function):
+    """Lean autograd bridge used by ``MCProbabilisticReparameterization.forward`` (two arguments instead of twelve)."""
+
+    @staticmethod
+    def forward(ctx, X: Tensor, module: "MCProbabilisticReparameterization"):
+        value, ctx.unit_grad = module._launch(X, ctx.needs_input_grad[0])
+        return value
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        if ctx.unit_grad is None:
+            return None, None
+        # the library evaluated the estimator for grad_output = 1; it is linear in grad_output (:613-633)
+        return (ctx.unit_grad * grad_output.unsqueeze(-1)).unsqueeze(-2), None
 
 
 class _MCProbabilisticReparameterization(Function):

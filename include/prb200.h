@@ -29,7 +29,7 @@ extern "C" {
 
 #define PRB_VERSION 100
 
-#define PRB_MAX_DIMS 32     /* kernel-input columns / theta columns */
+#define PRB_MAX_DIMS 64     /* kernel-input columns / theta columns (svm: 50 binary + 3 continuous = 53) */
 #define PRB_MAX_FACTORS 4   /* multiplicative (or additive) factors per term */
 #define PRB_MAX_TERMS 2     /* additive ScaleKernel terms */
 #define PRB_MAX_CAT 8       /* categorical parameters */

@@ -105,3 +105,30 @@ def test_python_layer_refuses_unsupported_inputs():
     from bo_pr_b200.kernels import kernel_terms
     with pytest.raises(NotImplementedError):
         kernel_terms(FakeTanimoto(), 3)
+
+
+def test_gp_state_is_rebuilt_when_hyperparameters_change():
+    """the cached device GP state must not outlive the hyper-parameters it was built from.  Evaluate, assign a
+    new lengthscale / mutate the targets in place, evaluate again: the result equals a freshly built model's."""
+    from tests.golden_util import load
+    from tests.product_util import product_acq, product_model
+    g = load("ackley13_ei")
+    model = product_model(g, DEV)
+    acq = product_acq(g, DEV, model=model)
+    X = g["theta"][:4].to(DEV)
+    with torch.no_grad():
+        v0 = acq(X).clone()
+    leaf = model.covar_module.base_kernel.kernels[0]
+    new_ls = (leaf.lengthscale * 1.7).clone()
+    leaf.lengthscale = new_ls  # no refresh()
+    with torch.no_grad():
+        v1 = acq(X).clone()
+    g2 = dict(g, hp=dict(g["hp"], cont_lengthscale=new_ls.reshape(-1).tolist()))
+    with torch.no_grad():
+        v_fresh = product_acq(g2, DEV)(X)
+    assert not torch.allclose(v0, v1)
+    assert torch.equal(v1, v_fresh)
+    model.train_targets.mul_(0.5)  # in-place mutation bumps the tensor's version counter
+    with torch.no_grad():
+        v2 = acq(X)
+    assert not torch.allclose(v1, v2)

@@ -267,3 +267,32 @@ def test_dedup_per_sample_values_and_fused_adam():
         outs.append(B.gen_candidates_torch(ics, prx, bounds[0], bounds[1], options={"maxiter": 15}))
     assert torch.allclose(outs[0][0], outs[1][0], rtol=0, atol=1e-10)
     assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-9, atol=1e-13)
+
+
+def test_svm_shape_53_dims_vs_oracle():
+    """the reference's svm / svm_TR configs have 50 binary + 3 continuous parameters (dim 53 > the old 32-column
+    limit).  50 binary dims do not fit the 32-bit code of the separable path, so this runs the generic kernels."""
+    from tests.random_cases import build_problem
+    d = 53
+    c = dict(dim=d, integer_indices=list(range(3, d)), integer_bounds=[[0.0] * 50, [1.0] * 50], categorical_features=None,
+             kernel_type="mixed", binary_dims=list(range(3, d)), n_train=140, b=4, mc=48, acq="ei", apply_numeric=False,
+             grad_estimator="reinforce_ma", seed=41, beta=1.0)
+    g = build_problem(c)
+    space, oacq = oracle_space(g), oracle_acq(g)
+    ref = P.mc_pr(space, g["theta"], oacq, g["base_samples"], None, grad_estimator="reinforce_ma", ma_counter=2.0,
+                  ma_hidden=0.01)
+    pr = product_mc_pr(g, DEV)
+    pr._ma_state.copy_(torch.tensor([2.0, 0.01], dtype=torch.float64))
+    X = g["theta"].to(DEV).requires_grad_(True)
+    val = pr(X)
+    grad = torch.autograd.grad(val.sum(), X)[0]
+    _assert_close(val, ref.value, "PR value (d = 53)")
+    _assert_close(grad, ref.grad, "PR gradient (d = 53)", atol=1e-11)
+    tilde = pr.input_transform(g["theta"].to(DEV).unsqueeze(-3))
+    assert torch.equal(tilde.cpu(), ref.tilde_x)
+    # multi-start Adam on the same problem: fused device loop == host loop
+    import bo_pr_b200 as B
+    lo, hi = torch.zeros(d, dtype=torch.float64, device=DEV), torch.ones(d, dtype=torch.float64, device=DEV)
+    cf, vf = B.gen_candidates_torch(g["theta"].to(DEV), product_mc_pr(g, DEV), lo, hi, options={"maxiter": 5})
+    ch, vh = B.gen_candidates_torch(g["theta"].to(DEV), product_mc_pr(g, DEV), lo, hi, options={"maxiter": 5, "fused": False})
+    assert torch.allclose(cf, ch, rtol=0, atol=1e-10) and torch.allclose(vf, vh, rtol=1e-8, atol=1e-12)

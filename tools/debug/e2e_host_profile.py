@@ -5,7 +5,7 @@ import torch
 from bench_workload import make_problem, make_theta
 from tests.product_util import product_acq, product_mc_pr
 dev = torch.device("cuda", 0)
-n, b, mc = 1000, 64, 1024
+n, b, mc = 1000, (int(sys.argv[1]) if len(sys.argv) > 1 else 64), 1024
 problem = make_problem(n, seed=0); problem["case"]["mc"] = mc; problem["base_samples"] = None; problem["base_samples_categorical"] = None
 acq = product_acq(problem, dev)
 pr = product_mc_pr(dict(problem, case=dict(problem["case"], grad_estimator="reinforce_ma")), dev, acq=acq)
