@@ -115,6 +115,30 @@ int make_spec(const prb_model_desc* d, DevSpec* out, double* kss) {
     }
     diag += T.outputscale * (T.additive ? double(T.n_factors) : 1.0);
   }
+  int nu = 0;
+  bool fits = true;
+  for (int t = 0; t < d->n_terms && fits; ++t)
+    for (int f = 0; f < out->t[t].n_factors && fits; ++f) {
+      const DevFactor& F = out->t[t].f[f];
+      int u = -1;
+      for (int k = 0; k < nu && u < 0; ++k) {
+        const DevFactor& G = out->t[out->first_t[k]].f[out->first_f[k]];
+        bool same = G.kind == F.kind && G.n_dims == F.n_dims;
+        for (int i = 0; i < F.n_dims && same; ++i) same = G.dims[i] == F.dims[i] && G.inv_ls[i] == F.inv_ls[i];
+        if (same) u = k;
+      }
+      if (u < 0) {
+        if (nu == 4) {
+          fits = false;
+          break;
+        }
+        u = nu++;
+        out->first_t[u] = int8_t(t);
+        out->first_f[u] = int8_t(f);
+      }
+      out->uid[t][f] = int8_t(u);
+    }
+  out->n_unique = fits ? int8_t(nu) : int8_t(0);
   *kss = diag;
   return PRB_OK;
 }
@@ -174,7 +198,7 @@ struct Plan {
   int64_t B, B_pad;
   int C, nchunks;
   size_t off_xk, off_z, off_prob, off_a, off_dmu, off_dvar, off_S_all, off_probs;
-  size_t off_panelA, off_panelV, off_norm, off_mu, off_S_part;
+  size_t off_panelA, off_panelV, off_panelQ, off_norm, off_mu, off_S_part;
   size_t off_Xc, off_grad, off_ones, off_val, off_step;
   size_t off_zbits, off_kc, off_Dc;
   size_t off_done, off_small, small_bytes;
@@ -201,9 +225,11 @@ Plan make_plan(const Model& m, int64_t n_points, int n_restarts, int d_theta, in
     // each way (2 x 8 n bytes per column against 2 n^2 flop), so L2 residency does not matter and wide panels win:
     // fewer launches, and the partial last wave of the triangular tile schedule is amortised over more tiles
     // (measured: 96 MB -> 5.22 ms, 1.1 GB -> 4.77 ms per 65 536-column step at n = 1000).
+    // PR calls (n_restarts > 0): panels wide enough that the benchmark shape (65 536 columns at n = 1000) is ONE panel and
+    // runs the fused step; the k* / v / Q panels are each streamed once per product, so L2 residency does not matter.
     size_t budget = panel_budget_bytes();
-    if (m.sep_ok && n_restarts > 0 && env_knobs().panel_mb <= 0) budget = size_t(2048) << 20;
-    C = int64_t(budget / (sizeof(double) * size_t(m.Mp1 + m.Mp2))) / 128 * 128;
+    if (n_restarts > 0 && env_knobs().panel_mb <= 0) budget = size_t(2048) << 20;
+    C = int64_t(budget / (sizeof(double) * size_t(m.Mp1 + m.Mp2 + (m.sep_ok && n_restarts > 0 ? 0 : m.Kp)))) / 128 * 128;
     if (C < 128) C = 128;
   }
   C = round_up64(C, 128);
@@ -229,6 +255,7 @@ Plan make_plan(const Model& m, int64_t n_points, int n_restarts, int d_theta, in
   p.off_probs = take(size_t(p.B_pad) * dbl);
   p.off_panelA = take(size_t(m.Mp2) * C * dbl);
   p.off_panelV = take(size_t(C) * m.Mp1 * dbl);
+  p.off_panelQ = take(size_t(C) * m.Kp * dbl);  // derivative-factor panel of the generic path (kstar_q_kernel)
   p.off_norm = take(size_t(m.Mp1 / GEMM_BM) * C * dbl);
   p.off_mu = take(size_t(C) * dbl);
   // small panels: 4 training rows per CTA of the generic gradient contraction instead of 128 (32x the CTAs; the kernel is
@@ -278,6 +305,9 @@ int run_engine(const Model& m, const DevAcq& aq, const Plan& pl, void* ws, const
   double* norm = at<double>(ws, pl.off_norm);
   double* mu = at<double>(ws, pl.off_mu);
   double* S_part = at<double>(ws, pl.off_S_part);
+  double* panelQ = at<double>(ws, pl.off_panelQ);
+  GradGroup gq;
+  const bool gq_ok = need_grad && m.rff_m == 0 && build_grad_group(m.spec, diffmask, &gq);
 
   if (m.rff_m > 0) {  // deterministic posterior sample: the acquisition value is the sample path itself (PosteriorMean)
     if (aq.kind != PRB_ACQ_MEAN) return PRB_ERR_INVALID;
@@ -288,7 +318,7 @@ int run_engine(const Model& m, const DevAcq& aq, const Plan& pl, void* ws, const
     const int ncols = int(B - c0 < pl.C ? B - c0 : pl.C);
     const int ncols_pad = round_up(ncols, 128);
     const double* xkc = xk + size_t(c0) * m.d_k;
-    CUDA_TRY(launch_kstar_panel(m, xkc, ncols, ncols_pad, panelA, st));
+    CUDA_TRY(launch_kstar_panel(m, xkc, ncols, ncols_pad, panelA, st, gq_ok ? &gq : nullptr, panelQ));
     FusedAcq fa;  // single row tile: the acquisition epilogue runs inside the lower product
     fa.aq = aq;
     fa.a = a + c0;
@@ -302,7 +332,14 @@ int run_engine(const Model& m, const DevAcq& aq, const Plan& pl, void* ws, const
       CUDA_TRY(launch_acq_epilogue(m, aq, norm, ncols_pad, mu, ncols, a + c0, dmu + c0, dvar + c0,
                                    out_mean ? out_mean + c0 : nullptr, out_var ? out_var + c0 : nullptr, nullptr, 0,
                                    st));
-    if (need_grad) {
+    if (need_grad && gq_ok) {
+      // gradient contraction fused into the upper product's epilogue: no W panel, no second kernel evaluation
+      CUDA_TRY(launch_tma_upper_gradq(m, panelV, pl.C, ncols, ncols_pad, gq, panelQ, xkc, dmu + c0, dvar + c0, S_part, st));
+      CUDA_TRY(launch_sum_splits(m, S_part, m.Mp2 / GEMM_BM, nullptr, ncols, ncols_pad, S_all + size_t(c0) * m.d_k,
+                                 nullptr, 0, st));
+    } else if (need_grad) {
+      // several distinct Matern factors carry a gradient (e.g. d acq / dx over the binary factor's dims too): W panel +
+      // the general contraction kernel
       CUDA_TRY(launch_tma_upper(m, panelV, pl.C, ncols_pad, panelA, st));
       CUDA_TRY(launch_grad_contract(m, diffmask, xkc, ncols, ncols_pad, panelA, dmu + c0, dvar + c0, S_part,
                                     pl.grad_jrows, st));
@@ -483,7 +520,11 @@ int generic_step(const Model& m, const DevSpace& sp, const DevAcq& aq, const Pla
                                     lr, step_ptr, m.done_ctr, st));
     return PRB_OK;
   }
-  CUDA_TRY(launch_kstar_panel(m, xk, ncols, ncols_pad, panelA, st));
+  double* panelQ = at<double>(ws, pl.off_panelQ);
+  GradGroup gq;
+  const bool gq_ok = need_path && build_grad_group(m.spec, cont_mask(sp), &gq);
+  PdlScope pdl(!env_knobs().no_pdl);  // the kernels below overlap their launch + prologue with their predecessor
+  CUDA_TRY(launch_kstar_panel(m, xk, ncols, ncols_pad, panelA, st, gq_ok ? &gq : nullptr, panelQ));
   FusedAcq fa;
   fa.aq = aq;
   fa.a = a;
@@ -494,14 +535,19 @@ int generic_step(const Model& m, const DevSpace& sp, const DevAcq& aq, const Pla
   CUDA_TRY(launch_tma_lower(m, panelA, pl.C, ncols_pad, need_path ? panelV : nullptr, norm, mu, fuse ? &fa : nullptr, st));
   if (!fuse)
     CUDA_TRY(launch_acq_epilogue(m, aq, norm, ncols_pad, mu, ncols, a, dmu, dvar, nullptr, nullptr, nullptr, 0, st));
-  if (need_path) {
+  int jblocks = m.Mp2 / pl.grad_jrows;
+  if (need_path && gq_ok) {
+    CUDA_TRY(launch_tma_upper_gradq(m, panelV, pl.C, ncols, ncols_pad, gq, panelQ, xk, dmu, dvar, S_part, st));
+    jblocks = m.Mp2 / GEMM_BM;
+  } else if (need_path) {
+    PdlScope plain(false);  // these two kernels do not carry the griddepcontrol protocol
     CUDA_TRY(launch_tma_upper(m, panelV, pl.C, ncols_pad, panelA, st));
     CUDA_TRY(launch_grad_contract(m, cont_mask(sp), xk, ncols, ncols_pad, panelA, dmu, dvar, S_part, pl.grad_jrows, st));
   }
   DimMap dm;
   dm.n = need_path ? sp.n_cont : 0;
   for (int i = 0; i < sp.n_cont; ++i) dm.dims[i] = sp.cont_cols[i];
-  CUDA_TRY(launch_sep_step_finish(sp, dm, m.d_k, 1, b, mc, a, z, prob, S_part, m.Mp2 / pl.grad_jrows, ncols_pad, estimator,
+  CUDA_TRY(launch_sep_step_finish(sp, dm, m.d_k, 1, b, mc, a, z, prob, S_part, jblocks, ncols_pad, estimator,
                                   ma_state, update_ma, grad_out, out_value, out_grad, need_grad ? 1 : 0, adam_theta,
                                   adam_m, adam_v, lr, step_ptr, m.done_ctr, st));
   return PRB_OK;
@@ -1164,6 +1210,7 @@ int prb_analytic_adam(prb_model* model, const prb_space_desc* space, const prb_a
     const int ncols = int(B), ncols_pad = round_up(int(B), 128), total = b * sp.d;
     double* panelA = at<double>(workspace, pl.off_panelA);
     double* panelV = at<double>(workspace, pl.off_panelV);
+    double* panelQ = at<double>(workspace, pl.off_panelQ);
     double* norm = at<double>(workspace, pl.off_norm);
     double* mu = at<double>(workspace, pl.off_mu);
     double* S_part = at<double>(workspace, pl.off_S_part);
@@ -1188,7 +1235,9 @@ int prb_analytic_adam(prb_model* model, const prb_space_desc* space, const prb_a
         CUDA_TRY(launch_analytic_build(sp, theta, b, n_options, options, xk, probs, st));
       }
       const bool need_path = with_grad && sp.n_cont > 0;
-      CUDA_TRY(launch_kstar_panel(m, xk, ncols, ncols_pad, panelA, st));
+      GradGroup gq;
+      const bool gq_ok = need_path && build_grad_group(m.spec, cont_mask(sp), &gq);
+      CUDA_TRY(launch_kstar_panel(m, xk, ncols, ncols_pad, panelA, st, gq_ok ? &gq : nullptr, panelQ));
       FusedAcq fa;
       fa.aq = aq;
       fa.a = a;
@@ -1200,14 +1249,18 @@ int prb_analytic_adam(prb_model* model, const prb_space_desc* space, const prb_a
                                 st));
       if (!fuse)
         CUDA_TRY(launch_acq_epilogue(m, aq, norm, ncols_pad, mu, ncols, a, dmu, dvar, nullptr, nullptr, nullptr, 0, st));
-      if (need_path) {
+      int jblocks = m.Mp2 / pl.grad_jrows;
+      if (need_path && gq_ok) {
+        CUDA_TRY(launch_tma_upper_gradq(m, panelV, pl.C, ncols, ncols_pad, gq, panelQ, xk, dmu, dvar, S_part, st));
+        jblocks = m.Mp2 / GEMM_BM;
+      } else if (need_path) {
         CUDA_TRY(launch_tma_upper(m, panelV, pl.C, ncols_pad, panelA, st));
         CUDA_TRY(launch_grad_contract(m, cont_mask(sp), xk, ncols, ncols_pad, panelA, dmu, dvar, S_part, pl.grad_jrows,
                                       st));
       }
       CUDA_TRY(launch_analytic_reduce(sp, X, b, n_options, options, a, probs, nullptr, with_grad ? ones : nullptr,
                                       value_out, with_grad ? grad : nullptr, st, need_path ? S_part : nullptr,
-                                      m.Mp2 / pl.grad_jrows, ncols_pad, with_grad ? theta : nullptr, adam_state,
+                                      jblocks, ncols_pad, with_grad ? theta : nullptr, adam_state,
                                       adam_state + total, lr, step, done));
       return PRB_OK;
     };

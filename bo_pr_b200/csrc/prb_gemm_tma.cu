@@ -45,6 +45,10 @@
 //   UPPER_W     stores W (generic path; the gradient contraction kernel consumes it).
 //   UPPER_GRAD  epilogue contracts W with the kernel derivative in registers:
 //               S[c, col] = sum_j (dA/dmu alpha_j - 2 dA/dvar W[j, col]) * kb(z_col, Z_j) * Dc[b(col), c, j]; W never hits HBM.
+//   UPPER_GRADQ the same fusion for kernel structures that do not separate (ordinals inside the ARD Matern, categorical
+//               kernels): T[j, col] = (dA/dmu alpha_j - 2 dA/dvar W[j, col]) * Q[col, j] with the derivative-factor panel Q
+//               written by kstar_q_kernel next to k*, then  S[dim, col] = w_dim * (x_dim[col] * sum_j T - sum_j T X[j, dim])
+//               for the dims of the gradient group.  Replaces upper(W panel) + grad_contract_kernel.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -67,7 +71,7 @@ constexpr int T_CHUNK_DOUBLES = T_BM * 4;              // one k-chunk (4 k value
 constexpr size_t tma_smem_bytes(int bn) { return size_t(T_STAGES) * (T_OPER_DOUBLES + bn * T_BK) * 8 + 2 * T_STAGES * 8 + 64 * 8; }
 constexpr size_t T_SMEM_BYTES = tma_smem_bytes(128);
 
-enum { MODE_LOWER_GEN = 0, MODE_LOWER_TMA = 1, MODE_UPPER_W = 2, MODE_UPPER_GRAD = 3 };
+enum { MODE_LOWER_GEN = 0, MODE_LOWER_TMA = 1, MODE_UPPER_W = 2, MODE_UPPER_GRAD = 3, MODE_UPPER_GRADQ = 4 };
 
 struct TmaGemmParams {
   int mtiles, ntiles, Kp, ncols_pad;
@@ -104,6 +108,12 @@ struct TmaGemmParams {
   double* acq_dmu;   // [ncols] dA/dmu
   double* acq_dvar;  // [ncols] dA/dsigma^2
   int acq_ncols;
+  // UPPER_GRADQ: gradient group, derivative-factor panel, kernel inputs of the panel's columns, training inputs
+  GradGroup gq;
+  const double* Qp;   // [panel rows = columns][Kp]
+  const double* xk;   // [ncols, d_k]
+  const double* Xtr;  // [n, d_k]
+  int n, d_k;
 };
 
 // BN = evaluation columns per tile: 128 for throughput; 32 for small problems, where a 128-wide tiling would leave most
@@ -112,7 +122,7 @@ template <int MODE, int BN, int THREADS = T_THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 2 : 1)
     trgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const TmaGemmParams p) {
-  constexpr bool UPPER = (MODE == MODE_UPPER_W || MODE == MODE_UPPER_GRAD);
+  constexpr bool UPPER = (MODE == MODE_UPPER_W || MODE == MODE_UPPER_GRAD || MODE == MODE_UPPER_GRADQ);
   constexpr bool GEN = (MODE == MODE_LOWER_GEN);
   constexpr int NWN = THREADS / 128;   // warps along N (4 along M)
   constexpr int TJ = BN / (8 * NWN);   // 8 x 8 accumulator tiles per warp along N (warp = 32 rows x 8 TJ columns)
@@ -452,6 +462,77 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 2 : 1)
     return;
   }
 
+  if constexpr (MODE == MODE_UPPER_GRADQ) {
+    // T[row, col] = (dA/dmu alpha_row - 2 dA/dvar W[row, col]) * Q[col, row], in place of the accumulators
+    double al[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) al[i] = p.alpha_pad[rows[i]];
+#pragma unroll
+    for (int j = 0; j < TJ; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = col_base + 8 * j + e;
+        const bool cv_ok = col < ncols_valid;
+        const double cm = cv_ok ? p.dmu[col] : 0.0;
+        const double cv = cv_ok ? -2.0 * p.dvar[col] : 0.0;
+        const double* qrow = p.Qp + size_t(col) * p.Kp;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const double q = (cv_ok && rows[i] < p.Kp) ? __ldg(qrow + rows[i]) : 0.0;
+          acc[i][j][e] = fma(cv, acc[i][j][e], cm * al[i]) * q;
+        }
+      }
+    double* s0buf = red + 4 * BN;  // [BN] sum_j T[j, col] of this row tile
+    for (int s = 0; s <= p.gq.n_dims; ++s) {
+      // slot 0: plain sum; slot s >= 1: weighted by the training inputs' column dims[s - 1]
+      double xr[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        xr[i] = (s == 0) ? 1.0 : (rows[i] < p.n ? __ldg(p.Xtr + size_t(rows[i]) * p.d_k + p.gq.dims[s - 1]) : 0.0);
+      double part[TJ][2];
+#pragma unroll
+      for (int j = 0; j < TJ; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          double v = 0.0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v = fma(acc[i][j][e], xr[i], v);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          part[j][e] = v;
+        }
+      if (frag_r == 0) {
+#pragma unroll
+        for (int j = 0; j < TJ; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) red[wm * BN + wn * (8 * TJ) + 8 * j + 2 * frag_k + e] = part[j][e];
+      }
+      __syncthreads();
+      if (tid < BN) {
+        const double sum = ((red[tid] + red[BN + tid]) + red[2 * BN + tid]) + red[3 * BN + tid];
+        if (s == 0) {
+          s0buf[tid] = sum;
+        } else {
+          const int dim = p.gq.dims[s - 1];
+          const int col = n0 + tid;
+          const double xd = col < ncols_valid ? p.xk[size_t(col) * p.d_k + dim] : 0.0;
+          p.S_part[(size_t(mt) * p.d_k + dim) * p.ncols_pad + col] = p.gq.w[s - 1] * fma(xd, s0buf[tid], -sum);
+        }
+      }
+      __syncthreads();
+    }
+    // kernel-input columns outside the group carry no pathwise gradient: the consumers sum every slot, so write zeros
+    if (tid < BN) {
+      for (int dim = 0; dim < p.d_k; ++dim) {
+        bool in_group = false;
+        for (int s = 0; s < p.gq.n_dims; ++s) in_group = in_group || p.gq.dims[s] == dim;
+        if (!in_group) p.S_part[(size_t(mt) * p.d_k + dim) * p.ncols_pad + n0 + tid] = 0.0;
+      }
+    }
+    return;
+  }
+
   if constexpr (!UPPER) {
   // lower: V^T[col, row]; 8 lanes (frag_r = 0..7) write 64 contiguous bytes per column
   double nrm[TJ][2];
@@ -533,6 +614,9 @@ cudaError_t tma_init() {
       reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_UPPER_W, 32>),
       reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_UPPER_GRAD, 128>),
       reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_UPPER_GRAD, 32>),
+      reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_UPPER_GRADQ, 64, 128>),
+      reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_UPPER_GRADQ, 32>),
+      reinterpret_cast<const void*>(&trgemm_tma_kernel<MODE_LOWER_TMA, 64, 128>),
   };
   for (const void* k : kernels) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(T_SMEM_BYTES));
@@ -646,7 +730,7 @@ cudaError_t launch_tma_lower(const Model& m, const double* panelK, int panel_row
                              double* norm_part, double* mu_dot, const FusedAcq* fa, cudaStream_t st) {
   ProfScope prof_(K_TRGEMM_LOWER, st);
   TmaGemmParams p;
-  const int bn = pick_bn_generic(m, ncols_pad, false);
+  const int bn = pick_bn_generic(m, ncols_pad, false) == 32 ? 32 : 64;  // 64: two 4-warp CTAs per SM (as the separable path)
   fill_common(p, m, ncols_pad, false, bn);
   p.C = VT;
   p.ldc = m.Mp1;
@@ -667,12 +751,15 @@ cudaError_t launch_tma_lower(const Model& m, const double* panelK, int panel_row
   if (e != cudaSuccess) return e;
   const CUtensorMap& mA = *reinterpret_cast<const CUtensorMap*>(&m.mapA1);
   const CUtensorMap& mB = *reinterpret_cast<const CUtensorMap*>(&mapK);
+  cudaError_t le;
   if (bn == 32)
-    trgemm_tma_kernel<MODE_LOWER_TMA, 32><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(mA, mB, p);
+    le = launch_kernel(trgemm_tma_kernel<MODE_LOWER_TMA, 32, T_THREADS>, dim3(p.mtiles * p.ntiles), dim3(T_THREADS),
+                       T_SMEM_BYTES, st, mA, mB, p);
   else
-    trgemm_tma_kernel<MODE_LOWER_TMA, 128><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(mA, mB, p);
+    le = launch_kernel(trgemm_tma_kernel<MODE_LOWER_TMA, 64, 128>, dim3(p.mtiles * p.ntiles), dim3(128),
+                       tma_smem_bytes(64), st, mA, mB, p);
   count_launch();
-  return cudaGetLastError();
+  return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 cudaError_t launch_tma_upper(const Model& m, const double* panelV, int panel_rows, int ncols_pad, double* W,
@@ -722,6 +809,39 @@ cudaError_t launch_tma_upper_grad(const Model& m, const double* panelV, int pane
   else
     e = launch_kernel(trgemm_tma_kernel<MODE_UPPER_GRAD, 128, T_THREADS>, dim3(p.mtiles * p.ntiles), dim3(T_THREADS),
                       T_SMEM_BYTES, st, mA, mB, p);
+  count_launch();
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+cudaError_t launch_tma_upper_gradq(const Model& m, const double* panelV, int panel_rows, int ncols, int ncols_pad,
+                                   const GradGroup& gq, const double* Qp, const double* xk, const double* dmu,
+                                   const double* dvar, double* S_part, cudaStream_t st) {
+  ProfScope prof_(K_TRGEMM_UPPER, st);
+  TmaGemmParams p;
+  const int bn = pick_bn_generic(m, ncols_pad, true) == 32 ? 32 : 64;  // 64: two 4-warp CTAs per SM, as UPPER_GRAD
+  fill_common(p, m, ncols_pad, true, bn);
+  p.alpha_pad = m.alpha_pad;
+  p.dmu = dmu;
+  p.dvar = dvar;
+  p.ncols = ncols;
+  p.S_part = S_part;
+  p.gq = gq;
+  p.Qp = Qp;
+  p.xk = xk;
+  p.Xtr = m.Xtr;
+  p.n = m.n;
+  p.d_k = m.d_k;
+  TensorMap mapV;  // the v panel [panel_rows, Mp1], box = 4 k values x bn columns
+  cudaError_t e = make_operand_map(&mapV, panelV, panel_rows, m.Kp, m.Mp1, bn);
+  if (e != cudaSuccess) return e;
+  const CUtensorMap& mA = *reinterpret_cast<const CUtensorMap*>(&m.mapA2);
+  const CUtensorMap& mB = *reinterpret_cast<const CUtensorMap*>(&mapV);
+  if (bn == 32)
+    e = launch_kernel(trgemm_tma_kernel<MODE_UPPER_GRADQ, 32, T_THREADS>, dim3(p.mtiles * p.ntiles), dim3(T_THREADS),
+                      T_SMEM_BYTES, st, mA, mB, p);
+  else
+    e = launch_kernel(trgemm_tma_kernel<MODE_UPPER_GRADQ, 64, 128>, dim3(p.mtiles * p.ntiles), dim3(128),
+                      tma_smem_bytes(64), st, mA, mB, p);
   count_launch();
   return e != cudaSuccess ? e : cudaGetLastError();
 }

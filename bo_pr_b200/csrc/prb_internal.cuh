@@ -32,6 +32,12 @@ struct DevSpec {
   int32_t n_terms;
   int32_t d_k;
   DevTerm t[PRB_MAX_TERMS];
+  // Distinct factor functions (kind, dims, lengthscales): "mixed_categorical" lists its factors in both of its terms
+  // (kernels.py:85-94), so the hot kernels evaluate each distinct function once.  uid[t][f] = index of factor (t, f)'s
+  // function, defined by factor (first_t[u], first_f[u]); at most PRB_MAX_UNIQUE of them, else n_unique = 0 (no sharing).
+  int8_t n_unique;
+  int8_t uid[PRB_MAX_TERMS][PRB_MAX_FACTORS];
+  int8_t first_t[4], first_f[4];
 };
 
 struct DevSpace {
@@ -150,6 +156,20 @@ struct DimMap {  // S_part slot -> kernel-input column
   int32_t dims[PRB_MAX_DIMS];
 };
 
+// Pathwise-gradient group of the generic path: the Matern factor(s) -- identical dims and lengthscales, e.g. the ARD factor
+// that appears in both terms of "mixed_categorical" -- through which the continuous PR parameters enter the kernel.
+//   d k*(col, j) / d x_dim = Q[col, j] * w[dim] * (x_dim - X[j, dim]),   Q = sum over member factors of
+//   outputscale_t * (d term / d F_f) * G_f,   G = (dF/dr)/r.
+// kstar_q_kernel writes Q next to k*; the upper product contracts it in its epilogue (MODE_UPPER_GRADQ).
+constexpr int GQ_MAX_DIMS = 16;
+struct GradGroup {
+  int32_t n_dims;
+  int32_t dims[GQ_MAX_DIMS];  // kernel-input columns that carry a gradient
+  double w[GQ_MAX_DIMS];      // 1 / lengthscale^2
+  int8_t member[PRB_MAX_TERMS][PRB_MAX_FACTORS];
+};
+bool build_grad_group(const DevSpec& spec, uint64_t diffmask, GradGroup* out);
+
 struct Model {
   int n, d_k;
   int Kp;        // round_up(n, 16): padded contraction length / leading dimension of the eval-major panels
@@ -224,6 +244,9 @@ cudaError_t launch_tma_lower(const Model& m, const double* panelK, int panel_row
                              double* norm_part, double* mu_dot, const FusedAcq* fa, cudaStream_t st);
 cudaError_t launch_tma_upper(const Model& m, const double* panelV, int panel_rows, int ncols_pad, double* W,
                              cudaStream_t st);
+cudaError_t launch_tma_upper_gradq(const Model& m, const double* panelV, int panel_rows, int ncols, int ncols_pad,
+                                   const GradGroup& gq, const double* Qp, const double* xk, const double* dmu,
+                                   const double* dvar, double* S_part, cudaStream_t st);
 cudaError_t launch_tma_upper_grad(const Model& m, const double* panelV, int panel_rows, const SepArgs& sa, int ncols,
                                   int ncols_pad, const double* dmu, const double* dvar, double* S_part,
                                   cudaStream_t st);

@@ -247,16 +247,245 @@ __global__ void __launch_bounds__(KS_ROWS) kstar_panel_kernel(const DevSpec spec
   }
 }
 
+// ---- hot-path variant: k* and, when the call needs the pathwise gradient, the derivative factor Q of the gradient group ----
+// Same grid and thread mapping as kstar_panel_kernel.  Branch-free sqrt / exp (one ulp) so that the per-column evaluations of
+// a thread interleave; the Matern value and its derivative factor share one sqrt and one exp, so Q costs a handful of
+// multiplies on top of k* -- the separate gradient-contraction kernel this replaces evaluated every Matern a second time
+// (4.1 ms against 4.4 ms of products at 65 536 x 1000).
+bool build_grad_group(const DevSpec& spec, uint64_t diffmask, GradGroup* out) {
+  memset(out, 0, sizeof(GradGroup));
+  const DevFactor* first = nullptr;
+  for (int t = 0; t < spec.n_terms; ++t) {
+    const DevTerm& T = spec.t[t];
+    for (int f = 0; f < T.n_factors; ++f) {
+      const DevFactor& F = T.f[f];
+      if (F.kind != PRB_FACTOR_MATERN52) continue;
+      bool touches = false;
+      for (int di = 0; di < F.n_dims; ++di) touches = touches || ((diffmask >> F.dims[di]) & 1u);
+      if (!touches) continue;
+      if (first == nullptr) {
+        first = &F;
+      } else {  // every member must be the same factor (dims and lengthscales): one Q panel serves them all
+        if (F.n_dims != first->n_dims) return false;
+        for (int di = 0; di < F.n_dims; ++di)
+          if (F.dims[di] != first->dims[di] || F.inv_ls[di] != first->inv_ls[di]) return false;
+      }
+      out->member[t][f] = 1;
+    }
+  }
+  if (first == nullptr || spec.n_unique == 0) return false;
+  for (int di = 0; di < first->n_dims; ++di) {
+    if (!((diffmask >> first->dims[di]) & 1u)) continue;
+    if (out->n_dims == GQ_MAX_DIMS) return false;
+    out->dims[out->n_dims] = first->dims[di];
+    out->w[out->n_dims] = first->inv_ls[di] * first->inv_ls[di];
+    ++out->n_dims;
+  }
+  return out->n_dims > 0;
+}
+
+static_assert(KS_COLS % 4 == 0, "double4 loads of the kernel-input tile");
+constexpr int KQ_NC = 4;  // columns evaluated together by a thread: FP64 latency on this part needs ILP x warps >= ~40 per
+                          // sub-partition (one chain per thread reached a third of the FP64 pipe)
+template <bool WITH_Q>
+__global__ void __launch_bounds__(KS_ROWS) kstar_q_kernel(const DevSpec spec, const GradGroup gq,
+                                                           const double* __restrict__ Xtr, int n, int Kp,
+                                                           const double* __restrict__ xk, int ncols, int ncols_store,
+                                                           double* __restrict__ KstarT, double* __restrict__ Qp,
+                                                           int ks_cols) {
+  extern __shared__ double sm[];
+  __shared__ int fdim_s[4][PRB_MAX_DIMS];     // dims / inverse lengthscales of the distinct factor functions: the inner loop
+  __shared__ double fils_s[4][PRB_MAX_DIMS];  // reads them from shared memory (indexed constant-bank loads cost an LDC each)
+  __shared__ int fnd_s[4], fkind_s[4];
+  __shared__ int tf_u[PRB_MAX_TERMS][PRB_MAX_FACTORS], tf_pw[PRB_MAX_TERMS][PRB_MAX_FACTORS],
+      tf_mem[PRB_MAX_TERMS][PRB_MAX_FACTORS], t_nf[PRB_MAX_TERMS], t_add[PRB_MAX_TERMS];
+  __shared__ double t_sc[PRB_MAX_TERMS];
+  const int d_k = spec.d_k;
+  double* Xs = sm;                  // [d_k][KS_ROWS]
+  double* xs = sm + d_k * KS_ROWS;  // [d_k][KS_COLS]  (dim-major: a thread's KQ_NC columns are contiguous)
+  double* vs = xs + d_k * KS_COLS;  // [4 functions][KQ_NC][KS_ROWS] factor values of the thread's current columns ...
+  double* gs = vs + 4 * KQ_NC * KS_ROWS;  // ... and their derivative factors (indexed by the runtime function id: shared
+                                          // memory instead of select chains over registers)
+  const int tid = threadIdx.x;
+  const int j = blockIdx.x * KS_ROWS + tid;
+  const int col0 = blockIdx.y * ks_cols;
+  const bool valid = j < n;
+  grid_dep_launch();
+  for (int idx = tid; idx < 4 * PRB_MAX_DIMS; idx += KS_ROWS) {
+    const int u = idx / PRB_MAX_DIMS, di = idx % PRB_MAX_DIMS;
+    if (u < spec.n_unique) {
+      const DevFactor& F = spec.t[spec.first_t[u]].f[spec.first_f[u]];
+      fdim_s[u][di] = di < F.n_dims ? F.dims[di] : 0;
+      fils_s[u][di] = di < F.n_dims ? F.inv_ls[di] : 0.0;
+      if (di == 0) {
+        fnd_s[u] = F.n_dims;
+        fkind_s[u] = F.kind;
+      }
+    }
+  }
+  if (tid < PRB_MAX_TERMS * PRB_MAX_FACTORS) {
+    const int t = tid / PRB_MAX_FACTORS, f = tid % PRB_MAX_FACTORS;
+    const bool live = t < spec.n_terms && f < spec.t[t].n_factors;
+    tf_u[t][f] = live ? spec.uid[t][f] : 0;
+    tf_pw[t][f] = live ? spec.t[t].f[f].power : 1;
+    tf_mem[t][f] = (WITH_Q && live) ? gq.member[t][f] : 0;
+    if (f == 0) {
+      t_nf[t] = t < spec.n_terms ? spec.t[t].n_factors : 0;
+      t_add[t] = t < spec.n_terms ? spec.t[t].additive : 0;
+      t_sc[t] = t < spec.n_terms ? spec.t[t].outputscale : 0.0;
+    }
+  }
+  for (int dd = 0; dd < d_k; ++dd) Xs[dd * KS_ROWS + tid] = valid ? Xtr[size_t(j) * d_k + dd] : 0.0;
+  grid_dep_wait();  // xk comes from the sampler kernel
+  for (int idx = tid; idx < ks_cols * d_k; idx += KS_ROWS) {
+    const int c = idx / d_k, dd = idx - c * d_k;
+    xs[dd * KS_COLS + c] = (col0 + c < ncols) ? xk[size_t(col0) * d_k + idx] : 0.0;
+  }
+  __syncthreads();
+  if (j >= Kp) return;
+  const double* Xj = Xs + tid;
+  const int n_unique = spec.n_unique;
+  for (int cb = 0; cb < ks_cols; cb += KQ_NC) {
+    if (col0 + cb >= ncols_store) break;
+    double kval[KQ_NC], qval[KQ_NC];
+#pragma unroll
+    for (int c = 0; c < KQ_NC; ++c) kval[c] = qval[c] = 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (u >= n_unique) continue;
+      const int nd = fnd_s[u];
+      double acc[KQ_NC];
+#pragma unroll
+      for (int c = 0; c < KQ_NC; ++c) acc[c] = 0.0;
+      if (fkind_s[u] == PRB_FACTOR_MATERN52) {
+        for (int di = 0; di < nd; ++di) {
+          const int dim = fdim_s[u][di];
+          const double il = fils_s[u][di];
+          const double xj = Xj[dim * KS_ROWS];
+          const double4 xv = *reinterpret_cast<const double4*>(xs + dim * KS_COLS + cb);
+          const double x4[KQ_NC] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+          for (int c = 0; c < KQ_NC; ++c) {
+            const double df = (x4[c] - xj) * il;
+            acc[c] = fma(df, df, acc[c]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < KQ_NC; ++c) {
+          double G;
+          vs[(u * KQ_NC + c) * KS_ROWS + tid] = matern52_nb(acc[c], &G);
+          if (WITH_Q) gs[(u * KQ_NC + c) * KS_ROWS + tid] = G;
+        }
+      } else {
+        for (int di = 0; di < nd; ++di) {
+          const int dim = fdim_s[u][di];
+          const double il = fils_s[u][di];
+          const double xj = Xj[dim * KS_ROWS];
+          const double4 xv = *reinterpret_cast<const double4*>(xs + dim * KS_COLS + cb);
+          const double x4[KQ_NC] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+          for (int c = 0; c < KQ_NC; ++c) acc[c] += (x4[c] != xj) ? il : 0.0;
+        }
+#pragma unroll
+        for (int c = 0; c < KQ_NC; ++c) {
+          vs[(u * KQ_NC + c) * KS_ROWS + tid] = exp_neg_nb(-acc[c]);
+          if (WITH_Q) gs[(u * KQ_NC + c) * KS_ROWS + tid] = 0.0;
+        }
+      }
+    }
+    // combine per term (runtime loops over the term's factors, the thread's columns unrolled inside): product or sum of
+    // F^p; Q adds outputscale * d(term)/dF_f * G_f for the gradient group's member factors
+    const int n_terms = spec.n_terms;
+    for (int t = 0; t < n_terms; ++t) {
+      const int nf = t_nf[t];
+      const bool additive = t_add[t] != 0;
+      const double sc = t_sc[t];
+      double acc[KQ_NC];
+#pragma unroll
+      for (int c = 0; c < KQ_NC; ++c) acc[c] = additive ? 0.0 : 1.0;
+      for (int f = 0; f < nf; ++f) {
+        const int u = tf_u[t][f], pw = tf_pw[t][f];
+#pragma unroll
+        for (int c = 0; c < KQ_NC; ++c) {
+          const double v = vs[(u * KQ_NC + c) * KS_ROWS + tid];
+          double Fp = v;
+          for (int i = 1; i < pw; ++i) Fp *= v;
+          acc[c] = additive ? acc[c] + Fp : acc[c] * Fp;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < KQ_NC; ++c) kval[c] = fma(sc, acc[c], kval[c]);
+      if (WITH_Q) {
+        for (int f = 0; f < nf; ++f) {
+          if (!tf_mem[t][f]) continue;
+          const int u = tf_u[t][f], pw = tf_pw[t][f];
+          double q[KQ_NC];
+#pragma unroll
+          for (int c = 0; c < KQ_NC; ++c) {
+            const double v = vs[(u * KQ_NC + c) * KS_ROWS + tid];
+            double dp = double(pw);
+            for (int i = 2; i < pw + 1 && pw > 1; ++i) dp *= v;  // p v^(p-1)
+            q[c] = sc * gs[(u * KQ_NC + c) * KS_ROWS + tid] * (pw > 1 ? dp : 1.0);
+          }
+          if (!additive) {
+            for (int g = 0; g < nf; ++g) {
+              if (g == f) continue;
+              const int u2 = tf_u[t][g], pw2 = tf_pw[t][g];
+#pragma unroll
+              for (int c = 0; c < KQ_NC; ++c) {
+                const double v2 = vs[(u2 * KQ_NC + c) * KS_ROWS + tid];
+                double Fp = v2;
+                for (int i = 1; i < pw2; ++i) Fp *= v2;
+                q[c] *= Fp;
+              }
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < KQ_NC; ++c) qval[c] += q[c];
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < KQ_NC; ++c) {
+      const int col = col0 + cb + c;
+      if (col < ncols_store) {
+        const bool live = valid && col < ncols;
+        KstarT[size_t(col) * Kp + j] = live ? kval[c] : 0.0;
+        if (WITH_Q) Qp[size_t(col) * Kp + j] = live ? qval[c] : 0.0;
+      }
+    }
+  }
+}
+
 cudaError_t launch_kstar_panel(const Model& m, const double* xk, int ncols, int ncols_pad, double* KstarT,
-                               cudaStream_t st) {
+                               cudaStream_t st, const GradGroup* gq, double* Qp) {
   ProfScope prof_(K_KSTAR, st);
   // few columns: 4 per CTA instead of 32, so that a small panel still spreads over the SMs
   const int ks_cols = (m.Kp + KS_ROWS - 1) / KS_ROWS * (ncols_pad / KS_COLS) < 148 ? 4 : KS_COLS;
   dim3 grid((m.Kp + KS_ROWS - 1) / KS_ROWS, ncols_pad / ks_cols);
   const size_t smem = size_t(m.d_k) * (KS_ROWS + KS_COLS) * sizeof(double);
-  kstar_panel_kernel<<<grid, KS_ROWS, smem, st>>>(m.spec, m.Xtr, m.n, m.Kp, xk, ncols, ncols_pad, KstarT, ks_cols);
+  const bool with_q = gq != nullptr && Qp != nullptr;
+  const size_t smem_q = smem + size_t(2) * 4 * KQ_NC * KS_ROWS * sizeof(double);  // + the factor value / derivative staging
+  if (m.spec.n_unique == 0) {  // more than four distinct factor functions: the general entry-by-entry kernel
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kstar_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+      if (e != cudaSuccess) return e;
+    }
+    kstar_panel_kernel<<<grid, KS_ROWS, smem, st>>>(m.spec, m.Xtr, m.n, m.Kp, xk, ncols, ncols_pad, KstarT, ks_cols);
+    count_launch();
+    return cudaGetLastError();
+  }
+  auto kern = with_q ? kstar_q_kernel<true> : kstar_q_kernel<false>;
+  if (smem_q > 40 * 1024) {  // the 48 KB default limit covers static (3.2 KB of tables) + dynamic shared memory
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_q));
+    if (e != cudaSuccess) return e;
+  }
+  GradGroup none;
+  memset(&none, 0, sizeof(none));
+  cudaError_t le = launch_kernel(kern, grid, dim3(KS_ROWS), smem_q, st, m.spec, with_q ? *gq : none, m.Xtr, m.n, m.Kp, xk,
+                                 ncols, ncols_pad, KstarT, Qp, ks_cols);
   count_launch();
-  return cudaGetLastError();
+  return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 // plain K(xk, X_train) -> out[n_points, n] (leading dimension n, nothing stored beyond n_points)
@@ -266,6 +495,10 @@ cudaError_t launch_kernel_matrix(const DevSpec& spec, const double* Xtr, int n, 
   if (n_points == 0) return cudaSuccess;
   dim3 grid((n + KS_ROWS - 1) / KS_ROWS, (n_points + KS_COLS - 1) / KS_COLS);
   const size_t smem = size_t(spec.d_k) * (KS_ROWS + KS_COLS) * sizeof(double);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kstar_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+  }
   kstar_panel_kernel<<<grid, KS_ROWS, smem, st>>>(spec, Xtr, n, n, xk, n_points, n_points, out, KS_COLS);
   count_launch();
   return cudaGetLastError();

@@ -28,7 +28,7 @@ cudaError_t launch_analytic_build(const DevSpace& sp, const double* theta, int b
                                   double* xk, double* probs, cudaStream_t st, const double* lower = nullptr,
                                   const double* upper = nullptr, double* Xc = nullptr);
 cudaError_t launch_kstar_panel(const Model& m, const double* xk, int ncols, int ncols_pad, double* KstarT,
-                               cudaStream_t st);
+                               cudaStream_t st, const GradGroup* gq = nullptr, double* Qp = nullptr);
 cudaError_t launch_kernel_matrix(const DevSpec& spec, const double* Xtr, int n, const double* xk, int n_points,
                                  double* out, cudaStream_t st);
 cudaError_t launch_rff_eval(const Model& m, const double* xk, int64_t ncols, uint64_t diffmask, bool need_grad, double* a,

@@ -296,3 +296,39 @@ def test_svm_shape_53_dims_vs_oracle():
     cf, vf = B.gen_candidates_torch(g["theta"].to(DEV), product_mc_pr(g, DEV), lo, hi, options={"maxiter": 5})
     ch, vh = B.gen_candidates_torch(g["theta"].to(DEV), product_mc_pr(g, DEV), lo, hi, options={"maxiter": 5, "fused": False})
     assert torch.allclose(cf, ch, rtol=0, atol=1e-10) and torch.allclose(vf, vh, rtol=1e-8, atol=1e-12)
+
+
+@pytest.mark.parametrize("kind,n,b,mc", [("rosenbrock", 500, 4, 64), ("rosenbrock", 1000, 3, 32), ("chemistry", 500, 3, 48),
+                                         ("chemistry", 1000, 3, 32)])
+def test_generic_path_vs_oracle_at_sweep_sizes(kind, n, b, mc):
+    """Kernel structures that do not separate (ordinals inside the ARD Matern; mixed_categorical) at several row tiles:
+    k* + derivative-factor panel -> lower product -> upper product with the gradient contraction fused into its epilogue.
+    Against the oracle, and three ways through the library: fused single-panel step, the multi-launch sequence
+    (PRB_OPT_UNFUSED), and narrow column panels (chunk_cols)."""
+    from bench_workload import make_generic_problem
+    from bo_pr_b200 import _capi as capi
+    g, theta = make_generic_problem(kind, n, b, mc, seed=3)
+    c = g["case"]
+    g["base_samples"] = sobol_base_samples(mc, n_cols=len(c["integer_indices"])) if c["integer_indices"] else None
+    g["base_samples_categorical"] = (sobol_base_samples(mc, n_cols=len(c["categorical_features"]), seed=77)
+                                     if c["categorical_features"] else None)
+    space, oacq = oracle_space(g), oracle_acq(g)
+    go = torch.linspace(0.7, 1.3, b, dtype=torch.float64)
+    ref = P.mc_pr(space, theta, oacq, g["base_samples"], g["base_samples_categorical"], grad_estimator="reinforce_ma",
+                  ma_counter=4.0, ma_hidden=0.2, apply_numeric=c["apply_numeric"], grad_output=go)
+    outs = []
+    for mode in ("fused", "unfused", "panels"):
+        pr = product_mc_pr(g, DEV)
+        st = pr.acq_function.state
+        st.set_option(capi.PRB_OPT_UNFUSED, int(mode == "unfused"))
+        st.chunk_cols = 128 if mode == "panels" else 0
+        pr._ma_state.copy_(torch.tensor([4.0, 0.2], dtype=torch.float64))
+        X = theta.to(DEV).requires_grad_(True)
+        val = pr(X)
+        grad = torch.autograd.grad(val, X, grad_outputs=go.to(DEV))[0]
+        _assert_close(val, ref.value, f"PR value [{mode}]")
+        _assert_close(grad, ref.grad, f"PR gradient [{mode}]", atol=1e-11)
+        outs.append((val.detach().clone(), grad.clone()))
+    for v, gr in outs[1:]:
+        _assert_close(v, outs[0][0], "value across paths", rtol=1e-12, atol=1e-14)
+        _assert_close(gr, outs[0][1], "gradient across paths", rtol=1e-10, atol=1e-13)

@@ -35,3 +35,24 @@ pr_ = cProfile.Profile(); pr_.enable()
 for _ in range(N): e2e_step()
 pr_.disable()
 pstats.Stats(pr_).sort_stats("cumulative").print_stats(28)
+
+# ---- split of the forward enqueue: Python before the library call / the library call itself / Python after
+cc = pr._call_ctx(dev)
+real_fn = cc["fn"]
+TT = {"c": 0.0, "n": 0}
+def timed_fn(*a):
+    t = time.perf_counter(); r = real_fn(*a); TT["c"] += time.perf_counter() - t; TT["n"] += 1; return r
+cc["fn"] = timed_fn
+T.clear()
+for _ in range(N): e2e_step()
+print("library call (prb_mc_value_grad, 5 launches):", round(TT["c"] / TT["n"] * 1e6, 1), "us of forward_enqueue", round(T["forward_enqueue"] / N * 1e6, 1), "us")
+cc["fn"] = real_fn
+X = theta_host.to(dev).requires_grad_(True)
+for name, f in (("module __call__ + Function.apply + _launch (no grad)", lambda: pr(X.detach())), ("_launch only", lambda: pr._launch(X, True)),
+                ("gp_state_from_model", lambda: __import__("bo_pr_b200").models.gp_state_from_model(pr.acq_function.model)),
+                ("acq_desc_of", lambda: __import__("bo_pr_b200").acquisition.acq_desc_of(pr.acq_function)),
+                ("torch.empty x2", lambda: (torch.empty(b, dtype=torch.float64, device=dev), torch.empty(b, 13, dtype=torch.float64, device=dev)))):
+    torch.cuda.synchronize(); t = time.perf_counter()
+    for _ in range(200): f()
+    dt = (time.perf_counter() - t) / 200; torch.cuda.synchronize()
+    print(f"{name}: {dt * 1e6:.1f} us")
