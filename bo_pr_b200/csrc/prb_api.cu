@@ -757,7 +757,7 @@ int prb_debug_small_timestamps(long long* out16) {
 }
 
 int prb_debug_fp64_peak(int mode, double* out_tflops, void* stream) {
-  if (!out_tflops || mode < 0 || mode > 2) return PRB_ERR_INVALID;
+  if (!out_tflops || mode < 0 || mode > 5) return PRB_ERR_INVALID;
   int dev = -1, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return PRB_ERR_NO_DEVICE;
   if (int rc_dev = check_device(dev)) return rc_dev;

@@ -36,6 +36,14 @@
 // as did unrolling the k-tile loop by 2 or 4 (4.49 / 4.48 ms).
 // The kernel as it stands is a fragile local optimum of ptxas' register allocation; the next step needs the main loop
 // pinned down (hand-scheduled or CUTLASS-style explicit pipelining) before restructuring around it.
+// Round 2 (tools/microbench/fp64_lds_mix.py, profiles/r02_fp64_lds_mix.txt): the SASS of the full k-tile body is already at
+// the pipe's pace -- every DMMA carries a 15-cycle stall + NOP, i.e. one m8n8k4 per 16 cycles per warp, and a register-fed
+// DMMA stream with this loop's 12 LDS.64 per 32 DMMAs measures 37.06 TFLOP/s against 37.07 from registers (24 LDS.64: 36.0),
+// so shared-memory loads do not compete with the tensor pipe.  DFMA does (DMMA + DFMA interleaved: 36.1 TFLOP/s together),
+// which is why the operand generator's 8 DMULs per thread and k-tile show up as `math` stalls.  What is left is per-CTA: a
+// 32-column / 4-warp / 3-stage variant with THREE independent CTAs per SM (160-168 registers, template parameters NST / NAH /
+// MINB) is SLOWER (4.71 vs 4.38 ms per step at 65 536 columns; 0.72 vs 0.60 ms at 8 192) -- twice the CTAs means twice the
+// prologues, epilogues and A-tile fetches, and that costs more than a third warp per sub-partition recovers.
 //
 // Four modes (template):
 //   LOWER_GEN   the B operand k*[col, k] = kc[b(col), k] * tab[popc(z[col] ^ Z[k])] is GENERATED into shared memory by the
@@ -68,7 +76,9 @@ constexpr int T_BM = 128, T_BN = 128, T_BK = 16, T_STAGES = PRB_T_STAGES, T_AHEA
 static_assert(T_AHEAD >= 1 && T_AHEAD <= T_STAGES - 1, "the producer may run at most T_STAGES - 1 k-tiles ahead");
 constexpr int T_OPER_DOUBLES = T_BM * T_BK;            // 2048 doubles = 16 KB per operand per stage
 constexpr int T_CHUNK_DOUBLES = T_BM * 4;              // one k-chunk (4 k values) of 128 rows
-constexpr size_t tma_smem_bytes(int bn) { return size_t(T_STAGES) * (T_OPER_DOUBLES + bn * T_BK) * 8 + 2 * T_STAGES * 8 + 64 * 8; }
+constexpr size_t tma_smem_bytes(int bn, int stages = T_STAGES) {
+  return size_t(stages) * (T_OPER_DOUBLES + bn * T_BK) * 8 + 2 * stages * 8 + 64 * 8;
+}
 constexpr size_t T_SMEM_BYTES = tma_smem_bytes(128);
 
 enum { MODE_LOWER_GEN = 0, MODE_LOWER_TMA = 1, MODE_UPPER_W = 2, MODE_UPPER_GRAD = 3, MODE_UPPER_GRADQ = 4 };
@@ -118,8 +128,8 @@ struct TmaGemmParams {
 
 // BN = evaluation columns per tile: 128 for throughput; 32 for small problems, where a 128-wide tiling would leave most
 // of the 148 SMs idle and the step is bound by ONE SM's DMMA rate (n = 119, 640 columns: 5 tiles, 23 us per product).
-template <int MODE, int BN, int THREADS = T_THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 128 ? 2 : 1)
+template <int MODE, int BN, int THREADS = T_THREADS, int NST = T_STAGES, int NAH = T_AHEAD, int MINB = (THREADS == 128 ? 2 : 1)>
+__global__ void __launch_bounds__(THREADS, MINB)
     trgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const TmaGemmParams p) {
   constexpr bool UPPER = (MODE == MODE_UPPER_W || MODE == MODE_UPPER_GRAD || MODE == MODE_UPPER_GRADQ);
@@ -127,15 +137,15 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 2 : 1)
   constexpr int NWN = THREADS / 128;   // warps along N (4 along M)
   constexpr int TJ = BN / (8 * NWN);   // 8 x 8 accumulator tiles per warp along N (warp = 32 rows x 8 TJ columns)
   constexpr int GEN_VPT = BN * T_BK / THREADS;  // generated operand values per thread and k-tile (8 or 2)
-  static_assert(GEN_VPT == 8 || GEN_VPT == 2, "operand generator mappings");
+  static_assert(GEN_VPT == 8 || GEN_VPT == 4 || GEN_VPT == 2, "operand generator mappings");
   constexpr int B_CHUNK = BN * 4;      // doubles per k-chunk of the B operand
   constexpr int B_OPER = BN * T_BK;    // doubles per k-tile of the B operand
   constexpr int STAGE_DOUBLES = T_OPER_DOUBLES + B_OPER;  // A tile + B tile of one k-tile
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* stages = reinterpret_cast<double*>(smem_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + size_t(T_STAGES) * STAGE_DOUBLES * 8);
-  uint64_t* empty = full + T_STAGES;
-  double* tab_s = reinterpret_cast<double*>(empty + T_STAGES);  // [64]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + size_t(NST) * STAGE_DOUBLES * 8);
+  uint64_t* empty = full + NST;
+  double* tab_s = reinterpret_cast<double*>(empty + NST);  // [64]
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -180,7 +190,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 2 : 1)
   if (tid == 0) {
     tma_prefetch_desc(&tmA);
     if (!GEN) tma_prefetch_desc(&tmB);
-    for (int s = 0; s < T_STAGES; ++s) {
+    for (int s = 0; s < NST; ++s) {
       mbar_init(&full[s], GEN ? 1 + THREADS : 1);
       mbar_init(&empty[s], THREADS / 32);
     }
@@ -208,8 +218,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 2 : 1)
   // TMA side of a k-tile (one elected thread): A always, B unless it is generated
   auto produce_tma = [&](int kt) {
     if (tid != 0) return;
-    const int s = kt % T_STAGES;
-    const int use = kt / T_STAGES;
+    const int s = kt % NST;
+    const int use = kt / NST;
     const int k0 = kbeg + kt * T_BK;
     double* As = stages + s * STAGE_DOUBLES;
     double* Bs = As + T_OPER_DOUBLES;
@@ -237,14 +247,19 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 2 : 1)
       g_k67 = __ldg(kc2 + 3);
       g_za = __ldg(zz);
       g_zc = __ldg(zz + 1);
+    } else if constexpr (GEN_VPT == 4) {
+      const double2* kc2 = reinterpret_cast<const double2*>(g_kc + k0 + ghalf * 4);
+      g_k01 = __ldg(kc2);
+      g_k23 = __ldg(kc2 + 1);
+      g_za = __ldg(reinterpret_cast<const uint4*>(p.Zbits + k0 + ghalf * 4));
     } else {
       g_k01 = __ldg(reinterpret_cast<const double2*>(g_kc + k0 + ghalf * 2));
       g_zs = __ldg(reinterpret_cast<const uint2*>(p.Zbits + k0 + ghalf * 2));
     }
   };
   auto gen_store = [&](int kt) {
-    const int s = kt % T_STAGES;
-    const int use = kt / T_STAGES;
+    const int s = kt % NST;
+    const int use = kt / NST;
     double* Bs = stages + s * STAGE_DOUBLES + T_OPER_DOUBLES;
     if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
     if constexpr (GEN_VPT == 8) {
@@ -263,6 +278,15 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 2 : 1)
       d0[1] = o1;
       d1[0] = o2;
       d1[1] = o3;
+    } else if constexpr (GEN_VPT == 4) {  // thread <-> (column, one k-chunk of the k-tile)
+      double2 o0, o1;
+      o0.x = g_k01.x * tab_s[__popc(g_zb ^ g_za.x)];
+      o0.y = g_k01.y * tab_s[__popc(g_zb ^ g_za.y)];
+      o1.x = g_k23.x * tab_s[__popc(g_zb ^ g_za.z)];
+      o1.y = g_k23.y * tab_s[__popc(g_zb ^ g_za.w)];
+      double2* d0 = reinterpret_cast<double2*>(Bs + ghalf * B_CHUNK + gcol * 4);
+      d0[0] = o0;
+      d0[1] = o1;
     } else {
       double2 o;
       o.x = g_k01.x * tab_s[__popc(g_zb ^ g_zs.x)];
@@ -278,7 +302,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 2 : 1)
 #pragma unroll
     for (int j = 0; j < TJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  for (int kt = 0; kt < T_AHEAD && kt < num_k; ++kt) {
+  for (int kt = 0; kt < NAH && kt < num_k; ++kt) {
     produce_tma(kt);
     if (GEN) {
       gen_load(kt);
@@ -301,13 +325,13 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 2 : 1)
   const int fb_off = (wn * (8 * TJ) + frag_r) * 4 + frag_k;
 
   for (int kt = 0; kt < num_k; ++kt) {
-    const int nk = kt + T_AHEAD;
+    const int nk = kt + NAH;
     if (nk < num_k) {
       produce_tma(nk);
       if (GEN) gen_load(nk);
     }
-    const int s = kt % T_STAGES;
-    mbar_wait(&full[s], (kt / T_STAGES) & 1);
+    const int s = kt % NST;
+    mbar_wait(&full[s], (kt / NST) & 1);
     const double* pa = stages + s * STAGE_DOUBLES;
     const double* pb = pa + T_OPER_DOUBLES + fb_off;
     const int q0 = kbeg + kt * T_BK - m0;  // offset of this k-tile inside the tile's diagonal block

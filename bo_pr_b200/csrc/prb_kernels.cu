@@ -1691,6 +1691,63 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* __restrict__ out
   out[size_t(blockIdx.x) * blockDim.x + threadIdx.x] = s;
 }
 
+// modes 3 / 4 / 5: the DMMA stream of the triangular products' inner loop -- 32 independent m8n8k4 per 4-deep k-chunk per
+// warp -- with its operands fetched from shared memory the way the product kernel does: mode 3 = 12 LDS.64 per chunk (4 A + 8 B
+// fragments), mode 4 = the same bytes as 6 LDS.128 (two chunks' fragments per load), mode 5 = 24 LDS.64 (a 32 x 32 warp tile's
+// ratio).  Tells whether shared-memory loads take issue bandwidth away from the FP64 tensor pipe.
+template <int LDS_MODE>
+__global__ void __launch_bounds__(256) fp64_lds_mix_kernel(double* __restrict__ out, int iters) {
+  __shared__ __align__(16) double buf[2][12][64];
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 2 * 12 * 64; i += 256) (&buf[0][0][0])[i] = 1.0 + 1e-9 * i;
+  __syncthreads();
+  double c[4][8][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+  for (int it = 0; it < iters; ++it) {
+    const int pb = it & 1;
+    double a[4], b[8];
+    if (LDS_MODE == 4) {
+      if ((it & 1) == 0) {  // one LDS.128 brings the fragments of two chunks
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const double2 v = *reinterpret_cast<const double2*>(&buf[pb][q][2 * lane]);
+          if (q < 2) { a[2 * q] = v.x; a[2 * q + 1] = v.y; } else { b[2 * (q - 2)] = v.x; b[2 * (q - 2) + 1] = v.y; }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const double2 v = *reinterpret_cast<const double2*>(&buf[pb][6 + q][2 * lane]);
+          if (q < 2) { a[2 * q] = v.x; a[2 * q + 1] = v.y; } else { b[2 * (q - 2)] = v.x; b[2 * (q - 2) + 1] = v.y; }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a[q] = buf[pb][q][lane];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) b[q] = buf[pb][4 + q][lane + (LDS_MODE == 5 ? 32 : 0)];
+      if (LDS_MODE == 5) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[q] += buf[pb ^ 1][q][lane];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) b[q] += buf[pb ^ 1][4 + q][lane];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dmma884(c[i][j][0], c[i][j][1], a[i], b[j]);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += c[i][j][0] + c[i][j][1];
+  out[size_t(blockIdx.x) * blockDim.x + threadIdx.x] = s;
+}
+
 cudaError_t run_fp64_peak(int mode, int iters, double* scratch /* [>= 2 * sms * 256] */, int sms, double* tflops,
                           cudaStream_t st) {
   cudaEvent_t e0, e1;
@@ -1706,7 +1763,10 @@ cudaError_t run_fp64_peak(int mode, int iters, double* scratch /* [>= 2 * sms * 
     cudaEventRecord(e0, st);
     if (mode == 0) fp64_peak_kernel<0><<<blocks, threads, 0, st>>>(scratch, iters, 0.5);
     else if (mode == 1) fp64_peak_kernel<1><<<blocks, threads, 0, st>>>(scratch, iters, 0.5);
-    else fp64_peak_kernel<2><<<blocks, threads, 0, st>>>(scratch, iters, 0.5);
+    else if (mode == 2) fp64_peak_kernel<2><<<blocks, threads, 0, st>>>(scratch, iters, 0.5);
+    else if (mode == 3) fp64_lds_mix_kernel<3><<<blocks, threads, 0, st>>>(scratch, iters / 4);
+    else if (mode == 4) fp64_lds_mix_kernel<4><<<blocks, threads, 0, st>>>(scratch, iters / 4);
+    else fp64_lds_mix_kernel<5><<<blocks, threads, 0, st>>>(scratch, iters / 4);
     count_launch();
     cudaEventRecord(e1, st);
     e = cudaEventSynchronize(e1);
@@ -1722,7 +1782,8 @@ cudaError_t run_fp64_peak(int mode, int iters, double* scratch /* [>= 2 * sms * 
   double flop;
   if (mode == 0) flop = warps * iters * per_warp_iter_mma;
   else if (mode == 1) flop = warps * iters * per_warp_iter_fma;
-  else flop = 0.5 * warps * iters * (per_warp_iter_mma + per_warp_iter_fma);
+  else if (mode == 2) flop = 0.5 * warps * iters * (per_warp_iter_mma + per_warp_iter_fma);
+  else flop = warps * double(iters / 4) * 32.0 * 512.0;
   *tflops = flop / (double(best) * 1e-3) * 1e-12;
   return cudaGetLastError();
 }
