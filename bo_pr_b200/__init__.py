@@ -6,6 +6,7 @@ mixed-kernel factory and the multi-start optimisation drivers.  All arithmetic o
 """
 from .acquisition import (  # noqa: F401
     AcquisitionFunction,
+    ConstrainedExpectedImprovement,
     ExpectedImprovement,
     PosteriorMean,
     UpperConfidenceBound,
@@ -26,7 +27,7 @@ from .kernels import (  # noqa: F401
     ScaleKernel,
     get_kernel,
 )
-from .models import FixedNoiseGP, GPState  # noqa: F401
+from .models import FixedNoiseGP, GPState, ModelListGP  # noqa: F401
 from .probabilistic_reparameterization import (  # noqa: F401
     AnalyticProbabilisticReparameterization,
     MCProbabilisticReparameterization,

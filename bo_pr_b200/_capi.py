@@ -15,6 +15,8 @@ PRB_MAX_FACTORS = 4
 PRB_MAX_TERMS = 2
 PRB_MAX_CAT = 8
 PRB_MAX_CARD = 32
+PRB_MAX_MODELS = 8
+PRB_MACQ_CEI = 0
 
 PRB_FACTOR_MATERN52 = 0
 PRB_FACTOR_CATEGORICAL = 1
@@ -32,7 +34,7 @@ EXPORTS = [
     "prb_version", "prb_abi_sizeof", "prb_debug_small_timestamps", "prb_debug_fp64_peak", "prb_launch_count", "prb_profile_enable", "prb_profile_read", "prb_status_string", "prb_last_cuda_error", "prb_model_create", "prb_rff_model_create", "prb_model_destroy", "prb_model_set_option",
     "prb_model_n", "prb_model_dk", "prb_workspace_bytes", "prb_philox_uniform", "prb_pr_sample",
     "prb_analytic_enumerate", "prb_kernel_matrix", "prb_acq_points", "prb_sample_candidates", "prb_finalize_candidates",
-    "prb_trust_region_bounds",
+    "prb_trust_region_bounds", "prb_workspace_bytes_multi", "prb_mc_value_grad_multi", "prb_acq_points_multi",
     "prb_mc_value_grad", "prb_mc_screen", "prb_analytic_value_grad", "prb_mc_adam", "prb_analytic_adam",
 ]
 
@@ -64,6 +66,13 @@ class PrbSpaceDesc(C.Structure):
 class PrbAcqDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("ei_variant", C.c_int32), ("param", C.c_double), ("min_variance", C.c_double),
                 ("acq_var_floor", C.c_double)]
+
+
+class PrbMultiAcqDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_models", C.c_int32), ("objective_index", C.c_int32), ("reserved", C.c_int32),
+                ("best_f", C.c_double), ("min_variance", C.c_double), ("sigma_floor", C.c_double),
+                ("has_lower", C.c_int32 * PRB_MAX_MODELS), ("has_upper", C.c_int32 * PRB_MAX_MODELS),
+                ("lower", C.c_double * PRB_MAX_MODELS), ("upper", C.c_double * PRB_MAX_MODELS)]
 
 
 class PrbError(RuntimeError):
@@ -109,6 +118,11 @@ def load_library() -> C.CDLL:
     lib.prb_finalize_candidates.argtypes = [vp, C.POINTER(PrbSpaceDesc), C.POINTER(PrbAcqDesc), vp, i32, vp, u64, u64, vp,
                                             vp, vp, vp, vp, sz, vp]
     lib.prb_trust_region_bounds.argtypes = [vp, vp, i32, i32, i32, dbl, vp, vp, vp, vp, vp, vp]
+    lib.prb_workspace_bytes_multi.restype = sz
+    lib.prb_workspace_bytes_multi.argtypes = [C.POINTER(vp), i32, i64, i32, i32]
+    lib.prb_mc_value_grad_multi.argtypes = [C.POINTER(vp), i32, C.POINTER(PrbSpaceDesc), C.POINTER(PrbMultiAcqDesc), vp, i32,
+                                            i32, vp, vp, u64, u64, i32, vp, i32, vp, vp, vp, vp, vp, sz, vp]
+    lib.prb_acq_points_multi.argtypes = [C.POINTER(vp), i32, C.POINTER(PrbMultiAcqDesc), vp, i64, vp, vp, vp, vp, sz, vp]
     lib.prb_analytic_enumerate.argtypes = [C.POINTER(PrbSpaceDesc), vp, i32, vp, i32, vp, vp, vp]
     lib.prb_kernel_matrix.argtypes = [C.POINTER(PrbModelDesc), vp, i64, vp, vp]
     lib.prb_acq_points.argtypes = [vp, C.POINTER(PrbAcqDesc), vp, i64, vp, vp, vp, vp, vp, sz, i32, vp]

@@ -13,7 +13,7 @@ import torch
 from torch import Tensor
 
 from . import _capi as capi
-from .models import MIN_VARIANCE, GPState, gp_state_from_model
+from .models import MIN_VARIANCE, GPState, gp_state_from_model, multi_state_from_model
 
 
 class AcquisitionFunction(torch.nn.Module):
@@ -121,6 +121,65 @@ class PosteriorMean(AnalyticAcquisitionFunction):
                                acq_var_floor=0.0)
 
 
+class ConstrainedExpectedImprovement(AcquisitionFunction):
+    """``botorch.acquisition.analytic.ConstrainedExpectedImprovement`` on a model list, as ``get_EI`` builds it for the
+    constrained problems (``experiment_utils.py:354-392``): ``constraints = {output index: (lower or None, upper or None)}``.
+    Evaluated by ``prb_acq_points_multi`` (values; the reference only differentiates it THROUGH a PR wrapper, which has its
+    own entry point ``prb_mc_value_grad_multi``)."""
+
+    def __init__(self, model, best_f, objective_index: int, constraints, maximize: bool = True, sigma_floor: float = 1e-9):
+        super().__init__(model=model)
+        if not maximize:
+            raise NotImplementedError("maximize=False is not used by the reference")
+        if not hasattr(model, "models"):
+            raise NotImplementedError("ConstrainedExpectedImprovement needs a ModelListGP (one GP per outcome)")
+        self.maximize = maximize
+        self.objective_index = int(objective_index)
+        self.constraints = {int(k): (None if v[0] is None else float(v[0]), None if v[1] is None else float(v[1]))
+                            for k, v in dict(constraints).items()}
+        if self.objective_index in self.constraints or any(k < 0 or k >= len(model.models) for k in self.constraints):
+            raise ValueError("constraint indices must name non-objective outputs of the model list")
+        self.register_buffer("best_f", torch.as_tensor(best_f, dtype=torch.float64).detach().clone())
+        self.sigma_floor = float(sigma_floor)
+
+    @property
+    def state(self):
+        return multi_state_from_model(self.model)
+
+    def multi_desc(self) -> capi.PrbMultiAcqDesc:
+        ver = (self.best_f.data_ptr(), self.best_f._version)
+        if getattr(self, "_desc_ver", None) != ver:
+            d = capi.PrbMultiAcqDesc(kind=capi.PRB_MACQ_CEI, n_models=len(self.model.models),
+                                     objective_index=self.objective_index, best_f=float(self.best_f),
+                                     min_variance=MIN_VARIANCE, sigma_floor=self.sigma_floor)
+            for k, (lo, hi) in self.constraints.items():
+                d.has_lower[k], d.has_upper[k] = int(lo is not None), int(hi is not None)
+                d.lower[k], d.upper[k] = (0.0 if lo is None else lo), (0.0 if hi is None else hi)
+            self._desc, self._desc_ver = d, ver
+        return self._desc
+
+    def forward(self, X: Tensor) -> Tensor:
+        if X.shape[-2] != 1:
+            raise AssertionError(f"Expected X to be `batch_shape x q=1 x d`, but got X with shape {tuple(X.shape)}.")
+        if X.requires_grad:
+            raise NotImplementedError("differentiate ConstrainedExpectedImprovement through a PR wrapper")
+        import ctypes as C
+        ms = self.state
+        capi.require_cuda(X, "X")
+        xk = X.detach().to(torch.float64).reshape(-1, X.shape[-1]).contiguous()
+        if xk.shape[-1] != ms.d_k:
+            raise ValueError(f"expected inputs with {ms.d_k} columns, got {xk.shape[-1]}")
+        n = xk.shape[0]
+        out = torch.empty(n, dtype=torch.float64, device=X.device)
+        ws = ms.workspace(n, ms.d_k, 1)
+        desc = self.multi_desc()
+        with torch.cuda.device(X.device):
+            st = torch.cuda.current_stream().cuda_stream
+            capi.check(ms.lib.prb_acq_points_multi(ms.handles, len(ms), C.byref(desc), xk.data_ptr(), n, out.data_ptr(), None,
+                                                   None, ws.data_ptr(), ws.numel(), st), "prb_acq_points_multi")
+        return out.reshape(X.shape[:-2])
+
+
 def acq_desc_of(acq_function) -> capi.PrbAcqDesc:
     """Descriptor for one of the classes above or a duck-typed BoTorch analytic AF (class name + ``best_f``/``beta``)."""
     if isinstance(acq_function, AnalyticAcquisitionFunction):
@@ -144,4 +203,4 @@ def acq_desc_of(acq_function) -> capi.PrbAcqDesc:
 
 def is_nonnegative(acq_function) -> bool:
     """``botorch.optim.initializers.is_nonnegative`` for the AFs above (used at ``run_one_replication.py:407-408``)."""
-    return type(acq_function).__name__ in ("ExpectedImprovement",)
+    return type(acq_function).__name__ in ("ExpectedImprovement", "ConstrainedExpectedImprovement")

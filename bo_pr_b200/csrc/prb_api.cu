@@ -746,6 +746,7 @@ int prb_abi_sizeof(int which) {
     case 2: return int(sizeof(prb_model_desc));
     case 3: return int(sizeof(prb_space_desc));
     case 4: return int(sizeof(prb_acq_desc));
+    case 5: return int(sizeof(prb_multi_acq_desc));
     default: return PRB_ERR_INVALID;
   }
 }
@@ -1120,6 +1121,167 @@ int prb_mc_value_grad(prb_model* model, const prb_space_desc* space, const prb_a
   if (workspace_bytes < pl.total) return PRB_ERR_WORKSPACE;
   return mc_core(model, sp, aq, pl, workspace, theta, b, mc, u_int, u_cat, seed, offset, estimator, ma_state,
                  update_ma, grad_out, out_value, out_grad, out_acq_values, static_cast<cudaStream_t>(stream));
+}
+
+// ---- model lists ------------------------------------------------------------------------------------------------------
+namespace {
+struct MultiCtx {
+  int nm;
+  const Model* M[PRB_MAX_MODELS];
+  Plan pl[PRB_MAX_MODELS];
+  size_t base[PRB_MAX_MODELS];
+  size_t total;
+};
+
+int multi_setup(prb_model* const* models, int n_models, int64_t n_points, int n_restarts, int d_theta, MultiCtx* c) {
+  if (!models || n_models < 1 || n_models > PRB_MAX_MODELS) return PRB_ERR_INVALID;
+  c->nm = n_models;
+  size_t off = 0;
+  for (int m = 0; m < n_models; ++m) {
+    if (!models[m]) return PRB_ERR_INVALID;
+    c->M[m] = reinterpret_cast<const Model*>(models[m]);
+    if (c->M[m]->rff_m > 0) return PRB_ERR_INVALID;
+    if (c->M[m]->d_k != c->M[0]->d_k || c->M[m]->n != c->M[0]->n) return PRB_ERR_INVALID;
+    c->pl[m] = make_plan(*c->M[m], n_points, n_restarts > 0 ? n_restarts : 1, d_theta, 0);
+    c->base[m] = off;
+    off += (c->pl[m].total + 255) / 256 * 256;
+  }
+  c->total = off;
+  return PRB_OK;
+}
+
+int fill_multi_args(const MultiCtx& c, const prb_multi_acq_desc* acq, void* ws, bool need_grad, MultiAcqArgs* ma) {
+  if (!acq || acq->kind != PRB_MACQ_CEI || acq->n_models != c.nm || acq->objective_index < 0 ||
+      acq->objective_index >= c.nm)
+    return PRB_ERR_INVALID;
+  memset(ma, 0, sizeof(MultiAcqArgs));
+  ma->n_models = c.nm;
+  ma->objective_index = acq->objective_index;
+  ma->best_f = acq->best_f;
+  ma->min_variance = acq->min_variance;
+  ma->sigma_floor = acq->sigma_floor;
+  for (int m = 0; m < c.nm; ++m) {
+    char* w = static_cast<char*>(ws) + c.base[m];
+    ma->has_lower[m] = acq->has_lower[m];
+    ma->has_upper[m] = acq->has_upper[m];
+    ma->lower[m] = acq->lower[m];
+    ma->upper[m] = acq->upper[m];
+    ma->mean_const[m] = c.M[m]->mean_const;
+    ma->kss[m] = c.M[m]->kss;
+    ma->norm_part[m] = at<double>(w, c.pl[m].off_norm);
+    ma->mu_dot[m] = at<double>(w, c.pl[m].off_mu);
+    ma->dmu[m] = need_grad ? at<double>(w, c.pl[m].off_dmu) : nullptr;
+    ma->dvar[m] = need_grad ? at<double>(w, c.pl[m].off_dvar) : nullptr;
+    ma->mtiles[m] = c.M[m]->Mp1 / GEMM_BM;
+  }
+  return PRB_OK;
+}
+}  // namespace
+
+size_t prb_workspace_bytes_multi(prb_model* const* models, int32_t n_models, int64_t n_points, int32_t n_restarts,
+                                 int32_t d_theta) {
+  MultiCtx c;
+  if (n_points < 0 || d_theta < 1 || multi_setup(models, n_models, n_points, n_restarts, d_theta, &c) != PRB_OK) return 0;
+  return c.total;
+}
+
+int prb_mc_value_grad_multi(prb_model* const* models, int32_t n_models, const prb_space_desc* space,
+                            const prb_multi_acq_desc* acq, const double* theta, int32_t b, int32_t mc,
+                            const double* u_int, const double* u_cat, uint64_t seed, uint64_t offset, int32_t estimator,
+                            double* ma_state, int32_t update_ma, const double* grad_out, double* out_value,
+                            double* out_grad, double* out_acq_values, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  if (!theta || !out_value || b < 0 || mc < 1 || !workspace) return PRB_ERR_INVALID;
+  if (grad_out && !out_grad) return PRB_ERR_INVALID;
+  if (estimator != PRB_EST_REINFORCE && estimator != PRB_EST_REINFORCE_MA) return PRB_ERR_INVALID;
+  if ((estimator == PRB_EST_REINFORCE_MA || update_ma) && !ma_state) return PRB_ERR_INVALID;
+  DevSpace sp;
+  int rc = make_space(space, &sp);
+  if (rc != PRB_OK) return rc;
+  if (b == 0) return PRB_OK;
+  MultiCtx c;
+  const int64_t B = int64_t(b) * mc;
+  if ((rc = multi_setup(models, n_models, B, b, sp.d, &c)) != PRB_OK) return rc;
+  if (sp.d_k != c.M[0]->d_k) return PRB_ERR_INVALID;
+  if (workspace_bytes < c.total) return PRB_ERR_WORKSPACE;
+  for (int m = 0; m < c.nm; ++m)
+    if (B > c.pl[m].C) return PRB_ERR_UNSUPPORTED;
+  const bool need_grad = grad_out != nullptr;
+  const bool need_path = need_grad && sp.n_cont > 0;
+  MultiAcqArgs ma;
+  if ((rc = fill_multi_args(c, acq, workspace, need_path, &ma)) != PRB_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* w0 = static_cast<char*>(workspace) + c.base[0];
+  const Plan& p0 = c.pl[0];
+  double* xk = at<double>(w0, p0.off_xk);
+  uint8_t* z = at<uint8_t>(w0, p0.off_z);
+  double* prob = at<double>(w0, p0.off_prob);
+  double* a = out_acq_values ? out_acq_values : at<double>(w0, p0.off_a);
+  const int ncols = int(B), ncols_pad = round_up(ncols, 128);
+  CUDA_TRY(launch_pr_sample(sp, theta, b, mc, u_int, u_cat, seed, offset, xk, nullptr, need_grad ? z : nullptr,
+                            need_grad ? prob : nullptr, nullptr, nullptr, st));
+  GradGroup gq[PRB_MAX_MODELS];
+  for (int m = 0; m < c.nm; ++m) {
+    const Model& M = *c.M[m];
+    char* w = static_cast<char*>(workspace) + c.base[m];
+    const Plan& pl = c.pl[m];
+    const bool gq_ok = need_path && build_grad_group(M.spec, cont_mask(sp), &gq[m]);
+    if (need_path && !gq_ok) return PRB_ERR_UNSUPPORTED;
+    CUDA_TRY(launch_kstar_panel(M, xk, ncols, ncols_pad, at<double>(w, pl.off_panelA), st, gq_ok ? &gq[m] : nullptr,
+                                at<double>(w, pl.off_panelQ)));
+    CUDA_TRY(launch_tma_lower(M, at<double>(w, pl.off_panelA), pl.C, ncols_pad,
+                              need_path ? at<double>(w, pl.off_panelV) : nullptr, at<double>(w, pl.off_norm),
+                              at<double>(w, pl.off_mu), nullptr, st));
+  }
+  CUDA_TRY(launch_multi_acq_epilogue(ma, ncols_pad, ncols, a, nullptr, nullptr, st));
+  double* S0 = at<double>(w0, p0.off_S_part);
+  if (need_path) {
+    for (int m = 0; m < c.nm; ++m) {
+      const Model& M = *c.M[m];
+      char* w = static_cast<char*>(workspace) + c.base[m];
+      const Plan& pl = c.pl[m];
+      double* Sm = at<double>(w, pl.off_S_part);
+      CUDA_TRY(launch_tma_upper_gradq(M, at<double>(w, pl.off_panelV), pl.C, ncols, ncols_pad, gq[m],
+                                      at<double>(w, pl.off_panelQ), xk, ma.dmu[m], ma.dvar[m], Sm, st));
+      if (m > 0) CUDA_TRY(launch_add_inplace(S0, Sm, size_t(M.Mp2 / GEMM_BM) * M.d_k * ncols_pad, st));
+    }
+  }
+  DimMap dm;
+  dm.n = need_path ? sp.n_cont : 0;
+  for (int i = 0; i < sp.n_cont; ++i) dm.dims[i] = sp.cont_cols[i];
+  const Model& M0 = *c.M[0];
+  CUDA_TRY(launch_sep_step_finish(sp, dm, M0.d_k, 1, b, mc, a, z, prob, S0, M0.Mp2 / GEMM_BM, ncols_pad, estimator, ma_state,
+                                  (update_ma && ma_state) ? 1 : 0, grad_out, out_value, out_grad, need_grad ? 1 : 0, nullptr,
+                                  nullptr, nullptr, 0.0, nullptr, M0.done_ctr, st));
+  return PRB_OK;
+}
+
+int prb_acq_points_multi(prb_model* const* models, int32_t n_models, const prb_multi_acq_desc* acq, const double* xk,
+                         int64_t n_points, double* out_acq, double* out_mean, double* out_var, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  if (!xk || !out_acq || n_points < 0 || !workspace) return PRB_ERR_INVALID;
+  if (n_points == 0) return PRB_OK;
+  MultiCtx c;
+  if (!models || n_models < 1 || !models[0]) return PRB_ERR_INVALID;
+  int rc = multi_setup(models, n_models, n_points, 1, reinterpret_cast<const Model*>(models[0])->d_k, &c);
+  if (rc != PRB_OK) return rc;
+  if (workspace_bytes < c.total) return PRB_ERR_WORKSPACE;
+  for (int m = 0; m < c.nm; ++m)
+    if (n_points > c.pl[m].C) return PRB_ERR_UNSUPPORTED;
+  MultiAcqArgs ma;
+  if ((rc = fill_multi_args(c, acq, workspace, false, &ma)) != PRB_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int ncols = int(n_points), ncols_pad = round_up(ncols, 128);
+  for (int m = 0; m < c.nm; ++m) {
+    const Model& M = *c.M[m];
+    char* w = static_cast<char*>(workspace) + c.base[m];
+    const Plan& pl = c.pl[m];
+    CUDA_TRY(launch_kstar_panel(M, xk, ncols, ncols_pad, at<double>(w, pl.off_panelA), st));
+    CUDA_TRY(launch_tma_lower(M, at<double>(w, pl.off_panelA), pl.C, ncols_pad, nullptr, at<double>(w, pl.off_norm),
+                              at<double>(w, pl.off_mu), nullptr, st));
+  }
+  CUDA_TRY(launch_multi_acq_epilogue(ma, ncols_pad, ncols, out_acq, out_mean, out_var, st));
+  return PRB_OK;
 }
 
 int prb_mc_screen(prb_model* model, const prb_space_desc* space, const prb_acq_desc* acq, const double* theta, int32_t n_rows,

@@ -219,4 +219,100 @@ cudaError_t launch_tr_bounds(const double* X, const double* Y, int n, int d, int
   return cudaGetLastError();
 }
 
+// =====================================================================================================================
+// Model lists: ConstrainedExpectedImprovement over independent GPs ([3P] botorch <= 0.8; experiment_utils.py:354-392).
+//   sigma_m = max(sqrt(max(var_m, min_variance)), sigma_floor);  A = EI(mu_o, sigma_o; best_f) * prod_m P_m,
+//   P_m = [1 - cdf((lower_m - mu_m)/sigma_m)] and / or [cdf((upper_m - mu_m)/sigma_m)], cdf(x) = 0.5 (1 + erf(x / sqrt2)).
+// One thread per evaluation point: raw variances from every model's row-tile norms, the value, and -- for the pathwise
+// gradient -- dA/dmu_m and dA/dsigma_m^2 of every model (product rule; the clamps pass no gradient where they bind).
+// =====================================================================================================================
+__global__ void multi_acq_epilogue_kernel(const MultiAcqArgs ma, int ncols_pad, int ncols, double* __restrict__ a,
+                                          double* __restrict__ out_mean, double* __restrict__ out_var) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncols) return;
+  double mu[PRB_MAX_MODELS], sg[PRB_MAX_MODELS], pass[PRB_MAX_MODELS];
+  for (int m = 0; m < ma.n_models; ++m) {
+    double vs = 0.0;
+    for (int t = 0; t < ma.mtiles[m]; ++t) vs += ma.norm_part[m][size_t(t) * ncols_pad + col];
+    const double var_raw = ma.kss[m] - vs;
+    const double var = fmax(var_raw, ma.min_variance);
+    const double s_raw = sqrt(var);
+    mu[m] = ma.mean_const[m] + ma.mu_dot[m][col];
+    sg[m] = fmax(s_raw, ma.sigma_floor);
+    pass[m] = (var_raw >= ma.min_variance && s_raw >= ma.sigma_floor) ? 1.0 : 0.0;
+    if (out_mean) out_mean[size_t(col) * ma.n_models + m] = mu[m];
+    if (out_var) out_var[size_t(col) * ma.n_models + m] = var;
+  }
+  const int o = ma.objective_index;
+  const double u = (mu[o] - ma.best_f) / sg[o];
+  const double pdf = exp(-(u * u) / 2.0 - PRB_LOG_SQRT_2PI);
+  const double cdf = 0.5 * (1.0 + erf(u * PRB_INV_SQRT2));
+  const double ei = sg[o] * (pdf + u * cdf);
+  double P[PRB_MAX_MODELS], dP_dmu[PRB_MAX_MODELS], dP_dvar[PRB_MAX_MODELS];
+  for (int m = 0; m < ma.n_models; ++m) {
+    P[m] = 1.0;
+    dP_dmu[m] = dP_dvar[m] = 0.0;
+    if (m == o) continue;
+    double hi_c = 1.0, lo_c = 0.0, g_mu = 0.0, g_s = 0.0;  // P = hi_c - lo_c
+    if (ma.has_upper[m]) {
+      const double d = (ma.upper[m] - mu[m]) / sg[m];
+      const double ph = exp(-(d * d) / 2.0 - PRB_LOG_SQRT_2PI);
+      hi_c = 0.5 * (1.0 + erf(d * PRB_INV_SQRT2));
+      g_mu -= ph / sg[m];
+      g_s -= ph * d / sg[m];
+    }
+    if (ma.has_lower[m]) {
+      const double d = (ma.lower[m] - mu[m]) / sg[m];
+      const double ph = exp(-(d * d) / 2.0 - PRB_LOG_SQRT_2PI);
+      lo_c = 0.5 * (1.0 + erf(d * PRB_INV_SQRT2));
+      g_mu += ph / sg[m];
+      g_s += ph * d / sg[m];
+    }
+    if (ma.has_lower[m] && !ma.has_upper[m]) {
+      P[m] = 1.0 - lo_c;  // botorch: prob_l = 1 - cdf(dist_l)
+    } else if (ma.has_lower[m] || ma.has_upper[m]) {
+      P[m] = hi_c - lo_c;
+    }
+    dP_dmu[m] = g_mu;
+    dP_dvar[m] = g_s / (2.0 * sg[m]) * pass[m];  // d/d sigma^2 = (d/d sigma) / (2 sigma)
+  }
+  double prod = 1.0;
+  for (int m = 0; m < ma.n_models; ++m) prod *= P[m];
+  a[col] = ei * prod;
+  if (ma.dmu[0] == nullptr) return;
+  for (int m = 0; m < ma.n_models; ++m) {
+    if (m == o) {
+      ma.dmu[m][col] = cdf * prod;
+      ma.dvar[m][col] = pdf / (2.0 * sg[o]) * pass[o] * prod;
+    } else {
+      double others = ei;
+      for (int k = 0; k < ma.n_models; ++k)
+        if (k != m) others *= P[k];
+      ma.dmu[m][col] = others * dP_dmu[m];
+      ma.dvar[m][col] = others * dP_dvar[m];
+    }
+  }
+}
+
+cudaError_t launch_multi_acq_epilogue(const MultiAcqArgs& ma, int ncols_pad, int ncols, double* a, double* out_mean,
+                                      double* out_var, cudaStream_t st) {
+  ProfScope prof_(K_EPILOGUE, st);
+  if (ncols == 0) return cudaSuccess;
+  multi_acq_epilogue_kernel<<<(ncols + 127) / 128, 128, 0, st>>>(ma, ncols_pad, ncols, a, out_mean, out_var);
+  count_launch();
+  return cudaGetLastError();
+}
+
+__global__ void add_inplace_kernel(double* __restrict__ dst, const double* __restrict__ src, size_t count) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < count) dst[i] += src[i];
+}
+cudaError_t launch_add_inplace(double* dst, const double* src, size_t count, cudaStream_t st) {
+  ProfScope prof_(K_SUM_SPLITS, st);
+  if (count == 0) return cudaSuccess;
+  add_inplace_kernel<<<unsigned((count + 255) / 256), 256, 0, st>>>(dst, src, count);
+  count_launch();
+  return cudaGetLastError();
+}
+
 }  // namespace prb

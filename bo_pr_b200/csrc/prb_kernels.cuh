@@ -66,6 +66,22 @@ cudaError_t launch_clamp(const double* theta, const double* lower, const double*
 cudaError_t launch_adam_step(double* theta, const double* acq_grad, double* m, double* v, int total, double lr,
                              int* step_ptr, cudaStream_t st);
 cudaError_t launch_fill(double* p, double v, int n, cudaStream_t st);
+// model lists (prb_finalize.cu): combined acquisition epilogue and the accumulation of the per-model gradient partials
+struct MultiAcqArgs {
+  int n_models, objective_index;
+  double best_f, min_variance, sigma_floor;
+  int has_lower[PRB_MAX_MODELS], has_upper[PRB_MAX_MODELS];
+  double lower[PRB_MAX_MODELS], upper[PRB_MAX_MODELS];
+  double mean_const[PRB_MAX_MODELS], kss[PRB_MAX_MODELS];
+  const double* norm_part[PRB_MAX_MODELS];  // [mtiles, ncols_pad] per model
+  const double* mu_dot[PRB_MAX_MODELS];     // [ncols] per model
+  double* dmu[PRB_MAX_MODELS];              // [ncols] dA/dmu_m   (NULL: value only)
+  double* dvar[PRB_MAX_MODELS];             // [ncols] dA/dsigma_m^2
+  int mtiles[PRB_MAX_MODELS];
+};
+cudaError_t launch_multi_acq_epilogue(const MultiAcqArgs& ma, int ncols_pad, int ncols, double* a, double* out_mean,
+                                      double* out_var, cudaStream_t st);
+cudaError_t launch_add_inplace(double* dst, const double* src, size_t count, cudaStream_t st);
 // prb_finalize.cu
 cudaError_t launch_sample_candidates(const DevSpace& sp, const double* theta, int b, const double* u, uint64_t seed,
                                      uint64_t offset, double* out_x, double* out_xk, cudaStream_t st);

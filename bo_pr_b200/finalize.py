@@ -30,6 +30,15 @@ def finalize_candidates(pr, candidates: Tensor, seed: Optional[int] = None, offs
         raise NotImplementedError("expected candidates of shape b x q=1 x d")
     b, d = candidates.shape[0], candidates.shape[-1]
     dev = candidates.device
+    if type(pr.acq_function).__name__ == "ConstrainedExpectedImprovement":
+        # model lists: sampler kernel, then the model-list acquisition on the sampled rows; argmax with device ops
+        rows, xk = pr._sample_candidates_device(candidates, 0 if seed is None else int(seed), int(offset), u, want_xk=True)
+        with torch.no_grad():
+            vals = pr.acq_function(xk.unsqueeze(-2))
+        i = torch.argmax(vals)
+        if return_all:
+            return rows[i], vals[i], rows, vals
+        return rows[i], vals[i]
     state = gp_state_from_model(pr.acq_function.model)
     sp, aq = pr._space(), acq_desc_of(pr.acq_function)
     theta = candidates.detach().to(torch.float64).reshape(b, d).contiguous()

@@ -243,6 +243,75 @@ class FixedNoiseGP(Model):
         return _Posterior(mean.reshape(*shape, 1), var.reshape(*shape, 1))
 
 
+class ModelListGP(Model):
+    """``botorch.models.ModelListGP`` surface the reference uses (``experiment_utils.py:337-346``): independent single-output
+    GPs over the same inputs, one per outcome (objective + constraints).  ``models`` / ``num_outputs`` / ``posterior``."""
+
+    def __init__(self, *gp_models):
+        super().__init__()
+        if len(gp_models) < 1 or len(gp_models) > capi.PRB_MAX_MODELS:
+            raise NotImplementedError(f"1 .. {capi.PRB_MAX_MODELS} models are supported")
+        self.models = torch.nn.ModuleList(gp_models)
+
+    @property
+    def num_outputs(self) -> int:
+        return len(self.models)
+
+    @property
+    def train_inputs(self):
+        return [m.train_inputs for m in self.models]
+
+    def posterior(self, X: Tensor, observation_noise: bool = False, **kwargs) -> _Posterior:
+        if observation_noise:
+            raise NotImplementedError
+        ps = [m.posterior(X) for m in self.models]
+        return _Posterior(torch.cat([p.mean for p in ps], dim=-1), torch.cat([p.variance for p in ps], dim=-1))
+
+
+class MultiState:
+    """The device GP states of a model list plus the pointer array and the shared workspace the ``*_multi`` entry points take."""
+
+    def __init__(self, states: Sequence[GPState]):
+        self.states = list(states)
+        s0 = self.states[0]
+        if any(s.d_k != s0.d_k or s.n != s0.n or s.device != s0.device for s in self.states):
+            raise NotImplementedError("the models of a list must share the training inputs' shape and the device")
+        self.lib, self.device, self.d_k = s0.lib, s0.device, s0.d_k
+        self.handles = (C.c_void_p * len(self.states))(*[s.handle for s in self.states])
+        self._ws: Optional[Tensor] = None
+        self._need = {}
+
+    def __len__(self) -> int:
+        return len(self.states)
+
+    def workspace(self, n_points: int, d_theta: int, n_restarts: int = 0) -> Tensor:
+        key = (int(n_points), int(n_restarts), int(d_theta))
+        need = self._need.get(key)
+        if need is None:
+            need = self._need[key] = int(self.lib.prb_workspace_bytes_multi(self.handles, len(self.states), key[0], key[1],
+                                                                            key[2]))
+            if need == 0:
+                raise capi.PrbError("prb_workspace_bytes_multi failed (model list not usable on the device path)")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+
+def multi_state_from_model(model) -> MultiState:
+    """``MultiState`` of a ``ModelListGP`` (ours or duck-typed: anything with ``.models``); rebuilt when a member's state is."""
+    members = list(model.models)
+    states = [gp_state_from_model(m) for m in members]
+    cached = getattr(model, "_prb_multi", None)
+    if cached is not None and len(cached[0]) == len(states) and all(a is b for a, b in zip(cached[0], states)):
+        return cached[1]
+    ms = MultiState(states)
+    try:
+        model._prb_multi = (states, ms)
+    except Exception:
+        pass
+    return ms
+
+
 def _tensor_fp(t) -> tuple:
     if torch.is_tensor(t):
         return (t.data_ptr(), t._version, tuple(t.shape))
@@ -270,7 +339,7 @@ def gp_state_from_model(model) -> GPState:
         if getattr(model, attr, None) is not None:
             raise NotImplementedError(f"model.{attr} is not supported by the B200 hot path")
     if hasattr(model, "models"):
-        raise NotImplementedError("ModelListGP is not supported by the B200 hot path")
+        raise NotImplementedError("a ModelListGP has one device state per member: use multi_state_from_model")
     fp = _model_fingerprint(model)
     cached = getattr(model, "_prb_state", None)
     if cached is not None and cached[0] == fp:

@@ -20,7 +20,7 @@ from torch.autograd import Function
 from torch.nn.functional import one_hot
 
 from . import _capi as capi
-from .acquisition import AcquisitionFunction, acq_desc_of
+from .acquisition import AcquisitionFunction, ConstrainedExpectedImprovement, acq_desc_of
 from .input import (
     AnalyticProbabilisticReparameterizationInputTransform,
     ChainedInputTransform,
@@ -388,6 +388,8 @@ class MCProbabilisticReparameterization(AbstractProbabilisticReparameterization)
         dev = X.device
         if b == 0:  # nothing to evaluate; the reference's EMA update would average an empty tensor (NaN): leave the state
             return X.new_empty(0, dtype=torch.float64), None
+        if isinstance(self.acq_function, ConstrainedExpectedImprovement):
+            return self._launch_multi(X, need)
         cc = self._call_ctx(dev)
         rnd = cc["rnd"]
         if cc["tau"] != rnd.tau or cc["ma_ptr"] != self._ma_state.data_ptr():  # tau edited / module moved: rebuild
@@ -419,6 +421,35 @@ class MCProbabilisticReparameterization(AbstractProbabilisticReparameterization)
             with torch.cuda.device(dev):
                 capi.check(cc["fn"](*args, torch._C._cuda_getCurrentRawStream(idx)), "prb_mc_value_grad")
         return value, grad
+
+
+def _launch_multi(self, X: Tensor, need: bool):
+    """Model-list acquisition functions (``ConstrainedExpectedImprovement``): ``prb_mc_value_grad_multi``."""
+    b, d = X.shape[0], X.shape[-1]
+    dev = X.device
+    acq = self.acq_function
+    ms = acq.state
+    rnd = self.input_transform["round"]
+    rnd.ensure_base_samples(1, dev)
+    u_int, u_cat = rnd.base_sample_ptrs()
+    theta = X.detach().to(torch.float64).reshape(b, d).contiguous()
+    value = torch.empty(b, dtype=torch.float64, device=dev)
+    grad = torch.empty(b, d, dtype=torch.float64, device=dev) if need else None
+    ones = torch.ones(b, dtype=torch.float64, device=dev) if need else None
+    mc = rnd.mc_samples
+    ws = ms.workspace(b * mc, d, b)
+    est = capi.PRB_EST_REINFORCE_MA if self.grad_estimator == "reinforce_ma" else capi.PRB_EST_REINFORCE
+    sp, desc = self._space(), acq.multi_desc()
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream().cuda_stream
+        capi.check(ms.lib.prb_mc_value_grad_multi(ms.handles, len(ms), C.byref(sp), C.byref(desc), theta.data_ptr(), b, mc,
+                                                  capi.ptr(u_int), capi.ptr(u_cat), 0, 0, est, self._ma_state.data_ptr(), 1,
+                                                  capi.ptr(ones), value.data_ptr(), capi.ptr(grad), None, ws.data_ptr(),
+                                                  ws.numel(), st), "prb_mc_value_grad_multi")
+    return value, grad
+
+
+MCProbabilisticReparameterization._launch_multi = _launch_multi
 
 
 class _MCPRCall(Function):

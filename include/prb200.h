@@ -111,10 +111,30 @@ typedef struct {
 
 typedef enum { PRB_EST_REINFORCE = 0, PRB_EST_REINFORCE_MA = 1 } prb_estimator;
 
+/* ---- acquisition function over a LIST of independent single-output GPs (botorch ModelListGP, experiment_utils.py:337-346).
+ * PRB_MACQ_CEI: botorch ConstrainedExpectedImprovement as get_EI builds it (experiment_utils.py:354-392):
+ *   EI(objective output; best_f) * prod_m P(lower_m <= Y_m <= upper_m),  sigma_m = max(sqrt(var_m), sigma_floor),
+ *   P from Normal.cdf(x) = 0.5 (1 + erf(x / sqrt2)); a missing bound drops its factor.                                    */
+#define PRB_MAX_MODELS 8
+typedef enum { PRB_MACQ_CEI = 0 } prb_multi_acq_kind;
+typedef struct {
+  int32_t kind;            /* prb_multi_acq_kind */
+  int32_t n_models;        /* outputs = models, in list order */
+  int32_t objective_index; /* which model is the objective */
+  int32_t reserved;
+  double best_f;
+  double min_variance;     /* gpytorch posterior variance floor (1e-10 in float64) */
+  double sigma_floor;      /* botorch: sqrt(var).clamp_min(1e-9) */
+  int32_t has_lower[PRB_MAX_MODELS];
+  int32_t has_upper[PRB_MAX_MODELS];
+  double lower[PRB_MAX_MODELS]; /* bounds on model m's output; ignored for the objective */
+  double upper[PRB_MAX_MODELS];
+} prb_multi_acq_desc;
+
 /* ---- library ---------------------------------------------------------------------------------------------------- */
 int prb_version(void);
 /* sizeof() of the descriptor structs as compiled into the library (0 prb_factor, 1 prb_term, 2 prb_model_desc,
- * 3 prb_space_desc, 4 prb_acq_desc): lets a foreign-language binding verify its mirror of the layout.               */
+ * 3 prb_space_desc, 4 prb_acq_desc, 5 prb_multi_acq_desc): lets a foreign-language binding verify its mirror of the layout.               */
 int prb_abi_sizeof(int which);
 const char* prb_status_string(int status);
 /* Number of CUDA kernels this library has launched in this process (graph replays included).  Diagnostic: bench.py
@@ -252,6 +272,25 @@ int prb_mc_value_grad(prb_model* model, const prb_space_desc* space, const prb_a
                       uint64_t offset, int32_t estimator, double* ma_state, int32_t update_ma,
                       const double* grad_out, double* out_value, double* out_grad, double* out_acq_values,
                       void* workspace, size_t workspace_bytes, int32_t chunk_cols, void* stream);
+
+/* The same call over a model list: every model contributes its own posterior (its own k*, Cholesky factor and -- for the
+ * pathwise gradient -- its own second product); the acquisition epilogue combines them by the product rule.
+ * Replaces: _MCProbabilisticReparameterization.forward/backward around ConstrainedExpectedImprovement on a ModelListGP
+ * (experiment_utils.py:354-392; the welded-beam / pressure-vessel style configs).  All models must share d_k and n.
+ * Workspace: prb_workspace_bytes_multi.  One column panel only (PRB_ERR_UNSUPPORTED beyond ~10^5 evaluation points).        */
+size_t prb_workspace_bytes_multi(prb_model* const* models, int32_t n_models, int64_t n_points, int32_t n_restarts,
+                                 int32_t d_theta);
+int prb_mc_value_grad_multi(prb_model* const* models, int32_t n_models, const prb_space_desc* space,
+                            const prb_multi_acq_desc* acq, const double* theta, int32_t b, int32_t mc,
+                            const double* u_int, const double* u_cat, uint64_t seed, uint64_t offset, int32_t estimator,
+                            double* ma_state, int32_t update_ma, const double* grad_out, double* out_value,
+                            double* out_grad, double* out_acq_values, void* workspace, size_t workspace_bytes,
+                            void* stream);
+/* Model-list acquisition value at explicit kernel-input points xk [n_points, d_k] (re-scoring of sampled candidates,
+ * run_one_replication.py:513-528).  out_acq [n_points]; out_mean / out_var [n_points, n_models] or NULL.                    */
+int prb_acq_points_multi(prb_model* const* models, int32_t n_models, const prb_multi_acq_desc* acq, const double* xk,
+                         int64_t n_points, double* out_acq, double* out_mean, double* out_var, void* workspace,
+                         size_t workspace_bytes, void* stream);
 
 /* Raw-sample screening: the value-only MC-PR forward of prb_mc_value_grad applied to theta [n_rows, d] in consecutive chunks
  * of `chunk_rows` rows, one enqueue after the other with no host work in between.  Each chunk counts as ONE forward call for

@@ -276,3 +276,55 @@ class OraclePosteriorMean(OracleAcq):
     def forward(self, X):
         mean, _ = self.model.posterior(X)
         return mean
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Model lists and constrained EI  [3P] botorch ModelListGP + ConstrainedExpectedImprovement (BoTorch 0.6-0.8),
+# call site experiment_utils.py:354-392 (get_EI with num_constraints > 0; welded_beam, pressure_vessel, ...)
+# ----------------------------------------------------------------------------------------------------------------------
+class OracleModelList(torch.nn.Module):
+    """Independent single-output GPs over the same inputs (``ModelListGP(*models)``, experiment_utils.py:337-346):
+    ``posterior(X)`` -> (mean [..., m], variance [..., m])."""
+
+    def __init__(self, *models: OracleGP):
+        super().__init__()
+        self.models = torch.nn.ModuleList(models)
+
+    def posterior(self, X: Tensor):
+        ms, vs = zip(*[m.posterior(X) for m in self.models])
+        return torch.stack(ms, dim=-1), torch.stack(vs, dim=-1)
+
+
+class OracleConstrainedEI(OracleAcq):
+    """``ConstrainedExpectedImprovement(model, best_f, objective_index, constraints)`` as BoTorch <= 0.8 computes it:
+    sigma = sqrt(var).clamp_min(1e-9) for EVERY output (note: the clamp is on sigma here, on the variance in plain EI);
+    EI of the objective output times prod_i P(lower_i <= Y_i <= upper_i) with Normal.cdf = 0.5 (1 + erf(x / sqrt2)):
+    lower only: 1 - cdf((lower - mean)/sigma); upper only: cdf((upper - mean)/sigma); both: the difference.
+    ``constraints = {output index: (lower or None, upper or None)}`` (get_EI passes ``(slack, None)``)."""
+
+    def __init__(self, model: OracleModelList, best_f, objective_index: int, constraints, sigma_floor: float = 1e-9):
+        super().__init__(model)
+        self.best_f = torch.as_tensor(best_f, dtype=torch.float64)
+        self.objective_index = int(objective_index)
+        self.constraints = dict(constraints)
+        self.sigma_floor = sigma_floor
+
+    def forward(self, X):
+        means, variances = self.model.posterior(X)
+        sigmas = variances.sqrt().clamp_min(self.sigma_floor)
+        mean_obj, sigma_obj = means[..., self.objective_index], sigmas[..., self.objective_index]
+        u = (mean_obj - self.best_f) / sigma_obj
+        ei_pdf = torch.exp(-(u ** 2) / 2 - _LOG_SQRT_2PI)
+        ei_cdf = 0.5 * (1 + torch.erf(u / math.sqrt(2)))
+        ei = sigma_obj * (ei_pdf + u * ei_cdf)
+        cdf = lambda x: 0.5 * (1 + torch.erf(x / math.sqrt(2)))  # noqa: E731
+        prob = torch.ones_like(ei)
+        for i, (lo, hi) in self.constraints.items():
+            m, s = means[..., i], sigmas[..., i]
+            if lo is not None and hi is not None:
+                prob = prob * (cdf((hi - m) / s) - cdf((lo - m) / s))
+            elif lo is not None:
+                prob = prob * (1 - cdf((lo - m) / s))
+            elif hi is not None:
+                prob = prob * cdf((hi - m) / s)
+        return ei * prob

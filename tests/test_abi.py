@@ -41,7 +41,8 @@ def test_version_and_status_strings(lib):
 
 
 def test_struct_layout_matches_c(lib):
-    for which, ty in enumerate([capi.PrbFactor, capi.PrbTerm, capi.PrbModelDesc, capi.PrbSpaceDesc, capi.PrbAcqDesc]):
+    for which, ty in enumerate([capi.PrbFactor, capi.PrbTerm, capi.PrbModelDesc, capi.PrbSpaceDesc, capi.PrbAcqDesc,
+                                capi.PrbMultiAcqDesc]):
         assert lib.prb_abi_sizeof(which) == C.sizeof(ty), ty.__name__
 
 
