@@ -31,7 +31,7 @@ PROFILE_SLOT_NAMES = ["pr_sample", "kstar_panel", "trgemm_lower", "acq_epilogue"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", os.environ.get("PRB_LIB_NAME", "libprb200.so"))
 
 EXPORTS = [
-    "prb_version", "prb_abi_sizeof", "prb_debug_small_timestamps", "prb_debug_fp64_peak", "prb_launch_count", "prb_profile_enable", "prb_profile_read", "prb_status_string", "prb_last_cuda_error", "prb_model_create", "prb_rff_model_create", "prb_model_destroy", "prb_model_set_option",
+    "prb_version", "prb_abi_sizeof", "prb_debug_small_timestamps", "prb_debug_fp64_peak", "prb_launch_count", "prb_profile_enable", "prb_profile_read", "prb_status_string", "prb_last_cuda_error", "prb_model_create", "prb_model_create_from_data", "prb_rff_model_create", "prb_model_destroy", "prb_model_set_option",
     "prb_model_n", "prb_model_dk", "prb_workspace_bytes", "prb_philox_uniform", "prb_pr_sample",
     "prb_analytic_enumerate", "prb_kernel_matrix", "prb_acq_points", "prb_sample_candidates", "prb_finalize_candidates",
     "prb_trust_region_bounds", "prb_workspace_bytes_multi", "prb_mc_value_grad_multi", "prb_acq_points_multi",
@@ -105,6 +105,7 @@ def load_library() -> C.CDLL:
     lib.prb_status_string.argtypes = [C.c_int]
     lib.prb_last_cuda_error.restype = C.c_char_p
     lib.prb_model_create.argtypes = [C.POINTER(vp), C.POINTER(PrbModelDesc), vp]
+    lib.prb_model_create_from_data.argtypes = [C.POINTER(vp), C.POINTER(PrbModelDesc), vp, vp, vp, vp, vp]
     lib.prb_rff_model_create.argtypes = [C.POINTER(vp), C.c_int32, C.c_int32, vp, vp, vp, C.c_double, vp]
     lib.prb_model_destroy.argtypes = [vp]
     lib.prb_model_set_option.argtypes = [vp, i32, i64]
@@ -149,7 +150,7 @@ def check(status: int, what: str) -> None:
         return
     lib = load_library()
     msg = lib.prb_status_string(status).decode()
-    if status == -4 or status == -5:
+    if status in (-4, -5, -6):
         msg += ": " + lib.prb_last_cuda_error().decode()
     raise PrbError(f"{what} failed: {msg} (status {status})")
 

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 # PRB_LIB_NAME / PRB_NVCC_EXTRA: build a tuning variant next to the default library (experiments only)
 OUT = os.path.join(HERE, "_lib", os.environ.get("PRB_LIB_NAME", "libprb200.so"))
-SOURCES = ["prb_gemm_tma.cu", "prb_small.cu", "prb_kernels.cu", "prb_finalize.cu", "prb_api.cu"]
+SOURCES = ["prb_gemm_tma.cu", "prb_small.cu", "prb_kernels.cu", "prb_finalize.cu", "prb_chol.cu", "prb_api.cu"]
 HEADERS = ["prb_internal.cuh", "prb_device.cuh", "prb_kernels.cuh", "prb_ptx.cuh", os.path.join(ROOT, "include", "prb200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

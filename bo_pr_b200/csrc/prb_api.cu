@@ -810,15 +810,31 @@ const char* prb_status_string(int status) {
     case PRB_ERR_WORKSPACE: return "workspace too small";
     case PRB_ERR_CUDA: return "CUDA error";
     case PRB_ERR_NO_DEVICE: return "no usable sm_100 device";
+    case PRB_ERR_NOT_PD: return "matrix is not positive definite";
     default: return "unknown status";
   }
 }
 
 const char* prb_last_cuda_error(void) { return g_cuda_err; }
 
+static int model_create_impl(prb_model** out, const prb_model_desc* desc, const double* y, const double* noise,
+                             double* out_Linv, double* out_alpha, void* stream);
+
 int prb_model_create(prb_model** out, const prb_model_desc* desc, void* stream) {
-  if (!out || !desc || desc->n < 1 || desc->d_k < 1 || !desc->X_train || !desc->Linv || !desc->alpha)
-    return PRB_ERR_INVALID;
+  if (!desc || !desc->Linv || !desc->alpha) return PRB_ERR_INVALID;
+  return model_create_impl(out, desc, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+int prb_model_create_from_data(prb_model** out, const prb_model_desc* desc, const double* y, const double* noise,
+                               double* out_Linv, double* out_alpha, void* stream) {
+  if (!y || !noise) return PRB_ERR_INVALID;
+  return model_create_impl(out, desc, y, noise, out_Linv, out_alpha, stream);
+}
+
+static int model_create_impl(prb_model** out, const prb_model_desc* desc, const double* y, const double* noise,
+                             double* out_Linv, double* out_alpha, void* stream) {
+  const bool from_data = y != nullptr;
+  if (!out || !desc || desc->n < 1 || desc->d_k < 1 || !desc->X_train) return PRB_ERR_INVALID;
   if (desc->d_k > PRB_MAX_DIMS) return PRB_ERR_UNSUPPORTED;
   int dev = -1;
   if (cudaGetDevice(&dev) != cudaSuccess) return PRB_ERR_NO_DEVICE;
@@ -848,13 +864,49 @@ int prb_model_create(prb_model** out, const prb_model_desc* desc, void* stream) 
     return cuda_fail(e, "cudaMalloc(model)");
   }
   e = cudaMemcpyAsync(m->Xtr, desc->X_train, size_t(m->n) * m->d_k * sizeof(double), cudaMemcpyDeviceToDevice, st);
-  if (e == cudaSuccess)
+  int chol_info = 0;
+  if (e == cudaSuccess && from_data) {
+    // K(X, X) by the library's own kernel, then the factorisation, the inverse factor, alpha and the packing (prb_chol.cu)
+    double* Kmat = nullptr;
+    void* scratch = nullptr;
+    int* info_dev = nullptr;
+    // stream-ordered pool allocations: cudaMalloc / cudaFree of a few hundred MB cost more than the factorisation itself.
+    // The pool keeps what it has handed out (release threshold raised once) so that the next BO iteration's build reuses it.
+    static std::once_flag pool_once;
+    std::call_once(pool_once, [dev] {
+      cudaMemPool_t pool = nullptr;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = uint64_t(2) << 30;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      (void)cudaGetLastError();
+    });
+    if ((e = cudaMallocAsync(&Kmat, size_t(m->n) * m->n * sizeof(double), st)) == cudaSuccess &&
+        (e = cudaMallocAsync(&scratch, chol_scratch_bytes(m->n), st)) == cudaSuccess &&
+        (e = cudaMallocAsync(&info_dev, sizeof(int), st)) == cudaSuccess &&
+        (e = launch_kernel_matrix(m->spec, m->Xtr, m->n, m->Xtr, m->n, Kmat, st)) == cudaSuccess &&
+        (e = build_gp_state(Kmat, noise, y, m->mean_const, m->n, m->Kp, m->Mp1, m->Mp2, m->A1, m->A2, m->alpha, out_Linv,
+                            scratch, info_dev, st)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(&chol_info, info_dev, sizeof(int), cudaMemcpyDeviceToHost, st)) == cudaSuccess)
+      e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && out_alpha)
+      e = cudaMemcpyAsync(out_alpha, m->alpha, size_t(m->n) * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    if (Kmat) cudaFreeAsync(Kmat, st);
+    if (scratch) cudaFreeAsync(scratch, st);
+    if (info_dev) cudaFreeAsync(info_dev, st);
+    if (e == cudaSuccess && chol_info != 0) {
+      snprintf(g_cuda_err, sizeof(g_cuda_err), "K + diag(noise) is not positive definite (pivot %d)", chol_info - 1);
+      prb_model_destroy(reinterpret_cast<prb_model*>(m));
+      return PRB_ERR_NOT_PD;
+    }
+  } else if (e == cudaSuccess) {
     e = cudaMemcpyAsync(m->alpha, desc->alpha, size_t(m->n) * sizeof(double), cudaMemcpyDeviceToDevice, st);
-  if (e == cudaSuccess) {
-    dim3 grid((m->Kp + 127) / 128, m->Mp1 > m->Mp2 ? m->Mp1 : m->Mp2);
-    pack_state_kernel<<<grid, 128, 0, st>>>(desc->Linv, desc->alpha, m->n, m->Kp, m->Mp1, m->Mp2, m->A1, m->A2);
-    e = cudaGetLastError();
-    count_launch();
+    if (e == cudaSuccess) {
+      dim3 grid((m->Kp + 127) / 128, m->Mp1 > m->Mp2 ? m->Mp1 : m->Mp2);
+      pack_state_kernel<<<grid, 128, 0, st>>>(desc->Linv, desc->alpha, m->n, m->Kp, m->Mp1, m->Mp2, m->A1, m->A2);
+      e = cudaGetLastError();
+      count_launch();
+    }
   }
   // second-generation engine: TMA descriptors of the packed factors, padded alpha, separable-structure tables
   const int n_pad = m->Mp1 > m->Mp2 ? m->Mp1 : m->Mp2;

@@ -82,6 +82,11 @@ struct MultiAcqArgs {
 cudaError_t launch_multi_acq_epilogue(const MultiAcqArgs& ma, int ncols_pad, int ncols, double* a, double* out_mean,
                                       double* out_var, cudaStream_t st);
 cudaError_t launch_add_inplace(double* dst, const double* src, size_t count, cudaStream_t st);
+// prb_chol.cu: GP-state builder (blocked Cholesky, divide-and-conquer triangular inverse, alpha, packing)
+size_t chol_scratch_bytes(int n);
+cudaError_t build_gp_state(const double* K, const double* noise, const double* y, double mean_const, int n, int Kp, int Mp1,
+                           int Mp2, double* A1, double* A2, double* alpha, double* Linv_out, void* scratch, int* info_dev,
+                           cudaStream_t st);
 // prb_finalize.cu
 cudaError_t launch_sample_candidates(const DevSpace& sp, const double* theta, int b, const double* u, uint64_t seed,
                                      uint64_t offset, double* out_x, double* out_xk, cudaStream_t st);

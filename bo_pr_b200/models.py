@@ -4,8 +4,9 @@ The reference builds a BoTorch ``FixedNoiseGP`` with a ``ConstantMean`` and the 
 (``discrete_mixed_bo/experiment_utils.py:237-351``) and lets GPyTorch's exact prediction strategy cache
 ``(K + Sigma)^-1 (y - c)`` and the inverse Cholesky root.  ``GPState`` is that cache as plain device tensors
 (``X_train``, ``Linv``, ``alpha``, constant, kernel structure) handed to ``libprb200`` through ``prb_model_create``.
-``K(X, X)`` is assembled by the library's own kernel (``prb_kernel_matrix``); the Cholesky factorisation and the
-triangular inverse are torch/cuSOLVER calls -- the step *before* the hot path.
+The whole build -- ``K(X, X)``, blocked Cholesky, triangular inverse, ``alpha``, packing -- runs in the library
+(``prb_model_create_from_data``, ``csrc/prb_chol.cu``: FP64 DMMA block GEMMs, no cuSOLVER / cuBLAS); the step *before* the
+hot path.  ``builder="torch"`` keeps the library factorisation as a cross-check for the tests.
 """
 from __future__ import annotations
 
@@ -130,7 +131,8 @@ class RFFState(DeviceState):
 class GPState(DeviceState):
     """Device-resident exact-GP caches + the ``prb_model`` handle.  One per (model, BO iteration)."""
 
-    def __init__(self, train_X: Tensor, train_Y: Tensor, terms: Sequence[TermT], noise, mean_const: float):
+    def __init__(self, train_X: Tensor, train_Y: Tensor, terms: Sequence[TermT], noise, mean_const: float,
+                 builder: str = "device"):
         capi.require_cuda(train_X, "train_X")
         self._init_common(train_X.device, train_X.shape[-1])
         X = train_X.detach().to(torch.float64).contiguous()
@@ -149,17 +151,30 @@ class GPState(DeviceState):
             desc = capi.PrbModelDesc()
             _fill_model_desc(desc, self.terms, n, d_k)
             desc.X_train = X.data_ptr()
-            K = torch.empty(n, n, dtype=torch.float64, device=self.device)
-            capi.check(self.lib.prb_kernel_matrix(C.byref(desc), X.data_ptr(), n, K.data_ptr(), stream),
-                       "prb_kernel_matrix")
-            K.diagonal().add_(self.noise)
-            L = torch.linalg.cholesky(K)
-            self.Linv = torch.linalg.solve_triangular(
-                L, torch.eye(n, dtype=torch.float64, device=self.device), upper=False).contiguous()
-            self.alpha = torch.cholesky_solve((y - self.mean_const).unsqueeze(-1), L).squeeze(-1).contiguous()
-            desc.Linv, desc.alpha, desc.mean_const = self.Linv.data_ptr(), self.alpha.data_ptr(), self.mean_const
+            desc.mean_const = self.mean_const
             handle = C.c_void_p()
-            capi.check(self.lib.prb_model_create(C.byref(handle), C.byref(desc), stream), "prb_model_create")
+            if builder == "device":
+                # K(X, X), blocked Cholesky, triangular inverse, alpha and the packed factors: all in the library
+                # (prb_chol.cu); Linv / alpha are exported for inspection and for the tests
+                self.Linv = torch.empty(n, n, dtype=torch.float64, device=self.device)
+                self.alpha = torch.empty(n, dtype=torch.float64, device=self.device)
+                capi.check(self.lib.prb_model_create_from_data(C.byref(handle), C.byref(desc), y.data_ptr(),
+                                                               self.noise.data_ptr(), self.Linv.data_ptr(),
+                                                               self.alpha.data_ptr(), stream), "prb_model_create_from_data")
+            elif builder == "torch":
+                # cross-check path of the test-suite (cuSOLVER / cuBLAS factorisation, then prb_model_create packs it)
+                K = torch.empty(n, n, dtype=torch.float64, device=self.device)
+                capi.check(self.lib.prb_kernel_matrix(C.byref(desc), X.data_ptr(), n, K.data_ptr(), stream),
+                           "prb_kernel_matrix")
+                K.diagonal().add_(self.noise)
+                L = torch.linalg.cholesky(K)
+                self.Linv = torch.linalg.solve_triangular(
+                    L, torch.eye(n, dtype=torch.float64, device=self.device), upper=False).contiguous()
+                self.alpha = torch.cholesky_solve((y - self.mean_const).unsqueeze(-1), L).squeeze(-1).contiguous()
+                desc.Linv, desc.alpha = self.Linv.data_ptr(), self.alpha.data_ptr()
+                capi.check(self.lib.prb_model_create(C.byref(handle), C.byref(desc), stream), "prb_model_create")
+            else:
+                raise ValueError("builder must be 'device' or 'torch'")
         self.handle = handle
         self._desc = desc
 

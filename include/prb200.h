@@ -41,7 +41,8 @@ typedef enum {
   PRB_ERR_UNSUPPORTED = -2,  /* exceeds a compile-time limit above */
   PRB_ERR_WORKSPACE = -3,    /* workspace too small */
   PRB_ERR_CUDA = -4,         /* a CUDA runtime call failed; see prb_last_cuda_error() */
-  PRB_ERR_NO_DEVICE = -5     /* no sm_100 device / wrong device */
+  PRB_ERR_NO_DEVICE = -5,    /* no sm_100 device / wrong device */
+  PRB_ERR_NOT_PD = -6        /* K + diag(noise) is not positive definite to working precision; see prb_last_cuda_error() */
 } prb_status;
 
 /* ---- kernel structure: what get_kernel() builds (kernels.py:18-101) -------------------------------------------
@@ -164,6 +165,15 @@ const char* prb_last_cuda_error(void);
  * BO iteration.  Replaces: the caches behind model.posterior() that acq_function(X) reads
  * (probabilistic_reparameterization.py:314, 491; [3P] gpytorch exact prediction strategy).                       */
 int prb_model_create(prb_model** out, const prb_model_desc* desc, void* stream);
+/* The same, starting from the DATA: K(X, X) + diag(noise) is assembled, factored (blocked Cholesky), inverted (triangular,
+ * divide and conquer) and packed by the library's own kernels (FP64 DMMA block GEMMs; no cuSOLVER / cuBLAS).  desc->Linv and
+ * desc->alpha are ignored.  y [n] targets, noise [n] observation variances (device).  out_Linv [n, n] (lower, zeros above) and
+ * out_alpha [n] receive copies when not NULL.  Returns PRB_ERR_NOT_PD if the matrix is not positive definite to working
+ * precision (prb_last_cuda_error() names the pivot).  Allocates scratch (3 n^2 doubles, released before returning) and
+ * synchronises `stream` once.  Replaces: the prediction-strategy caches behind model.posterior, built from
+ * experiment_utils.py:237-351's FixedNoiseGP ([3P] psd_safe_cholesky, explicit inverse root, mean_cache).                   */
+int prb_model_create_from_data(prb_model** out, const prb_model_desc* desc, const double* y, const double* noise,
+                               double* out_Linv, double* out_alpha, void* stream);
 /* A deterministic posterior SAMPLE as the model (Thompson sampling, label `pr__ts`):
  *   f(x) = scale * sum_j weights[j] * cos(x . W[:, j] + bias[j]),   W [d_k, n_features] row-major (lengthscales folded in),
  * used with PRB_ACQ_MEAN in every entry point that takes a prb_model (other acquisition kinds return PRB_ERR_INVALID).
