@@ -14,8 +14,10 @@ is an extra key.  NCCL appears where the path has its exchange: the all-gathers 
 the per-restart results inside the `bo_iter_sharded` leg (optimize_acqf(shard=True)), timed there.
 
 `value`      device-resident inputs, straight through the C ABI (prb_mc_value_grad), CUDA events, max over ranks.
-`e2e`        the same metric through the reference-facing API (MCProbabilisticReparameterization.forward + autograd),
-             theta in pinned HOST memory, host<->device copies inside the timed region.
+`e2e`        the same metric with HOST buffers: MCProbabilisticReparameterization.value_and_grad_host -> the C ABI's host-buffer
+             entry prb_mc_value_grad_host (pinned theta in, pinned value + gradient out; host->device copy, fused step,
+             device->host copies and the wait for them inside the timed region, every step).  `e2e.via_forward_autograd`
+             is the same step through nn.Module.forward + torch.autograd on device tensors made from the pinned buffers.
 `roofline`   the dominant kernel (the FP64 DMMA triangular products), timed live with CUDA events per launch; the
              denominator is measured in the same run (`peak_live`: mma.sync.m8n8k4.f64 from registers) next to the
              library baseline for the same two products (cuBLAS dtrmm / dgemm).
@@ -522,6 +524,12 @@ def run_ours(a):
         grad_host = torch.empty(b, 1, d, dtype=torch.float64).pin_memory()
 
         def e2e_step():
+            # the host-buffer entry of the C ABI (prb_mc_value_grad_host) through its Python method: pinned theta in, pinned
+            # value + gradient out, H2D copy -> fused step -> D2H copies in one call that returns when the results have landed
+            pr.value_and_grad_host(theta_host, val_host, grad_host, synchronize=True)
+
+        def e2e_autograd_step():
+            # the same step through nn.Module.forward + torch.autograd with device tensors made from the pinned buffers
             X = theta_host.to(dev, non_blocking=True).requires_grad_(True)
             v = pr(X)
             g = torch.autograd.grad(v.sum(), X)[0]
@@ -529,19 +537,27 @@ def run_ours(a):
             grad_host.copy_(g, non_blocking=True)
             torch.cuda.synchronize()
 
-        for _ in range(a.warmup):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(a.steps):
-            e2e_step()
-        barrier()
-        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": evals_per_step / (float(t) / a.steps), "unit": UNIT,
+        def wall(fn):
+            for _ in range(a.warmup):
+                fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(a.steps):
+                fn()
+            barrier()
+            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t) / a.steps
+
+        sec = wall(e2e_step)
+        sec_ag = wall(e2e_autograd_step)
+        e2e = {"value": evals_per_step / sec, "unit": UNIT,
                "h2d_bytes_per_step": a.restarts * d * 8, "d2h_bytes_per_step": a.restarts * (1 + d) * 8,
-               "ms_per_step": float(t) / a.steps * 1e3}
+               "ms_per_step": sec * 1e3,
+               "api": "MCProbabilisticReparameterization.value_and_grad_host -> prb_mc_value_grad_host (C ABI, host buffers)",
+               "via_forward_autograd": {"value": evals_per_step / sec_ag, "ms_per_step": sec_ag * 1e3,
+                                        "api": "pinned theta .to(device) -> forward -> autograd.grad -> .copy_ to pinned"}}
     clocks = sampler.stop() if sampler is not None else None
 
     # ---- value-only evaluation (raw-sample screening) and MC de-duplication: rank 0, N = 1, reported separately ---------

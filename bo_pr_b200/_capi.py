@@ -35,7 +35,7 @@ EXPORTS = [
     "prb_model_n", "prb_model_dk", "prb_workspace_bytes", "prb_philox_uniform", "prb_pr_sample",
     "prb_analytic_enumerate", "prb_kernel_matrix", "prb_acq_points", "prb_sample_candidates", "prb_finalize_candidates",
     "prb_trust_region_bounds", "prb_workspace_bytes_multi", "prb_mc_value_grad_multi", "prb_acq_points_multi",
-    "prb_mc_value_grad", "prb_mc_screen", "prb_analytic_value_grad", "prb_mc_adam", "prb_analytic_adam",
+    "prb_mc_value_grad", "prb_mc_value_grad_host", "prb_mc_screen", "prb_analytic_value_grad", "prb_mc_adam", "prb_analytic_adam",
 ]
 
 
@@ -129,6 +129,8 @@ def load_library() -> C.CDLL:
     lib.prb_acq_points.argtypes = [vp, C.POINTER(PrbAcqDesc), vp, i64, vp, vp, vp, vp, vp, sz, i32, vp]
     lib.prb_mc_value_grad.argtypes = [vp, C.POINTER(PrbSpaceDesc), C.POINTER(PrbAcqDesc), vp, i32, i32, vp, vp, u64,
                                       u64, i32, vp, i32, vp, vp, vp, vp, vp, sz, i32, vp]
+    lib.prb_mc_value_grad_host.argtypes = [vp, C.POINTER(PrbSpaceDesc), C.POINTER(PrbAcqDesc), vp, i32, i32, vp, vp, u64,
+                                           u64, i32, vp, i32, i32, vp, vp, vp, sz, i32, vp]
     lib.prb_mc_screen.argtypes = [vp, C.POINTER(PrbSpaceDesc), C.POINTER(PrbAcqDesc), vp, i32, i32, i32, vp, vp, u64, u64,
                                   i32, vp, vp, vp, sz, i32, vp]
     lib.prb_analytic_value_grad.argtypes = [vp, C.POINTER(PrbSpaceDesc), C.POINTER(PrbAcqDesc), vp, i32, vp, i32, vp,

@@ -370,6 +370,44 @@ class MCProbabilisticReparameterization(AbstractProbabilisticReparameterization)
         _check_X(X, self.dim)
         return _MCPRCall.apply(X, self)
 
+    def value_and_grad_host(self, theta_host: Tensor, value_host: Tensor, grad_host: Optional[Tensor] = None,
+                            device=None, synchronize: bool = True) -> None:
+        """Host-buffer entry (``prb_mc_value_grad_host``): ``theta_host [b, 1, d]`` (float64, contiguous, ideally pinned) in,
+        ``value_host [b]`` and ``grad_host [b, 1, d]`` (d value.sum() / d theta) out -- host->device copy, the fused step and
+        the device->host copies in ONE library call on the current stream of ``device`` (default: the model's).  Same
+        arithmetic and EMA-baseline side effects as ``forward`` + ``autograd.grad``; this is the path a caller without
+        device tensors uses, and what ``bench.py`` times as ``e2e``."""
+        state = gp_state_from_model(self.acq_function.model)
+        dev = state.device if device is None else torch.device(device)
+        for t, nm in ((theta_host, "theta_host"), (value_host, "value_host"), (grad_host, "grad_host")):
+            if t is not None and (t.is_cuda or t.dtype != torch.float64 or not t.is_contiguous()):
+                raise ValueError(f"{nm} must be a contiguous float64 HOST tensor")
+        b, d = theta_host.shape[0], theta_host.shape[-1]
+        if theta_host.numel() != b * d or d != self.dim:
+            raise ValueError(f"expected theta_host of shape b x 1 x {self.dim}")
+        if b == 0:
+            return
+        cc = self._call_ctx(dev)
+        rnd = cc["rnd"]
+        state.set_option(capi.PRB_OPT_DEDUP, int(self.dedup))
+        if rnd.resample or cc.get("u_ver") is None:
+            rnd.ensure_base_samples(1, dev)
+            ui, uc = rnd.base_sample_ptrs()
+            cc["u_ver"] = (capi.ptr(ui), capi.ptr(uc), ui, uc)
+        mc = rnd.mc_samples
+        ws = state.workspace(b * mc, d, b)
+        aq = acq_desc_of(self.acq_function)
+        idx = cc["idx"]
+        fn = capi.load_library().prb_mc_value_grad_host
+        args = (state.handle, cc["sp"], C.byref(aq), theta_host.data_ptr(), b, mc, cc["u_ver"][0], cc["u_ver"][1], 0, 0,
+                cc["est"], self._ma_state.data_ptr(), 1, int(grad_host is not None), value_host.data_ptr(),
+                capi.ptr(grad_host), ws.data_ptr(), ws.numel(), int(synchronize))
+        if torch._C._cuda_getDevice() == idx:
+            capi.check(fn(*args, torch._C._cuda_getCurrentRawStream(idx)), "prb_mc_value_grad_host")
+        else:
+            with torch.cuda.device(dev):
+                capi.check(fn(*args, torch._C._cuda_getCurrentRawStream(idx)), "prb_mc_value_grad_host")
+
     def _call_ctx(self, dev: torch.device):
         cc = self.__dict__.get("_cc")
         if cc is None or cc["dev"] != dev:

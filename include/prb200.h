@@ -283,6 +283,18 @@ int prb_mc_value_grad(prb_model* model, const prb_space_desc* space, const prb_a
                       const double* grad_out, double* out_value, double* out_grad, double* out_acq_values,
                       void* workspace, size_t workspace_bytes, int32_t chunk_cols, void* stream);
 
+/* The same call with HOST buffers: theta_host [b, d] is copied in, out_value_host [b] and out_grad_host [b, d] (unit upstream
+ * gradient; required iff want_grad) are copied out, all enqueued on `stream` around the kernels -- one call, no device tensors
+ * on the caller's side.  Pinned host memory makes the copies asynchronous; pageable memory works (the runtime stages it).
+ * u_int / u_cat / ma_state stay DEVICE pointers (they are the wrapper's buffers).  synchronize != 0: the call returns after
+ * the results have landed in the host buffers (the one entry point that synchronises, by request).  The device staging
+ * lives in the caller's workspace (same prb_workspace_bytes).                                                              */
+int prb_mc_value_grad_host(prb_model* model, const prb_space_desc* space, const prb_acq_desc* acq,
+                           const double* theta_host, int32_t b, int32_t mc, const double* u_int, const double* u_cat,
+                           uint64_t seed, uint64_t offset, int32_t estimator, double* ma_state, int32_t update_ma,
+                           int32_t want_grad, double* out_value_host, double* out_grad_host, void* workspace,
+                           size_t workspace_bytes, int32_t synchronize, void* stream);
+
 /* The same call over a model list: every model contributes its own posterior (its own k*, Cholesky factor and -- for the
  * pathwise gradient -- its own second product); the acquisition epilogue combines them by the product rule.
  * Replaces: _MCProbabilisticReparameterization.forward/backward around ConstrainedExpectedImprovement on a ModelListGP

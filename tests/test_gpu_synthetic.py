@@ -332,3 +332,28 @@ def test_generic_path_vs_oracle_at_sweep_sizes(kind, n, b, mc):
     for v, gr in outs[1:]:
         _assert_close(v, outs[0][0], "value across paths", rtol=1e-12, atol=1e-14)
         _assert_close(gr, outs[0][1], "gradient across paths", rtol=1e-10, atol=1e-13)
+
+
+def test_host_buffer_entry_equals_forward_autograd():
+    """prb_mc_value_grad_host (pinned host buffers in and out, one call) == forward + autograd on device tensors, bit for bit,
+    EMA state included; also with pageable host memory."""
+    g = _problem(300, 128)
+    theta = make_theta(6)
+    pr_a = product_mc_pr(g, DEV)
+    X = theta.to(DEV).requires_grad_(True)
+    val = pr_a(X)
+    grad = torch.autograd.grad(val.sum(), X)[0]
+    for pinned in (True, False):
+        pr_b = product_mc_pr(g, DEV)
+        th = theta.clone().pin_memory() if pinned else theta.clone()
+        v_h = torch.empty(6, dtype=torch.float64)
+        g_h = torch.empty(6, 1, 13, dtype=torch.float64)
+        if pinned:
+            v_h, g_h = v_h.pin_memory(), g_h.pin_memory()
+        pr_b.value_and_grad_host(th, v_h, g_h, device=DEV)
+        assert torch.equal(v_h, val.detach().cpu()) and torch.equal(g_h, grad.cpu())
+        assert torch.equal(pr_a._ma_state, pr_b._ma_state)
+    v_only = torch.empty(6, dtype=torch.float64)
+    pr_c = product_mc_pr(g, DEV)
+    pr_c.value_and_grad_host(theta.clone(), v_only, None, device=DEV)
+    assert torch.equal(v_only, val.detach().cpu())
