@@ -89,12 +89,8 @@ def ours(c, g, repeats=3):
             pr = product_mc_pr(g, DEV, acq=acq)
         cand, vals = B.optimize_acqf(pr, bounds, q=1, num_restarts=20, raw_samples=1024, options=opts, stochastic=True,
                                      return_best_only=False)
-        final = pr.sample_candidates(cand)
-        if pr.one_hot_to_numeric is not None:
-            final = pr.one_hot_to_numeric(final)
-        with torch.no_grad():
-            best = acq(final).argmax()
-        final[best].cpu()
+        chosen, _ = B.finalize_candidates(pr, cand, seed=rep)  # device: sample + numeric map + base-AF re-score + argmax
+        chosen.cpu()
         torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
     return sorted(times[1:])[len(times[1:]) // 2]
