@@ -83,8 +83,9 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ W, 
     const double piv = colA[buf][c];
     const bool ok = piv > 0.0;
     if (!ok && tid == 0) atomicCAS(info, 0, 1 + k * CB + c);
-    // 1 / sqrt(pivot) straight from a single-precision seed and two Newton steps (FP64 dependent-issue latency is ~40 cycles
-    // on this part: sqrt followed by a divide was 2/3 of the step), then d = pivot * inv
+    // 1 / sqrt(pivot) straight from a single-precision seed and two Newton steps, then d = pivot * inv: one ~75-cycle seed +
+    // seven 8-cycle FP64 ops on the step's critical path instead of sqrt (~79) followed by a divide (~59)
+    // (profiles/r02_fp64_latency.txt)
     const double pv = ok ? piv : 1.0;
     double inv = double(rsqrtf(__double2float_rn(pv)));
     const double hp = 0.5 * pv;
@@ -100,16 +101,31 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ W, 
       lc[j] = (4 * tc + j > c) ? colA[buf][4 * tc + j] * inv : 0.0;
       xr[j] = rowX[buf][4 * tc + j] * inv;
     }
+    // Unconditional updates: lr is zero for finished rows, lc for finished columns, xr beyond column c -- and entries above
+    // the diagonal are never read or stored -- so no per-element predicate is needed (they were half of the instructions).
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int r = 4 * tr + i, cc = 4 * tc + j;
-        if (cc > c && r >= cc) a[i][j] = fma(-lr[i], lc[j], a[i][j]);
-        if (cc == c) a[i][j] = (r > c) ? lr[i] : (r == c ? d : 0.0);
-        if (r > c) x[i][j] = fma(-lr[i], xr[j], x[i][j]);
-        if (r == c) x[i][j] = xr[j];
+        a[i][j] = fma(-lr[i], lc[j], a[i][j]);
+        x[i][j] = fma(-lr[i], xr[j], x[i][j]);
       }
+    if (tc == cq) {  // column c of L is final: scaled entries below the pivot, the pivot's square root on the diagonal
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j == cm) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a[i][j] = (4 * tr + i > c) ? lr[i] : (4 * tr + i == c ? d : a[i][j]);
+        }
+    }
+    if (tr == cq) {  // row c of X is final
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i == cm) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) x[i][j] = xr[j];
+        }
+    }
   }
   double* dv = Dinv + size_t(k) * CB * CB;
 #pragma unroll

@@ -285,8 +285,8 @@ bool build_grad_group(const DevSpec& spec, uint64_t diffmask, GradGroup* out) {
 }
 
 static_assert(KS_COLS % 4 == 0, "double4 loads of the kernel-input tile");
-constexpr int KQ_NC = 4;  // columns evaluated together by a thread: FP64 latency on this part needs ILP x warps >= ~40 per
-                          // sub-partition (one chain per thread reached a third of the FP64 pipe)
+constexpr int KQ_NC = 4;  // columns evaluated together by a thread: amortises the per-dim loads and loop overhead over four
+                          // independent distance / sqrt / exp chains
 template <bool WITH_Q>
 __global__ void __launch_bounds__(KS_ROWS) kstar_q_kernel(const DevSpec spec, const GradGroup gq,
                                                            const double* __restrict__ Xtr, int n, int Kp,
@@ -1454,13 +1454,23 @@ __global__ void __launch_bounds__(FINISH_THREADS) sep_step_finish_kernel(
   grid_dep_wait();
   const int bi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t c0 = size_t(bi) * mc;
-  // everything that depends on the pre-call optimiser / EMA state is read before this CTA signals completion
-  double baseline = 0.0;
-  if (estimator == PRB_EST_REINFORCE_MA && ma_state != nullptr) {
-    const double cnt = ma_state[0];
-    if (cnt != 0.0) baseline = ma_state[1] / (1.0 - pow(0.7, cnt));
+  // Everything that depends on the pre-call optimiser / EMA state is read before this CTA signals completion.  The three
+  // pow() calls (EMA bias correction of the baseline, Adam's two bias corrections) are long dependent chains (microseconds
+  // each): ONE thread of the last warp evaluates them while the other warps run the reductions; the baseline enters the
+  // score-function sums only afterwards (sum_i (a_i - beta)(z_i - p) = sum_i a_i (z_i - p) - beta sum_i (z_i - p)).
+  __shared__ double pre_s[3];                                  // baseline, 1 - 0.9^t, 1 - 0.999^t
+  __shared__ double s1_s[PRB_MAX_DIMS], s2_s[PRB_MAX_DIMS];    // per discrete column: sum a (z - p), sum (z - p)
+  if (warp == FINISH_THREADS / 32 - 1 && lane == 0) {
+    double baseline = 0.0;
+    if (estimator == PRB_EST_REINFORCE_MA && ma_state != nullptr) {
+      const double cnt = ma_state[0];
+      if (cnt != 0.0) baseline = ma_state[1] / (1.0 - pow(0.7, cnt));
+    }
+    pre_s[0] = baseline;
+    const double t_step = step_ptr ? double(*step_ptr + 1) : 1.0;
+    pre_s[1] = theta != nullptr ? 1.0 - pow(0.9, t_step) : 1.0;
+    pre_s[2] = theta != nullptr ? 1.0 - pow(0.999, t_step) : 1.0;
   }
-  const double t_step = step_ptr ? double(*step_ptr + 1) : 1.0;
   const double go = (need_grad && grad_out) ? grad_out[bi] : 1.0;
   // S_part is [mtiles][slots][ncols_pad]: the separable path stores one slot per continuous dim (slot = index in dm), the
   // generic gradient contraction one slot per kernel-input column (slot = the column itself).  With many row blocks (the
@@ -1513,23 +1523,40 @@ __global__ void __launch_bounds__(FINISH_THREADS) sep_step_finish_kernel(
       // discrete columns: integers first, then the one-hot columns (the order of `discrete_indices`, input.py:574-597)
       const int kd = task - 1 - n_cont_tasks;
       const double p = prob[size_t(bi) * sp.n_disc + kd];
+      double tz[FIN_ILP];
+#pragma unroll
+      for (int q = 0; q < FIN_ILP; ++q) tz[q] = 0.0;
       for (int i0 = lane; i0 < mc; i0 += 32 * FIN_ILP) {
 #pragma unroll
         for (int q = 0; q < FIN_ILP; ++q) {
           const int i = i0 + 32 * q;
           if (i < mc) {
-            const double zi = double(z[(c0 + i) * sp.n_disc + kd]);
-            tc[q] += ((a[c0 + i] - baseline) * (zi - p)) / sp.tau;
+            const double zp = double(z[(c0 + i) * sp.n_disc + kd]) - p;
+            tc[q] = fma(a[c0 + i], zp, tc[q]);
+            tz[q] += zp;
           }
         }
       }
+      double t2 = 0.0;
 #pragma unroll
-      for (int q = 0; q < FIN_ILP; ++q) t += tc[q];
+      for (int q = 0; q < FIN_ILP; ++q) {
+        t += tc[q];
+        t2 += tz[q];
+      }
       t = warp_sum(t);
-      if (lane == 0) g_s[kd < sp.n_int ? sp.int_cols[kd] : cat0 + (kd - sp.n_int)] = go * (t / double(mc));
+      t2 = warp_sum(t2);
+      if (lane == 0) {
+        s1_s[kd] = t;
+        s2_s[kd] = t2;
+      }
     }
   }
   __syncthreads();
+  if (need_grad && tid < sp.n_disc) {
+    const int kd = tid;
+    const double sc = (s1_s[kd] - pre_s[0] * s2_s[kd]) / sp.tau;
+    g_s[kd < sp.n_int ? sp.int_cols[kd] : cat0 + (kd - sp.n_int)] = go * (sc / double(mc));
+  }
   if (need_grad && tid < dm.n) {
     double t = csum[tid][0];
     for (int part = 1; part < nsplit; ++part) t += csum[tid][part];
@@ -1547,8 +1574,7 @@ __global__ void __launch_bounds__(FINISH_THREADS) sep_step_finish_kernel(
       const double vi = adam_v[idx] * b2 + (1.0 - b2) * g * g;
       adam_m[idx] = mi;
       adam_v[idx] = vi;
-      const double bc1 = 1.0 - pow(b1, t_step);
-      const double bc2 = 1.0 - pow(b2, t_step);
+      const double bc1 = pre_s[1], bc2 = pre_s[2];
       theta[idx] = theta[idx] - (lr / bc1) * (mi / (sqrt(vi) / sqrt(bc2) + eps));
     }
   }
