@@ -25,6 +25,7 @@ const EnvKnobs& env_knobs() {
     e.panel_mb = getenv("PRB_PANEL_MB") ? atol(getenv("PRB_PANEL_MB")) : 0;
     e.force_bn = getenv("PRB_BN") ? atoi(getenv("PRB_BN")) : 0;
     e.group_waves = getenv("PRB_GROUP_WAVES") ? atoi(getenv("PRB_GROUP_WAVES")) : 4;
+    e.mixed_order = getenv("PRB_MIXED_ORDER") ? atoi(getenv("PRB_MIXED_ORDER")) : 1;
     return e;
   }();
   return k;

@@ -34,6 +34,7 @@
 // one tile per CTA -- merely wrapping the tile body in a loop costs 4 % through ptxas' scheduling of the hot loop -- and
 // 4.66 ms persistent.  Moving the per-dim CTA barriers of the UPPER_GRAD epilogue into one also lost (2.12 -> 2.15 ms),
 // as did unrolling the k-tile loop by 2 or 4 (4.49 / 4.48 ms).
+// (That reading of the dispatch was wrong -- see the per-CTA trace below: one tile per CTA runs in lockstep too.)
 // The kernel as it stands is a fragile local optimum of ptxas' register allocation; the next step needs the main loop
 // pinned down (hand-scheduled or CUTLASS-style explicit pipelining) before restructuring around it.
 // Round 2 (tools/microbench/fp64_lds_mix.py, profiles/r02_fp64_lds_mix.txt): the SASS of the full k-tile body is already at
@@ -44,6 +45,19 @@
 // 32-column / 4-warp / 3-stage variant with THREE independent CTAs per SM (160-168 registers, template parameters NST / NAH /
 // MINB) is SLOWER (4.71 vs 4.38 ms per step at 65 536 columns; 0.72 vs 0.60 ms at 8 192) -- twice the CTAs means twice the
 // prologues, epilogues and A-tile fetches, and that costs more than a third warp per sub-partition recovers.
+//
+// Per-CTA clock trace (PRB_TRACE_CTAS build + tools/debug/cta_trace.py, profiles/r02_cta_trace.txt): with the plain
+// heavy-first tile order the two CTAs of an SM -- and all SMs -- run in LOCKSTEP for the whole launch (equal-length tiles
+// that start together share the pipe evenly, end together, and so do their successors): both are outside their k loop at
+// the same time for 6.1 % (lower) / 7.6 % (upper) of the launch, against 1.2 % / 4.0 % with exactly one inside, and inside
+// the loop the pair keeps the pipe 96 % busy.  A lone 4-warp CTA, however, only reaches ~62 % of the pipe (one CTA per SM:
+// 6.20 vs 4.33 ms per step), so breaking the lockstep recovers less than the idle share: the MIXED tile order (heaviest and
+// lightest row tile of a column tile alternate in the queue; last scheduling group stays heavy-first for the tail) takes
+// the both-outside share to 1.4 % / 3.3 % and the step from 4.370 to 4.326 ms; mixing the last group as well costs more in
+// the tail (4.399 ms).  A start-up stagger of the second CTA on each SM (0.5-2 tile units) decays within a few tiles
+// (4.353 ms) and adds nothing on top of the mixed order.  Generating the operand by a GATHER from a per-restart table
+// kc[b][j] * tab[h] (no DMUL, no table LDS in the consumer warps) changes nothing (4.370 vs 4.373 ms): the `math` stalls of
+// the generator are time the pipe spends on the sibling CTA's DMMAs, not lost time.
 //
 // Four modes (template):
 //   LOWER_GEN   the B operand k*[col, k] = kc[b(col), k] * tab[popc(z[col] ^ Z[k])] is GENERATED into shared memory by the
@@ -83,7 +97,32 @@ constexpr size_t T_SMEM_BYTES = tma_smem_bytes(128);
 
 enum { MODE_LOWER_GEN = 0, MODE_LOWER_TMA = 1, MODE_UPPER_W = 2, MODE_UPPER_GRAD = 3, MODE_UPPER_GRADQ = 4 };
 
+// PRB_TRACE_CTAS=1 builds record, per CTA, {smid, clock64 at entry, after the first full-barrier wait, after the k loop, at
+// exit} into the buffer set with prb_debug_set_cta_trace (tools/debug/cta_trace.py); product builds carry none of it.
+#ifndef PRB_TRACE_CTAS
+#define PRB_TRACE_CTAS 0
+#endif
+#if PRB_TRACE_CTAS
+static long long* g_cta_trace = nullptr;
+static int g_cta_trace_launch = 0;
+constexpr int CTA_TRACE_STRIDE = 8 * 16384;
+extern "C" void prb_debug_set_cta_trace(long long* buf) {
+  g_cta_trace = buf;
+  g_cta_trace_launch = 0;
+}
+#define CTA_TRACE(slot)                                                        \
+  do {                                                                         \
+    if (p.trace != nullptr && tid == 0) p.trace[size_t(blockIdx.x) * 8 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define CTA_TRACE(slot) \
+  do {                  \
+  } while (0)
+#endif
+
 struct TmaGemmParams {
+  long long* trace = nullptr;
+  int mixed_groups = 0;    // leading scheduling groups that use the mixed (heavy / light alternating) order
   int mtiles, ntiles, Kp, ncols_pad;
   int ngroup;  // column tiles per scheduling group (see the launch order in the kernel)
   // lower epilogue
@@ -157,13 +196,36 @@ __global__ void __launch_bounds__(THREADS, MINB)
   // back to back (heavy first: lower -> largest row block first, upper -> smallest row block first), so the B-operand
   // columns that the row tiles of one column tile re-read (the v panel in the upper product, the k* panel on the generic
   // path) are still in L2 instead of coming from HBM once per row tile.  p.ngroup = ntiles: plain row-tile-major order.
+  CTA_TRACE(1);
+#if PRB_TRACE_CTAS
+  if (p.trace != nullptr && tid == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.trace[size_t(blockIdx.x) * 8] = smid;
+  }
+#endif
   const int t = blockIdx.x;
   const int per_group = p.ngroup * p.mtiles;
   const int grp_i = t / per_group;
   const int r_in = t - grp_i * per_group;
   const int gcols = min(p.ngroup, p.ntiles - grp_i * p.ngroup);  // column tiles in this (possibly last, shorter) group
-  const int mi_sched = r_in / gcols;
-  const int nt = grp_i * p.ngroup + (r_in - mi_sched * gcols);
+  int mi_sched = r_in / gcols;
+  int nt = grp_i * p.ngroup + (r_in - mi_sched * gcols);
+  if (grp_i < p.mixed_groups) {
+    // Mixed order (all groups but the last): heaviest and lightest remaining row tile of a column tile alternate in the
+    // queue, so the CTAs that share an SM -- and the SMs among each other -- differ in length and drift out of phase.  In
+    // the plain heavy-first order whole waves have equal length: every CTA pair starts, stores and restarts in lockstep
+    // (tools/debug/cta_trace.py), the FP64 pipe idles through both epilogues and the stores of all SMs hit L2 at once.
+    const int pair = r_in / (2 * gcols);
+    if (pair < p.mtiles / 2) {
+      const int rem = r_in - pair * 2 * gcols;
+      mi_sched = (rem & 1) ? p.mtiles - 1 - pair : pair;
+      nt = grp_i * p.ngroup + (rem >> 1);
+    } else {  // odd number of row tiles: the middle one comes last
+      mi_sched = p.mtiles / 2;
+      nt = grp_i * p.ngroup + (r_in - (p.mtiles / 2) * 2 * gcols);
+    }
+  }
   const int mt = UPPER ? mi_sched : (p.mtiles - 1 - mi_sched);
   const int m0 = mt * T_BM;
   const int n0 = nt * BN;
@@ -332,6 +394,9 @@ __global__ void __launch_bounds__(THREADS, MINB)
     }
     const int s = kt % NST;
     mbar_wait(&full[s], (kt / NST) & 1);
+#if PRB_TRACE_CTAS
+    if (kt == 0) CTA_TRACE(2);
+#endif
     const double* pa = stages + s * STAGE_DOUBLES;
     const double* pb = pa + T_OPER_DOUBLES + fb_off;
     const int q0 = kbeg + kt * T_BK - m0;  // offset of this k-tile inside the tile's diagonal block
@@ -380,6 +445,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
     if (GEN && nk < num_k) gen_store(nk);
   }
   __syncthreads();  // every stage consumed, no TMA in flight: the stage buffers are free for the epilogue
+  CTA_TRACE(3);
 
   // ---- epilogues ---------------------------------------------------------------------------------------------------
   int rows[4];  // global row of accumulator sub-tile i for this lane
@@ -395,6 +461,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
 #pragma unroll
       for (int j = 0; j < TJ; ++j) *reinterpret_cast<double2*>(crow + 8 * j) = make_double2(acc[i][j][0], acc[i][j][1]);
     }
+    CTA_TRACE(4);
     return;
   }
 
@@ -483,6 +550,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
       }
       __syncthreads();
     }
+    CTA_TRACE(4);
     return;
   }
 
@@ -554,11 +622,19 @@ __global__ void __launch_bounds__(THREADS, MINB)
         if (!in_group) p.S_part[(size_t(mt) * p.d_k + dim) * p.ncols_pad + n0 + tid] = 0.0;
       }
     }
+    CTA_TRACE(4);
     return;
   }
 
   if constexpr (!UPPER) {
-  // lower: V^T[col, row]; 8 lanes (frag_r = 0..7) write 64 contiguous bytes per column
+  // lower: V^T[col, row].  4-warp variants: the tile is staged in the (now free) stage buffers, one 1 KB row of V^T per
+  // column at a pitch of 132 doubles (the four frag_k groups of a warp land on disjoint bank halves), and leaves as 64 bulk
+  // shared->global copies that the TMA engine drains while the CTA finishes -- direct 8-byte stores (eight 32-byte sectors
+  // per warp instruction, 128 instructions per thread) measured ~6 400 cycles per CTA with the FP64 pipe idle.
+  // 8-warp variants: 8 lanes (frag_r = 0..7) write 64 contiguous bytes per column.
+  constexpr bool BULK_EPI = (BN == 64 && THREADS == 128);
+  constexpr int VT_PITCH = 132;
+  double* vt = stages + 512;  // behind red[5 * BN]
   double nrm[TJ][2];
 #pragma unroll
   for (int j = 0; j < TJ; ++j) nrm[j][0] = nrm[j][1] = 0.0;
@@ -571,7 +647,12 @@ __global__ void __launch_bounds__(THREADS, MINB)
       for (int e = 0; e < 2; ++e) {
         const int col = col_base + 8 * j + e;
         const double v = acc[i][j][e];
-        if (p.C) p.C[size_t(col) * p.ldc + row] = v;
+        if (p.C) {
+          if constexpr (BULK_EPI)
+            vt[(col - n0) * VT_PITCH + (row - m0)] = v;
+          else
+            p.C[size_t(col) * p.ldc + row] = v;
+        }
         if (row == p.special_row) {
           p.mu_dot[col] = v;
           red[4 * BN + col - n0] = v;
@@ -597,7 +678,12 @@ __global__ void __launch_bounds__(THREADS, MINB)
 #pragma unroll
       for (int e = 0; e < 2; ++e) red[wm * BN + wn * (8 * TJ) + 8 * j + 2 * frag_k + e] = nrm[j][e];
   }
+  if (BULK_EPI && p.C) fence_proxy_async_smem();
   __syncthreads();
+  if (BULK_EPI && p.C && tid < BN) {
+    bulk_store_1d(p.C + size_t(n0 + tid) * p.ldc + m0, vt + tid * VT_PITCH, T_BM * sizeof(double));
+    bulk_commit();
+  }
   if (tid < BN) {
     const double s = ((red[tid] + red[BN + tid]) + red[2 * BN + tid]) + red[3 * BN + tid];
     p.norm_part[size_t(mt) * p.ncols_pad + n0 + tid] = s;
@@ -609,6 +695,8 @@ __global__ void __launch_bounds__(THREADS, MINB)
       p.acq_dvar[n0 + tid] = d_var;
     }
   }
+  if (BULK_EPI && p.C && tid < BN) bulk_wait_read0();
+  CTA_TRACE(4);
   }
 }
 
@@ -677,6 +765,9 @@ static int pick_bn(const Model& m, int ncols_pad, bool upper) {
 
 static void fill_common(TmaGemmParams& p, const Model& m, int ncols_pad, bool upper, int bn = T_BN) {
   memset(&p, 0, sizeof(p));
+#if PRB_TRACE_CTAS
+  p.trace = g_cta_trace ? g_cta_trace + size_t(g_cta_trace_launch++) * CTA_TRACE_STRIDE : nullptr;
+#endif
   p.mtiles = (upper ? m.Mp2 : m.Mp1) / T_BM;
   p.ntiles = ncols_pad / bn;
   p.Kp = m.Kp;
@@ -690,6 +781,9 @@ static void fill_common(TmaGemmParams& p, const Model& m, int ncols_pad, bool up
   int g = waves > 0 ? (waves * slots) / (p.mtiles > 0 ? p.mtiles : 1) : p.ntiles;
   if (g < 1) g = 1;
   p.ngroup = g < p.ntiles ? g : p.ntiles;
+  const int ngroups = (p.ntiles + p.ngroup - 1) / p.ngroup;
+  const int mixed = env_knobs().mixed_order;  // 0 off, 1 all groups but the last, 2 every group
+  p.mixed_groups = (bn == 64 && mixed > 0) ? (mixed == 2 ? ngroups : ngroups - 1) : 0;
 }
 
 static void fill_sep(TmaGemmParams& p, const Model& m, const SepArgs& sa) {

@@ -73,6 +73,7 @@ struct EnvKnobs {
   long panel_mb;        // PRB_PANEL_MB: column-panel budget override (0 = default)
   int force_bn;         // PRB_BN: column-tile width override of the separable products (0 = pick by tile count)
   int group_waves;      // PRB_GROUP_WAVES: scheduling-group size in waves of CTAs (default 4; 0 = row-tile-major)
+  int mixed_order;      // PRB_MIXED_ORDER: heavy / light alternating tile order (1: all groups but the last, 2: all, 0: off)
 };
 const EnvKnobs& env_knobs();
 
