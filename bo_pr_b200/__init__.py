@@ -14,7 +14,10 @@ from .acquisition import (  # noqa: F401
 )
 from .input import (  # noqa: F401
     AnalyticProbabilisticReparameterizationInputTransform,
+    CategoricalSpec,
     ChainedInputTransform,
+    LatentCategoricalEmbedding,
+    LatentCategoricalSpec,
     MCProbabilisticReparameterizationInputTransform,
     Normalize,
     OneHotToNumeric,

@@ -60,7 +60,7 @@ class PrbSpaceDesc(C.Structure):
                 ("int_cols", C.c_int32 * PRB_MAX_DIMS), ("int_lo", C.c_double * PRB_MAX_DIMS),
                 ("int_hi", C.c_double * PRB_MAX_DIMS), ("cat_start", C.c_int32 * PRB_MAX_CAT),
                 ("cat_card", C.c_int32 * PRB_MAX_CAT), ("tau", C.c_double), ("raw_integer_space", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("latent_dim", C.c_int32 * PRB_MAX_CAT), ("latent_tables", C.c_void_p)]
 
 
 class PrbAcqDesc(C.Structure):

@@ -64,6 +64,9 @@ class AnalyticAcquisitionFunction(AcquisitionFunction):
     def forward(self, X: Tensor) -> Tensor:
         if X.shape[-2] != 1:
             raise AssertionError(f"Expected X to be `batch_shape x q=1 x d`, but got X with shape {tuple(X.shape)}.")
+        tf = getattr(self.model, "input_transform", None)
+        if tf is not None:  # LatentCategoricalEmbedding: numeric layout -> kernel input (torch gather, differentiable in
+            X = tf.transform(X)  # the non-categorical columns)
         return _PointsFn.apply(X.squeeze(-2), self.state, self.acq_desc())
 
 

@@ -177,6 +177,21 @@ int make_space(const prb_space_desc* s, DevSpace* out) {
   if (expect != s->d) return PRB_ERR_INVALID;  // one-hot blocks must run contiguously to the last column
   out->n_disc = n_disc;
   out->d_k = (s->apply_numeric && s->n_cat > 0) ? s->cat_start[0] + s->n_cat : s->d;
+  if (s->latent_tables != nullptr && s->n_cat > 0) {
+    if (!s->apply_numeric) return PRB_ERR_INVALID;
+    int col = 0, off = 0;
+    for (int j = 0; j < s->n_cat; ++j) {
+      if (s->latent_dim[j] < 1 || s->latent_dim[j] > PRB_MAX_DIMS) return PRB_ERR_INVALID;
+      out->latent_dim[j] = s->latent_dim[j];
+      out->latent_col[j] = col;
+      out->latent_off[j] = off;
+      col += s->latent_dim[j];
+      off += s->latent_dim[j] * s->cat_card[j];
+    }
+    out->latent_tab = s->latent_tables;
+    out->d_k = s->cat_start[0] + col;
+    if (out->d_k > PRB_MAX_DIMS) return PRB_ERR_UNSUPPORTED;
+  }
   int nc = 0;
   for (int c = 0; c < s->d; ++c)
     if (!is_disc[c]) out->cont_cols[nc++] = c;

@@ -207,6 +207,20 @@ __device__ __forceinline__ double pr_sample_int(const DevSpace& sp, const double
   return tn;
 }
 
+// Kernel-input columns of categorical j on the numeric layout: the category index (OneHotToNumeric, input.py:69-88) or,
+// with a latent embedding, row `cat` of the categorical's table (EmbeddingTransform.transform, input.py:784-802).
+__device__ __forceinline__ void write_categorical_input(const DevSpace& sp, double* __restrict__ xr, int numeric_start,
+                                                        int j, int cat) {
+  if (sp.latent_tab == nullptr) {
+    xr[numeric_start + j] = double(cat);
+    return;
+  }
+  const int e = sp.latent_dim[j];
+  const double* row = sp.latent_tab + sp.latent_off[j] + size_t(cat) * e;
+  double* dst = xr + numeric_start + sp.latent_col[j];
+  for (int t = 0; t < e; ++t) dst[t] = row[t];
+}
+
 // One (restart, MC sample i) of the sampler.  `th` = the restart's theta row, ps / offs from pr_restart_probs.
 // Row outputs (any may be NULL): xr [d_k] kernel input, tr [d] tilde_x, zr [n_disc] rounding components; returns the bit
 // code over the binary dims selected by `bm`.
@@ -256,7 +270,7 @@ __device__ __forceinline__ uint32_t pr_sample_point(const DevSpace& sp, const do
       if (xr && !sp.apply_numeric) xr[s + k] = oh;
       if (zr) zr[zpos + k] = (k == cat) ? 1 : 0;
     }
-    if (xr && sp.apply_numeric) xr[numeric_start + j] = double(cat);
+    if (xr && sp.apply_numeric) write_categorical_input(sp, xr, numeric_start, j, cat);
     zpos += card;
   }
   return bits;

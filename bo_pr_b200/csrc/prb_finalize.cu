@@ -69,7 +69,7 @@ __global__ void sample_candidates_kernel(const DevSpace sp, const double* __rest
       if (xr) xr[s + k] = oh;
       if (kr && !sp.apply_numeric) kr[s + k] = oh;
     }
-    if (kr && sp.apply_numeric) kr[numeric_start + j] = double(cat);
+    if (kr && sp.apply_numeric) write_categorical_input(sp, kr, numeric_start, j, cat);
   }
 }
 

@@ -50,6 +50,12 @@ struct DevSpace {
   int32_t cat_card[PRB_MAX_CAT];
   int32_t cont_cols[PRB_MAX_DIMS];  // theta columns that are continuous (same index in the kernel-input layout)
   double tau;
+  // latent categorical embedding (latent_tab == nullptr: off): categorical j -> latent_dim[j] kernel-input columns starting
+  // at cat_start[0] + latent_col[j], read from row `category` of the table at latent_tab + latent_off[j]
+  int32_t latent_dim[PRB_MAX_CAT];
+  int32_t latent_col[PRB_MAX_CAT];
+  int32_t latent_off[PRB_MAX_CAT];
+  const double* latent_tab;
 };
 
 struct DevAcq {

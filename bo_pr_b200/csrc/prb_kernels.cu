@@ -157,7 +157,7 @@ __global__ void analytic_build_kernel(const DevSpace sp, const double* __restric
     P *= sel * (1.0 / sum);
     if (xr) {
       if (sp.apply_numeric) {
-        xr[numeric_start + j] = double(cat);
+        write_categorical_input(sp, xr, numeric_start, j, cat);
       } else {
         for (int k = 0; k < card; ++k) xr[s + k] = (k == cat) ? 1.0 : 0.0;
       }

@@ -1,6 +1,7 @@
 """PR input transforms backed by the CUDA sampler.
 
-API mirror of ``discrete_mixed_bo/input.py`` for the PR path: ``OneHotToNumeric`` (30-117),
+API mirror of ``discrete_mixed_bo/input.py`` for the PR path: ``OneHotToNumeric`` (30-117), ``LatentCategoricalEmbedding``
+(766-952; inside a PR call the device sampler performs the table lookup, see ``prb_space_desc.latent_tables``),
 ``AnalyticProbabilisticReparameterizationInputTransform`` (245-502), ``MCProbabilisticReparameterizationInputTransform``
 (505-763), plus the BoTorch ``InputTransform`` / ``Normalize`` / ``ChainedInputTransform`` surface they plug into.
 The discrete sampling, probabilities and enumeration run in ``libprb200`` (``pr_sample_kernel``,
@@ -10,8 +11,10 @@ ops on the device (inside the fused PR call the kernels do both).
 from __future__ import annotations
 
 import ctypes as C
+import math
 from collections import OrderedDict
-from typing import Dict, List, Optional
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
 from torch import Tensor
@@ -111,7 +114,8 @@ def _categorical_layout(categorical_features: Optional[Dict[int, int]]):
 
 def make_space_desc(dim: int, integer_indices, integer_bounds: Optional[Tensor],
                     categorical_features: Optional[Dict[int, int]], tau: float, apply_numeric: bool = False,
-                    raw_integer_space: bool = False) -> capi.PrbSpaceDesc:
+                    raw_integer_space: bool = False, latent: Optional["LatentCategoricalEmbedding"] = None,
+                    device=None) -> capi.PrbSpaceDesc:
     ints = [int(i) for i in (integer_indices if integer_indices is not None else [])]
     starts, ends = _categorical_layout(categorical_features)
     if dim > capi.PRB_MAX_DIMS:
@@ -131,6 +135,18 @@ def make_space_desc(dim: int, integer_indices, integer_bounds: Optional[Tensor],
         if e - s > capi.PRB_MAX_CARD:
             raise NotImplementedError(f"categorical cardinality {e - s} > {capi.PRB_MAX_CARD}")
         sp.cat_start[j], sp.cat_card[j] = s, e - s
+    if latent is not None:
+        if not sp.apply_numeric:
+            raise NotImplementedError("a latent categorical embedding needs apply_numeric=True (OneHotToNumeric first)")
+        want = [starts[0] + j for j in range(len(starts))]
+        if latent.categ_idcs.tolist() != want or [c.num_categories for c in latent._specs] != [e - s for s, e in
+                                                                                                zip(starts, ends)]:
+            raise ValueError("the latent embedding's categorical specs do not match the numeric layout of the search space")
+        flat, dims = latent.device_tables(device)
+        for j, e in enumerate(dims):
+            sp.latent_dim[j] = int(e)
+        sp.latent_tables = flat.data_ptr()
+        sp._keepalive = flat  # the descriptor points into this tensor
     return sp
 
 
@@ -182,6 +198,123 @@ class OneHotToNumeric(InputTransform, Module):
         one_hots = [torch.nn.functional.one_hot(X[..., idx].long(), num_classes=card).to(X)
                     for idx, card in sorted(self.categorical_features.items(), key=lambda kv: kv[0])]
         return torch.cat([X[..., : min(self.categorical_features.keys())], *one_hots], dim=-1)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Latent categorical embedding (kernel_type "mixed_latent")
+# ----------------------------------------------------------------------------------------------------------------------
+@dataclass
+class CategoricalSpec:
+    """``input.py:766-769``."""
+    idx: int
+    num_categories: int
+
+
+@dataclass
+class LatentCategoricalSpec(CategoricalSpec):
+    """``input.py:772-774``."""
+    latent_dim: int
+
+
+class LatentCategoricalEmbedding(InputTransform, Module):
+    """``input.py:777-952``: every categorical column (an integer code, i.e. the ``OneHotToNumeric`` layout) is replaced by
+    the row of a learned ``num_categories x latent_dim`` table; the output is ``[non-categorical columns, embeddings in
+    spec order]``.  The tables are parameters named ``raw_latent_emb_tables_{idx}`` as in the reference (fitted with the
+    GP hyper-parameters, outside the hot path); ``get_emb_table`` pins row 0 to the origin and entry ``[1, 0]`` to zero
+    (``input.py:902-909``).  Applied on its own this is a torch gather; inside a PR call the sampler kernel writes the
+    embedding rows straight into the kernel input (``device_tables`` feeds ``prb_space_desc.latent_tables``)."""
+
+    def __init__(self, categorical_specs: Sequence[LatentCategoricalSpec], dim: int, transform_on_train: bool = True,
+                 transform_on_eval: bool = True, transform_on_preprocess: bool = False,
+                 transform_on_fantasize: bool = False, eps: float = 1e-7) -> None:
+        super().__init__()
+        self._eps = eps
+        self.dim = int(dim)
+        self.transform_on_train = transform_on_train
+        self.transform_on_eval = transform_on_eval
+        self.transform_on_preprocess = transform_on_preprocess
+        self.transform_on_fantasize = transform_on_fantasize
+        self._emb_dim = 0
+        self._specs: List[LatentCategoricalSpec] = []
+        categ_idcs: List[int] = []
+        for c in categorical_specs:
+            idx = int(c.idx) + (self.dim if c.idx < 0 else 0)
+            if not 0 <= idx < self.dim:
+                raise ValueError(f"categorical index {c.idx} is out of range for dim {dim}")
+            categ_idcs.append(idx)
+            self._specs.append(LatentCategoricalSpec(idx=idx, num_categories=int(c.num_categories),
+                                                     latent_dim=int(c.latent_dim)))
+            # initial table: quasi-random standard-normal rows (the reference draws them with BoTorch's
+            # draw_sobol_normal_samples; the values are a starting point for the fit, not part of the path's arithmetic)
+            u = SobolEngine(int(c.latent_dim), scramble=True, seed=idx).draw(int(c.num_categories), dtype=torch.float64)
+            v = 0.5 + (1.0 - 1e-10) * (u - 0.5)
+            self.register_parameter(f"raw_latent_emb_tables_{idx}",
+                                    torch.nn.Parameter(math.sqrt(2.0) * torch.erfinv(2.0 * v - 1.0)))
+            self._emb_dim += int(c.latent_dim)
+        self.register_buffer("categ_idcs", torch.tensor(categ_idcs, dtype=torch.long))
+        mask = torch.ones(self.dim, dtype=torch.bool)
+        mask[self.categ_idcs] = False
+        self.register_buffer("non_categ_mask", mask)
+        self._dev_tables: Optional[Tuple[tuple, Tensor]] = None
+
+    def get_emb_table(self, idx: int) -> Tensor:
+        raw = getattr(self, f"raw_latent_emb_tables_{idx}")
+        with torch.no_grad():
+            if bool((raw[0] != 0).any()):
+                raw[0] = 0
+            if raw.shape[1] > 1 and raw.shape[0] > 1 and bool(raw[1, 0] != 0):
+                raw[1, 0] = 0
+        return raw
+
+    def transform(self, X: Tensor) -> Tensor:
+        parts = [X[..., self.non_categ_mask]]
+        for idx in self.categ_idcs.tolist():
+            table = self.get_emb_table(idx).to(X)
+            codes = X[..., idx].reshape(-1).long()
+            parts.append(table.index_select(0, codes).reshape(*X.shape[:-1], table.shape[-1]))
+        return torch.cat(parts, dim=-1)
+
+    def transform_bounds(self, bounds: Tensor) -> Tensor:
+        d_cont = self.dim - self.categ_idcs.shape[0]
+        out = torch.zeros(2, d_cont + self._emb_dim, dtype=bounds.dtype, device=bounds.device)
+        out[:, :d_cont] = bounds[:, self.non_categ_mask]
+        out[1, d_cont:] = 1
+        return out
+
+    def untransform(self, X: Tensor, dist_func: Optional[Callable[[Tensor, Tensor, int], Tensor]] = None) -> Tensor:
+        """Nearest-embedding decoding back to integer codes (not differentiable), ``input.py:911-952``."""
+        out = torch.empty(*X.shape[:-1], self.dim, dtype=X.dtype, device=X.device)
+        n_plain = X.shape[-1] - self._emb_dim
+        out[..., self.non_categ_mask] = X[..., :n_plain]
+        start = self.dim - self.categ_idcs.shape[0]
+        for idx in self.categ_idcs.tolist():
+            table = self.get_emb_table(idx).to(X)
+            end = start + table.shape[-1]
+            x = X[..., start:end].unsqueeze(-2)
+            t = table.unsqueeze(-3)
+            dist = dist_func(x, t, start) if dist_func is not None else torch.norm(x - t, dim=-1)
+            out[..., idx] = dist.argmin(dim=-1).to(X.dtype)
+            start = end
+        return out
+
+    # ---- device side ------------------------------------------------------------------------------------------------
+    def fingerprint(self) -> tuple:
+        out = []
+        for idx in self.categ_idcs.tolist():
+            t = getattr(self, f"raw_latent_emb_tables_{idx}")
+            out += [t.data_ptr(), t._version]
+        return tuple(out)
+
+    def device_tables(self, device) -> Tuple[Tensor, List[int]]:
+        """The pinned tables back to back (categorical order, row-major, float64) on ``device`` + their latent dims; cached
+        until a table changes."""
+        fp = (str(device),) + self.fingerprint()
+        if self._dev_tables is None or self._dev_tables[0] != fp:
+            flat = torch.cat([self.get_emb_table(i).detach().to(device=device, dtype=torch.float64).reshape(-1)
+                              for i in self.categ_idcs.tolist()]).contiguous()
+            fp = (str(device),) + self.fingerprint()  # get_emb_table may have pinned entries in place
+            self._dev_tables = (fp, flat)
+        return self._dev_tables[1], [s.latent_dim for s in self._specs]
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -120,8 +120,10 @@ def get_kernel(
 
     ``"mixed"``: ``Scale(M52_ARD(non-binary dims) * M52(binary dims))``; ``"mixed_categorical"``:
     ``Scale(prod) + Scale(sum)`` where -- replicating the reference's second ``prod_kernel *= k`` loop
-    (``kernels.py:90-94``) -- every factor but the first enters the product squared.  ``"mixed_latent"``,
-    ``"ard_combo"`` and ``"iso_combo"`` are outside the hot-path scope and raise.
+    (``kernels.py:90-94``) -- every factor but the first enters the product squared.  ``"mixed_latent"``
+    (``kernels.py:73-84``): ``Scale(M52_ARD(continuous) * M52(binary) * prod_j M52_iso(latent columns of categorical j))``
+    over the ``LatentCategoricalEmbedding`` layout, ``categorical_transformed_features = {first latent column: latent
+    dim}``.  ``"ard_combo"`` and ``"iso_combo"`` are outside the hot-path scope and raise.
     """
     if kernel_type == "mixed_categorical":
         categorical_dims = list(categorical_transformed_features.keys())
@@ -131,9 +133,9 @@ def get_kernel(
             categorical_dims = list(range(start, dim))
         else:
             categorical_dims = []
-    if kernel_type in ("mixed", "mixed_categorical"):
+    if kernel_type in ("mixed", "mixed_categorical", "mixed_latent"):
         cont_dims = sorted(set(range(dim)) - set(binary_dims))
-        if kernel_type == "mixed_categorical":
+        if kernel_type in ("mixed_categorical", "mixed_latent"):
             cont_dims = sorted(set(cont_dims) - set(categorical_dims))
         kernels: List[Kernel] = []
         if len(cont_dims) > 0:
@@ -145,6 +147,12 @@ def get_kernel(
         if kernel_type == "mixed_categorical" and len(categorical_dims) > 0:
             kernels.append(CategoricalKernel(ard_num_dims=len(categorical_dims), active_dims=categorical_dims,
                                              lengthscale_constraint=Interval(1e-3, 20.0)))
+        if kernel_type == "mixed_latent":
+            for start, latent_dim in categorical_transformed_features.items():
+                # one isotropic kernel per set of latent embedding columns
+                kernels.append(MaternKernel(nu=2.5, ard_num_dims=None,
+                                            active_dims=list(range(start, start + latent_dim)),
+                                            lengthscale_constraint=Interval(1e-3, 20.0)))
         prod_kernel = kernels[0]
         for k in kernels[1:]:
             prod_kernel = prod_kernel * k
@@ -157,7 +165,7 @@ def get_kernel(
         return ScaleKernel(prod_kernel) + ScaleKernel(sum_kernel)
     elif kernel_type == "botorch_default":
         return None
-    elif kernel_type in ("mixed_latent", "ard_combo", "iso_combo"):
+    elif kernel_type in ("ard_combo", "iso_combo"):
         raise NotImplementedError(
             f"kernel_type={kernel_type!r} is outside the B200 hot-path scope (no named config uses it).")
     raise ValueError(f"{kernel_type} is not supported.")

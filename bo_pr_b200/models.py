@@ -204,15 +204,19 @@ class FixedNoiseGP(Model):
 
     Hyperparameters are set by assignment on ``covar_module`` / ``mean_module`` (fitting the marginal likelihood is the
     reference's ``fit_gpytorch_model`` step, outside the hot path); call ``refresh()`` after changing them.
-    Model-level input/outcome transforms and multi-output models are not supported (raise)."""
+    ``input_transform`` may be a ``LatentCategoricalEmbedding`` (``kernel_type="mixed_latent"``,
+    ``experiment_utils.py:289-313``): ``train_X`` and ``posterior(X)`` inputs are then in the numeric layout and the device
+    state is built on the embedded inputs.  Other model-level transforms and multi-output models are not supported (raise)."""
 
     num_outputs = 1
 
     def __init__(self, train_X: Tensor, train_Y: Tensor, train_Yvar: Tensor, covar_module=None,
                  outcome_transform=None, input_transform=None, mean_const: float = 0.0):
         super().__init__()
-        if outcome_transform is not None or input_transform is not None:
-            raise NotImplementedError("model-level transforms are outside the B200 hot path")
+        if outcome_transform is not None or (input_transform is not None and not hasattr(input_transform, "get_emb_table")):
+            raise NotImplementedError("model-level transforms other than LatentCategoricalEmbedding are outside the B200 "
+                                      "hot path")
+        self.input_transform = input_transform
         if train_Y.ndim == 2 and train_Y.shape[-1] != 1:
             raise NotImplementedError("multi-output models are outside the B200 hot path")
         if covar_module is None:
@@ -243,6 +247,9 @@ class FixedNoiseGP(Model):
         fp = self._fingerprint()
         if self._state is None or self._state_fp != fp:
             X = self.train_inputs[0]
+            if self.input_transform is not None:
+                with torch.no_grad():
+                    X = self.input_transform.to(X.device).transform(X).contiguous()
             self._state = GPState(X, self.train_targets, kernel_terms(self.covar_module, X.shape[-1]),
                                   self.likelihood.noise, float(self.mean_module.constant))
             self._state_fp = fp
@@ -253,8 +260,10 @@ class FixedNoiseGP(Model):
             raise NotImplementedError
         desc = capi.PrbAcqDesc(kind=capi.PRB_ACQ_MEAN, ei_variant=0, param=0.0, min_variance=MIN_VARIANCE,
                                acq_var_floor=0.0)
-        _, mean, var, _ = self.state.acq_points(desc, X, want_post=True)
         shape = X.shape[:-1]
+        if self.input_transform is not None:
+            X = self.input_transform.transform(X)
+        _, mean, var, _ = self.state.acq_points(desc, X, want_post=True)
         return _Posterior(mean.reshape(*shape, 1), var.reshape(*shape, 1))
 
 
@@ -315,6 +324,9 @@ class MultiState:
 def multi_state_from_model(model) -> MultiState:
     """``MultiState`` of a ``ModelListGP`` (ours or duck-typed: anything with ``.models``); rebuilt when a member's state is."""
     members = list(model.models)
+    if any(getattr(m, "input_transform", None) is not None for m in members):
+        # every member would embed the sampled categories with ITS OWN tables; the model-list path shares one kernel input
+        raise NotImplementedError("model lists whose members carry a LatentCategoricalEmbedding are not supported")
     states = [gp_state_from_model(m) for m in members]
     cached = getattr(model, "_prb_multi", None)
     if cached is not None and len(cached[0]) == len(states) and all(a is b for a, b in zip(cached[0], states)):
@@ -341,8 +353,10 @@ def _model_fingerprint(model) -> tuple:
     const = getattr(mm, "raw_constant", None)
     if const is None:
         const = getattr(mm, "constant", None)
+    tf = getattr(model, "input_transform", None)
     return (_tensor_fp(model.train_inputs[0]), _tensor_fp(model.train_targets), _tensor_fp(model.likelihood.noise),
-            _tensor_fp(const), kernel_fingerprint(model.covar_module))
+            _tensor_fp(const), kernel_fingerprint(model.covar_module),
+            tf.fingerprint() if hasattr(tf, "fingerprint") else None)
 
 
 def gp_state_from_model(model) -> GPState:

@@ -135,12 +135,20 @@ class AbstractProbabilisticReparameterization(AcquisitionFunctionWrapper, ABC):
 
     def _space(self) -> capi.PrbSpaceDesc:
         tau = self.input_transform["round"].tau
+        # a model-level LatentCategoricalEmbedding (kernel_type "mixed_latent") is applied by the sampler kernel
+        latent = getattr(getattr(self.acq_function, "model", None), "input_transform", None)
+        if latent is not None and not hasattr(latent, "device_tables"):
+            latent = None
+        key = (tau, None if latent is None else latent.fingerprint())
         cached = self.__dict__.get("_space_cached")
-        if cached is None or cached[0] != tau:
+        if cached is None or cached[0] != key:
             sp = make_space_desc(self.dim, self.integer_indices.tolist(),
                                  self.integer_bounds if self.integer_indices.numel() > 0 else None,
-                                 self.categorical_features, tau, apply_numeric=self.apply_numeric)
-            cached = self.__dict__["_space_cached"] = (tau, sp)
+                                 self.categorical_features, tau, apply_numeric=self.apply_numeric, latent=latent,
+                                 device=self._ma_state.device)
+            if latent is not None:
+                key = (tau, latent.fingerprint())
+            cached = self.__dict__["_space_cached"] = (key, sp)
         return cached[1]
 
     def sample_candidates(self, X: Tensor, rng: str = "torch", seed: Optional[int] = None, offset: int = 1 << 32,
@@ -210,7 +218,11 @@ class AbstractProbabilisticReparameterization(AcquisitionFunctionWrapper, ABC):
 # ----------------------------------------------------------------------------------------------------------------------
 def sp_dk(sp: capi.PrbSpaceDesc) -> int:
     """Kernel-input width of a PR space: numeric layout when the base AF sees OneHotToNumeric inputs."""
-    return (sp.cat_start[0] + sp.n_cat) if (sp.apply_numeric and sp.n_cat > 0) else sp.d
+    if sp.apply_numeric and sp.n_cat > 0:
+        if sp.latent_tables:
+            return sp.cat_start[0] + sum(sp.latent_dim[j] for j in range(sp.n_cat))
+        return sp.cat_start[0] + sp.n_cat
+    return sp.d
 
 
 def _check_X(X: Tensor, dim: int):

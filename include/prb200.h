@@ -97,6 +97,14 @@ typedef struct {
   int32_t raw_integer_space; /* 1: theta's integer columns are already UN-normalised and outputs stay so (the bare
                                 "round" member of the transform chain, input.py:637-746, without the Normalize pair) */
   int32_t reserved;
+  /* Latent categorical embedding (kernel_type "mixed_latent": the model's LatentCategoricalEmbedding input transform,
+   * input.py:777-802, 833-908, applied after OneHotToNumeric).  latent_tables == NULL: off.  Otherwise apply_numeric must
+   * be 1 and categorical j's numeric column is replaced by row `category` of its table: the kernel input is
+   * [non-categorical columns..., table_0 row, table_1 row, ...], d_k = cat_start[0] + sum_j latent_dim[j].
+   * latent_tables: DEVICE pointer, the tables back to back in categorical order, table j [cat_card[j], latent_dim[j]]
+   * row-major; it must stay valid for as long as calls use this descriptor.                                          */
+  int32_t latent_dim[PRB_MAX_CAT];
+  const double* latent_tables;
 } prb_space_desc;
 
 /* ---- base acquisition function (botorch analytic AFs; experiment_utils.py:391-393, 476-480, 489-492) ----------- */

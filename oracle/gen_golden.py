@@ -31,6 +31,7 @@ import torch  # noqa: E402
 
 from oracle import gp_oracle as G  # noqa: E402
 
+from discrete_mixed_bo.input import LatentCategoricalEmbedding, LatentCategoricalSpec  # noqa: E402  (reference code)
 from discrete_mixed_bo.probabilistic_reparameterization import (  # noqa: E402  (reference code)
     AnalyticProbabilisticReparameterization,
     MCProbabilisticReparameterization,
@@ -61,6 +62,11 @@ def make_cases():
     )
     cases["chemistry_mc_ei"] = dict(chem, mc=64, grad_estimator="reinforce", analytic=False, calls=2)
     cases["chemistry_analytic_ei"] = dict(chem, mc=0, grad_estimator=None, analytic=True, calls=1)
+    # C'. the same search-space shape under kernel_type "mixed_latent": the model embeds the numeric codes with the
+    # reference's LatentCategoricalEmbedding (latent dims 2, 2, 1 as experiment_utils.py:297-303 picks them)
+    lat = dict(chem, dim=21, categorical_features={2: 4, 3: 12, 4: 3}, kernel_type="mixed_latent", seed=17)
+    cases["chemistry_latent_mc_ei"] = dict(lat, mc=64, grad_estimator="reinforce_ma", analytic=False, calls=2)
+    cases["chemistry_latent_analytic_ei"] = dict(lat, mc=0, grad_estimator=None, analytic=True, calls=1, n_train=25, b=3)
     # D. mixed_int_f1 : 8 continuous + 8 integers with ranges 1,1,2,2,4,4,6,6 (two binary dims)
     cases["mixed_int_f1_ei"] = dict(
         dim=16, integer_indices=list(range(8, 16)),
@@ -123,29 +129,56 @@ def build_problem(c):
         Xk = torch.cat(cols, dim=-1)
     else:
         Xk = X
+    latent = None
+    X_numeric = Xk
+    ctf = cf if c["kernel_type"] == "mixed_categorical" else {}
+    if c["kernel_type"] == "mixed_latent":
+        # experiment_utils.py:289-313: one LatentCategoricalSpec per numeric categorical column, latent dim 1 (card <= 3)
+        # or 2; categorical_transformed_features = {first latent column: latent dim}
+        start = min(cf.keys())
+        specs, ctf, col = [], {}, start
+        for j, (idx, card) in enumerate(cf.items()):
+            ldim = 1 if card <= 3 else 2
+            specs.append(LatentCategoricalSpec(idx=start + j, num_categories=card, latent_dim=ldim))
+            ctf[col] = ldim
+            col += ldim
+        emb = LatentCategoricalEmbedding(specs, dim=X_numeric.shape[-1])
+        emb.eval()
+        with torch.no_grad():
+            for sp_ in specs:  # stand-in for fitted tables
+                getattr(emb, f"raw_latent_emb_tables_{sp_.idx}").copy_(
+                    0.8 * torch.randn(sp_.num_categories, sp_.latent_dim, generator=g))
+            Xk = emb.transform(X_numeric)
+            tables = [emb.get_emb_table(sp_.idx).detach().clone() for sp_ in specs]
+        latent = dict(specs=[(sp_.idx, sp_.num_categories, sp_.latent_dim) for sp_ in specs], tables=tables, ctf=ctf,
+                      transform=emb.transform)
     dk = Xk.shape[-1]
     binary = c["binary_dims"]
     if c["kernel_type"] == "mixed_categorical":
         cat_dims = list(cf.keys())
+    elif c["kernel_type"] == "mixed_latent":
+        cat_dims = list(range(min(ctf.keys()), dk))
     else:
         cat_dims = []
     cont_dims = sorted(set(range(dk)) - set(binary) - set(cat_dims))
     hp = dict(
         cont_lengthscale=(0.3 + 0.9 * torch.rand(len(cont_dims), generator=g)).tolist(),
         binary_lengthscale=[1.2] if binary else [],
-        categorical_lengthscale=(0.5 + 1.5 * torch.rand(len(cat_dims), generator=g)).tolist(),
+        categorical_lengthscale=(0.5 + 1.5 * torch.rand(len(cat_dims), generator=g)).tolist()
+        if c["kernel_type"] == "mixed_categorical" else [],
         outputscale=1.3, outputscale_sum=0.4,
     )
-    spec = G.reference_kernel_spec(c["kernel_type"], dk, binary,
-                                   cf if c["kernel_type"] == "mixed_categorical" else {}, **hp)
+    if latent is not None:
+        hp["latent_lengthscale"] = (0.6 + 1.2 * torch.rand(len(ctf), generator=g)).tolist()
+    spec = G.reference_kernel_spec(c["kernel_type"], dk, binary, ctf, **hp)
     # y: a draw from the GP prior, standardised
     K = G.eval_kernel(spec, Xk, Xk) + 1e-6 * torch.eye(n)
     y = torch.linalg.cholesky(K) @ torch.randn(n, generator=g)
     y = (y - y.mean()) / y.std()
     noise = 1e-6
     mean_const = 0.1
-    return dict(X_onehot=X, X_model=Xk, y=y, hp=hp, noise=noise, mean_const=mean_const, spec=spec,
-                cont_dims=cont_dims, cat_dims=cat_dims)
+    return dict(X_onehot=X, X_model=Xk, X_numeric=X_numeric, y=y, hp=hp, noise=noise, mean_const=mean_const, spec=spec,
+                cont_dims=cont_dims, cat_dims=cat_dims, latent=latent)
 
 
 def make_theta(c, g):
@@ -161,7 +194,10 @@ def make_theta(c, g):
 
 
 def make_acq(c, prob):
-    model = G.OracleGP(prob["X_model"], prob["y"], prob["spec"], prob["noise"], prob["mean_const"])
+    lat = prob.get("latent")
+    # mixed_latent: the model-level input transform is the REFERENCE's LatentCategoricalEmbedding.transform
+    model = G.OracleGP(prob["X_model"], prob["y"], prob["spec"], prob["noise"], prob["mean_const"],
+                       input_transform=None if lat is None else lat["transform"])
     if c["acq"] == "ei":
         return G.OracleEI(model, best_f=prob["y"].max())
     if c["acq"] == "ucb":
@@ -178,6 +214,9 @@ def run_case(name, c):
     out = dict(case=dict(c), theta=theta, train_X_onehot=prob["X_onehot"], train_X_model=prob["X_model"],
                train_Y=prob["y"], hp=prob["hp"], noise=prob["noise"], mean_const=prob["mean_const"],
                cont_dims=prob["cont_dims"], cat_dims=prob["cat_dims"], calls=[])
+    if prob.get("latent") is not None:
+        out["train_X_numeric"] = prob["X_numeric"]
+        out["latent"] = {k: v for k, v in prob["latent"].items() if k != "transform"}
     if c["analytic"]:
         pr = AnalyticProbabilisticReparameterization(
             acq_function=acq, dim=c["dim"], dtype=torch.float64, device=torch.device("cpu"),

@@ -64,6 +64,7 @@ def reference_kernel_spec(
     outputscale: float = 1.0,
     outputscale_sum: float = 1.0,
     use_ard_binary: bool = False,
+    latent_lengthscale: Sequence[float] = (),
 ) -> KernelSpec:
     """Structure of ``get_kernel`` (``kernels.py:18-101``) with explicit hyperparameters.
 
@@ -77,8 +78,11 @@ def reference_kernel_spec(
     * ``kernels.py:90-94``  "mixed_categorical": the second loop multiplies ``prod_kernel`` by ``kernels[1:]``
       AGAIN, so every factor but the first is squared:  Scale(k0 * k1^2 * ...) + Scale(k0 + k1 + ...)
       (SURVEY.md App. C.1 -- replicated, not fixed).
+    * ``kernels.py:73-84``  "mixed_latent": ``categorical_transformed_features = {first latent column: latent dim}`` over
+      the LatentCategoricalEmbedding layout; categorical dims = everything from the first latent column on; one isotropic
+      Matern-5/2 per set of latent columns (``latent_lengthscale``: one value per categorical); Scale(product).
     """
-    if kernel_type not in ("mixed", "mixed_categorical"):
+    if kernel_type not in ("mixed", "mixed_categorical", "mixed_latent"):
         raise ValueError(f"{kernel_type} is not supported by the oracle.")
     if kernel_type == "mixed_categorical":
         categorical_dims = list(categorical_transformed_features.keys())
@@ -87,7 +91,7 @@ def reference_kernel_spec(
     else:
         categorical_dims = []
     cont_dims = sorted(set(range(dim)) - set(binary_dims))
-    if kernel_type == "mixed_categorical":
+    if kernel_type in ("mixed_categorical", "mixed_latent"):
         cont_dims = sorted(set(cont_dims) - set(categorical_dims))
     factors: List[Factor] = []
     if len(cont_dims) > 0:
@@ -104,7 +108,11 @@ def reference_kernel_spec(
     if kernel_type == "mixed_categorical" and len(categorical_dims) > 0:
         assert len(categorical_lengthscale) == len(categorical_dims)
         factors.append(Factor("categorical", list(categorical_dims), [float(v) for v in categorical_lengthscale]))
-    if kernel_type == "mixed":
+    if kernel_type == "mixed_latent":
+        assert len(latent_lengthscale) == len(categorical_transformed_features)
+        for (start, latent_dim), ls in zip(categorical_transformed_features.items(), latent_lengthscale):
+            factors.append(Factor("matern52", list(range(start, start + latent_dim)), [float(ls)] * latent_dim))
+    if kernel_type in ("mixed", "mixed_latent"):
         return [Term(float(outputscale), [Factor(f.kind, f.dims, f.lengthscale, 1) for f in factors])]
     prod = [Factor(f.kind, f.dims, f.lengthscale, 1 if i == 0 else 2) for i, f in enumerate(factors)]
     summ = [Factor(f.kind, f.dims, f.lengthscale, 1) for f in factors]
@@ -167,6 +175,23 @@ def kernel_diag(spec: KernelSpec, dtype=torch.float64) -> float:
 # ----------------------------------------------------------------------------------------------------------------------
 # Exact GP  [3P] botorch FixedNoiseGP + gpytorch DefaultPredictionStrategy (Cholesky path), SURVEY.md App. B.3
 # ----------------------------------------------------------------------------------------------------------------------
+def latent_embedding_transform(tables: Sequence[Tensor], categ_idcs: Sequence[int], dim: int):
+    """``EmbeddingTransform.transform`` (``input.py:784-802``) with fixed tables: categorical column ``categ_idcs[j]`` (an
+    integer code) -> row of ``tables[j]``; output ``[non-categorical columns, embeddings in order]``.  The tables are taken
+    as given (``get_emb_table``'s pinning of row 0 / entry [1, 0], ``input.py:902-909``, is applied by the caller)."""
+    mask = torch.ones(dim, dtype=torch.bool)
+    mask[list(categ_idcs)] = False
+
+    def transform(X: Tensor) -> Tensor:
+        parts = [X[..., mask]]
+        for idx, table in zip(categ_idcs, tables):
+            codes = X[..., idx].reshape(-1).long()
+            parts.append(table.to(X).index_select(0, codes).reshape(*X.shape[:-1], table.shape[-1]))
+        return torch.cat(parts, dim=-1)
+
+    return transform
+
+
 class OracleGP(torch.nn.Module):
     """FixedNoiseGP with a constant mean, in eval mode, exact Cholesky caches.
 
@@ -177,8 +202,11 @@ class OracleGP(torch.nn.Module):
     """
 
     def __init__(self, train_X: Tensor, train_Y: Tensor, spec: KernelSpec, noise, mean_const: float,
-                 min_variance: float = 1e-10):
+                 min_variance: float = 1e-10, input_transform=None):
+        """``input_transform``: callable applied to the inputs of ``posterior`` (a model-level LatentCategoricalEmbedding,
+        input.py:777-802); ``train_X`` is given already transformed."""
         super().__init__()
+        self.input_transform = input_transform
         train_X = train_X.detach().to(torch.float64).cpu()
         y = train_Y.detach().to(torch.float64).cpu().reshape(-1)
         n = train_X.shape[0]
@@ -203,6 +231,8 @@ class OracleGP(torch.nn.Module):
             Xp = X.squeeze(-2)
         else:
             Xp = X
+        if self.input_transform is not None:
+            Xp = self.input_transform(Xp)
         ks = eval_kernel(self.spec, Xp, self.train_X)  # [..., n]
         mean = self.mean_const + ks @ self.alpha
         root = ks @ self.Linv.transpose(-1, -2)  # k*^T L^-T

@@ -17,8 +17,14 @@ def draw_sobol_samples(bounds, n, q, batch_shape=None, seed=None):
     return lower + rng * samples_raw
 
 
-def draw_sobol_normal_samples(d, n, device=None, dtype=None, seed=None):  # imported by input.py:14, unused on the PR path
-    raise NotImplementedError
+def draw_sobol_normal_samples(d, n, device=None, dtype=None, seed=None):
+    """Quasi-random standard-normal rows (input.py:873 uses them as the INITIAL latent embedding tables; the golden cases
+    overwrite the tables with seeded values, so only shape / dtype matter here): scrambled Sobol through the inverse
+    normal CDF."""
+    u = SobolEngine(d, scramble=True, seed=seed).draw(n, dtype=torch.float64)
+    v = 0.5 + (1.0 - 1e-10) * (u - 0.5)
+    out = (2.0 ** 0.5) * torch.erfinv(2.0 * v - 1.0)
+    return out.to(device=device, dtype=dtype or torch.get_default_dtype())
 
 
 def sample_simplex(d, n=1, qmc=False, seed=None, device=None, dtype=None):  # imported by input.py:16, unused on the PR path

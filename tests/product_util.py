@@ -30,14 +30,18 @@ def _scales(k, out=None):
     return out
 
 
-def product_covar(case, hp, train_Xk, train_Y):
+def product_covar(case, hp, train_Xk, train_Y, ctf=None):
     cf = case["categorical_features"] or {}
     dk = train_Xk.shape[-1]
     covar = B.get_kernel(case["kernel_type"], dk, case["binary_dims"],
-                         cf if case["kernel_type"] == "mixed_categorical" else {}, train_Xk, train_Y)
+                         ctf if ctf is not None else (cf if case["kernel_type"] == "mixed_categorical" else {}),
+                         train_Xk, train_Y)
+    latent_starts = list(ctf.keys()) if ctf is not None else []
     for leaf in _unique_leaves(covar):
         dims = leaf.active_dims.tolist()
-        if type(leaf).__name__ == "CategoricalKernel":
+        if ctf is not None and dims[0] in latent_starts and len(dims) == ctf[dims[0]]:
+            leaf.lengthscale = [hp["latent_lengthscale"][latent_starts.index(dims[0])]]
+        elif type(leaf).__name__ == "CategoricalKernel":
             leaf.lengthscale = hp["categorical_lengthscale"]
         elif len(case["binary_dims"]) > 0 and dims == list(case["binary_dims"]):
             leaf.lengthscale = hp["binary_lengthscale"]
@@ -54,6 +58,19 @@ def product_model(g, device):
     c = g["case"]
     Xk = g["train_X_model"].to(device)
     y = g["train_Y"].to(device)
+    lat = g.get("latent")
+    if lat is not None:
+        # kernel_type "mixed_latent" as experiment_utils.py:289-313 builds it: numeric training inputs + a model-level
+        # LatentCategoricalEmbedding whose (fitted) tables come from the fixture
+        Xn = g["train_X_numeric"].to(device)
+        emb = B.LatentCategoricalEmbedding([B.LatentCategoricalSpec(idx=i, num_categories=k, latent_dim=e)
+                                            for i, k, e in lat["specs"]], dim=Xn.shape[-1]).to(device)
+        with torch.no_grad():
+            for (i, _, _), t in zip(lat["specs"], lat["tables"]):
+                getattr(emb, f"raw_latent_emb_tables_{i}").copy_(t.to(device))
+        covar = product_covar(c, g["hp"], Xk, y, ctf=lat["ctf"])
+        return B.FixedNoiseGP(Xn, y.unsqueeze(-1), torch.full_like(y, g["noise"]).unsqueeze(-1), covar_module=covar,
+                              input_transform=emb, mean_const=g["mean_const"])
     covar = product_covar(c, g["hp"], Xk, y)
     return B.FixedNoiseGP(Xk, y.unsqueeze(-1), torch.full_like(y, g["noise"]).unsqueeze(-1), covar_module=covar,
                           mean_const=g["mean_const"])

@@ -18,7 +18,8 @@ def _bounds(d):
     return torch.stack([torch.zeros(d, dtype=torch.float64), torch.ones(d, dtype=torch.float64)]).to(DEV)
 
 
-@pytest.mark.parametrize("name", ["ackley13_ei", "rosenbrock10_ucb", "mixed_int_f1_ei"])
+@pytest.mark.parametrize("name", ["ackley13_ei", "rosenbrock10_ucb", "mixed_int_f1_ei", "chemistry_mc_ei",
+                                  "chemistry_latent_mc_ei"])
 def test_fused_adam_matches_host_loop_and_oracle(name):
     g = load(name)
     c = g["case"]
@@ -42,13 +43,15 @@ def test_fused_adam_matches_host_loop_and_oracle(name):
 
     def vg(X):
         r = P.mc_pr(space, X, oacq, g["base_samples"], g["base_samples_categorical"],
-                    grad_estimator=c["grad_estimator"], ma_counter=st["c"], ma_hidden=st["h"])
+                    grad_estimator=c["grad_estimator"], ma_counter=st["c"], ma_hidden=st["h"],
+                    apply_numeric=c["apply_numeric"])
         st["c"], st["h"] = r.ma_counter, r.ma_hidden
         return r.value, r.grad
 
     def vo(X):
         r = P.mc_pr(space, X, oacq, g["base_samples"], g["base_samples_categorical"],
-                    grad_estimator=c["grad_estimator"], ma_counter=st["c"], ma_hidden=st["h"], with_grad=False)
+                    grad_estimator=c["grad_estimator"], ma_counter=st["c"], ma_hidden=st["h"], with_grad=False,
+                    apply_numeric=c["apply_numeric"])
         st["c"], st["h"] = r.ma_counter, r.ma_hidden
         return r.value
 

@@ -12,7 +12,8 @@ import torch
 from oracle import gp_oracle as G
 from oracle import pr_oracle as P
 from oracle.philox import philox_uniform
-from tests.golden_util import ANALYTIC_CASES, MC_CASES, load, oracle_acq, oracle_space, oracle_spec
+from tests.golden_util import (ANALYTIC_CASES, MC_CASES, load, oracle_acq, oracle_latent_transform, oracle_space,
+                               oracle_spec)
 from tests.product_util import (close, integer_bounds, product_acq, product_analytic_pr, product_mc_pr,
                                 product_model)
 
@@ -31,9 +32,10 @@ def test_kernel_matrix_and_posterior(name):
     """a9/a10: K(x*, X) and the posterior (mean, variance) against the L0 oracle."""
     g = load(name)
     model = product_model(g, DEV)
-    ogp = G.OracleGP(g["train_X_model"], g["train_Y"], oracle_spec(g), g["noise"], g["mean_const"])
+    tf = oracle_latent_transform(g)  # mixed_latent: the model's inputs are the numeric layout, embedded by the model
+    ogp = G.OracleGP(g["train_X_model"], g["train_Y"], oracle_spec(g), g["noise"], g["mean_const"], input_transform=tf)
     gen = torch.Generator().manual_seed(5)
-    Xk = g["train_X_model"]
+    Xk = g["train_X_model"] if tf is None else g["train_X_numeric"]
     # test points: perturbed training points (hard: small variance) and fresh points with valid discrete codes
     idx = torch.randint(0, Xk.shape[0], (64,), generator=gen)
     Xt = Xk[idx].clone()
@@ -48,11 +50,12 @@ def test_kernel_matrix_and_posterior(name):
     st = model.state
     lib = st.lib
     K = torch.empty(64, st.n, dtype=torch.float64, device=DEV)
-    xt = Xt.to(DEV).contiguous()
+    Xt_k = Xt if tf is None else tf(Xt)
+    xt = Xt_k.to(DEV).contiguous()
     rc = lib.prb_kernel_matrix(C.byref(st._desc), xt.data_ptr(), 64, K.data_ptr(), None)
     assert rc == 0
     torch.cuda.synchronize()
-    _assert_close(K, G.eval_kernel(oracle_spec(g), Xt, Xk), "K(x*, X)", rtol=1e-13, atol=1e-15)
+    _assert_close(K, G.eval_kernel(oracle_spec(g), Xt_k, g["train_X_model"]), "K(x*, X)", rtol=1e-13, atol=1e-15)
 
 
 @pytest.mark.parametrize("name", MC_CASES)
@@ -62,7 +65,7 @@ def test_base_acq_value_and_gradient(name):
     acq = product_acq(g, DEV)
     oacq = oracle_acq(g)
     gen = torch.Generator().manual_seed(6)
-    Xk = g["train_X_model"]
+    Xk = g["train_X_model"] if g.get("latent") is None else g["train_X_numeric"]
     idx = torch.randint(0, Xk.shape[0], (48,), generator=gen)
     Xt = Xk[idx].clone()
     cont = g["cont_dims"]
