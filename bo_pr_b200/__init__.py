@@ -7,7 +7,9 @@ mixed-kernel factory and the multi-start optimisation drivers.  All arithmetic o
 from .acquisition import (  # noqa: F401
     AcquisitionFunction,
     ConstrainedExpectedImprovement,
+    ExpectedHypervolumeImprovement,
     ExpectedImprovement,
+    ModelListAcquisitionFunction,
     PosteriorMean,
     UpperConfidenceBound,
     is_nonnegative,
@@ -31,6 +33,7 @@ from .kernels import (  # noqa: F401
     get_kernel,
 )
 from .models import FixedNoiseGP, GPState, ModelListGP  # noqa: F401
+from .multi_objective import FastNondominatedPartitioning, NondominatedPartitioning, is_non_dominated  # noqa: F401
 from .probabilistic_reparameterization import (  # noqa: F401
     AnalyticProbabilisticReparameterization,
     MCProbabilisticReparameterization,

@@ -17,6 +17,7 @@ PRB_MAX_CAT = 8
 PRB_MAX_CARD = 32
 PRB_MAX_MODELS = 8
 PRB_MACQ_CEI = 0
+PRB_MACQ_EHVI = 1
 
 PRB_FACTOR_MATERN52 = 0
 PRB_FACTOR_CATEGORICAL = 1
@@ -72,7 +73,8 @@ class PrbMultiAcqDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("n_models", C.c_int32), ("objective_index", C.c_int32), ("reserved", C.c_int32),
                 ("best_f", C.c_double), ("min_variance", C.c_double), ("sigma_floor", C.c_double),
                 ("has_lower", C.c_int32 * PRB_MAX_MODELS), ("has_upper", C.c_int32 * PRB_MAX_MODELS),
-                ("lower", C.c_double * PRB_MAX_MODELS), ("upper", C.c_double * PRB_MAX_MODELS)]
+                ("lower", C.c_double * PRB_MAX_MODELS), ("upper", C.c_double * PRB_MAX_MODELS),
+                ("var_floor", C.c_double), ("n_cells", C.c_int32), ("reserved2", C.c_int32), ("cell_bounds", C.c_void_p)]
 
 
 class PrbError(RuntimeError):

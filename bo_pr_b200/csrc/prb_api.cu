@@ -1263,10 +1263,15 @@ int multi_setup(prb_model* const* models, int n_models, int64_t n_points, int n_
 }
 
 int fill_multi_args(const MultiCtx& c, const prb_multi_acq_desc* acq, void* ws, bool need_grad, MultiAcqArgs* ma) {
-  if (!acq || acq->kind != PRB_MACQ_CEI || acq->n_models != c.nm || acq->objective_index < 0 ||
-      acq->objective_index >= c.nm)
+  if (!acq || (acq->kind != PRB_MACQ_CEI && acq->kind != PRB_MACQ_EHVI) || acq->n_models != c.nm) return PRB_ERR_INVALID;
+  if (acq->kind == PRB_MACQ_CEI && (acq->objective_index < 0 || acq->objective_index >= c.nm)) return PRB_ERR_INVALID;
+  if (acq->kind == PRB_MACQ_EHVI && (acq->n_cells < 0 || (acq->n_cells > 0 && acq->cell_bounds == nullptr) || c.nm < 2))
     return PRB_ERR_INVALID;
   memset(ma, 0, sizeof(MultiAcqArgs));
+  ma->kind = acq->kind;
+  ma->var_floor = acq->var_floor;
+  ma->n_cells = acq->n_cells;
+  ma->cell_bounds = acq->cell_bounds;
   ma->n_models = c.nm;
   ma->objective_index = acq->objective_index;
   ma->best_f = acq->best_f;

@@ -226,6 +226,69 @@ cudaError_t launch_tr_bounds(const double* X, const double* Y, int n, int d, int
 // One thread per evaluation point: raw variances from every model's row-tile norms, the value, and -- for the pathwise
 // gradient -- dA/dmu_m and dA/dsigma_m^2 of every model (product rule; the clamps pass no gradient where they bind).
 // =====================================================================================================================
+//
+// Expected hypervolume improvement ([3P] botorch <= 0.8 multi_objective/analytic.py; experiment_utils.py:395-402), q = 1, all
+// models objectives:  sigma_m = sqrt(max(var_m, var_floor)),  EHVI = sum_cells prod_m s_m(cell),
+//   s = psi(l, l) - psi(l, u) + nu(l, u)   (botorch sums the 2^M products of {psi_diff, nu} choices: the same number),
+//   d s / d mu = cdf(t_u) - cdf(t_l),   d s / d sigma = pdf(t_l) - pdf(t_u),   t = (bound - mu) / sigma.
+// One thread per evaluation point; the cells are read by every thread in the same order (broadcast loads).
+__global__ void multi_ehvi_epilogue_kernel(const MultiAcqArgs ma, int ncols_pad, int ncols, double* __restrict__ a,
+                                           double* __restrict__ out_mean, double* __restrict__ out_var) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncols) return;
+  const int M = ma.n_models;
+  double mu[PRB_MAX_MODELS], sg[PRB_MAX_MODELS], pass[PRB_MAX_MODELS];
+  for (int m = 0; m < M; ++m) {
+    double vs = 0.0;
+    for (int t = 0; t < ma.mtiles[m]; ++t) vs += ma.norm_part[m][size_t(t) * ncols_pad + col];
+    const double var_post = fmax(ma.kss[m] - vs, ma.min_variance);  // gpytorch floor, then botorch's clamp_min
+    mu[m] = ma.mean_const[m] + ma.mu_dot[m][col];
+    sg[m] = sqrt(fmax(var_post, ma.var_floor));
+    pass[m] = (ma.kss[m] - vs >= ma.min_variance && var_post >= ma.var_floor) ? 1.0 : 0.0;
+    if (out_mean) out_mean[size_t(col) * M + m] = mu[m];
+    if (out_var) out_var[size_t(col) * M + m] = var_post;
+  }
+  const bool grad = ma.dmu[0] != nullptr;
+  double total = 0.0, g_mu[PRB_MAX_MODELS], g_sg[PRB_MAX_MODELS];
+  for (int m = 0; m < M; ++m) g_mu[m] = g_sg[m] = 0.0;
+  const double* lo = ma.cell_bounds;
+  const double* hi = ma.cell_bounds + size_t(ma.n_cells) * M;
+  for (int c = 0; c < ma.n_cells; ++c) {
+    double s[PRB_MAX_MODELS], ds_mu[PRB_MAX_MODELS], ds_sg[PRB_MAX_MODELS];
+    double prod = 1.0;
+    for (int m = 0; m < M; ++m) {
+      const double l = lo[size_t(c) * M + m];
+      const double u = fmin(hi[size_t(c) * M + m], 1e10);
+      const double tl = (l - mu[m]) / sg[m], tu = (u - mu[m]) / sg[m];
+      const double pl = exp(-(tl * tl) / 2.0 - PRB_LOG_SQRT_2PI), pu = exp(-(tu * tu) / 2.0 - PRB_LOG_SQRT_2PI);
+      const double cl = 0.5 * (1.0 + erf(tl * PRB_INV_SQRT2)), cu = 0.5 * (1.0 + erf(tu * PRB_INV_SQRT2));
+      const double psi_ll = sg[m] * pl + (mu[m] - l) * (1.0 - cl);
+      const double psi_lu = sg[m] * pu + (mu[m] - l) * (1.0 - cu);
+      const double nu = (u - l) * (1.0 - cu);
+      s[m] = (psi_ll - psi_lu) + nu;
+      ds_mu[m] = cu - cl;
+      ds_sg[m] = pl - pu;
+      prod *= s[m];
+    }
+    total += prod;
+    if (grad) {
+      for (int m = 0; m < M; ++m) {
+        double others = 1.0;
+        for (int k = 0; k < M; ++k)
+          if (k != m) others *= s[k];
+        g_mu[m] = fma(others, ds_mu[m], g_mu[m]);
+        g_sg[m] = fma(others, ds_sg[m], g_sg[m]);
+      }
+    }
+  }
+  a[col] = total;
+  if (!grad) return;
+  for (int m = 0; m < M; ++m) {
+    ma.dmu[m][col] = g_mu[m];
+    ma.dvar[m][col] = g_sg[m] / (2.0 * sg[m]) * pass[m];
+  }
+}
+
 __global__ void multi_acq_epilogue_kernel(const MultiAcqArgs ma, int ncols_pad, int ncols, double* __restrict__ a,
                                           double* __restrict__ out_mean, double* __restrict__ out_var) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
@@ -298,7 +361,10 @@ cudaError_t launch_multi_acq_epilogue(const MultiAcqArgs& ma, int ncols_pad, int
                                       double* out_var, cudaStream_t st) {
   ProfScope prof_(K_EPILOGUE, st);
   if (ncols == 0) return cudaSuccess;
-  multi_acq_epilogue_kernel<<<(ncols + 127) / 128, 128, 0, st>>>(ma, ncols_pad, ncols, a, out_mean, out_var);
+  if (ma.kind == PRB_MACQ_EHVI)
+    multi_ehvi_epilogue_kernel<<<(ncols + 127) / 128, 128, 0, st>>>(ma, ncols_pad, ncols, a, out_mean, out_var);
+  else
+    multi_acq_epilogue_kernel<<<(ncols + 127) / 128, 128, 0, st>>>(ma, ncols_pad, ncols, a, out_mean, out_var);
   count_launch();
   return cudaGetLastError();
 }

@@ -68,8 +68,12 @@ cudaError_t launch_adam_step(double* theta, const double* acq_grad, double* m, d
 cudaError_t launch_fill(double* p, double v, int n, cudaStream_t st);
 // model lists (prb_finalize.cu): combined acquisition epilogue and the accumulation of the per-model gradient partials
 struct MultiAcqArgs {
+  int kind;  // prb_multi_acq_kind
   int n_models, objective_index;
   double best_f, min_variance, sigma_floor;
+  double var_floor;           // EHVI
+  int n_cells;                // EHVI
+  const double* cell_bounds;  // EHVI: [2, n_cells, n_models]
   int has_lower[PRB_MAX_MODELS], has_upper[PRB_MAX_MODELS];
   double lower[PRB_MAX_MODELS], upper[PRB_MAX_MODELS];
   double mean_const[PRB_MAX_MODELS], kss[PRB_MAX_MODELS];

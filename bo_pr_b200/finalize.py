@@ -30,7 +30,7 @@ def finalize_candidates(pr, candidates: Tensor, seed: Optional[int] = None, offs
         raise NotImplementedError("expected candidates of shape b x q=1 x d")
     b, d = candidates.shape[0], candidates.shape[-1]
     dev = candidates.device
-    if type(pr.acq_function).__name__ == "ConstrainedExpectedImprovement":
+    if hasattr(pr.acq_function, "multi_desc"):
         # model lists: sampler kernel, then the model-list acquisition on the sampled rows; argmax with device ops
         rows, xk = pr._sample_candidates_device(candidates, 0 if seed is None else int(seed), int(offset), u, want_xk=True)
         with torch.no_grad():

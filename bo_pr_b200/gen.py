@@ -102,7 +102,7 @@ def _is_fusable(acquisition_function, options, callback, optimizer, fixed_featur
 
     if not isinstance(acquisition_function, (MCProbabilisticReparameterization, AnalyticProbabilisticReparameterization)):
         return False
-    if type(acquisition_function.acq_function).__name__ == "ConstrainedExpectedImprovement":
+    if hasattr(acquisition_function.acq_function, "multi_desc"):
         return False  # model lists: host-driven loop over prb_mc_value_grad_multi
     rnd = acquisition_function.input_transform["round"]
     if getattr(rnd, "resample", False):

@@ -20,7 +20,7 @@ from torch.autograd import Function
 from torch.nn.functional import one_hot
 
 from . import _capi as capi
-from .acquisition import AcquisitionFunction, ConstrainedExpectedImprovement, acq_desc_of
+from .acquisition import AcquisitionFunction, ModelListAcquisitionFunction, acq_desc_of
 from .input import (
     AnalyticProbabilisticReparameterizationInputTransform,
     ChainedInputTransform,
@@ -438,7 +438,7 @@ class MCProbabilisticReparameterization(AbstractProbabilisticReparameterization)
         dev = X.device
         if b == 0:  # nothing to evaluate; the reference's EMA update would average an empty tensor (NaN): leave the state
             return X.new_empty(0, dtype=torch.float64), None
-        if isinstance(self.acq_function, ConstrainedExpectedImprovement):
+        if isinstance(self.acq_function, ModelListAcquisitionFunction):
             return self._launch_multi(X, need)
         cc = self._call_ctx(dev)
         rnd = cc["rnd"]
@@ -474,7 +474,8 @@ class MCProbabilisticReparameterization(AbstractProbabilisticReparameterization)
 
 
 def _launch_multi(self, X: Tensor, need: bool):
-    """Model-list acquisition functions (``ConstrainedExpectedImprovement``): ``prb_mc_value_grad_multi``."""
+    """Model-list acquisition functions (``ConstrainedExpectedImprovement``, ``ExpectedHypervolumeImprovement``):
+    ``prb_mc_value_grad_multi``."""
     b, d = X.shape[0], X.shape[-1]
     dev = X.device
     acq = self.acq_function

@@ -123,9 +123,14 @@ typedef enum { PRB_EST_REINFORCE = 0, PRB_EST_REINFORCE_MA = 1 } prb_estimator;
 /* ---- acquisition function over a LIST of independent single-output GPs (botorch ModelListGP, experiment_utils.py:337-346).
  * PRB_MACQ_CEI: botorch ConstrainedExpectedImprovement as get_EI builds it (experiment_utils.py:354-392):
  *   EI(objective output; best_f) * prod_m P(lower_m <= Y_m <= upper_m),  sigma_m = max(sqrt(var_m), sigma_floor),
- *   P from Normal.cdf(x) = 0.5 (1 + erf(x / sqrt2)); a missing bound drops its factor.                                    */
+ *   P from Normal.cdf(x) = 0.5 (1 + erf(x / sqrt2)); a missing bound drops its factor.
+ * PRB_MACQ_EHVI: botorch's analytic ExpectedHypervolumeImprovement (q = 1) as get_EHVI builds it (experiment_utils.py:395-402)
+ *   over a box decomposition of the non-dominated region (cell_bounds, the partitioning's get_hypercell_bounds()):
+ *   sigma_m = sqrt(max(var_m, var_floor));  EHVI = sum_cells prod_m [psi(l, l) - psi(l, u) + nu(l, u)]_m,
+ *   psi(l, u) = sigma pdf((u - mu)/sigma) + (mu - l) (1 - cdf((u - mu)/sigma)),  nu(l, u) = (u - l)(1 - cdf((u - mu)/sigma)),
+ *   upper bounds clamped to 1e10 (the +inf cells).  Every model of the list is an objective.                              */
 #define PRB_MAX_MODELS 8
-typedef enum { PRB_MACQ_CEI = 0 } prb_multi_acq_kind;
+typedef enum { PRB_MACQ_CEI = 0, PRB_MACQ_EHVI = 1 } prb_multi_acq_kind;
 typedef struct {
   int32_t kind;            /* prb_multi_acq_kind */
   int32_t n_models;        /* outputs = models, in list order */
@@ -138,6 +143,11 @@ typedef struct {
   int32_t has_upper[PRB_MAX_MODELS];
   double lower[PRB_MAX_MODELS]; /* bounds on model m's output; ignored for the objective */
   double upper[PRB_MAX_MODELS];
+  /* PRB_MACQ_EHVI only */
+  double var_floor;          /* botorch: posterior.variance.clamp_min(1e-9) */
+  int32_t n_cells;
+  int32_t reserved2;
+  const double* cell_bounds; /* DEVICE [2, n_cells, n_models] row-major: lower corners, then upper corners (+inf allowed) */
 } prb_multi_acq_desc;
 
 /* ---- library ---------------------------------------------------------------------------------------------------- */

@@ -358,3 +358,79 @@ class OracleConstrainedEI(OracleAcq):
             elif hi is not None:
                 prob = prob * cdf((hi - m) / s)
         return ei * prob
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Analytic expected hypervolume improvement  [3P] botorch.acquisition.multi_objective.analytic.ExpectedHypervolumeImprovement
+# (BoTorch 0.6-0.8), call site experiment_utils.py:395-402 (get_EHVI; label pr__ehvi).  PARITY UNPINNED: BoTorch is absent
+# from this image and the reference repository holds no recorded EHVI values; the formulas below restate the published
+# method (Yang et al. 2019 as BoTorch implements it) and are cross-checked against a Monte Carlo estimate of the
+# hypervolume improvement in tests/test_ehvi_host.py.
+# ----------------------------------------------------------------------------------------------------------------------
+def grid_nondominated_cells(pareto_Y: Tensor, ref_point: Tensor) -> Tensor:
+    """A box decomposition of the non-dominated region above ``ref_point`` INDEPENDENT of the product's: the full grid
+    spanned by every objective's distinct Pareto values (plus ref and +inf), keeping the boxes whose lower corner no Pareto
+    point dominates.  ``O((K + 1)^m)`` boxes -- test infrastructure only.  Returns ``[2, n_cells, m]``."""
+    import itertools
+    m = ref_point.numel()
+    P = pareto_Y.reshape(-1, m).to(torch.float64)
+    ref = ref_point.to(torch.float64)
+    edges = []
+    for k in range(m):
+        vals = sorted({float(ref[k])} | {float(v) for v in P[:, k] if float(v) > float(ref[k])})
+        edges.append(vals + [math.inf])
+    lows, highs = [], []
+    for idx in itertools.product(*[range(len(e) - 1) for e in edges]):
+        lo = torch.tensor([edges[k][i] for k, i in enumerate(idx)], dtype=torch.float64)
+        hi = torch.tensor([edges[k][i + 1] for k, i in enumerate(idx)], dtype=torch.float64)
+        # the open box (lo, hi) is dominated iff some Pareto point is >= hi everywhere (grid boxes are never split)
+        if P.numel() > 0 and bool((P >= hi).all(-1).any()):
+            continue
+        lows.append(lo)
+        highs.append(hi)
+    return torch.stack([torch.stack(lows), torch.stack(highs)])
+
+
+class OracleEHVI(OracleAcq):
+    """q = 1 analytic EHVI over a model list, every output an objective (maximised):
+
+        mu, sigma = posterior mean, sqrt(variance.clamp_min(1e-9));  upper cell bounds clamp_max(1e10)
+        psi(l, u) = sigma * exp(Normal.log_prob((u - mu)/sigma)) + (mu - l) * (1 - cdf((u - mu)/sigma))
+        nu(l, u)  = (u - l) * (1 - cdf((u - mu)/sigma))
+        EHVI = sum over cells, sum over the 2^m choices of {psi(l, l) - psi(l, u), nu(l, u)} per objective, of the product.
+    """
+
+    def __init__(self, model: OracleModelList, ref_point, cell_bounds: Tensor, var_floor: float = 1e-9):
+        super().__init__(model)
+        self.ref_point = torch.as_tensor(ref_point, dtype=torch.float64)
+        self.cell_lower_bounds = cell_bounds[0].to(torch.float64)
+        self.cell_upper_bounds = cell_bounds[1].to(torch.float64)
+        self.var_floor = var_floor
+        import itertools
+        m = self.ref_point.numel()
+        self._choices = torch.tensor(list(itertools.product(*[[0, 1] for _ in range(m)])), dtype=torch.long)
+
+    @staticmethod
+    def _cdf(x):
+        return 0.5 * (1 + torch.erf(x / math.sqrt(2)))
+
+    def _psi(self, lower, upper, mu, sigma):
+        u = (upper - mu) / sigma
+        return sigma * torch.exp(-(u ** 2) / 2 - _LOG_SQRT_2PI) + (mu - lower) * (1 - self._cdf(u))
+
+    def _nu(self, lower, upper, mu, sigma):
+        return (upper - lower) * (1 - self._cdf((upper - mu) / sigma))
+
+    def forward(self, X):
+        means, variances = self.model.posterior(X)  # [..., m]
+        mu = means.unsqueeze(-2)  # [..., 1, m] against cells [n_cells, m]
+        sigma = variances.clamp_min(self.var_floor).sqrt().unsqueeze(-2)
+        upper = self.cell_upper_bounds.clamp_max(1e10)
+        lower = self.cell_lower_bounds
+        psi_lu = self._psi(lower, upper, mu, sigma)
+        psi_ll = self._psi(lower, lower, mu, sigma)
+        nu = self._nu(lower, upper, mu, sigma)
+        stacked = torch.stack([psi_ll - psi_lu, nu], dim=-2)  # [..., n_cells, 2, m]
+        m = lower.shape[-1]
+        picked = torch.stack([stacked[..., self._choices[:, k], k] for k in range(m)], dim=-1)  # [..., n_cells, 2^m, m]
+        return picked.prod(dim=-1).sum(dim=-1).sum(dim=-1)

@@ -1,5 +1,6 @@
-"""Model lists: ConstrainedExpectedImprovement over independent GPs under MC-PR
-(experiment_utils.py:354-392 -- the welded-beam / pressure-vessel style configs), CUDA path vs the oracle."""
+"""Model lists under MC-PR, CUDA path vs the oracle: ConstrainedExpectedImprovement over independent GPs
+(experiment_utils.py:354-392 -- the welded-beam / pressure-vessel style configs) and analytic ExpectedHypervolumeImprovement
+(experiment_utils.py:395-402 -- the multi-objective configs, label pr__ehvi)."""
 import pytest
 import torch
 
@@ -111,4 +112,77 @@ def test_mc_pr_over_model_list_vs_oracle(name):
     assert cand.shape == theta.shape and bool((cand >= 0).all()) and bool((cand <= 1).all())
     assert float(v1.sum()) >= float(v0.sum()) - 1e-9
     chosen, value = B.finalize_candidates(pr, cand, seed=1)
+    assert chosen.shape == (1, c["dim"]) and float(value) >= 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Expected hypervolume improvement (experiment_utils.py:395-402, label pr__ehvi): every model an objective.
+# Oracle: the BoTorch formula restated (2^m cross product) over an INDEPENDENT grid decomposition of the non-dominated
+# region; product: multi_ehvi_epilogue_kernel over the dimension-sweep decomposition (bo_pr_b200/multi_objective.py).
+# ---------------------------------------------------------------------------------------------------------------------
+def _build_ehvi(name, n_obj):
+    c = CASES[name]
+    gs = _outputs(c, n_out=n_obj)
+    ogps = [G.OracleGP(g["train_X_model"], g["train_Y"], oracle_spec(g), g["noise"], g["mean_const"]) for g in gs]
+    Y = torch.stack([g["train_Y"] for g in gs], dim=-1)
+    ref = Y.quantile(0.2, dim=0)
+    part = B.FastNondominatedPartitioning(ref_point=ref, Y=Y)
+    assert part.pareto_Y.shape[0] >= 2
+    oacq = G.OracleEHVI(G.OracleModelList(*ogps), ref, G.grid_nondominated_cells(part.pareto_Y, ref))
+    model = B.ModelListGP(*[product_model(g, DEV) for g in gs])
+    acq = B.ExpectedHypervolumeImprovement(model, ref_point=ref.tolist(), partitioning=part)
+    pr = B.MCProbabilisticReparameterization(
+        acq_function=acq, dim=c["dim"], integer_indices=c["integer_indices"], integer_bounds=integer_bounds(c, DEV),
+        categorical_features=c["categorical_features"], mc_samples=c["mc"], grad_estimator=c["grad_estimator"], tau=0.1)
+    rnd = pr.input_transform["round"]
+    g0 = gs[0]
+    if g0["base_samples"] is not None:
+        rnd.register_buffer("base_samples", g0["base_samples"].to(DEV).contiguous())
+    if g0["base_samples_categorical"] is not None:
+        rnd.register_buffer("base_samples_categorical", g0["base_samples_categorical"].to(DEV).contiguous())
+    return c, g0, oacq, acq, pr
+
+
+@pytest.mark.parametrize("name,n_obj", [("welded_like", 2), ("mixed_cont", 2), ("mixed_cont", 3)])
+def test_ehvi_points_vs_oracle(name, n_obj):
+    c, g0, oacq, acq, pr = _build_ehvi(name, n_obj)
+    gen = torch.Generator().manual_seed(4)
+    Xk = g0["train_X_model"]
+    idx = torch.randint(0, Xk.shape[0], (40,), generator=gen)
+    Xt = Xk[idx].clone()
+    cont = g0["cont_dims"]
+    if cont:
+        Xt[:, cont] = (Xt[:, cont] + 0.2 * torch.randn(40, len(cont), generator=gen, dtype=torch.float64)).clamp(0, 1)
+    with torch.no_grad():
+        ref = oacq(Xt.unsqueeze(-2))
+        out = acq(Xt.to(DEV).unsqueeze(-2))
+    assert float(ref.max()) > 0.0
+    ok, worst = close(out, ref, 1e-9, 1e-13)
+    assert ok, f"EHVI at explicit points: {worst:.3g} x tolerance"
+
+
+@pytest.mark.parametrize("name,n_obj", [("welded_like", 2), ("mixed_cont", 2), ("mixed_cont", 3)])
+def test_mc_pr_ehvi_vs_oracle(name, n_obj):
+    c, g0, oacq, acq, pr = _build_ehvi(name, n_obj)
+    space = oracle_space(g0)
+    theta = g0["theta"]
+    go = torch.linspace(0.6, 1.4, c["b"], dtype=torch.float64)
+    pre = (2.0, 0.01) if c["grad_estimator"] == "reinforce_ma" else (0.0, 0.0)
+    ref = P.mc_pr(space, theta, oacq, g0["base_samples"], g0["base_samples_categorical"],
+                  grad_estimator=c["grad_estimator"], ma_counter=pre[0], ma_hidden=pre[1], grad_output=go)
+    pr._ma_state.copy_(torch.tensor(pre, dtype=torch.float64))
+    X = theta.to(DEV).requires_grad_(True)
+    val = pr(X)
+    grad = torch.autograd.grad(val, X, grad_outputs=go.to(DEV))[0]
+    ok, w = close(val, ref.value, 1e-9, 1e-13)
+    assert ok, f"PR-EHVI value: {w:.3g} x tolerance"
+    ok, w = close(grad, ref.grad, 1e-9, 1e-12)
+    assert ok, f"PR-EHVI gradient (score function + pathwise through every objective): {w:.3g} x tolerance"
+    lo = torch.zeros(c["dim"], dtype=torch.float64, device=DEV)
+    hi = torch.ones(c["dim"], dtype=torch.float64, device=DEV)
+    with torch.no_grad():
+        v0 = pr(theta.to(DEV))
+    cand, v1 = B.gen_candidates_torch(theta.to(DEV), pr, lo, hi, options={"maxiter": 10})
+    assert float(v1.sum()) >= float(v0.sum()) - 1e-9
+    chosen, value = B.finalize_candidates(pr, cand, seed=2)
     assert chosen.shape == (1, c["dim"]) and float(value) >= 0.0
