@@ -57,7 +57,8 @@
 // the tail (4.399 ms).  A start-up stagger of the second CTA on each SM (0.5-2 tile units) decays within a few tiles
 // (4.353 ms) and adds nothing on top of the mixed order.  Generating the operand by a GATHER from a per-restart table
 // kc[b][j] * tab[h] (no DMUL, no table LDS in the consumer warps) changes nothing (4.370 vs 4.373 ms): the `math` stalls of
-// the generator are time the pipe spends on the sibling CTA's DMMAs, not lost time.
+// the generator are time the pipe spends on the sibling CTA's DMMAs, not lost time.  Two 8-warp CTAs per SM with 32 x 32 warp
+// tiles (128 registers, four warps per sub-partition, so that a lone CTA still has two) are slower: 4.553 vs 4.328 ms.
 //
 // Four modes (template):
 //   LOWER_GEN   the B operand k*[col, k] = kc[b(col), k] * tab[popc(z[col] ^ Z[k])] is GENERATED into shared memory by the
