@@ -1228,7 +1228,10 @@ int prb_mc_value_grad_host(prb_model* model, const prb_space_desc* space, const 
   };
   // (A cached executable graph of this whole sequence -- one cudaGraphLaunch instead of ~8 runtime calls -- was measured and
   // changes nothing: 0.645 vs 0.648 ms per 8-restart step.  The ~43 us this call costs over the device-resident step are the
-  // copies' own latencies and the wake-up after the synchronise, not launch overhead.)
+  // copies' own latencies and the wake-up after the synchronise, not launch overhead.  Letting the kernels read theta from
+  // and write the results to the pinned (device-mapped) host buffers directly, with no copy operations at all, was measured
+  // too: 0.6307 vs 0.6326 ms at 8 restarts, 4.369 vs 4.379 ms at 64 -- within noise, and the generic path's sampler would
+  // re-read theta over the bus once per MC sample, so the staged copies stay.)
   rc = sequence(st);
   if (rc != PRB_OK) return rc;
   if (synchronize) CUDA_TRY(cudaStreamSynchronize(st));
