@@ -938,6 +938,8 @@ static int model_create_impl(prb_model** out, const prb_model_desc* desc, const 
   if (e == cudaSuccess) e = cudaMemsetAsync(m->Zbits, 0, size_t(n_pad) * sizeof(uint32_t), st);
   if (e == cudaSuccess) e = make_operand_map(&m->mapA1, m->A1, m->Mp1, m->Kp, m->Kp);
   if (e == cudaSuccess) e = make_operand_map(&m->mapA2, m->A2, m->Mp2, m->Kp, m->Kp);
+  if (e == cudaSuccess) e = make_operand_map3(&m->mapA1k, m->A1, m->Mp1, m->Kp, m->Kp);
+  if (e == cudaSuccess) e = make_operand_map3(&m->mapA2k, m->A2, m->Mp2, m->Kp, m->Kp);
   // separable candidate: one product term of two Matern-5/2 factors, one of them isotropic over <= 32 dims
   m->sep_ok = 0;
   if (e == cudaSuccess && m->spec.n_terms == 1 && !m->spec.t[0].additive && m->spec.t[0].n_factors == 2) {

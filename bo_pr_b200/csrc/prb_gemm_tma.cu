@@ -121,6 +121,9 @@ extern "C" void prb_debug_set_cta_trace(long long* buf) {
   } while (0)
 #endif
 
+#ifndef PRB_GEN_ROTATE
+#define PRB_GEN_ROTATE 0
+#endif
 struct TmaGemmParams {
   long long* trace = nullptr;
   int mixed_groups = 0;    // leading scheduling groups that use the mixed (heavy / light alternating) order
@@ -280,7 +283,10 @@ __global__ void __launch_bounds__(THREADS, MINB)
 
   // TMA side of a k-tile (one elected thread): A always, B unless it is generated
   auto produce_tma = [&](int kt) {
-    if (tid != 0) return;
+    // A + B by TMA: the four M-warps take turns as producer, which spreads the elected thread's issue work over the warps
+    // (upper product 2.111 -> 2.075 ms).  With the B operand generated by all threads the rotation is SLOWER (lower product
+    // 2.197 -> 2.226 ms), so there warp 0 stays the producer.
+    if (tid != ((GEN && !PRB_GEN_ROTATE) ? 0 : 32 * (kt & 3))) return;
     const int s = kt % NST;
     const int use = kt / NST;
     const int k0 = kbeg + kt * T_BK;
@@ -288,12 +294,9 @@ __global__ void __launch_bounds__(THREADS, MINB)
     double* Bs = As + T_OPER_DOUBLES;
     if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
     mbar_arrive_expect_tx(&full[s], (T_OPER_DOUBLES + (GEN ? 0 : B_OPER)) * 8);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) tma_load_2d(As + c * T_CHUNK_DOUBLES, &tmA, &full[s], k0 + 4 * c, m0);
-    if (!GEN) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tma_load_2d(Bs + c * B_CHUNK, &tmB, &full[s], k0 + 4 * c, n0);
-    }
+    // one 3-D box (4 k values x rows x 4 k-chunks) per operand lands as the [k-chunk][row][4] stage layout
+    tma_load_3d(As, &tmA, &full[s], 0, m0, k0 >> 2);
+    if (!GEN) tma_load_3d(Bs, &tmB, &full[s], 0, n0, k0 >> 2);
   };
   // generated B operand: global loads are issued a whole k-tile of DMMA work before they are consumed
   double2 g_k01, g_k23, g_k45, g_k67;
@@ -752,6 +755,22 @@ cudaError_t make_operand_map(TensorMap* out, const double* base, int rows, int k
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// 3-D view of the same matrix: (k mod 4, row, k div 4) with strides (8, 8 ld, 32) bytes; box = 4 x box_rows x 4 -> one TMA
+// instruction delivers a whole k-tile of an operand in the [k-chunk][row][4] layout (four 2-D boxes before: the elected
+// thread's issue work per k-tile fell from 8 instructions to 2)
+cudaError_t make_operand_map3(TensorMap* out, const double* base, int rows, int k_extent, int ld, int box_rows) {
+  if (!g_encode) return cudaErrorNotReady;
+  cuuint64_t gdim[3] = {4, cuuint64_t(rows), cuuint64_t(k_extent / 4)};
+  cuuint64_t gstride[2] = {cuuint64_t(ld) * sizeof(double), 4 * sizeof(double)};
+  cuuint32_t box[3] = {4, cuuint32_t(box_rows), 4};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
+                        const_cast<double*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 // Column-tile width of the separable-path products (PRB_BN overrides, for A/B runs):
 //   64  (default) 4 warps of 32 x 64 per CTA, TWO CTAs per SM: one CTA's TMA prologue, epilogue and end-of-tile barrier
 //       overlap the other's main loop -- 1-2 % faster than one 8-warp 128-column CTA per SM at every n from 200 to 4000;
@@ -824,7 +843,7 @@ cudaError_t launch_tma_lower_gen(const Model& m, const SepArgs& sa, int ncols_pa
     p.acq_dvar = fa->dvar;
     p.acq_ncols = fa->ncols;
   }
-  const CUtensorMap& mA = *reinterpret_cast<const CUtensorMap*>(&m.mapA1);
+  const CUtensorMap& mA = *reinterpret_cast<const CUtensorMap*>(&m.mapA1k);
   cudaError_t le;
   if (bn == 32)
     le = launch_kernel(trgemm_tma_kernel<MODE_LOWER_GEN, 32, T_THREADS>, dim3(p.mtiles * p.ntiles), dim3(T_THREADS),
@@ -866,9 +885,9 @@ cudaError_t launch_tma_lower(const Model& m, const double* panelK, int panel_row
     p.acq_ncols = fa->ncols;
   }
   TensorMap mapK;  // the k* panel [panel_rows, Kp], box = 4 k values x bn columns
-  cudaError_t e = make_operand_map(&mapK, panelK, panel_rows, m.Kp, m.Kp, bn);
+  cudaError_t e = make_operand_map3(&mapK, panelK, panel_rows, m.Kp, m.Kp, bn);
   if (e != cudaSuccess) return e;
-  const CUtensorMap& mA = *reinterpret_cast<const CUtensorMap*>(&m.mapA1);
+  const CUtensorMap& mA = *reinterpret_cast<const CUtensorMap*>(&m.mapA1k);
   const CUtensorMap& mB = *reinterpret_cast<const CUtensorMap*>(&mapK);
   cudaError_t le;
   if (bn == 32)
@@ -890,9 +909,9 @@ cudaError_t launch_tma_upper(const Model& m, const double* panelV, int panel_row
   p.C = W;
   p.ldc = ncols_pad;
   TensorMap mapV;
-  cudaError_t e = make_operand_map(&mapV, panelV, panel_rows, m.Kp, m.Mp1, bn);
+  cudaError_t e = make_operand_map3(&mapV, panelV, panel_rows, m.Kp, m.Mp1, bn);
   if (e != cudaSuccess) return e;
-  const CUtensorMap& mA = *reinterpret_cast<const CUtensorMap*>(&m.mapA2);
+  const CUtensorMap& mA = *reinterpret_cast<const CUtensorMap*>(&m.mapA2k);
   const CUtensorMap& mB = *reinterpret_cast<const CUtensorMap*>(&mapV);
   if (bn == 32)
     trgemm_tma_kernel<MODE_UPPER_W, 32><<<p.mtiles * p.ntiles, T_THREADS, T_SMEM_BYTES, st>>>(mA, mB, p);
@@ -915,9 +934,9 @@ cudaError_t launch_tma_upper_grad(const Model& m, const double* panelV, int pane
   p.ncols = ncols;
   p.S_part = S_part;
   TensorMap mapV;  // the v panel [panel_rows, Mp1], box = 4 k values x bn columns
-  cudaError_t e = make_operand_map(&mapV, panelV, panel_rows, m.Kp, m.Mp1, bn);
+  cudaError_t e = make_operand_map3(&mapV, panelV, panel_rows, m.Kp, m.Mp1, bn);
   if (e != cudaSuccess) return e;
-  const CUtensorMap& mA = *reinterpret_cast<const CUtensorMap*>(&m.mapA2);
+  const CUtensorMap& mA = *reinterpret_cast<const CUtensorMap*>(&m.mapA2k);
   const CUtensorMap& mB = *reinterpret_cast<const CUtensorMap*>(&mapV);
   if (bn == 32)
     e = launch_kernel(trgemm_tma_kernel<MODE_UPPER_GRAD, 32, T_THREADS>, dim3(p.mtiles * p.ntiles), dim3(T_THREADS),
@@ -951,9 +970,9 @@ cudaError_t launch_tma_upper_gradq(const Model& m, const double* panelV, int pan
   p.n = m.n;
   p.d_k = m.d_k;
   TensorMap mapV;  // the v panel [panel_rows, Mp1], box = 4 k values x bn columns
-  cudaError_t e = make_operand_map(&mapV, panelV, panel_rows, m.Kp, m.Mp1, bn);
+  cudaError_t e = make_operand_map3(&mapV, panelV, panel_rows, m.Kp, m.Mp1, bn);
   if (e != cudaSuccess) return e;
-  const CUtensorMap& mA = *reinterpret_cast<const CUtensorMap*>(&m.mapA2);
+  const CUtensorMap& mA = *reinterpret_cast<const CUtensorMap*>(&m.mapA2k);
   const CUtensorMap& mB = *reinterpret_cast<const CUtensorMap*>(&mapV);
   if (bn == 32)
     e = launch_kernel(trgemm_tma_kernel<MODE_UPPER_GRADQ, 32, T_THREADS>, dim3(p.mtiles * p.ntiles), dim3(T_THREADS),

@@ -191,7 +191,8 @@ struct Model {
   DevSpec spec;
   int device;
   // ---- second-generation engine (TMA operands) ----
-  TensorMap mapA1, mapA2;
+  TensorMap mapA1, mapA2;    // 2-D maps (box = 4 k values x 128 rows): the single-kernel step of prb_small.cu
+  TensorMap mapA1k, mapA2k;  // 3-D maps (box = 4 k values x 128 rows x 4 k-chunks): one TMA per operand and k-tile
   double* alpha_pad;  // [max(Mp1, Mp2)] alpha, zero padded
   // separable structure: one term = Matern52(continuous dims) x isotropic Matern52(binary dims), binary training columns
   int sep_ok;
@@ -245,6 +246,7 @@ cudaError_t launch_small_adam_persistent(const Model& m, bool gen, const DevSpac
 // prb_gemm_tma.cu
 cudaError_t tma_init();
 cudaError_t make_operand_map(TensorMap* out, const double* base, int rows, int k_extent, int ld, int box_rows = 128);
+cudaError_t make_operand_map3(TensorMap* out, const double* base, int rows, int k_extent, int ld, int box_rows = 128);
 cudaError_t launch_tma_lower_gen(const Model& m, const SepArgs& sa, int ncols_pad, double* VT, double* norm_part,
                                  double* mu_dot, const FusedAcq* fa, cudaStream_t st);
 cudaError_t launch_tma_lower(const Model& m, const double* panelK, int panel_rows, int ncols_pad, double* VT,
