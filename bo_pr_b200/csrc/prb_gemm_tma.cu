@@ -59,6 +59,11 @@
 // kc[b][j] * tab[h] (no DMUL, no table LDS in the consumer warps) changes nothing (4.370 vs 4.373 ms): the `math` stalls of
 // the generator are time the pipe spends on the sibling CTA's DMMAs, not lost time.  Two 8-warp CTAs per SM with 32 x 32 warp
 // tiles (128 registers, four warps per sub-partition, so that a lone CTA still has two) are slower: 4.553 vs 4.328 ms.
+// What DID pay after the trace: the elected producer thread's issue work.  One 3-D TMA box per operand and k-tile instead
+// of four 2-D boxes, and -- where both operands arrive by TMA -- the four M-warps taking turns as producer: upper product
+// 2.111 -> 2.024 ms, generic-path step 4.98 -> 4.77 ms, bench step 4.326 -> 4.247 ms.  In LOWER_GEN (every thread generates)
+// the rotation is slower (2.201 -> 2.226 ms, 2.208 -> 2.214 with 3-D boxes), and so is one full-barrier arrival per warp
+// after a __syncwarp instead of one per thread (2.208 -> 2.255 ms).
 //
 // Four modes (template):
 //   LOWER_GEN   the B operand k*[col, k] = kc[b(col), k] * tab[popc(z[col] ^ Z[k])] is GENERATED into shared memory by the
