@@ -779,13 +779,25 @@ cudaError_t make_operand_map3(TensorMap* out, const double* base, int rows, int 
 // Column-tile width of the separable-path products (PRB_BN overrides, for A/B runs):
 //   64  (default) 4 warps of 32 x 64 per CTA, TWO CTAs per SM: one CTA's TMA prologue, epilogue and end-of-tile barrier
 //       overlap the other's main loop -- 1-2 % faster than one 8-warp 128-column CTA per SM at every n from 200 to 4000;
-//   32  when even 128-wide tiling leaves most SMs without a tile: small problems are bound by ONE SM's DMMA rate;
+//   32  when the heaviest row tile, not the total work, bounds the launch (narrow_tiles_win): few columns per GPU;
 //   128 one 8-warp CTA per SM (the generic-path kernels use this shape).
+// 32-column tiles (one 8-warp CTA per SM) against 64-column tiles (two 4-warp CTAs per SM) by a two-term time estimate in
+// units of (one k-block of 128) x (one column): the launch takes at least its heaviest row tile -- mtiles k-blocks at the
+// rate ONE CTA gets -- and at least the total triangular work spread over 148 SMs.  Rates as measured: a 4-warp CTA gets
+// ~0.6 of an SM whether alone or paired, an 8-warp 32-column CTA ~0.8; full launches run at ~0.9 resp. ~0.75 of the SMs.
+// The heaviest tile decides for few columns: n = 2000 with 1 024 columns (the 8-GPU share at mc = 128) is 0.345 ms with
+// 32-column tiles and 0.581 ms with 64 (r02's tile-count rule picked 64 there); every other swept shape keeps its choice.
+static bool narrow_tiles_win(int mtiles, int ncols_pad) {
+  const double work = double(ncols_pad) * mtiles * (mtiles + 1) / 2.0;
+  const double est64 = fmax(mtiles * 64.0 / 0.6, work / (148.0 * 0.9));
+  const double est32 = fmax(mtiles * 32.0 / 0.8, work / (148.0 * 0.75));
+  return est32 < est64;
+}
+
 static int pick_bn(const Model& m, int ncols_pad, bool upper) {
   const int force = env_knobs().force_bn;
   if (force == 32 || force == 64 || force == 128) return force;
-  const int tiles128 = ((upper ? m.Mp2 : m.Mp1) / T_BM) * (ncols_pad / 128);
-  return tiles128 < 120 ? 32 : 64;
+  return narrow_tiles_win((upper ? m.Mp2 : m.Mp1) / T_BM, ncols_pad) ? 32 : 64;
 }
 
 static void fill_common(TmaGemmParams& p, const Model& m, int ncols_pad, bool upper, int bn = T_BN) {
@@ -865,8 +877,7 @@ cudaError_t launch_tma_lower_gen(const Model& m, const SepArgs& sa, int ncols_pa
 
 // generic path (materialised operands): 128-column tiles, or 32 when that leaves most SMs idle
 static int pick_bn_generic(const Model& m, int ncols_pad, bool upper) {
-  const int tiles128 = ((upper ? m.Mp2 : m.Mp1) / T_BM) * (ncols_pad / 128);
-  return tiles128 < 120 ? 32 : 128;
+  return narrow_tiles_win((upper ? m.Mp2 : m.Mp1) / T_BM, ncols_pad) ? 32 : 128;
 }
 
 cudaError_t launch_tma_lower(const Model& m, const double* panelK, int panel_rows, int ncols_pad, double* VT,
