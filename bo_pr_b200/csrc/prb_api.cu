@@ -872,49 +872,96 @@ static int model_create_impl(prb_model** out, const prb_model_desc* desc, const 
   m->device = dev;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
-  if ((e = cudaMalloc(&m->A1, size_t(m->Mp1) * m->Kp * sizeof(double))) != cudaSuccess ||
-      (e = cudaMalloc(&m->A2, size_t(m->Mp2) * m->Kp * sizeof(double))) != cudaSuccess ||
-      (e = cudaMalloc(&m->Xtr, size_t(m->n) * m->d_k * sizeof(double))) != cudaSuccess ||
-      (e = cudaMalloc(&m->alpha, size_t(m->n) * sizeof(double))) != cudaSuccess) {
-    prb_model_destroy(reinterpret_cast<prb_model*>(m));
-    return cuda_fail(e, "cudaMalloc(model)");
+  // Stream-ordered pool allocations throughout: four cudaMalloc calls for the model arrays cost 630 us per build at
+  // n = 1000 -- a third of the whole build -- and cudaMalloc / cudaFree of the factorisation scratch more than the
+  // factorisation itself.  The pool keeps what it has handed out (release threshold raised once), so the next BO
+  // iteration's build reuses it.  All device arrays of the model live in ONE block.
+  static std::once_flag pool_once;
+  std::call_once(pool_once, [dev] {
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = uint64_t(2) << 30;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    (void)cudaGetLastError();
+  });
+  const int n_pad = m->Mp1 > m->Mp2 ? m->Mp1 : m->Mp2;
+  size_t off = 0;
+  auto carve = [&off](size_t bytes) {
+    const size_t o = off;
+    off += (bytes + 255) & ~size_t(255);
+    return o;
+  };
+  const size_t o_A1 = carve(size_t(m->Mp1) * m->Kp * sizeof(double));
+  const size_t o_A2 = carve(size_t(m->Mp2) * m->Kp * sizeof(double));
+  const size_t o_X = carve(size_t(m->n) * m->d_k * sizeof(double));
+  const size_t o_alpha = carve(size_t(m->n) * sizeof(double));
+  const size_t o_apad = carve(size_t(n_pad) * sizeof(double));
+  const size_t o_Zb = carve(size_t(n_pad) * sizeof(uint32_t));
+  const size_t o_tab = carve(64 * sizeof(double));
+  const size_t o_ctr = carve(64);
+  const size_t o_flags = carve(64);  // [0] Cholesky info, [1] separable-structure check
+  if ((e = cudaMallocAsync(&m->block, off, st)) != cudaSuccess) {
+    delete m;
+    return cuda_fail(e, "cudaMallocAsync(model)");
   }
+  char* blk = static_cast<char*>(m->block);
+  m->A1 = reinterpret_cast<double*>(blk + o_A1);
+  m->A2 = reinterpret_cast<double*>(blk + o_A2);
+  m->Xtr = reinterpret_cast<double*>(blk + o_X);
+  m->alpha = reinterpret_cast<double*>(blk + o_alpha);
+  m->alpha_pad = reinterpret_cast<double*>(blk + o_apad);
+  m->Zbits = reinterpret_cast<uint32_t*>(blk + o_Zb);
+  m->sep_tab = reinterpret_cast<double*>(blk + o_tab);
+  m->done_ctr = reinterpret_cast<unsigned int*>(blk + o_ctr);
+  int* flags_dev = reinterpret_cast<int*>(blk + o_flags);
   e = cudaMemcpyAsync(m->Xtr, desc->X_train, size_t(m->n) * m->d_k * sizeof(double), cudaMemcpyDeviceToDevice, st);
-  int chol_info = 0;
+  if (e == cudaSuccess) e = cudaMemsetAsync(blk + o_ctr, 0, 128, st);  // completion counter + both flags
+  if (e == cudaSuccess) e = cudaMemsetAsync(m->Zbits, 0, size_t(n_pad) * sizeof(uint32_t), st);
+  if (e == cudaSuccess) e = tma_init();
+  if (e == cudaSuccess) e = small_step_init();
+  // separable candidates: one product term of two Matern-5/2 factors, one of them isotropic over <= 32 dims.  The check that
+  // the factor's training columns really are {0, 1} runs on the device; its flag is read back with the factorisation's.
+  int sep_cand[2] = {0, 0};
+  if (m->spec.n_terms == 1 && !m->spec.t[0].additive && m->spec.t[0].n_factors == 2) {
+    const DevTerm& T = m->spec.t[0];
+    for (int fb = 0; fb < 2; ++fb) {
+      const DevFactor& F = T.f[fb];
+      const DevFactor& O = T.f[1 - fb];
+      bool cand = F.kind == PRB_FACTOR_MATERN52 && O.kind == PRB_FACTOR_MATERN52 && F.power == 1 && O.power == 1 &&
+                  F.n_dims <= 32;
+      for (int i = 1; i < F.n_dims && cand; ++i) cand = F.inv_ls[i] == F.inv_ls[0];
+      for (int i = 0; i < F.n_dims && cand; ++i)
+        for (int k = 0; k < O.n_dims && cand; ++k) cand = F.dims[i] != O.dims[k];
+      sep_cand[fb] = cand ? 1 : 0;
+    }
+  }
+  auto start_sep_check = [&](int fb) -> cudaError_t {
+    m->sep_bin_factor = fb;
+    m->sep_cont_factor = 1 - fb;
+    m->sep_nbits = m->spec.t[0].f[fb].n_dims;
+    cudaError_t r = cudaMemsetAsync(flags_dev + 1, 0, sizeof(int), st);
+    if (r == cudaSuccess) r = cudaMemsetAsync(m->Zbits, 0, size_t(n_pad) * sizeof(uint32_t), st);
+    if (r == cudaSuccess) r = launch_sep_model_prep(*m, n_pad, flags_dev + 1, st);
+    return r;
+  };
+  m->sep_ok = 0;
+  const int first = sep_cand[0] ? 0 : (sep_cand[1] ? 1 : -1);
+  if (e == cudaSuccess && first >= 0) e = start_sep_check(first);
+  int flags_host[2] = {0, 1};  // Cholesky info (0 = fine), separable check (0 = columns are {0, 1})
   if (e == cudaSuccess && from_data) {
     // K(X, X) by the library's own kernel, then the factorisation, the inverse factor, alpha and the packing (prb_chol.cu)
     double* Kmat = nullptr;
     void* scratch = nullptr;
-    int* info_dev = nullptr;
-    // stream-ordered pool allocations: cudaMalloc / cudaFree of a few hundred MB cost more than the factorisation itself.
-    // The pool keeps what it has handed out (release threshold raised once) so that the next BO iteration's build reuses it.
-    static std::once_flag pool_once;
-    std::call_once(pool_once, [dev] {
-      cudaMemPool_t pool = nullptr;
-      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t keep = uint64_t(2) << 30;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-      }
-      (void)cudaGetLastError();
-    });
     if ((e = cudaMallocAsync(&Kmat, size_t(m->n) * m->n * sizeof(double), st)) == cudaSuccess &&
         (e = cudaMallocAsync(&scratch, chol_scratch_bytes(m->n), st)) == cudaSuccess &&
-        (e = cudaMallocAsync(&info_dev, sizeof(int), st)) == cudaSuccess &&
-        (e = launch_kernel_matrix(m->spec, m->Xtr, m->n, m->Xtr, m->n, Kmat, st)) == cudaSuccess &&
-        (e = build_gp_state(Kmat, noise, y, m->mean_const, m->n, m->Kp, m->Mp1, m->Mp2, m->A1, m->A2, m->alpha, out_Linv,
-                            scratch, info_dev, st)) == cudaSuccess &&
-        (e = cudaMemcpyAsync(&chol_info, info_dev, sizeof(int), cudaMemcpyDeviceToHost, st)) == cudaSuccess)
-      e = cudaStreamSynchronize(st);
+        (e = launch_kernel_matrix(m->spec, m->Xtr, m->n, m->Xtr, m->n, Kmat, st)) == cudaSuccess)
+      e = build_gp_state(Kmat, noise, y, m->mean_const, m->n, m->Kp, m->Mp1, m->Mp2, m->A1, m->A2, m->alpha, out_Linv,
+                         scratch, flags_dev, st);
     if (e == cudaSuccess && out_alpha)
       e = cudaMemcpyAsync(out_alpha, m->alpha, size_t(m->n) * sizeof(double), cudaMemcpyDeviceToDevice, st);
     if (Kmat) cudaFreeAsync(Kmat, st);
     if (scratch) cudaFreeAsync(scratch, st);
-    if (info_dev) cudaFreeAsync(info_dev, st);
-    if (e == cudaSuccess && chol_info != 0) {
-      snprintf(g_cuda_err, sizeof(g_cuda_err), "K + diag(noise) is not positive definite (pivot %d)", chol_info - 1);
-      prb_model_destroy(reinterpret_cast<prb_model*>(m));
-      return PRB_ERR_NOT_PD;
-    }
   } else if (e == cudaSuccess) {
     e = cudaMemcpyAsync(m->alpha, desc->alpha, size_t(m->n) * sizeof(double), cudaMemcpyDeviceToDevice, st);
     if (e == cudaSuccess) {
@@ -924,50 +971,31 @@ static int model_create_impl(prb_model** out, const prb_model_desc* desc, const 
       count_launch();
     }
   }
-  // second-generation engine: TMA descriptors of the packed factors, padded alpha, separable-structure tables
-  const int n_pad = m->Mp1 > m->Mp2 ? m->Mp1 : m->Mp2;
-  int* bad_flag = nullptr;
-  if (e == cudaSuccess) e = tma_init();
-  if (e == cudaSuccess) e = small_step_init();
-  if (e == cudaSuccess) e = cudaMalloc(&m->alpha_pad, size_t(n_pad) * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc(&m->Zbits, size_t(n_pad) * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&m->sep_tab, 64 * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc(&m->done_ctr, 64);
-  if (e == cudaSuccess) e = cudaMemsetAsync(m->done_ctr, 0, 64, st);
   if (e == cudaSuccess) e = launch_pad_copy(m->alpha, m->n, n_pad, m->alpha_pad, st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(m->Zbits, 0, size_t(n_pad) * sizeof(uint32_t), st);
+  // ONE synchronisation: the factorisation's status and the separable-structure check come back together
+  if (e == cudaSuccess) e = cudaMemcpyAsync(flags_host, flags_dev, 2 * sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess && from_data && flags_host[0] != 0) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "K + diag(noise) is not positive definite (pivot %d)", flags_host[0] - 1);
+    prb_model_destroy(reinterpret_cast<prb_model*>(m));
+    return PRB_ERR_NOT_PD;
+  }
+  if (e == cudaSuccess && first >= 0) {
+    if (flags_host[1] == 0) {
+      m->sep_ok = 1;  // the factor's training columns are exactly {0, 1}
+    } else if (first == 0 && sep_cand[1]) {  // rare: the other factor order is a structural candidate too
+      int bad = 1;
+      if ((e = start_sep_check(1)) == cudaSuccess &&
+          (e = cudaMemcpyAsync(&bad, flags_dev + 1, sizeof(int), cudaMemcpyDeviceToHost, st)) == cudaSuccess &&
+          (e = cudaStreamSynchronize(st)) == cudaSuccess && !bad)
+        m->sep_ok = 1;
+    }
+  }
+  // second-generation engine: TMA descriptors of the packed factors
   if (e == cudaSuccess) e = make_operand_map(&m->mapA1, m->A1, m->Mp1, m->Kp, m->Kp);
   if (e == cudaSuccess) e = make_operand_map(&m->mapA2, m->A2, m->Mp2, m->Kp, m->Kp);
   if (e == cudaSuccess) e = make_operand_map3(&m->mapA1k, m->A1, m->Mp1, m->Kp, m->Kp);
   if (e == cudaSuccess) e = make_operand_map3(&m->mapA2k, m->A2, m->Mp2, m->Kp, m->Kp);
-  // separable candidate: one product term of two Matern-5/2 factors, one of them isotropic over <= 32 dims
-  m->sep_ok = 0;
-  if (e == cudaSuccess && m->spec.n_terms == 1 && !m->spec.t[0].additive && m->spec.t[0].n_factors == 2) {
-    const DevTerm& T = m->spec.t[0];
-    for (int fb = 0; fb < 2 && !m->sep_ok; ++fb) {
-      const DevFactor& F = T.f[fb];
-      const DevFactor& O = T.f[1 - fb];
-      bool cand = F.kind == PRB_FACTOR_MATERN52 && O.kind == PRB_FACTOR_MATERN52 && F.power == 1 && O.power == 1 &&
-                  F.n_dims <= 32;
-      for (int i = 1; i < F.n_dims && cand; ++i) cand = F.inv_ls[i] == F.inv_ls[0];
-      for (int i = 0; i < F.n_dims && cand; ++i)
-        for (int k = 0; k < O.n_dims && cand; ++k) cand = F.dims[i] != O.dims[k];
-      if (!cand) continue;
-      m->sep_bin_factor = fb;
-      m->sep_cont_factor = 1 - fb;
-      m->sep_nbits = F.n_dims;
-      if ((e = cudaMalloc(&bad_flag, sizeof(int))) != cudaSuccess) break;
-      if ((e = cudaMemsetAsync(bad_flag, 0, sizeof(int), st)) != cudaSuccess) break;
-      if ((e = launch_sep_model_prep(*m, n_pad, bad_flag, st)) != cudaSuccess) break;
-      int bad = 1;
-      if ((e = cudaMemcpyAsync(&bad, bad_flag, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
-      if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
-      cudaFree(bad_flag);
-      bad_flag = nullptr;
-      if (!bad) m->sep_ok = 1;  // the factor's training columns are exactly {0, 1}
-    }
-  }
-  if (bad_flag) cudaFree(bad_flag);
   if (e != cudaSuccess) {
     prb_model_destroy(reinterpret_cast<prb_model*>(m));
     return cuda_fail(e, "prb_model_create");
@@ -1016,20 +1044,21 @@ int prb_rff_model_create(prb_model** out, int32_t d_k, int32_t n_features, const
 int prb_model_destroy(prb_model* model) {
   if (!model) return PRB_OK;
   Model* m = reinterpret_cast<Model*>(model);
-  cudaFree(m->rff_W);  // cudaFree synchronises the device: no replay of a cached graph is in flight past this point
+  // synchronise the device first: no replay of a cached graph is in flight past this point
+  if (m->block)
+    cudaDeviceSynchronize();
+  else
+    cudaFree(m->rff_W);
   for (int i = 0; i < 2; ++i)
     if (m->graph_exec[i]) cudaGraphExecDestroy(m->graph_exec[i]);
   for (int i = 0; i < m->n_graph_dead; ++i) cudaGraphExecDestroy(m->graph_dead[i]);
-  cudaFree(m->done_ctr);
-  cudaFree(m->rff_b);
-  cudaFree(m->rff_w);
-  cudaFree(m->A1);
-  cudaFree(m->A2);
-  cudaFree(m->Xtr);
-  cudaFree(m->alpha);
-  cudaFree(m->alpha_pad);
-  cudaFree(m->Zbits);
-  cudaFree(m->sep_tab);
+  if (m->block) {
+    cudaFree(m->block);  // pool memory: synchronises like any cudaFree, then goes back to the pool for the next build
+  } else {
+    cudaFree(m->done_ctr);  // RFF sample models own their arrays one by one
+    cudaFree(m->rff_b);
+    cudaFree(m->rff_w);
+  }
   delete m;
   return PRB_OK;
 }

@@ -182,6 +182,7 @@ struct Model {
   int Kp;        // round_up(n, 16): padded contraction length / leading dimension of the eval-major panels
   int Mp1;       // round_up(n + 1, 128): rows of A1 = [Linv ; alpha^T ; 0]
   int Mp2;       // round_up(n, 128): rows of A2 = Linv^T
+  void* block;   // GP models: ONE stream-ordered pool allocation that every device array below points into
   double* A1;    // [Mp1, Kp] row-major
   double* A2;    // [Mp2, Kp] row-major (upper triangular: A2[m, k] = Linv[k, m], k >= m)
   double* Xtr;   // [n, d_k]
