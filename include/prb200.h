@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PRB_VERSION 100
+#define PRB_VERSION 200 /* 200: r02 layouts (prb_space_desc latent fields, prb_multi_acq_desc EHVI fields) */
 
 #define PRB_MAX_DIMS 64     /* kernel-input columns / theta columns (svm: 50 binary + 3 continuous = 53) */
 #define PRB_MAX_FACTORS 4   /* multiplicative (or additive) factors per term */

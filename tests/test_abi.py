@@ -35,7 +35,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_version_and_status_strings(lib):
-    assert lib.prb_version() == 100
+    assert lib.prb_version() == 200
     assert lib.prb_status_string(0) == b"ok"
     assert b"workspace" in lib.prb_status_string(-3)
 
