@@ -28,7 +28,8 @@ def _assert_close(a, b, what, rtol=1e-9, atol=1e-12):
 
 
 @pytest.mark.parametrize("n,b,mc,acq", [(200, 8, 128, "ei"), (333, 5, 96, "ucb"), (1000, 4, 256, "ei"),
-                                        (1537, 3, 64, "ei")])
+                                        (1537, 3, 64, "ei"),
+                                        (2000, 8, 128, "ei")])  # 16 row tiles x 1 024 columns: the 32-column tile choice
 def test_value_grad_vs_oracle(n, b, mc, acq):
     g = _problem(n, mc, acq)
     space, oacq = oracle_space(g), oracle_acq(g)
