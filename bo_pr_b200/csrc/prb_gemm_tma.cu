@@ -64,6 +64,9 @@
 // 2.111 -> 2.024 ms, generic-path step 4.98 -> 4.77 ms, bench step 4.326 -> 4.247 ms.  In LOWER_GEN (every thread generates)
 // the rotation is slower (2.201 -> 2.226 ms, 2.208 -> 2.214 with 3-D boxes), and so is one full-barrier arrival per warp
 // after a __syncwarp instead of one per thread (2.208 -> 2.255 ms).
+// Evaluating the acquisition function of a CTA's own columns inside the UPPER_GRAD prologue (while the first TMA tiles
+// are in flight; removes the separate epilogue launch from the fused step) saves 3 us at 8 192 columns but the added
+// code costs the 65 536-column step 0.03-0.04 ms even when it is switched off at run time (4.247 -> 4.28-4.29 ms): reverted.
 //
 // Four modes (template):
 //   LOWER_GEN   the B operand k*[col, k] = kc[b(col), k] * tab[popc(z[col] ^ Z[k])] is GENERATED into shared memory by the
