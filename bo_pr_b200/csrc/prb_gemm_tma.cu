@@ -331,21 +331,29 @@ __global__ void __launch_bounds__(THREADS, MINB)
       g_zs = __ldg(reinterpret_cast<const uint2*>(p.Zbits + k0 + ghalf * 2));
     }
   };
+  // GEN_VPT == 8: the operand values of the NEXT generated k-tile are formed in registers in the middle of the current
+  // k-tile's DMMA block (gen_compute: popc -> table LDS -> DMUL, in the same basic block as the DMMAs, so their latencies
+  // hide behind the warp's own 16-cycle DMMA cadence) and only stored at the end of the k-tile (gen_store)
+  double2 g_o0, g_o1, g_o2, g_o3;
+  auto gen_compute = [&]() {
+    if constexpr (GEN_VPT == 8) {
+      g_o0.x = g_k01.x * tab_s[__popc(g_zb ^ g_za.x)];
+      g_o0.y = g_k01.y * tab_s[__popc(g_zb ^ g_za.y)];
+      g_o1.x = g_k23.x * tab_s[__popc(g_zb ^ g_za.z)];
+      g_o1.y = g_k23.y * tab_s[__popc(g_zb ^ g_za.w)];
+      g_o2.x = g_k45.x * tab_s[__popc(g_zb ^ g_zc.x)];
+      g_o2.y = g_k45.y * tab_s[__popc(g_zb ^ g_zc.y)];
+      g_o3.x = g_k67.x * tab_s[__popc(g_zb ^ g_zc.z)];
+      g_o3.y = g_k67.y * tab_s[__popc(g_zb ^ g_zc.w)];
+    }
+  };
   auto gen_store = [&](int kt) {
     const int s = kt % NST;
     const int use = kt / NST;
     double* Bs = stages + s * STAGE_DOUBLES + T_OPER_DOUBLES;
     if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
     if constexpr (GEN_VPT == 8) {
-      double2 o0, o1, o2, o3;
-      o0.x = g_k01.x * tab_s[__popc(g_zb ^ g_za.x)];
-      o0.y = g_k01.y * tab_s[__popc(g_zb ^ g_za.y)];
-      o1.x = g_k23.x * tab_s[__popc(g_zb ^ g_za.z)];
-      o1.y = g_k23.y * tab_s[__popc(g_zb ^ g_za.w)];
-      o2.x = g_k45.x * tab_s[__popc(g_zb ^ g_zc.x)];
-      o2.y = g_k45.y * tab_s[__popc(g_zb ^ g_zc.y)];
-      o3.x = g_k67.x * tab_s[__popc(g_zb ^ g_zc.z)];
-      o3.y = g_k67.y * tab_s[__popc(g_zb ^ g_zc.w)];
+      const double2 o0 = g_o0, o1 = g_o1, o2 = g_o2, o3 = g_o3;
       double2* d0 = reinterpret_cast<double2*>(Bs + (2 * ghalf) * B_CHUNK + gcol * 4);
       double2* d1 = reinterpret_cast<double2*>(Bs + (2 * ghalf + 1) * B_CHUNK + gcol * 4);
       d0[0] = o0;
@@ -380,6 +388,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
     produce_tma(kt);
     if (GEN) {
       gen_load(kt);
+      gen_compute();
       gen_store(kt);
     }
   }
@@ -420,6 +429,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
         for (int i = 0; i < 4; ++i) a[i] = pa[c * T_CHUNK_DOUBLES + fa_off[i]];
 #pragma unroll
         for (int j = 0; j < TJ; ++j) b[j] = pb[c * B_CHUNK + j * 32];
+        if (GEN && c == 3 && nk < num_k) gen_compute();  // the loads of gen_load(nk) were issued three chunks ago
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -451,6 +461,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
           }
         }
       }
+      if (GEN && nk < num_k) gen_compute();
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
