@@ -67,6 +67,13 @@
 // Evaluating the acquisition function of a CTA's own columns inside the UPPER_GRAD prologue (while the first TMA tiles
 // are in flight; removes the separate epilogue launch from the fused step) saves 3 us at 8 192 columns but the added
 // code costs the 65 536-column step 0.03-0.04 ms even when it is switched off at run time (4.247 -> 4.28-4.29 ms): reverted.
+// LOWER_GEN against LOWER_TMA (2.208 vs 2.036 ms), by timing-only variants: the popc -> table LDS -> DMUL chain 0.08 ms, the
+// generator's global loads 0.03 ms, the per-thread barrier protocol 0.06 ms, the stores nothing.  Forming the operand values
+// in registers in the MIDDLE of the current k-tile's DMMA block (gen_compute at chunk 3; the in-order warp no longer sits
+// through the chain after its last DMMA) took the lower product to 2.148 ms and the step to 4.190 ms.  Also tried, slower:
+// the same at chunks 1 / 2 (2.154 / 2.158), storing inside the block as well (2.155), the generator's loads inside the
+// block (2.158).  st.async stores that signal their bytes on the full barrier (no per-thread arrive) raise an illegal
+// instruction outside a cluster launch.
 //
 // Four modes (template):
 //   LOWER_GEN   the B operand k*[col, k] = kc[b(col), k] * tab[popc(z[col] ^ Z[k])] is GENERATED into shared memory by the
