@@ -73,7 +73,8 @@
 // through the chain after its last DMMA) took the lower product to 2.148 ms and the step to 4.190 ms.  Also tried, slower:
 // the same at chunks 1 / 2 (2.154 / 2.158), storing inside the block as well (2.155), the generator's loads inside the
 // block (2.158).  st.async stores that signal their bytes on the full barrier (no per-thread arrive) raise an illegal
-// instruction outside a cluster launch.
+// instruction outside a cluster launch; a non-blocking test of the stage's empty barrier inside the block (blocking wait
+// only if it failed) is slower too (2.195 ms): a volatile barrier instruction in the block disturbs the DMMA schedule.
 //
 // Four modes (template):
 //   LOWER_GEN   the B operand k*[col, k] = kc[b(col), k] * tab[popc(z[col] ^ Z[k])] is GENERATED into shared memory by the
