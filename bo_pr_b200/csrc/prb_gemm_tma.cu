@@ -353,6 +353,9 @@ __global__ void __launch_bounds__(THREADS, MINB)
       g_o2.y = g_k45.y * tab_s[__popc(g_zb ^ g_zc.y)];
       g_o3.x = g_k67.x * tab_s[__popc(g_zb ^ g_zc.z)];
       g_o3.y = g_k67.y * tab_s[__popc(g_zb ^ g_zc.w)];
+    } else if constexpr (GEN_VPT == 2) {
+      g_o0.x = g_k01.x * tab_s[__popc(g_zb ^ g_zs.x)];
+      g_o0.y = g_k01.y * tab_s[__popc(g_zb ^ g_zs.y)];
     }
   };
   auto gen_store = [&](int kt) {
@@ -378,9 +381,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
       d0[0] = o0;
       d0[1] = o1;
     } else {
-      double2 o;
-      o.x = g_k01.x * tab_s[__popc(g_zb ^ g_zs.x)];
-      o.y = g_k01.y * tab_s[__popc(g_zb ^ g_zs.y)];
+      const double2 o = g_o0;
       *reinterpret_cast<double2*>(Bs + (ghalf >> 1) * B_CHUNK + gcol * 4 + (ghalf & 1) * 2) = o;
     }
     mbar_arrive(&full[s]);
