@@ -557,8 +557,10 @@ def run_ours(a):
     e2e = None
     if not a.no_e2e:
         theta_host = theta.clone().pin_memory()
-        val_host = torch.empty(b, dtype=torch.float64).pin_memory()
-        grad_host = torch.empty(b, 1, d, dtype=torch.float64).pin_memory()
+        # one pinned block, [b, d] gradient then [b] values: the library returns both with a single device->host copy
+        out_host = torch.empty(b * d + b, dtype=torch.float64).pin_memory()
+        grad_host = out_host[: b * d].view(b, 1, d)
+        val_host = out_host[b * d:]
 
         def e2e_step():
             # the host-buffer entry of the C ABI (prb_mc_value_grad_host) through its Python method: pinned theta in, pinned

@@ -901,6 +901,7 @@ static int model_create_impl(prb_model** out, const prb_model_desc* desc, const 
   const size_t o_tab = carve(64 * sizeof(double));
   const size_t o_ctr = carve(64);
   const size_t o_flags = carve(64);  // [0] Cholesky info, [1] separable-structure check
+  const size_t o_ones = carve(MODEL_ONES * sizeof(double));
   if ((e = cudaMallocAsync(&m->block, off, st)) != cudaSuccess) {
     delete m;
     return cuda_fail(e, "cudaMallocAsync(model)");
@@ -915,9 +916,11 @@ static int model_create_impl(prb_model** out, const prb_model_desc* desc, const 
   m->sep_tab = reinterpret_cast<double*>(blk + o_tab);
   m->done_ctr = reinterpret_cast<unsigned int*>(blk + o_ctr);
   int* flags_dev = reinterpret_cast<int*>(blk + o_flags);
+  m->ones = reinterpret_cast<double*>(blk + o_ones);
   e = cudaMemcpyAsync(m->Xtr, desc->X_train, size_t(m->n) * m->d_k * sizeof(double), cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess) e = cudaMemsetAsync(blk + o_ctr, 0, 128, st);  // completion counter + both flags
   if (e == cudaSuccess) e = cudaMemsetAsync(m->Zbits, 0, size_t(n_pad) * sizeof(uint32_t), st);
+  if (e == cudaSuccess) e = launch_fill(m->ones, 1.0, MODEL_ONES, st);
   if (e == cudaSuccess) e = tma_init();
   if (e == cudaSuccess) e = small_step_init();
   // separable candidates: one product term of two Matern-5/2 factors, one of them isotropic over <= 32 dims.  The check that
@@ -1243,18 +1246,27 @@ int prb_mc_value_grad_host(prb_model* model, const prb_space_desc* space, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // device staging inside the caller's workspace: theta, value, gradient, unit upstream gradient
   double* theta_dev = at<double>(workspace, pl.off_Xc);
-  double* value_dev = at<double>(workspace, pl.off_val);
   double* grad_dev = at<double>(workspace, pl.off_grad);
-  double* ones = at<double>(workspace, pl.off_ones);
+  // value staged right behind the gradient rows: a caller whose host buffers are laid out the same way ([b, d] gradient, then
+  // [b] values, e.g. two views of one pinned block) gets both back with ONE device->host copy
+  const bool fits = size_t(b) * (sp.d + 1) <= size_t(pl.B_pad) * sp.d;  // the gradient region holds B_pad x d doubles
+  double* value_dev = (want_grad && fits) ? grad_dev + size_t(b) * sp.d : at<double>(workspace, pl.off_val);
+  const bool resident_ones = m.ones != nullptr && b <= MODEL_ONES;
+  double* ones = resident_ones ? m.ones : at<double>(workspace, pl.off_ones);
   const size_t row_bytes = size_t(b) * sp.d * sizeof(double);
+  const bool one_copy = want_grad && fits && out_value_host == out_grad_host + size_t(b) * sp.d;
   auto sequence = [&](cudaStream_t s) -> int {
     CUDA_TRY(cudaMemcpyAsync(theta_dev, theta_host, row_bytes, cudaMemcpyHostToDevice, s));
-    if (want_grad) CUDA_TRY(launch_fill(ones, 1.0, b, s));
+    if (want_grad && !resident_ones) CUDA_TRY(launch_fill(ones, 1.0, b, s));
     int r = mc_core(model, sp, aq, pl, workspace, theta_dev, b, mc, u_int, u_cat, seed, offset, estimator, ma_state, update_ma,
                     want_grad ? ones : nullptr, value_dev, want_grad ? grad_dev : nullptr, nullptr, s);
     if (r != PRB_OK) return r;
-    CUDA_TRY(cudaMemcpyAsync(out_value_host, value_dev, size_t(b) * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (want_grad) CUDA_TRY(cudaMemcpyAsync(out_grad_host, grad_dev, row_bytes, cudaMemcpyDeviceToHost, s));
+    if (one_copy) {
+      CUDA_TRY(cudaMemcpyAsync(out_grad_host, grad_dev, row_bytes + size_t(b) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(out_value_host, value_dev, size_t(b) * sizeof(double), cudaMemcpyDeviceToHost, s));
+      if (want_grad) CUDA_TRY(cudaMemcpyAsync(out_grad_host, grad_dev, row_bytes, cudaMemcpyDeviceToHost, s));
+    }
     return PRB_OK;
   };
   // (A cached executable graph of this whole sequence -- one cudaGraphLaunch instead of ~8 runtime calls -- was measured and

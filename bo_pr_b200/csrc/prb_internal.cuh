@@ -63,6 +63,7 @@ struct DevAcq {
   double param, min_variance, acq_var_floor;
 };
 
+constexpr int MODEL_ONES = 4096;
 constexpr int GEMM_BM = 128;  // row tile of the triangular products (prb_gemm_tma.cu)
 constexpr int GEMM_BK = 16;   // contraction tile; Kp is a multiple of it
 
@@ -195,6 +196,7 @@ struct Model {
   TensorMap mapA1, mapA2;    // 2-D maps (box = 4 k values x 128 rows): the single-kernel step of prb_small.cu
   TensorMap mapA1k, mapA2k;  // 3-D maps (box = 4 k values x 128 rows x 4 k-chunks): one TMA per operand and k-tile
   double* alpha_pad;  // [max(Mp1, Mp2)] alpha, zero padded
+  double* ones;       // [MODEL_ONES] 1.0: the unit upstream gradient of the host-buffer entry (no fill launch per call)
   // separable structure: one term = Matern52(continuous dims) x isotropic Matern52(binary dims), binary training columns
   int sep_ok;
   int sep_cont_factor, sep_bin_factor;  // indices into spec.t[0].f

@@ -306,7 +306,8 @@ int prb_mc_value_grad(prb_model* model, const prb_space_desc* space, const prb_a
  * on the caller's side.  Pinned host memory makes the copies asynchronous; pageable memory works (the runtime stages it).
  * u_int / u_cat / ma_state stay DEVICE pointers (they are the wrapper's buffers).  synchronize != 0: the call returns after
  * the results have landed in the host buffers (the one entry point that synchronises, by request).  The device staging
- * lives in the caller's workspace (same prb_workspace_bytes).                                                              */
+ * lives in the caller's workspace (same prb_workspace_bytes).  If out_value_host == out_grad_host + b * d (gradient rows
+ * and values are two views of one host block) both come back with a single device->host copy.                            */
 int prb_mc_value_grad_host(prb_model* model, const prb_space_desc* space, const prb_acq_desc* acq,
                            const double* theta_host, int32_t b, int32_t mc, const double* u_int, const double* u_cat,
                            uint64_t seed, uint64_t offset, int32_t estimator, double* ma_state, int32_t update_ma,

@@ -358,3 +358,8 @@ def test_host_buffer_entry_equals_forward_autograd():
     pr_c = product_mc_pr(g, DEV)
     pr_c.value_and_grad_host(theta.clone(), v_only, None, device=DEV)
     assert torch.equal(v_only, val.detach().cpu())
+    # gradient rows and values as two views of ONE pinned block ([b, d] then [b]): a single device->host copy returns both
+    block = torch.full((6 * 13 + 6,), float("nan"), dtype=torch.float64).pin_memory()
+    pr_d = product_mc_pr(g, DEV)
+    pr_d.value_and_grad_host(theta.clone().pin_memory(), block[6 * 13:], block[: 6 * 13].view(6, 1, 13), device=DEV)
+    assert torch.equal(block[6 * 13:], val.detach().cpu()) and torch.equal(block[: 6 * 13].view(6, 1, 13), grad.cpu())
