@@ -445,6 +445,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
           for (int j = 0; j < TJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
       }
     } else {
+      bool gen_done = false;
       // diagonal block: sub-block (8 rows of group g) x (4 k values at offset q) of A is all zero when
       //   lower (k <= row):  q > 8 g + 7          upper (k >= row):  q + 3 < 8 g
 #pragma unroll
@@ -461,6 +462,10 @@ __global__ void __launch_bounds__(THREADS, MINB)
         double b[TJ];
 #pragma unroll
         for (int j = 0; j < TJ; ++j) b[j] = pb[c * B_CHUNK + j * 32];
+        if (GEN && c == 3 && nk < num_k) {  // as in the full-tile body; chunk 3 of a generating diagonal tile has active
+          gen_compute();                     // rows for every warp (q <= 92 there), the flag covers the general case
+          gen_done = true;
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (act[i]) {
@@ -470,7 +475,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
           }
         }
       }
-      if (GEN && nk < num_k) gen_compute();
+      if (GEN && nk < num_k && !gen_done) gen_compute();
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
