@@ -140,6 +140,9 @@ extern "C" void prb_debug_set_cta_trace(long long* buf) {
 #ifndef PRB_GEN_ROTATE
 #define PRB_GEN_ROTATE 0
 #endif
+#ifndef PRB_UPPER_EPI_SMEM
+#define PRB_UPPER_EPI_SMEM 1
+#endif
 struct TmaGemmParams {
   long long* trace = nullptr;
   int mixed_groups = 0;    // leading scheduling groups that use the mixed (heavy / light alternating) order
@@ -530,6 +533,72 @@ __global__ void __launch_bounds__(THREADS, MINB)
     if (b_lo > p.nb - 1) b_lo = p.nb - 1;
     if (b_hi > p.nb - 1) b_hi = p.nb - 1;
     const bool single = (b_lo == b_hi);
+#if PRB_UPPER_EPI_SMEM
+    // Column sums of T * D over the tile's 128 rows, all dims of a batch behind ONE CTA barrier: every thread stores its
+    // partial sums over its four row groups as [dim][wm * 8 + frag_r][column] (row pitch BN + 8 doubles: the STS.128 of a
+    // warp fall on disjoint bank groups), then one thread per (dim, column) adds the 32 partials in a fixed order.  The
+    // shuffle tree + two barriers per dim this replaces made the epilogue 9-12 k cycles per CTA.
+    constexpr int EP = BN + 8;
+    constexpr int ECAP = (NST * STAGE_DOUBLES) / (32 * EP);  // dims per batch that fit the (now free) stage buffers
+    double* part_s = stages;
+    const int slot = wm * 8 + frag_r;
+    for (int c0 = 0; c0 < p.n_cont; c0 += ECAP) {
+      const int nc = min(ECAP, p.n_cont - c0);
+      for (int cc = 0; cc < nc; ++cc) {
+        const int c = c0 + cc;
+        double part[TJ][2];
+        if (single) {
+          const double* D = p.Dc + (size_t(b_lo) * p.n_cont + c) * p.Kp;
+          double dr[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dr[i] = (rows[i] < p.Kp) ? D[rows[i]] : 0.0;
+#pragma unroll
+          for (int j = 0; j < TJ; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              double sacc = 0.0;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) sacc = fma(acc[i][j][e], dr[i], sacc);
+              part[j][e] = sacc;
+            }
+        } else {
+#pragma unroll
+          for (int j = 0; j < TJ; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              int64_t br = p.colb ? int64_t(p.colb[col_base + 8 * j + e]) : (p.col0 + col_base + 8 * j + e) / p.mc;
+              if (br > p.nb - 1) br = p.nb - 1;
+              const double* D = p.Dc + (size_t(br) * p.n_cont + c) * p.Kp;
+              double sacc = 0.0;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int row = rows[i];
+                sacc = fma(acc[i][j][e], row < p.Kp ? D[row] : 0.0, sacc);
+              }
+              part[j][e] = sacc;
+            }
+        }
+        double* prow = part_s + (size_t(cc) * 32 + slot) * EP + wn * (8 * TJ) + 2 * frag_k;
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) *reinterpret_cast<double2*>(prow + 8 * j) = make_double2(part[j][0], part[j][1]);
+      }
+      __syncthreads();
+      for (int idx = tid; idx < nc * BN; idx += THREADS) {
+        const int cc = idx / BN, col = idx - cc * BN;
+        const double* src = part_s + size_t(cc) * 32 * EP + col;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int r = 0; r < 32; r += 4) {
+          s0 += src[(r + 0) * EP];
+          s1 += src[(r + 1) * EP];
+          s2 += src[(r + 2) * EP];
+          s3 += src[(r + 3) * EP];
+        }
+        p.S_part[(size_t(mt) * p.n_cont + c0 + cc) * p.ncols_pad + n0 + col] = (s0 + s1) + (s2 + s3);
+      }
+      if (c0 + ECAP < p.n_cont) __syncthreads();
+    }
+#else
     for (int c = 0; c < p.n_cont; ++c) {
       double part[TJ][2];
       if (single) {
@@ -587,6 +656,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
       }
       __syncthreads();
     }
+#endif
     CTA_TRACE(4);
     return;
   }
