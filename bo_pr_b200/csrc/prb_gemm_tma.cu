@@ -108,7 +108,7 @@ static_assert(T_AHEAD >= 1 && T_AHEAD <= T_STAGES - 1, "the producer may run at 
 constexpr int T_OPER_DOUBLES = T_BM * T_BK;            // 2048 doubles = 16 KB per operand per stage
 constexpr int T_CHUNK_DOUBLES = T_BM * 4;              // one k-chunk (4 k values) of 128 rows
 constexpr size_t tma_smem_bytes(int bn, int stages = T_STAGES) {
-  return size_t(stages) * (T_OPER_DOUBLES + bn * T_BK) * 8 + 2 * stages * 8 + 64 * 8;
+  return size_t(stages) * (T_OPER_DOUBLES + bn * T_BK) * 8 + 2 * stages * 8 + 64 * 8 + (3 * 128 + 6 * 128) * 8;
 }
 constexpr size_t T_SMEM_BYTES = tma_smem_bytes(128);
 
@@ -142,6 +142,9 @@ extern "C" void prb_debug_set_cta_trace(long long* buf) {
 #endif
 #ifndef PRB_UPPER_EPI_SMEM
 #define PRB_UPPER_EPI_SMEM 1
+#endif
+#ifndef PRB_UPPER_EPI_PRELOAD
+#define PRB_UPPER_EPI_PRELOAD 1
 #endif
 struct TmaGemmParams {
   long long* trace = nullptr;
@@ -208,6 +211,13 @@ __global__ void __launch_bounds__(THREADS, MINB)
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + size_t(NST) * STAGE_DOUBLES * 8);
   uint64_t* empty = full + NST;
   double* tab_s = reinterpret_cast<double*>(empty + NST);  // [64]
+  // UPPER_GRAD: the epilogue's operands, fetched in the prologue while the first TMA tiles are in flight
+  double* e_cm = tab_s + 64;                            // [BN] dA/dmu of the tile's columns (0 beyond the valid ones)
+  double* e_cv = e_cm + 128;                            // [BN] -2 dA/dsigma^2
+  uint32_t* e_zc = reinterpret_cast<uint32_t*>(e_cv + 128);  // [BN] bit codes of the columns
+  double* e_al = e_cv + 256;                            // [128] alpha of the tile's rows
+  uint32_t* e_Zr = reinterpret_cast<uint32_t*>(e_al + 128);  // [128] bit codes of the rows
+  double* e_D = e_al + 256;                             // [4][128] derivative rows of the first four dims (one restart per tile)
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -405,6 +415,37 @@ __global__ void __launch_bounds__(THREADS, MINB)
     }
   }
 
+#if PRB_UPPER_EPI_PRELOAD
+  bool e_single = false;
+  int64_t e_blo = 0;
+  if constexpr (MODE == MODE_UPPER_GRAD) {
+    // restart index of the tile's first / last column: one restart per tile is the common case (mc % 128 == 0)
+    int64_t b_hi = p.colb ? int64_t(p.colb[n0 + BN - 1]) : (p.col0 + n0 + BN - 1) / p.mc;
+    e_blo = p.colb ? int64_t(p.colb[n0]) : (p.col0 + n0) / p.mc;
+    if (e_blo > p.nb - 1) e_blo = p.nb - 1;
+    if (b_hi > p.nb - 1) b_hi = p.nb - 1;
+    e_single = (e_blo == b_hi);
+    for (int t2 = tid; t2 < BN; t2 += THREADS) {
+      const int col = n0 + t2;
+      const bool ok = col < ncols_valid;
+      e_cm[t2] = ok ? p.dmu[col] : 0.0;
+      e_cv[t2] = ok ? -2.0 * p.dvar[col] : 0.0;
+      e_zc[t2] = p.zbits[col];
+    }
+    for (int r = tid; r < T_BM; r += THREADS) {
+      e_al[r] = p.alpha_pad[m0 + r];
+      e_Zr[r] = p.Zbits[m0 + r];
+    }
+    if (e_single) {
+      const int nd = p.n_cont < 4 ? p.n_cont : 4;
+      for (int idx = tid; idx < nd * T_BM; idx += THREADS) {
+        const int c = idx / T_BM, r = idx - c * T_BM;
+        e_D[idx] = (m0 + r < p.Kp) ? p.Dc[(size_t(e_blo) * p.n_cont + c) * p.Kp + m0 + r] : 0.0;
+      }
+    }
+  }
+#endif
+
   // Row ownership: M-warp wm owns the 8-row groups {wm, 7 - wm, 8 + wm, 15 - wm} of the tile, so that the triangular work
   // inside a diagonal block (where whole 8 x 4 sub-blocks of A are zero and their DMMAs are skipped) is split evenly.
   const int frag_r = lane >> 2;
@@ -511,28 +552,44 @@ __global__ void __launch_bounds__(THREADS, MINB)
     uint32_t Zr[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
+#if PRB_UPPER_EPI_PRELOAD
+      al[i] = e_al[rows[i] - m0];
+      Zr[i] = e_Zr[rows[i] - m0];
+#else
       al[i] = p.alpha_pad[rows[i]];
       Zr[i] = p.Zbits[rows[i]];
+#endif
     }
 #pragma unroll
     for (int j = 0; j < TJ; ++j)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int col = col_base + 8 * j + e;
+#if PRB_UPPER_EPI_PRELOAD
+        const double cm = e_cm[col - n0];
+        const double cv = e_cv[col - n0];
+        const uint32_t zc = e_zc[col - n0];
+#else
         const bool cv_ok = col < ncols_valid;
         const double cm = cv_ok ? p.dmu[col] : 0.0;
         const double cv = cv_ok ? -2.0 * p.dvar[col] : 0.0;
         const uint32_t zc = p.zbits[col];
+#endif
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           acc[i][j][e] = fma(cv, acc[i][j][e], cm * al[i]) * tab_s[__popc(zc ^ Zr[i])];
       }
     // restart index of the tile's first / last column: one restart per tile is the common case (mc % 128 == 0)
+#if PRB_UPPER_EPI_PRELOAD
+    const int64_t b_lo = e_blo;
+    const bool single = e_single;
+#else
     int64_t b_lo = p.colb ? int64_t(p.colb[n0]) : (p.col0 + n0) / p.mc;
     int64_t b_hi = p.colb ? int64_t(p.colb[n0 + BN - 1]) : (p.col0 + n0 + BN - 1) / p.mc;
     if (b_lo > p.nb - 1) b_lo = p.nb - 1;
     if (b_hi > p.nb - 1) b_hi = p.nb - 1;
     const bool single = (b_lo == b_hi);
+#endif
 #if PRB_UPPER_EPI_SMEM
     // Column sums of T * D over the tile's 128 rows, all dims of a batch behind ONE CTA barrier: every thread stores its
     // partial sums over its four row groups as [dim][wm * 8 + frag_r][column] (row pitch BN + 8 doubles: the STS.128 of a
@@ -550,8 +607,16 @@ __global__ void __launch_bounds__(THREADS, MINB)
         if (single) {
           const double* D = p.Dc + (size_t(b_lo) * p.n_cont + c) * p.Kp;
           double dr[4];
+#if PRB_UPPER_EPI_PRELOAD
+          if (c < 4) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) dr[i] = (rows[i] < p.Kp) ? D[rows[i]] : 0.0;
+            for (int i = 0; i < 4; ++i) dr[i] = e_D[c * T_BM + rows[i] - m0];
+          } else
+#endif
+          {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dr[i] = (rows[i] < p.Kp) ? D[rows[i]] : 0.0;
+          }
 #pragma unroll
           for (int j = 0; j < TJ; ++j)
 #pragma unroll
