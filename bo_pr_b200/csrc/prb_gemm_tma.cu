@@ -75,6 +75,10 @@
 // block (2.158).  st.async stores that signal their bytes on the full barrier (no per-thread arrive) raise an illegal
 // instruction outside a cluster launch; a non-blocking test of the stage's empty barrier inside the block (blocking wait
 // only if it failed) is slower too (2.195 ms): a volatile barrier instruction in the block disturbs the DMMA schedule.
+// UPPER_GRAD epilogue (9-12 k cycles of a ~140 k-cycle CTA: shuffle trees + two CTA barriers per gradient dim, ~70 global
+// loads per thread after the k loop): partial column sums of ALL dims through the free stage buffers behind one barrier
+// (upper product 2.023 -> 2.004 ms), and the epilogue's operands fetched into shared memory in the PROLOGUE, while the first
+// TMA tiles are in flight (-> 1.986 ms; bench step 4.148 ms).
 //
 // Four modes (template):
 //   LOWER_GEN   the B operand k*[col, k] = kc[b(col), k] * tab[popc(z[col] ^ Z[k])] is GENERATED into shared memory by the
